@@ -1,0 +1,682 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE ONLY (see lc_oracle.c header).
+
+ctypes binding of oracle/liblc_oracle.so plus an event-group level restatement of the four
+reference processors' ``Process(PipelineEventGroup&)`` so that the reference's own unit-test
+fixtures (tests/golden/*.json) can be replayed.  Nothing under loongcollector_b200/ imports this.
+
+Reference lines restated here (paths relative to the reference checkout):
+  * LogEvent content semantics ........ core/models/LogEvent.cpp:50-106
+  * group/event JSON ................. core/models/PipelineEventGroup.cpp:405-483, LogEvent.cpp:170-208,
+                                         RawEvent.cpp:52-73
+  * split ............................. core/plugin/processor/inner/ProcessorSplitLogStringNative.cpp:74-161
+  * multiline ......................... core/plugin/processor/inner/ProcessorSplitMultilineLogStringNative.cpp:95-340
+  * regex parse ....................... core/plugin/processor/ProcessorParseRegexNative.cpp:29-253
+  * delimiter ......................... core/plugin/processor/ProcessorParseDelimiterNative.cpp:30-409
+  * common options .................... core/plugin/processor/CommonParserOptions.cpp:28-117
+  * multiline options ................. core/file_server/MultilineOptions.cpp:22-222
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liblc_oracle.so")
+    src = os.path.join(_HERE, "lc_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    L = C.CDLL(build())
+    L.orc_regex_compile.restype = C.c_void_p
+    L.orc_regex_compile.argtypes = [C.c_char_p, C.c_uint64, C.c_int]
+    L.orc_regex_free.argtypes = [C.c_void_p]
+    L.orc_regex_ngroups.restype = C.c_uint32
+    L.orc_regex_ngroups.argtypes = [C.c_void_p]
+    L.orc_matcher_create.restype = C.c_void_p
+    L.orc_matcher_create.argtypes = [C.c_void_p]
+    L.orc_matcher_free.argtypes = [C.c_void_p]
+    L.orc_regex_prefix_match.restype = C.c_int
+    L.orc_regex_prefix_match.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.orc_regex_full_match.restype = C.c_int
+    L.orc_regex_full_match.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.orc_regex_parse_batch.restype = None
+    L.orc_regex_parse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_split_lines.restype = C.c_uint64
+    L.orc_split_lines.argtypes = [C.c_void_p, C.c_uint64, C.c_uint8, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.orc_multiline_split.restype = C.c_uint64
+    L.orc_multiline_split.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.orc_delim_trim.restype = C.c_int
+    L.orc_delim_trim.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.orc_delim_fsm.restype = C.c_int64
+    L.orc_delim_fsm.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint8, C.c_uint8, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int64]
+    L.orc_delim_unquote.restype = C.c_uint32
+    L.orc_delim_unquote.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint8, C.c_void_p]
+    L.orc_delim_split.restype = C.c_int64
+    L.orc_delim_split.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_int64]
+    L.orc_delim_parse_batch.restype = None
+    L.orc_delim_parse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
+                                        C.c_uint8, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _LIB = L
+    return L
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _as_u8(buf) -> np.ndarray:
+    if isinstance(buf, np.ndarray):
+        assert buf.dtype == np.uint8
+        return np.ascontiguousarray(buf)
+    return np.frombuffer(bytes(buf), dtype=np.uint8)
+
+
+# ----------------------------------------------------------------------------- flat API
+class Regex:
+    """boost::regex(pattern) stand-in (PCRE2, DOTALL|MULTILINE, bytes). One matcher scratch per object."""
+
+    def __init__(self, pattern, jit: bool = False):
+        if isinstance(pattern, str):
+            pattern = pattern.encode("utf-8")
+        self.pattern = pattern
+        L = lib()
+        self._re = L.orc_regex_compile(pattern, len(pattern), 1 if jit else 0)
+        if not self._re:
+            raise ValueError("oracle: invalid regex %r" % (pattern,))
+        self.ngroups = int(L.orc_regex_ngroups(self._re))
+        self._m = L.orc_matcher_create(self._re)
+
+    def new_matcher(self):
+        """An extra matcher scratch over the same compiled code (one per CPU thread)."""
+        return lib().orc_matcher_create(self._re)
+
+    def prefix_match(self, data: bytes) -> bool:
+        a = _as_u8(data)
+        return bool(lib().orc_regex_prefix_match(self._m, _ptr(a) if a.size else None, a.size))
+
+    def full_match(self, data: bytes):
+        """-> None, or list of (off,len) for groups 1..ngroups (unset = (len(data), 0))."""
+        a = _as_u8(data)
+        co = np.zeros(max(self.ngroups, 1), np.uint32)
+        cl = np.zeros(max(self.ngroups, 1), np.uint32)
+        ok = lib().orc_regex_full_match(self._m, _ptr(a) if a.size else None, a.size, _ptr(co), _ptr(cl))
+        if not ok:
+            return None
+        return [(int(co[g]), int(cl[g])) for g in range(self.ngroups)]
+
+    def __del__(self):
+        try:
+            L = lib()
+            if getattr(self, "_m", None):
+                L.orc_matcher_free(self._m)
+            if getattr(self, "_re", None):
+                L.orc_regex_free(self._re)
+        except Exception:
+            pass
+
+
+def split_lines(buf, split_char: int = 10):
+    a = _as_u8(buf)
+    L = lib()
+    n = int(L.orc_split_lines(_ptr(a), a.size, split_char, None, None, 0)) if a.size else 0
+    off = np.zeros(n, np.uint32)
+    ln = np.zeros(n, np.uint32)
+    if n:
+        L.orc_split_lines(_ptr(a), a.size, split_char, _ptr(off), _ptr(ln), n)
+    return off, ln
+
+
+def multiline_split(buf, start: Optional[Regex], cont: Optional[Regex], end: Optional[Regex], discard: bool):
+    """-> (off, len, flags[bit0 isLast, bit1 matched], counters[matched_events, input_lines, unmatch_lines])"""
+    a = _as_u8(buf)
+    L = lib()
+    ctr = np.zeros(3, np.uint64)
+    s = start._m if start else None
+    c = cont._m if cont else None
+    e = end._m if end else None
+    if a.size == 0:
+        return np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.uint8), ctr
+    n = int(L.orc_multiline_split(_ptr(a), a.size, s, c, e, int(discard), None, None, None, 0, None))
+    off = np.zeros(n, np.uint32)
+    ln = np.zeros(n, np.uint32)
+    fl = np.zeros(n, np.uint8)
+    L.orc_multiline_split(_ptr(a), a.size, s, c, e, int(discard), _ptr(off), _ptr(ln), _ptr(fl), n, _ptr(ctr))
+    return off, ln, fl, ctr
+
+
+def regex_parse_batch(rx: Regex, base, ev_off, ev_len, nkeys: int, matcher=None):
+    a = _as_u8(base)
+    ev_off = np.ascontiguousarray(ev_off, np.uint32)
+    ev_len = np.ascontiguousarray(ev_len, np.uint32)
+    n = ev_off.size
+    G = rx.ngroups
+    status = np.zeros(n, np.uint8)
+    co = np.zeros((n, max(G, 1)), np.uint32)
+    cl = np.zeros((n, max(G, 1)), np.uint32)
+    if G == 0:
+        # degenerate: no groups; keep the row stride of 1 but pass G=0 semantics by looping
+        m = matcher or rx._m
+        for i in range(n):
+            ok = lib().orc_regex_full_match(m, C.c_void_p(a.ctypes.data + int(ev_off[i])), int(ev_len[i]), None, None)
+            status[i] = 0 if (ok and 1 > nkeys) else (2 if ok else 1)
+        return status, co[:, :0], cl[:, :0]
+    lib().orc_regex_parse_batch(matcher or rx._m, _ptr(a), _ptr(ev_off), _ptr(ev_len), n, nkeys, _ptr(status),
+                                _ptr(co), _ptr(cl))
+    return status, co, cl
+
+
+def delim_parse_batch(base, ev_off, ev_len, sep: bytes, quote: int, nkeys: int, extend: bool, allow_short: bool,
+                      max_fields: int):
+    a = _as_u8(base)
+    ev_off = np.ascontiguousarray(ev_off, np.uint32)
+    ev_len = np.ascontiguousarray(ev_len, np.uint32)
+    n = ev_off.size
+    mode_quote = 1 if (len(sep) == 1 and quote != sep[0]) else 0
+    status = np.zeros(n, np.uint8)
+    nf = np.zeros(n, np.uint32)
+    fo = np.zeros((n, max_fields), np.uint32)
+    fl = np.zeros((n, max_fields), np.uint32)
+    fd = np.zeros((n, max_fields), np.uint32)
+    sp = np.frombuffer(sep, np.uint8)
+    lib().orc_delim_parse_batch(_ptr(a), _ptr(ev_off), _ptr(ev_len), n, _ptr(sp), len(sep), quote, mode_quote, nkeys,
+                                int(extend), int(allow_short), max_fields, _ptr(status), _ptr(nf), _ptr(fo), _ptr(fl),
+                                _ptr(fd))
+    return status, nf, fo, fl, fd
+
+
+# ----------------------------------------------------------------------------- event model
+LOG, METRIC, SPAN, RAW = 1, 2, 3, 4  # PipelineEvent::Type (core/models/PipelineEvent.h)
+
+# metadata keys that FromJson understands (PipelineEventGroup.cpp:396-407); everything else -> UNKNOWN
+_KNOWN_META = {"log.file.path_resolved", "source.id", "has.part.log", "log.file.offset"}
+META_LOG_FILE_OFFSET_KEY = "log.file.offset"  # EventGroupMetaKey::LOG_FILE_OFFSET_KEY (PipelineEventGroup.cpp:348,375)
+
+
+class Event:
+    __slots__ = ("type", "contents", "timestamp", "ns", "pos", "raw", "extra")
+
+    def __init__(self, type_=LOG):
+        self.type = type_
+        self.contents = []  # list of [key(bytes), val(bytes), live]
+        self.timestamp = 0
+        self.ns = None
+        self.pos = (0, 0)
+        self.raw = b""
+        self.extra = None  # opaque JSON for metric/span events (passed through)
+
+    # --- LogEvent.cpp:50-106
+    def _find(self, key):
+        for it in reversed(self.contents):
+            if it[0] == key and it[2]:
+                return it
+        return None
+
+    def has(self, key):
+        return self._find(key) is not None
+
+    def get(self, key):
+        it = self._find(key)
+        return it[1] if it else b""
+
+    def set(self, key, val):
+        it = self._find(key)
+        if it:
+            it[0], it[1] = key, val
+        else:
+            self.contents.append([key, val, True])
+
+    def delete(self, key):
+        it = self._find(key)
+        if it:
+            it[2] = False
+
+    def live(self):
+        return [(k, v) for k, v, l in self.contents if l]
+
+    def size(self):
+        return sum(1 for c in self.contents if c[2])
+
+
+class Group:
+    def __init__(self):
+        self.events = []
+        self.metadata = {}
+        self.tags = {}
+
+    @staticmethod
+    def from_json(s):
+        root = json.loads(s) if isinstance(s, (str, bytes)) else s
+        g = Group()
+        if root is None:
+            return g
+        for k in sorted(root.get("metadata", {})):
+            g.metadata[k if k in _KNOWN_META or k == META_LOG_FILE_OFFSET_KEY else "unknown"] = root["metadata"][k]
+        for k in sorted(root.get("tags", {})):
+            g.tags[k] = root["tags"][k]
+        for ev in root.get("events", []):
+            t = int(ev["type"])
+            e = Event(t if t in (LOG, METRIC, SPAN) else RAW)
+            e.timestamp = int(ev.get("timestamp", 0))
+            if "timestampNanosecond" in ev:
+                e.ns = int(ev["timestampNanosecond"])
+            if e.type == LOG:
+                if "fileOffset" in ev and "rawSize" in ev:
+                    e.pos = (int(ev["fileOffset"]), int(ev["rawSize"]))
+                for k in sorted(ev.get("contents", {}), key=lambda x: x.encode("utf-8")):
+                    e.set(k.encode("utf-8"), ev["contents"][k].encode("utf-8"))
+            elif e.type == RAW:
+                e.raw = ev.get("content", "").encode("utf-8")
+            else:
+                e.extra = ev
+            g.events.append(e)
+        return g
+
+    def to_json(self, enable_event_meta=False):
+        """Same shape as PipelineEventGroup::ToJson; an empty group serialises to None ("null")."""
+        root = {}
+        if self.metadata:
+            root["metadata"] = dict(self.metadata)
+        if self.tags:
+            root["tags"] = dict(self.tags)
+        if self.events:
+            evs = []
+            for e in self.events:
+                if e.type in (METRIC, SPAN):
+                    evs.append(e.extra)
+                    continue
+                d = {"type": e.type, "timestamp": e.timestamp}
+                if e.ns is not None:
+                    d["timestampNanosecond"] = e.ns
+                if e.type == RAW:
+                    d["content"] = e.raw.decode("utf-8", "surrogateescape")
+                else:
+                    if enable_event_meta:
+                        d["fileOffset"], d["rawSize"] = e.pos
+                    live = e.live()
+                    if live:
+                        d["contents"] = {k.decode("utf-8", "surrogateescape"): v.decode("utf-8", "surrogateescape")
+                                         for k, v in live}
+                evs.append(d)
+            root["events"] = evs
+        return root or None
+
+
+# ----------------------------------------------------------------------------- processors
+def _b(x):
+    return x.encode("utf-8") if isinstance(x, str) else x
+
+
+def _last_segment(cfg: dict, dotted: str, default=None):
+    """ParamExtractor resolves dotted names to their last segment (core/common/ParamExtractor.cpp:23-29)."""
+    key = dotted.split(".")[-1]
+    return cfg.get(key, default)
+
+
+class CommonParserOptions:
+    """CommonParserOptions.cpp:28-117"""
+
+    legacy_raw_key = b"__raw_log__"
+
+    def __init__(self, cfg):
+        self.keep_fail = bool(cfg.get("KeepingSourceWhenParseFail", False)) if isinstance(
+            cfg.get("KeepingSourceWhenParseFail", False), bool) else False
+        self.keep_ok = bool(cfg.get("KeepingSourceWhenParseSucceed", False)) if isinstance(
+            cfg.get("KeepingSourceWhenParseSucceed", False), bool) else False
+        r = cfg.get("RenamedSourceKey", "")
+        self.renamed = _b(r) if isinstance(r, str) and r else _b(cfg["SourceKey"])
+        self.coping_raw = bool(cfg.get("CopingRawLog", False)) if isinstance(cfg.get("CopingRawLog", False),
+                                                                              bool) else False
+
+    def should_add_source(self, ok):
+        return (ok and self.keep_ok) or ((not ok) and self.keep_fail)
+
+    def should_add_legacy_raw(self, ok):
+        return (not ok) and self.keep_fail and self.coping_raw
+
+    def should_erase(self, ok, ev: Event, metadata):
+        if (not ok) and (not self.keep_fail):
+            live = ev.live()
+            if not live:
+                return True
+            offkey = metadata.get(META_LOG_FILE_OFFSET_KEY)
+            if len(live) == 1 and offkey is not None and live[0][0] == _b(offkey):
+                return True
+            if len(live) == 2 and ev.has(b"_time_") and ev.has(b"_source_"):
+                return True
+        return False
+
+
+def _add_log(ev: Event, key, val, overwritten=True):
+    if (not overwritten) and ev.has(key):
+        return
+    ev.set(key, val)
+
+
+class ProcessorSplitLogStringNative:
+    name = "processor_split_string_native"
+
+    def __init__(self, cfg):
+        self.source_key = _b(cfg.get("SourceKey", "content"))
+        sc = cfg.get("SplitChar", 10)
+        self.split_char = (int(sc) & 0xFF) if isinstance(sc, int) and not isinstance(sc, bool) else 10
+        self.raw = bool(cfg.get("EnableRawContent", False))
+
+    def process(self, g: Group):
+        if not g.events:
+            return
+        new = []
+        for e in g.events:
+            if e.type != LOG or e.size() != 1 or not e.has(self.source_key):
+                new.append(e)
+                continue
+            val = e.get(self.source_key)
+            off, ln = split_lines(val, self.split_char)
+            for o, l in zip(off.tolist(), ln.tolist()):
+                content = val[o:o + l]
+                if self.raw:
+                    t = Event(RAW)
+                    t.raw = content
+                    t.timestamp, t.ns = e.timestamp, e.ns
+                else:
+                    t = Event(LOG)
+                    t.set(self.source_key, content)
+                    t.timestamp, t.ns = e.timestamp, e.ns
+                    offset = e.pos[0] + o
+                    length = (e.pos[1] - o) if (o + l == len(val)) else l + 1
+                    t.pos = (offset, length)
+                    if META_LOG_FILE_OFFSET_KEY in g.metadata:
+                        t.set(_b(g.metadata[META_LOG_FILE_OFFSET_KEY]), str(offset).encode())
+                new.append(t)
+        g.events = new
+
+
+class MultilineOptions:
+    """MultilineOptions.cpp:22-222 (custom mode only; JSON mode selects the plain splitter upstream)."""
+
+    def __init__(self, cfg):
+        self.ok = True
+        self.start = self.cont = self.end = ""
+        has = {}
+        for name in ("StartPattern", "ContinuePattern", "EndPattern"):
+            pat = _last_segment(cfg, "Multiline." + name, "")
+            if not isinstance(pat, str):
+                pat = ""
+            valid, compiled = self._parse_regex(pat)
+            if not valid:
+                pat, compiled = "", False
+            has[name] = compiled
+            setattr(self, {"StartPattern": "start", "ContinuePattern": "cont", "EndPattern": "end"}[name], pat)
+        # NB: the combination rules (:125-160) reset only the *RegPtr members; the processor keys off the
+        # pattern STRINGS (ProcessorSplitMultilineLogStringNative.cpp:68-80), so all three strings stay.
+        self.is_multiline = has["StartPattern"] or has["EndPattern"]
+        t = _last_segment(cfg, "Multiline.UnmatchedContentTreatment", "single_line")
+        self.discard = (t == "discard")
+
+    @staticmethod
+    def _parse_regex(pattern):
+        p = pattern
+        if p.endswith("$"):
+            p = p[:-1]
+        while p.endswith(".*"):
+            p = p[:-2]
+        if not p:
+            return True, False
+        try:
+            Regex(p)
+        except ValueError:
+            return False, False
+        return True, True
+
+
+class ProcessorSplitMultilineLogStringNative:
+    name = "processor_split_multiline_log_string_native"
+
+    def __init__(self, cfg):
+        self.source_key = _b(cfg.get("SourceKey", "content"))
+        self.opts = MultilineOptions(cfg)
+        self.raw = bool(cfg.get("EnableRawContent", False))
+        self.start = Regex(self.opts.start) if self.opts.start else None
+        self.cont = Regex(self.opts.cont) if self.opts.cont else None
+        self.end = Regex(self.opts.end) if self.opts.end else None
+        self.counters = {"matched_events": 0, "matched_lines": 0, "unmatched_lines": 0}
+
+    def process(self, g: Group):
+        if not g.events:
+            return
+        new = []
+        in_lines = un_lines = 0
+        for e in g.events:
+            if e.type != LOG or e.size() != 1 or not e.has(self.source_key):
+                new.append(e)
+                continue
+            val = e.get(self.source_key)
+            off, ln, fl, ctr = multiline_split(val, self.start, self.cont, self.end, self.opts.discard)
+            self.counters["matched_events"] += int(ctr[0])
+            in_lines += int(ctr[1])
+            un_lines += int(ctr[2])
+            for o, l, f in zip(off.tolist(), ln.tolist(), fl.tolist()):
+                content = val[o:o + l]
+                if self.raw:
+                    t = Event(RAW)
+                    t.raw = content
+                    t.timestamp, t.ns = e.timestamp, e.ns
+                else:
+                    t = Event(LOG)
+                    t.set(self.source_key, content)
+                    t.timestamp, t.ns = e.timestamp, e.ns
+                    offset = e.pos[0] + o
+                    length = (e.pos[1] - o) if (f & 1) else l + 1
+                    t.pos = (offset, length)
+                    if META_LOG_FILE_OFFSET_KEY in g.metadata:
+                        t.set(_b(g.metadata[META_LOG_FILE_OFFSET_KEY]), str(offset).encode())
+                new.append(t)
+        self.counters["matched_lines"] += in_lines - un_lines
+        self.counters["unmatched_lines"] += un_lines
+        g.events = new
+
+
+def _keys_param(cfg):
+    keys = cfg.get("Keys")
+    if not isinstance(keys, list):
+        raise ValueError("mandatory list param Keys")
+    return [_b(k) for k in keys]
+
+
+class ProcessorParseRegexNative:
+    name = "processor_parse_regex_native"
+
+    def __init__(self, cfg):
+        self.source_key = _b(cfg["SourceKey"])
+        self.regex_str = cfg["Regex"]
+        self.rx = Regex(self.regex_str)
+        self.whole_line = self.regex_str == "(.*)"
+        self.keys = _keys_param(cfg)
+        if len(self.keys) == 1 and b"," in self.keys[0]:
+            self.keys = [k for k in self.keys[0].split(b",")]
+        self.source_overwritten = self.source_key in self.keys
+        self.common = CommonParserOptions(cfg)
+        self.counters = {"discarded": 0, "out_failed": 0, "out_key_not_found": 0, "out_successful": 0}
+
+    def process(self, g: Group):
+        if not g.events:
+            return
+        out = []
+        for e in g.events:
+            if self._event(e, g.metadata):
+                out.append(e)
+        g.events = out
+
+    def _event(self, e: Event, metadata):
+        if e.type != LOG:
+            self.counters["out_failed"] += 1
+            return True
+        if not e.has(self.source_key):
+            self.counters["out_key_not_found"] += 1
+            return True
+        raw = e.get(self.source_key)
+        if self.whole_line:
+            _add_log(e, self.keys[0] if self.keys else b"content", raw)
+            ok = True
+        else:
+            caps = self.rx.full_match(raw)
+            if caps is None:
+                self.counters["out_failed"] += 1
+                ok = False
+            elif self.rx.ngroups + 1 <= len(self.keys):
+                ok = False
+            else:
+                ok = True
+                for i, k in enumerate(self.keys):
+                    o, l = caps[i]
+                    _add_log(e, k, raw[o:o + l])
+        if (not ok) or (not self.source_overwritten):
+            e.delete(self.source_key)
+        if self.common.should_add_source(ok):
+            _add_log(e, self.common.renamed, raw, False)
+        if self.common.should_add_legacy_raw(ok):
+            _add_log(e, self.common.legacy_raw_key, raw, False)
+        if self.common.should_erase(ok, e, metadata):
+            self.counters["discarded"] += 1
+            return False
+        self.counters["out_successful"] += 1
+        return True
+
+
+class ProcessorParseDelimiterNative:
+    name = "processor_parse_delimiter_native"
+
+    def __init__(self, cfg):
+        self.source_key = _b(cfg["SourceKey"])
+        sep = cfg["Separator"]
+        if len(_b(sep)) > 4:
+            raise ValueError("Separator has more than 4 chars")
+        if sep == "\\t":
+            sep = "\t"
+        self.sep = _b(sep)
+        q = cfg.get("Quote", "")
+        self.quote = ord('"')
+        if len(self.sep) == 1:
+            if isinstance(q, str) and len(_b(q)) > 1:
+                raise ValueError("Quote is not a single char")
+            if isinstance(q, str) and q:
+                self.quote = _b(q)[0]
+        # multi-char separator: a configured Quote is ignored with a warning (:97-107)
+        self.keys = _keys_param(cfg)
+        self.source_overwritten = self.source_key in self.keys
+        a = cfg.get("AllowingShortenedFields", True)
+        self.allow_short = a if isinstance(a, bool) else True
+        t = cfg.get("OverflowedFieldsTreatment", "extend")
+        self.overflow = t if t in ("keep", "discard") else "extend"
+        self.partial = self.overflow == "discard"
+        self.common = CommonParserOptions(cfg)
+        self.counters = {"discarded": 0, "out_failed": 0, "out_key_not_found": 0, "out_successful": 0}
+
+    def process(self, g: Group):
+        if not g.events:
+            return
+        g.events = [e for e in g.events if self._event(e, g.metadata)]
+
+    def _event(self, e: Event, metadata):
+        L = lib()
+        if e.type != LOG:
+            self.counters["out_failed"] += 1
+            return True
+        if not e.has(self.source_key):
+            self.counters["out_key_not_found"] += 1
+            return True
+        buf = e.get(self.source_key)
+        a = _as_u8(buf)
+        b = C.c_int32(0)
+        en = C.c_int32(0)
+        if a.size == 0 or not L.orc_delim_trim(_ptr(a), a.size, C.byref(b), C.byref(en)):
+            self.counters["out_failed"] += 1
+            return True
+        beg, end = b.value, en.value
+        extend = self.overflow == "extend"
+        use_quote = len(self.sep) == 1 and self.quote != self.sep[0]
+        ok = False
+        cols = []
+        if self.keys:
+            cap = a.size + 2
+            fo = np.zeros(cap, np.uint32)
+            fl = np.zeros(cap, np.uint32)
+            fd = np.zeros(cap, np.uint32)
+            if use_quote:
+                k = int(L.orc_delim_fsm(_ptr(a), beg, end, self.sep[0], self.quote, _ptr(fo), _ptr(fl), _ptr(fd),
+                                        cap))
+                ok = k >= 0
+                if ok:
+                    for j in range(k):
+                        if fd[j]:
+                            dst = np.zeros(int(fl[j]) + 1, np.uint8)
+                            w = L.orc_delim_unquote(_ptr(a), int(fo[j]), int(fl[j]), self.quote, _ptr(dst))
+                            assert w == int(fl[j]) - int(fd[j])
+                            cols.append(bytes(dst[:w]))
+                        else:
+                            cols.append(buf[int(fo[j]):int(fo[j]) + int(fl[j])])
+                    if (not extend) and len(cols) > len(self.keys):
+                        extra = b"".join(self.sep[:1] + c for c in cols[len(self.keys):])
+                        cols = cols[:len(self.keys)] + [extra]
+            else:
+                sp = np.frombuffer(self.sep, np.uint8)
+                k = int(L.orc_delim_split(_ptr(a), beg, end, _ptr(sp), len(self.sep), len(self.keys), int(extend),
+                                          _ptr(fo), _ptr(fl), cap))
+                ok = k > 0
+                cols = [buf[int(fo[j]):int(fo[j]) + int(fl[j])] for j in range(max(k, 0))]
+            if ok:
+                if len(cols) <= 0 or ((not self.allow_short) and len(cols) < len(self.keys)):
+                    ok = False
+        if ok:
+            for idx, c in enumerate(cols):
+                if idx < len(self.keys):
+                    if self.partial and self.keys[idx] == b"_":
+                        continue
+                    _add_log(e, self.keys[idx], c)
+                else:
+                    if self.partial:
+                        continue
+                    _add_log(e, b"__column%d__" % idx, c)
+            self.counters["out_successful"] += 1
+        else:
+            self.counters["out_failed"] += 1
+        if (not ok) or (not self.source_overwritten):
+            e.delete(self.source_key)
+        if self.common.should_add_source(ok):
+            _add_log(e, self.common.renamed, buf, False)
+        if self.common.should_add_legacy_raw(ok):
+            _add_log(e, self.common.legacy_raw_key, buf, False)
+        if self.common.should_erase(ok, e, metadata):
+            self.counters["discarded"] += 1
+            return False
+        return True
+
+
+PROCESSORS = {
+    p.name: p
+    for p in (ProcessorSplitLogStringNative, ProcessorSplitMultilineLogStringNative, ProcessorParseRegexNative,
+              ProcessorParseDelimiterNative)
+}
