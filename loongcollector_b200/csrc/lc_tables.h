@@ -1,0 +1,71 @@
+// lc_tables.h -- POD layout of a compiled regex ("program blob") shared by the host compiler
+// (regex_compiler.cpp) and the sm_100a kernels (kernels_regex.cu).
+//
+// A compiled pattern is ONE contiguous blob: a fixed header followed by 16-byte aligned arrays
+// addressed by byte offsets from the blob start, so the same bytes can live in host memory,
+// in HBM and be staged into shared memory by a kernel without any pointer fix-up.
+//
+// Three automata are derived from one prioritised (Perl leftmost-first) Thompson NFA:
+//   * PREFIX   boolean DFA: "does some prefix of the line match" == boost::regex_search(...,
+//              match_continuous) (reference: core/common/StringTools.cpp:263-288).  Used by the
+//              multiline splitter.
+//   * FWD1     forward-only tagged automaton over NFA "walker" states.  Exact for patterns whose
+//              highest-priority viable transition never depends on look-ahead (checked at compile
+//              time against the reverse DFA).  One table look-up per input byte.
+//   * REV+FWD2 general case: a reverse DFA pass labels every position with the set of NFA
+//              transitions that can still reach a full match; the forward walk then takes, at
+//              every byte, the highest-priority viable transition -- which is exactly the path a
+//              backtracking matcher (boost perl_matcher, regex_match) returns first.
+#pragma once
+#include <stdint.h>
+
+#define LC_REGEX_MAGIC 0x4C435258u /* 'LCRX' */
+#define LC_MAX_GROUPS 32u
+#define LC_NONE_ENTRY 0xFFFFFFFFu
+#define LC_PREFIX_DEAD 0u
+#define LC_PREFIX_ACCEPT 0xFFFFu
+#define LC_REV_DEAD 0u
+
+enum LcRegexMode {
+    LC_MODE_FWD1 = 0,   // forward-only tagged automaton
+    LC_MODE_TWOPASS = 1 // reverse DFA + guided forward walk
+};
+
+// Entry of the forward tables: bits 0..15 next walker state, bits 16..31 action id
+// (index into the save-mask list; action 0 == no capture boundary crossed).
+// LC_NONE_ENTRY == no viable transition (the line does not match).
+#define LC_ENTRY_NEXT(e) ((e) & 0xFFFFu)
+#define LC_ENTRY_ACT(e) ((e) >> 16)
+
+struct LcRegexHeader {
+    uint32_t magic;
+    uint32_t total_bytes;
+    uint32_t ngroups;  // capture groups (what.size() - 1)
+    uint32_t nclasses; // byte equivalence classes
+    uint32_t mode;     // LcRegexMode
+    uint32_t npc;      // number of "previous byte" context kinds (1 when no context assertions)
+    uint32_t nw;       // walker states (0 == START)
+    uint32_t nact;     // actions (save masks)
+    // PREFIX dfa
+    uint32_t pre_nstates;
+    uint32_t pre_start;
+    // reverse dfa (TWOPASS)
+    uint32_t rev_nstates;
+    uint32_t rev_start; // state at position n (end of input)
+    // byte offsets of the arrays inside the blob
+    uint32_t off_byte_class; // u8  [256]
+    uint32_t off_class_pc;   // u8  [nclasses]   class -> prev-context kind
+    uint32_t off_actions;    // u64 [nact]       bit s set => capture slot s := current position
+    uint32_t off_pre_next;   // u16 [pre_nstates][nclasses]  (0 dead, 0xFFFF accept before this byte)
+    uint32_t off_pre_acc;    // u8  [pre_nstates]            accept at end of input
+    uint32_t off_fwd;        // u32 FWD1: [nw*npc][nclasses]   TWOPASS: [nw*npc][rev_nstates]
+    uint32_t off_fwd_eof;    // u32 FWD1: [nw*npc]  entry taken at end of input (next ignored)
+    uint32_t off_rev_next;   // u16 [rev_nstates][nclasses]
+    uint32_t fwd_cols;       // row length of the fwd table
+    uint32_t flags;          // bit0: pattern can match only the empty prefix trivially (unused)
+    uint32_t reserved[10];
+};
+
+#ifdef __cplusplus
+static_assert(sizeof(LcRegexHeader) % 16 == 0, "header must keep 16B alignment of what follows");
+#endif

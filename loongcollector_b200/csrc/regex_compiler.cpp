@@ -1,0 +1,1439 @@
+// regex_compiler.cpp -- see regex_compiler.h.  Pure host C++ (no CUDA, no torch).
+#include "regex_compiler.h"
+
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <set>
+#include <stdexcept>
+
+namespace lcb200 {
+namespace {
+
+// ------------------------------------------------------------------------------------------ byte sets
+struct ByteSet {
+    uint64_t w[4] = {0, 0, 0, 0};
+    void set(unsigned b) { w[b >> 6] |= 1ull << (b & 63); }
+    void set_range(unsigned lo, unsigned hi) {
+        for (unsigned b = lo; b <= hi; ++b)
+            set(b);
+    }
+    bool test(unsigned b) const { return (w[b >> 6] >> (b & 63)) & 1; }
+    void invert() {
+        for (auto& x : w)
+            x = ~x;
+    }
+    void merge(const ByteSet& o) {
+        for (int i = 0; i < 4; ++i)
+            w[i] |= o.w[i];
+    }
+    bool empty() const { return !(w[0] | w[1] | w[2] | w[3]); }
+    bool operator<(const ByteSet& o) const { return memcmp(w, o.w, sizeof w) < 0; }
+    bool operator==(const ByteSet& o) const { return memcmp(w, o.w, sizeof w) == 0; }
+};
+
+// C-locale classes on `char`: bytes >= 0x80 belong to none of them.
+ByteSet cls_digit() {
+    ByteSet s;
+    s.set_range('0', '9');
+    return s;
+}
+ByteSet cls_lower() {
+    ByteSet s;
+    s.set_range('a', 'z');
+    return s;
+}
+ByteSet cls_upper() {
+    ByteSet s;
+    s.set_range('A', 'Z');
+    return s;
+}
+ByteSet cls_alpha() {
+    ByteSet s = cls_lower();
+    s.merge(cls_upper());
+    return s;
+}
+ByteSet cls_alnum() {
+    ByteSet s = cls_alpha();
+    s.merge(cls_digit());
+    return s;
+}
+ByteSet cls_word() {
+    ByteSet s = cls_alnum();
+    s.set('_');
+    return s;
+}
+ByteSet cls_space() {
+    ByteSet s;
+    s.set(' ');
+    s.set_range('\t', '\r'); // \t \n \v \f \r
+    return s;
+}
+ByteSet cls_blank() {
+    ByteSet s;
+    s.set(' ');
+    s.set('\t');
+    return s;
+}
+ByteSet cls_vspace() {
+    ByteSet s;
+    s.set_range('\n', '\r'); // \n \v \f \r
+    return s;
+}
+ByteSet cls_cntrl() {
+    ByteSet s;
+    s.set_range(0, 31);
+    s.set(127);
+    return s;
+}
+ByteSet cls_print() {
+    ByteSet s;
+    s.set_range(32, 126);
+    return s;
+}
+ByteSet cls_graph() {
+    ByteSet s;
+    s.set_range(33, 126);
+    return s;
+}
+ByteSet cls_punct() {
+    ByteSet s = cls_graph();
+    ByteSet a = cls_alnum();
+    for (int i = 0; i < 4; ++i)
+        s.w[i] &= ~a.w[i];
+    return s;
+}
+ByteSet cls_xdigit() {
+    ByteSet s = cls_digit();
+    s.set_range('a', 'f');
+    s.set_range('A', 'F');
+    return s;
+}
+ByteSet negate(ByteSet s) {
+    s.invert();
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------ AST
+enum AssertKind : uint32_t {
+    A_BOL = 1u << 0,   // ^   (line start; boost default is multi-line)
+    A_EOL = 1u << 1,   // $
+    A_BOT = 1u << 2,   // \A \`
+    A_EOT = 1u << 3,   // \z \'
+    A_WORDB = 1u << 4, // \b
+};
+
+enum NodeKind { N_EMPTY, N_SET, N_CAT, N_ALT, N_REP, N_GROUP, N_ASSERT };
+
+struct Node {
+    NodeKind kind = N_EMPTY;
+    ByteSet set;
+    std::vector<int> kids;
+    int min = 0, max = 0; // max < 0 == unbounded
+    bool greedy = true;
+    int cap = -1; // capture index (1-based) or -1
+    uint32_t akind = 0;
+};
+
+struct Unsupported : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct Invalid : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+struct Parser {
+    const unsigned char* p;
+    size_t n, i = 0;
+    std::vector<Node> nodes;
+    int ncap = 0;
+    bool icase = false;
+
+    Parser(const char* s, size_t len) : p((const unsigned char*)s), n(len) {}
+
+    int mk(NodeKind k) {
+        nodes.emplace_back();
+        nodes.back().kind = k;
+        return (int)nodes.size() - 1;
+    }
+    bool more() const { return i < n; }
+    int peek() const { return i < n ? p[i] : -1; }
+
+    int mk_set(ByteSet s) {
+        if (icase) {
+            for (unsigned c = 'a'; c <= 'z'; ++c) {
+                if (s.test(c) || s.test(c - 32)) {
+                    s.set(c);
+                    s.set(c - 32);
+                }
+            }
+        }
+        int id = mk(N_SET);
+        nodes[id].set = s;
+        return id;
+    }
+    int mk_byte(unsigned b) {
+        ByteSet s;
+        s.set(b);
+        return mk_set(s);
+    }
+
+    int parse_alt() {
+        std::vector<int> alts;
+        alts.push_back(parse_cat());
+        while (peek() == '|') {
+            ++i;
+            alts.push_back(parse_cat());
+        }
+        if (alts.size() == 1)
+            return alts[0];
+        int id = mk(N_ALT);
+        nodes[id].kids = alts;
+        return id;
+    }
+
+    int parse_cat() {
+        std::vector<int> items;
+        while (more() && peek() != '|' && peek() != ')') {
+            int a = parse_repeat();
+            if (a >= 0)
+                items.push_back(a);
+        }
+        if (items.empty())
+            return mk(N_EMPTY);
+        if (items.size() == 1)
+            return items[0];
+        int id = mk(N_CAT);
+        nodes[id].kids = items;
+        return id;
+    }
+
+    static bool is_digit(int c) { return c >= '0' && c <= '9'; }
+
+    // returns -1 for constructs that produce nothing (comments, flag groups)
+    int parse_repeat() {
+        bool is_atom = true;
+        int a = parse_atom(is_atom);
+        if (a < 0)
+            return a;
+        while (more()) {
+            int c = peek();
+            int mn, mx;
+            if (c == '*') {
+                mn = 0;
+                mx = -1;
+                ++i;
+            } else if (c == '+') {
+                mn = 1;
+                mx = -1;
+                ++i;
+            } else if (c == '?') {
+                mn = 0;
+                mx = 1;
+                ++i;
+            } else if (c == '{') {
+                size_t save = i;
+                ++i;
+                while (peek() == ' ')
+                    ++i;
+                if (!is_digit(peek()))
+                    throw Invalid("invalid content of repeat range");
+                long a1 = 0;
+                while (is_digit(peek())) {
+                    a1 = a1 * 10 + (p[i++] - '0');
+                    if (a1 > 100000)
+                        throw Unsupported("repeat count too large");
+                }
+                long a2 = a1;
+                while (peek() == ' ')
+                    ++i;
+                if (peek() == ',') {
+                    ++i;
+                    while (peek() == ' ')
+                        ++i;
+                    if (is_digit(peek())) {
+                        a2 = 0;
+                        while (is_digit(peek())) {
+                            a2 = a2 * 10 + (p[i++] - '0');
+                            if (a2 > 100000)
+                                throw Unsupported("repeat count too large");
+                        }
+                    } else {
+                        a2 = -1;
+                    }
+                    while (peek() == ' ')
+                        ++i;
+                }
+                if (peek() != '}')
+                    throw Invalid("invalid content of repeat range");
+                ++i;
+                (void)save;
+                if (a2 >= 0 && a2 < a1)
+                    throw Invalid("repeat range min > max");
+                mn = (int)a1;
+                mx = (int)a2;
+            } else {
+                break;
+            }
+            if (!is_atom)
+                throw Invalid("nothing to repeat");
+            bool greedy = true;
+            if (peek() == '?') {
+                greedy = false;
+                ++i;
+            } else if (peek() == '+') {
+                throw Unsupported("possessive quantifier");
+            }
+            int r = mk(N_REP);
+            nodes[r].kids = {a};
+            nodes[r].min = mn;
+            nodes[r].max = mx;
+            nodes[r].greedy = greedy;
+            a = r;
+            // a further quantifier directly applied to a quantifier ("a**") is rejected
+            int c2 = peek();
+            if (c2 == '*' || c2 == '+' || c2 == '?' || c2 == '{')
+                throw Unsupported("stacked quantifiers");
+        }
+        return a;
+    }
+
+    int parse_group() {
+        // at '('
+        ++i;
+        int cap = -1;
+        bool saved_icase = icase;
+        if (peek() == '?') {
+            ++i;
+            int c = peek();
+            if (c == ':') {
+                ++i;
+            } else if (c == '#') {
+                while (more() && peek() != ')')
+                    ++i;
+                if (!more())
+                    throw Invalid("unterminated comment");
+                ++i;
+                return -1;
+            } else if (c == '<' || c == '\'') {
+                int close = c == '<' ? '>' : '\'';
+                if (i + 1 < n && (p[i + 1] == '=' || p[i + 1] == '!'))
+                    throw Unsupported("look-behind assertion");
+                ++i;
+                size_t s = i;
+                while (more() && peek() != close)
+                    ++i;
+                if (!more() || i == s)
+                    throw Invalid("bad group name");
+                ++i;
+                cap = ++ncap;
+            } else if (c == '=' || c == '!') {
+                throw Unsupported("look-ahead assertion");
+            } else if (c == '>') {
+                throw Unsupported("atomic group");
+            } else if (c == 'P') {
+                throw Invalid("(?P is not boost syntax");
+            } else {
+                // inline flags: (?i) (?-i) (?i:...) ; s and m only in their default (on) state
+                bool neg = false, any = false;
+                bool new_icase = icase;
+                while (more()) {
+                    c = peek();
+                    if (c == '-') {
+                        neg = true;
+                        ++i;
+                    } else if (c == 'i') {
+                        new_icase = !neg;
+                        any = true;
+                        ++i;
+                    } else if (c == 's' || c == 'm') {
+                        if (neg)
+                            throw Unsupported("(?-s) / (?-m)");
+                        any = true;
+                        ++i;
+                    } else if (c == 'x') {
+                        throw Unsupported("(?x)");
+                    } else {
+                        break;
+                    }
+                }
+                if (!any)
+                    throw Unsupported("unsupported (? construct");
+                if (peek() == ')') {
+                    ++i;
+                    icase = new_icase; // applies to the rest of the enclosing group
+                    return -1;
+                }
+                if (peek() != ':')
+                    throw Invalid("bad inline flags");
+                ++i;
+                icase = new_icase;
+            }
+        } else {
+            cap = ++ncap;
+        }
+        int inner = parse_alt();
+        if (peek() != ')')
+            throw Invalid("missing )");
+        ++i;
+        icase = saved_icase;
+        int g = mk(N_GROUP);
+        nodes[g].kids = {inner};
+        nodes[g].cap = cap;
+        return g;
+    }
+
+    static int hexval(int c) {
+        if (c >= '0' && c <= '9')
+            return c - '0';
+        if (c >= 'a' && c <= 'f')
+            return c - 'a' + 10;
+        if (c >= 'A' && c <= 'F')
+            return c - 'A' + 10;
+        return -1;
+    }
+
+    // class escapes shared by atom and set context; returns true if c named a class
+    static bool class_escape(int c, ByteSet& out) {
+        switch (c) {
+            case 'd':
+                out = cls_digit();
+                return true;
+            case 'D':
+                out = negate(cls_digit());
+                return true;
+            case 'w':
+                out = cls_word();
+                return true;
+            case 'W':
+                out = negate(cls_word());
+                return true;
+            case 's':
+                out = cls_space();
+                return true;
+            case 'S':
+                out = negate(cls_space());
+                return true;
+            case 'l':
+                out = cls_lower();
+                return true;
+            case 'u':
+                out = cls_upper();
+                return true;
+            default:
+                return false;
+        }
+    }
+
+    // single-character escapes; returns byte value or -1
+    int char_escape(int c) {
+        switch (c) {
+            case 'a':
+                return 7;
+            case 'e':
+                return 27;
+            case 'f':
+                return 12;
+            case 'n':
+                return 10;
+            case 'r':
+                return 13;
+            case 't':
+                return 9;
+            case 'x': {
+                if (peek() == '{') {
+                    ++i;
+                    long v = 0;
+                    int nd = 0;
+                    while (hexval(peek()) >= 0) {
+                        v = v * 16 + hexval(p[i++]);
+                        ++nd;
+                        if (v > 255)
+                            throw Unsupported("\\x{...} beyond one byte");
+                    }
+                    if (peek() != '}' || nd == 0)
+                        throw Invalid("bad \\x{}");
+                    ++i;
+                    return (int)v;
+                }
+                int v = 0, nd = 0;
+                while (nd < 2 && hexval(peek()) >= 0) {
+                    v = v * 16 + hexval(p[i++]);
+                    ++nd;
+                }
+                if (nd == 0)
+                    throw Invalid("bad \\x");
+                return v;
+            }
+            case 'c': {
+                if (!more())
+                    throw Invalid("bad \\c");
+                int v = p[i++];
+                return v & 0x1F;
+            }
+            case '0': {
+                int v = 0, nd = 0;
+                while (nd < 3 && peek() >= '0' && peek() <= '7') {
+                    v = v * 8 + (p[i++] - '0');
+                    ++nd;
+                }
+                return v & 0xFF;
+            }
+            default:
+                return -1;
+        }
+    }
+
+    int parse_escape_atom(bool& is_atom) {
+        // at char after '\'
+        if (!more())
+            throw Invalid("trailing backslash");
+        int c = p[i++];
+        ByteSet cs;
+        if (class_escape(c, cs))
+            return mk_set(cs);
+        if (c == 'h')
+            return mk_set(cls_blank());
+        if (c == 'H')
+            return mk_set(negate(cls_blank()));
+        if (c == 'v')
+            return mk_set(cls_vspace());
+        if (c == 'V')
+            return mk_set(negate(cls_vspace()));
+        int v = char_escape(c);
+        if (v >= 0)
+            return mk_byte((unsigned)v);
+        if (c >= '1' && c <= '9')
+            throw Unsupported("back-reference");
+        uint32_t ak = 0;
+        switch (c) {
+            case 'b':
+                ak = A_WORDB;
+                break;
+            case 'A':
+            case '`':
+                ak = A_BOT;
+                break;
+            case 'z':
+            case '\'':
+                ak = A_EOT;
+                break;
+            case 'Q': {
+                std::vector<int> items;
+                while (more()) {
+                    if (p[i] == '\\' && i + 1 < n && p[i + 1] == 'E') {
+                        i += 2;
+                        break;
+                    }
+                    items.push_back(mk_byte(p[i++]));
+                }
+                if (items.empty()) {
+                    is_atom = false;
+                    return -1;
+                }
+                if (items.size() == 1)
+                    return items[0];
+                // a quantifier after \Q..\E applies to the last literal only: keep it simple and reject
+                int c2 = peek();
+                if (c2 == '*' || c2 == '+' || c2 == '?' || c2 == '{')
+                    throw Unsupported("quantifier after \\Q..\\E");
+                int id = mk(N_CAT);
+                nodes[id].kids = items;
+                return id;
+            }
+            case 'B':
+            case 'Z':
+            case '<':
+            case '>':
+            case 'G':
+            case 'K':
+            case 'X':
+            case 'C':
+            case 'R':
+            case 'N':
+            case 'p':
+            case 'P':
+            case 'g':
+            case 'k':
+            case 'E':
+            case 'L':
+            case 'U':
+                throw Unsupported(std::string("escape \\") + (char)c);
+            default:
+                break;
+        }
+        if (ak) {
+            is_atom = false;
+            int id = mk(N_ASSERT);
+            nodes[id].akind = ak;
+            return id;
+        }
+        if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'))
+            throw Unsupported(std::string("escape \\") + (char)c);
+        return mk_byte((unsigned)c); // escaped punctuation / any other byte: the byte itself
+    }
+
+    int parse_set() {
+        // at char after '['
+        ByteSet s;
+        bool neg = false;
+        if (peek() == '^') {
+            neg = true;
+            ++i;
+        }
+        bool first = true;
+        for (;;) {
+            if (!more())
+                throw Invalid("unterminated character set");
+            int c = p[i];
+            if (c == ']' && !first) {
+                ++i;
+                break;
+            }
+            first = false;
+            int lo = -1;
+            ByteSet cs;
+            bool is_class = false;
+            if (c == '[' && i + 1 < n && (p[i + 1] == ':' || p[i + 1] == '.' || p[i + 1] == '=')) {
+                int kind = p[i + 1];
+                size_t s0 = i + 2, e = s0;
+                while (e + 1 < n && !(p[e] == kind && p[e + 1] == ']'))
+                    ++e;
+                if (e + 1 >= n)
+                    throw Invalid("unterminated [: :]");
+                std::string name((const char*)p + s0, e - s0);
+                i = e + 2;
+                if (kind != ':')
+                    throw Unsupported("collating element / equivalence class");
+                bool nneg = false;
+                if (!name.empty() && name[0] == '^') {
+                    nneg = true;
+                    name = name.substr(1);
+                }
+                if (name == "alnum")
+                    cs = cls_alnum();
+                else if (name == "alpha")
+                    cs = cls_alpha();
+                else if (name == "blank")
+                    cs = cls_blank();
+                else if (name == "cntrl")
+                    cs = cls_cntrl();
+                else if (name == "digit" || name == "d")
+                    cs = cls_digit();
+                else if (name == "graph")
+                    cs = cls_graph();
+                else if (name == "lower" || name == "l")
+                    cs = cls_lower();
+                else if (name == "print")
+                    cs = cls_print();
+                else if (name == "punct")
+                    cs = cls_punct();
+                else if (name == "space" || name == "s")
+                    cs = cls_space();
+                else if (name == "upper" || name == "u")
+                    cs = cls_upper();
+                else if (name == "xdigit")
+                    cs = cls_xdigit();
+                else if (name == "word" || name == "w")
+                    cs = cls_word();
+                else
+                    throw Invalid("unknown character class name");
+                if (nneg)
+                    cs.invert();
+                is_class = true;
+            } else if (c == '\\') {
+                ++i;
+                if (!more())
+                    throw Invalid("trailing backslash in set");
+                int e = p[i++];
+                if (class_escape(e, cs)) {
+                    is_class = true;
+                } else {
+                    int v = char_escape(e);
+                    if (v >= 0) {
+                        lo = v;
+                    } else if ((e >= 'a' && e <= 'z') || (e >= 'A' && e <= 'Z') || (e >= '1' && e <= '9')) {
+                        throw Unsupported(std::string("escape \\") + (char)e + " inside a set");
+                    } else {
+                        lo = e;
+                    }
+                }
+            } else {
+                lo = c;
+                ++i;
+            }
+            if (is_class) {
+                if (peek() == '-' && i + 1 < n && p[i + 1] != ']')
+                    throw Unsupported("range starting at a class");
+                if (icase) {
+                    // classes are closed under ASCII case except lower/upper: fold them
+                    for (unsigned b = 'a'; b <= 'z'; ++b)
+                        if (cs.test(b) || cs.test(b - 32)) {
+                            cs.set(b);
+                            cs.set(b - 32);
+                        }
+                }
+                s.merge(cs);
+                continue;
+            }
+            int hi = lo;
+            if (peek() == '-' && i + 1 < n && p[i + 1] != ']') {
+                ++i;
+                int c2 = p[i];
+                if (c2 == '[' && i + 1 < n && (p[i + 1] == ':' || p[i + 1] == '.' || p[i + 1] == '='))
+                    throw Unsupported("range ending at a class");
+                if (c2 == '\\') {
+                    ++i;
+                    if (!more())
+                        throw Invalid("trailing backslash in set");
+                    int e = p[i++];
+                    ByteSet tmp;
+                    if (class_escape(e, tmp))
+                        throw Unsupported("range ending at a class");
+                    int v = char_escape(e);
+                    if (v >= 0)
+                        hi = v;
+                    else if ((e >= 'a' && e <= 'z') || (e >= 'A' && e <= 'Z') || (e >= '1' && e <= '9'))
+                        throw Unsupported("escape inside a set");
+                    else
+                        hi = e;
+                } else {
+                    hi = c2;
+                    ++i;
+                }
+                if (hi < lo)
+                    throw Invalid("invalid range in character set");
+            }
+            for (int b = lo; b <= hi; ++b) {
+                s.set((unsigned)b);
+                if (icase) {
+                    if (b >= 'a' && b <= 'z')
+                        s.set((unsigned)b - 32);
+                    if (b >= 'A' && b <= 'Z')
+                        s.set((unsigned)b + 32);
+                }
+            }
+        }
+        if (neg)
+            s.invert();
+        int id = mk(N_SET);
+        nodes[id].set = s;
+        return id;
+    }
+
+    int parse_atom(bool& is_atom) {
+        int c = p[i];
+        switch (c) {
+            case '(': {
+                int g = parse_group();
+                if (g < 0)
+                    is_atom = false;
+                return g;
+            }
+            case '[':
+                ++i;
+                return parse_set();
+            case '.': {
+                ++i;
+                ByteSet s;
+                s.invert(); // boost default: '.' matches every char including '\n' and NUL
+                int id = mk(N_SET);
+                nodes[id].set = s;
+                return id;
+            }
+            case '^': {
+                ++i;
+                is_atom = false;
+                int id = mk(N_ASSERT);
+                nodes[id].akind = A_BOL;
+                return id;
+            }
+            case '$': {
+                ++i;
+                is_atom = false;
+                int id = mk(N_ASSERT);
+                nodes[id].akind = A_EOL;
+                return id;
+            }
+            case '\\':
+                ++i;
+                return parse_escape_atom(is_atom);
+            case '*':
+            case '+':
+            case '?':
+                throw Invalid("nothing to repeat");
+            case '{':
+                throw Invalid("unexpected {");
+            default:
+                ++i;
+                return mk_byte((unsigned)c);
+        }
+    }
+
+    int parse_all() {
+        int r = parse_alt();
+        if (more()) {
+            if (peek() == ')')
+                throw Invalid("unmatched )");
+            throw Invalid("trailing characters");
+        }
+        return r;
+    }
+};
+
+// ------------------------------------------------------------------------------------------ NFA program
+enum Op { OP_CHAR, OP_SPLIT, OP_JMP, OP_SAVE, OP_ASSERT, OP_MATCH };
+struct Inst {
+    Op op;
+    int x = -1, y = -1; // CHAR/SAVE/ASSERT/JMP: x = next ; SPLIT: x preferred, y alternative
+    int arg = 0;        // CHAR: set id ; SAVE: slot ; ASSERT: kind mask
+};
+
+struct Compiler {
+    const std::vector<Node>& nodes;
+    std::vector<Inst> prog;
+    std::vector<ByteSet> sets;
+    std::map<ByteSet, int> set_ids;
+    size_t max_insts = 6000;
+
+    explicit Compiler(const std::vector<Node>& n) : nodes(n) {}
+
+    int emit(Op op, int arg = 0) {
+        if (prog.size() >= max_insts)
+            throw Unsupported("pattern too large after expansion");
+        Inst in;
+        in.op = op;
+        in.arg = arg;
+        prog.push_back(in);
+        return (int)prog.size() - 1;
+    }
+    int set_id(const ByteSet& s) {
+        auto it = set_ids.find(s);
+        if (it != set_ids.end())
+            return it->second;
+        int id = (int)sets.size();
+        sets.push_back(s);
+        set_ids[s] = id;
+        return id;
+    }
+
+    bool nullable(int id) const {
+        const Node& nd = nodes[id];
+        switch (nd.kind) {
+            case N_EMPTY:
+            case N_ASSERT:
+                return true;
+            case N_SET:
+                return false;
+            case N_CAT:
+                for (int k : nd.kids)
+                    if (!nullable(k))
+                        return false;
+                return true;
+            case N_ALT:
+                for (int k : nd.kids)
+                    if (nullable(k))
+                        return true;
+                return false;
+            case N_REP:
+                return nd.min == 0 || nullable(nd.kids[0]);
+            case N_GROUP:
+                return nullable(nd.kids[0]);
+        }
+        return true;
+    }
+
+    // A fragment is "open": control falls through to the next emitted instruction; dangling jumps are
+    // collected in `outs` and patched by the caller to the instruction that follows the fragment.
+    void patch(std::vector<int*>& outs, int target) {
+        for (int* o : outs)
+            *o = target;
+        outs.clear();
+    }
+
+    // Emits code for node; on return, every pointer in `holes` must be set to the index of the next
+    // instruction emitted after this fragment.  Since `prog` may reallocate we store (inst, field) pairs.
+    struct Hole {
+        int inst;
+        int field; // 0 = x, 1 = y
+    };
+    void fill(std::vector<Hole>& holes, int target) {
+        for (auto h : holes)
+            (h.field ? prog[h.inst].y : prog[h.inst].x) = target;
+        holes.clear();
+    }
+
+    // Returns the list of holes to be pointed at whatever comes next.
+    std::vector<Hole> gen(int id) {
+        const Node& nd = nodes[id];
+        std::vector<Hole> holes;
+        switch (nd.kind) {
+            case N_EMPTY:
+                break;
+            case N_SET: {
+                if (nd.set.empty()) {
+                    // matches nothing: a CHAR over the empty set is a dead end
+                }
+                int c = emit(OP_CHAR, set_id(nd.set));
+                holes.push_back({c, 0});
+                break;
+            }
+            case N_ASSERT: {
+                int a = emit(OP_ASSERT, (int)nd.akind);
+                holes.push_back({a, 0});
+                break;
+            }
+            case N_GROUP: {
+                if (nd.cap >= 0) {
+                    int s0 = emit(OP_SAVE, 2 * (nd.cap - 1));
+                    std::vector<Hole> h0 = {{s0, 0}};
+                    fill(h0, (int)prog.size());
+                    auto h = gen(nd.kids[0]);
+                    int s1 = emit(OP_SAVE, 2 * (nd.cap - 1) + 1);
+                    fill(h, s1);
+                    holes.push_back({s1, 0});
+                } else {
+                    holes = gen(nd.kids[0]);
+                }
+                break;
+            }
+            case N_CAT: {
+                std::vector<Hole> pending;
+                for (int k : nd.kids) {
+                    fill(pending, (int)prog.size());
+                    pending = gen(k);
+                }
+                holes = pending;
+                break;
+            }
+            case N_ALT: {
+                // split chain preferring earlier alternatives
+                size_t na = nd.kids.size();
+                for (size_t a = 0; a < na; ++a) {
+                    if (a + 1 < na) {
+                        int sp = emit(OP_SPLIT);
+                        prog[sp].x = (int)prog.size();
+                        auto h = gen(nd.kids[a]);
+                        // the alternative may be empty (no instruction emitted): then x already points at
+                        // the next instruction, which is wrong -- route it through an explicit JMP hole
+                        int j = emit(OP_JMP);
+                        fill(h, j);
+                        holes.push_back({j, 0});
+                        prog[sp].y = (int)prog.size();
+                    } else {
+                        auto h = gen(nd.kids[a]);
+                        int j = emit(OP_JMP);
+                        fill(h, j);
+                        holes.push_back({j, 0});
+                    }
+                }
+                break;
+            }
+            case N_REP: {
+                int child = nd.kids[0];
+                if ((nd.max < 0 || nd.max > 1) && nullable(child))
+                    throw Unsupported("repeat of a sub-expression that can match the empty string");
+                std::vector<Hole> pending;
+                for (int r = 0; r < nd.min; ++r) {
+                    fill(pending, (int)prog.size());
+                    pending = gen(child);
+                }
+                if (nd.max < 0) {
+                    // star:  L: SPLIT body, exit ; body ; JMP L
+                    int sp = emit(OP_SPLIT);
+                    fill(pending, sp);
+                    int body = (int)prog.size();
+                    auto h = gen(child);
+                    int j = emit(OP_JMP);
+                    fill(h, j);
+                    prog[j].x = sp;
+                    if (nd.greedy) {
+                        prog[sp].x = body;
+                        holes.push_back({sp, 1});
+                    } else {
+                        prog[sp].y = body;
+                        holes.push_back({sp, 0});
+                    }
+                } else {
+                    // (max - min) nested optionals, all skipping to the common end
+                    for (int r = nd.min; r < nd.max; ++r) {
+                        int sp = emit(OP_SPLIT);
+                        fill(pending, sp);
+                        int body = (int)prog.size();
+                        pending = gen(child);
+                        if (pending.empty() && body == (int)prog.size()) {
+                            // empty body: nothing emitted
+                        }
+                        if (nd.greedy) {
+                            prog[sp].x = body;
+                            holes.push_back({sp, 1});
+                        } else {
+                            prog[sp].y = body;
+                            holes.push_back({sp, 0});
+                        }
+                    }
+                    for (auto h : pending)
+                        holes.push_back(h);
+                }
+                break;
+            }
+        }
+        return holes;
+    }
+};
+
+// ------------------------------------------------------------------------------------------ context kinds
+enum Kind { K_EDGE = 0, K_LF = 1, K_CR = 2, K_FF = 3, K_WORD = 4, K_OTHER = 5, K_COUNT = 6 };
+
+int byte_kind(unsigned b) {
+    if (b == '\n')
+        return K_LF;
+    if (b == '\r')
+        return K_CR;
+    if (b == '\f')
+        return K_FF;
+    if ((b >= '0' && b <= '9') || (b >= 'a' && b <= 'z') || (b >= 'A' && b <= 'Z') || b == '_')
+        return K_WORD;
+    return K_OTHER;
+}
+
+// boost perl_matcher::match_start_line / match_end_line / match_word_boundary semantics on (prev kind, next kind);
+// K_EDGE means start of input (prev) or end of input (next).
+bool asserts_hold(uint32_t mask, int pk, int nk) {
+    auto sep = [](int k) { return k == K_LF || k == K_CR || k == K_FF; };
+    if (mask & A_BOL) {
+        if (!(pk == K_EDGE || (sep(pk) && !(pk == K_CR && nk == K_LF))))
+            return false;
+    }
+    if (mask & A_EOL) {
+        if (!(nk == K_EDGE || (sep(nk) && !(pk == K_CR && nk == K_LF))))
+            return false;
+    }
+    if ((mask & A_BOT) && pk != K_EDGE)
+        return false;
+    if ((mask & A_EOT) && nk != K_EDGE)
+        return false;
+    if (mask & A_WORDB) {
+        if ((pk == K_WORD) == (nk == K_WORD))
+            return false;
+    }
+    return true;
+}
+
+struct Cand {
+    int target; // walker index (>=1) of a CHAR inst, or -1 for MATCH
+    uint64_t saves;
+    uint32_t asserts;
+};
+
+template <class T>
+void put(std::vector<uint8_t>& blob, uint32_t& off_field, const std::vector<T>& v) {
+    while (blob.size() % 16)
+        blob.push_back(0);
+    off_field = (uint32_t)blob.size();
+    const uint8_t* p = (const uint8_t*)v.data();
+    blob.insert(blob.end(), p, p + v.size() * sizeof(T));
+}
+
+} // namespace
+
+CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_bytes) {
+    CompileResult res;
+    try {
+        Parser ps(pattern, len);
+        int root = ps.parse_all();
+        res.valid = true;
+        res.ngroups = (uint32_t)ps.ncap;
+        if (ps.ncap > (int)LC_MAX_GROUPS)
+            throw Unsupported("more than 32 capture groups");
+
+        Compiler cc(ps.nodes);
+        auto holes = cc.gen(root);
+        int m = cc.emit(OP_MATCH);
+        cc.fill(holes, m);
+        const std::vector<Inst>& prog = cc.prog;
+        res.n_insts = (uint32_t)prog.size();
+
+        bool has_ctx = false;
+        for (auto& in : prog)
+            if (in.op == OP_ASSERT)
+                has_ctx = true;
+        const int npc = has_ctx ? K_COUNT : 1;
+        auto kind_of = [&](unsigned b) { return has_ctx ? byte_kind(b) : 0; };
+
+        // ---- walker states: 0 = START, 1.. = CHAR instructions
+        std::vector<int> walker_of(prog.size(), -1), inst_of_walker = {-1};
+        for (size_t k = 0; k < prog.size(); ++k)
+            if (prog[k].op == OP_CHAR) {
+                walker_of[k] = (int)inst_of_walker.size();
+                inst_of_walker.push_back((int)k);
+            }
+        const int nw = (int)inst_of_walker.size();
+        if (nw > 4000)
+            throw Unsupported("too many NFA states");
+        res.n_walkers = (uint32_t)nw;
+
+        // ---- priority-ordered candidate lists
+        std::vector<std::vector<Cand>> cand(nw);
+        {
+            std::vector<std::vector<uint32_t>> seen;
+            std::vector<Cand>* out = nullptr;
+            size_t budget = 0;
+            struct Rec {
+                const std::vector<Inst>& prog;
+                const std::vector<int>& walker_of;
+                std::vector<std::vector<uint32_t>>& seen;
+                std::vector<Cand>*& out;
+                size_t& budget;
+                void go(int pc, uint64_t saves, uint32_t am) {
+                    if (++budget > 2000000)
+                        throw Unsupported("epsilon closure too large");
+                    for (uint32_t mk : seen[pc])
+                        if ((mk & am) == mk)
+                            return; // an earlier (higher priority) arrival dominates
+                    seen[pc].push_back(am);
+                    const Inst& in = prog[pc];
+                    switch (in.op) {
+                        case OP_CHAR:
+                            out->push_back({walker_of[pc], saves, am});
+                            break;
+                        case OP_MATCH:
+                            out->push_back({-1, saves, am});
+                            break;
+                        case OP_JMP:
+                            go(in.x, saves, am);
+                            break;
+                        case OP_SPLIT:
+                            go(in.x, saves, am);
+                            go(in.y, saves, am);
+                            break;
+                        case OP_SAVE:
+                            go(in.x, saves | (1ull << in.arg), am);
+                            break;
+                        case OP_ASSERT:
+                            go(in.x, saves, am | (uint32_t)in.arg);
+                            break;
+                    }
+                }
+            } rec{prog, walker_of, seen, out, budget};
+            for (int w = 0; w < nw; ++w) {
+                seen.assign(prog.size(), {});
+                out = &cand[w];
+                budget = 0;
+                int entry = (w == 0) ? 0 : prog[inst_of_walker[w]].x;
+                rec.go(entry, 0, 0);
+            }
+        }
+
+        // ---- byte classes
+        uint8_t byte_class[256];
+        int nclasses = 0;
+        {
+            std::map<std::vector<uint8_t>, int> sig_to_class;
+            for (unsigned b = 0; b < 256; ++b) {
+                std::vector<uint8_t> sig;
+                sig.reserve(cc.sets.size() + 1);
+                for (auto& s : cc.sets)
+                    sig.push_back(s.test(b));
+                sig.push_back((uint8_t)kind_of(b));
+                auto it = sig_to_class.find(sig);
+                if (it == sig_to_class.end()) {
+                    it = sig_to_class.emplace(sig, nclasses++).first;
+                }
+                byte_class[b] = (uint8_t)it->second;
+            }
+        }
+        std::vector<unsigned> class_rep(nclasses); // a representative byte
+        for (int b = 255; b >= 0; --b)
+            class_rep[byte_class[b]] = (unsigned)b;
+        std::vector<uint8_t> class_kind(nclasses);
+        for (int c = 0; c < nclasses; ++c)
+            class_kind[c] = (uint8_t)kind_of(class_rep[c]);
+        auto walker_has = [&](int w, int c) { return cc.sets[prog[inst_of_walker[w]].arg].test(class_rep[c]); };
+        // kinds the byte consumed by walker w can have (prev context when standing in w)
+        std::vector<uint32_t> walker_pcs(nw, 0);
+        walker_pcs[0] = 1u << 0; // START: K_EDGE (or the single collapsed kind)
+        for (int w = 1; w < nw; ++w)
+            for (int c = 0; c < nclasses; ++c)
+                if (walker_has(w, c))
+                    walker_pcs[w] |= 1u << class_kind[c];
+
+        // ---- actions
+        std::vector<uint64_t> actions = {0};
+        std::map<uint64_t, uint32_t> action_id = {{0ull, 0u}};
+        auto act = [&](uint64_t mask) {
+            auto it = action_id.find(mask);
+            if (it != action_id.end())
+                return it->second;
+            uint32_t id = (uint32_t)actions.size();
+            if (id >= 0xFFFF)
+                throw Unsupported("too many distinct capture actions");
+            actions.push_back(mask);
+            action_id[mask] = id;
+            return id;
+        };
+        auto entry_of = [&](const Cand& cd) {
+            uint32_t nxt = cd.target < 0 ? 0xFFFFu : (uint32_t)cd.target;
+            return nxt | (act(cd.saves) << 16);
+        };
+
+        // ---- PREFIX dfa (forward subset construction; boolean, order-insensitive)
+        std::vector<uint16_t> pre_next;
+        std::vector<uint8_t> pre_acc;
+        uint32_t pre_start = 1;
+        {
+            typedef std::pair<std::vector<int>, int> Key; // (sorted walker set, prev kind)
+            std::map<Key, uint32_t> ids;
+            std::vector<Key> states;
+            states.push_back(Key()); // 0 = dead
+            auto intern = [&](Key k) -> uint32_t {
+                if (k.first.empty())
+                    return 0;
+                auto it = ids.find(k);
+                if (it != ids.end())
+                    return it->second;
+                if (states.size() >= 8000)
+                    throw Unsupported("prefix DFA too large");
+                uint32_t id = (uint32_t)states.size();
+                ids[k] = id;
+                states.push_back(k);
+                return id;
+            };
+            pre_start = intern(Key({0}, 0));
+            for (size_t s = 0; s < states.size(); ++s) {
+                pre_next.resize((s + 1) * nclasses, 0);
+                pre_acc.resize(s + 1, 0);
+                if (s == 0)
+                    continue;
+                Key cur = states[s]; // copy: `states` grows
+                int pk = cur.second;
+                for (int w : cur.first)
+                    for (auto& cd : cand[w])
+                        if (cd.target < 0 && asserts_hold(cd.asserts, pk, K_EDGE))
+                            pre_acc[s] = 1;
+                for (int c = 0; c < nclasses; ++c) {
+                    int nk = class_kind[c];
+                    bool accept_now = false;
+                    std::set<int> nxt;
+                    for (int w : cur.first)
+                        for (auto& cd : cand[w]) {
+                            if (!asserts_hold(cd.asserts, pk, has_ctx ? nk : 0) && has_ctx)
+                                continue;
+                            if (cd.target < 0)
+                                accept_now = true;
+                            else if (walker_has(cd.target, c))
+                                nxt.insert(cd.target);
+                        }
+                    uint32_t v;
+                    if (accept_now)
+                        v = LC_PREFIX_ACCEPT;
+                    else
+                        v = intern(Key(std::vector<int>(nxt.begin(), nxt.end()), nk));
+                    pre_next[s * nclasses + c] = (uint16_t)v;
+                }
+            }
+            res.n_prefix = (uint32_t)states.size();
+        }
+        // NB: when !has_ctx every kind is 0 == K_EDGE and no cand carries asserts, so asserts_hold is vacuous.
+
+        // ---- reverse DFA over viable-target sets
+        // state = (sorted set of targets {walker idx, or 0 for MATCH}, next kind)
+        typedef std::pair<std::vector<int>, int> RKey;
+        std::vector<RKey> rstates;
+        std::vector<uint16_t> rev_next;
+        std::vector<std::vector<uint8_t>> rev_incoming; // classes on which each state is entered
+        uint32_t rev_start = 1;
+        {
+            std::map<RKey, uint32_t> ids;
+            rstates.push_back(RKey()); // 0 dead
+            auto intern = [&](RKey k) -> uint32_t {
+                if (k.first.empty())
+                    return 0;
+                auto it = ids.find(k);
+                if (it != ids.end())
+                    return it->second;
+                if (rstates.size() >= 8000)
+                    throw Unsupported("reverse DFA too large");
+                uint32_t id = (uint32_t)rstates.size();
+                ids[k] = id;
+                rstates.push_back(k);
+                return id;
+            };
+            rev_start = intern(RKey({0}, 0)); // {MATCH}, next = EDGE
+            for (size_t s = 0; s < rstates.size(); ++s) {
+                rev_next.resize((s + 1) * nclasses, 0);
+                rev_incoming.resize(rstates.size());
+                if (s == 0)
+                    continue;
+                RKey cur = rstates[s];
+                std::vector<char> inR(nw, 0);
+                bool match_in = false;
+                for (int t : cur.first) {
+                    if (t == 0)
+                        match_in = true;
+                    else
+                        inR[t] = 1;
+                }
+                int nk = cur.second;
+                for (int c = 0; c < nclasses; ++c) {
+                    int pk = class_kind[c];
+                    std::vector<int> nxt;
+                    for (int q = 1; q < nw; ++q) {
+                        if (!walker_has(q, c))
+                            continue;
+                        bool viable = false;
+                        for (auto& cd : cand[q]) {
+                            bool in = cd.target < 0 ? match_in : (bool)inR[cd.target];
+                            if (in && asserts_hold(cd.asserts, pk, nk)) {
+                                viable = true;
+                                break;
+                            }
+                        }
+                        if (viable)
+                            nxt.push_back(q);
+                    }
+                    uint32_t v = intern(RKey(nxt, pk));
+                    rev_next[s * nclasses + c] = (uint16_t)v;
+                    rev_incoming.resize(rstates.size());
+                    if (v)
+                        rev_incoming[v].push_back((uint8_t)c);
+                }
+            }
+            res.n_rev = (uint32_t)rstates.size();
+        }
+        const int nD = (int)rstates.size();
+
+        // first viable candidate of walker w under prev kind pk in reverse state D (index into cand[w] or -1)
+        auto first_viable = [&](int w, int pk, int D) -> int {
+            const RKey& k = rstates[D];
+            for (size_t ci = 0; ci < cand[w].size(); ++ci) {
+                const Cand& cd = cand[w][ci];
+                int t = cd.target < 0 ? 0 : cd.target;
+                if (std::binary_search(k.first.begin(), k.first.end(), t) && asserts_hold(cd.asserts, pk, k.second))
+                    return (int)ci;
+            }
+            return -1;
+        };
+        // first class-compatible candidate (forward-only choice)
+        auto first_fwd = [&](int w, int pk, int c /* class or -1 for EOF */) -> int {
+            int nk = c < 0 ? K_EDGE : class_kind[c];
+            for (size_t ci = 0; ci < cand[w].size(); ++ci) {
+                const Cand& cd = cand[w][ci];
+                if (!asserts_hold(cd.asserts, pk, has_ctx ? nk : 0) && has_ctx)
+                    continue;
+                if (c < 0) {
+                    if (cd.target < 0)
+                        return (int)ci;
+                } else if (cd.target >= 0 && walker_has(cd.target, c)) {
+                    return (int)ci;
+                }
+            }
+            return -1;
+        };
+
+        // ---- is the forward-only automaton exact?
+        bool fwd1_safe = true;
+        for (int D = 1; D < nD && fwd1_safe; ++D) {
+            for (int w = 0; w < nw && fwd1_safe; ++w) {
+                for (int pk = 0; pk < npc && fwd1_safe; ++pk) {
+                    if (!(walker_pcs[w] >> pk & 1))
+                        continue;
+                    int v = first_viable(w, pk, D);
+                    if (v < 0)
+                        continue;
+                    if ((uint32_t)D == rev_start) {
+                        if (first_fwd(w, pk, -1) != v)
+                            fwd1_safe = false;
+                    }
+                    for (uint8_t c : rev_incoming[D])
+                        if (first_fwd(w, pk, c) != v) {
+                            fwd1_safe = false;
+                            break;
+                        }
+                }
+            }
+        }
+
+        // ---- forward tables
+        std::vector<uint32_t> fwd, fwd_eof;
+        uint32_t fwd_cols;
+        uint32_t mode;
+        if (fwd1_safe) {
+            mode = LC_MODE_FWD1;
+            fwd_cols = (uint32_t)nclasses;
+            fwd.assign((size_t)nw * npc * fwd_cols, LC_NONE_ENTRY);
+            fwd_eof.assign((size_t)nw * npc, LC_NONE_ENTRY);
+            for (int w = 0; w < nw; ++w)
+                for (int pk = 0; pk < npc; ++pk) {
+                    for (int c = 0; c < nclasses; ++c) {
+                        int ci = first_fwd(w, pk, c);
+                        if (ci >= 0)
+                            fwd[((size_t)w * npc + pk) * fwd_cols + c] = entry_of(cand[w][ci]);
+                    }
+                    int ci = first_fwd(w, pk, -1);
+                    if (ci >= 0)
+                        fwd_eof[(size_t)w * npc + pk] = entry_of(cand[w][ci]);
+                }
+        } else {
+            mode = LC_MODE_TWOPASS;
+            fwd_cols = (uint32_t)nD;
+            if ((size_t)nw * npc * fwd_cols * 4 > max_table_bytes)
+                throw Unsupported("two-pass forward table too large");
+            fwd.assign((size_t)nw * npc * fwd_cols, LC_NONE_ENTRY);
+            fwd_eof.assign((size_t)nw * npc, LC_NONE_ENTRY);
+            for (int w = 0; w < nw; ++w)
+                for (int pk = 0; pk < npc; ++pk)
+                    for (int D = 1; D < nD; ++D) {
+                        int ci = first_viable(w, pk, D);
+                        if (ci >= 0)
+                            fwd[((size_t)w * npc + pk) * fwd_cols + D] = entry_of(cand[w][ci]);
+                    }
+        }
+
+        // ---- pack the blob
+        LcRegexHeader h;
+        memset(&h, 0, sizeof h);
+        h.magic = LC_REGEX_MAGIC;
+        h.ngroups = res.ngroups;
+        h.nclasses = (uint32_t)nclasses;
+        h.mode = mode;
+        h.npc = (uint32_t)npc;
+        h.nw = (uint32_t)nw;
+        h.nact = (uint32_t)actions.size();
+        h.pre_nstates = res.n_prefix;
+        h.pre_start = pre_start;
+        h.rev_nstates = (uint32_t)nD;
+        h.rev_start = rev_start;
+        h.fwd_cols = fwd_cols;
+        std::vector<uint8_t> blob(sizeof h, 0);
+        std::vector<uint8_t> bc(byte_class, byte_class + 256);
+        put(blob, h.off_byte_class, bc);
+        put(blob, h.off_class_pc, class_kind);
+        put(blob, h.off_actions, actions);
+        put(blob, h.off_pre_next, pre_next);
+        put(blob, h.off_pre_acc, pre_acc);
+        put(blob, h.off_fwd, fwd);
+        put(blob, h.off_fwd_eof, fwd_eof);
+        if (mode == LC_MODE_TWOPASS)
+            put(blob, h.off_rev_next, rev_next);
+        while (blob.size() % 16)
+            blob.push_back(0);
+        h.total_bytes = (uint32_t)blob.size();
+        memcpy(blob.data(), &h, sizeof h);
+        if (blob.size() > max_table_bytes)
+            throw Unsupported("automaton tables too large");
+        res.blob.swap(blob);
+        res.supported = true;
+    } catch (const Invalid& e) {
+        res.valid = false;
+        res.supported = false;
+        res.error = std::string("invalid regex: ") + e.what();
+    } catch (const Unsupported& e) {
+        res.supported = false;
+        res.error = std::string("unsupported regex: ") + e.what();
+    }
+    return res;
+}
+
+} // namespace lcb200

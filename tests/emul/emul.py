@@ -1,0 +1,74 @@
+"""ctypes wrapper of the TEST-ONLY emulation library (tests/emul/lc_emul.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liblc_emul.so")
+        srcs = [os.path.join(_HERE, "lc_emul.cpp")] + [
+            os.path.join(_HERE, "..", "..", "loongcollector_b200", "csrc", f)
+            for f in ("regex_compiler.cpp", "regex_compiler.h", "lc_exec.cuh", "lc_tables.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call([os.path.join(_HERE, "build.sh")])
+        L = C.CDLL(so)
+        L.emul_compile.restype = C.c_void_p
+        L.emul_compile.argtypes = [C.c_char_p, C.c_uint64]
+        L.emul_free.argtypes = [C.c_void_p]
+        for f in ("emul_valid", "emul_supported"):
+            getattr(L, f).restype = C.c_int
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.emul_error.restype = C.c_char_p
+        L.emul_error.argtypes = [C.c_void_p]
+        L.emul_ngroups.restype = C.c_uint32
+        L.emul_ngroups.argtypes = [C.c_void_p]
+        L.emul_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.emul_prefix_match.restype = C.c_int
+        L.emul_prefix_match.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
+        L.emul_full_match.restype = C.c_int
+        L.emul_full_match.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+class EmulRegex:
+    def __init__(self, pattern):
+        if isinstance(pattern, str):
+            pattern = pattern.encode("utf-8")
+        L = lib()
+        self._h = L.emul_compile(pattern, len(pattern))
+        self.valid = bool(L.emul_valid(self._h))
+        self.supported = bool(L.emul_supported(self._h))
+        self.error = L.emul_error(self._h).decode()
+        self.ngroups = int(L.emul_ngroups(self._h))
+        info = np.zeros(8, np.uint32)
+        L.emul_info(self._h, info.ctypes.data_as(C.c_void_p))
+        self.mode, self.nclasses, self.nw, self.npc, self.nrev, self.npre, self.blob_bytes, self.ninsts = \
+            [int(x) for x in info]
+
+    def prefix_match(self, data: bytes) -> bool:
+        assert self.supported, self.error
+        return bool(lib().emul_prefix_match(self._h, data, len(data)))
+
+    def full_match(self, data: bytes):
+        assert self.supported, self.error
+        co = np.zeros(max(self.ngroups, 1), np.uint32)
+        cl = np.zeros(max(self.ngroups, 1), np.uint32)
+        ok = lib().emul_full_match(self._h, data, len(data), co.ctypes.data_as(C.c_void_p),
+                                   cl.ctypes.data_as(C.c_void_p))
+        if not ok:
+            return None
+        return [(int(co[g]), int(cl[g])) for g in range(self.ngroups)]
+
+    def __del__(self):
+        try:
+            lib().emul_free(self._h)
+        except Exception:
+            pass

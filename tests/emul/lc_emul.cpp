@@ -1,0 +1,70 @@
+// lc_emul.cpp -- TEST-ONLY host emulation of the device-side table interpreter.
+//
+// Builds the product's regex COMPILER (loongcollector_b200/csrc/regex_compiler.cpp) together with the
+// __host__ __device__ interpreter statements of lc_exec.cuh into a CPU shared object so that the
+// "not gpu" test tier can check compiler + table semantics against the oracle without a B200.
+// It is NOT part of the product library, is never loaded by loongcollector_b200/, and nothing here is a
+// CPU fallback: the product C-ABI has no path that reaches this file.
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../loongcollector_b200/csrc/lc_exec.cuh"
+#include "../../loongcollector_b200/csrc/regex_compiler.h"
+
+struct EmulRegex {
+    lcb200::CompileResult r;
+};
+
+extern "C" {
+
+EmulRegex* emul_compile(const char* pattern, uint64_t len) {
+    EmulRegex* e = new EmulRegex;
+    e->r = lcb200::compile_regex(pattern, (size_t)len);
+    return e;
+}
+void emul_free(EmulRegex* e) { delete e; }
+int emul_valid(const EmulRegex* e) { return e->r.valid; }
+int emul_supported(const EmulRegex* e) { return e->r.supported; }
+const char* emul_error(const EmulRegex* e) { return e->r.error.c_str(); }
+uint32_t emul_ngroups(const EmulRegex* e) { return e->r.ngroups; }
+// info[0..7] = mode, nclasses, nw, npc, rev_nstates, pre_nstates, blob bytes, n_insts
+void emul_info(const EmulRegex* e, uint32_t* info) {
+    memset(info, 0, 8 * sizeof(uint32_t));
+    if (!e->r.supported)
+        return;
+    const LcRegexHeader* h = (const LcRegexHeader*)e->r.blob.data();
+    info[0] = h->mode;
+    info[1] = h->nclasses;
+    info[2] = h->nw;
+    info[3] = h->npc;
+    info[4] = h->rev_nstates;
+    info[5] = h->pre_nstates;
+    info[6] = h->total_bytes;
+    info[7] = e->r.n_insts;
+}
+int emul_prefix_match(const EmulRegex* e, const uint8_t* s, uint32_t n) {
+    LcProgView v = lc_view(e->r.blob.data());
+    return lc_prefix_match(v, s, n) ? 1 : 0;
+}
+int emul_full_match(const EmulRegex* e, const uint8_t* s, uint32_t n, uint32_t* cap_off, uint32_t* cap_len) {
+    LcProgView v = lc_view(e->r.blob.data());
+    uint32_t slots[2 * LC_MAX_GROUPS];
+    for (uint32_t k = 0; k < 2 * LC_MAX_GROUPS; ++k)
+        slots[k] = LC_SLOT_UNSET;
+    bool ok;
+    if (v.h->mode == LC_MODE_FWD1) {
+        ok = lc_full_match_fwd1(v, s, n, slots);
+    } else {
+        std::vector<uint16_t> lab(n + 1);
+        ok = lc_rev_label(v, s, n, lab.data()) && lc_fwd_walk(v, s, n, lab.data(), slots);
+    }
+    if (!ok)
+        return 0;
+    for (uint32_t g = 0; g < v.h->ngroups; ++g)
+        lc_slots_to_cap(slots, g, n, cap_off + g, cap_len + g);
+    return 1;
+}
+}

@@ -1,0 +1,209 @@
+"""CPU tier: the product's regex compiler (tables) interpreted by the test-only emulation library
+(tests/emul) must agree with the oracle (PCRE2) and with Python `re` -- two independent
+Perl-semantics engines -- on golden vectors and on seeded random patterns/inputs."""
+import json
+import os
+import random
+import re
+
+import pytest
+
+from oracle import oracle as orc
+from tests.emul.emul import EmulRegex
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _misc():
+    with open(os.path.join(HERE, "golden", "ref_misc.json"), encoding="utf-8") as f:
+        return json.load(f)
+
+
+def test_golden_vectors():
+    d = _misc()
+    for c in d["prefix_search"] + d["multiline_start"]:
+        r = EmulRegex(c["pattern"])
+        assert r.supported, r.error
+        assert [r.prefix_match(i.encode()) for i in c["inputs"]] == c["expected"], c["source"]
+    for c in d["full_match_fields"]:
+        r = EmulRegex(c["pattern"])
+        assert r.supported, r.error
+        b = c["input"].encode()
+        caps = r.full_match(b)
+        assert caps is not None and [b[o:o + l].decode() for o, l in caps] == c["fields"], c["source"]
+
+
+UNIT_PATTERNS = [r"Exception.*", r"\s+at\s.*", r"\s*\.\.\.\d+ more", r"(\w+)\t(\w+).*"]
+
+
+def test_multiline_unit_patterns_prefix():
+    lines = [b"Exception in thread 'main' java.lang.NullPointerException",
+             b"    at com.example.myproject.Book.getTitle(Book.java:16)", b"    ...23 more", b"unmatch log", b"",
+             b" at x", b"...1 more"]
+    for p in UNIT_PATTERNS:
+        e, o = EmulRegex(p), orc.Regex(p)
+        assert e.supported, e.error
+        for ln in lines:
+            assert e.prefix_match(ln) == o.prefix_match(ln), (p, ln)
+
+
+@pytest.mark.parametrize("pattern,why", [
+    (r"(a)\1", "back-reference"), (r"a(?=b)", "look-ahead"), (r"(?<=a)b", "look-behind"), (r"(a*)*", "empty"),
+    (r"a++", "possessive"), (r"(?>a)", "atomic"), (r"\Bx", "escape"),
+])
+def test_unsupported_is_reported_not_guessed(pattern, why):
+    r = EmulRegex(pattern)
+    assert not r.supported
+    assert why in r.error
+
+
+@pytest.mark.parametrize("pattern", [r"(", r"a)", r"[a", r"*a", r"a{2,1}", "a\\"])
+def test_invalid_patterns(pattern):
+    r = EmulRegex(pattern)
+    assert not r.valid and not r.supported
+
+
+# ----------------------------------------------------------------------------- random patterns
+ATOMS = ["a", "b", "c", "x", " ", "-", "1", "2", r"\d", r"\w", r"\s", r"\S", r"\D", r"\W", ".", "[ab]", "[^a]", "[a-c1]",
+         r"[\d\.]", r"[^\s\]]", r"\[", r"\]", r"\.", '"', "[^\"]", r"\t", r"[[:alpha:]]", r"\x41", ":", "/"]
+QUANTS = ["", "", "", "*", "+", "?", "*?", "+?", "??", "{2}", "{1,3}", "{0,2}?", "{2,}"]
+
+
+def gen(rng, depth=0):
+    n = rng.randint(1, 4)
+    parts = []
+    for _ in range(n):
+        r = rng.random()
+        if depth < 3 and r < 0.25:
+            inner = gen(rng, depth + 1)
+            if rng.random() < 0.35:
+                inner = inner + "|" + gen(rng, depth + 1)
+                if rng.random() < 0.2:
+                    inner += "|"
+            atom = ("(" if rng.random() < 0.75 else "(?:") + inner + ")"
+        else:
+            atom = rng.choice(ATOMS)
+        parts.append(atom + rng.choice(QUANTS))
+    if depth == 0 and rng.random() < 0.15:
+        parts.insert(0, "^")
+    if depth == 0 and rng.random() < 0.15:
+        parts.append("$")
+    if rng.random() < 0.05:
+        parts.insert(rng.randint(0, len(parts)), r"\b")
+    if rng.random() < 0.04:
+        parts.insert(rng.randint(0, len(parts)), rng.choice(["^", "$"]))
+    return "".join(parts)
+
+
+ALPHA = "abcx  --12\t\"[].:/A_\n"
+
+
+def rand_input(rng, alpha):
+    return "".join(rng.choice(alpha) for _ in range(rng.randint(0, 14))).encode()
+
+
+def _bol_at_end_corner(pat, s):
+    return "^" in pat[1:] and s[-1:] in (b"\n", b"\r")
+
+
+def py_caps(m, n):
+    out = []
+    for g in range(1, m.re.groups + 1):
+        s, e = m.span(g)
+        out.append((n, 0) if s < 0 else (s, e - s))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_patterns_agree_with_pcre2_and_python(seed):
+    rng = random.Random(20260922 + seed)
+    checked = n_sup = n_two = 0
+    for _ in range(400):
+        pat = gen(rng)
+        try:
+            o = orc.Regex(pat)
+        except ValueError:
+            continue
+        e = EmulRegex(pat)
+        assert e.valid, (pat, e.error)
+        if not e.supported:
+            assert "empty string" in e.error or "too large" in e.error, (pat, e.error)
+            continue
+        n_sup += 1
+        n_two += e.mode
+        assert e.ngroups == o.ngroups, pat
+        try:
+            pr = re.compile(pat.encode(), re.S | re.M)
+        except re.error:
+            pr = None
+        if pr is not None and re.search(rb"\\[vhVH]|\[\[:", pat.encode()):
+            pr = None  # python spells these classes differently
+        for _ in range(25):
+            s = rand_input(rng, ALPHA)
+            want = o.full_match(s)
+            got = e.full_match(s)
+            if _bol_at_end_corner(pat, s):
+                # boost (and Python) let a mid-pattern '^' match at END of input after a trailing newline;
+                # PCRE2 does not.  The engine follows boost; only Python can arbitrate this corner.
+                if pr is not None:
+                    m = pr.fullmatch(s)
+                    assert (py_caps(m, len(s)) if m else None) == got, (pat, s)
+                    assert (pr.match(s) is not None) == e.prefix_match(s), (pat, s)
+                continue
+            assert got == want, (pat, s, got, want)
+            assert e.prefix_match(s) == o.prefix_match(s), (pat, s)
+            if pr is not None:
+                m = pr.fullmatch(s)
+                assert (m is None) == (want is None), (pat, s)
+                if m is not None:
+                    assert py_caps(m, len(s)) == want, (pat, s)
+                assert (pr.match(s) is not None) == e.prefix_match(s), (pat, s)
+            checked += 1
+    assert checked > 2000 and n_sup > 100
+
+
+def test_random_crlf_line_anchors_agree_with_pcre2_anycrlf():
+    """boost treats \\n, \\r (and \\r\\n as a unit) as line separators for ^ and $;
+    PCRE2's ANYCRLF convention is the same rule set minus \\f, so inputs here avoid \\f."""
+    rng = random.Random(77)
+    alpha = "ab \r\n\r\n"
+    n = 0
+    for _ in range(600):
+        pat = gen(rng)
+        if "^" not in pat and "$" not in pat:
+            continue
+        try:
+            o = orc.Regex("(*ANYCRLF)" + pat)
+        except ValueError:
+            continue
+        e = EmulRegex(pat)
+        if not e.supported:
+            continue
+        for _ in range(30):
+            s = rand_input(rng, alpha)
+            if _bol_at_end_corner(pat, s) or b"\r\n" in s:
+                continue  # boost never anchors BETWEEN \r and \n; PCRE2 does -- see test_boost_crlf_unit
+            assert e.full_match(s) == o.full_match(s), (pat, s)
+            assert e.prefix_match(s) == o.prefix_match(s), (pat, s)
+            n += 1
+    assert n > 500
+
+
+def test_boost_crlf_unit():
+    """perl_matcher::match_start_line / match_end_line (Boost.Regex 1.68, perl_matcher_common.hpp): a \\r\\n pair is
+    ONE separator: '$' matches before the \\r, '^' after the \\n, neither in between.  \\f is a separator too."""
+    e = EmulRegex(r"a$.^b")
+    assert e.full_match(b"a\nb") == []
+    assert e.full_match(b"a\rb") == []
+    assert e.full_match(b"a\fb") == []
+    assert e.full_match(b"a b") is None
+    e = EmulRegex(r"a$..^b")
+    assert e.full_match(b"a\r\nb") == []
+    e = EmulRegex(r"a.$.^b")
+    assert e.full_match(b"a\r\nb") is None      # '$' between \r and \n
+    assert e.full_match(b"a\n\nb") == []
+    e = EmulRegex(r"a$.^.b")
+    assert e.full_match(b"a\r\nb") is None      # '^' between \r and \n
+    assert e.full_match(b"a\n\rb") == []
+    e = EmulRegex(r"a\n^")
+    assert e.full_match(b"a\n") == []            # '^' at end of input after a trailing separator (boost, Python)
