@@ -1,0 +1,144 @@
+/*
+ * lc_b200.h -- C-ABI of the B200-native log-parsing engine (libloongcollector_b200.so).
+ *
+ * POD only: plain pointers and sizes, int return codes, no exceptions, no C++/torch types.
+ * These are the entry points a LoongCollector build binds to replace the CPU arithmetic inside
+ *   Processor::Process(PipelineEventGroup&)      core/collection_pipeline/plugin/interface/Processor.h:27-37
+ * for the four native processors on the hot path; each function cites the reference code whose
+ * RESULT it reproduces bit-exactly.  The reference-side binding is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - "base" is the contiguous SourceBuffer allocation holding the group's bytes
+ *    (core/common/memory/SourceBuffer.h:98-131,156-181); every offset is u32 relative to base.
+ *  - Host-pointer entry points (no suffix) copy base + the event table to the GPU, run the kernels and
+ *    copy the results back before returning.  *_dev entry points take DEVICE pointers and a CUDA stream
+ *    and never touch host memory (used when the arena is already resident in HBM).
+ *  - One lc_engine per (GPU, host thread): mirrors the reference's per-thread regex copies
+ *    (ProcessorParseRegexNative.cpp:64-67,255-257).  An engine is not thread-safe; regexes are immutable
+ *    after compilation and may be shared between engines.
+ *  - There is NO CPU fallback: if no CUDA device is usable every compute call fails with LC_ERR_CUDA.
+ */
+#ifndef LC_B200_H
+#define LC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LC_OK 0
+#define LC_ERR_INVALID_ARG 1
+#define LC_ERR_CUDA 2          /* no device / CUDA runtime failure (message in lc_last_error) */
+#define LC_ERR_REGEX_INVALID 3 /* pattern does not parse (reference: Init returns false, ParamExtractor.cpp:199-209) */
+#define LC_ERR_REGEX_UNSUPPORTED 4 /* valid for boost but outside the automaton subset (back-refs, look-around...) */
+#define LC_ERR_CAPACITY 5      /* caller-provided output capacity too small; *n_out holds the needed count */
+#define LC_ERR_TOO_LARGE 6     /* buffer >= 4 GiB or >= 2^30 lines in one call */
+
+/* per-event status of lc_regex_parse (ProcessorParseRegexNative.cpp:186-253) */
+#define LC_REGEX_OK 0
+#define LC_REGEX_NOMATCH 1       /* regex_match false            -> out_failed++ (:225) */
+#define LC_REGEX_KEYS_MISMATCH 2 /* what.size() <= keys.size()   -> fail, out_failed NOT incremented (:227-244) */
+
+/* per-event status of lc_delim_parse (ProcessorParseDelimiterNative.cpp:206-364) */
+#define LC_DELIM_OK 0
+#define LC_DELIM_PARSE_FAIL 1 /* FSM error (DelimiterModeFsmParser.cpp:260-294) or SplitString false */
+#define LC_DELIM_BLANK 2      /* empty / all-blank value: out_failed++, event left untouched (:220-242) */
+#define LC_DELIM_COLUMNS 3    /* column-count rule failed (:285) */
+
+/* flag bits of lc_multiline_split output events */
+#define LC_ML_IS_LAST 1u /* isLastLog flag the reference passes to CreateNewEvent (rawSize rule, :329-332) */
+#define LC_ML_MATCHED 2u /* emitted as a matched record (matched_events++), else an unmatched single line */
+
+typedef struct lc_engine lc_engine_t;
+typedef struct lc_regex lc_regex_t;
+
+/* ---- library / engine ---------------------------------------------------------------------- */
+const char* lc_version(void);
+/* Thread-local message of the last failing call on this thread. */
+const char* lc_last_error(void);
+/* Number of visible CUDA devices (0 if none / runtime unusable). */
+int lc_device_count(void);
+/* Creates an engine bound to CUDA device `device` with its own stream, workspace and pinned staging. */
+int lc_engine_create(int device, lc_engine_t** out);
+void lc_engine_destroy(lc_engine_t* e);
+/* Blocks until all work queued on the engine's stream is complete. */
+int lc_engine_sync(lc_engine_t* e);
+/* CUDA stream (cudaStream_t) owned by the engine, for callers that enqueue their own work. */
+void* lc_engine_stream(lc_engine_t* e);
+/* Number of kernel launches issued by this engine so far (bench.py's gpu_launches). */
+uint64_t lc_engine_launch_count(const lc_engine_t* e);
+/* Pinned host memory helpers (a SourceBuffer arena allocated here is DMA-able without staging). */
+void* lc_host_alloc(size_t bytes);
+void lc_host_free(void* p);
+
+/* ---- regex compilation (host only, no GPU needed) -------------------------------------------
+ * Replaces boost::regex(pattern) at ProcessorParseRegexNative.cpp:66 and
+ * ProcessorSplitMultilineLogStringNative.cpp:72-78.  *out is set (and must be freed) whenever the
+ * return code is LC_OK or LC_ERR_REGEX_UNSUPPORTED/INVALID so that lc_regex_error() can be read. */
+int lc_regex_compile(const char* pattern, size_t len, lc_regex_t** out);
+void lc_regex_free(lc_regex_t* r);
+const char* lc_regex_error(const lc_regex_t* r);
+uint32_t lc_regex_ngroups(const lc_regex_t* r);
+/* info[0..7] = mode (0 forward-only, 1 two-pass), byte classes, NFA walker states, context kinds,
+ * reverse-DFA states, prefix-DFA states, table bytes, NFA instructions. */
+void lc_regex_info(const lc_regex_t* r, uint32_t info[8]);
+
+/* ---- a1: ProcessorSplitLogStringNative::ProcessEvent (inner/ProcessorSplitLogStringNative.cpp:101-174)
+ * Cuts buf[0,len) on split_char.  Piece k = (out_off[k], out_len[k]); empty pieces kept; a trailing
+ * split char yields no extra empty piece.  *n_out = number of pieces (even when > cap => LC_ERR_CAPACITY). */
+int lc_split_lines(lc_engine_t* e, const uint8_t* buf, uint64_t len, uint8_t split_char, uint32_t* out_off,
+                   uint32_t* out_len, uint64_t cap, uint64_t* n_out);
+int lc_split_lines_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, uint8_t split_char, uint32_t* d_out_off,
+                       uint32_t* d_out_len, uint64_t cap, uint64_t* n_out /* host */);
+
+/* ---- a3: ProcessorParseRegexNative::RegexLogLineParser (ProcessorParseRegexNative.cpp:186-253)
+ * For each event i (value = base[ev_off[i], +ev_len[i])): boost::regex_match over the whole value
+ * (StringTools.cpp:183-211).  status[i] as LC_REGEX_*; on LC_REGEX_OK row i of cap_off/cap_len
+ * ([n][ngroups], offsets relative to base) holds what[g+1] = (begin, length); groups that did not
+ * participate report (end of value, 0).  Rows of failed events are zero-filled. */
+int lc_regex_parse(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, uint64_t base_len,
+                   const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n, uint32_t nkeys, uint8_t* status,
+                   uint32_t* cap_off, uint32_t* cap_len);
+int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
+                       const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                       uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len);
+
+/* Anchored prefix probe == BoostRegexSearch / regex_search(match_continuous) (StringTools.cpp:263-288),
+ * one boolean per event. */
+int lc_regex_prefix_match(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, uint64_t base_len,
+                          const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n, uint8_t* out_match);
+
+/* ---- a2: ProcessorSplitMultilineLogStringNative::ProcessEvent (inner/...Multiline...cpp:127-393)
+ * One source value buf[0,len).  start/cont/end: compiled pattern or NULL (pattern string empty, :68-70).
+ * Output event k = (out_off[k], out_len[k], out_flags[k] = LC_ML_*) in reference emission order.
+ * counters[0..2] += matched_events, input_lines, unmatched_lines (:82-84,106-107). */
+int lc_multiline_split(lc_engine_t* e, const uint8_t* buf, uint64_t len, const lc_regex_t* start,
+                       const lc_regex_t* cont, const lc_regex_t* end, int discard_unmatched, uint32_t* out_off,
+                       uint32_t* out_len, uint8_t* out_flags, uint64_t cap, uint64_t* n_out, uint64_t counters[3]);
+int lc_multiline_split_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, const lc_regex_t* start,
+                           const lc_regex_t* cont, const lc_regex_t* end, int discard_unmatched, uint32_t* d_out_off,
+                           uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, uint64_t* n_out /* host */,
+                           uint64_t counters[3] /* host */);
+
+/* ---- a4: ProcessorParseDelimiterNative::ProcessEvent (ProcessorParseDelimiterNative.cpp:206-409)
+ *          + DelimiterModeFsmParser::ParseDelimiterLine (core/parser/DelimiterModeFsmParser.cpp:260-294)
+ * Per event: trim (:226-238), then the quote FSM (sep_len == 1 && quote != sep[0]) or the multi-char
+ * SplitString (:366-409).  status[i] as LC_DELIM_*; nfields[i] = parsed column count; rows of
+ * f_off/f_len/f_dq are [n][max_fields]: raw span of column j and, for the FSM path, the number of doubled
+ * quotes inside it (the un-escaped value has f_len - f_dq bytes; the host shim materialises it in the
+ * arena exactly as AddFieldWithUnQuote does, :83-113).  Columns beyond max_fields are counted, not stored. */
+int lc_delim_parse(lc_engine_t* e, const uint8_t* base, uint64_t base_len, const uint32_t* ev_off,
+                   const uint32_t* ev_len, uint64_t n, const uint8_t* sep, uint32_t sep_len, uint8_t quote,
+                   uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* status,
+                   uint32_t* nfields, uint32_t* f_off, uint32_t* f_len, uint32_t* f_dq);
+int lc_delim_parse_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len, const uint32_t* d_ev_off,
+                       const uint32_t* d_ev_len, uint64_t n, const uint8_t* sep, uint32_t sep_len, uint8_t quote,
+                       uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* d_status,
+                       uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len, uint32_t* d_f_dq);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LC_B200_H */

@@ -1,0 +1,636 @@
+// lc_capi.cu -- implementation of the C-ABI declared in include/lc_b200.h: engine (stream, grow-only
+// HBM workspace, look-back descriptors), host<->device staging, and the per-processor pipelines.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/lc_b200.h"
+#include "lc_kernels.cuh"
+#include "lc_tables.h"
+#include "regex_compiler.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                                  \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess)                                                                                         \
+            return fail(LC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                               \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256; // grow-only with slack
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess)
+            cap = want;
+        return e;
+    }
+    void release() {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+std::atomic<uint64_t> g_regex_ids{1};
+
+} // namespace
+
+struct lc_regex {
+    uint64_t id;
+    lcb200::CompileResult res;
+    std::string pattern;
+};
+
+struct lc_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    // staging / workspace (grow-only)
+    DevBuf in, ev_off, ev_len, out_a, out_b, out_c, out_d, out_e;
+    DevBuf lines_off, lines_len, flags, state, cnt, pos, lab_sizes, lab_off, lab;
+    DevBuf desc;   // look-back descriptors (3 regions)
+    DevBuf small;  // tickets + counters: [0..3] u32 tickets, +16: u32 n_out, +32: u64 total, +64: u64 counters[2]
+    void* h_small = nullptr; // pinned mirror of `small`
+    std::unordered_map<uint64_t, void*> blobs; // regex id -> device blob
+};
+
+namespace {
+
+cudaError_t engine_blob(lc_engine* e, const lc_regex* r, const void** out) {
+    *out = nullptr;
+    if (!r)
+        return cudaSuccess;
+    auto it = e->blobs.find(r->id);
+    if (it != e->blobs.end()) {
+        *out = it->second;
+        return cudaSuccess;
+    }
+    void* d = nullptr;
+    cudaError_t er = cudaMalloc(&d, r->res.blob.size());
+    if (er != cudaSuccess)
+        return er;
+    er = cudaMemcpyAsync(d, r->res.blob.data(), r->res.blob.size(), cudaMemcpyHostToDevice, e->stream);
+    if (er != cudaSuccess)
+        return er;
+    e->blobs[r->id] = d;
+    *out = d;
+    return cudaSuccess;
+}
+
+struct Small {
+    uint32_t tickets[4];
+    uint32_t n_out;
+    uint32_t pad0[3];
+    uint64_t total;
+    uint64_t pad1[3];
+    unsigned long long counters[2];
+};
+
+int bind(lc_engine* e) {
+    CU_TRY(cudaSetDevice(e->device));
+    return LC_OK;
+}
+
+// descriptor regions: [0] split tiles, [1] state tiles, [2] sum tiles
+struct DescPlan {
+    uint64_t* r[3];
+};
+
+int prep_desc(lc_engine* e, size_t n0, size_t n1, size_t n2, DescPlan& plan) {
+    size_t tot = n0 + n1 + n2 + 3;
+    CU_TRY(e->desc.ensure(tot * 8));
+    CU_TRY(cudaMemsetAsync(e->desc.p, 0, tot * 8, e->stream));
+    CU_TRY(cudaMemsetAsync(e->small.p, 0, sizeof(Small), e->stream));
+    plan.r[0] = e->desc.as<uint64_t>();
+    plan.r[1] = plan.r[0] + n0 + 1;
+    plan.r[2] = plan.r[1] + n1 + 1;
+    return LC_OK;
+}
+
+int check_regex_usable(const lc_regex* r, const char* what) {
+    if (!r->res.supported)
+        return fail(r->res.valid ? LC_ERR_REGEX_UNSUPPORTED : LC_ERR_REGEX_INVALID,
+                    std::string(what) + ": " + r->res.error);
+    return LC_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* lc_version(void) { return "loongcollector_b200 0.1.0 (sm_100a)"; }
+const char* lc_last_error(void) { return g_err.c_str(); }
+
+int lc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int lc_engine_create(int device, lc_engine_t** out) {
+    if (!out)
+        return fail(LC_ERR_INVALID_ARG, "lc_engine_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t er = cudaGetDeviceCount(&n);
+    if (er != cudaSuccess || n == 0)
+        return fail(LC_ERR_CUDA, std::string("lc_engine_create: no usable CUDA device (") +
+                                     (er != cudaSuccess ? cudaGetErrorString(er) : "device count 0") +
+                                     "); this engine has no CPU fallback");
+    if (device < 0 || device >= n)
+        return fail(LC_ERR_INVALID_ARG, "lc_engine_create: bad device index");
+    lc_engine* e = new (std::nothrow) lc_engine;
+    if (!e)
+        return fail(LC_ERR_CUDA, "out of host memory");
+    e->device = device;
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU_TRY(e->small.ensure(sizeof(Small)));
+    CU_TRY(cudaMallocHost(&e->h_small, sizeof(Small)));
+    *out = e;
+    return LC_OK;
+}
+
+void lc_engine_destroy(lc_engine_t* e) {
+    if (!e)
+        return;
+    cudaSetDevice(e->device);
+    if (e->stream)
+        cudaStreamSynchronize(e->stream);
+    DevBuf* bufs[] = {&e->in, &e->ev_off, &e->ev_len, &e->out_a, &e->out_b, &e->out_c, &e->out_d, &e->out_e,
+                      &e->lines_off, &e->lines_len, &e->flags, &e->state, &e->cnt, &e->pos, &e->lab_sizes,
+                      &e->lab_off, &e->lab, &e->desc, &e->small};
+    for (DevBuf* b : bufs)
+        b->release();
+    for (auto& kv : e->blobs)
+        cudaFree(kv.second);
+    if (e->h_small)
+        cudaFreeHost(e->h_small);
+    if (e->stream)
+        cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int lc_engine_sync(lc_engine_t* e) {
+    if (!e)
+        return fail(LC_ERR_INVALID_ARG, "engine is NULL");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return LC_OK;
+}
+
+void* lc_engine_stream(lc_engine_t* e) { return e ? (void*)e->stream : nullptr; }
+uint64_t lc_engine_launch_count(const lc_engine_t* e) { return e ? e->launches : 0; }
+
+void* lc_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        g_err = "lc_host_alloc: cudaMallocHost failed";
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void lc_host_free(void* p) {
+    if (p)
+        cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------------ regex
+int lc_regex_compile(const char* pattern, size_t len, lc_regex_t** out) {
+    if (!out || (!pattern && len))
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_compile: bad arguments");
+    lc_regex* r = new (std::nothrow) lc_regex;
+    if (!r)
+        return fail(LC_ERR_CUDA, "out of host memory");
+    r->id = g_regex_ids.fetch_add(1);
+    r->pattern.assign(pattern ? pattern : "", len);
+    r->res = lcb200::compile_regex(r->pattern.data(), r->pattern.size());
+    *out = r;
+    if (!r->res.valid)
+        return fail(LC_ERR_REGEX_INVALID, r->res.error);
+    if (!r->res.supported)
+        return fail(LC_ERR_REGEX_UNSUPPORTED, r->res.error);
+    return LC_OK;
+}
+
+void lc_regex_free(lc_regex_t* r) { delete r; }
+const char* lc_regex_error(const lc_regex_t* r) { return r ? r->res.error.c_str() : ""; }
+uint32_t lc_regex_ngroups(const lc_regex_t* r) { return r ? r->res.ngroups : 0; }
+
+void lc_regex_info(const lc_regex_t* r, uint32_t info[8]) {
+    memset(info, 0, 8 * sizeof(uint32_t));
+    if (!r || !r->res.supported)
+        return;
+    const LcRegexHeader* h = reinterpret_cast<const LcRegexHeader*>(r->res.blob.data());
+    info[0] = h->mode;
+    info[1] = h->nclasses;
+    info[2] = h->nw;
+    info[3] = h->npc;
+    info[4] = h->rev_nstates;
+    info[5] = h->pre_nstates;
+    info[6] = h->total_bytes;
+    info[7] = r->res.n_insts;
+}
+
+// ------------------------------------------------------------------------------------------------ split
+int lc_split_lines_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, uint8_t split_char, uint32_t* d_out_off,
+                       uint32_t* d_out_len, uint64_t cap, uint64_t* n_out) {
+    if (!e || !n_out || (len && !d_buf))
+        return fail(LC_ERR_INVALID_ARG, "lc_split_lines_dev: bad arguments");
+    *n_out = 0;
+    if (len == 0)
+        return LC_OK;
+    if (len >= 0xFFFFFFF0ull)
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB per call");
+    int rc = bind(e);
+    if (rc)
+        return rc;
+    uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
+    DescPlan plan;
+    rc = prep_desc(e, lck::split_tiles(len, shift), 0, 0, plan);
+    if (rc)
+        return rc;
+    Small* ds = e->small.as<Small>();
+    uint32_t cap32 = cap > 0x3FFFFFFFull ? 0x3FFFFFFFu : (uint32_t)cap;
+    lck::launch_split(d_buf, (uint32_t)len, split_char, d_out_off, d_out_len, cap32, plan.r[0], &ds->tickets[0],
+                      &ds->n_out, e->stream);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    Small* hs = (Small*)e->h_small;
+    CU_TRY(cudaMemcpyAsync(&hs->n_out, &ds->n_out, 4, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    *n_out = hs->n_out;
+    if (*n_out > cap)
+        return fail(LC_ERR_CAPACITY, "lc_split_lines: output capacity too small");
+    return LC_OK;
+}
+
+int lc_split_lines(lc_engine_t* e, const uint8_t* buf, uint64_t len, uint8_t split_char, uint32_t* out_off,
+                   uint32_t* out_len, uint64_t cap, uint64_t* n_out) {
+    if (!e || !n_out || (len && !buf))
+        return fail(LC_ERR_INVALID_ARG, "lc_split_lines: bad arguments");
+    *n_out = 0;
+    if (len == 0)
+        return LC_OK;
+    if (len >= 0xFFFFFFF0ull)
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB per call");
+    int rc = bind(e);
+    if (rc)
+        return rc;
+    uint64_t dcap = cap < len ? cap : len;
+    CU_TRY(e->in.ensure(len + 16));
+    CU_TRY(e->out_a.ensure((dcap + 1) * 4));
+    CU_TRY(e->out_b.ensure((dcap + 1) * 4));
+    CU_TRY(cudaMemcpyAsync(e->in.p, buf, len, cudaMemcpyHostToDevice, e->stream));
+    rc = lc_split_lines_dev(e, e->in.as<uint8_t>(), len, split_char, e->out_a.as<uint32_t>(),
+                            e->out_b.as<uint32_t>(), dcap, n_out);
+    if (rc)
+        return rc;
+    if (*n_out) {
+        CU_TRY(cudaMemcpyAsync(out_off, e->out_a.p, *n_out * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaMemcpyAsync(out_len, e->out_b.p, *n_out * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return LC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ regex parse
+int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
+                       const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                       uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len) {
+    if (!e || !re)
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_dev: bad arguments");
+    int rc = check_regex_usable(re, "lc_regex_parse");
+    if (rc)
+        return rc;
+    if (n == 0)
+        return LC_OK;
+    if (base_len >= 0xFFFFFFF0ull || n >= (1ull << 30))
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB and < 2^30 events per call");
+    rc = bind(e);
+    if (rc)
+        return rc;
+    const void* d_blob;
+    CU_TRY(engine_blob(e, re, &d_blob));
+    const LcRegexHeader* h = reinterpret_cast<const LcRegexHeader*>(re->res.blob.data());
+    const uint64_t* d_lab_off = nullptr;
+    uint16_t* d_lab = nullptr;
+    if (h->mode == LC_MODE_TWOPASS) {
+        // label scratch: (len + 1) u16 labels per event, placed by an exclusive sum
+        DescPlan plan;
+        rc = prep_desc(e, 0, 0, lck::scan_tiles(n), plan);
+        if (rc)
+            return rc;
+        CU_TRY(e->lab_sizes.ensure(n * 4));
+        CU_TRY(e->lab_off.ensure(n * 8));
+        Small* ds = e->small.as<Small>();
+        lck::launch_label_sizes(d_ev_len, n, e->lab_sizes.as<uint32_t>(), e->stream);
+        lck::launch_exclusive_sum(e->lab_sizes.as<uint32_t>(), n, e->lab_off.as<uint64_t>(), &ds->total, plan.r[2],
+                                  &ds->tickets[2], e->stream);
+        e->launches += 2;
+        CU_TRY(cudaGetLastError());
+        // upper bound without a sync: every event needs at most len+8 labels and events may overlap, so the
+        // exact total is read back (one 8-byte D2H)
+        Small* hs = (Small*)e->h_small;
+        CU_TRY(cudaMemcpyAsync(&hs->total, &ds->total, 8, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        CU_TRY(e->lab.ensure(hs->total * 2 + 16));
+        d_lab_off = e->lab_off.as<uint64_t>();
+        d_lab = e->lab.as<uint16_t>();
+    }
+    lck::launch_regex_parse_basic(d_blob, h->mode, h->ngroups, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
+                                  d_cap_off, d_cap_len, d_lab_off, d_lab, e->stream);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    return LC_OK;
+}
+
+int lc_regex_parse(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, uint64_t base_len,
+                   const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n, uint32_t nkeys, uint8_t* status,
+                   uint32_t* cap_off, uint32_t* cap_len) {
+    if (!e || !re || (n && (!ev_off || !ev_len || !status)) || (base_len && !base))
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_parse: bad arguments");
+    int rc = check_regex_usable(re, "lc_regex_parse");
+    if (rc)
+        return rc;
+    if (n == 0)
+        return LC_OK;
+    rc = bind(e);
+    if (rc)
+        return rc;
+    const uint32_t G = re->res.ngroups;
+    CU_TRY(e->in.ensure(base_len + 16));
+    CU_TRY(e->ev_off.ensure(n * 4));
+    CU_TRY(e->ev_len.ensure(n * 4));
+    CU_TRY(e->out_a.ensure(n));
+    CU_TRY(e->out_b.ensure(n * G * 4 + 4));
+    CU_TRY(e->out_c.ensure(n * G * 4 + 4));
+    CU_TRY(cudaMemcpyAsync(e->in.p, base, base_len, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->ev_off.p, ev_off, n * 4, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->ev_len.p, ev_len, n * 4, cudaMemcpyHostToDevice, e->stream));
+    rc = lc_regex_parse_dev(e, re, e->in.as<uint8_t>(), base_len, e->ev_off.as<uint32_t>(),
+                            e->ev_len.as<uint32_t>(), n, nkeys, e->out_a.as<uint8_t>(), e->out_b.as<uint32_t>(),
+                            e->out_c.as<uint32_t>());
+    if (rc)
+        return rc;
+    CU_TRY(cudaMemcpyAsync(status, e->out_a.p, n, cudaMemcpyDeviceToHost, e->stream));
+    if (G) {
+        CU_TRY(cudaMemcpyAsync(cap_off, e->out_b.p, n * G * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaMemcpyAsync(cap_len, e->out_c.p, n * G * 4, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return LC_OK;
+}
+
+int lc_regex_prefix_match(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, uint64_t base_len,
+                          const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n, uint8_t* out_match) {
+    if (!e || !re || (n && (!ev_off || !ev_len || !out_match)) || (base_len && !base))
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_prefix_match: bad arguments");
+    int rc = check_regex_usable(re, "lc_regex_prefix_match");
+    if (rc)
+        return rc;
+    if (n == 0)
+        return LC_OK;
+    rc = bind(e);
+    if (rc)
+        return rc;
+    const void* d_blob;
+    CU_TRY(engine_blob(e, re, &d_blob));
+    CU_TRY(e->in.ensure(base_len + 16));
+    CU_TRY(e->ev_off.ensure(n * 4));
+    CU_TRY(e->ev_len.ensure(n * 4));
+    CU_TRY(e->out_a.ensure(n));
+    CU_TRY(cudaMemcpyAsync(e->in.p, base, base_len, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->ev_off.p, ev_off, n * 4, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->ev_len.p, ev_len, n * 4, cudaMemcpyHostToDevice, e->stream));
+    lck::launch_prefix_match(d_blob, e->in.as<uint8_t>(), e->ev_off.as<uint32_t>(), e->ev_len.as<uint32_t>(), n,
+                             e->out_a.as<uint8_t>(), e->stream);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out_match, e->out_a.p, n, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return LC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multiline
+int lc_multiline_split_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, const lc_regex_t* start,
+                           const lc_regex_t* cont, const lc_regex_t* end, int discard_unmatched, uint32_t* d_out_off,
+                           uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, uint64_t* n_out,
+                           uint64_t counters[3]) {
+    if (!e || !n_out || (len && !d_buf))
+        return fail(LC_ERR_INVALID_ARG, "lc_multiline_split_dev: bad arguments");
+    *n_out = 0;
+    int rc;
+    for (const lc_regex_t* r : {start, cont, end})
+        if (r && (rc = check_regex_usable(r, "lc_multiline_split")))
+            return rc;
+    if (len == 0)
+        return LC_OK;
+    if (len >= 0xFFFFFFF0ull)
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB per call");
+    rc = bind(e);
+    if (rc)
+        return rc;
+    lck::MlConfig cfg;
+    CU_TRY(engine_blob(e, start, &cfg.blob_start));
+    CU_TRY(engine_blob(e, cont, &cfg.blob_cont));
+    CU_TRY(engine_blob(e, end, &cfg.blob_end));
+    cfg.discard = discard_unmatched;
+
+    Small* ds = e->small.as<Small>();
+    Small* hs = (Small*)e->h_small;
+    // 1. line table (grow the workspace until it fits; typical logs fit the first estimate)
+    uint64_t lcap = len / 24 + 4096;
+    uint64_t n = 0;
+    uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
+    for (;;) {
+        if (lcap > len)
+            lcap = len;
+        CU_TRY(e->lines_off.ensure((lcap + 1) * 4));
+        CU_TRY(e->lines_len.ensure((lcap + 1) * 4));
+        DescPlan plan;
+        rc = prep_desc(e, lck::split_tiles(len, shift), 0, 0, plan);
+        if (rc)
+            return rc;
+        lck::launch_split(d_buf, (uint32_t)len, '\n', e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(),
+                          (uint32_t)(lcap > 0x3FFFFFFFull ? 0x3FFFFFFFull : lcap), plan.r[0], &ds->tickets[0],
+                          &ds->n_out, e->stream);
+        e->launches++;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(&hs->n_out, &ds->n_out, 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        n = hs->n_out;
+        if (n <= lcap)
+            break;
+        lcap = n;
+    }
+    if (n >= (1ull << 30) - 2)
+        return fail(LC_ERR_TOO_LARGE, "more than 2^30 lines in one call");
+    // 2. per-line prefix probes
+    CU_TRY(e->flags.ensure(n + 1));
+    lck::launch_ml_probe(cfg, d_buf, e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(), n,
+                         e->flags.as<uint8_t>(), e->stream);
+    // 3. state scan + event counts, 4. output slots
+    DescPlan plan;
+    rc = prep_desc(e, 0, lck::scan_tiles(n + 1), lck::scan_tiles(n + 1), plan);
+    if (rc)
+        return rc;
+    CU_TRY(e->state.ensure((n + 1) * 4));
+    CU_TRY(e->cnt.ensure((n + 1) * 4));
+    CU_TRY(e->pos.ensure((n + 1) * 8));
+    lck::launch_ml_state(cfg, e->flags.as<uint8_t>(), n, e->state.as<uint32_t>(), e->cnt.as<uint32_t>(), plan.r[1],
+                         &ds->tickets[1], e->stream);
+    lck::launch_exclusive_sum(e->cnt.as<uint32_t>(), n + 1, e->pos.as<uint64_t>(), &ds->total, plan.r[2],
+                              &ds->tickets[2], e->stream);
+    // 5. emission
+    lck::launch_ml_emit(cfg, e->flags.as<uint8_t>(), e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(), n,
+                        (uint32_t)len, e->state.as<uint32_t>(), e->pos.as<uint64_t>(), d_out_off, d_out_len,
+                        d_out_flags, cap, ds->counters, e->stream);
+    e->launches += 4;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    *n_out = hs->total;
+    if (counters) {
+        counters[0] += hs->counters[0];
+        counters[1] += n;
+        counters[2] += hs->counters[1];
+    }
+    if (*n_out > cap)
+        return fail(LC_ERR_CAPACITY, "lc_multiline_split: output capacity too small");
+    return LC_OK;
+}
+
+int lc_multiline_split(lc_engine_t* e, const uint8_t* buf, uint64_t len, const lc_regex_t* start,
+                       const lc_regex_t* cont, const lc_regex_t* end, int discard_unmatched, uint32_t* out_off,
+                       uint32_t* out_len, uint8_t* out_flags, uint64_t cap, uint64_t* n_out, uint64_t counters[3]) {
+    if (!e || !n_out || (len && !buf))
+        return fail(LC_ERR_INVALID_ARG, "lc_multiline_split: bad arguments");
+    *n_out = 0;
+    if (len == 0)
+        return LC_OK;
+    if (len >= 0xFFFFFFF0ull)
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB per call");
+    int rc = bind(e);
+    if (rc)
+        return rc;
+    uint64_t dcap = cap < len ? cap : len; // an output event covers at least one input byte or one line
+    CU_TRY(e->in.ensure(len + 16));
+    CU_TRY(e->out_a.ensure((dcap + 1) * 4));
+    CU_TRY(e->out_b.ensure((dcap + 1) * 4));
+    CU_TRY(e->out_c.ensure(dcap + 1));
+    CU_TRY(cudaMemcpyAsync(e->in.p, buf, len, cudaMemcpyHostToDevice, e->stream));
+    rc = lc_multiline_split_dev(e, e->in.as<uint8_t>(), len, start, cont, end, discard_unmatched,
+                                e->out_a.as<uint32_t>(), e->out_b.as<uint32_t>(), e->out_c.as<uint8_t>(), dcap, n_out,
+                                counters);
+    if (rc)
+        return rc;
+    if (*n_out) {
+        CU_TRY(cudaMemcpyAsync(out_off, e->out_a.p, *n_out * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaMemcpyAsync(out_len, e->out_b.p, *n_out * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaMemcpyAsync(out_flags, e->out_c.p, *n_out, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return LC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ delimiter
+int lc_delim_parse_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len, const uint32_t* d_ev_off,
+                       const uint32_t* d_ev_len, uint64_t n, const uint8_t* sep, uint32_t sep_len, uint8_t quote,
+                       uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* d_status,
+                       uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len, uint32_t* d_f_dq) {
+    if (!e || !sep || sep_len < 1 || sep_len > 4 || max_fields == 0)
+        return fail(LC_ERR_INVALID_ARG, "lc_delim_parse_dev: bad arguments (separator must be 1..4 bytes)");
+    if (n == 0)
+        return LC_OK;
+    if (base_len >= 0xFFFFFFF0ull)
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB per call");
+    int rc = bind(e);
+    if (rc)
+        return rc;
+    lck::DelimConfig cfg;
+    memset(&cfg, 0, sizeof cfg);
+    memcpy(cfg.sep, sep, sep_len);
+    cfg.sep_len = sep_len;
+    cfg.quote = quote;
+    cfg.nkeys = nkeys;
+    cfg.extend = extend;
+    cfg.allow_short = allow_short;
+    cfg.max_fields = max_fields;
+    lck::launch_delim(cfg, d_base, d_ev_off, d_ev_len, n, d_status, d_nfields, d_f_off, d_f_len, d_f_dq, e->stream);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    return LC_OK;
+}
+
+int lc_delim_parse(lc_engine_t* e, const uint8_t* base, uint64_t base_len, const uint32_t* ev_off,
+                   const uint32_t* ev_len, uint64_t n, const uint8_t* sep, uint32_t sep_len, uint8_t quote,
+                   uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* status,
+                   uint32_t* nfields, uint32_t* f_off, uint32_t* f_len, uint32_t* f_dq) {
+    if (!e || (n && (!ev_off || !ev_len || !status || !nfields || !f_off || !f_len || !f_dq)) || (base_len && !base))
+        return fail(LC_ERR_INVALID_ARG, "lc_delim_parse: bad arguments");
+    if (n == 0)
+        return LC_OK;
+    int rc = bind(e);
+    if (rc)
+        return rc;
+    size_t fbytes = (size_t)n * max_fields * 4;
+    CU_TRY(e->in.ensure(base_len + 16));
+    CU_TRY(e->ev_off.ensure(n * 4));
+    CU_TRY(e->ev_len.ensure(n * 4));
+    CU_TRY(e->out_a.ensure(n));
+    CU_TRY(e->out_b.ensure(n * 4));
+    CU_TRY(e->out_c.ensure(fbytes));
+    CU_TRY(e->out_d.ensure(fbytes));
+    CU_TRY(e->out_e.ensure(fbytes));
+    CU_TRY(cudaMemcpyAsync(e->in.p, base, base_len, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->ev_off.p, ev_off, n * 4, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->ev_len.p, ev_len, n * 4, cudaMemcpyHostToDevice, e->stream));
+    rc = lc_delim_parse_dev(e, e->in.as<uint8_t>(), base_len, e->ev_off.as<uint32_t>(), e->ev_len.as<uint32_t>(), n,
+                            sep, sep_len, quote, nkeys, extend, allow_short, max_fields, e->out_a.as<uint8_t>(),
+                            e->out_b.as<uint32_t>(), e->out_c.as<uint32_t>(), e->out_d.as<uint32_t>(),
+                            e->out_e.as<uint32_t>());
+    if (rc)
+        return rc;
+    CU_TRY(cudaMemcpyAsync(status, e->out_a.p, n, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(nfields, e->out_b.p, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(f_off, e->out_c.p, fbytes, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(f_len, e->out_d.p, fbytes, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(f_dq, e->out_e.p, fbytes, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return LC_OK;
+}
+
+} // extern "C"

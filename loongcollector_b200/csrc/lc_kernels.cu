@@ -1,0 +1,743 @@
+// lc_kernels.cu -- sm_100a kernels of the log-parsing engine.
+//
+// All work is HBM-bound byte / integer indexing (no tensor cores): the split kernel streams the
+// SourceBuffer bytes once with 16-byte coalesced loads and ranks every line with a single-pass
+// decoupled look-back scan; the regex kernels interpret the automaton tables produced by
+// regex_compiler.cpp once per log line; the multiline splitter turns the reference's sequential
+// start/continue/end state machine into a prefix scan over 2-state transition functions.
+//
+// Reference behaviour reproduced (paths relative to the reference checkout):
+//   split      core/plugin/processor/inner/ProcessorSplitLogStringNative.cpp:127-174
+//   multiline  core/plugin/processor/inner/ProcessorSplitMultilineLogStringNative.cpp:162-393
+//   regex      core/plugin/processor/ProcessorParseRegexNative.cpp:186-253, core/common/StringTools.cpp:183-288
+//   delimiter  core/plugin/processor/ProcessorParseDelimiterNative.cpp:219-409, core/parser/DelimiterModeFsmParser.cpp:49-294
+#include "lc_kernels.cuh"
+
+#include "lc_exec.cuh"
+#include "lc_scan.cuh"
+
+namespace lck {
+
+using namespace lcscan;
+
+// ================================================================================================ split
+// 16 input bytes -> 16-bit mask of bytes equal to the (replicated) split char
+__device__ __forceinline__ uint32_t match16(uint4 v, uint32_t splat) {
+    uint32_t m = 0;
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t eq = __vcmpeq4(w[k], splat) & 0x01010101u; // bit 0 of each equal byte
+        m |= (((eq * 0x01020408u) >> 24) & 0xFu) << (4 * k);
+    }
+    return m;
+}
+
+template <int THREADS, int ROWS>
+__global__ void __launch_bounds__(THREADS)
+    split_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
+                 uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap, volatile uint64_t* desc,
+                 uint32_t* ticket, uint32_t ntiles, uint32_t* n_out) {
+    __shared__ uint64_t s_scan[THREADS / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_prefix;
+    const int tid = threadIdx.x;
+    if (tid == 0)
+        s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint4* vbuf = reinterpret_cast<const uint4*>(buf - shift);
+    const uint64_t total_v = (uint64_t)len + shift; // virtual length including the alignment lead-in
+    const uint64_t chunk0 = (uint64_t)tile * THREADS * ROWS;
+
+    uint32_t mask[ROWS];
+    uint64_t pay[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        uint64_t chunk = chunk0 + (uint64_t)r * THREADS + tid;
+        uint64_t vpos = chunk * 16;
+        uint32_t m = 0;
+        if (vpos < total_v) {
+            uint4 v = __ldg(vbuf + chunk);
+            m = match16(v, splat);
+            if (vpos == 0 && shift) // alignment lead-in bytes in front of the buffer (shift < 16)
+                m &= ~((1u << shift) - 1u);
+            uint64_t rem = total_v - vpos;
+            if (rem < 16)
+                m &= (1u << rem) - 1u;
+        }
+        mask[r] = m;
+        uint32_t last = m ? (uint32_t)(vpos + (31 - __clz(m)) + 1 - shift) : 0u;
+        pay[r] = OpCountMax::make(__popc(m), last);
+    }
+
+    uint64_t excl[ROWS], rowpre[ROWS];
+    uint64_t carry = OpCountMax::identity();
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        uint64_t tot;
+        excl[r] = block_exclusive_scan<OpCountMax, THREADS>(pay[r], tot, s_scan);
+        rowpre[r] = carry;
+        carry = OpCountMax::combine(carry, tot);
+    }
+    if (tid < 32) {
+        uint64_t p = lookback<OpCountMax>(desc, tile, carry);
+        if (tid == 0)
+            s_prefix = p;
+    }
+    __syncthreads();
+    const uint64_t tile_prefix = s_prefix;
+
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        uint64_t pre = OpCountMax::combine(tile_prefix, OpCountMax::combine(rowpre[r], excl[r]));
+        uint32_t k = OpCountMax::count(pre);
+        uint32_t start = OpCountMax::maxv(pre);
+        uint32_t m = mask[r];
+        uint64_t vpos = (chunk0 + (uint64_t)r * THREADS + tid) * 16;
+        while (m) {
+            int b = __ffs(m) - 1;
+            m &= m - 1;
+            uint32_t p = (uint32_t)(vpos + b - shift);
+            if (k < cap) {
+                out_off[k] = start;
+                out_len[k] = p - start;
+            }
+            ++k;
+            start = p + 1;
+        }
+        if (tile == ntiles - 1 && r == ROWS - 1 && tid == THREADS - 1) {
+            // inclusive total of the whole buffer: the unterminated last piece, if any
+            if (start < len) {
+                if (k < cap) {
+                    out_off[k] = start;
+                    out_len[k] = len - start;
+                }
+                ++k;
+            }
+            *n_out = k;
+        }
+    }
+}
+
+void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
+                  uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out, cudaStream_t st) {
+    uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
+    uint32_t ntiles = split_tiles(len, shift);
+    uint32_t splat = split_char * 0x01010101u;
+    split_kernel<kSplitThreads, kSplitRows><<<ntiles, kSplitThreads, 0, st>>>(
+        d_buf, len, shift, splat, d_off, d_len, cap, (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out);
+}
+
+// ================================================================================================ sums
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+    exclusive_sum_kernel(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ out, uint64_t* total,
+                         volatile uint64_t* desc, uint32_t* ticket, uint32_t ntiles) {
+    __shared__ uint64_t s_scan[THREADS / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_prefix;
+    const int tid = threadIdx.x;
+    if (tid == 0)
+        s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t base = (uint64_t)tile * THREADS * ITEMS + (uint64_t)tid * ITEMS;
+    uint32_t v[ITEMS];
+    uint64_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        sum += v[k];
+    }
+    uint64_t tot;
+    uint64_t ex = block_exclusive_scan<OpSum, THREADS>(sum, tot, s_scan);
+    if (tid < 32) {
+        uint64_t p = lookback<OpSum>(desc, tile, tot);
+        if (tid == 0)
+            s_prefix = p;
+    }
+    __syncthreads();
+    uint64_t run = s_prefix + ex;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (base + k < n)
+            out[base + k] = run;
+        run += v[k];
+    }
+    if (tile == ntiles - 1 && tid == THREADS - 1)
+        *total = run;
+}
+
+void launch_exclusive_sum(const uint32_t* d_in, uint64_t n, uint64_t* d_out, uint64_t* d_total, uint64_t* d_desc,
+                          uint32_t* d_ticket, cudaStream_t st) {
+    uint32_t ntiles = scan_tiles(n);
+    if (ntiles == 0)
+        return;
+    exclusive_sum_kernel<kScanThreads, kScanItems>
+        <<<ntiles, kScanThreads, 0, st>>>(d_in, n, d_out, d_total, (volatile uint64_t*)d_desc, d_ticket, ntiles);
+}
+
+// ================================================================================================ regex (baseline)
+__global__ void label_sizes_kernel(const uint32_t* __restrict__ ev_len, uint64_t n, uint32_t* __restrict__ sizes) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        sizes[i] = (ev_len[i] + 1 + 7) & ~7u;
+}
+void launch_label_sizes(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_sizes, cudaStream_t st) {
+    if (!n)
+        return;
+    label_sizes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ev_len, n, d_sizes);
+}
+
+// One thread per event; tables read through the read-only path from global memory.
+__global__ void __launch_bounds__(128)
+    regex_parse_basic_kernel(const void* __restrict__ blob, uint32_t mode, uint32_t G, const uint8_t* __restrict__ base,
+                             const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
+                             uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
+                             uint32_t* __restrict__ cap_len, const uint64_t* __restrict__ lab_off,
+                             uint16_t* __restrict__ lab) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    LcProgView v = lc_view(blob);
+    const uint32_t off = ev_off[i], len = ev_len[i];
+    const uint8_t* s = base + off;
+    uint32_t slots[2 * LC_MAX_GROUPS];
+    for (uint32_t k = 0; k < 2 * G; ++k)
+        slots[k] = LC_SLOT_UNSET;
+    bool ok;
+    if (mode == LC_MODE_FWD1) {
+        ok = lc_full_match_fwd1(v, s, len, slots);
+    } else {
+        uint16_t* my = lab + lab_off[i];
+        ok = lc_rev_label(v, s, len, my) && lc_fwd_walk(v, s, len, my, slots);
+    }
+    uint8_t st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
+    status[i] = st;
+    uint32_t* co = cap_off + i * G;
+    uint32_t* cl = cap_len + i * G;
+    for (uint32_t g = 0; g < G; ++g) {
+        uint32_t o = 0, l = 0;
+        if (st == 0) {
+            lc_slots_to_cap(slots, g, len, &o, &l);
+            o += off;
+        }
+        co[g] = o;
+        cl[g] = l;
+    }
+}
+
+void launch_regex_parse_basic(const void* d_blob, uint32_t mode, uint32_t ngroups, const uint8_t* d_base,
+                              const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                              uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, const uint64_t* d_lab_off,
+                              uint16_t* d_lab, cudaStream_t st) {
+    if (!n)
+        return;
+    regex_parse_basic_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(
+        d_blob, mode, ngroups, d_base, d_ev_off, d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len, d_lab_off, d_lab);
+}
+
+__global__ void __launch_bounds__(128)
+    prefix_match_kernel(const void* __restrict__ blob, const uint8_t* __restrict__ base,
+                        const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
+                        uint8_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    LcProgView v = lc_view(blob);
+    out[i] = lc_prefix_match(v, base + ev_off[i], ev_len[i]) ? 1 : 0;
+}
+
+void launch_prefix_match(const void* d_blob, const uint8_t* d_base, const uint32_t* d_ev_off,
+                         const uint32_t* d_ev_len, uint64_t n, uint8_t* d_out, cudaStream_t st) {
+    if (!n)
+        return;
+    prefix_match_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_blob, d_base, d_ev_off, d_ev_len, n, d_out);
+}
+
+// ================================================================================================ multiline
+__global__ void __launch_bounds__(128)
+    ml_probe_kernel(const void* __restrict__ bs, const void* __restrict__ bc, const void* __restrict__ be,
+                    const uint8_t* __restrict__ buf, const uint32_t* __restrict__ off, const uint32_t* __restrict__ len,
+                    uint64_t n, uint8_t* __restrict__ flags) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const uint8_t* s = buf + off[i];
+    uint32_t l = len[i];
+    uint8_t f = 0;
+    if (bs && lc_prefix_match(lc_view(bs), s, l))
+        f |= 1;
+    if (bc && lc_prefix_match(lc_view(bc), s, l))
+        f |= 2;
+    if (be && lc_prefix_match(lc_view(be), s, l))
+        f |= 4;
+    flags[i] = f;
+}
+
+void launch_ml_probe(const MlConfig& cfg, const uint8_t* d_buf, const uint32_t* d_off, const uint32_t* d_len,
+                     uint64_t n, uint8_t* d_flags, cudaStream_t st) {
+    if (!n)
+        return;
+    ml_probe_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cfg.blob_start, cfg.blob_cont, cfg.blob_end, d_buf,
+                                                                  d_off, d_len, n, d_flags);
+}
+
+struct MlMode {
+    bool S, C, E, discard;
+};
+
+// Transition of line `fl` from state s_in (0 not partial / 1 partial):
+// s_out and which line (0 none, 1 this line, 2 the next line) becomes multiStartIndex.
+// Restates ProcessorSplitMultilineLogStringNative.cpp:175-283 without the emission side effects.
+__device__ __forceinline__ void ml_trans(const MlMode& m, uint32_t fl, uint32_t s_in, uint32_t& s_out,
+                                         uint32_t& begin) {
+    const bool mS = fl & 1, mC = fl & 2, mE = fl & 4;
+    begin = 0;
+    if (!s_in) {
+        bool probe = m.S ? mS : (m.C ? mC : false);
+        if (probe) {
+            s_out = 1;
+            begin = 1;
+        } else {
+            s_out = 0;
+        }
+        return;
+    }
+    if (m.C && mC) {
+        s_out = 1;
+        return;
+    }
+    if (m.E) {
+        if (m.C) {
+            s_out = 0;
+        } else if (mE) {
+            if (m.S) {
+                s_out = 0;
+            } else {
+                s_out = 1;
+                begin = 2;
+            }
+        } else {
+            s_out = 1;
+        }
+        return;
+    }
+    if (!m.C) {
+        s_out = 1;
+        if (mS)
+            begin = 1;
+    } else {
+        if (mS) {
+            s_out = 1;
+            begin = 1;
+        } else {
+            s_out = 0;
+        }
+    }
+}
+
+// Events produced by line j (or by the virtual end-of-buffer element j == n).  Sink methods:
+//   single(j, matched)          the line itself                       (CreateNewEvent / HandleUnmatchLogs on one line)
+//   to_end(lb, j)               [start of line lb, end of line j]     matched record
+//   to_prev(lb, j)              [start of line lb, start of line j - 1) matched record
+//   span(lb, j_last, flag_line) unmatched lines lb..j_last, each carrying flag_line's isLast flag
+//   to_eof(lb)                  [start of line lb, end of buffer)     matched record, isLast = true
+template <class Sink>
+__device__ __forceinline__ void ml_actions(const MlMode& m, uint32_t fl, uint32_t s_in, uint32_t lb, uint32_t j,
+                                           uint32_t n, Sink& sink) {
+    if (j == n) { // :289-308
+        if (s_in && lb < n) {
+            if (!m.E)
+                sink.to_eof(lb);
+            else
+                sink.span(lb, n - 1, n);
+        }
+        return;
+    }
+    const bool mS = fl & 1, mC = fl & 2, mE = fl & 4;
+    if (!s_in) {
+        bool probe = m.S ? mS : (m.C ? mC : false);
+        if (probe)
+            return;
+        if (m.E && !m.S && m.C && mE)
+            sink.single(j, true);
+        else
+            sink.single(j, false);
+        return;
+    }
+    if (m.C && mC)
+        return;
+    if (m.E) {
+        if (m.C) {
+            if (mE)
+                sink.to_end(lb, j);
+            else
+                sink.span(lb, j, j);
+        } else if (mE) {
+            sink.to_end(lb, j);
+        }
+        return;
+    }
+    if (!m.C) {
+        if (mS)
+            sink.to_prev(lb, j);
+    } else {
+        sink.to_prev(lb, j);
+        if (!mS)
+            sink.single(j, false);
+    }
+}
+
+struct MlCountSink {
+    bool discard;
+    uint32_t cnt = 0;
+    __device__ void single(uint32_t, bool matched) { cnt += (matched || !discard) ? 1 : 0; }
+    __device__ void to_end(uint32_t, uint32_t) { cnt += 1; }
+    __device__ void to_prev(uint32_t, uint32_t) { cnt += 1; }
+    __device__ void to_eof(uint32_t) { cnt += 1; }
+    __device__ void span(uint32_t lb, uint32_t jl, uint32_t) { cnt += discard ? 0 : (jl - lb + 1); }
+};
+
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+    ml_state_kernel(MlMode m, const uint8_t* __restrict__ flags, uint64_t n, uint32_t* __restrict__ state,
+                    uint32_t* __restrict__ cnt, volatile uint64_t* desc, uint32_t* ticket) {
+    __shared__ uint64_t s_scan[THREADS / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_prefix;
+    const int tid = threadIdx.x;
+    if (tid == 0)
+        s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t base = (uint64_t)tile * THREADS * ITEMS + (uint64_t)tid * ITEMS;
+    // elements 0..n-1 are lines, element n is the virtual end-of-buffer (identity transition)
+    uint64_t el[ITEMS];
+    uint32_t fl[ITEMS];
+    uint64_t agg = OpMlState::identity();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        uint64_t j = base + k;
+        uint64_t e = OpMlState::identity();
+        fl[k] = 0;
+        if (j < n) {
+            fl[k] = flags[j];
+            uint32_t o0, b0, o1, b1;
+            ml_trans(m, fl[k], 0, o0, b0);
+            ml_trans(m, fl[k], 1, o1, b1);
+            uint32_t l0 = b0 ? (uint32_t)j + b0 : 0u; // (index + 1) of the opening line
+            uint32_t l1 = b1 ? (uint32_t)j + b1 : 0u;
+            e = OpMlState::make(o0, o1, l0, l1);
+        }
+        el[k] = e;
+        agg = OpMlState::combine(agg, e);
+    }
+    uint64_t tot;
+    uint64_t ex = block_exclusive_scan<OpMlState, THREADS>(agg, tot, s_scan);
+    if (tid < 32) {
+        uint64_t p = lookback<OpMlState>(desc, tile, tot);
+        if (tid == 0)
+            s_prefix = p;
+    }
+    __syncthreads();
+    uint64_t run = OpMlState::combine(s_prefix, ex);
+    // initial condition (:165-169): End-only mode starts partial with multiStartIndex = line 0
+    const uint32_t s0 = (!m.S && !m.C && m.E) ? 1u : 0u;
+    const uint32_t lb_init = s0 ? 1u : 0u;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        uint64_t j = base + k;
+        if (j <= n) {
+            uint32_t s_in = OpMlState::f(run, s0);
+            uint32_t lbp = OpMlState::lb(run, s0);
+            if (!lbp)
+                lbp = lb_init;
+            uint32_t lb = lbp ? lbp - 1 : 0u; // line index of multiStartIndex (valid only when s_in)
+            state[j] = (s_in << 31) | lb;
+            MlCountSink sink;
+            sink.discard = m.discard;
+            ml_actions(m, fl[k], s_in, lb, (uint32_t)j, (uint32_t)n, sink);
+            cnt[j] = sink.cnt;
+        }
+        run = OpMlState::combine(run, el[k]);
+    }
+}
+
+void launch_ml_state(const MlConfig& cfg, const uint8_t* d_flags, uint64_t n, uint32_t* d_state, uint32_t* d_cnt,
+                     uint64_t* d_desc, uint32_t* d_ticket, cudaStream_t st) {
+    MlMode m{cfg.blob_start != nullptr, cfg.blob_cont != nullptr, cfg.blob_end != nullptr, cfg.discard != 0};
+    uint32_t ntiles = scan_tiles(n + 1);
+    ml_state_kernel<kScanThreads, kScanItems>
+        <<<ntiles, kScanThreads, 0, st>>>(m, d_flags, n, d_state, d_cnt, (volatile uint64_t*)d_desc, d_ticket);
+}
+
+struct MlEmitSink {
+    bool discard;
+    const uint32_t* off;
+    const uint32_t* len;
+    uint32_t total_len;
+    uint32_t* out_off;
+    uint32_t* out_len;
+    uint8_t* out_flags;
+    uint64_t cap;
+    uint64_t pos;
+    uint32_t is_last; // isLastLog of the line being processed
+    uint32_t matched_events = 0, unmatch_lines = 0;
+    __device__ void put(uint32_t o, uint32_t l, uint32_t fl) {
+        if (pos < cap) {
+            out_off[pos] = o;
+            out_len[pos] = l;
+            out_flags[pos] = (uint8_t)fl;
+        }
+        ++pos;
+    }
+    __device__ void single(uint32_t j, bool matched) {
+        if (matched) {
+            put(off[j], len[j], is_last | 2u);
+            ++matched_events;
+        } else {
+            ++unmatch_lines;
+            if (!discard)
+                put(off[j], len[j], is_last);
+        }
+    }
+    __device__ void to_end(uint32_t lb, uint32_t j) {
+        uint32_t o = off[lb];
+        put(o, off[j] + len[j] - o, is_last | 2u);
+        ++matched_events;
+    }
+    __device__ void to_prev(uint32_t lb, uint32_t j) {
+        uint32_t o = off[lb];
+        put(o, off[j] - 1 - o, is_last | 2u);
+        ++matched_events;
+    }
+    __device__ void to_eof(uint32_t lb) {
+        uint32_t o = off[lb];
+        put(o, total_len - o, 1u | 2u);
+        ++matched_events;
+    }
+    __device__ void span(uint32_t lb, uint32_t jl, uint32_t) {
+        unmatch_lines += jl - lb + 1;
+        if (!discard)
+            for (uint32_t k = lb; k <= jl; ++k)
+                put(off[k], len[k], is_last);
+    }
+};
+
+__global__ void __launch_bounds__(128)
+    ml_emit_kernel(MlMode m, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ off,
+                   const uint32_t* __restrict__ len, uint64_t n, uint32_t total_len, const uint32_t* __restrict__ state,
+                   const uint64_t* __restrict__ pos, uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len,
+                   uint8_t* __restrict__ out_flags, uint64_t cap, unsigned long long* counters) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t me = 0, ul = 0;
+    if (j <= n) {
+        uint32_t st = state[j];
+        MlEmitSink sink;
+        sink.discard = m.discard;
+        sink.off = off;
+        sink.len = len;
+        sink.total_len = total_len;
+        sink.out_off = out_off;
+        sink.out_len = out_len;
+        sink.out_flags = out_flags;
+        sink.cap = cap;
+        sink.pos = pos[j];
+        // begin + content.size() == sourceVal.size() (:174); the end-of-buffer element always passes true
+        sink.is_last = (j == n) ? 1u : ((off[j] + len[j] == total_len) ? 1u : 0u);
+        ml_actions(m, j < n ? flags[j] : 0u, st >> 31, st & 0x7FFFFFFFu, (uint32_t)j, (uint32_t)n, sink);
+        me = sink.matched_events;
+        ul = sink.unmatch_lines;
+    }
+    // block reduction of the two counters
+    for (int d = 16; d; d >>= 1) {
+        me += __shfl_down_sync(0xFFFFFFFFu, me, d);
+        ul += __shfl_down_sync(0xFFFFFFFFu, ul, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (me)
+            atomicAdd(&counters[0], (unsigned long long)me);
+        if (ul)
+            atomicAdd(&counters[1], (unsigned long long)ul);
+    }
+}
+
+void launch_ml_emit(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len,
+                    uint64_t n, uint32_t total_len, const uint32_t* d_state, const uint64_t* d_pos, uint32_t* d_out_off,
+                    uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, unsigned long long* d_counters,
+                    cudaStream_t st) {
+    MlMode m{cfg.blob_start != nullptr, cfg.blob_cont != nullptr, cfg.blob_end != nullptr, cfg.discard != 0};
+    ml_emit_kernel<<<(unsigned)((n + 1 + 127) / 128), 128, 0, st>>>(m, d_flags, d_off, d_len, n, total_len, d_state,
+                                                                    d_pos, d_out_off, d_out_len, d_out_flags, cap,
+                                                                    d_counters);
+}
+
+// ================================================================================================ delimiter
+__global__ void __launch_bounds__(128)
+    delim_kernel(DelimConfig cfg, const uint8_t* __restrict__ base, const uint32_t* __restrict__ ev_off,
+                 const uint32_t* __restrict__ ev_len, uint64_t n, uint8_t* __restrict__ status,
+                 uint32_t* __restrict__ nfields, uint32_t* __restrict__ f_off, uint32_t* __restrict__ f_len,
+                 uint32_t* __restrict__ f_dq) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const uint32_t eo = ev_off[i];
+    const uint8_t* v = base + eo;
+    const uint32_t MF = cfg.max_fields;
+    uint32_t* fo = f_off + i * MF;
+    uint32_t* fl = f_len + i * MF;
+    uint32_t* fd = f_dq + i * MF;
+    uint32_t nf = 0; // columns counted
+    uint8_t st;
+    // trim (:226-238)
+    int32_t endIdx = (int32_t)ev_len[i];
+    int32_t begIdx = 0;
+    bool blank = endIdx == 0;
+    if (!blank) {
+        while (endIdx > 0 && (v[endIdx - 1] == ' ' || v[endIdx - 1] == '\r'))
+            --endIdx;
+        while (begIdx < endIdx && v[begIdx] == ' ')
+            ++begIdx;
+        blank = begIdx >= endIdx;
+    }
+    auto push = [&](uint32_t o, uint32_t l, uint32_t dq) {
+        if (nf < MF) {
+            fo[nf] = eo + o;
+            fl[nf] = l;
+            fd[nf] = dq;
+        }
+        ++nf;
+    };
+    bool ok = true;
+    if (blank) {
+        st = 2;
+    } else if (cfg.nkeys == 0) {
+        st = 1;
+        ok = false;
+    } else {
+        const bool use_quote = cfg.sep_len == 1 && cfg.quote != cfg.sep[0];
+        if (use_quote) {
+            // DelimiterModeFsmParser::ParseDelimiterLine (zero-copy variant, :260-294)
+            const uint8_t sep = cfg.sep[0], quote = cfg.quote;
+            int state = 0; // 0 INITIAL 1 QUOTE 2 DATA 3 DOUBLE_QUOTE
+            int dq = 0;
+            int fs = begIdx, fe = begIdx;
+            for (int32_t k = begIdx; k < endIdx && ok; ++k) {
+                uint8_t c = v[k];
+                if (c == sep) {
+                    if (state == 1) {
+                        fe++;
+                    } else if (state == 3) {
+                        state = 0;
+                        dq--;
+                        push(fs, fe - fs, dq);
+                        dq = 0;
+                        fe += 2;
+                        fs = fe;
+                    } else {
+                        state = 0;
+                        push(fs, fe - fs, dq);
+                        dq = 0;
+                        fs = ++fe;
+                    }
+                } else if (c == quote) {
+                    if (state == 0) {
+                        state = 1;
+                        fs++;
+                    } else if (state == 1) {
+                        state = 3;
+                        dq++;
+                        fe++;
+                    } else if (state == 2) {
+                        ok = false;
+                    } else {
+                        state = 1;
+                        fe++;
+                    }
+                } else {
+                    if (state == 0) {
+                        state = 2;
+                        fe++;
+                    } else if (state == 3) {
+                        ok = false;
+                    } else {
+                        fe++;
+                    }
+                }
+            }
+            if (ok) {
+                if (state == 3)
+                    dq--;
+                if (state == 1)
+                    ok = false;
+                else
+                    push(fs, fe - fs, dq);
+            }
+        } else {
+            // ProcessorParseDelimiterNative::SplitString (:366-409)
+            const uint32_t d = cfg.sep_len;
+            const uint32_t size = endIdx - begIdx;
+            if (d > size) {
+                push(begIdx, size, 0);
+            } else {
+                uint32_t pos = begIdx, top = endIdx - d;
+                bool done = false;
+                while (pos <= top && !done) {
+                    uint32_t pos2 = endIdx;
+                    for (uint32_t q = pos; q + d <= (uint32_t)endIdx; ++q) {
+                        bool eq = true;
+                        for (uint32_t t = 0; t < d; ++t)
+                            eq = eq && v[q + t] == cfg.sep[t];
+                        if (eq) {
+                            pos2 = q;
+                            break;
+                        }
+                    }
+                    push(pos, pos2 - pos, 0);
+                    if (pos2 == (uint32_t)endIdx) {
+                        done = true;
+                        break;
+                    }
+                    pos = pos2 + d;
+                    if (nf >= cfg.nkeys && !cfg.extend) {
+                        push(pos2, endIdx - pos2, 0);
+                        done = true;
+                    }
+                }
+                if (!done && pos <= (uint32_t)endIdx)
+                    push(pos, endIdx - pos, 0);
+            }
+            if (nf == 0)
+                ok = false;
+        }
+        if (!ok) {
+            st = 1;
+            nf = 0;
+        } else {
+            uint32_t cols = nf;
+            if (use_quote && !cfg.extend && cols > cfg.nkeys)
+                cols = cfg.nkeys + 1; // overflow columns are joined into one (:258-275)
+            st = (cols == 0 || (!cfg.allow_short && cols < cfg.nkeys)) ? 3 : 0;
+        }
+    }
+    status[i] = st;
+    nfields[i] = nf;
+    for (uint32_t k = (st == 1 || st == 2) ? 0 : (nf < MF ? nf : MF); k < MF; ++k) {
+        fo[k] = 0;
+        fl[k] = 0;
+        fd[k] = 0;
+    }
+}
+
+void launch_delim(const DelimConfig& cfg, const uint8_t* d_base, const uint32_t* d_ev_off, const uint32_t* d_ev_len,
+                  uint64_t n, uint8_t* d_status, uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len,
+                  uint32_t* d_f_dq, cudaStream_t st) {
+    if (!n)
+        return;
+    delim_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cfg, d_base, d_ev_off, d_ev_len, n, d_status, d_nfields,
+                                                              d_f_off, d_f_len, d_f_dq);
+}
+
+} // namespace lck

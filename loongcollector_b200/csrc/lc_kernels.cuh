@@ -1,0 +1,76 @@
+// lc_kernels.cuh -- launch interface between the C-ABI layer (lc_capi.cu) and the sm_100a kernels
+// (lc_kernels.cu).  Device pointers + stream in, nothing else.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lck {
+
+constexpr int kSplitThreads = 256;
+constexpr int kSplitRows = 4;
+constexpr uint32_t kSplitTileBytes = kSplitThreads * kSplitRows * 16; // 16 KiB of input per tile
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr uint32_t kScanTile = kScanThreads * kScanItems;
+
+inline uint32_t split_tiles(uint64_t len, uint32_t shift) {
+    return (uint32_t)((len + shift + kSplitTileBytes - 1) / kSplitTileBytes);
+}
+inline uint32_t scan_tiles(uint64_t n) { return (uint32_t)((n + kScanTile - 1) / kScanTile); }
+
+// a1: newline split.  desc: >= split_tiles() u64 (zeroed), ticket: u32 (zeroed), n_out: u32 device counter.
+void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
+                  uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out, cudaStream_t st);
+
+// exclusive sum of u32 -> u64 (out has n entries; *d_total receives the grand total)
+void launch_exclusive_sum(const uint32_t* d_in, uint64_t n, uint64_t* d_out, uint64_t* d_total, uint64_t* d_desc,
+                          uint32_t* d_ticket, cudaStream_t st);
+
+// a3: regex_match + capture groups, one thread per event (baseline kernel, tables read from global memory)
+// d_lab_off: per-event byte offset into d_lab (two-pass label scratch, u16 labels); unused for forward-only.
+void launch_regex_parse_basic(const void* d_blob, uint32_t mode, uint32_t ngroups, const uint8_t* d_base,
+                              const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                              uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, const uint64_t* d_lab_off,
+                              uint16_t* d_lab, cudaStream_t st);
+// per-event scratch need of the two-pass matcher: len + 1 labels, rounded up to 8 labels (16 B)
+void launch_label_sizes(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_sizes, cudaStream_t st);
+
+// anchored prefix probe, one bool per event
+void launch_prefix_match(const void* d_blob, const uint8_t* d_base, const uint32_t* d_ev_off,
+                         const uint32_t* d_ev_len, uint64_t n, uint8_t* d_out, cudaStream_t st);
+
+// a2: multiline.  Lines (d_off,d_len,n) come from launch_split over the same buffer.
+struct MlConfig {
+    const void* blob_start; // device blobs or nullptr
+    const void* blob_cont;
+    const void* blob_end;
+    int discard;
+};
+// flags[i] bit0/1/2 = start/continue/end pattern matches a prefix of line i
+void launch_ml_probe(const MlConfig& cfg, const uint8_t* d_buf, const uint32_t* d_off, const uint32_t* d_len,
+                     uint64_t n, uint8_t* d_flags, cudaStream_t st);
+// state scan over n lines + 1 virtual EOF element: d_state[i] = (s_in << 31) | lb_in, d_cnt[i] = output events
+void launch_ml_state(const MlConfig& cfg, const uint8_t* d_flags, uint64_t n, uint32_t* d_state, uint32_t* d_cnt,
+                     uint64_t* d_desc, uint32_t* d_ticket, cudaStream_t st);
+// emission: d_pos = exclusive sum of d_cnt; d_counters[0..1] += matched_events, unmatch_lines
+void launch_ml_emit(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len,
+                    uint64_t n, uint32_t total_len, const uint32_t* d_state, const uint64_t* d_pos, uint32_t* d_out_off,
+                    uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, unsigned long long* d_counters,
+                    cudaStream_t st);
+
+// a4: delimiter
+struct DelimConfig {
+    uint8_t sep[4];
+    uint32_t sep_len;
+    uint8_t quote;
+    uint32_t nkeys;
+    int extend;
+    int allow_short;
+    uint32_t max_fields;
+};
+void launch_delim(const DelimConfig& cfg, const uint8_t* d_base, const uint32_t* d_ev_off, const uint32_t* d_ev_len,
+                  uint64_t n, uint8_t* d_status, uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len,
+                  uint32_t* d_f_dq, cudaStream_t st);
+
+} // namespace lck
