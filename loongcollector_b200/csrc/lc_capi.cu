@@ -1,9 +1,12 @@
 // lc_capi.cu -- implementation of the C-ABI declared in include/lc_b200.h: engine (stream, grow-only
 // HBM workspace, look-back descriptors), host<->device staging, and the per-processor pipelines.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <new>
 #include <string>
@@ -73,6 +76,11 @@ struct lc_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
+    int num_sms = 148;
+    int smem_per_block_optin = 0;
+    int smem_per_sm = 0;
+    bool force_basic_regex = false; // env LC_B200_REGEX_KERNEL=basic
+    uint64_t scratch_hint = 0;
     // staging / workspace (grow-only)
     DevBuf in, ev_off, ev_len, out_a, out_b, out_c, out_d, out_e;
     DevBuf lines_off, lines_len, flags, state, cnt, pos, lab_sizes, lab_off, lab;
@@ -108,9 +116,12 @@ cudaError_t engine_blob(lc_engine* e, const lc_regex* r, const void** out) {
 struct Small {
     uint32_t tickets[4];
     uint32_t n_out;
-    uint32_t pad0[3];
+    uint32_t overflow;
+    uint32_t pad0[2];
     uint64_t total;
-    uint64_t pad1[3];
+    unsigned long long bump;
+    unsigned long long next_batch;
+    uint64_t pad1[1];
     unsigned long long counters[2];
 };
 
@@ -176,6 +187,13 @@ int lc_engine_create(int device, lc_engine_t** out) {
     e->device = device;
     CU_TRY(cudaSetDevice(device));
     CU_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device));
+    CU_TRY(cudaDeviceGetAttribute(&e->smem_per_block_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CU_TRY(cudaDeviceGetAttribute(&e->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    {
+        const char* k = getenv("LC_B200_REGEX_KERNEL");
+        e->force_basic_regex = k && !strcmp(k, "basic");
+    }
     CU_TRY(e->small.ensure(sizeof(Small)));
     CU_TRY(cudaMallocHost(&e->h_small, sizeof(Small)));
     *out = e;
@@ -345,25 +363,78 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
     const void* d_blob;
     CU_TRY(engine_blob(e, re, &d_blob));
     const LcRegexHeader* h = reinterpret_cast<const LcRegexHeader*>(re->res.blob.data());
+    Small* ds = e->small.as<Small>();
+    Small* hs = (Small*)e->h_small;
+    const bool force_basic = e->force_basic_regex;
+    const uint32_t blob_bytes = h->total_bytes;
+    // shared-memory plan of the persistent kernel: one automaton copy per block, the rest holds labels
+    const uint32_t per = (h->mode == LC_MODE_TWOPASS && h->rev_label_bytes == 2) ? 2u : 4u;
+    const size_t smem_max = (size_t)e->smem_per_block_optin;
+    if (!force_basic && blob_bytes + 4096 <= smem_max) {
+        uint32_t lab_words = 0, threads = 1024, blocks_per_sm = 1;
+        if (h->mode == LC_MODE_TWOPASS) {
+            uint64_t avg = base_len / n + 1;
+            lab_words = (uint32_t)((avg + avg / 8) / per + 2);
+            if (lab_words < 16)
+                lab_words = 16;
+            size_t budget = smem_max - blob_bytes - 1024;
+            uint32_t warps = (uint32_t)(budget / ((size_t)lab_words * 128));
+            if (warps < 4) { // very long average lines: keep 4 warps and let long events use the global slab
+                warps = 4;
+                lab_words = (uint32_t)(budget / (4 * 128));
+            }
+            if (warps > 32)
+                warps = 32;
+            threads = warps * 32;
+            if (warps <= 16 && 2 * (blob_bytes + (size_t)warps * lab_words * 128 + 1024) <= (size_t)e->smem_per_sm)
+                blocks_per_sm = 2;
+        } else {
+            threads = 512;
+            blocks_per_sm = 2;
+        }
+        uint64_t need_blocks = (n + threads - 1) / threads;
+        uint32_t grid = (uint32_t)std::min<uint64_t>(need_blocks, (uint64_t)e->num_sms * blocks_per_sm);
+        // global label slab for events longer than the shared-memory budget: start small, remember what worked
+        uint64_t full = base_len / per + 2 * n + 1024;
+        uint64_t scratch_words = std::max<uint64_t>(e->scratch_hint, std::min<uint64_t>(full, 16ull << 20));
+        for (int attempt = 0; attempt < 8; ++attempt) {
+            if (h->mode == LC_MODE_TWOPASS)
+                CU_TRY(e->lab.ensure(scratch_words * 4));
+            CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof(Small) - offsetof(Small, overflow), e->stream));
+            int er = lck::launch_regex_parse_fast(d_blob, blob_bytes, h->rev_label_bytes, h->ngroups, d_base, d_ev_off,
+                                                  d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len, lab_words,
+                                                  threads, grid, e->lab.as<uint32_t>(), scratch_words, &ds->bump,
+                                                  &ds->overflow, &ds->next_batch, e->stream);
+            e->launches++;
+            if (er)
+                return fail(LC_ERR_CUDA, std::string("regex kernel launch: ") + cudaGetErrorString((cudaError_t)er));
+            if (h->mode != LC_MODE_TWOPASS)
+                return LC_OK;
+            CU_TRY(cudaMemcpyAsync(&hs->overflow, &ds->overflow, 4, cudaMemcpyDeviceToHost, e->stream));
+            CU_TRY(cudaStreamSynchronize(e->stream));
+            if (!hs->overflow) {
+                e->scratch_hint = scratch_words;
+                return LC_OK;
+            }
+            scratch_words = scratch_words < full ? std::min<uint64_t>(full, scratch_words * 4) : scratch_words * 2;
+        }
+        return fail(LC_ERR_CUDA, "label scratch exhausted after retries");
+    }
+    // ---- baseline kernel (tables in global memory); kept for A/B checks and for automata beyond shared memory
     const uint64_t* d_lab_off = nullptr;
     uint16_t* d_lab = nullptr;
     if (h->mode == LC_MODE_TWOPASS) {
-        // label scratch: (len + 1) u16 labels per event, placed by an exclusive sum
         DescPlan plan;
         rc = prep_desc(e, 0, 0, lck::scan_tiles(n), plan);
         if (rc)
             return rc;
         CU_TRY(e->lab_sizes.ensure(n * 4));
         CU_TRY(e->lab_off.ensure(n * 8));
-        Small* ds = e->small.as<Small>();
         lck::launch_label_sizes(d_ev_len, n, e->lab_sizes.as<uint32_t>(), e->stream);
         lck::launch_exclusive_sum(e->lab_sizes.as<uint32_t>(), n, e->lab_off.as<uint64_t>(), &ds->total, plan.r[2],
                                   &ds->tickets[2], e->stream);
         e->launches += 2;
         CU_TRY(cudaGetLastError());
-        // upper bound without a sync: every event needs at most len+8 labels and events may overlap, so the
-        // exact total is read back (one 8-byte D2H)
-        Small* hs = (Small*)e->h_small;
         CU_TRY(cudaMemcpyAsync(&hs->total, &ds->total, 8, cudaMemcpyDeviceToHost, e->stream));
         CU_TRY(cudaStreamSynchronize(e->stream));
         CU_TRY(e->lab.ensure(hs->total * 2 + 16));

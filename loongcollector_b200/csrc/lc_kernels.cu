@@ -238,6 +238,213 @@ void launch_regex_parse_basic(const void* d_blob, uint32_t mode, uint32_t ngroup
         d_blob, mode, ngroups, d_base, d_ev_off, d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len, d_lab_off, d_lab);
 }
 
+
+// ================================================================================================ regex (fast path)
+// Thread-per-event kernels with the whole automaton blob staged in shared memory.
+//
+// Two-pass matcher: the reverse pass needs one label per input position.  Labels of short events live in
+// shared memory, packed 4 (u8) or 2 (u16) per 32-bit word; a warp's words are interleaved
+// [word][lane] so that lane == bank and the accesses are conflict-free whatever position each lane is at.
+// Events longer than the shared-memory budget bump-allocate their label words from a global scratch slab
+// (order is irrelevant); if the slab is exhausted the kernel raises *overflow and the host retries bigger.
+
+struct LabSmem {
+    uint32_t* p; // warp region base + lane
+    __device__ __forceinline__ void st(uint32_t widx, uint32_t v) const { p[widx * 32] = v; }
+    __device__ __forceinline__ uint32_t ld(uint32_t widx) const { return p[widx * 32]; }
+};
+struct LabGlobal {
+    uint32_t* p;
+    __device__ __forceinline__ void st(uint32_t widx, uint32_t v) const { p[widx] = v; }
+    __device__ __forceinline__ uint32_t ld(uint32_t widx) const { return p[widx]; }
+};
+
+// byte `a` (absolute address) through aligned 32-bit read-only loads; `cur`/`cur_word` cache the last word
+__device__ __forceinline__ uint32_t ld_byte(const uint8_t* __restrict__ base, uint64_t a, uint64_t& cur_word,
+                                            uint32_t& cur) {
+    uint64_t w = a >> 2;
+    if (w != cur_word) {
+        cur_word = w;
+        cur = __ldg(reinterpret_cast<const uint32_t*>(base) + w);
+    }
+    return (cur >> (8 * (uint32_t)(a & 3))) & 0xFFu;
+}
+
+template <class LabT, class Lab>
+__device__ __forceinline__ bool twopass_event(const LcProgView& v, const LabT* __restrict__ rev_byte,
+                                              const uint8_t* __restrict__ abase, uint64_t a0, uint32_t n, Lab lab,
+                                              uint32_t* slots) {
+    constexpr uint32_t PER = 4 / sizeof(LabT);     // labels per word
+    constexpr uint32_t BITS = 8 * sizeof(LabT);
+    constexpr uint32_t MASK = (1u << BITS) - 1u;
+    // ---- reverse labelling
+    uint32_t d = v.h->rev_start;
+    uint32_t lw = d << (BITS * (n % PER));
+    uint64_t cw = ~0ull;
+    uint32_t cur = 0;
+    for (uint32_t i = n; i-- > 0;) {
+        uint32_t b = ld_byte(abase, a0 + i, cw, cur);
+        d = rev_byte[d * 256 + b];
+        if (d == LC_REV_DEAD)
+            return false;
+        if ((i % PER) == PER - 1) {
+            lab.st((i + 1) / PER, lw);
+            lw = 0;
+        }
+        lw |= d << (BITS * (i % PER));
+    }
+    lab.st(0, lw);
+    // ---- guided forward walk
+    const uint32_t cols = v.h->fwd_cols;
+    const uint32_t npc = v.h->npc;
+    uint32_t w = 0, pk = 0;
+    cw = ~0ull;
+    for (uint32_t i = 0; i <= n; ++i) {
+        if ((i % PER) == 0 && i)
+            lw = lab.ld(i / PER);
+        uint32_t l = (lw >> (BITS * (i % PER))) & MASK;
+        uint32_t e = v.fwd[(w * npc + pk) * cols + l];
+        if (e == LC_NONE_ENTRY)
+            return false;
+        uint32_t a = LC_ENTRY_ACT(e);
+        if (a)
+            lc_apply_action(v, a, i, slots);
+        w = LC_ENTRY_NEXT(e);
+        if (npc > 1 && i < n)
+            pk = v.class_pc[v.byte_class[ld_byte(abase, a0 + i, cw, cur)]];
+    }
+    return true;
+}
+
+__device__ __forceinline__ bool fwd1_event(const LcProgView& v, const uint32_t* __restrict__ fwd_byte,
+                                           const uint8_t* __restrict__ abase, uint64_t a0, uint32_t n,
+                                           uint32_t* slots) {
+    uint32_t w = 0;
+    uint64_t cw = ~0ull;
+    uint32_t cur = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t b = ld_byte(abase, a0 + i, cw, cur);
+        uint32_t e = fwd_byte[w * 256 + b];
+        if (e == LC_NONE_ENTRY)
+            return false;
+        uint32_t a = LC_ENTRY_ACT(e);
+        if (a)
+            lc_apply_action(v, a, i, slots);
+        w = LC_ENTRY_NEXT(e);
+    }
+    uint32_t e = v.fwd_eof[w];
+    if (e == LC_NONE_ENTRY)
+        return false;
+    uint32_t a = LC_ENTRY_ACT(e);
+    if (a)
+        lc_apply_action(v, a, n, slots);
+    return true;
+}
+
+template <class LabT>
+__global__ void __launch_bounds__(1024)
+    regex_parse_smem_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, uint32_t G,
+                            const uint8_t* __restrict__ base, const uint32_t* __restrict__ ev_off,
+                            const uint32_t* __restrict__ ev_len, uint64_t n, uint32_t nkeys,
+                            uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
+                            uint32_t* __restrict__ cap_len, uint32_t lab_words /* per thread, in smem */,
+                            uint32_t* __restrict__ scratch, unsigned long long scratch_words,
+                            unsigned long long* bump, uint32_t* overflow, unsigned long long* next_batch) {
+    extern __shared__ uint4 smem[];
+    // stage the automaton
+    for (uint32_t k = threadIdx.x; k < blob_bytes / 16; k += blockDim.x)
+        smem[k] = __ldg(blob + k);
+    __syncthreads();
+    const LcProgView v = lc_view(smem);
+    uint32_t* lab_base = reinterpret_cast<uint32_t*>(smem) + blob_bytes / 4;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // persistent warps: each warp claims batches of 32 consecutive events from a global counter
+    for (;;) {
+    unsigned long long batch = 0;
+    if (lane == 0)
+        batch = atomicAdd(next_batch, 32ull);
+    batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+    if (batch >= n)
+        break;
+    const uint64_t i = batch + lane;
+    if (i >= n)
+        continue;
+    const uint32_t off = ev_off[i], len = ev_len[i];
+    // aligned view of the arena: byte loads go through 32-bit words of the 4-byte aligned base
+    const uint32_t mis = (uint32_t)((uintptr_t)base & 3u);
+    const uint8_t* abase = base - mis;
+    const uint64_t a0 = (uint64_t)off + mis;
+    uint32_t slots[2 * LC_MAX_GROUPS];
+    for (uint32_t k = 0; k < 2 * G; ++k)
+        slots[k] = LC_SLOT_UNSET;
+    bool ok;
+    if (v.h->mode == LC_MODE_FWD1 && v.h->off_fwd_byte) {
+        ok = fwd1_event(v, reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(smem) +
+                                                             v.h->off_fwd_byte),
+                        abase, a0, len, slots);
+    } else if (v.h->mode == LC_MODE_FWD1) {
+        ok = lc_full_match_fwd1(v, base + off, len, slots);
+    } else {
+        const LabT* rev_byte =
+            reinterpret_cast<const LabT*>(reinterpret_cast<const uint8_t*>(smem) + v.h->off_rev_byte);
+        constexpr uint32_t PER = 4 / sizeof(LabT);
+        const uint32_t need = len / PER + 1; // words for labels 0..len
+        if (need <= lab_words) {
+            LabSmem lab{lab_base + (size_t)wid * lab_words * 32 + lane};
+            ok = twopass_event<LabT>(v, rev_byte, abase, a0, len, lab, slots);
+        } else {
+            unsigned long long at = atomicAdd(bump, (unsigned long long)need);
+            if (at + need > scratch_words) {
+                atomicExch(overflow, 1u);
+                ok = false;
+            } else {
+                LabGlobal lab{scratch + at};
+                ok = twopass_event<LabT>(v, rev_byte, abase, a0, len, lab, slots);
+            }
+        }
+    }
+    uint8_t st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
+    status[i] = st;
+    uint32_t* co = cap_off + i * G;
+    uint32_t* cl = cap_len + i * G;
+    for (uint32_t g = 0; g < G; ++g) {
+        uint32_t o = 0, l = 0;
+        if (st == 0) {
+            lc_slots_to_cap(slots, g, len, &o, &l);
+            o += off;
+        }
+        co[g] = o;
+        cl[g] = l;
+    }
+    } // persistent loop
+}
+
+int launch_regex_parse_fast(const void* d_blob, uint32_t blob_bytes, uint32_t rev_label_bytes, uint32_t ngroups,
+                            const uint8_t* d_base, const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n,
+                            uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
+                            uint32_t lab_words, uint32_t threads, uint32_t grid, uint32_t* d_scratch,
+                            uint64_t scratch_words, unsigned long long* d_bump, uint32_t* d_overflow,
+                            unsigned long long* d_next_batch, cudaStream_t st) {
+    if (!n)
+        return 0;
+    size_t smem = blob_bytes + (size_t)(threads / 32) * lab_words * 32 * 4;
+    auto k8 = regex_parse_smem_kernel<uint8_t>;
+    auto k16 = regex_parse_smem_kernel<uint16_t>;
+    cudaError_t er = cudaFuncSetAttribute(rev_label_bytes == 2 ? k16 : k8,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (er != cudaSuccess)
+        return (int)er;
+    if (rev_label_bytes == 2)
+        k16<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, ngroups, d_base, d_ev_off, d_ev_len, n, nkeys,
+                                         d_status, d_cap_off, d_cap_len, lab_words, d_scratch, scratch_words, d_bump,
+                                         d_overflow, d_next_batch);
+    else
+        k8<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, ngroups, d_base, d_ev_off, d_ev_len, n, nkeys,
+                                        d_status, d_cap_off, d_cap_len, lab_words, d_scratch, scratch_words, d_bump,
+                                        d_overflow, d_next_batch);
+    return (int)cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(128)
     prefix_match_kernel(const void* __restrict__ blob, const uint8_t* __restrict__ base,
                         const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,

@@ -36,6 +36,17 @@ void launch_regex_parse_basic(const void* d_blob, uint32_t mode, uint32_t ngroup
 // per-event scratch need of the two-pass matcher: len + 1 labels, rounded up to 8 labels (16 B)
 void launch_label_sizes(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_sizes, cudaStream_t st);
 
+// a3 fast path: persistent kernel, automaton staged in shared memory.  Labels of events needing
+// <= lab_words 32-bit words stay in shared memory, longer events bump-allocate from d_scratch.
+// d_bump, d_overflow and d_next_batch must be zeroed by the caller.  Dynamic shared memory =
+// blob_bytes + (threads / 32) * lab_words * 128.  Returns a cudaError_t value (0 on success).
+int launch_regex_parse_fast(const void* d_blob, uint32_t blob_bytes, uint32_t rev_label_bytes, uint32_t ngroups,
+                            const uint8_t* d_base, const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n,
+                            uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
+                            uint32_t lab_words, uint32_t threads, uint32_t grid, uint32_t* d_scratch,
+                            uint64_t scratch_words, unsigned long long* d_bump, uint32_t* d_overflow,
+                            unsigned long long* d_next_batch, cudaStream_t st);
+
 // anchored prefix probe, one bool per event
 void launch_prefix_match(const void* d_blob, const uint8_t* d_base, const uint32_t* d_ev_off,
                          const uint32_t* d_ev_len, uint64_t n, uint8_t* d_out, cudaStream_t st);

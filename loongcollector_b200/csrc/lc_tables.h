@@ -62,8 +62,11 @@ struct LcRegexHeader {
     uint32_t off_fwd_eof;    // u32 FWD1: [nw*npc]  entry taken at end of input (next ignored)
     uint32_t off_rev_next;   // u16 [rev_nstates][nclasses]
     uint32_t fwd_cols;       // row length of the fwd table
-    uint32_t flags;          // bit0: pattern can match only the empty prefix trivially (unused)
-    uint32_t reserved[10];
+    uint32_t flags;          // unused
+    uint32_t off_rev_byte;   // TWOPASS: LabT [rev_nstates][256] reverse transition indexed by raw byte
+    uint32_t rev_label_bytes; // 1 when rev_nstates <= 256 (LabT = u8) else 2 (u16)
+    uint32_t off_fwd_byte;   // FWD1 (npc == 1 only): u32 [nw][256] forward entry indexed by raw byte, else 0
+    uint32_t reserved[7];
 };
 
 #ifdef __cplusplus

@@ -1055,11 +1055,10 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
         const std::vector<Inst>& prog = cc.prog;
         res.n_insts = (uint32_t)prog.size();
 
-        bool has_ctx = false;
+        bool has_ctx = false; // any assertion at all: byte classes are refined by context kind
         for (auto& in : prog)
             if (in.op == OP_ASSERT)
                 has_ctx = true;
-        const int npc = has_ctx ? K_COUNT : 1;
         auto kind_of = [&](unsigned b) { return has_ctx ? byte_kind(b) : 0; };
 
         // ---- walker states: 0 = START, 1.. = CHAR instructions
@@ -1125,6 +1124,25 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                 rec.go(entry, 0, 0);
             }
         }
+
+        // ---- static resolution of assertions whose context is fixed.
+        // START always stands at offset 0 (prev == EDGE): ^ and \A hold.  Every automaton strips those.
+        for (auto& cd : cand[0])
+            cd.asserts &= ~(uint32_t)(A_BOL | A_BOT);
+        // The PREFIX dfa keeps everything else; the full-match automata additionally know that MATCH is only
+        // ever taken at end of input (next == EDGE): $ and \z hold there.
+        std::vector<std::vector<Cand>> cand_prefix = cand;
+        bool ctx_prefix = false, ctx_full = false;
+        for (auto& lst : cand)
+            for (auto& cd : lst) {
+                if (cd.asserts)
+                    ctx_prefix = true;
+                if (cd.target < 0)
+                    cd.asserts &= ~(uint32_t)(A_EOL | A_EOT);
+                if (cd.asserts)
+                    ctx_full = true;
+            }
+        const int npc = ctx_full ? K_COUNT : 1;
 
         // ---- byte classes
         uint8_t byte_class[256];
@@ -1209,7 +1227,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                 Key cur = states[s]; // copy: `states` grows
                 int pk = cur.second;
                 for (int w : cur.first)
-                    for (auto& cd : cand[w])
+                    for (auto& cd : cand_prefix[w])
                         if (cd.target < 0 && asserts_hold(cd.asserts, pk, K_EDGE))
                             pre_acc[s] = 1;
                 for (int c = 0; c < nclasses; ++c) {
@@ -1217,8 +1235,8 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                     bool accept_now = false;
                     std::set<int> nxt;
                     for (int w : cur.first)
-                        for (auto& cd : cand[w]) {
-                            if (!asserts_hold(cd.asserts, pk, has_ctx ? nk : 0) && has_ctx)
+                        for (auto& cd : cand_prefix[w]) {
+                            if (cd.asserts && !asserts_hold(cd.asserts, pk, nk))
                                 continue;
                             if (cd.target < 0)
                                 accept_now = true;
@@ -1229,13 +1247,13 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                     if (accept_now)
                         v = LC_PREFIX_ACCEPT;
                     else
-                        v = intern(Key(std::vector<int>(nxt.begin(), nxt.end()), nk));
+                        v = intern(Key(std::vector<int>(nxt.begin(), nxt.end()), ctx_prefix ? nk : 0));
                     pre_next[s * nclasses + c] = (uint16_t)v;
                 }
             }
             res.n_prefix = (uint32_t)states.size();
         }
-        // NB: when !has_ctx every kind is 0 == K_EDGE and no cand carries asserts, so asserts_hold is vacuous.
+        // NB: a zero assertion mask always holds, so context kinds are irrelevant wherever masks were stripped.
 
         // ---- reverse DFA over viable-target sets
         // state = (sorted set of targets {walker idx, or 0 for MATCH}, next kind)
@@ -1293,7 +1311,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                         if (viable)
                             nxt.push_back(q);
                     }
-                    uint32_t v = intern(RKey(nxt, pk));
+                    uint32_t v = intern(RKey(nxt, ctx_full ? pk : 0));
                     rev_next[s * nclasses + c] = (uint16_t)v;
                     rev_incoming.resize(rstates.size());
                     if (v)
@@ -1320,7 +1338,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
             int nk = c < 0 ? K_EDGE : class_kind[c];
             for (size_t ci = 0; ci < cand[w].size(); ++ci) {
                 const Cand& cd = cand[w][ci];
-                if (!asserts_hold(cd.asserts, pk, has_ctx ? nk : 0) && has_ctx)
+                if (cd.asserts && !asserts_hold(cd.asserts, pk, nk))
                     continue;
                 if (c < 0) {
                     if (cd.target < 0)
@@ -1337,7 +1355,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
         for (int D = 1; D < nD && fwd1_safe; ++D) {
             for (int w = 0; w < nw && fwd1_safe; ++w) {
                 for (int pk = 0; pk < npc && fwd1_safe; ++pk) {
-                    if (!(walker_pcs[w] >> pk & 1))
+                    if (npc > 1 && !(walker_pcs[w] >> pk & 1))
                         continue;
                     int v = first_viable(w, pk, D);
                     if (v < 0)
@@ -1415,8 +1433,29 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
         put(blob, h.off_pre_acc, pre_acc);
         put(blob, h.off_fwd, fwd);
         put(blob, h.off_fwd_eof, fwd_eof);
-        if (mode == LC_MODE_TWOPASS)
+        if (mode == LC_MODE_TWOPASS) {
             put(blob, h.off_rev_next, rev_next);
+            h.rev_label_bytes = nD <= 256 ? 1 : 2;
+            if (nD <= 256) {
+                std::vector<uint8_t> rb((size_t)nD * 256);
+                for (int d = 0; d < nD; ++d)
+                    for (int b = 0; b < 256; ++b)
+                        rb[(size_t)d * 256 + b] = (uint8_t)rev_next[(size_t)d * nclasses + byte_class[b]];
+                put(blob, h.off_rev_byte, rb);
+            } else {
+                std::vector<uint16_t> rb((size_t)nD * 256);
+                for (int d = 0; d < nD; ++d)
+                    for (int b = 0; b < 256; ++b)
+                        rb[(size_t)d * 256 + b] = rev_next[(size_t)d * nclasses + byte_class[b]];
+                put(blob, h.off_rev_byte, rb);
+            }
+        } else if (npc == 1) {
+            std::vector<uint32_t> fb((size_t)nw * 256);
+            for (int w = 0; w < nw; ++w)
+                for (int b = 0; b < 256; ++b)
+                    fb[(size_t)w * 256 + b] = fwd[(size_t)w * fwd_cols + byte_class[b]];
+            put(blob, h.off_fwd_byte, fb);
+        }
         while (blob.size() % 16)
             blob.push_back(0);
         h.total_bytes = (uint32_t)blob.size();
@@ -1430,6 +1469,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
         res.supported = false;
         res.error = std::string("invalid regex: ") + e.what();
     } catch (const Unsupported& e) {
+        res.valid = true; // boost accepts it; this engine's automaton subset does not
         res.supported = false;
         res.error = std::string("unsupported regex: ") + e.what();
     }
