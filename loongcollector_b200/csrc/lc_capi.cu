@@ -374,7 +374,7 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
         uint32_t lab_words = 0, threads = 1024, blocks_per_sm = 1;
         if (h->mode == LC_MODE_TWOPASS) {
             uint64_t avg = base_len / n + 1;
-            lab_words = (uint32_t)((avg + avg / 8) / per + 2);
+            lab_words = (uint32_t)((avg + avg / 8 + 16) / per + 2);
             if (lab_words < 16)
                 lab_words = 16;
             size_t budget = smem_max - blob_bytes - 1024;
@@ -581,7 +581,8 @@ int lc_multiline_split_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, c
     CU_TRY(e->state.ensure((n + 1) * 4));
     CU_TRY(e->cnt.ensure((n + 1) * 4));
     CU_TRY(e->pos.ensure((n + 1) * 8));
-    lck::launch_ml_state(cfg, e->flags.as<uint8_t>(), n, e->state.as<uint32_t>(), e->cnt.as<uint32_t>(), plan.r[1],
+    lck::launch_ml_state(cfg, e->flags.as<uint8_t>(), e->lines_len.as<uint32_t>(), n, e->state.as<uint32_t>(),
+                         e->cnt.as<uint32_t>(), plan.r[1],
                          &ds->tickets[1], e->stream);
     lck::launch_exclusive_sum(e->cnt.as<uint32_t>(), n + 1, e->pos.as<uint64_t>(), &ds->total, plan.r[2],
                               &ds->tickets[2], e->stream);

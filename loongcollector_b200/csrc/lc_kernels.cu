@@ -341,8 +341,114 @@ __device__ __forceinline__ bool fwd1_event(const LcProgView& v, const uint32_t* 
     return true;
 }
 
+
+// Fast two-pass walk (u8 labels, no context kinds).  Input bytes are consumed as 16-byte aligned chunks and the
+// label of position i is stored at virtual index q = i + (address & 15), so that input words and label words
+// share their boundaries: full chunks run 16 fully unrolled steps without any per-byte predicate.
+// sfwd is the forward table re-encoded at staging time: entry = byte offset of the next walker's row
+// (bits 0..21) | action id << 22.
+#define LC_FAST_ROW_MASK 0x3FFFFFu
+#define LC_FAST_ACT_SHIFT 22
+
+template <class Lab>
+__device__ __forceinline__ bool twopass_event_fast(const LcProgView& v, const uint8_t* __restrict__ rev_byte,
+                                                   const uint8_t* __restrict__ sfwd, const uint4* __restrict__ chunks,
+                                                   uint32_t mis, uint32_t n, Lab lab, uint32_t* slots) {
+    const uint32_t Q = n + mis;
+    const int top = (int)(Q >> 4);
+    const uint32_t rev_start = v.h->rev_start;
+    uint32_t d = rev_start;
+    // ---- reverse labelling
+    for (int qc = top; qc >= 0; --qc) {
+        const uint32_t lo = (uint32_t)qc * 16;
+        uint4 vv = make_uint4(0, 0, 0, 0);
+        if (lo < Q)
+            vv = __ldg(chunks + qc);
+        const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+        if (lo >= mis && lo + 15 < Q) {
+#pragma unroll
+            for (int wi = 3; wi >= 0; --wi) {
+                const uint32_t x = w[wi];
+                d = rev_byte[d * 256 + (x >> 24)];
+                uint32_t lw = d << 24;
+                d = rev_byte[d * 256 + ((x >> 16) & 0xFFu)];
+                lw |= d << 16;
+                d = rev_byte[d * 256 + ((x >> 8) & 0xFFu)];
+                lw |= d << 8;
+                d = rev_byte[d * 256 + (x & 0xFFu)];
+                lw |= d;
+                lab.st(qc * 4 + wi, lw);
+            }
+        } else {
+#pragma unroll
+            for (int wi = 3; wi >= 0; --wi) {
+                const uint32_t x = w[wi];
+                uint32_t lw = 0;
+                bool any = false;
+#pragma unroll
+                for (int k = 3; k >= 0; --k) {
+                    const uint32_t q = lo + wi * 4 + k;
+                    if (q == Q) {
+                        lw |= rev_start << (8 * k);
+                        any = true;
+                    } else if (q < Q && q >= mis) {
+                        d = rev_byte[d * 256 + ((x >> (8 * k)) & 0xFFu)];
+                        lw |= d << (8 * k);
+                        any = true;
+                    }
+                }
+                if (any)
+                    lab.st(qc * 4 + wi, lw);
+            }
+        }
+        if (d == LC_REV_DEAD)
+            return false;
+    }
+    // ---- guided forward walk; d == label of position 0
+    if (*reinterpret_cast<const uint32_t*>(sfwd + d * 4) == LC_NONE_ENTRY)
+        return false;
+    uint32_t row = 0; // byte offset of the current walker's row (START)
+    for (int qc = 0; qc <= top; ++qc) {
+        const uint32_t lo = (uint32_t)qc * 16;
+        if (lo >= mis && lo + 15 <= Q) {
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi) {
+                const uint32_t lw = lab.ld(qc * 4 + wi);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t l4 = k == 0 ? ((lw << 2) & 0x3FCu) : ((lw >> (8 * k - 2)) & 0x3FCu);
+                    const uint32_t e = *reinterpret_cast<const uint32_t*>(sfwd + row + l4);
+                    if (e >> LC_FAST_ACT_SHIFT)
+                        lc_apply_action(v, e >> LC_FAST_ACT_SHIFT, lo + wi * 4 + k - mis, slots);
+                    row = e & LC_FAST_ROW_MASK;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi) {
+                const uint32_t q0 = lo + wi * 4;
+                if (q0 + 3 < mis || q0 > Q)
+                    continue;
+                const uint32_t lw = lab.ld(qc * 4 + wi);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t q = q0 + k;
+                    if (q >= mis && q <= Q) {
+                        const uint32_t l4 = ((lw >> (8 * k)) & 0xFFu) * 4;
+                        const uint32_t e = *reinterpret_cast<const uint32_t*>(sfwd + row + l4);
+                        if (e >> LC_FAST_ACT_SHIFT)
+                            lc_apply_action(v, e >> LC_FAST_ACT_SHIFT, q - mis, slots);
+                        row = e & LC_FAST_ROW_MASK;
+                    }
+                }
+            }
+        }
+    }
+    return true;
+}
+
 template <class LabT>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 1)
     regex_parse_smem_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, uint32_t G,
                             const uint8_t* __restrict__ base, const uint32_t* __restrict__ ev_off,
                             const uint32_t* __restrict__ ev_len, uint64_t n, uint32_t nkeys,
@@ -356,6 +462,21 @@ __global__ void __launch_bounds__(1024)
         smem[k] = __ldg(blob + k);
     __syncthreads();
     const LcProgView v = lc_view(smem);
+    // fast walk: u8 labels, no context kinds, row offsets and action ids fit the packed entry
+    const bool fast = v.h->mode == LC_MODE_TWOPASS && sizeof(LabT) == 1 && v.h->npc == 1 &&
+                      (uint64_t)v.h->nw * v.h->fwd_cols * 4 <= LC_FAST_ROW_MASK && v.h->nact < 1024;
+    if (fast) {
+        uint32_t* f = const_cast<uint32_t*>(v.fwd);
+        const uint32_t cells = v.h->nw * v.h->fwd_cols, cols = v.h->fwd_cols;
+        for (uint32_t k = threadIdx.x; k < cells; k += blockDim.x) {
+            uint32_t e = f[k];
+            if (e != LC_NONE_ENTRY) {
+                uint32_t nxt = LC_ENTRY_NEXT(e);
+                f[k] = (nxt == 0xFFFFu ? 0u : nxt * cols * 4) | (LC_ENTRY_ACT(e) << LC_FAST_ACT_SHIFT);
+            }
+        }
+        __syncthreads();
+    }
     uint32_t* lab_base = reinterpret_cast<uint32_t*>(smem) + blob_bytes / 4;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // persistent warps: each warp claims batches of 32 consecutive events from a global counter
@@ -388,10 +509,18 @@ __global__ void __launch_bounds__(1024)
         const LabT* rev_byte =
             reinterpret_cast<const LabT*>(reinterpret_cast<const uint8_t*>(smem) + v.h->off_rev_byte);
         constexpr uint32_t PER = 4 / sizeof(LabT);
-        const uint32_t need = len / PER + 1; // words for labels 0..len
+        // label words: the fast walk shifts labels by the 16-byte misalignment of the event
+        const uint64_t a16 = (uint64_t)(uintptr_t)(base + off);
+        const uint32_t mis16 = (uint32_t)(a16 & 15u);
+        const uint4* chunks = reinterpret_cast<const uint4*>(a16 - mis16);
+        const uint32_t need = fast ? ((len + mis16) / 4 + 1) : (len / PER + 1);
         if (need <= lab_words) {
             LabSmem lab{lab_base + (size_t)wid * lab_words * 32 + lane};
-            ok = twopass_event<LabT>(v, rev_byte, abase, a0, len, lab, slots);
+            if (fast)
+                ok = twopass_event_fast(v, reinterpret_cast<const uint8_t*>(rev_byte),
+                                        reinterpret_cast<const uint8_t*>(v.fwd), chunks, mis16, len, lab, slots);
+            else
+                ok = twopass_event<LabT>(v, rev_byte, abase, a0, len, lab, slots);
         } else {
             unsigned long long at = atomicAdd(bump, (unsigned long long)need);
             if (at + need > scratch_words) {
@@ -399,7 +528,11 @@ __global__ void __launch_bounds__(1024)
                 ok = false;
             } else {
                 LabGlobal lab{scratch + at};
-                ok = twopass_event<LabT>(v, rev_byte, abase, a0, len, lab, slots);
+                if (fast)
+                    ok = twopass_event_fast(v, reinterpret_cast<const uint8_t*>(rev_byte),
+                                            reinterpret_cast<const uint8_t*>(v.fwd), chunks, mis16, len, lab, slots);
+                else
+                    ok = twopass_event<LabT>(v, rev_byte, abase, a0, len, lab, slots);
             }
         }
     }
@@ -597,19 +730,48 @@ __device__ __forceinline__ void ml_actions(const MlMode& m, uint32_t fl, uint32_
     }
 }
 
+// HandleUnmatchLogs re-splits its span with `while (begin < size)` (:342-380): an EMPTY unmatched line yields
+// nothing (not even unmatch_lines++), and a span that ends with an empty line loses that last line; only the
+// end-of-buffer span (which includes the trailing '\n') keeps it.
+__device__ __forceinline__ uint32_t ml_span_last(const uint32_t* len, uint32_t lb, uint32_t jl, bool tail,
+                                                 bool& none) {
+    none = false;
+    if (!tail && len[jl] == 0) {
+        if (jl == lb) {
+            none = true;
+            return jl;
+        }
+        return jl - 1;
+    }
+    return jl;
+}
+
 struct MlCountSink {
     bool discard;
+    const uint32_t* len;
+    uint32_t n;
     uint32_t cnt = 0;
-    __device__ void single(uint32_t, bool matched) { cnt += (matched || !discard) ? 1 : 0; }
+    __device__ void single(uint32_t j, bool matched) {
+        if (matched)
+            cnt += 1;
+        else if (!discard && len[j] != 0)
+            cnt += 1;
+    }
     __device__ void to_end(uint32_t, uint32_t) { cnt += 1; }
     __device__ void to_prev(uint32_t, uint32_t) { cnt += 1; }
     __device__ void to_eof(uint32_t) { cnt += 1; }
-    __device__ void span(uint32_t lb, uint32_t jl, uint32_t) { cnt += discard ? 0 : (jl - lb + 1); }
+    __device__ void span(uint32_t lb, uint32_t jl, uint32_t flag_line) {
+        bool none;
+        uint32_t last = ml_span_last(len, lb, jl, flag_line == n, none);
+        if (!none && !discard)
+            cnt += last - lb + 1;
+    }
 };
 
 template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS)
-    ml_state_kernel(MlMode m, const uint8_t* __restrict__ flags, uint64_t n, uint32_t* __restrict__ state,
+    ml_state_kernel(MlMode m, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ len, uint64_t n,
+                    uint32_t* __restrict__ state,
                     uint32_t* __restrict__ cnt, volatile uint64_t* desc, uint32_t* ticket) {
     __shared__ uint64_t s_scan[THREADS / 32 + 1];
     __shared__ uint32_t s_tile;
@@ -665,6 +827,8 @@ __global__ void __launch_bounds__(THREADS)
             state[j] = (s_in << 31) | lb;
             MlCountSink sink;
             sink.discard = m.discard;
+            sink.len = len;
+            sink.n = (uint32_t)n;
             ml_actions(m, fl[k], s_in, lb, (uint32_t)j, (uint32_t)n, sink);
             cnt[j] = sink.cnt;
         }
@@ -672,12 +836,13 @@ __global__ void __launch_bounds__(THREADS)
     }
 }
 
-void launch_ml_state(const MlConfig& cfg, const uint8_t* d_flags, uint64_t n, uint32_t* d_state, uint32_t* d_cnt,
+void launch_ml_state(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_len, uint64_t n, uint32_t* d_state,
+                     uint32_t* d_cnt,
                      uint64_t* d_desc, uint32_t* d_ticket, cudaStream_t st) {
     MlMode m{cfg.blob_start != nullptr, cfg.blob_cont != nullptr, cfg.blob_end != nullptr, cfg.discard != 0};
     uint32_t ntiles = scan_tiles(n + 1);
     ml_state_kernel<kScanThreads, kScanItems>
-        <<<ntiles, kScanThreads, 0, st>>>(m, d_flags, n, d_state, d_cnt, (volatile uint64_t*)d_desc, d_ticket);
+        <<<ntiles, kScanThreads, 0, st>>>(m, d_flags, d_len, n, d_state, d_cnt, (volatile uint64_t*)d_desc, d_ticket);
 }
 
 struct MlEmitSink {
@@ -691,6 +856,7 @@ struct MlEmitSink {
     uint64_t cap;
     uint64_t pos;
     uint32_t is_last; // isLastLog of the line being processed
+    uint32_t n;       // number of lines
     uint32_t matched_events = 0, unmatch_lines = 0;
     __device__ void put(uint32_t o, uint32_t l, uint32_t fl) {
         if (pos < cap) {
@@ -704,7 +870,7 @@ struct MlEmitSink {
         if (matched) {
             put(off[j], len[j], is_last | 2u);
             ++matched_events;
-        } else {
+        } else if (len[j] != 0) {
             ++unmatch_lines;
             if (!discard)
                 put(off[j], len[j], is_last);
@@ -725,10 +891,14 @@ struct MlEmitSink {
         put(o, total_len - o, 1u | 2u);
         ++matched_events;
     }
-    __device__ void span(uint32_t lb, uint32_t jl, uint32_t) {
-        unmatch_lines += jl - lb + 1;
+    __device__ void span(uint32_t lb, uint32_t jl, uint32_t flag_line) {
+        bool none;
+        uint32_t last = ml_span_last(len, lb, jl, flag_line == n, none);
+        if (none)
+            return;
+        unmatch_lines += last - lb + 1;
         if (!discard)
-            for (uint32_t k = lb; k <= jl; ++k)
+            for (uint32_t k = lb; k <= last; ++k)
                 put(off[k], len[k], is_last);
     }
 };
@@ -752,6 +922,7 @@ __global__ void __launch_bounds__(128)
         sink.out_flags = out_flags;
         sink.cap = cap;
         sink.pos = pos[j];
+        sink.n = (uint32_t)n;
         // begin + content.size() == sourceVal.size() (:174); the end-of-buffer element always passes true
         sink.is_last = (j == n) ? 1u : ((off[j] + len[j] == total_len) ? 1u : 0u);
         ml_actions(m, j < n ? flags[j] : 0u, st >> 31, st & 0x7FFFFFFFu, (uint32_t)j, (uint32_t)n, sink);

@@ -62,8 +62,8 @@ struct MlConfig {
 void launch_ml_probe(const MlConfig& cfg, const uint8_t* d_buf, const uint32_t* d_off, const uint32_t* d_len,
                      uint64_t n, uint8_t* d_flags, cudaStream_t st);
 // state scan over n lines + 1 virtual EOF element: d_state[i] = (s_in << 31) | lb_in, d_cnt[i] = output events
-void launch_ml_state(const MlConfig& cfg, const uint8_t* d_flags, uint64_t n, uint32_t* d_state, uint32_t* d_cnt,
-                     uint64_t* d_desc, uint32_t* d_ticket, cudaStream_t st);
+void launch_ml_state(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_len, uint64_t n, uint32_t* d_state,
+                     uint32_t* d_cnt, uint64_t* d_desc, uint32_t* d_ticket, cudaStream_t st);
 // emission: d_pos = exclusive sum of d_cnt; d_counters[0..1] += matched_events, unmatch_lines
 void launch_ml_emit(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len,
                     uint64_t n, uint32_t total_len, const uint32_t* d_state, const uint64_t* d_pos, uint32_t* d_out_off,
