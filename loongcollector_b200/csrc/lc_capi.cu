@@ -79,7 +79,8 @@ struct lc_engine {
     int num_sms = 148;
     int smem_per_block_optin = 0;
     int smem_per_sm = 0;
-    bool force_basic_regex = false; // env LC_B200_REGEX_KERNEL=basic
+    bool force_basic_regex = false;   // env LC_B200_REGEX_KERNEL=basic   (tables in global memory)
+    bool force_generic_regex = false; // env LC_B200_REGEX_KERNEL=generic (smem-staged generic interpreter)
     uint64_t scratch_hint = 0;
     // staging / workspace (grow-only)
     DevBuf in, ev_off, ev_len, out_a, out_b, out_c, out_d, out_e;
@@ -92,23 +93,25 @@ struct lc_engine {
 
 namespace {
 
-cudaError_t engine_blob(lc_engine* e, const lc_regex* r, const void** out) {
+cudaError_t engine_blob(lc_engine* e, const lc_regex* r, const void** out, bool fast = false) {
     *out = nullptr;
     if (!r)
         return cudaSuccess;
-    auto it = e->blobs.find(r->id);
+    const std::vector<uint8_t>& src = fast ? r->res.fast_blob : r->res.blob;
+    const uint64_t key = r->id * 2 + (fast ? 1 : 0);
+    auto it = e->blobs.find(key);
     if (it != e->blobs.end()) {
         *out = it->second;
         return cudaSuccess;
     }
     void* d = nullptr;
-    cudaError_t er = cudaMalloc(&d, r->res.blob.size());
+    cudaError_t er = cudaMalloc(&d, src.size());
     if (er != cudaSuccess)
         return er;
-    er = cudaMemcpyAsync(d, r->res.blob.data(), r->res.blob.size(), cudaMemcpyHostToDevice, e->stream);
+    er = cudaMemcpyAsync(d, src.data(), src.size(), cudaMemcpyHostToDevice, e->stream);
     if (er != cudaSuccess)
         return er;
-    e->blobs[r->id] = d;
+    e->blobs[key] = d;
     *out = d;
     return cudaSuccess;
 }
@@ -193,6 +196,7 @@ int lc_engine_create(int device, lc_engine_t** out) {
     {
         const char* k = getenv("LC_B200_REGEX_KERNEL");
         e->force_basic_regex = k && !strcmp(k, "basic");
+        e->force_generic_regex = k && !strcmp(k, "generic");
     }
     CU_TRY(e->small.ensure(sizeof(Small)));
     CU_TRY(cudaMallocHost(&e->h_small, sizeof(Small)));
@@ -366,7 +370,11 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
     Small* ds = e->small.as<Small>();
     Small* hs = (Small*)e->h_small;
     const bool force_basic = e->force_basic_regex;
-    const uint32_t blob_bytes = h->total_bytes;
+    const bool use_fast = !re->res.fast_blob.empty() && !e->force_generic_regex;
+    const void* d_fast = nullptr;
+    if (use_fast)
+        CU_TRY(engine_blob(e, re, &d_fast, true));
+    const uint32_t blob_bytes = use_fast ? (uint32_t)re->res.fast_blob.size() : h->total_bytes;
     // shared-memory plan of the persistent kernel: one automaton copy per block, the rest holds labels
     const uint32_t per = (h->mode == LC_MODE_TWOPASS && h->rev_label_bytes == 2) ? 2u : 4u;
     const size_t smem_max = (size_t)e->smem_per_block_optin;
@@ -401,7 +409,14 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
             if (h->mode == LC_MODE_TWOPASS)
                 CU_TRY(e->lab.ensure(scratch_words * 4));
             CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof(Small) - offsetof(Small, overflow), e->stream));
-            int er = lck::launch_regex_parse_fast(d_blob, blob_bytes, h->rev_label_bytes, h->ngroups, d_base, d_ev_off,
+            int er;
+            if (use_fast)
+                er = lck::launch_regex_twopass_fast(d_fast, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
+                                                    d_cap_off, d_cap_len, lab_words, threads, grid,
+                                                    e->lab.as<uint32_t>(), scratch_words, &ds->bump, &ds->overflow,
+                                                    &ds->next_batch, e->stream);
+            else
+                er = lck::launch_regex_parse_fast(d_blob, blob_bytes, h->rev_label_bytes, h->ngroups, d_base, d_ev_off,
                                                   d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len, lab_words,
                                                   threads, grid, e->lab.as<uint32_t>(), scratch_words, &ds->bump,
                                                   &ds->overflow, &ds->next_batch, e->stream);

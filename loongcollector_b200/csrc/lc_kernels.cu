@@ -342,21 +342,43 @@ __device__ __forceinline__ bool fwd1_event(const LcProgView& v, const uint32_t* 
 }
 
 
-// Fast two-pass walk (u8 labels, no context kinds).  Input bytes are consumed as 16-byte aligned chunks and the
-// label of position i is stored at virtual index q = i + (address & 15), so that input words and label words
-// share their boundaries: full chunks run 16 fully unrolled steps without any per-byte predicate.
-// sfwd is the forward table re-encoded at staging time: entry = byte offset of the next walker's row
-// (bits 0..21) | action id << 22.
-#define LC_FAST_ROW_MASK 0x3FFFFFu
-#define LC_FAST_ACT_SHIFT 22
+// ---- fast two-pass kernel over the host-built fast blob (lc_tables.h: LcFastHeader) -------------------------
+// Input bytes are consumed as 16-byte aligned chunks and the label of position i is stored at virtual index
+// q = i + (address & 15), so input words and label words share their boundaries: full chunks run 16 fully
+// unrolled steps without per-byte predicates.  Capture actions are rare (2 per group per line) and resolved
+// through a tiny side table so that the divergent branch body stays a handful of instructions.
+struct FastView {
+    const LcFastHeader* h;
+    const uint8_t* rev;
+    const uint8_t* fwd; // byte-addressed
+    const uint32_t* act2;
+    const uint64_t* masks;
+};
+
+__device__ __forceinline__ void fast_action(const FastView& f, uint32_t act, uint32_t pos, uint32_t* slots) {
+    const uint32_t a = f.act2[act];
+    slots[a & 0xFFu] = pos; // every action sets at least one slot
+    const uint32_t sb = (a >> 8) & 0xFFu;
+    if (sb != 0xFFu)
+        slots[sb] = pos;
+    if (a >> 16) {
+        uint64_t m = f.masks[act];
+        while (m) {
+            int s = __ffsll((long long)m) - 1;
+            slots[s] = pos;
+            m &= m - 1;
+        }
+    }
+}
 
 template <class Lab>
-__device__ __forceinline__ bool twopass_event_fast(const LcProgView& v, const uint8_t* __restrict__ rev_byte,
-                                                   const uint8_t* __restrict__ sfwd, const uint4* __restrict__ chunks,
-                                                   uint32_t mis, uint32_t n, Lab lab, uint32_t* slots) {
+__device__ __forceinline__ bool twopass_event_fast(const FastView& f, const uint4* __restrict__ chunks, uint32_t mis,
+                                                   uint32_t n, Lab lab, uint32_t* slots) {
     const uint32_t Q = n + mis;
     const int top = (int)(Q >> 4);
-    const uint32_t rev_start = v.h->rev_start;
+    const uint32_t rev_start = f.h->rev_start;
+    const uint32_t stride = f.h->rev_stride;
+    const uint8_t* __restrict__ rev = f.rev;
     uint32_t d = rev_start;
     // ---- reverse labelling
     for (int qc = top; qc >= 0; --qc) {
@@ -369,13 +391,13 @@ __device__ __forceinline__ bool twopass_event_fast(const LcProgView& v, const ui
 #pragma unroll
             for (int wi = 3; wi >= 0; --wi) {
                 const uint32_t x = w[wi];
-                d = rev_byte[d * 256 + (x >> 24)];
+                d = rev[d * stride + (x >> 24)];
                 uint32_t lw = d << 24;
-                d = rev_byte[d * 256 + ((x >> 16) & 0xFFu)];
+                d = rev[d * stride + ((x >> 16) & 0xFFu)];
                 lw |= d << 16;
-                d = rev_byte[d * 256 + ((x >> 8) & 0xFFu)];
+                d = rev[d * stride + ((x >> 8) & 0xFFu)];
                 lw |= d << 8;
-                d = rev_byte[d * 256 + (x & 0xFFu)];
+                d = rev[d * stride + (x & 0xFFu)];
                 lw |= d;
                 lab.st(qc * 4 + wi, lw);
             }
@@ -392,7 +414,7 @@ __device__ __forceinline__ bool twopass_event_fast(const LcProgView& v, const ui
                         lw |= rev_start << (8 * k);
                         any = true;
                     } else if (q < Q && q >= mis) {
-                        d = rev_byte[d * 256 + ((x >> (8 * k)) & 0xFFu)];
+                        d = rev[d * stride + ((x >> (8 * k)) & 0xFFu)];
                         lw |= d << (8 * k);
                         any = true;
                     }
@@ -405,7 +427,8 @@ __device__ __forceinline__ bool twopass_event_fast(const LcProgView& v, const ui
             return false;
     }
     // ---- guided forward walk; d == label of position 0
-    if (*reinterpret_cast<const uint32_t*>(sfwd + d * 4) == LC_NONE_ENTRY)
+    const uint8_t* __restrict__ fwd = f.fwd;
+    if (*reinterpret_cast<const uint32_t*>(fwd + d * 4) == LC_NONE_ENTRY)
         return false;
     uint32_t row = 0; // byte offset of the current walker's row (START)
     for (int qc = 0; qc <= top; ++qc) {
@@ -417,9 +440,9 @@ __device__ __forceinline__ bool twopass_event_fast(const LcProgView& v, const ui
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t l4 = k == 0 ? ((lw << 2) & 0x3FCu) : ((lw >> (8 * k - 2)) & 0x3FCu);
-                    const uint32_t e = *reinterpret_cast<const uint32_t*>(sfwd + row + l4);
+                    const uint32_t e = *reinterpret_cast<const uint32_t*>(fwd + row + l4);
                     if (e >> LC_FAST_ACT_SHIFT)
-                        lc_apply_action(v, e >> LC_FAST_ACT_SHIFT, lo + wi * 4 + k - mis, slots);
+                        fast_action(f, e >> LC_FAST_ACT_SHIFT, lo + wi * 4 + k - mis, slots);
                     row = e & LC_FAST_ROW_MASK;
                 }
             }
@@ -435,9 +458,9 @@ __device__ __forceinline__ bool twopass_event_fast(const LcProgView& v, const ui
                     const uint32_t q = q0 + k;
                     if (q >= mis && q <= Q) {
                         const uint32_t l4 = ((lw >> (8 * k)) & 0xFFu) * 4;
-                        const uint32_t e = *reinterpret_cast<const uint32_t*>(sfwd + row + l4);
+                        const uint32_t e = *reinterpret_cast<const uint32_t*>(fwd + row + l4);
                         if (e >> LC_FAST_ACT_SHIFT)
-                            lc_apply_action(v, e >> LC_FAST_ACT_SHIFT, q - mis, slots);
+                            fast_action(f, e >> LC_FAST_ACT_SHIFT, q - mis, slots);
                         row = e & LC_FAST_ROW_MASK;
                     }
                 }
@@ -445,6 +468,94 @@ __device__ __forceinline__ bool twopass_event_fast(const LcProgView& v, const ui
         }
     }
     return true;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+    regex_twopass_fast_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, const uint8_t* __restrict__ base,
+                              const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
+                              uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
+                              uint32_t* __restrict__ cap_len, uint32_t lab_words, uint32_t* __restrict__ scratch,
+                              unsigned long long scratch_words, unsigned long long* bump, uint32_t* overflow,
+                              unsigned long long* next_batch) {
+    extern __shared__ uint4 smem[];
+    for (uint32_t k = threadIdx.x; k < blob_bytes / 16; k += blockDim.x)
+        smem[k] = __ldg(blob + k);
+    __syncthreads();
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(smem);
+    FastView f;
+    f.h = reinterpret_cast<const LcFastHeader*>(sb);
+    f.rev = sb + f.h->off_rev;
+    f.fwd = sb + f.h->off_fwd;
+    f.act2 = reinterpret_cast<const uint32_t*>(sb + f.h->off_act2);
+    f.masks = reinterpret_cast<const uint64_t*>(sb + f.h->off_masks);
+    const uint32_t G = f.h->ngroups;
+    uint32_t* lab_base = reinterpret_cast<uint32_t*>(smem) + blob_bytes / 4;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (;;) {
+        unsigned long long batch = 0;
+        if (lane == 0)
+            batch = atomicAdd(next_batch, 32ull);
+        batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+        if (batch >= n)
+            break;
+        const uint64_t i = batch + lane;
+        if (i >= n)
+            continue;
+        const uint32_t off = ev_off[i], len = ev_len[i];
+        uint32_t slots[2 * LC_MAX_GROUPS];
+        for (uint32_t k = 0; k < 2 * G; ++k)
+            slots[k] = LC_SLOT_UNSET;
+        const uint64_t a16 = (uint64_t)(uintptr_t)(base + off);
+        const uint32_t mis16 = (uint32_t)(a16 & 15u);
+        const uint4* chunks = reinterpret_cast<const uint4*>(a16 - mis16);
+        const uint32_t need = (len + mis16) / 4 + 1;
+        bool ok;
+        if (need <= lab_words) {
+            LabSmem lab{lab_base + (size_t)wid * lab_words * 32 + lane};
+            ok = twopass_event_fast(f, chunks, mis16, len, lab, slots);
+        } else {
+            unsigned long long at = atomicAdd(bump, (unsigned long long)need);
+            if (at + need > scratch_words) {
+                atomicExch(overflow, 1u);
+                ok = false;
+            } else {
+                LabGlobal lab{scratch + at};
+                ok = twopass_event_fast(f, chunks, mis16, len, lab, slots);
+            }
+        }
+        uint8_t st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
+        status[i] = st;
+        uint32_t* co = cap_off + i * G;
+        uint32_t* cl = cap_len + i * G;
+        for (uint32_t g = 0; g < G; ++g) {
+            uint32_t o = 0, l = 0;
+            if (st == 0) {
+                lc_slots_to_cap(slots, g, len, &o, &l);
+                o += off;
+            }
+            co[g] = o;
+            cl[g] = l;
+        }
+    }
+}
+
+int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, const uint8_t* d_base,
+                              const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                              uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t lab_words,
+                              uint32_t threads, uint32_t grid, uint32_t* d_scratch, uint64_t scratch_words,
+                              unsigned long long* d_bump, uint32_t* d_overflow, unsigned long long* d_next_batch,
+                              cudaStream_t st) {
+    if (!n)
+        return 0;
+    size_t smem = blob_bytes + (size_t)(threads / 32) * lab_words * 32 * 4;
+    cudaError_t er =
+        cudaFuncSetAttribute(regex_twopass_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (er != cudaSuccess)
+        return (int)er;
+    regex_twopass_fast_kernel<<<grid, threads, smem, st>>>((const uint4*)d_fast_blob, blob_bytes, d_base, d_ev_off,
+                                                           d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len, lab_words,
+                                                           d_scratch, scratch_words, d_bump, d_overflow, d_next_batch);
+    return (int)cudaGetLastError();
 }
 
 template <class LabT>
@@ -462,21 +573,6 @@ __global__ void __launch_bounds__(1024, 1)
         smem[k] = __ldg(blob + k);
     __syncthreads();
     const LcProgView v = lc_view(smem);
-    // fast walk: u8 labels, no context kinds, row offsets and action ids fit the packed entry
-    const bool fast = v.h->mode == LC_MODE_TWOPASS && sizeof(LabT) == 1 && v.h->npc == 1 &&
-                      (uint64_t)v.h->nw * v.h->fwd_cols * 4 <= LC_FAST_ROW_MASK && v.h->nact < 1024;
-    if (fast) {
-        uint32_t* f = const_cast<uint32_t*>(v.fwd);
-        const uint32_t cells = v.h->nw * v.h->fwd_cols, cols = v.h->fwd_cols;
-        for (uint32_t k = threadIdx.x; k < cells; k += blockDim.x) {
-            uint32_t e = f[k];
-            if (e != LC_NONE_ENTRY) {
-                uint32_t nxt = LC_ENTRY_NEXT(e);
-                f[k] = (nxt == 0xFFFFu ? 0u : nxt * cols * 4) | (LC_ENTRY_ACT(e) << LC_FAST_ACT_SHIFT);
-            }
-        }
-        __syncthreads();
-    }
     uint32_t* lab_base = reinterpret_cast<uint32_t*>(smem) + blob_bytes / 4;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // persistent warps: each warp claims batches of 32 consecutive events from a global counter
@@ -509,18 +605,10 @@ __global__ void __launch_bounds__(1024, 1)
         const LabT* rev_byte =
             reinterpret_cast<const LabT*>(reinterpret_cast<const uint8_t*>(smem) + v.h->off_rev_byte);
         constexpr uint32_t PER = 4 / sizeof(LabT);
-        // label words: the fast walk shifts labels by the 16-byte misalignment of the event
-        const uint64_t a16 = (uint64_t)(uintptr_t)(base + off);
-        const uint32_t mis16 = (uint32_t)(a16 & 15u);
-        const uint4* chunks = reinterpret_cast<const uint4*>(a16 - mis16);
-        const uint32_t need = fast ? ((len + mis16) / 4 + 1) : (len / PER + 1);
+        const uint32_t need = len / PER + 1; // words for labels 0..len
         if (need <= lab_words) {
             LabSmem lab{lab_base + (size_t)wid * lab_words * 32 + lane};
-            if (fast)
-                ok = twopass_event_fast(v, reinterpret_cast<const uint8_t*>(rev_byte),
-                                        reinterpret_cast<const uint8_t*>(v.fwd), chunks, mis16, len, lab, slots);
-            else
-                ok = twopass_event<LabT>(v, rev_byte, abase, a0, len, lab, slots);
+            ok = twopass_event<LabT>(v, rev_byte, abase, a0, len, lab, slots);
         } else {
             unsigned long long at = atomicAdd(bump, (unsigned long long)need);
             if (at + need > scratch_words) {
@@ -528,11 +616,7 @@ __global__ void __launch_bounds__(1024, 1)
                 ok = false;
             } else {
                 LabGlobal lab{scratch + at};
-                if (fast)
-                    ok = twopass_event_fast(v, reinterpret_cast<const uint8_t*>(rev_byte),
-                                            reinterpret_cast<const uint8_t*>(v.fwd), chunks, mis16, len, lab, slots);
-                else
-                    ok = twopass_event<LabT>(v, rev_byte, abase, a0, len, lab, slots);
+                ok = twopass_event<LabT>(v, rev_byte, abase, a0, len, lab, slots);
             }
         }
     }

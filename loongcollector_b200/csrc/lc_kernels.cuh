@@ -47,6 +47,14 @@ int launch_regex_parse_fast(const void* d_blob, uint32_t blob_bytes, uint32_t re
                             uint64_t scratch_words, unsigned long long* d_bump, uint32_t* d_overflow,
                             unsigned long long* d_next_batch, cudaStream_t st);
 
+// a3 fastest path: two-pass automaton in the host-built fast layout (LcFastHeader); same launch contract as above.
+int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, const uint8_t* d_base,
+                              const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                              uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t lab_words,
+                              uint32_t threads, uint32_t grid, uint32_t* d_scratch, uint64_t scratch_words,
+                              unsigned long long* d_bump, uint32_t* d_overflow, unsigned long long* d_next_batch,
+                              cudaStream_t st);
+
 // anchored prefix probe, one bool per event
 void launch_prefix_match(const void* d_blob, const uint8_t* d_base, const uint32_t* d_ev_off,
                          const uint32_t* d_ev_len, uint64_t n, uint8_t* d_out, cudaStream_t st);

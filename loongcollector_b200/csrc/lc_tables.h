@@ -69,6 +69,34 @@ struct LcRegexHeader {
     uint32_t reserved[7];
 };
 
+// ---- "fast blob": kernel-ready re-layout of a TWOPASS automaton without context kinds and with <= 256
+// reverse states (the common case for log patterns).  Built once per pattern on the host.
+//   rev   u8  [rev_nstates][rev_stride]   reverse transition by raw byte; rev_stride = 260 so that rows are skewed
+//                                         across shared-memory banks (bank = (state + byte/4) mod 32)
+//   fwd   u32 [nw][fwd_cols]              entry = byte offset of the next walker's row | action id << 22;
+//                                         fwd_cols is padded to an odd number of words
+//   act2  u32 [nact]                      slot_a | slot_b << 8 | complex << 16   (0xFF = no slot)
+//   masks u64 [nact]                      full save mask (used when complex)
+#define LC_FAST_MAGIC 0x4C434658u /* 'LCFX' */
+#define LC_FAST_ROW_MASK 0x3FFFFFu
+#define LC_FAST_ACT_SHIFT 22
+struct LcFastHeader {
+    uint32_t magic;
+    uint32_t total_bytes;
+    uint32_t ngroups;
+    uint32_t rev_start;
+    uint32_t rev_stride;
+    uint32_t fwd_cols;
+    uint32_t nw;
+    uint32_t nact;
+    uint32_t off_rev;
+    uint32_t off_fwd;
+    uint32_t off_act2;
+    uint32_t off_masks;
+    uint32_t reserved[4];
+};
+
 #ifdef __cplusplus
+static_assert(sizeof(LcFastHeader) % 16 == 0, "fast header must keep 16B alignment");
 static_assert(sizeof(LcRegexHeader) % 16 == 0, "header must keep 16B alignment of what follows");
 #endif

@@ -306,3 +306,19 @@ def test_delim_matches_oracle(eng, sep, quote, extend, allow_short):
         want = orc.delim_parse_batch(base, off, ln, sep, quote, nkeys, extend, allow_short, mf)
         for g, w, name in zip(got, want, ("status", "nfields", "f_off", "f_len", "f_dq")):
             assert np.array_equal(g, w), (name, sep, quote, extend, allow_short, nkeys, mf)
+
+
+# ------------------------------------------------------------------------------------------- kernel variants
+@pytest.mark.parametrize("variant", ["basic", "generic"])
+def test_regex_kernel_variants_agree(variant, monkeypatch):
+    """The baseline (tables in global memory) and generic (smem interpreter) kernels stay parity-checked too."""
+    lc = _lc()
+    monkeypatch.setenv("LC_B200_REGEX_KERNEL", variant)
+    e = lc.Engine(0)
+    try:
+        rng = random.Random(17)
+        lines = _noise_lines(rng, 1500) + _nginx_lines(rng, 1500) + [b"x" * 5000, b"[" + b"y" * 3000 + b"] [z] q"]
+        for pattern in PATTERNS[:6]:
+            _check_parse(e, pattern, lines)
+    finally:
+        e.close()
