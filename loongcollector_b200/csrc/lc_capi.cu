@@ -375,6 +375,8 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
     if (use_fast)
         CU_TRY(engine_blob(e, re, &d_fast, true));
     const uint32_t blob_bytes = use_fast ? (uint32_t)re->res.fast_blob.size() : h->total_bytes;
+    const bool fast_multi =
+        use_fast && reinterpret_cast<const LcFastHeader*>(re->res.fast_blob.data())->reserved[0] != 0;
     // shared-memory plan of the persistent kernel: one automaton copy per block, the rest holds labels
     const uint32_t per = (h->mode == LC_MODE_TWOPASS && h->rev_label_bytes == 2) ? 2u : 4u;
     const size_t smem_max = (size_t)e->smem_per_block_optin;
@@ -386,15 +388,18 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
             if (lab_words < 16)
                 lab_words = 16;
             size_t budget = smem_max - blob_bytes - 1024;
-            uint32_t warps = (uint32_t)(budget / ((size_t)lab_words * 128));
+            // per warp: labels (lab_words * 128 B) + capture slots of its 32 threads (fast layout only)
+            size_t slot_bytes = use_fast ? (size_t)32 * lck::fast_slot_pitch(h->ngroups) * 4 : 0;
+            uint32_t warps = (uint32_t)(budget / ((size_t)lab_words * 128 + slot_bytes));
             if (warps < 4) { // very long average lines: keep 4 warps and let long events use the global slab
                 warps = 4;
-                lab_words = (uint32_t)(budget / (4 * 128));
+                lab_words = (uint32_t)((budget / 4 - slot_bytes) / 128);
             }
             if (warps > 32)
                 warps = 32;
             threads = warps * 32;
-            if (warps <= 16 && 2 * (blob_bytes + (size_t)warps * lab_words * 128 + 1024) <= (size_t)e->smem_per_sm)
+            if (warps <= 16 &&
+                2 * (blob_bytes + (size_t)warps * (lab_words * 128 + slot_bytes) + 1024) <= (size_t)e->smem_per_sm)
                 blocks_per_sm = 2;
         } else {
             threads = 512;
@@ -411,8 +416,8 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
             CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof(Small) - offsetof(Small, overflow), e->stream));
             int er;
             if (use_fast)
-                er = lck::launch_regex_twopass_fast(d_fast, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
-                                                    d_cap_off, d_cap_len, lab_words, threads, grid,
+                er = lck::launch_regex_twopass_fast(d_fast, blob_bytes, fast_multi, h->ngroups, d_base, d_ev_off, d_ev_len,
+                                                    n, nkeys, d_status, d_cap_off, d_cap_len, lab_words, threads, grid,
                                                     e->lab.as<uint32_t>(), scratch_words, &ds->bump, &ds->overflow,
                                                     &ds->next_batch, e->stream);
             else

@@ -345,60 +345,71 @@ __device__ __forceinline__ bool fwd1_event(const LcProgView& v, const uint32_t* 
 // ---- fast two-pass kernel over the host-built fast blob (lc_tables.h: LcFastHeader) -------------------------
 // Input bytes are consumed as 16-byte aligned chunks and the label of position i is stored at virtual index
 // q = i + (address & 15), so input words and label words share their boundaries: full chunks run 16 fully
-// unrolled steps without per-byte predicates.  Capture actions are rare (2 per group per line) and resolved
-// through a tiny side table so that the divergent branch body stays a handful of instructions.
+// unrolled steps without per-byte predicates.
+//   reverse step : b = PRMT(word) ; d4 = rev[d4 * 65 + b] ; lw = lw * 256 + d4          (labels pre-multiplied by 4)
+//   forward step : addr = PRMT(entry, lw) ; entry = fwd[addr] ; if (entry & 0xFF) slots[..] = pos   (predicated)
+// Capture boundaries are rare per line but happen on SOME lane at almost every step of a warp, so they must not
+// branch: a single-slot boundary is one predicated local store; only multi-slot boundaries take a branch.
 struct FastView {
     const LcFastHeader* h;
     const uint8_t* rev;
-    const uint8_t* fwd; // byte-addressed
-    const uint32_t* act2;
+    const uint8_t* fwd; // byte-addressed, 256-byte rows
+    const uint8_t* cx;
     const uint64_t* masks;
 };
 
-__device__ __forceinline__ void fast_action(const FastView& f, uint32_t act, uint32_t pos, uint32_t* slots) {
-    const uint32_t a = f.act2[act];
-    slots[a & 0xFFu] = pos; // every action sets at least one slot
-    const uint32_t sb = (a >> 8) & 0xFFu;
-    if (sb != 0xFFu)
-        slots[sb] = pos;
-    if (a >> 16) {
-        uint64_t m = f.masks[act];
-        while (m) {
-            int s = __ffsll((long long)m) - 1;
-            slots[s] = pos;
-            m &= m - 1;
-        }
+__device__ __noinline__ void fast_multi_action(const FastView& f, uint32_t addr, uint32_t pos, uint32_t* slots) {
+    uint64_t m = f.masks[f.cx[addr >> 2]];
+    while (m) {
+        int s = __ffsll((long long)m) - 1;
+        slots[s] = pos;
+        m &= m - 1;
     }
 }
 
-template <class Lab>
+// slots live in shared memory ([thread][slot], odd word pitch): a capture boundary is one predicated STS
+#define LC_FWD_STEP(K, POS)                                                                                           \
+    {                                                                                                                  \
+        const uint32_t addr = __byte_perm(e, lw, 0x2214 + (K)) /* (row << 8) | label4; entry byte 2 is always 0 */;                                                        \
+        e = *reinterpret_cast<const uint32_t*>(fwd + addr);                                                            \
+        const uint32_t sl = e & 0xFFu;                                                                                 \
+        if (sl)                                                                                                        \
+            *reinterpret_cast<uint32_t*>(slots_m4 + sl) = (POS);                                                       \
+        if (MULTI && (int32_t)e < 0)                                                                                   \
+            fast_multi_action(f, addr, (POS), reinterpret_cast<uint32_t*>(slots_m4 + 4));                              \
+    }
+
+template <bool MULTI, class Lab>
 __device__ __forceinline__ bool twopass_event_fast(const FastView& f, const uint4* __restrict__ chunks, uint32_t mis,
-                                                   uint32_t n, Lab lab, uint32_t* slots) {
+                                                   uint32_t n, Lab lab, uint8_t* slots_m4 /* slot area - 4 bytes */) {
     const uint32_t Q = n + mis;
     const int top = (int)(Q >> 4);
-    const uint32_t rev_start = f.h->rev_start;
-    const uint32_t stride = f.h->rev_stride;
+    const uint32_t rev_start4 = f.h->rev_start4;
     const uint8_t* __restrict__ rev = f.rev;
-    uint32_t d = rev_start;
-    // ---- reverse labelling
+    uint32_t d4 = rev_start4;
+    // ---- reverse labelling (software-pipelined chunk loads)
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if ((uint32_t)top * 16 < Q)
+        nxt = __ldg(chunks + top);
     for (int qc = top; qc >= 0; --qc) {
         const uint32_t lo = (uint32_t)qc * 16;
-        uint4 vv = make_uint4(0, 0, 0, 0);
-        if (lo < Q)
-            vv = __ldg(chunks + qc);
+        const uint4 vv = nxt;
+        if (qc > 0)
+            nxt = __ldg(chunks + qc - 1);
         const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
         if (lo >= mis && lo + 15 < Q) {
 #pragma unroll
             for (int wi = 3; wi >= 0; --wi) {
                 const uint32_t x = w[wi];
-                d = rev[d * stride + (x >> 24)];
-                uint32_t lw = d << 24;
-                d = rev[d * stride + ((x >> 16) & 0xFFu)];
-                lw |= d << 16;
-                d = rev[d * stride + ((x >> 8) & 0xFFu)];
-                lw |= d << 8;
-                d = rev[d * stride + (x & 0xFFu)];
-                lw |= d;
+                uint32_t lw;
+                d4 = rev[d4 * 65 + __byte_perm(x, 0, 0x4443)];
+                lw = d4;
+                d4 = rev[d4 * 65 + __byte_perm(x, 0, 0x4442)];
+                lw = lw * 256 + d4;
+                d4 = rev[d4 * 65 + __byte_perm(x, 0, 0x4441)];
+                lw = lw * 256 + d4;
+                d4 = rev[d4 * 65 + __byte_perm(x, 0, 0x4440)];
+                lw = lw * 256 + d4;
                 lab.st(qc * 4 + wi, lw);
             }
         } else {
@@ -411,11 +422,11 @@ __device__ __forceinline__ bool twopass_event_fast(const FastView& f, const uint
                 for (int k = 3; k >= 0; --k) {
                     const uint32_t q = lo + wi * 4 + k;
                     if (q == Q) {
-                        lw |= rev_start << (8 * k);
+                        lw |= rev_start4 << (8 * k);
                         any = true;
                     } else if (q < Q && q >= mis) {
-                        d = rev[d * stride + ((x >> (8 * k)) & 0xFFu)];
-                        lw |= d << (8 * k);
+                        d4 = rev[d4 * 65 + ((x >> (8 * k)) & 0xFFu)];
+                        lw |= d4 << (8 * k);
                         any = true;
                     }
                 }
@@ -423,28 +434,25 @@ __device__ __forceinline__ bool twopass_event_fast(const FastView& f, const uint
                     lab.st(qc * 4 + wi, lw);
             }
         }
-        if (d == LC_REV_DEAD)
+        if (d4 == 0)
             return false;
     }
-    // ---- guided forward walk; d == label of position 0
+    // ---- guided forward walk; d4 == 4 * label of position 0
     const uint8_t* __restrict__ fwd = f.fwd;
-    if (*reinterpret_cast<const uint32_t*>(fwd + d * 4) == LC_NONE_ENTRY)
+    if (*reinterpret_cast<const uint32_t*>(fwd + d4) == LC_NONE_ENTRY)
         return false;
-    uint32_t row = 0; // byte offset of the current walker's row (START)
+    uint32_t e = 0; // current entry: row index in bits 8.., START row = 0
     for (int qc = 0; qc <= top; ++qc) {
         const uint32_t lo = (uint32_t)qc * 16;
+        const uint32_t pos0 = lo - mis;
         if (lo >= mis && lo + 15 <= Q) {
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
                 const uint32_t lw = lab.ld(qc * 4 + wi);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t l4 = k == 0 ? ((lw << 2) & 0x3FCu) : ((lw >> (8 * k - 2)) & 0x3FCu);
-                    const uint32_t e = *reinterpret_cast<const uint32_t*>(fwd + row + l4);
-                    if (e >> LC_FAST_ACT_SHIFT)
-                        fast_action(f, e >> LC_FAST_ACT_SHIFT, lo + wi * 4 + k - mis, slots);
-                    row = e & LC_FAST_ROW_MASK;
-                }
+                LC_FWD_STEP(0, pos0 + wi * 4 + 0)
+                LC_FWD_STEP(1, pos0 + wi * 4 + 1)
+                LC_FWD_STEP(2, pos0 + wi * 4 + 2)
+                LC_FWD_STEP(3, pos0 + wi * 4 + 3)
             }
         } else {
 #pragma unroll
@@ -456,13 +464,8 @@ __device__ __forceinline__ bool twopass_event_fast(const FastView& f, const uint
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t q = q0 + k;
-                    if (q >= mis && q <= Q) {
-                        const uint32_t l4 = ((lw >> (8 * k)) & 0xFFu) * 4;
-                        const uint32_t e = *reinterpret_cast<const uint32_t*>(fwd + row + l4);
-                        if (e >> LC_FAST_ACT_SHIFT)
-                            fast_action(f, e >> LC_FAST_ACT_SHIFT, q - mis, slots);
-                        row = e & LC_FAST_ROW_MASK;
-                    }
+                    if (q >= mis && q <= Q)
+                        LC_FWD_STEP(k, q - mis)
                 }
             }
         }
@@ -470,13 +473,14 @@ __device__ __forceinline__ bool twopass_event_fast(const FastView& f, const uint
     return true;
 }
 
+template <bool MULTI>
 __global__ void __launch_bounds__(1024, 1)
     regex_twopass_fast_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, const uint8_t* __restrict__ base,
                               const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
                               uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
-                              uint32_t* __restrict__ cap_len, uint32_t lab_words, uint32_t* __restrict__ scratch,
-                              unsigned long long scratch_words, unsigned long long* bump, uint32_t* overflow,
-                              unsigned long long* next_batch) {
+                              uint32_t* __restrict__ cap_len, uint32_t lab_words, uint32_t slot_pitch,
+                              uint32_t* __restrict__ scratch, unsigned long long scratch_words,
+                              unsigned long long* bump, uint32_t* overflow, unsigned long long* next_batch) {
     extern __shared__ uint4 smem[];
     for (uint32_t k = threadIdx.x; k < blob_bytes / 16; k += blockDim.x)
         smem[k] = __ldg(blob + k);
@@ -486,10 +490,13 @@ __global__ void __launch_bounds__(1024, 1)
     f.h = reinterpret_cast<const LcFastHeader*>(sb);
     f.rev = sb + f.h->off_rev;
     f.fwd = sb + f.h->off_fwd;
-    f.act2 = reinterpret_cast<const uint32_t*>(sb + f.h->off_act2);
+    f.cx = sb + f.h->off_cx;
     f.masks = reinterpret_cast<const uint64_t*>(sb + f.h->off_masks);
     const uint32_t G = f.h->ngroups;
+    // shared memory: [blob][labels: warps x lab_words x 32 words][slots: threads x slot_pitch words]
     uint32_t* lab_base = reinterpret_cast<uint32_t*>(smem) + blob_bytes / 4;
+    uint32_t* slots = lab_base + (size_t)(blockDim.x / 32) * lab_words * 32 + (size_t)threadIdx.x * slot_pitch;
+    uint8_t* slots_m4 = reinterpret_cast<uint8_t*>(slots) - 4;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (;;) {
         unsigned long long batch = 0;
@@ -502,7 +509,6 @@ __global__ void __launch_bounds__(1024, 1)
         if (i >= n)
             continue;
         const uint32_t off = ev_off[i], len = ev_len[i];
-        uint32_t slots[2 * LC_MAX_GROUPS];
         for (uint32_t k = 0; k < 2 * G; ++k)
             slots[k] = LC_SLOT_UNSET;
         const uint64_t a16 = (uint64_t)(uintptr_t)(base + off);
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(1024, 1)
         bool ok;
         if (need <= lab_words) {
             LabSmem lab{lab_base + (size_t)wid * lab_words * 32 + lane};
-            ok = twopass_event_fast(f, chunks, mis16, len, lab, slots);
+            ok = twopass_event_fast<MULTI>(f, chunks, mis16, len, lab, slots_m4);
         } else {
             unsigned long long at = atomicAdd(bump, (unsigned long long)need);
             if (at + need > scratch_words) {
@@ -520,7 +526,7 @@ __global__ void __launch_bounds__(1024, 1)
                 ok = false;
             } else {
                 LabGlobal lab{scratch + at};
-                ok = twopass_event_fast(f, chunks, mis16, len, lab, slots);
+                ok = twopass_event_fast<MULTI>(f, chunks, mis16, len, lab, slots_m4);
             }
         }
         uint8_t st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
@@ -539,22 +545,23 @@ __global__ void __launch_bounds__(1024, 1)
     }
 }
 
-int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, const uint8_t* d_base,
-                              const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
-                              uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t lab_words,
-                              uint32_t threads, uint32_t grid, uint32_t* d_scratch, uint64_t scratch_words,
-                              unsigned long long* d_bump, uint32_t* d_overflow, unsigned long long* d_next_batch,
-                              cudaStream_t st) {
+int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, bool multi, uint32_t ngroups,
+                              const uint8_t* d_base, const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n,
+                              uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
+                              uint32_t lab_words, uint32_t threads, uint32_t grid, uint32_t* d_scratch,
+                              uint64_t scratch_words, unsigned long long* d_bump, uint32_t* d_overflow,
+                              unsigned long long* d_next_batch, cudaStream_t st) {
     if (!n)
         return 0;
-    size_t smem = blob_bytes + (size_t)(threads / 32) * lab_words * 32 * 4;
-    cudaError_t er =
-        cudaFuncSetAttribute(regex_twopass_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const uint32_t slot_pitch = fast_slot_pitch(ngroups);
+    size_t smem = fast_smem_bytes(blob_bytes, ngroups, lab_words, threads);
+    auto k = multi ? regex_twopass_fast_kernel<true> : regex_twopass_fast_kernel<false>;
+    cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (er != cudaSuccess)
         return (int)er;
-    regex_twopass_fast_kernel<<<grid, threads, smem, st>>>((const uint4*)d_fast_blob, blob_bytes, d_base, d_ev_off,
-                                                           d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len, lab_words,
-                                                           d_scratch, scratch_words, d_bump, d_overflow, d_next_batch);
+    k<<<grid, threads, smem, st>>>((const uint4*)d_fast_blob, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
+                                   d_cap_off, d_cap_len, lab_words, slot_pitch, d_scratch, scratch_words, d_bump,
+                                   d_overflow, d_next_batch);
     return (int)cudaGetLastError();
 }
 

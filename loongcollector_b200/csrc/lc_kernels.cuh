@@ -47,13 +47,18 @@ int launch_regex_parse_fast(const void* d_blob, uint32_t blob_bytes, uint32_t re
                             uint64_t scratch_words, unsigned long long* d_bump, uint32_t* d_overflow,
                             unsigned long long* d_next_batch, cudaStream_t st);
 
-// a3 fastest path: two-pass automaton in the host-built fast layout (LcFastHeader); same launch contract as above.
-int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, const uint8_t* d_base,
-                              const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
-                              uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t lab_words,
-                              uint32_t threads, uint32_t grid, uint32_t* d_scratch, uint64_t scratch_words,
-                              unsigned long long* d_bump, uint32_t* d_overflow, unsigned long long* d_next_batch,
-                              cudaStream_t st);
+// a3 fastest path: two-pass automaton in the host-built fast layout (LcFastHeader).  Shared memory per block =
+// blob + labels (threads/32 * lab_words * 128 B) + capture slots (threads * slot_pitch * 4 B).
+inline uint32_t fast_slot_pitch(uint32_t ngroups) { return (2 * ngroups + 1) | 1u; } // odd word pitch
+inline size_t fast_smem_bytes(uint32_t blob_bytes, uint32_t ngroups, uint32_t lab_words, uint32_t threads) {
+    return (size_t)blob_bytes + (size_t)(threads / 32) * lab_words * 128 + (size_t)threads * fast_slot_pitch(ngroups) * 4;
+}
+int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, bool multi, uint32_t ngroups,
+                              const uint8_t* d_base, const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n,
+                              uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
+                              uint32_t lab_words, uint32_t threads, uint32_t grid, uint32_t* d_scratch,
+                              uint64_t scratch_words, unsigned long long* d_bump, uint32_t* d_overflow,
+                              unsigned long long* d_next_batch, cudaStream_t st);
 
 // anchored prefix probe, one bool per event
 void launch_prefix_match(const void* d_blob, const uint8_t* d_base, const uint32_t* d_ev_off,

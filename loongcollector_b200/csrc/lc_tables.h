@@ -69,31 +69,36 @@ struct LcRegexHeader {
     uint32_t reserved[7];
 };
 
-// ---- "fast blob": kernel-ready re-layout of a TWOPASS automaton without context kinds and with <= 256
-// reverse states (the common case for log patterns).  Built once per pattern on the host.
-//   rev   u8  [rev_nstates][rev_stride]   reverse transition by raw byte; rev_stride = 260 so that rows are skewed
-//                                         across shared-memory banks (bank = (state + byte/4) mod 32)
-//   fwd   u32 [nw][fwd_cols]              entry = byte offset of the next walker's row | action id << 22;
-//                                         fwd_cols is padded to an odd number of words
-//   act2  u32 [nact]                      slot_a | slot_b << 8 | complex << 16   (0xFF = no slot)
-//   masks u64 [nact]                      full save mask (used when complex)
+// ---- "fast blob": kernel-ready re-layout of a TWOPASS automaton without context kinds, with <= 63 reverse
+// states, <= 255 walkers and <= 31 capture groups (the common case for log patterns).  Built once per pattern
+// on the host; the kernel copies it verbatim into shared memory.
+//   rev   u8  [rev_nstates][260]   reverse transition by raw byte, value = next_state * 4 (labels are stored
+//                                  pre-multiplied so that they index 32-bit forward entries directly).  The 260-byte
+//                                  row pitch skews rows across shared-memory banks: bank = (state + byte/4) mod 32.
+//   fwd   u32 [nw][64]             256-byte rows.  entry = slot_byte | next_row_index << 8 | multi << 31 where
+//                                  slot_byte: 0 = no capture boundary, 4*slot+4 = set that one slot;
+//                                  multi = several slots are set (action id in cx; reserved[0] = has_multi).
+//                                  address of the next look-up = (entry & 0x00FFFF00) | label  -- one PRMT.
+//   cx    u8  [nw][64]             action id of multi-slot entries (0 elsewhere)
+//   masks u64 [nact]               save masks of the actions
 #define LC_FAST_MAGIC 0x4C434658u /* 'LCFX' */
-#define LC_FAST_ROW_MASK 0x3FFFFFu
-#define LC_FAST_ACT_SHIFT 22
+#define LC_FAST_REV_PITCH 260u
+#define LC_FAST_MAX_REV 63u
+#define LC_FAST_MAX_WALKERS 255u
+#define LC_FAST_MAX_GROUPS 31u
 struct LcFastHeader {
     uint32_t magic;
     uint32_t total_bytes;
     uint32_t ngroups;
-    uint32_t rev_start;
-    uint32_t rev_stride;
-    uint32_t fwd_cols;
+    uint32_t rev_start4; // start state * 4
+    uint32_t nrev;
     uint32_t nw;
     uint32_t nact;
     uint32_t off_rev;
     uint32_t off_fwd;
-    uint32_t off_act2;
+    uint32_t off_cx;
     uint32_t off_masks;
-    uint32_t reserved[4];
+    uint32_t reserved[5];
 };
 
 #ifdef __cplusplus

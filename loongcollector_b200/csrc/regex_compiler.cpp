@@ -1466,61 +1466,58 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
         res.supported = true;
 
         // ---- kernel-ready "fast" layout (see lc_tables.h)
-        if (mode == LC_MODE_TWOPASS && npc == 1 && nD <= 256 && actions.size() < 1024) {
-            const uint32_t stride = 260;
-            uint32_t cols_p = (uint32_t)nD | 1u;
-            if ((uint64_t)nw * cols_p * 4 <= LC_FAST_ROW_MASK) {
-                LcFastHeader fh;
-                memset(&fh, 0, sizeof fh);
-                fh.magic = LC_FAST_MAGIC;
-                fh.ngroups = res.ngroups;
-                fh.rev_start = rev_start;
-                fh.rev_stride = stride;
-                fh.fwd_cols = cols_p;
-                fh.nw = (uint32_t)nw;
-                fh.nact = (uint32_t)actions.size();
-                std::vector<uint8_t> rv((size_t)nD * stride, 0);
-                for (int d = 0; d < nD; ++d)
-                    for (int b = 0; b < 256; ++b)
-                        rv[(size_t)d * stride + b] = (uint8_t)rev_next[(size_t)d * nclasses + byte_class[b]];
-                std::vector<uint32_t> fw((size_t)nw * cols_p, LC_NONE_ENTRY);
-                for (int w = 0; w < nw; ++w)
-                    for (int D = 0; D < nD; ++D) {
-                        uint32_t e = fwd[(size_t)w * fwd_cols + D];
-                        if (e == LC_NONE_ENTRY)
-                            continue;
-                        uint32_t nxt = LC_ENTRY_NEXT(e);
-                        fw[(size_t)w * cols_p + D] =
-                            (nxt == 0xFFFFu ? 0u : nxt * cols_p * 4) | (LC_ENTRY_ACT(e) << LC_FAST_ACT_SHIFT);
-                    }
-                std::vector<uint32_t> a2(actions.size(), 0xFFFFu);
-                for (size_t a = 0; a < actions.size(); ++a) {
+        if (mode == LC_MODE_TWOPASS && npc == 1 && (uint32_t)nD <= LC_FAST_MAX_REV &&
+            (uint32_t)nw <= LC_FAST_MAX_WALKERS && res.ngroups <= LC_FAST_MAX_GROUPS && actions.size() < 256) {
+            LcFastHeader fh;
+            memset(&fh, 0, sizeof fh);
+            fh.magic = LC_FAST_MAGIC;
+            fh.ngroups = res.ngroups;
+            fh.rev_start4 = rev_start * 4;
+            fh.nrev = (uint32_t)nD;
+            fh.nw = (uint32_t)nw;
+            fh.nact = (uint32_t)actions.size();
+            std::vector<uint8_t> rv((size_t)nD * LC_FAST_REV_PITCH, 0);
+            for (int d = 0; d < nD; ++d)
+                for (int b = 0; b < 256; ++b)
+                    rv[(size_t)d * LC_FAST_REV_PITCH + b] =
+                        (uint8_t)(4 * rev_next[(size_t)d * nclasses + byte_class[b]]);
+            std::vector<uint32_t> fw((size_t)nw * 64, LC_NONE_ENTRY);
+            std::vector<uint8_t> cx((size_t)nw * 64, 0);
+            for (int w = 0; w < nw; ++w)
+                for (int D = 0; D < nD; ++D) {
+                    uint32_t e = fwd[(size_t)w * fwd_cols + D];
+                    if (e == LC_NONE_ENTRY)
+                        continue;
+                    uint32_t nxt = LC_ENTRY_NEXT(e);
+                    uint32_t a = LC_ENTRY_ACT(e);
                     uint64_t mk = actions[a];
-                    uint32_t sa = 0xFF, sb = 0xFF, cx = 0;
-                    int cnt = 0;
-                    for (int bit = 0; bit < 64; ++bit)
-                        if (mk >> bit & 1) {
-                            if (cnt == 0)
-                                sa = (uint32_t)bit;
-                            else if (cnt == 1)
-                                sb = (uint32_t)bit;
-                            else
-                                cx = 1;
-                            ++cnt;
+                    uint32_t slot_byte = 0, multi_flag = 0;
+                    if (mk) {
+                        if ((mk & (mk - 1)) == 0) {
+                            int bit = 0;
+                            while (!(mk >> bit & 1))
+                                ++bit;
+                            slot_byte = 4u * (uint32_t)bit + 4u;
+                        } else {
+                            multi_flag = 0x80000000u; // several slots: out-of-line path, action id in cx
+                            cx[(size_t)w * 64 + D] = (uint8_t)a;
+                            fh.reserved[0] = 1;       // has_multi
                         }
-                    a2[a] = sa | (sb << 8) | (cx << 16);
+                    }
+                    fw[(size_t)w * 64 + D] = slot_byte | ((nxt == 0xFFFFu ? 0u : nxt) << 8) | multi_flag;
                 }
-                std::vector<uint8_t> fb(sizeof fh, 0);
-                put(fb, fh.off_rev, rv);
-                put(fb, fh.off_fwd, fw);
-                put(fb, fh.off_act2, a2);
-                put(fb, fh.off_masks, actions);
-                while (fb.size() % 16)
-                    fb.push_back(0);
-                fh.total_bytes = (uint32_t)fb.size();
-                memcpy(fb.data(), &fh, sizeof fh);
-                res.fast_blob.swap(fb);
-            }
+            std::vector<uint8_t> fb(sizeof fh, 0);
+            put(fb, fh.off_rev, rv);
+            while (fb.size() % 256) // forward rows are addressed by OR-ing the label into the row base
+                fb.push_back(0);
+            put(fb, fh.off_fwd, fw);
+            put(fb, fh.off_cx, cx);
+            put(fb, fh.off_masks, actions);
+            while (fb.size() % 16)
+                fb.push_back(0);
+            fh.total_bytes = (uint32_t)fb.size();
+            memcpy(fb.data(), &fh, sizeof fh);
+            res.fast_blob.swap(fb);
         }
     } catch (const Invalid& e) {
         res.valid = false;
