@@ -248,3 +248,59 @@ class Engine:
         _check(lib().lc_delim_parse_dev(self._h, _p(d_base), base_len, _p(d_ev_off), _p(d_ev_len), n, _p(sp),
                                         len(sep), quote, nkeys, int(bool(extend)), int(bool(allow_short)), max_fields,
                                         _p(d_status), _p(d_nf), _p(d_fo), _p(d_fl), _p(d_fd)))
+
+
+class HostProcessor:
+    """A B200-backed Processor of the C++ host layer (include/lc_b200_host.h), driven with JSON event groups
+    the way the reference's unit tests drive the original classes."""
+
+    def __init__(self, ptype: str, config: dict):
+        import json
+        L = lib()
+        L.lc_host_processor_create.restype = C.c_void_p
+        L.lc_host_processor_create.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.lc_host_processor_destroy.argtypes = [C.c_void_p]
+        L.lc_host_processor_process.restype = C.c_void_p
+        L.lc_host_processor_process.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.lc_host_processor_counters.restype = C.c_void_p
+        L.lc_host_processor_counters.argtypes = [C.c_void_p]
+        L.lc_host_string_free.argtypes = [C.c_void_p]
+        err = C.c_void_p()
+        self._h = L.lc_host_processor_create(ptype.encode(), json.dumps(config).encode("utf-8"), C.byref(err))
+        if not self._h:
+            msg = C.string_at(err.value).decode() if err.value else "unknown error"
+            if err.value:
+                L.lc_host_string_free(err)
+            raise LcError(LC_ERR_INVALID_ARG, msg)
+        self.type = ptype
+
+    def process(self, group, enable_event_meta=True):
+        """group: dict in the reference's event-group JSON shape (or None). Returns the processed group."""
+        import json
+        L = lib()
+        err = C.c_void_p()
+        out = L.lc_host_processor_process(self._h, json.dumps(group).encode("utf-8"), int(enable_event_meta),
+                                          C.byref(err))
+        if not out:
+            msg = C.string_at(err.value).decode() if err.value else "unknown error"
+            if err.value:
+                L.lc_host_string_free(err)
+            raise LcError(LC_ERR_CUDA, msg)
+        s = C.string_at(out).decode("utf-8")
+        L.lc_host_string_free(out)
+        return json.loads(s)
+
+    def counters(self):
+        import json
+        L = lib()
+        out = L.lc_host_processor_counters(self._h)
+        s = C.string_at(out).decode()
+        L.lc_host_string_free(out)
+        return json.loads(s)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().lc_host_processor_destroy(self._h)
+        except Exception:
+            pass

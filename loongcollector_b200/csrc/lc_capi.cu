@@ -383,10 +383,19 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
     if (!force_basic && blob_bytes + 4096 <= smem_max) {
         uint32_t lab_words = 0, threads = 1024, blocks_per_sm = 1;
         if (h->mode == LC_MODE_TWOPASS) {
-            uint64_t avg = base_len / n + 1;
-            lab_words = (uint32_t)((avg + avg / 8 + 16) / per + 2);
-            if (lab_words < 16)
-                lab_words = 16;
+            // size the per-thread label area from the actual length distribution: cover the longest event when
+            // the batch is near-uniform, else ~1.25x the mean (longer events spill to the global slab)
+            CU_TRY(cudaMemsetAsync(ds->counters, 0, sizeof ds->counters, e->stream));
+            lck::launch_len_stats(d_ev_len, n, ds->counters, e->stream);
+            e->launches++;
+            CU_TRY(cudaMemcpyAsync(hs->counters, ds->counters, sizeof ds->counters, cudaMemcpyDeviceToHost,
+                                   e->stream));
+            CU_TRY(cudaStreamSynchronize(e->stream));
+            uint64_t mx = hs->counters[0], avg = hs->counters[1] / n + 1;
+            uint64_t cover = (mx <= avg + avg / 2 + 64) ? mx : (avg + avg / 4);
+            lab_words = (uint32_t)((cover + 15) / per + 2); // + 15: labels are shifted by the 16 B misalignment
+            if (lab_words < 8)
+                lab_words = 8;
             size_t budget = smem_max - blob_bytes - 1024;
             // per warp: labels (lab_words * 128 B) + capture slots of its 32 threads (fast layout only)
             size_t slot_bytes = use_fast ? (size_t)32 * lck::fast_slot_pitch(h->ngroups) * 4 : 0;

@@ -13,6 +13,8 @@
 //   delimiter  core/plugin/processor/ProcessorParseDelimiterNative.cpp:219-409, core/parser/DelimiterModeFsmParser.cpp:49-294
 #include "lc_kernels.cuh"
 
+#include <algorithm>
+
 #include "lc_exec.cuh"
 #include "lc_scan.cuh"
 
@@ -188,6 +190,32 @@ void launch_label_sizes(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_sizes,
     if (!n)
         return;
     label_sizes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ev_len, n, d_sizes);
+}
+
+// max and sum of the event lengths (sizes the shared-memory label area of the persistent kernels)
+__global__ void __launch_bounds__(256)
+    len_stats_kernel(const uint32_t* __restrict__ ev_len, uint64_t n, unsigned long long* __restrict__ out /* [2] */) {
+    uint32_t mx = 0;
+    unsigned long long sum = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t l = ev_len[i];
+        mx = max(mx, l);
+        sum += l;
+    }
+    for (int d = 16; d; d >>= 1) {
+        mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, d));
+        sum += __shfl_down_sync(0xFFFFFFFFu, sum, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&out[0], (unsigned long long)mx);
+        atomicAdd(&out[1], sum);
+    }
+}
+void launch_len_stats(const uint32_t* d_ev_len, uint64_t n, unsigned long long* d_out, cudaStream_t st) {
+    if (!n)
+        return;
+    unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 1184);
+    len_stats_kernel<<<grid, 256, 0, st>>>(d_ev_len, n, d_out);
 }
 
 // One thread per event; tables read through the read-only path from global memory.

@@ -36,6 +36,9 @@ void launch_regex_parse_basic(const void* d_blob, uint32_t mode, uint32_t ngroup
 // per-event scratch need of the two-pass matcher: len + 1 labels, rounded up to 8 labels (16 B)
 void launch_label_sizes(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_sizes, cudaStream_t st);
 
+// d_out[0] = max(ev_len), d_out[1] = sum(ev_len); d_out must be zeroed by the caller
+void launch_len_stats(const uint32_t* d_ev_len, uint64_t n, unsigned long long* d_out, cudaStream_t st);
+
 // a3 fast path: persistent kernel, automaton staged in shared memory.  Labels of events needing
 // <= lab_words 32-bit words stay in shared memory, longer events bump-allocate from d_scratch.
 // d_bump, d_overflow and d_next_batch must be zeroed by the caller.  Dynamic shared memory =

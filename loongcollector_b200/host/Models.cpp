@@ -1,0 +1,227 @@
+#include "Models.h"
+
+#include <algorithm>
+
+namespace logtail {
+
+std::shared_ptr<SourceBuffer>& PipelineEvent::GetSourceBuffer() {
+    return mGroup->GetSourceBuffer();
+}
+
+// ---- LogEvent: newest live entry wins (reverse scan), deletion leaves a tombstone (LogEvent.cpp:50-106)
+StringView LogEvent::GetContent(StringView key) const {
+    for (auto it = mContents.rbegin(); it != mContents.rend(); ++it)
+        if (it->second && it->first.first == key)
+            return it->first.second;
+    return StringView();
+}
+
+bool LogEvent::HasContent(StringView key) const {
+    for (auto it = mContents.rbegin(); it != mContents.rend(); ++it)
+        if (it->second && it->first.first == key)
+            return true;
+    return false;
+}
+
+void LogEvent::SetContent(StringView key, StringView val) {
+    StringBuffer k = GetSourceBuffer()->CopyString(key);
+    StringBuffer v = GetSourceBuffer()->CopyString(val);
+    SetContentNoCopy(k, v);
+}
+
+void LogEvent::SetContentNoCopy(StringView key, StringView val) {
+    for (auto it = mContents.rbegin(); it != mContents.rend(); ++it)
+        if (it->second && it->first.first == key) {
+            it->first = std::make_pair(key, val);
+            return;
+        }
+    ++mContentCnt;
+    mContents.emplace_back(std::make_pair(key, val), true);
+}
+
+void LogEvent::DelContent(StringView key) {
+    for (auto it = mContents.rbegin(); it != mContents.rend(); ++it)
+        if (it->second && it->first.first == key) {
+            it->second = false;
+            --mContentCnt;
+            return;
+        }
+}
+
+Json::Value LogEvent::ToJson(bool enableEventMeta) const {
+    Json::Value root(Json::objectValue);
+    root["type"] = Json::Value((int)GetType());
+    root["timestamp"] = Json::Value((int64_t)GetTimestamp());
+    if (GetTimestampNanosecond())
+        root["timestampNanosecond"] = Json::Value((int64_t)GetTimestampNanosecond().value());
+    if (enableEventMeta) {
+        root["fileOffset"] = Json::Value((uint64_t)mFileOffset);
+        root["rawSize"] = Json::Value((uint64_t)mRawSize);
+    }
+    if (!Empty()) {
+        Json::Value contents(Json::objectValue);
+        for (auto& c : mContents)
+            if (c.second)
+                contents[c.first.first.to_string()] = Json::Value(c.first.second.to_string());
+        root["contents"] = contents;
+    }
+    return root;
+}
+
+bool LogEvent::FromJson(const Json::Value& root) {
+    if (root.isMember("timestampNanosecond"))
+        SetTimestamp(root["timestamp"].asInt64(), (uint32_t)root["timestampNanosecond"].asInt64());
+    else
+        SetTimestamp(root["timestamp"].asInt64());
+    if (root.isMember("fileOffset") && root.isMember("rawSize"))
+        SetPosition(root["fileOffset"].asUInt64(), root["rawSize"].asUInt64());
+    if (root.isMember("contents")) {
+        const Json::Value& contents = root["contents"];
+        for (const auto& key : contents.getMemberNames())
+            SetContent(key, contents[key].asString());
+    }
+    return true;
+}
+
+void RawEvent::SetContent(const std::string& c) {
+    StringBuffer b = GetSourceBuffer()->CopyString(c);
+    mContent = StringView(b.data, b.size);
+}
+
+Json::Value RawEvent::ToJson(bool) const {
+    Json::Value root(Json::objectValue);
+    root["type"] = Json::Value((int)GetType());
+    root["timestamp"] = Json::Value((int64_t)GetTimestamp());
+    if (GetTimestampNanosecond())
+        root["timestampNanosecond"] = Json::Value((int64_t)GetTimestampNanosecond().value());
+    root["content"] = Json::Value(mContent.to_string());
+    return root;
+}
+
+bool RawEvent::FromJson(const Json::Value& root) {
+    if (root.isMember("timestampNanosecond"))
+        SetTimestamp(root["timestamp"].asInt64(), (uint32_t)root["timestampNanosecond"].asInt64());
+    else
+        SetTimestamp(root["timestamp"].asInt64());
+    if (root.isMember("content"))
+        SetContent(root["content"].asString());
+    return true;
+}
+
+// ---- group
+LogEvent* PipelineEventGroup::AddLogEvent() {
+    auto e = std::make_unique<LogEvent>(this);
+    LogEvent* p = e.get();
+    mEvents.emplace_back(std::move(e));
+    return p;
+}
+
+RawEvent* PipelineEventGroup::AddRawEvent() {
+    auto e = std::make_unique<RawEvent>(this);
+    RawEvent* p = e.get();
+    mEvents.emplace_back(std::move(e));
+    return p;
+}
+
+void PipelineEventGroup::SetMetadata(EventGroupMetaKey key, const std::string& val) {
+    StringBuffer b = mSourceBuffer->CopyString(val);
+    mMetadata[key] = StringView(b.data, b.size);
+}
+
+StringView PipelineEventGroup::GetMetadata(EventGroupMetaKey key) const {
+    auto it = mMetadata.find(key);
+    return it == mMetadata.end() ? StringView() : it->second;
+}
+
+void PipelineEventGroup::SetTag(const std::string& key, const std::string& val) {
+    StringBuffer k = mSourceBuffer->CopyString(key);
+    StringBuffer v = mSourceBuffer->CopyString(val);
+    mTags[StringView(k.data, k.size)] = StringView(v.data, v.size);
+}
+
+static const char* MetaKeyName(EventGroupMetaKey k) {
+    switch (k) {
+        case EventGroupMetaKey::LOG_FILE_PATH_RESOLVED:
+            return "log.file.path_resolved";
+        case EventGroupMetaKey::LOG_FILE_OFFSET_KEY:
+            return "log.file.offset";
+        case EventGroupMetaKey::SOURCE_ID:
+            return "source.id";
+        case EventGroupMetaKey::HAS_PART_LOG:
+            return "has.part.log";
+        default:
+            return "unknown";
+    }
+}
+
+static EventGroupMetaKey MetaKeyFromName(const std::string& s) {
+    if (s == "log.file.path_resolved")
+        return EventGroupMetaKey::LOG_FILE_PATH_RESOLVED;
+    if (s == "log.file.offset") // not settable from JSON upstream; accepted here so fixtures can carry it
+        return EventGroupMetaKey::LOG_FILE_OFFSET_KEY;
+    if (s == "source.id")
+        return EventGroupMetaKey::SOURCE_ID;
+    if (s == "has.part.log")
+        return EventGroupMetaKey::HAS_PART_LOG;
+    return EventGroupMetaKey::UNKNOWN;
+}
+
+Json::Value PipelineEventGroup::ToJson(bool enableEventMeta) const {
+    Json::Value root; // null when the group is empty, like jsoncpp's default-constructed root
+    if (!mMetadata.empty()) {
+        Json::Value md(Json::objectValue);
+        for (auto& kv : mMetadata)
+            md[MetaKeyName(kv.first)] = Json::Value(kv.second.to_string());
+        root["metadata"] = md;
+    }
+    if (!mTags.empty()) {
+        Json::Value tags(Json::objectValue);
+        for (auto& kv : mTags)
+            tags[kv.first.to_string()] = Json::Value(kv.second.to_string());
+        root["tags"] = tags;
+    }
+    if (!mEvents.empty()) {
+        Json::Value evs(Json::arrayValue);
+        for (auto& e : mEvents)
+            evs.append(e->ToJson(enableEventMeta));
+        root["events"] = evs;
+    }
+    return root;
+}
+
+bool PipelineEventGroup::FromJson(const Json::Value& root) {
+    if (root.isMember("metadata")) {
+        const Json::Value& md = root["metadata"];
+        for (const auto& key : md.getMemberNames())
+            SetMetadata(MetaKeyFromName(key), md[key].asString());
+    }
+    if (root.isMember("tags")) {
+        const Json::Value& tags = root["tags"];
+        for (const auto& key : tags.getMemberNames())
+            SetTag(key, tags[key].asString());
+    }
+    if (root.isMember("events")) {
+        for (const auto& ev : root["events"]) {
+            int t = ev["type"].asInt();
+            if (t == (int)PipelineEvent::Type::LOG)
+                AddLogEvent()->FromJson(ev);
+            else if (t == (int)PipelineEvent::Type::METRIC || t == (int)PipelineEvent::Type::SPAN)
+                mEvents.emplace_back(std::make_unique<OpaqueEvent>((PipelineEvent::Type)t, this, ev));
+            else
+                AddRawEvent()->FromJson(ev);
+        }
+    }
+    return true;
+}
+
+bool PipelineEventGroup::FromJsonString(const std::string& inJson) {
+    Json::Value root;
+    std::string err;
+    if (!Json::Value::parse(inJson.data(), inJson.data() + inJson.size(), root, err))
+        return false;
+    if (root.isNull())
+        return true;
+    return FromJson(root);
+}
+
+} // namespace logtail

@@ -1,0 +1,260 @@
+// Models.h -- host-side event model kept by the engine's C++ host, mirroring the names and observable
+// behaviour of the reference's L5 data model so that a B200-backed processor is a drop-in:
+//   StringView / SourceBuffer     core/common/StringView.h, core/common/memory/SourceBuffer.h:98-181
+//   LogEvent / RawEvent           core/models/LogEvent.{h,cpp} (contents with tombstones, :50-106), RawEvent.cpp
+//   PipelineEventPtr / Group      core/models/PipelineEventPtr.h:32-96, PipelineEventGroup.{h,cpp}
+// Independent implementation (std::string_view instead of boost::string_view, no event pool): only the
+// behaviour the four processors and their unit-test fixtures observe is reproduced.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <optional>
+#include <string>
+#include <string_view>
+#include <vector>
+
+#include "Json.h"
+
+namespace logtail {
+
+class StringView : public std::string_view {
+public:
+    using std::string_view::string_view;
+    StringView() = default;
+    StringView(const std::string_view& v) : std::string_view(v) {}
+    StringView(const std::string& s) : std::string_view(s) {}
+    std::string to_string() const { return std::string(data(), size()); }
+};
+
+struct StringBuffer {
+    char* data = nullptr;
+    size_t size = 0;
+    size_t capacity = 0;
+};
+
+// Chunked bump arena.  Chunks double from 4 KiB up to 128 KiB; a request of at least half the current chunk
+// size gets its own allocation (same growth rule as the reference so that a file read lands in ONE chunk).
+// Every string buffer is NUL-terminated one past its end.
+class SourceBuffer {
+public:
+    SourceBuffer() = default;
+    SourceBuffer(const SourceBuffer&) = delete;
+    SourceBuffer& operator=(const SourceBuffer&) = delete;
+
+    StringBuffer AllocateStringBuffer(size_t size) {
+        char* p = Allocate(size + 1);
+        p[size] = '\0';
+        StringBuffer b;
+        b.data = p;
+        b.size = size;
+        b.capacity = size + 1;
+        return b;
+    }
+    StringBuffer CopyString(const char* data, size_t len) {
+        StringBuffer b = AllocateStringBuffer(len);
+        if (len)
+            memcpy(b.data, data, len);
+        return b;
+    }
+    StringBuffer CopyString(StringView s) { return CopyString(s.data(), s.size()); }
+    StringBuffer CopyString(const std::string& s) { return CopyString(s.data(), s.size()); }
+
+    // chunk that contains [p, p + n) entirely, or nullptr (used to hand a zero-copy span to the engine)
+    const char* ChunkContaining(const char* p, size_t n, size_t* chunk_size) const {
+        for (auto& c : mChunks)
+            if (p >= c.mem.get() && p + n <= c.mem.get() + c.used) {
+                *chunk_size = c.used;
+                return c.mem.get();
+            }
+        return nullptr;
+    }
+
+private:
+    struct Chunk {
+        std::unique_ptr<char[]> mem;
+        size_t cap = 0, used = 0;
+    };
+    char* Allocate(size_t bytes) {
+        if (bytes * 2 >= mNextChunk) { // oversize: own allocation
+            Chunk c;
+            c.mem.reset(new char[bytes]);
+            c.cap = c.used = bytes;
+            mChunks.insert(mChunks.begin(), std::move(c)); // keep the current bump chunk last
+            return mChunks.front().mem.get();
+        }
+        if (mChunks.empty() || mChunks.back().used + bytes > mChunks.back().cap || mChunks.back().cap != mCurCap) {
+            Chunk c;
+            c.mem.reset(new char[mNextChunk]);
+            c.cap = mNextChunk;
+            mCurCap = mNextChunk;
+            mChunks.push_back(std::move(c));
+            if (mNextChunk < 128 * 1024)
+                mNextChunk *= 2;
+        }
+        Chunk& c = mChunks.back();
+        char* p = c.mem.get() + c.used;
+        c.used += bytes;
+        return p;
+    }
+    std::vector<Chunk> mChunks;
+    size_t mNextChunk = 4096, mCurCap = 0;
+};
+
+class PipelineEventGroup;
+
+class PipelineEvent {
+public:
+    enum class Type { NONE = 0, LOG = 1, METRIC = 2, SPAN = 3, RAW = 4 };
+    virtual ~PipelineEvent() = default;
+    Type GetType() const { return mType; }
+    time_t GetTimestamp() const { return mTimestamp; }
+    std::optional<uint32_t> GetTimestampNanosecond() const { return mTimestampNanosecond; }
+    void SetTimestamp(time_t t) { mTimestamp = t; }
+    void SetTimestamp(time_t t, std::optional<uint32_t> ns) {
+        mTimestamp = t;
+        mTimestampNanosecond = ns;
+    }
+    std::shared_ptr<SourceBuffer>& GetSourceBuffer();
+    virtual Json::Value ToJson(bool enableEventMeta) const = 0;
+
+protected:
+    PipelineEvent(Type t, PipelineEventGroup* g) : mType(t), mGroup(g) {}
+    Type mType;
+    time_t mTimestamp = 0;
+    std::optional<uint32_t> mTimestampNanosecond;
+    PipelineEventGroup* mGroup;
+};
+
+class LogEvent : public PipelineEvent {
+public:
+    explicit LogEvent(PipelineEventGroup* g) : PipelineEvent(Type::LOG, g) { mContents.reserve(16); }
+    using Content = std::pair<std::pair<StringView, StringView>, bool>; // ((key, value), live)
+
+    StringView GetContent(StringView key) const;
+    bool HasContent(StringView key) const;
+    void SetContent(StringView key, StringView val); // copies both into the arena
+    void SetContentNoCopy(StringView key, StringView val);
+    void SetContentNoCopy(const StringBuffer& key, const StringBuffer& val) {
+        SetContentNoCopy(StringView(key.data, key.size), StringView(val.data, val.size));
+    }
+    void DelContent(StringView key);
+    bool Empty() const { return mContentCnt == 0; }
+    size_t Size() const { return mContentCnt; }
+    const std::vector<Content>& RawContents() const { return mContents; }
+    // first live content (LogEvent::cbegin() skips tombstones)
+    const Content* FirstLive() const {
+        for (auto& c : mContents)
+            if (c.second)
+                return &c;
+        return nullptr;
+    }
+    void SetPosition(uint64_t offset, uint64_t size) {
+        mFileOffset = offset;
+        mRawSize = size;
+    }
+    std::pair<uint64_t, uint64_t> GetPosition() const { return {mFileOffset, mRawSize}; }
+    Json::Value ToJson(bool enableEventMeta) const override;
+    bool FromJson(const Json::Value& root);
+
+private:
+    std::vector<Content> mContents;
+    size_t mContentCnt = 0;
+    uint64_t mFileOffset = 0, mRawSize = 0;
+};
+
+class RawEvent : public PipelineEvent {
+public:
+    explicit RawEvent(PipelineEventGroup* g) : PipelineEvent(Type::RAW, g) {}
+    StringView GetContent() const { return mContent; }
+    void SetContentNoCopy(StringView c) { mContent = c; }
+    void SetContent(const std::string& c);
+    Json::Value ToJson(bool enableEventMeta) const override;
+    bool FromJson(const Json::Value& root);
+
+private:
+    StringView mContent;
+};
+
+// Metric / span events are outside the hot path: they are carried through untouched.
+class OpaqueEvent : public PipelineEvent {
+public:
+    OpaqueEvent(Type t, PipelineEventGroup* g, const Json::Value& v) : PipelineEvent(t, g), mJson(v) {}
+    Json::Value ToJson(bool) const override { return mJson; }
+
+private:
+    Json::Value mJson;
+};
+
+class PipelineEventPtr {
+public:
+    PipelineEventPtr() = default;
+    explicit PipelineEventPtr(std::unique_ptr<PipelineEvent>&& p) : mData(std::move(p)) {}
+    PipelineEventPtr(std::unique_ptr<PipelineEvent>&& p, bool /*fromPool*/, void* /*pool*/) : mData(std::move(p)) {}
+    template <class T>
+    bool Is() const;
+    template <class T>
+    T& Cast() {
+        return static_cast<T&>(*mData);
+    }
+    template <class T>
+    const T& Cast() const {
+        return static_cast<const T&>(*mData);
+    }
+    PipelineEvent* operator->() { return mData.get(); }
+    const PipelineEvent* operator->() const { return mData.get(); }
+    explicit operator bool() const { return (bool)mData; }
+
+private:
+    std::unique_ptr<PipelineEvent> mData;
+};
+template <>
+inline bool PipelineEventPtr::Is<LogEvent>() const {
+    return mData && mData->GetType() == PipelineEvent::Type::LOG;
+}
+template <>
+inline bool PipelineEventPtr::Is<RawEvent>() const {
+    return mData && mData->GetType() == PipelineEvent::Type::RAW;
+}
+
+using EventsContainer = std::vector<PipelineEventPtr>;
+
+enum class EventGroupMetaKey { UNKNOWN, LOG_FILE_PATH_RESOLVED, LOG_FILE_OFFSET_KEY, SOURCE_ID, HAS_PART_LOG };
+using GroupMetadata = std::map<EventGroupMetaKey, StringView>;
+
+class PipelineEventGroup {
+public:
+    explicit PipelineEventGroup(const std::shared_ptr<SourceBuffer>& sb) : mSourceBuffer(sb) {}
+    PipelineEventGroup(PipelineEventGroup&&) = default;
+    PipelineEventGroup& operator=(PipelineEventGroup&&) = default;
+
+    const EventsContainer& GetEvents() const { return mEvents; }
+    EventsContainer& MutableEvents() { return mEvents; }
+    void SwapEvents(EventsContainer& other) { mEvents.swap(other); }
+    std::unique_ptr<LogEvent> CreateLogEvent(bool /*fromPool*/ = false) { return std::make_unique<LogEvent>(this); }
+    std::unique_ptr<RawEvent> CreateRawEvent(bool /*fromPool*/ = false) { return std::make_unique<RawEvent>(this); }
+    LogEvent* AddLogEvent();
+    RawEvent* AddRawEvent();
+    std::shared_ptr<SourceBuffer>& GetSourceBuffer() { return mSourceBuffer; }
+
+    void SetMetadata(EventGroupMetaKey key, const std::string& val);
+    StringView GetMetadata(EventGroupMetaKey key) const;
+    bool HasMetadata(EventGroupMetaKey key) const { return mMetadata.count(key) != 0; }
+    const GroupMetadata& GetAllMetadata() const { return mMetadata; }
+    void SetTag(const std::string& key, const std::string& val);
+
+    Json::Value ToJson(bool enableEventMeta = false) const;
+    bool FromJson(const Json::Value& root);
+    std::string ToJsonString(bool enableEventMeta = false) const { return ToJson(enableEventMeta).toString(); }
+    bool FromJsonString(const std::string& inJson);
+
+private:
+    EventsContainer mEvents;
+    GroupMetadata mMetadata;
+    std::map<StringView, StringView> mTags;
+    std::shared_ptr<SourceBuffer> mSourceBuffer;
+};
+
+} // namespace logtail

@@ -1,0 +1,695 @@
+#include "Processors.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <stdexcept>
+
+namespace logtail {
+
+// ------------------------------------------------------------------------------------------------ engine per thread
+namespace {
+
+// One engine per (GPU, host thread): the reference keeps one regex copy per ProcessorRunner thread
+// (ProcessorParseRegexNative.cpp:64-67); here the per-thread state is the engine's stream and workspace.
+struct ThreadEngine {
+    lc_engine_t* e = nullptr;
+    ~ThreadEngine() {
+        if (e)
+            lc_engine_destroy(e);
+    }
+};
+
+lc_engine_t* Engine() {
+    static thread_local ThreadEngine t;
+    if (!t.e) {
+        const char* d = getenv("LC_B200_DEVICE");
+        int dev = d ? atoi(d) : 0;
+        if (lc_engine_create(dev, &t.e) != LC_OK)
+            throw std::runtime_error(std::string("loongcollector_b200: ") + lc_last_error());
+    }
+    return t.e;
+}
+
+void Check(int rc, const char* what) {
+    if (rc != LC_OK)
+        throw std::runtime_error(std::string(what) + ": " + lc_last_error());
+}
+
+// Flattens the source values of the events to be parsed into (base, off[], len[]).  If every value lies
+// inside ONE arena chunk (the production shape: all lines alias the file read buffer) the span is handed to
+// the engine as is; otherwise the values are packed into a staging buffer.
+struct FlatBatch {
+    std::vector<uint32_t> off, len;
+    std::vector<size_t> eventIndex;
+    std::vector<const char*> origin; // original data pointer of each value
+    const uint8_t* base = nullptr;
+    uint64_t baseLen = 0;
+    std::vector<uint8_t> packed;
+
+    void Add(size_t idx, StringView v) {
+        eventIndex.push_back(idx);
+        origin.push_back(v.data());
+        len.push_back((uint32_t)v.size());
+    }
+    void Finish(SourceBuffer& sb) {
+        size_t n = origin.size();
+        off.resize(n);
+        if (!n)
+            return;
+        const char* lo = origin[0];
+        const char* hi = origin[0] + len[0];
+        for (size_t i = 1; i < n; ++i) {
+            lo = std::min(lo, origin[i]);
+            hi = std::max(hi, origin[i] + len[i]);
+        }
+        size_t chunkSize = 0;
+        if ((uint64_t)(hi - lo) < 0xFFFFFFF0ull && sb.ChunkContaining(lo, (size_t)(hi - lo), &chunkSize)) {
+            base = reinterpret_cast<const uint8_t*>(lo);
+            baseLen = (uint64_t)(hi - lo);
+            for (size_t i = 0; i < n; ++i)
+                off[i] = (uint32_t)(origin[i] - lo);
+            return;
+        }
+        size_t total = 0;
+        for (size_t i = 0; i < n; ++i)
+            total += len[i];
+        packed.resize(total + 1);
+        size_t at = 0;
+        for (size_t i = 0; i < n; ++i) {
+            off[i] = (uint32_t)at;
+            if (len[i])
+                memcpy(packed.data() + at, origin[i], len[i]);
+            at += len[i];
+        }
+        base = packed.data();
+        baseLen = total;
+    }
+    // view of [o, o + l) (offsets relative to base) for event i, mapped back onto the original bytes
+    StringView View(size_t i, uint32_t o, uint32_t l) const { return StringView(origin[i] + (o - off[i]), l); }
+};
+
+bool GetString(const Json::Value& cfg, const char* key, std::string& out) {
+    if (cfg.isMember(key) && cfg[key].isString()) {
+        out = cfg[key].asString();
+        return true;
+    }
+    return false;
+}
+void GetBool(const Json::Value& cfg, const char* key, bool& out) {
+    if (cfg.isMember(key) && cfg[key].isBool())
+        out = cfg[key].asBool();
+}
+
+void AddLog(LogEvent& ev, StringView key, StringView value, bool overwritten = true) {
+    if (!overwritten && ev.HasContent(key))
+        return;
+    ev.SetContentNoCopy(key, value);
+}
+
+std::string ToString(uint64_t v) {
+    return std::to_string(v);
+}
+
+// CreateNewEvent of both splitters (ProcessorSplitLogStringNative.cpp:135-157,
+// ProcessorSplitMultilineLogStringNative.cpp:311-340)
+void EmitSplitEvent(PipelineEventGroup& group, const LogEvent& src, StringView sourceVal, const StringBuffer& sourceKey,
+                    StringView content, bool isLast, bool raw, EventsContainer& out) {
+    if (raw) {
+        auto t = group.CreateRawEvent(true);
+        t->SetContentNoCopy(content);
+        t->SetTimestamp(src.GetTimestamp(), src.GetTimestampNanosecond());
+        out.emplace_back(std::move(t), true, nullptr);
+        return;
+    }
+    auto t = group.CreateLogEvent(true);
+    t->SetContentNoCopy(StringView(sourceKey.data, sourceKey.size), content);
+    t->SetTimestamp(src.GetTimestamp(), src.GetTimestampNanosecond());
+    uint64_t rel = (uint64_t)(content.data() - sourceVal.data());
+    uint64_t offset = src.GetPosition().first + rel;
+    uint64_t length = isLast ? src.GetPosition().second - rel : content.size() + 1;
+    t->SetPosition(offset, length);
+    if (group.HasMetadata(EventGroupMetaKey::LOG_FILE_OFFSET_KEY)) {
+        StringBuffer offStr = group.GetSourceBuffer()->CopyString(ToString(offset));
+        t->SetContentNoCopy(group.GetMetadata(EventGroupMetaKey::LOG_FILE_OFFSET_KEY),
+                            StringView(offStr.data, offStr.size));
+    }
+    out.emplace_back(std::move(t), true, nullptr);
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------ options
+const std::string CommonParserOptions::legacyUnmatchedRawLogKey = "__raw_log__";
+
+bool CommonParserOptions::Init(const Json::Value& config) {
+    GetBool(config, "KeepingSourceWhenParseFail", mKeepingSourceWhenParseFail);
+    GetBool(config, "KeepingSourceWhenParseSucceed", mKeepingSourceWhenParseSucceed);
+    GetString(config, "RenamedSourceKey", mRenamedSourceKey);
+    if (mRenamedSourceKey.empty())
+        mRenamedSourceKey = config["SourceKey"].asString();
+    GetBool(config, "CopingRawLog", mCopingRawLog);
+    return true;
+}
+bool CommonParserOptions::ShouldAddSourceContent(bool ok) const {
+    return (ok && mKeepingSourceWhenParseSucceed) || (!ok && mKeepingSourceWhenParseFail);
+}
+bool CommonParserOptions::ShouldAddLegacyUnmatchedRawLog(bool ok) const {
+    return !ok && mKeepingSourceWhenParseFail && mCopingRawLog;
+}
+bool CommonParserOptions::ShouldEraseEvent(bool ok, const LogEvent& ev, const GroupMetadata& md) const {
+    if (!ok && !mKeepingSourceWhenParseFail) {
+        if (ev.Empty())
+            return true;
+        size_t size = ev.Size();
+        auto offsetKey = md.find(EventGroupMetaKey::LOG_FILE_OFFSET_KEY);
+        if (size == 1 && offsetKey != md.end() && ev.FirstLive()->first.first == offsetKey->second)
+            return true;
+        if (size == 2 && ev.HasContent("_time_") && ev.HasContent("_source_"))
+            return true;
+    }
+    return false;
+}
+
+CompiledRegex::~CompiledRegex() {
+    if (mRe)
+        lc_regex_free(mRe);
+}
+bool CompiledRegex::Compile(const std::string& pattern, std::string& err) {
+    if (mRe) {
+        lc_regex_free(mRe);
+        mRe = nullptr;
+    }
+    int rc = lc_regex_compile(pattern.data(), pattern.size(), &mRe);
+    if (rc != LC_OK) {
+        err = lc_last_error();
+        if (mRe) {
+            lc_regex_free(mRe);
+            mRe = nullptr;
+        }
+        return false;
+    }
+    return true;
+}
+
+static bool EndsWith(const std::string& s, const char* suf) {
+    size_t n = strlen(suf);
+    return s.size() >= n && !s.compare(s.size() - n, n, suf);
+}
+
+bool MultilineOptions::Init(const Json::Value& config, std::string& err) {
+    // dotted parameter names resolve to their last segment (ParamExtractor.cpp:23-29)
+    struct {
+        const char* key;
+        std::string* dst;
+    } pats[] = {{"StartPattern", &mStartPattern}, {"ContinuePattern", &mContinuePattern}, {"EndPattern", &mEndPattern}};
+    bool compiled[3] = {false, false, false};
+    int k = 0;
+    for (auto& p : pats) {
+        std::string pattern;
+        if (GetString(config, p.key, pattern)) {
+            // validation strips a trailing '$' and trailing ".*"s, yet the ORIGINAL pattern is stored (:205-222)
+            std::string probe = pattern;
+            if (!probe.empty() && EndsWith(probe, "$"))
+                probe.pop_back();
+            while (!probe.empty() && EndsWith(probe, ".*"))
+                probe.resize(probe.size() - 2);
+            bool valid = true;
+            if (!probe.empty()) {
+                CompiledRegex tmp;
+                std::string e;
+                lc_regex_t* raw = nullptr;
+                int rc = lc_regex_compile(probe.data(), probe.size(), &raw);
+                if (raw)
+                    lc_regex_free(raw);
+                valid = rc != LC_ERR_REGEX_INVALID;
+                compiled[k] = valid;
+            }
+            if (valid)
+                *p.dst = pattern;
+        }
+        ++k;
+    }
+    if (compiled[0] || compiled[2])
+        mIsMultiline = true;
+    std::string t;
+    if (GetString(config, "UnmatchedContentTreatment", t) && t == "discard")
+        mUnmatchedContentTreatment = UnmatchedContentTreatment::DISCARD;
+    GetBool(config, "IgnoringUnmatchWarning", mIgnoringUnmatchWarning);
+    (void)err;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ split
+const std::string ProcessorSplitLogStringNative::sName = "processor_split_string_native";
+
+bool ProcessorSplitLogStringNative::Init(const Json::Value& config) {
+    GetString(config, "SourceKey", mSourceKey);
+    if (config.isMember("SplitChar") && config["SplitChar"].isInt())
+        mSplitChar = (char)config["SplitChar"].asInt();
+    GetBool(config, "EnableRawContent", mEnableRawContent);
+    return true;
+}
+
+void ProcessorSplitLogStringNative::Process(PipelineEventGroup& group) {
+    if (group.GetEvents().empty())
+        return;
+    EventsContainer newEvents;
+    std::vector<uint32_t> off, len;
+    for (PipelineEventPtr& e : group.MutableEvents()) {
+        if (!IsSupportedEvent(e)) {
+            newEvents.emplace_back(std::move(e));
+            continue;
+        }
+        LogEvent& src = e.Cast<LogEvent>();
+        if (src.Size() != 1 || !src.HasContent(mSourceKey)) {
+            newEvents.emplace_back(std::move(e));
+            continue;
+        }
+        StringView val = src.GetContent(mSourceKey);
+        StringBuffer sourceKey = group.GetSourceBuffer()->CopyString(mSourceKey);
+        if (val.empty())
+            continue;
+        // a1 on the GPU: one (offset, length) per piece
+        uint64_t n = 0;
+        uint64_t cap = std::max<uint64_t>(1024, val.size() / 16);
+        for (;;) {
+            off.resize(cap);
+            len.resize(cap);
+            int rc = lc_split_lines(Engine(), reinterpret_cast<const uint8_t*>(val.data()), val.size(),
+                                    (uint8_t)mSplitChar, off.data(), len.data(), cap, &n);
+            if (rc == LC_ERR_CAPACITY) {
+                cap = n;
+                continue;
+            }
+            Check(rc, "lc_split_lines");
+            break;
+        }
+        for (uint64_t k = 0; k < n; ++k) {
+            StringView content(val.data() + off[k], len[k]);
+            bool isLast = (uint64_t)off[k] + len[k] == val.size();
+            EmitSplitEvent(group, src, val, sourceKey, content, isLast, mEnableRawContent, newEvents);
+        }
+    }
+    group.SwapEvents(newEvents);
+}
+
+// ------------------------------------------------------------------------------------------------ multiline
+const std::string ProcessorSplitMultilineLogStringNative::sName = "processor_split_multiline_log_string_native";
+
+bool ProcessorSplitMultilineLogStringNative::Init(const Json::Value& config) {
+    GetString(config, "SourceKey", mSourceKey);
+    std::string err;
+    if (!mMultiline.Init(config, err))
+        return Fail(err);
+    GetBool(config, "EnableRawContent", mEnableRawContent);
+    // the processor compiles the ORIGINAL pattern strings (:70-80); an unsupported pattern fails Init loudly
+    if (!mMultiline.mStartPattern.empty() && !mStart.Compile(mMultiline.mStartPattern, err))
+        return Fail("Multiline.StartPattern: " + err);
+    if (!mMultiline.mContinuePattern.empty() && !mContinue.Compile(mMultiline.mContinuePattern, err))
+        return Fail("Multiline.ContinuePattern: " + err);
+    if (!mMultiline.mEndPattern.empty() && !mEnd.Compile(mMultiline.mEndPattern, err))
+        return Fail("Multiline.EndPattern: " + err);
+    return true;
+}
+
+std::vector<std::pair<std::string, uint64_t>> ProcessorSplitMultilineLogStringNative::Counters() const {
+    return {{"matched_events", mMatchedEventsTotal.v},
+            {"matched_lines", mMatchedLinesTotal.v},
+            {"unmatched_lines", mUnmatchedLinesTotal.v}};
+}
+
+void ProcessorSplitMultilineLogStringNative::Process(PipelineEventGroup& group) {
+    if (group.GetEvents().empty())
+        return;
+    EventsContainer newEvents;
+    uint64_t inputLines = 0, unmatchLines = 0;
+    std::vector<uint32_t> off, len;
+    std::vector<uint8_t> flags;
+    for (PipelineEventPtr& e : group.MutableEvents()) {
+        if (!IsSupportedEvent(e)) {
+            newEvents.emplace_back(std::move(e));
+            continue;
+        }
+        LogEvent& src = e.Cast<LogEvent>();
+        if (src.Size() != 1 || !src.HasContent(mSourceKey)) {
+            newEvents.emplace_back(std::move(e));
+            continue;
+        }
+        StringView val = src.GetContent(mSourceKey);
+        StringBuffer sourceKey = group.GetSourceBuffer()->CopyString(mSourceKey);
+        if (val.empty())
+            continue;
+        uint64_t n = 0, ctr[3] = {0, 0, 0};
+        uint64_t cap = std::max<uint64_t>(1024, val.size() / 16);
+        for (;;) {
+            off.resize(cap);
+            len.resize(cap);
+            flags.resize(cap);
+            uint64_t c[3] = {0, 0, 0};
+            int rc = lc_multiline_split(
+                Engine(), reinterpret_cast<const uint8_t*>(val.data()), val.size(), mStart.get(), mContinue.get(),
+                mEnd.get(), mMultiline.mUnmatchedContentTreatment == MultilineOptions::UnmatchedContentTreatment::DISCARD,
+                off.data(), len.data(), flags.data(), cap, &n, c);
+            if (rc == LC_ERR_CAPACITY) {
+                cap = n;
+                continue;
+            }
+            Check(rc, "lc_multiline_split");
+            memcpy(ctr, c, sizeof ctr);
+            break;
+        }
+        mMatchedEventsTotal.Add(ctr[0]);
+        inputLines += ctr[1];
+        unmatchLines += ctr[2];
+        for (uint64_t k = 0; k < n; ++k)
+            EmitSplitEvent(group, src, val, sourceKey, StringView(val.data() + off[k], len[k]),
+                           (flags[k] & LC_ML_IS_LAST) != 0, mEnableRawContent, newEvents);
+    }
+    mMatchedLinesTotal.Add(inputLines - unmatchLines);
+    mUnmatchedLinesTotal.Add(unmatchLines);
+    group.SwapEvents(newEvents);
+}
+
+// ------------------------------------------------------------------------------------------------ regex parse
+const std::string ProcessorParseRegexNative::sName = "processor_parse_regex_native";
+
+static bool GetKeys(const Json::Value& config, std::vector<std::string>& keys) {
+    if (!config.isMember("Keys") || !config["Keys"].isArray())
+        return false;
+    keys.clear();
+    for (const auto& k : config["Keys"]) {
+        if (!k.isString())
+            return false;
+        keys.push_back(k.asString());
+    }
+    return true;
+}
+
+bool ProcessorParseRegexNative::Init(const Json::Value& config) {
+    if (!GetString(config, "SourceKey", mSourceKey))
+        return Fail("mandatory string param SourceKey is missing");
+    if (!GetString(config, "Regex", mRegex))
+        return Fail("mandatory string param Regex is missing");
+    mIsWholeLineMode = mRegex == "(.*)";
+    std::string err;
+    if (!mIsWholeLineMode && !mReg.Compile(mRegex, err))
+        return Fail("mandatory string param Regex is not usable: " + err);
+    if (!GetKeys(config, mKeys))
+        return Fail("mandatory list param Keys is missing");
+    // legacy ["k1,k2"] form (:80-88)
+    if (mKeys.size() == 1 && mKeys[0].find(',') != std::string::npos) {
+        std::vector<std::string> parts;
+        size_t start = 0;
+        const std::string joined = mKeys[0];
+        for (;;) {
+            size_t pos = joined.find(',', start);
+            parts.push_back(joined.substr(start, pos == std::string::npos ? std::string::npos : pos - start));
+            if (pos == std::string::npos)
+                break;
+            start = pos + 1;
+        }
+        mKeys = parts;
+    }
+    for (const auto& k : mKeys)
+        if (k == mSourceKey)
+            mSourceKeyOverwritten = true;
+    return mCommonParserOptions.Init(config);
+}
+
+std::vector<std::pair<std::string, uint64_t>> ProcessorParseRegexNative::Counters() const {
+    return {{"discarded", mDiscardedEventsTotal.v},
+            {"out_failed", mOutFailedEventsTotal.v},
+            {"out_key_not_found", mOutKeyNotFoundEventsTotal.v},
+            {"out_successful", mOutSuccessfulEventsTotal.v}};
+}
+
+void ProcessorParseRegexNative::Process(PipelineEventGroup& group) {
+    if (group.GetEvents().empty())
+        return;
+    EventsContainer& events = group.MutableEvents();
+    // gather the events that reach RegexLogLineParser and run ONE batched regex_match over them
+    FlatBatch batch;
+    if (!mIsWholeLineMode) {
+        for (size_t i = 0; i < events.size(); ++i) {
+            if (!IsSupportedEvent(events[i]))
+                continue;
+            const LogEvent& ev = events[i].Cast<LogEvent>();
+            if (ev.HasContent(mSourceKey))
+                batch.Add(i, ev.GetContent(mSourceKey));
+        }
+        batch.Finish(*group.GetSourceBuffer());
+    }
+    const uint32_t G = mReg.groups();
+    const size_t nb = batch.eventIndex.size();
+    std::vector<uint8_t> status(nb);
+    std::vector<uint32_t> capOff(nb * G + 1), capLen(nb * G + 1);
+    if (nb)
+        Check(lc_regex_parse(Engine(), mReg.get(), batch.base, batch.baseLen, batch.off.data(), batch.len.data(), nb,
+                             (uint32_t)mKeys.size(), status.data(), capOff.data(), capLen.data()),
+              "lc_regex_parse");
+
+    size_t wIdx = 0, b = 0;
+    for (size_t rIdx = 0; rIdx < events.size(); ++rIdx) {
+        bool keep = true;
+        PipelineEventPtr& e = events[rIdx];
+        if (!IsSupportedEvent(e)) {
+            mOutFailedEventsTotal.Add(1);
+        } else {
+            LogEvent& ev = e.Cast<LogEvent>();
+            if (!ev.HasContent(mSourceKey)) {
+                mOutKeyNotFoundEventsTotal.Add(1);
+            } else {
+                StringView rawContent = ev.GetContent(mSourceKey);
+                bool ok = true;
+                if (mIsWholeLineMode) {
+                    AddLog(ev, mKeys.empty() ? StringView("content") : StringView(mKeys[0]), rawContent);
+                } else {
+                    uint8_t st = status[b];
+                    if (st == LC_REGEX_NOMATCH) {
+                        mOutFailedEventsTotal.Add(1);
+                        ok = false;
+                    } else if (st == LC_REGEX_KEYS_MISMATCH) {
+                        ok = false;
+                    } else {
+                        for (uint32_t k = 0; k < mKeys.size(); ++k)
+                            AddLog(ev, mKeys[k], batch.View(b, capOff[b * G + k], capLen[b * G + k]));
+                    }
+                    ++b;
+                }
+                if (!ok || !mSourceKeyOverwritten)
+                    ev.DelContent(mSourceKey);
+                if (mCommonParserOptions.ShouldAddSourceContent(ok))
+                    AddLog(ev, mCommonParserOptions.mRenamedSourceKey, rawContent, false);
+                if (mCommonParserOptions.ShouldAddLegacyUnmatchedRawLog(ok))
+                    AddLog(ev, CommonParserOptions::legacyUnmatchedRawLogKey, rawContent, false);
+                if (mCommonParserOptions.ShouldEraseEvent(ok, ev, group.GetAllMetadata())) {
+                    mDiscardedEventsTotal.Add(1);
+                    keep = false;
+                } else {
+                    mOutSuccessfulEventsTotal.Add(1);
+                }
+            }
+        }
+        if (keep) {
+            if (wIdx != rIdx)
+                events[wIdx] = std::move(events[rIdx]);
+            ++wIdx;
+        }
+    }
+    events.resize(wIdx);
+}
+
+// ------------------------------------------------------------------------------------------------ delimiter
+const std::string ProcessorParseDelimiterNative::sName = "processor_parse_delimiter_native";
+
+bool ProcessorParseDelimiterNative::Init(const Json::Value& config) {
+    if (!GetString(config, "SourceKey", mSourceKey))
+        return Fail("mandatory string param SourceKey is missing");
+    if (!GetString(config, "Separator", mSeparator) || mSeparator.empty())
+        return Fail("mandatory string param Separator is missing");
+    if (mSeparator.size() > 4)
+        return Fail("mandatory string param Separator has more than 4 chars");
+    if (mSeparator == "\\t")
+        mSeparator = "\t";
+    std::string quote;
+    bool hasQuote = GetString(config, "Quote", quote);
+    if (mSeparator.size() == 1) {
+        if (hasQuote && quote.size() > 1)
+            return Fail("string param Quote is not a single char");
+        if (hasQuote && !quote.empty())
+            mQuote = quote[0];
+    } // multi-char separator: a configured Quote is ignored (warning upstream)
+    if (!GetKeys(config, mKeys))
+        return Fail("mandatory list param Keys is missing");
+    for (const auto& k : mKeys)
+        if (k == mSourceKey)
+            mSourceKeyOverwritten = true;
+    GetBool(config, "AllowingShortenedFields", mAllowingShortenedFields);
+    std::string t;
+    if (GetString(config, "OverflowedFieldsTreatment", t)) {
+        if (t == "keep")
+            mOverflowedFieldsTreatment = OverflowedFieldsTreatment::KEEP;
+        else if (t == "discard")
+            mOverflowedFieldsTreatment = OverflowedFieldsTreatment::DISCARD;
+    }
+    mExtractingPartialFields = mOverflowedFieldsTreatment == OverflowedFieldsTreatment::DISCARD;
+    return mCommonParserOptions.Init(config);
+}
+
+std::vector<std::pair<std::string, uint64_t>> ProcessorParseDelimiterNative::Counters() const {
+    return {{"discarded", mDiscardedEventsTotal.v},
+            {"out_failed", mOutFailedEventsTotal.v},
+            {"out_key_not_found", mOutKeyNotFoundEventsTotal.v},
+            {"out_successful", mOutSuccessfulEventsTotal.v}};
+}
+
+void ProcessorParseDelimiterNative::Process(PipelineEventGroup& group) {
+    if (group.GetEvents().empty())
+        return;
+    EventsContainer& events = group.MutableEvents();
+    FlatBatch batch;
+    for (size_t i = 0; i < events.size(); ++i) {
+        if (!IsSupportedEvent(events[i]))
+            continue;
+        const LogEvent& ev = events[i].Cast<LogEvent>();
+        if (ev.HasContent(mSourceKey))
+            batch.Add(i, ev.GetContent(mSourceKey));
+    }
+    batch.Finish(*group.GetSourceBuffer());
+    const size_t nb = batch.eventIndex.size();
+    const bool extend = mOverflowedFieldsTreatment == OverflowedFieldsTreatment::EXTEND;
+    const bool useQuote = mSeparator.size() == 1 && mQuote != mSeparator[0];
+    uint32_t MF = (uint32_t)mKeys.size() + 16;
+    std::vector<uint8_t> status(nb);
+    std::vector<uint32_t> nf(nb), fo, fl, fd;
+    for (int pass = 0; nb && pass < 2; ++pass) {
+        fo.assign((size_t)nb * MF, 0);
+        fl.assign((size_t)nb * MF, 0);
+        fd.assign((size_t)nb * MF, 0);
+        Check(lc_delim_parse(Engine(), batch.base, batch.baseLen, batch.off.data(), batch.len.data(), nb,
+                             reinterpret_cast<const uint8_t*>(mSeparator.data()), (uint32_t)mSeparator.size(),
+                             (uint8_t)mQuote, (uint32_t)mKeys.size(), extend, mAllowingShortenedFields, MF,
+                             status.data(), nf.data(), fo.data(), fl.data(), fd.data()),
+              "lc_delim_parse");
+        uint32_t mx = 0;
+        for (size_t i = 0; i < nb; ++i)
+            mx = std::max(mx, nf[i]);
+        if (mx <= MF)
+            break;
+        MF = mx; // a line with more columns than the table holds: rerun (still on the GPU) with room for all
+    }
+
+    size_t wIdx = 0, b = 0;
+    std::vector<StringView> cols;
+    for (size_t rIdx = 0; rIdx < events.size(); ++rIdx) {
+        bool keep = true;
+        PipelineEventPtr& e = events[rIdx];
+        if (!IsSupportedEvent(e)) {
+            mOutFailedEventsTotal.Add(1);
+        } else {
+            LogEvent& ev = e.Cast<LogEvent>();
+            if (!ev.HasContent(mSourceKey)) {
+                mOutKeyNotFoundEventsTotal.Add(1);
+            } else {
+                StringView buffer = ev.GetContent(mSourceKey);
+                const uint8_t st = status[b];
+                if (st == LC_DELIM_BLANK) {
+                    // empty / blank value: out_failed++, event untouched (:220-242)
+                    mOutFailedEventsTotal.Add(1);
+                } else {
+                    bool ok = st == LC_DELIM_OK;
+                    if (ok) {
+                        cols.clear();
+                        SourceBuffer& sb = *group.GetSourceBuffer();
+                        for (uint32_t j = 0; j < nf[b]; ++j) {
+                            uint32_t o = fo[(size_t)b * MF + j], l = fl[(size_t)b * MF + j], dq = fd[(size_t)b * MF + j];
+                            StringView raw = batch.View(b, o, l);
+                            if (useQuote && dq) {
+                                // AddFieldWithUnQuote (:83-113): collapse doubled quotes into a fresh arena string
+                                StringBuffer f = sb.AllocateStringBuffer(l - dq);
+                                size_t w = 0;
+                                for (size_t i = 0; i < raw.size(); ++i) {
+                                    if (raw[i] == mQuote) {
+                                        if (i + 1 < raw.size() && raw[i + 1] == mQuote) {
+                                            f.data[w++] = mQuote;
+                                            ++i;
+                                        }
+                                    } else {
+                                        f.data[w++] = raw[i];
+                                    }
+                                }
+                                cols.emplace_back(f.data, l - dq);
+                            } else {
+                                cols.push_back(raw);
+                            }
+                        }
+                        if (useQuote && !extend && cols.size() > mKeys.size()) {
+                            // overflow columns re-joined as sep + value each (:258-275)
+                            size_t need = 0;
+                            for (size_t j = mKeys.size(); j < cols.size(); ++j)
+                                need += 1 + cols[j].size();
+                            StringBuffer x = sb.AllocateStringBuffer(need);
+                            char* p = x.data;
+                            for (size_t j = mKeys.size(); j < cols.size(); ++j) {
+                                *p++ = mSeparator[0];
+                                memcpy(p, cols[j].data(), cols[j].size());
+                                p += cols[j].size();
+                            }
+                            cols.resize(mKeys.size());
+                            cols.emplace_back(x.data, need);
+                        }
+                        for (uint32_t idx = 0; idx < cols.size(); ++idx) {
+                            if (idx < mKeys.size()) {
+                                if (mExtractingPartialFields && mKeys[idx] == "_")
+                                    continue;
+                                AddLog(ev, mKeys[idx], cols[idx]);
+                            } else {
+                                if (mExtractingPartialFields)
+                                    continue;
+                                std::string key = "__column" + ToString(idx) + "__";
+                                StringBuffer kb = sb.CopyString(key);
+                                AddLog(ev, StringView(kb.data, kb.size), cols[idx]);
+                            }
+                        }
+                        mOutSuccessfulEventsTotal.Add(1);
+                    } else {
+                        mOutFailedEventsTotal.Add(1);
+                    }
+                    if (!ok || !mSourceKeyOverwritten)
+                        ev.DelContent(mSourceKey);
+                    if (mCommonParserOptions.ShouldAddSourceContent(ok))
+                        AddLog(ev, mCommonParserOptions.mRenamedSourceKey, buffer, false);
+                    if (mCommonParserOptions.ShouldAddLegacyUnmatchedRawLog(ok))
+                        AddLog(ev, CommonParserOptions::legacyUnmatchedRawLogKey, buffer, false);
+                    if (mCommonParserOptions.ShouldEraseEvent(ok, ev, group.GetAllMetadata())) {
+                        mDiscardedEventsTotal.Add(1);
+                        keep = false;
+                    }
+                }
+                ++b;
+            }
+        }
+        if (keep) {
+            if (wIdx != rIdx)
+                events[wIdx] = std::move(events[rIdx]);
+            ++wIdx;
+        }
+    }
+    events.resize(wIdx);
+}
+
+Processor* CreateProcessor(const std::string& type) {
+    if (type == ProcessorSplitLogStringNative::sName)
+        return new ProcessorSplitLogStringNative;
+    if (type == ProcessorSplitMultilineLogStringNative::sName)
+        return new ProcessorSplitMultilineLogStringNative;
+    if (type == ProcessorParseRegexNative::sName)
+        return new ProcessorParseRegexNative;
+    if (type == ProcessorParseDelimiterNative::sName)
+        return new ProcessorParseDelimiterNative;
+    return nullptr;
+}
+
+} // namespace logtail

@@ -1,0 +1,168 @@
+// Processors.h -- B200-backed replacements of LoongCollector's four native log-parsing processors behind the
+// reference's own plugin API: same class names, Init(const Json::Value&) parameters, Process(PipelineEventGroup&)
+// side effects and counters.  The per-byte work (newline scan, regex automata, delimiter FSM) happens on the
+// GPU through include/lc_b200.h; this file keeps only the host-side policy that needs the event object graph.
+//   Processor interface ............ core/collection_pipeline/plugin/interface/Processor.h:27-37
+//   CommonParserOptions ............ core/plugin/processor/CommonParserOptions.cpp:28-117
+//   MultilineOptions ............... core/file_server/MultilineOptions.cpp:22-222
+//   processors ..................... core/plugin/processor/{ProcessorParseRegexNative,ProcessorParseDelimiterNative}.cpp,
+//                                    core/plugin/processor/inner/{ProcessorSplitLogStringNative,ProcessorSplitMultilineLogStringNative}.cpp
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/lc_b200.h"
+#include "Models.h"
+
+namespace logtail {
+
+struct Counter {
+    uint64_t v = 0;
+    uint64_t GetValue() const { return v; }
+    void Add(uint64_t d) { v += d; }
+};
+
+class Processor {
+public:
+    virtual ~Processor() = default;
+    virtual const std::string& Name() const = 0;
+    virtual bool Init(const Json::Value& config) = 0;
+    virtual void Process(std::vector<PipelineEventGroup>& groups) {
+        for (auto& g : groups)
+            Process(g);
+    }
+    virtual void Process(PipelineEventGroup& group) = 0;
+    const std::string& LastError() const { return mError; }
+    // name -> value of every counter the reference registers for this plugin
+    virtual std::vector<std::pair<std::string, uint64_t>> Counters() const { return {}; }
+
+protected:
+    virtual bool IsSupportedEvent(const PipelineEventPtr& e) const = 0;
+    bool Fail(const std::string& msg) {
+        mError = msg;
+        return false;
+    }
+    std::string mError;
+};
+
+struct CommonParserOptions {
+    bool mKeepingSourceWhenParseFail = false;
+    bool mKeepingSourceWhenParseSucceed = false;
+    std::string mRenamedSourceKey;
+    bool mCopingRawLog = false;
+    static const std::string legacyUnmatchedRawLogKey;
+    bool Init(const Json::Value& config);
+    bool ShouldAddSourceContent(bool parseSuccess) const;
+    bool ShouldAddLegacyUnmatchedRawLog(bool parseSuccess) const;
+    bool ShouldEraseEvent(bool parseSuccess, const LogEvent& sourceEvent, const GroupMetadata& metadata) const;
+};
+
+struct MultilineOptions {
+    enum class UnmatchedContentTreatment { DISCARD, SINGLE_LINE };
+    std::string mStartPattern, mContinuePattern, mEndPattern;
+    UnmatchedContentTreatment mUnmatchedContentTreatment = UnmatchedContentTreatment::SINGLE_LINE;
+    bool mIgnoringUnmatchWarning = false;
+    bool mIsMultiline = false;
+    bool Init(const Json::Value& config, std::string& err);
+};
+
+class CompiledRegex {
+public:
+    CompiledRegex() = default;
+    ~CompiledRegex();
+    CompiledRegex(const CompiledRegex&) = delete;
+    CompiledRegex& operator=(const CompiledRegex&) = delete;
+    bool Compile(const std::string& pattern, std::string& err);
+    lc_regex_t* get() const { return mRe; }
+    uint32_t groups() const { return mRe ? lc_regex_ngroups(mRe) : 0; }
+
+private:
+    lc_regex_t* mRe = nullptr;
+};
+
+class ProcessorSplitLogStringNative : public Processor {
+public:
+    static const std::string sName;
+    const std::string& Name() const override { return sName; }
+    bool Init(const Json::Value& config) override;
+    void Process(PipelineEventGroup& group) override;
+    using Processor::Process;
+    std::string mSourceKey = "content";
+    char mSplitChar = '\n';
+    bool mEnableRawContent = false;
+
+protected:
+    bool IsSupportedEvent(const PipelineEventPtr& e) const override { return e.Is<LogEvent>(); }
+};
+
+class ProcessorSplitMultilineLogStringNative : public Processor {
+public:
+    static const std::string sName;
+    const std::string& Name() const override { return sName; }
+    bool Init(const Json::Value& config) override;
+    void Process(PipelineEventGroup& group) override;
+    using Processor::Process;
+    std::vector<std::pair<std::string, uint64_t>> Counters() const override;
+    std::string mSourceKey = "content";
+    MultilineOptions mMultiline;
+    bool mEnableRawContent = false;
+    Counter mMatchedEventsTotal, mMatchedLinesTotal, mUnmatchedLinesTotal;
+
+protected:
+    bool IsSupportedEvent(const PipelineEventPtr& e) const override { return e.Is<LogEvent>(); }
+
+private:
+    CompiledRegex mStart, mContinue, mEnd;
+};
+
+class ProcessorParseRegexNative : public Processor {
+public:
+    static const std::string sName;
+    const std::string& Name() const override { return sName; }
+    bool Init(const Json::Value& config) override;
+    void Process(PipelineEventGroup& group) override;
+    using Processor::Process;
+    std::vector<std::pair<std::string, uint64_t>> Counters() const override;
+    std::string mSourceKey, mRegex;
+    std::vector<std::string> mKeys;
+    CommonParserOptions mCommonParserOptions;
+    Counter mDiscardedEventsTotal, mOutFailedEventsTotal, mOutKeyNotFoundEventsTotal, mOutSuccessfulEventsTotal;
+
+protected:
+    bool IsSupportedEvent(const PipelineEventPtr& e) const override { return e.Is<LogEvent>(); }
+
+private:
+    bool mSourceKeyOverwritten = false;
+    bool mIsWholeLineMode = false;
+    CompiledRegex mReg;
+};
+
+class ProcessorParseDelimiterNative : public Processor {
+public:
+    enum class OverflowedFieldsTreatment { EXTEND, KEEP, DISCARD };
+    static const std::string sName;
+    const std::string& Name() const override { return sName; }
+    bool Init(const Json::Value& config) override;
+    void Process(PipelineEventGroup& group) override;
+    using Processor::Process;
+    std::vector<std::pair<std::string, uint64_t>> Counters() const override;
+    std::string mSourceKey, mSeparator;
+    char mQuote = '"';
+    std::vector<std::string> mKeys;
+    bool mAllowingShortenedFields = true;
+    OverflowedFieldsTreatment mOverflowedFieldsTreatment = OverflowedFieldsTreatment::EXTEND;
+    bool mExtractingPartialFields = false;
+    CommonParserOptions mCommonParserOptions;
+    Counter mDiscardedEventsTotal, mOutFailedEventsTotal, mOutKeyNotFoundEventsTotal, mOutSuccessfulEventsTotal;
+
+protected:
+    bool IsSupportedEvent(const PipelineEventPtr& e) const override { return e.Is<LogEvent>(); }
+
+private:
+    bool mSourceKeyOverwritten = false;
+};
+
+// Factory by plugin type name (the names the reference registers, PluginRegistry.cpp:183-200).
+Processor* CreateProcessor(const std::string& type);
+
+} // namespace logtail

@@ -1,0 +1,86 @@
+// host_capi.cpp -- JSON-driven C entry points over the host Processor classes (include/lc_b200_host.h).
+#include <stdlib.h>
+#include <string.h>
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/lc_b200_host.h"
+#include "Processors.h"
+
+using namespace logtail;
+
+struct lc_host_processor {
+    std::unique_ptr<Processor> proc;
+};
+
+static char* dup(const std::string& s) {
+    char* p = (char*)malloc(s.size() + 1);
+    memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+}
+
+extern "C" {
+
+lc_host_processor_t* lc_host_processor_create(const char* type, const char* config_json, char** err_out) {
+    if (err_out)
+        *err_out = nullptr;
+    std::unique_ptr<Processor> p(CreateProcessor(type ? type : ""));
+    if (!p) {
+        if (err_out)
+            *err_out = dup(std::string("unknown processor type: ") + (type ? type : "(null)"));
+        return nullptr;
+    }
+    Json::Value cfg(Json::objectValue);
+    std::string err;
+    const char* cj = config_json ? config_json : "{}";
+    if (!Json::Value::parse(cj, cj + strlen(cj), cfg, err)) {
+        if (err_out)
+            *err_out = dup("config is not valid JSON: " + err);
+        return nullptr;
+    }
+    try {
+        if (!p->Init(cfg)) {
+            if (err_out)
+                *err_out = dup("Init failed: " + p->LastError());
+            return nullptr;
+        }
+    } catch (const std::exception& e) {
+        if (err_out)
+            *err_out = dup(std::string("Init threw: ") + e.what());
+        return nullptr;
+    }
+    auto* h = new lc_host_processor;
+    h->proc = std::move(p);
+    return h;
+}
+
+void lc_host_processor_destroy(lc_host_processor_t* p) { delete p; }
+
+char* lc_host_processor_process(lc_host_processor_t* p, const char* group_json, int enable_event_meta, char** err_out) {
+    if (err_out)
+        *err_out = nullptr;
+    try {
+        auto sb = std::make_shared<SourceBuffer>();
+        PipelineEventGroup group(sb);
+        if (!group.FromJsonString(group_json ? group_json : "null"))
+            throw std::runtime_error("group JSON does not parse");
+        p->proc->Process(group);
+        return dup(group.ToJsonString(enable_event_meta != 0));
+    } catch (const std::exception& e) {
+        if (err_out)
+            *err_out = dup(e.what());
+        return nullptr;
+    }
+}
+
+char* lc_host_processor_counters(const lc_host_processor_t* p) {
+    Json::Value v(Json::objectValue);
+    for (auto& kv : p->proc->Counters())
+        v[kv.first] = Json::Value((uint64_t)kv.second);
+    return dup(v.toString());
+}
+
+void lc_host_string_free(char* s) { free(s); }
+}
