@@ -80,7 +80,7 @@ struct lc_engine {
     int smem_per_block_optin = 0;
     int smem_per_sm = 0;
     bool force_basic_regex = false;   // env LC_B200_REGEX_KERNEL=basic   (tables in global memory)
-    bool force_generic_regex = false; // env LC_B200_REGEX_KERNEL=generic (smem-staged generic interpreter)
+    int regex_variant = 0; // env LC_B200_REGEX_KERNEL: 0 auto, 1 "fast" (stride-1), 2 "fast2" (stride-2), 3 "generic"
     uint64_t scratch_hint = 0;
     // staging / workspace (grow-only)
     DevBuf in, ev_off, ev_len, out_a, out_b, out_c, out_d, out_e;
@@ -93,12 +93,12 @@ struct lc_engine {
 
 namespace {
 
-cudaError_t engine_blob(lc_engine* e, const lc_regex* r, const void** out, bool fast = false) {
+cudaError_t engine_blob(lc_engine* e, const lc_regex* r, const void** out, int layout = 0) {
     *out = nullptr;
     if (!r)
         return cudaSuccess;
-    const std::vector<uint8_t>& src = fast ? r->res.fast_blob : r->res.blob;
-    const uint64_t key = r->id * 2 + (fast ? 1 : 0);
+    const std::vector<uint8_t>& src = layout == 2 ? r->res.fast2_blob : (layout == 1 ? r->res.fast_blob : r->res.blob);
+    const uint64_t key = r->id * 4 + (uint64_t)layout;
     auto it = e->blobs.find(key);
     if (it != e->blobs.end()) {
         *out = it->second;
@@ -196,7 +196,7 @@ int lc_engine_create(int device, lc_engine_t** out) {
     {
         const char* k = getenv("LC_B200_REGEX_KERNEL");
         e->force_basic_regex = k && !strcmp(k, "basic");
-        e->force_generic_regex = k && !strcmp(k, "generic");
+        e->regex_variant = !k ? 0 : (!strcmp(k, "fast") ? 1 : (!strcmp(k, "fast2") ? 2 : (!strcmp(k, "generic") ? 3 : 0)));
     }
     CU_TRY(e->small.ensure(sizeof(Small)));
     CU_TRY(cudaMallocHost(&e->h_small, sizeof(Small)));
@@ -370,18 +370,10 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
     Small* ds = e->small.as<Small>();
     Small* hs = (Small*)e->h_small;
     const bool force_basic = e->force_basic_regex;
-    const bool use_fast = !re->res.fast_blob.empty() && !e->force_generic_regex;
-    const void* d_fast = nullptr;
-    if (use_fast)
-        CU_TRY(engine_blob(e, re, &d_fast, true));
-    const uint32_t blob_bytes = use_fast ? (uint32_t)re->res.fast_blob.size() : h->total_bytes;
-    const bool fast_multi =
-        use_fast && reinterpret_cast<const LcFastHeader*>(re->res.fast_blob.data())->reserved[0] != 0;
-    // shared-memory plan of the persistent kernel: one automaton copy per block, the rest holds labels
-    const uint32_t per = (h->mode == LC_MODE_TWOPASS && h->rev_label_bytes == 2) ? 2u : 4u;
     const size_t smem_max = (size_t)e->smem_per_block_optin;
-    if (!force_basic && blob_bytes + 4096 <= smem_max) {
-        uint32_t lab_words = 0, threads = 1024, blocks_per_sm = 1;
+    if (!force_basic) {
+        // ---- pick the kernel variant: stride-2 layout > stride-1 fast layout > generic shared-memory interpreter
+        uint64_t mx = 0, avg = base_len / n + 1;
         if (h->mode == LC_MODE_TWOPASS) {
             // size the per-thread label area from the actual length distribution: cover the longest event when
             // the batch is near-uniform, else ~1.25x the mean (longer events spill to the global slab)
@@ -391,63 +383,98 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
             CU_TRY(cudaMemcpyAsync(hs->counters, ds->counters, sizeof ds->counters, cudaMemcpyDeviceToHost,
                                    e->stream));
             CU_TRY(cudaStreamSynchronize(e->stream));
-            uint64_t mx = hs->counters[0], avg = hs->counters[1] / n + 1;
-            uint64_t cover = (mx <= avg + avg / 2 + 64) ? mx : (avg + avg / 4);
-            lab_words = (uint32_t)((cover + 15) / per + 2); // + 15: labels are shifted by the 16 B misalignment
-            if (lab_words < 8)
-                lab_words = 8;
-            size_t budget = smem_max - blob_bytes - 1024;
-            // per warp: labels (lab_words * 128 B) + capture slots of its 32 threads (fast layout only)
-            size_t slot_bytes = use_fast ? (size_t)32 * lck::fast_slot_pitch(h->ngroups) * 4 : 0;
-            uint32_t warps = (uint32_t)(budget / ((size_t)lab_words * 128 + slot_bytes));
-            if (warps < 4) { // very long average lines: keep 4 warps and let long events use the global slab
-                warps = 4;
-                lab_words = (uint32_t)((budget / 4 - slot_bytes) / 128);
-            }
-            if (warps > 32)
-                warps = 32;
-            threads = warps * 32;
-            if (warps <= 16 &&
-                2 * (blob_bytes + (size_t)warps * (lab_words * 128 + slot_bytes) + 1024) <= (size_t)e->smem_per_sm)
-                blocks_per_sm = 2;
-        } else {
-            threads = 512;
-            blocks_per_sm = 2;
+            mx = hs->counters[0];
+            avg = hs->counters[1] / n + 1;
         }
-        uint64_t need_blocks = (n + threads - 1) / threads;
-        uint32_t grid = (uint32_t)std::min<uint64_t>(need_blocks, (uint64_t)e->num_sms * blocks_per_sm);
-        // global label slab for events longer than the shared-memory budget: start small, remember what worked
-        uint64_t full = base_len / per + 2 * n + 1024;
-        uint64_t scratch_words = std::max<uint64_t>(e->scratch_hint, std::min<uint64_t>(full, 16ull << 20));
-        for (int attempt = 0; attempt < 8; ++attempt) {
-            if (h->mode == LC_MODE_TWOPASS)
-                CU_TRY(e->lab.ensure(scratch_words * 4));
-            CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof(Small) - offsetof(Small, overflow), e->stream));
-            int er;
-            if (use_fast)
-                er = lck::launch_regex_twopass_fast(d_fast, blob_bytes, fast_multi, h->ngroups, d_base, d_ev_off, d_ev_len,
-                                                    n, nkeys, d_status, d_cap_off, d_cap_len, lab_words, threads, grid,
-                                                    e->lab.as<uint32_t>(), scratch_words, &ds->bump, &ds->overflow,
-                                                    &ds->next_batch, e->stream);
-            else
-                er = lck::launch_regex_parse_fast(d_blob, blob_bytes, h->rev_label_bytes, h->ngroups, d_base, d_ev_off,
-                                                  d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len, lab_words,
-                                                  threads, grid, e->lab.as<uint32_t>(), scratch_words, &ds->bump,
-                                                  &ds->overflow, &ds->next_batch, e->stream);
-            e->launches++;
-            if (er)
-                return fail(LC_ERR_CUDA, std::string("regex kernel launch: ") + cudaGetErrorString((cudaError_t)er));
-            if (h->mode != LC_MODE_TWOPASS)
-                return LC_OK;
-            CU_TRY(cudaMemcpyAsync(&hs->overflow, &ds->overflow, 4, cudaMemcpyDeviceToHost, e->stream));
-            CU_TRY(cudaStreamSynchronize(e->stream));
-            if (!hs->overflow) {
-                e->scratch_hint = scratch_words;
-                return LC_OK;
+        const uint64_t cover = (mx <= avg + avg / 2 + 64) ? mx : (avg + avg / 4);
+        enum { V_FAST2, V_FAST, V_GENERIC } variant = V_GENERIC;
+        if (e->regex_variant == 0 || e->regex_variant == 2)
+            if (!re->res.fast2_blob.empty() && mx < 65535 && re->res.fast2_blob.size() + 32768 <= smem_max)
+                variant = V_FAST2;
+        if (variant == V_GENERIC && (e->regex_variant == 0 || e->regex_variant == 1) && !re->res.fast_blob.empty() &&
+            re->res.fast_blob.size() + 32768 <= smem_max)
+            variant = V_FAST;
+        const std::vector<uint8_t>& vb =
+            variant == V_FAST2 ? re->res.fast2_blob : (variant == V_FAST ? re->res.fast_blob : re->res.blob);
+        const uint32_t blob_bytes = (uint32_t)vb.size();
+        if (blob_bytes + 4096 <= smem_max) {
+            const void* d_vblob = d_blob;
+            if (variant != V_GENERIC)
+                CU_TRY(engine_blob(e, re, &d_vblob, variant == V_FAST2 ? 2 : 1));
+            // labels per 32-bit word: stride-2 -> 8 bytes of input, stride-1 u8 -> 4, u16 -> 2
+            const uint32_t per = variant == V_FAST2 ? 8u
+                                                    : ((h->mode == LC_MODE_TWOPASS && h->rev_label_bytes == 2 &&
+                                                        variant == V_GENERIC)
+                                                           ? 2u
+                                                           : 4u);
+            uint32_t lab_words = 0, threads = 512, blocks_per_sm = 2;
+            size_t slot_bytes = 0; // per warp
+            if (h->mode == LC_MODE_TWOPASS) {
+                lab_words = (uint32_t)((cover + 15) / per + 2); // + 15: labels are shifted by the 16 B misalignment
+                if (lab_words < 8)
+                    lab_words = 8;
+                if (variant == V_FAST2)
+                    slot_bytes = (size_t)32 * lck::fast2_slot_pitch(h->ngroups) * 2;
+                else if (variant == V_FAST)
+                    slot_bytes = (size_t)32 * lck::fast_slot_pitch(h->ngroups) * 4;
+                size_t budget = smem_max - blob_bytes - 1024;
+                uint32_t warps = (uint32_t)(budget / ((size_t)lab_words * 128 + slot_bytes));
+                if (warps < 4) { // very long average lines: keep 4 warps and let long events use the global slab
+                    warps = 4;
+                    lab_words = (uint32_t)((budget / 4 - slot_bytes) / 128);
+                }
+                if (warps > 32)
+                    warps = 32;
+                threads = warps * 32;
+                blocks_per_sm = 1;
+                if (warps <= 16 && 2 * (blob_bytes + (size_t)warps * (lab_words * 128 + slot_bytes) + 1024) <=
+                                       (size_t)e->smem_per_sm)
+                    blocks_per_sm = 2;
             }
-            scratch_words = scratch_words < full ? std::min<uint64_t>(full, scratch_words * 4) : scratch_words * 2;
+            uint64_t need_blocks = (n + threads - 1) / threads;
+            uint32_t grid = (uint32_t)std::min<uint64_t>(need_blocks, (uint64_t)e->num_sms * blocks_per_sm);
+            // global label slab for events longer than the shared-memory budget: start small, remember what worked
+            uint64_t full = base_len / per + 2 * n + 1024;
+            uint64_t scratch_words = std::max<uint64_t>(e->scratch_hint, std::min<uint64_t>(full, 16ull << 20));
+            for (int attempt = 0; attempt < 8; ++attempt) {
+                if (h->mode == LC_MODE_TWOPASS)
+                    CU_TRY(e->lab.ensure(scratch_words * 4));
+                CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof(Small) - offsetof(Small, overflow), e->stream));
+                int er;
+                if (variant == V_FAST2) {
+                    const bool multi = reinterpret_cast<const LcFast2Header*>(vb.data())->has_multi != 0;
+                    er = lck::launch_regex_fast2(d_vblob, blob_bytes, multi, h->ngroups, d_base, d_ev_off, d_ev_len, n,
+                                                 nkeys, d_status, d_cap_off, d_cap_len, lab_words, threads, grid,
+                                                 e->lab.as<uint32_t>(), scratch_words, &ds->bump, &ds->overflow,
+                                                 &ds->next_batch, e->stream);
+                } else if (variant == V_FAST) {
+                    const bool multi = reinterpret_cast<const LcFastHeader*>(vb.data())->reserved[0] != 0;
+                    er = lck::launch_regex_twopass_fast(d_vblob, blob_bytes, multi, h->ngroups, d_base, d_ev_off,
+                                                        d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len, lab_words,
+                                                        threads, grid, e->lab.as<uint32_t>(), scratch_words, &ds->bump,
+                                                        &ds->overflow, &ds->next_batch, e->stream);
+                } else {
+                    er = lck::launch_regex_parse_fast(d_vblob, blob_bytes, h->rev_label_bytes, h->ngroups, d_base,
+                                                      d_ev_off, d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len,
+                                                      lab_words, threads, grid, e->lab.as<uint32_t>(), scratch_words,
+                                                      &ds->bump, &ds->overflow, &ds->next_batch, e->stream);
+                }
+                e->launches++;
+                if (er)
+                    return fail(LC_ERR_CUDA,
+                                std::string("regex kernel launch: ") + cudaGetErrorString((cudaError_t)er));
+                if (h->mode != LC_MODE_TWOPASS)
+                    return LC_OK;
+                CU_TRY(cudaMemcpyAsync(&hs->overflow, &ds->overflow, 4, cudaMemcpyDeviceToHost, e->stream));
+                CU_TRY(cudaStreamSynchronize(e->stream));
+                if (!hs->overflow) {
+                    e->scratch_hint = scratch_words;
+                    return LC_OK;
+                }
+                scratch_words = scratch_words < full ? std::min<uint64_t>(full, scratch_words * 4) : scratch_words * 2;
+            }
+            return fail(LC_ERR_CUDA, "label scratch exhausted after retries");
         }
-        return fail(LC_ERR_CUDA, "label scratch exhausted after retries");
     }
     // ---- baseline kernel (tables in global memory); kept for A/B checks and for automata beyond shared memory
     const uint64_t* d_lab_off = nullptr;

@@ -147,3 +147,144 @@ LC_HD void lc_slots_to_cap(const uint32_t* slots, uint32_t g, uint32_t n, uint32
         *len = e - b;
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Stride-2 two-pass matcher over the fast2 layout (lc_tables.h: LcFast2Header): reference (loop) formulation.
+// The kernel's unrolled middle section is a specialisation of exactly these statements.
+struct LcFast2View {
+    const LcFast2Header* h;
+    const uint16_t* cls_hi;
+    const uint16_t* cls_lo;
+    const uint8_t* t2row; // byte addressed (u16 entries)
+    const uint8_t* t2pair;
+    const uint8_t* pid;
+    const uint8_t* pair_l;
+    const uint8_t* rev1;
+    const uint8_t* f2row;
+    const uint16_t* f2act;
+    const uint32_t* fwd1;
+    const uint64_t* masks;
+};
+
+LC_HD LcFast2View lc_fast2_view(const void* blob) {
+    const uint8_t* b = (const uint8_t*)blob;
+    const LcFast2Header* h = (const LcFast2Header*)blob;
+    LcFast2View v;
+    v.h = h;
+    v.cls_hi = (const uint16_t*)(b + h->off_cls_hi);
+    v.cls_lo = (const uint16_t*)(b + h->off_cls_lo);
+    v.t2row = b + h->off_t2row;
+    v.t2pair = b + h->off_t2pair;
+    v.pid = b + h->off_pid;
+    v.pair_l = b + h->off_pair_l;
+    v.rev1 = b + h->off_rev1;
+    v.f2row = b + h->off_f2row;
+    v.f2act = (const uint16_t*)(b + h->off_f2act);
+    v.fwd1 = (const uint32_t*)(b + h->off_fwd1);
+    v.masks = (const uint64_t*)(b + h->off_masks);
+    return v;
+}
+
+#define LC_SLOT16_UNSET 0xFFFFu
+
+LC_HD void lc_fast2_apply_mask(const LcFast2View& v, uint32_t act, uint32_t pos, uint16_t* slots) {
+    uint64_t m = v.masks[act];
+    while (m) {
+#if defined(__CUDA_ARCH__)
+        int s = __ffsll((long long)m) - 1;
+#else
+        int s = __builtin_ctzll(m);
+#endif
+        slots[s] = (uint16_t)pos;
+        m &= m - 1;
+    }
+}
+
+// single forward step of walker w under label L at position pos; returns the next walker
+LC_HD uint32_t lc_fast2_single(const LcFast2View& v, uint32_t w, uint32_t L, uint32_t pos, uint16_t* slots) {
+    const uint32_t e = v.fwd1[w * v.h->nrev + L];
+    const uint32_t a = LC_ENTRY_ACT(e);
+    if (a)
+        lc_fast2_apply_mask(v, a, pos, slots);
+    const uint32_t nx = LC_ENTRY_NEXT(e);
+    return nx == 0xFFFFu ? 0u : nx;
+}
+
+// slow path of a pair step whose first or second transition sets several slots
+LC_HD void lc_fast2_pair_slow(const LcFast2View& v, uint32_t w, uint32_t P, uint32_t pos, uint16_t* slots) {
+    const uint32_t La = v.pair_l[2 * P], Lb = v.pair_l[2 * P + 1];
+    const uint32_t w1 = lc_fast2_single(v, w, La, pos, slots);
+    (void)lc_fast2_single(v, w1, Lb, pos + 1, slots);
+}
+
+// s = first byte of the event; `mis` = virtual index of that byte (address & 15 on the device).
+// lab[j] receives the pair id of positions (2j, 2j+1) in virtual indexing; needs (n + mis) / 2 + 1 bytes.
+// slots: 2 * ngroups u16 entries preset to LC_SLOT16_UNSET.  n must be < 65535.
+LC_HD bool lc_fast2_event(const LcFast2View& v, const uint8_t* s, uint32_t mis, uint32_t n, uint8_t* lab,
+                          uint16_t* slots) {
+    const uint32_t Q = n + mis;
+    const uint32_t nrev = v.h->nrev, ncls = v.h->ncls, row_bytes = v.h->row_bytes;
+    const uint32_t start = v.h->rev_start;
+    // ---- reverse: labels of positions Q (== start) down to mis
+    uint32_t d = start;
+    uint32_t q = Q;
+    if ((q & 1) && q > mis) { // byte q-1 is the first slot of the pair (q-1, q): second slot is the end position
+        --q;
+        d = v.rev1[d * ncls + v.cls_lo[s[q - mis]] / 2];
+        if (!d)
+            return false;
+        lab[q / 2] = v.pid[d * nrev + start];
+    }
+    while (q >= mis + 2) { // full byte pair (q-2, q-1)
+        q -= 2;
+        const uint32_t addr = d * row_bytes + (uint32_t)v.cls_hi[s[q + 1 - mis]] + v.cls_lo[s[q - mis]];
+        lab[q / 2] = v.t2pair[addr >> 1];
+        d = *(const uint16_t*)(v.t2row + addr) / row_bytes;
+        if (!d)
+            return false;
+    }
+    if (q > mis) { // one byte left: it sits in the second slot of a pair whose first slot precedes the event
+        --q;
+        d = v.rev1[d * ncls + v.cls_lo[s[q - mis]] / 2];
+        if (!d)
+            return false;
+    }
+    // ---- forward; d == label of position mis
+    if (v.fwd1[d] == LC_NONE_ENTRY) // START row
+        return false;
+    uint32_t w = 0;
+    q = mis;
+    if (q & 1) {
+        w = lc_fast2_single(v, w, d, 0, slots);
+        ++q;
+    }
+    while (q + 1 <= Q) {
+        const uint32_t P = lab[q / 2];
+        const uint32_t act = v.f2act[w * 256 + P];
+        const uint32_t sa = act & 0xFFu, sb = act >> 8;
+        if (act == LC_FAST2_ACT_MULTI) {
+            lc_fast2_pair_slow(v, w, P, q - mis, slots);
+        } else {
+            if (sa)
+                slots[(sa - 2) / 2] = (uint16_t)(q - mis);
+            if (sb)
+                slots[(sb - 2) / 2] = (uint16_t)(q + 1 - mis);
+        }
+        w = v.f2row[w * 256 + P];
+        q += 2;
+    }
+    if (q == Q)
+        (void)lc_fast2_single(v, w, start, q - mis, slots);
+    return true;
+}
+
+LC_HD void lc_slots16_to_cap(const uint16_t* slots, uint32_t g, uint32_t n, uint32_t* off, uint32_t* len) {
+    uint32_t b = slots[2 * g], e = slots[2 * g + 1];
+    if (b == LC_SLOT16_UNSET || e == LC_SLOT16_UNSET || e < b) {
+        *off = n;
+        *len = 0;
+    } else {
+        *off = b;
+        *len = e - b;
+    }
+}

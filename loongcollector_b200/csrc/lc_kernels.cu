@@ -593,6 +593,274 @@ int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, bool
     return (int)cudaGetLastError();
 }
 
+// ---- stride-2 two-pass kernel over the fast2 layout (lc_tables.h: LcFast2Header) -------------------------------
+// Two input bytes per dependent look-up and one label byte per byte pair: half the dependency chain and half the
+// shared-memory label footprint of the stride-1 kernel, so twice the lines in flight at half the latency each.
+//   reverse pair step : off = cls_hi[b1] + cls_lo[b0] ; addr = row + off ; row = t2row[addr] (chain) ; P = t2pair[addr/2]
+//   forward pair step : addr = PRMT(walker, labels) = walker << 8 | P ; walker = f2row[addr] (chain) ;
+//                       act = f2act[addr] -> up to two predicated 16-bit STS into the thread's capture slots
+// Pairs are aligned on even addresses; an odd first byte / odd end position is peeled as a single step.
+struct Fast2Dev {
+    const uint8_t* cls_hi; // byte addressed u16 tables
+    const uint8_t* cls_lo;
+    const uint8_t* t2row;
+    const uint8_t* t2pair;
+    const uint8_t* f2row;
+    const uint8_t* f2act;
+    uint32_t rev_start, row_bytes;
+};
+
+struct LabSmemB { // label words interleaved [word][lane]; byte-level access for peeled / partial chunks
+    uint32_t* p;
+    __device__ __forceinline__ void st(uint32_t widx, uint32_t v) const { p[widx * 32] = v; }
+    __device__ __forceinline__ uint32_t ld(uint32_t widx) const { return p[widx * 32]; }
+    __device__ __forceinline__ void stb(uint32_t j, uint32_t v) const {
+        reinterpret_cast<uint8_t*>(p + (j >> 2) * 32)[j & 3] = (uint8_t)v;
+    }
+};
+struct LabGlobalB {
+    uint32_t* p;
+    __device__ __forceinline__ void st(uint32_t widx, uint32_t v) const { p[widx] = v; }
+    __device__ __forceinline__ uint32_t ld(uint32_t widx) const { return p[widx]; }
+    __device__ __forceinline__ void stb(uint32_t j, uint32_t v) const { reinterpret_cast<uint8_t*>(p)[j] = (uint8_t)v; }
+};
+
+#define LC2_REV_PAIR(X, HI)                                                                                           \
+    {                                                                                                                  \
+        const uint32_t b1 = __byte_perm((X), 0, (HI) ? 0x4443 : 0x4441);                                               \
+        const uint32_t b0 = __byte_perm((X), 0, (HI) ? 0x4442 : 0x4440);                                               \
+        const uint32_t off = *reinterpret_cast<const uint16_t*>(t.cls_hi + 2 * b1) +                                   \
+                             *reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * b0);                                    \
+        const uint32_t addr = row + off;                                                                               \
+        row = *reinterpret_cast<const uint16_t*>(t.t2row + addr);                                                      \
+        P = t.t2pair[addr >> 1];                                                                                       \
+    }
+
+#define LC2_FWD_PAIR(K, POS)                                                                                          \
+    {                                                                                                                  \
+        const uint32_t addr = __byte_perm(w, lw, 0x1104 + (K));                                                        \
+        w = t.f2row[addr];                                                                                             \
+        const uint32_t act = *reinterpret_cast<const uint16_t*>(t.f2act + 2 * addr);                                   \
+        const uint32_t sa = act & 0x7Fu, sb = (act >> 8) & 0x7Fu;                                                      \
+        if (sa)                                                                                                        \
+            *reinterpret_cast<uint16_t*>(slots_m2 + sa) = (uint16_t)(POS);                                             \
+        if (sb)                                                                                                        \
+            *reinterpret_cast<uint16_t*>(slots_m2 + sb) = (uint16_t)((POS) + 1);                                       \
+        if (MULTI && (act & LC_FAST2_ACT_MULTI))                                                                       \
+            lc_fast2_pair_slow(v, addr >> 8, addr & 0xFFu, (POS), reinterpret_cast<uint16_t*>(slots_m2 + 2));          \
+    }
+
+template <bool MULTI, class Lab>
+__device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev& t, const uint8_t* __restrict__ s,
+                                            const uint4* __restrict__ chunks, uint32_t mis, uint32_t n, Lab lab,
+                                            uint8_t* slots_m2 /* slot area - 2 bytes */) {
+    const uint32_t Q = n + mis;
+    const uint32_t qlo = mis + (mis & 1);      // first even position whose pair lies inside the event
+    const uint32_t Qe = Q & ~1u;               // reverse pairs cover [qlo, Qe)
+    const uint32_t Qf = (Q + 1) & ~1u;         // forward pairs cover [qlo, Qf)
+    const uint32_t ncls = v.h->ncls, nrev = v.h->nrev;
+    uint32_t d = t.rev_start;
+    // ---- reverse: peel the byte whose pair partner is the end position
+    if ((Q & 1) && n) {
+        const uint32_t b = s[n - 1];
+        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * b) >> 1)];
+        if (!d)
+            return false;
+        lab.stb((Q - 1) >> 1, v.pid[d * nrev + t.rev_start]);
+    }
+    uint32_t row = d * t.row_bytes;
+    if (Qe > qlo) {
+        const int c_hi = (int)((Qe - 1) >> 4), c_lo = (int)(qlo >> 4);
+        uint4 nxt = __ldg(chunks + c_hi);
+        for (int qc = c_hi; qc >= c_lo; --qc) {
+            const uint32_t lo = (uint32_t)qc * 16;
+            const uint4 vv = nxt;
+            if (qc > c_lo)
+                nxt = __ldg(chunks + qc - 1);
+            uint32_t P;
+            if (lo >= qlo && lo + 16 <= Qe) {
+                uint32_t lw;
+                LC2_REV_PAIR(vv.w, 1)
+                lw = P;
+                LC2_REV_PAIR(vv.w, 0)
+                lw = lw * 256 + P;
+                LC2_REV_PAIR(vv.z, 1)
+                lw = lw * 256 + P;
+                LC2_REV_PAIR(vv.z, 0)
+                lw = lw * 256 + P;
+                lab.st(qc * 2 + 1, lw);
+                LC2_REV_PAIR(vv.y, 1)
+                lw = P;
+                LC2_REV_PAIR(vv.y, 0)
+                lw = lw * 256 + P;
+                LC2_REV_PAIR(vv.x, 1)
+                lw = lw * 256 + P;
+                LC2_REV_PAIR(vv.x, 0)
+                lw = lw * 256 + P;
+                lab.st(qc * 2, lw);
+            } else {
+                const uint32_t wd[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+                for (int pi = 7; pi >= 0; --pi) {
+                    const uint32_t q = lo + 2 * pi;
+                    if (q >= qlo && q < Qe) {
+                        LC2_REV_PAIR(wd[pi >> 1], pi & 1)
+                        lab.stb(q >> 1, P);
+                    }
+                }
+            }
+            if (row == 0)
+                return false;
+        }
+    }
+    d = row / t.row_bytes;
+    // the first byte sits in the second slot of a pair whose first slot precedes the event
+    if ((mis & 1) && n) {
+        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * s[0]) >> 1)];
+        if (!d)
+            return false;
+    }
+    // ---- forward; d == label of position mis
+    if (v.fwd1[d] == LC_NONE_ENTRY)
+        return false;
+    uint32_t w = 0;
+    if (mis & 1)
+        w = lc_fast2_single(v, w, d, 0, reinterpret_cast<uint16_t*>(slots_m2 + 2));
+    if (Qf > qlo) {
+        const int c_lo = (int)(qlo >> 4), c_hi = (int)((Qf - 1) >> 4);
+        for (int qc = c_lo; qc <= c_hi; ++qc) {
+            const uint32_t lo = (uint32_t)qc * 16;
+            const uint32_t pos0 = lo - mis;
+            if (lo >= qlo && lo + 16 <= Qf) {
+                uint32_t lw = lab.ld(qc * 2);
+                LC2_FWD_PAIR(0, pos0 + 0)
+                LC2_FWD_PAIR(1, pos0 + 2)
+                LC2_FWD_PAIR(2, pos0 + 4)
+                LC2_FWD_PAIR(3, pos0 + 6)
+                lw = lab.ld(qc * 2 + 1);
+                LC2_FWD_PAIR(0, pos0 + 8)
+                LC2_FWD_PAIR(1, pos0 + 10)
+                LC2_FWD_PAIR(2, pos0 + 12)
+                LC2_FWD_PAIR(3, pos0 + 14)
+            } else {
+#pragma unroll
+                for (int wi = 0; wi < 2; ++wi) {
+                    const uint32_t q0 = lo + wi * 8;
+                    if (q0 + 8 <= qlo || q0 >= Qf)
+                        continue;
+                    const uint32_t lw = lab.ld(qc * 2 + wi);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t q = q0 + 2 * k;
+                        if (q >= qlo && q < Qf)
+                            LC2_FWD_PAIR(k, q - mis)
+                    }
+                }
+            }
+        }
+    }
+    if (!(Q & 1))
+        (void)lc_fast2_single(v, w, t.rev_start, n, reinterpret_cast<uint16_t*>(slots_m2 + 2));
+    return true;
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(1024, 1)
+    regex_fast2_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, const uint8_t* __restrict__ base,
+                       const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
+                       uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
+                       uint32_t* __restrict__ cap_len, uint32_t lab_words, uint32_t slot_pitch /* halfwords */,
+                       uint32_t* __restrict__ scratch, unsigned long long scratch_words, unsigned long long* bump,
+                       uint32_t* overflow, unsigned long long* next_batch) {
+    extern __shared__ uint4 smem[];
+    for (uint32_t k = threadIdx.x; k < blob_bytes / 16; k += blockDim.x)
+        smem[k] = __ldg(blob + k);
+    __syncthreads();
+    const LcFast2View v = lc_fast2_view(smem);
+    Fast2Dev t;
+    t.cls_hi = reinterpret_cast<const uint8_t*>(v.cls_hi);
+    t.cls_lo = reinterpret_cast<const uint8_t*>(v.cls_lo);
+    t.t2row = v.t2row;
+    t.t2pair = v.t2pair;
+    t.f2row = v.f2row;
+    t.f2act = reinterpret_cast<const uint8_t*>(v.f2act);
+    t.rev_start = v.h->rev_start;
+    t.row_bytes = v.h->row_bytes;
+    const uint32_t G = v.h->ngroups;
+    // shared memory: [blob][labels: warps x lab_words x 32 words][slots: threads x slot_pitch halfwords]
+    uint32_t* lab_base = reinterpret_cast<uint32_t*>(smem) + blob_bytes / 4;
+    uint16_t* slots = reinterpret_cast<uint16_t*>(lab_base + (size_t)(blockDim.x / 32) * lab_words * 32) +
+                      (size_t)threadIdx.x * slot_pitch;
+    uint8_t* slots_m2 = reinterpret_cast<uint8_t*>(slots) - 2;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (;;) {
+        unsigned long long batch = 0;
+        if (lane == 0)
+            batch = atomicAdd(next_batch, 32ull);
+        batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+        if (batch >= n)
+            break;
+        const uint64_t i = batch + lane;
+        if (i >= n)
+            continue;
+        const uint32_t off = ev_off[i], len = ev_len[i];
+        for (uint32_t k = 0; k < 2 * G; ++k)
+            slots[k] = LC_SLOT16_UNSET;
+        const uint8_t* s = base + off;
+        const uint64_t a16 = (uint64_t)(uintptr_t)s;
+        const uint32_t mis16 = (uint32_t)(a16 & 15u);
+        const uint4* chunks = reinterpret_cast<const uint4*>(a16 - mis16);
+        const uint32_t need = (len + mis16) / 8 + 1; // label words: one byte per byte pair
+        bool ok;
+        if (need <= lab_words) {
+            LabSmemB lab{lab_base + (size_t)wid * lab_words * 32 + lane};
+            ok = fast2_event<MULTI>(v, t, s, chunks, mis16, len, lab, slots_m2);
+        } else {
+            unsigned long long at = atomicAdd(bump, (unsigned long long)need);
+            if (at + need > scratch_words) {
+                atomicExch(overflow, 1u);
+                ok = false;
+            } else {
+                LabGlobalB lab{scratch + at};
+                ok = fast2_event<MULTI>(v, t, s, chunks, mis16, len, lab, slots_m2);
+            }
+        }
+        uint8_t st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
+        status[i] = st;
+        uint32_t* co = cap_off + i * G;
+        uint32_t* cl = cap_len + i * G;
+        for (uint32_t g = 0; g < G; ++g) {
+            uint32_t o = 0, l = 0;
+            if (st == 0) {
+                lc_slots16_to_cap(slots, g, len, &o, &l);
+                o += off;
+            }
+            co[g] = o;
+            cl[g] = l;
+        }
+    }
+}
+
+int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, uint32_t ngroups, const uint8_t* d_base,
+                       const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                       uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t lab_words,
+                       uint32_t threads, uint32_t grid, uint32_t* d_scratch, uint64_t scratch_words,
+                       unsigned long long* d_bump, uint32_t* d_overflow, unsigned long long* d_next_batch,
+                       cudaStream_t st) {
+    if (!n)
+        return 0;
+    const uint32_t slot_pitch = fast2_slot_pitch(ngroups);
+    size_t smem = fast2_smem_bytes(blob_bytes, ngroups, lab_words, threads);
+    auto k = multi ? regex_fast2_kernel<true> : regex_fast2_kernel<false>;
+    cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (er != cudaSuccess)
+        return (int)er;
+    k<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
+                                   d_cap_off, d_cap_len, lab_words, slot_pitch, d_scratch, scratch_words, d_bump,
+                                   d_overflow, d_next_batch);
+    return (int)cudaGetLastError();
+}
+
 template <class LabT>
 __global__ void __launch_bounds__(1024, 1)
     regex_parse_smem_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, uint32_t G,

@@ -63,6 +63,19 @@ int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, bool
                               uint64_t scratch_words, unsigned long long* d_bump, uint32_t* d_overflow,
                               unsigned long long* d_next_batch, cudaStream_t st);
 
+// a3 stride-2 path (LcFast2Header): labels take (len + 15) / 8 + 1 words, capture slots are u16.
+// Only valid when every event is shorter than 65535 bytes.
+inline uint32_t fast2_slot_pitch(uint32_t ngroups) { return ((ngroups + 1) | 1u) * 2; } // halfwords; odd WORD pitch
+inline size_t fast2_smem_bytes(uint32_t blob_bytes, uint32_t ngroups, uint32_t lab_words, uint32_t threads) {
+    return (size_t)blob_bytes + (size_t)(threads / 32) * lab_words * 128 + (size_t)threads * fast2_slot_pitch(ngroups) * 2;
+}
+int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, uint32_t ngroups, const uint8_t* d_base,
+                       const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                       uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t lab_words,
+                       uint32_t threads, uint32_t grid, uint32_t* d_scratch, uint64_t scratch_words,
+                       unsigned long long* d_bump, uint32_t* d_overflow, unsigned long long* d_next_batch,
+                       cudaStream_t st);
+
 // anchored prefix probe, one bool per event
 void launch_prefix_match(const void* d_blob, const uint8_t* d_base, const uint32_t* d_ev_off,
                          const uint32_t* d_ev_len, uint64_t n, uint8_t* d_out, cudaStream_t st);

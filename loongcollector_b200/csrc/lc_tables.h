@@ -101,7 +101,54 @@ struct LcFastHeader {
     uint32_t reserved[5];
 };
 
+// ---- "fast2 blob": stride-2 layout of the same two-pass automaton.  Two input bytes are consumed per dependent
+// look-up and ONE label byte is stored per byte pair, which halves both the dependency chain and the
+// shared-memory footprint per in-flight line.  Pairs are aligned on even addresses.
+//   cls_hi u16 [256]                  class(b) * ncls * 2      } byte offset of (c1, c0) inside a t2row row
+//   cls_lo u16 [256]                  class(b) * 2             }
+//   t2row  u16 [nrev][ncls*ncls]      reverse pair step from state D over bytes (b1 = later, b0 = earlier):
+//                                     next_state * row_bytes (the byte offset of its row), row_bytes = ncls*ncls*2.
+//                                     This is the ONLY table on the reverse dependency chain: addr' = t2row[addr] + off.
+//   t2pair u8  [nrev][ncls*ncls]      pair id (label of the byte pair) at the same index
+//   pid    u8  [nrev][nrev]           pair id of (label(q), label(q+1)); 0 = impossible
+//   pair_l u8  [npairs][2]            inverse of pid
+//   rev1   u8  [nrev][ncls]           single reverse step by class (line head / tail)
+//   f2row  u8  [nw][256]              forward pair step: next walker after both steps
+//   f2act  u16 [nw][256]              slot_a | slot_b << 8 : capture slot set by the 1st / 2nd step, encoded
+//                                     2*slot + 2 (0 = none); 0x8000 alone = some step sets several slots
+//                                     (slow path via pair_l + fwd1 + masks)
+//   fwd1   u32 [nw][nrev]             single forward step: next walker | action id << 16 (LC_NONE_ENTRY = no path)
+//   masks  u64 [nact]
+#define LC_FAST2_MAGIC 0x4C434632u /* 'LCF2' */
+#define LC_FAST2_ACT_MULTI 0x8000u
+struct LcFast2Header {
+    uint32_t magic;
+    uint32_t total_bytes;
+    uint32_t ngroups;
+    uint32_t rev_start;
+    uint32_t nrev;
+    uint32_t ncls;
+    uint32_t nw;
+    uint32_t npairs;
+    uint32_t nact;
+    uint32_t row_bytes; // ncls * ncls * 2
+    uint32_t off_cls_hi;
+    uint32_t off_cls_lo;
+    uint32_t off_t2row;
+    uint32_t off_t2pair;
+    uint32_t off_pid;
+    uint32_t off_pair_l;
+    uint32_t off_rev1;
+    uint32_t off_f2row;
+    uint32_t off_f2act;
+    uint32_t off_fwd1;
+    uint32_t off_masks;
+    uint32_t has_multi;
+    uint32_t reserved[2];
+};
+
 #ifdef __cplusplus
+static_assert(sizeof(LcFast2Header) % 16 == 0, "fast2 header must keep 16B alignment");
 static_assert(sizeof(LcFastHeader) % 16 == 0, "fast header must keep 16B alignment");
 static_assert(sizeof(LcRegexHeader) % 16 == 0, "header must keep 16B alignment of what follows");
 #endif

@@ -1519,6 +1519,124 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
             memcpy(fb.data(), &fh, sizeof fh);
             res.fast_blob.swap(fb);
         }
+        // ---- stride-2 layout (see lc_tables.h: LcFast2Header)
+        if (mode == LC_MODE_TWOPASS && npc == 1 && (uint32_t)nD <= 255 && (uint32_t)nw <= 255 &&
+            res.ngroups <= LC_FAST_MAX_GROUPS && actions.size() < 65535 &&
+            (uint64_t)nD * nclasses * nclasses * 2 < 65536) {
+            const uint32_t ncl = (uint32_t)nclasses;
+            auto delta = [&](uint32_t D, uint32_t c) -> uint32_t { return rev_next[(size_t)D * ncl + c]; };
+            // pair ids over (label(q), label(q+1)) combinations the reverse DFA can produce
+            std::vector<uint8_t> pid((size_t)nD * nD, 0);
+            std::vector<uint8_t> pair_l(2, 0); // id 0 = impossible
+            bool fits = true;
+            for (int Lb = 1; Lb < nD && fits; ++Lb)
+                for (uint32_t c = 0; c < ncl && fits; ++c) {
+                    uint32_t La = delta((uint32_t)Lb, c);
+                    if (!La || pid[(size_t)La * nD + Lb])
+                        continue;
+                    if (pair_l.size() / 2 >= 256) {
+                        fits = false;
+                        break;
+                    }
+                    pid[(size_t)La * nD + Lb] = (uint8_t)(pair_l.size() / 2);
+                    pair_l.push_back((uint8_t)La);
+                    pair_l.push_back((uint8_t)Lb);
+                }
+            if (fits) {
+                const uint32_t npairs = (uint32_t)pair_l.size() / 2;
+                LcFast2Header fh;
+                memset(&fh, 0, sizeof fh);
+                fh.magic = LC_FAST2_MAGIC;
+                fh.ngroups = res.ngroups;
+                fh.rev_start = rev_start;
+                fh.nrev = (uint32_t)nD;
+                fh.ncls = ncl;
+                fh.nw = (uint32_t)nw;
+                fh.npairs = npairs;
+                fh.nact = (uint32_t)actions.size();
+                fh.row_bytes = ncl * ncl * 2;
+                std::vector<uint16_t> cls_hi(256), cls_lo(256);
+                for (int b = 0; b < 256; ++b) {
+                    cls_hi[b] = (uint16_t)(byte_class[b] * ncl * 2);
+                    cls_lo[b] = (uint16_t)(byte_class[b] * 2);
+                }
+                std::vector<uint16_t> t2row((size_t)nD * ncl * ncl, 0);
+                std::vector<uint8_t> t2pair((size_t)nD * ncl * ncl, 0);
+                for (int D = 1; D < nD; ++D)
+                    for (uint32_t c1 = 0; c1 < ncl; ++c1) {
+                        uint32_t Lb = delta((uint32_t)D, c1);
+                        if (!Lb)
+                            continue;
+                        for (uint32_t c0 = 0; c0 < ncl; ++c0) {
+                            uint32_t La = delta(Lb, c0);
+                            if (!La)
+                                continue;
+                            t2row[((size_t)D * ncl + c1) * ncl + c0] = (uint16_t)(La * fh.row_bytes);
+                            t2pair[((size_t)D * ncl + c1) * ncl + c0] = pid[(size_t)La * nD + Lb];
+                        }
+                    }
+                std::vector<uint8_t> rev1((size_t)nD * ncl, 0);
+                for (int D = 0; D < nD; ++D)
+                    for (uint32_t c = 0; c < ncl; ++c)
+                        rev1[(size_t)D * ncl + c] = (uint8_t)delta((uint32_t)D, c);
+                // forward pair tables
+                const uint32_t kMulti = 0xFFFFu;
+                auto slot_code = [&](uint32_t act_id) -> uint32_t {
+                    uint64_t mk = actions[act_id];
+                    if (!mk)
+                        return 0;
+                    if (mk & (mk - 1))
+                        return kMulti;
+                    int bit = 0;
+                    while (!(mk >> bit & 1))
+                        ++bit;
+                    return 2u * (uint32_t)bit + 2u;
+                };
+                std::vector<uint8_t> f2row((size_t)nw * 256, 0);
+                std::vector<uint16_t> f2act((size_t)nw * 256, 0);
+                for (int w = 0; w < nw; ++w)
+                    for (uint32_t P = 1; P < npairs; ++P) {
+                        uint32_t La = pair_l[2 * P], Lb = pair_l[2 * P + 1];
+                        uint32_t e1 = fwd[(size_t)w * fwd_cols + La];
+                        if (e1 == LC_NONE_ENTRY || LC_ENTRY_NEXT(e1) == 0xFFFFu)
+                            continue; // not viable / MATCH cannot be followed by another step
+                        uint32_t w1 = LC_ENTRY_NEXT(e1);
+                        uint32_t e2 = fwd[(size_t)w1 * fwd_cols + Lb];
+                        if (e2 == LC_NONE_ENTRY)
+                            continue;
+                        uint32_t w2 = LC_ENTRY_NEXT(e2) == 0xFFFFu ? 0u : LC_ENTRY_NEXT(e2);
+                        uint32_t sa = slot_code(LC_ENTRY_ACT(e1)), sb = slot_code(LC_ENTRY_ACT(e2));
+                        f2row[(size_t)w * 256 + P] = (uint8_t)w2;
+                        if (sa == kMulti || sb == kMulti) {
+                            fh.has_multi = 1;
+                            f2act[(size_t)w * 256 + P] = (uint16_t)LC_FAST2_ACT_MULTI;
+                        } else {
+                            f2act[(size_t)w * 256 + P] = (uint16_t)(sa | (sb << 8));
+                        }
+                    }
+                std::vector<uint32_t> fwd1((size_t)nw * nD, LC_NONE_ENTRY);
+                for (int w = 0; w < nw; ++w)
+                    for (int D = 0; D < nD; ++D)
+                        fwd1[(size_t)w * nD + D] = fwd[(size_t)w * fwd_cols + D];
+                std::vector<uint8_t> fb(sizeof fh, 0);
+                put(fb, fh.off_cls_hi, cls_hi);
+                put(fb, fh.off_cls_lo, cls_lo);
+                put(fb, fh.off_t2row, t2row);
+                put(fb, fh.off_t2pair, t2pair);
+                put(fb, fh.off_pid, pid);
+                put(fb, fh.off_pair_l, pair_l);
+                put(fb, fh.off_rev1, rev1);
+                put(fb, fh.off_f2row, f2row);
+                put(fb, fh.off_f2act, f2act);
+                put(fb, fh.off_fwd1, fwd1);
+                put(fb, fh.off_masks, actions);
+                while (fb.size() % 16)
+                    fb.push_back(0);
+                fh.total_bytes = (uint32_t)fb.size();
+                memcpy(fb.data(), &fh, sizeof fh);
+                res.fast2_blob.swap(fb);
+            }
+        }
     } catch (const Invalid& e) {
         res.valid = false;
         res.supported = false;

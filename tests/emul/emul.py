@@ -34,6 +34,12 @@ def lib():
         L.emul_prefix_match.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
         L.emul_full_match.restype = C.c_int
         L.emul_full_match.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.emul_full_match_fast2.restype = C.c_int
+        L.emul_full_match_fast2.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.emul_fast2_bytes.restype = C.c_uint32
+        L.emul_fast2_bytes.argtypes = [C.c_void_p]
+        L.emul_fast_bytes.restype = C.c_uint32
+        L.emul_fast_bytes.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -66,6 +72,26 @@ class EmulRegex:
         if not ok:
             return None
         return [(int(co[g]), int(cl[g])) for g in range(self.ngroups)]
+
+    def full_match_fast2(self, data: bytes, mis: int = 0):
+        """stride-2 tables; returns 'n/a' when the pattern has no fast2 layout"""
+        co = np.zeros(max(self.ngroups, 1), np.uint32)
+        cl = np.zeros(max(self.ngroups, 1), np.uint32)
+        rc = lib().emul_full_match_fast2(self._h, data, len(data), mis, co.ctypes.data_as(C.c_void_p),
+                                         cl.ctypes.data_as(C.c_void_p))
+        if rc < 0:
+            return "n/a"
+        if rc == 0:
+            return None
+        return [(int(co[g]), int(cl[g])) for g in range(self.ngroups)]
+
+    @property
+    def fast2_bytes(self):
+        return int(lib().emul_fast2_bytes(self._h))
+
+    @property
+    def fast_bytes(self):
+        return int(lib().emul_fast_bytes(self._h))
 
     def __del__(self):
         try:

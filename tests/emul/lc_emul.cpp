@@ -49,6 +49,25 @@ int emul_prefix_match(const EmulRegex* e, const uint8_t* s, uint32_t n) {
     LcProgView v = lc_view(e->r.blob.data());
     return lc_prefix_match(v, s, n) ? 1 : 0;
 }
+// stride-2 layout: returns -1 when the pattern has no fast2 blob; `mis` emulates the device-side 16-byte misalignment
+int emul_full_match_fast2(const EmulRegex* e, const uint8_t* s, uint32_t n, uint32_t mis, uint32_t* cap_off,
+                          uint32_t* cap_len) {
+    if (e->r.fast2_blob.empty())
+        return -1;
+    LcFast2View v = lc_fast2_view(e->r.fast2_blob.data());
+    std::vector<uint8_t> lab((n + mis) / 2 + 2, 0);
+    uint16_t slots[2 * LC_MAX_GROUPS];
+    for (uint32_t k = 0; k < 2 * LC_MAX_GROUPS; ++k)
+        slots[k] = LC_SLOT16_UNSET;
+    if (!lc_fast2_event(v, s, mis, n, lab.data(), slots))
+        return 0;
+    for (uint32_t g = 0; g < v.h->ngroups; ++g)
+        lc_slots16_to_cap(slots, g, n, cap_off + g, cap_len + g);
+    return 1;
+}
+uint32_t emul_fast2_bytes(const EmulRegex* e) { return (uint32_t)e->r.fast2_blob.size(); }
+uint32_t emul_fast_bytes(const EmulRegex* e) { return (uint32_t)e->r.fast_blob.size(); }
+
 int emul_full_match(const EmulRegex* e, const uint8_t* s, uint32_t n, uint32_t* cap_off, uint32_t* cap_len) {
     LcProgView v = lc_view(e->r.blob.data());
     uint32_t slots[2 * LC_MAX_GROUPS];

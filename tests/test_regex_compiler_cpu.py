@@ -152,6 +152,8 @@ def test_random_patterns_agree_with_pcre2_and_python(seed):
                 continue
             assert got == want, (pat, s, got, want)
             assert e.prefix_match(s) == o.prefix_match(s), (pat, s)
+            f2 = e.full_match_fast2(s, rng.randint(0, 15))
+            assert f2 == "n/a" or f2 == want, ("fast2", pat, s, f2, want)
             if pr is not None:
                 m = pr.fullmatch(s)
                 assert (m is None) == (want is None), (pat, s)
