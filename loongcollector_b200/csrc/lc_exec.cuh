@@ -155,13 +155,11 @@ struct LcFast2View {
     const LcFast2Header* h;
     const uint16_t* cls_hi;
     const uint16_t* cls_lo;
-    const uint8_t* t2row; // byte addressed (u16 entries)
-    const uint8_t* t2pair;
+    const uint8_t* t2; // byte addressed (u32 entries)
     const uint8_t* pid;
     const uint8_t* pair_l;
     const uint8_t* rev1;
-    const uint8_t* f2row;
-    const uint16_t* f2act;
+    const uint32_t* f2;
     const uint32_t* fwd1;
     const uint64_t* masks;
 };
@@ -173,13 +171,11 @@ LC_HD LcFast2View lc_fast2_view(const void* blob) {
     v.h = h;
     v.cls_hi = (const uint16_t*)(b + h->off_cls_hi);
     v.cls_lo = (const uint16_t*)(b + h->off_cls_lo);
-    v.t2row = b + h->off_t2row;
-    v.t2pair = b + h->off_t2pair;
+    v.t2 = b + h->off_t2;
     v.pid = b + h->off_pid;
     v.pair_l = b + h->off_pair_l;
     v.rev1 = b + h->off_rev1;
-    v.f2row = b + h->off_f2row;
-    v.f2act = (const uint16_t*)(b + h->off_f2act);
+    v.f2 = (const uint32_t*)(b + h->off_f2);
     v.fwd1 = (const uint32_t*)(b + h->off_fwd1);
     v.masks = (const uint64_t*)(b + h->off_masks);
     return v;
@@ -230,7 +226,7 @@ LC_HD bool lc_fast2_event(const LcFast2View& v, const uint8_t* s, uint32_t mis, 
     uint32_t q = Q;
     if ((q & 1) && q > mis) { // byte q-1 is the first slot of the pair (q-1, q): second slot is the end position
         --q;
-        d = v.rev1[d * ncls + v.cls_lo[s[q - mis]] / 2];
+        d = v.rev1[d * ncls + v.cls_lo[s[q - mis]] / 4];
         if (!d)
             return false;
         lab[q / 2] = v.pid[d * nrev + start];
@@ -238,14 +234,15 @@ LC_HD bool lc_fast2_event(const LcFast2View& v, const uint8_t* s, uint32_t mis, 
     while (q >= mis + 2) { // full byte pair (q-2, q-1)
         q -= 2;
         const uint32_t addr = d * row_bytes + (uint32_t)v.cls_hi[s[q + 1 - mis]] + v.cls_lo[s[q - mis]];
-        lab[q / 2] = v.t2pair[addr >> 1];
-        d = *(const uint16_t*)(v.t2row + addr) / row_bytes;
+        const uint32_t e = *(const uint32_t*)(v.t2 + addr);
+        lab[q / 2] = (uint8_t)(e >> 16);
+        d = (e & 0xFFFFu) / row_bytes;
         if (!d)
             return false;
     }
     if (q > mis) { // one byte left: it sits in the second slot of a pair whose first slot precedes the event
         --q;
-        d = v.rev1[d * ncls + v.cls_lo[s[q - mis]] / 2];
+        d = v.rev1[d * ncls + v.cls_lo[s[q - mis]] / 4];
         if (!d)
             return false;
     }
@@ -260,9 +257,9 @@ LC_HD bool lc_fast2_event(const LcFast2View& v, const uint8_t* s, uint32_t mis, 
     }
     while (q + 1 <= Q) {
         const uint32_t P = lab[q / 2];
-        const uint32_t act = v.f2act[w * 256 + P];
-        const uint32_t sa = act & 0xFFu, sb = act >> 8;
-        if (act == LC_FAST2_ACT_MULTI) {
+        const uint32_t e = v.f2[w * 256 + P];
+        const uint32_t sa = (e >> 8) & 0x7Fu, sb = (e >> 16) & 0x7Fu;
+        if (e & LC_FAST2_ACT_MULTI) {
             lc_fast2_pair_slow(v, w, P, q - mis, slots);
         } else {
             if (sa)
@@ -270,7 +267,7 @@ LC_HD bool lc_fast2_event(const LcFast2View& v, const uint8_t* s, uint32_t mis, 
             if (sb)
                 slots[(sb - 2) / 2] = (uint16_t)(q + 1 - mis);
         }
-        w = v.f2row[w * 256 + P];
+        w = e & 0xFFu;
         q += 2;
     }
     if (q == Q)

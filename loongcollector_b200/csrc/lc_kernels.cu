@@ -596,17 +596,15 @@ int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, bool
 // ---- stride-2 two-pass kernel over the fast2 layout (lc_tables.h: LcFast2Header) -------------------------------
 // Two input bytes per dependent look-up and one label byte per byte pair: half the dependency chain and half the
 // shared-memory label footprint of the stride-1 kernel, so twice the lines in flight at half the latency each.
-//   reverse pair step : off = cls_hi[b1] + cls_lo[b0] ; addr = row + off ; row = t2row[addr] (chain) ; P = t2pair[addr/2]
-//   forward pair step : addr = PRMT(walker, labels) = walker << 8 | P ; walker = f2row[addr] (chain) ;
-//                       act = f2act[addr] -> up to two predicated 16-bit STS into the thread's capture slots
+//   reverse pair step : off = cls_hi[b1] + cls_lo[b0] ; e = t2[row + off] ; row = e & 0xFFFF (chain) ; P = e >> 16
+//   forward pair step : idx = PRMT(entry, labels) = walker << 8 | P ; entry = f2[idx] (chain: PRMT + LDS) ;
+//                       entry bytes 1,2 -> up to two predicated 16-bit STS into the thread's capture slots
 // Pairs are aligned on even addresses; an odd first byte / odd end position is peeled as a single step.
 struct Fast2Dev {
     const uint8_t* cls_hi; // byte addressed u16 tables
     const uint8_t* cls_lo;
-    const uint8_t* t2row;
-    const uint8_t* t2pair;
-    const uint8_t* f2row;
-    const uint8_t* f2act;
+    const uint8_t* t2;     // byte addressed u32 entries
+    const uint32_t* f2;
     uint32_t rev_start, row_bytes;
 };
 
@@ -631,23 +629,22 @@ struct LabGlobalB {
         const uint32_t b0 = __byte_perm((X), 0, (HI) ? 0x4442 : 0x4440);                                               \
         const uint32_t off = *reinterpret_cast<const uint16_t*>(t.cls_hi + 2 * b1) +                                   \
                              *reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * b0);                                    \
-        const uint32_t addr = row + off;                                                                               \
-        row = *reinterpret_cast<const uint16_t*>(t.t2row + addr);                                                      \
-        P = t.t2pair[addr >> 1];                                                                                       \
+        const uint32_t e2 = *reinterpret_cast<const uint32_t*>(t.t2 + row + off);                                      \
+        row = e2 & 0xFFFFu;                                                                                            \
+        P = e2 >> 16;                                                                                                  \
     }
 
 #define LC2_FWD_PAIR(K, POS)                                                                                          \
     {                                                                                                                  \
-        const uint32_t addr = __byte_perm(w, lw, 0x1104 + (K));                                                        \
-        w = t.f2row[addr];                                                                                             \
-        const uint32_t act = *reinterpret_cast<const uint16_t*>(t.f2act + 2 * addr);                                   \
-        const uint32_t sa = act & 0x7Fu, sb = (act >> 8) & 0x7Fu;                                                      \
+        const uint32_t idx = __byte_perm(e, lw, 0x3304 + (K)); /* walker << 8 | pair id */                             \
+        e = t.f2[idx];                                                                                                 \
+        const uint32_t sa = (e >> 8) & 0x7Fu, sb = (e >> 16) & 0x7Fu;                                                  \
         if (sa)                                                                                                        \
             *reinterpret_cast<uint16_t*>(slots_m2 + sa) = (uint16_t)(POS);                                             \
         if (sb)                                                                                                        \
             *reinterpret_cast<uint16_t*>(slots_m2 + sb) = (uint16_t)((POS) + 1);                                       \
-        if (MULTI && (act & LC_FAST2_ACT_MULTI))                                                                       \
-            lc_fast2_pair_slow(v, addr >> 8, addr & 0xFFu, (POS), reinterpret_cast<uint16_t*>(slots_m2 + 2));          \
+        if (MULTI && (e & LC_FAST2_ACT_MULTI))                                                                         \
+            lc_fast2_pair_slow(v, idx >> 8, idx & 0xFFu, (POS), reinterpret_cast<uint16_t*>(slots_m2 + 2));            \
     }
 
 template <bool MULTI, class Lab>
@@ -723,9 +720,9 @@ __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev
     // ---- forward; d == label of position mis
     if (v.fwd1[d] == LC_NONE_ENTRY)
         return false;
-    uint32_t w = 0;
+    uint32_t e = 0; // forward entry; byte 0 = current walker
     if (mis & 1)
-        w = lc_fast2_single(v, w, d, 0, reinterpret_cast<uint16_t*>(slots_m2 + 2));
+        e = lc_fast2_single(v, 0, d, 0, reinterpret_cast<uint16_t*>(slots_m2 + 2));
     if (Qf > qlo) {
         const int c_lo = (int)(qlo >> 4), c_hi = (int)((Qf - 1) >> 4);
         for (int qc = c_lo; qc <= c_hi; ++qc) {
@@ -760,7 +757,7 @@ __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev
         }
     }
     if (!(Q & 1))
-        (void)lc_fast2_single(v, w, t.rev_start, n, reinterpret_cast<uint16_t*>(slots_m2 + 2));
+        (void)lc_fast2_single(v, e & 0xFFu, t.rev_start, n, reinterpret_cast<uint16_t*>(slots_m2 + 2));
     return true;
 }
 
@@ -780,10 +777,8 @@ __global__ void __launch_bounds__(1024, 1)
     Fast2Dev t;
     t.cls_hi = reinterpret_cast<const uint8_t*>(v.cls_hi);
     t.cls_lo = reinterpret_cast<const uint8_t*>(v.cls_lo);
-    t.t2row = v.t2row;
-    t.t2pair = v.t2pair;
-    t.f2row = v.f2row;
-    t.f2act = reinterpret_cast<const uint8_t*>(v.f2act);
+    t.t2 = v.t2;
+    t.f2 = v.f2;
     t.rev_start = v.h->rev_start;
     t.row_bytes = v.h->row_bytes;
     const uint32_t G = v.h->ngroups;

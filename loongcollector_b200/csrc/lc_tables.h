@@ -104,23 +104,22 @@ struct LcFastHeader {
 // ---- "fast2 blob": stride-2 layout of the same two-pass automaton.  Two input bytes are consumed per dependent
 // look-up and ONE label byte is stored per byte pair, which halves both the dependency chain and the
 // shared-memory footprint per in-flight line.  Pairs are aligned on even addresses.
-//   cls_hi u16 [256]                  class(b) * ncls * 2      } byte offset of (c1, c0) inside a t2row row
-//   cls_lo u16 [256]                  class(b) * 2             }
-//   t2row  u16 [nrev][ncls*ncls]      reverse pair step from state D over bytes (b1 = later, b0 = earlier):
-//                                     next_state * row_bytes (the byte offset of its row), row_bytes = ncls*ncls*2.
-//                                     This is the ONLY table on the reverse dependency chain: addr' = t2row[addr] + off.
-//   t2pair u8  [nrev][ncls*ncls]      pair id (label of the byte pair) at the same index
+//   cls_hi u16 [256]                  class(b) * ncls * 4      } byte offset of (c1, c0) inside a t2 row
+//   cls_lo u16 [256]                  class(b) * 4             }
+//   t2     u32 [nrev][ncls*ncls]      reverse pair step from state D over bytes (b1 = later, b0 = earlier):
+//                                     entry = next_state * row_bytes (bits 0..15, the byte offset of its row,
+//                                     row_bytes = ncls*ncls*4) | pair_id << 16.  addr' = (t2[addr] & 0xFFFF) + off.
 //   pid    u8  [nrev][nrev]           pair id of (label(q), label(q+1)); 0 = impossible
 //   pair_l u8  [npairs][2]            inverse of pid
-//   rev1   u8  [nrev][ncls]           single reverse step by class (line head / tail)
-//   f2row  u8  [nw][256]              forward pair step: next walker after both steps
-//   f2act  u16 [nw][256]              slot_a | slot_b << 8 : capture slot set by the 1st / 2nd step, encoded
-//                                     2*slot + 2 (0 = none); 0x8000 alone = some step sets several slots
-//                                     (slow path via pair_l + fwd1 + masks)
+//   rev1   u8  [nrev][ncls]           single reverse step by class (peeled first / last byte)
+//   f2     u32 [nw][256]              forward pair step: byte0 = next walker after both steps, byte1 = slot set by
+//                                     the 1st step, byte2 = slot set by the 2nd step (2*slot + 2, 0 = none; bit 7 of
+//                                     byte1 = some step sets several slots -> slow path via pair_l + fwd1 + masks),
+//                                     byte3 = 0.  index of the next look-up = PRMT(entry, labels) = walker << 8 | pair.
 //   fwd1   u32 [nw][nrev]             single forward step: next walker | action id << 16 (LC_NONE_ENTRY = no path)
 //   masks  u64 [nact]
 #define LC_FAST2_MAGIC 0x4C434632u /* 'LCF2' */
-#define LC_FAST2_ACT_MULTI 0x8000u
+#define LC_FAST2_ACT_MULTI 0x8000u /* bit 7 of byte1 of an f2 entry */
 struct LcFast2Header {
     uint32_t magic;
     uint32_t total_bytes;
@@ -131,20 +130,18 @@ struct LcFast2Header {
     uint32_t nw;
     uint32_t npairs;
     uint32_t nact;
-    uint32_t row_bytes; // ncls * ncls * 2
+    uint32_t row_bytes; // ncls * ncls * 4
     uint32_t off_cls_hi;
     uint32_t off_cls_lo;
-    uint32_t off_t2row;
-    uint32_t off_t2pair;
+    uint32_t off_t2;
     uint32_t off_pid;
     uint32_t off_pair_l;
     uint32_t off_rev1;
-    uint32_t off_f2row;
-    uint32_t off_f2act;
+    uint32_t off_f2;
     uint32_t off_fwd1;
     uint32_t off_masks;
     uint32_t has_multi;
-    uint32_t reserved[2];
+    uint32_t reserved[4];
 };
 
 #ifdef __cplusplus

@@ -1522,7 +1522,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
         // ---- stride-2 layout (see lc_tables.h: LcFast2Header)
         if (mode == LC_MODE_TWOPASS && npc == 1 && (uint32_t)nD <= 255 && (uint32_t)nw <= 255 &&
             res.ngroups <= LC_FAST_MAX_GROUPS && actions.size() < 65535 &&
-            (uint64_t)nD * nclasses * nclasses * 2 < 65536) {
+            (uint64_t)nD * nclasses * nclasses * 4 < 65536) {
             const uint32_t ncl = (uint32_t)nclasses;
             auto delta = [&](uint32_t D, uint32_t c) -> uint32_t { return rev_next[(size_t)D * ncl + c]; };
             // pair ids over (label(q), label(q+1)) combinations the reverse DFA can produce
@@ -1554,14 +1554,13 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                 fh.nw = (uint32_t)nw;
                 fh.npairs = npairs;
                 fh.nact = (uint32_t)actions.size();
-                fh.row_bytes = ncl * ncl * 2;
+                fh.row_bytes = ncl * ncl * 4;
                 std::vector<uint16_t> cls_hi(256), cls_lo(256);
                 for (int b = 0; b < 256; ++b) {
-                    cls_hi[b] = (uint16_t)(byte_class[b] * ncl * 2);
-                    cls_lo[b] = (uint16_t)(byte_class[b] * 2);
+                    cls_hi[b] = (uint16_t)(byte_class[b] * ncl * 4);
+                    cls_lo[b] = (uint16_t)(byte_class[b] * 4);
                 }
-                std::vector<uint16_t> t2row((size_t)nD * ncl * ncl, 0);
-                std::vector<uint8_t> t2pair((size_t)nD * ncl * ncl, 0);
+                std::vector<uint32_t> t2((size_t)nD * ncl * ncl, 0);
                 for (int D = 1; D < nD; ++D)
                     for (uint32_t c1 = 0; c1 < ncl; ++c1) {
                         uint32_t Lb = delta((uint32_t)D, c1);
@@ -1571,8 +1570,8 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                             uint32_t La = delta(Lb, c0);
                             if (!La)
                                 continue;
-                            t2row[((size_t)D * ncl + c1) * ncl + c0] = (uint16_t)(La * fh.row_bytes);
-                            t2pair[((size_t)D * ncl + c1) * ncl + c0] = pid[(size_t)La * nD + Lb];
+                            t2[((size_t)D * ncl + c1) * ncl + c0] =
+                                (La * fh.row_bytes) | ((uint32_t)pid[(size_t)La * nD + Lb] << 16);
                         }
                     }
                 std::vector<uint8_t> rev1((size_t)nD * ncl, 0);
@@ -1592,8 +1591,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                         ++bit;
                     return 2u * (uint32_t)bit + 2u;
                 };
-                std::vector<uint8_t> f2row((size_t)nw * 256, 0);
-                std::vector<uint16_t> f2act((size_t)nw * 256, 0);
+                std::vector<uint32_t> f2((size_t)nw * 256, 0);
                 for (int w = 0; w < nw; ++w)
                     for (uint32_t P = 1; P < npairs; ++P) {
                         uint32_t La = pair_l[2 * P], Lb = pair_l[2 * P + 1];
@@ -1606,12 +1604,11 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                             continue;
                         uint32_t w2 = LC_ENTRY_NEXT(e2) == 0xFFFFu ? 0u : LC_ENTRY_NEXT(e2);
                         uint32_t sa = slot_code(LC_ENTRY_ACT(e1)), sb = slot_code(LC_ENTRY_ACT(e2));
-                        f2row[(size_t)w * 256 + P] = (uint8_t)w2;
                         if (sa == kMulti || sb == kMulti) {
                             fh.has_multi = 1;
-                            f2act[(size_t)w * 256 + P] = (uint16_t)LC_FAST2_ACT_MULTI;
+                            f2[(size_t)w * 256 + P] = w2 | LC_FAST2_ACT_MULTI;
                         } else {
-                            f2act[(size_t)w * 256 + P] = (uint16_t)(sa | (sb << 8));
+                            f2[(size_t)w * 256 + P] = w2 | (sa << 8) | (sb << 16);
                         }
                     }
                 std::vector<uint32_t> fwd1((size_t)nw * nD, LC_NONE_ENTRY);
@@ -1621,13 +1618,11 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                 std::vector<uint8_t> fb(sizeof fh, 0);
                 put(fb, fh.off_cls_hi, cls_hi);
                 put(fb, fh.off_cls_lo, cls_lo);
-                put(fb, fh.off_t2row, t2row);
-                put(fb, fh.off_t2pair, t2pair);
+                put(fb, fh.off_t2, t2);
                 put(fb, fh.off_pid, pid);
                 put(fb, fh.off_pair_l, pair_l);
                 put(fb, fh.off_rev1, rev1);
-                put(fb, fh.off_f2row, f2row);
-                put(fb, fh.off_f2act, f2act);
+                put(fb, fh.off_f2, f2);
                 put(fb, fh.off_fwd1, fwd1);
                 put(fb, fh.off_masks, actions);
                 while (fb.size() % 16)
