@@ -660,7 +660,7 @@ __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev
     // ---- reverse: peel the byte whose pair partner is the end position
     if ((Q & 1) && n) {
         const uint32_t b = s[n - 1];
-        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * b) >> 1)];
+        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * b) >> 2)];
         if (!d)
             return false;
         lab.stb((Q - 1) >> 1, v.pid[d * nrev + t.rev_start]);
@@ -713,7 +713,7 @@ __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev
     d = row / t.row_bytes;
     // the first byte sits in the second slot of a pair whose first slot precedes the event
     if ((mis & 1) && n) {
-        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * s[0]) >> 1)];
+        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * s[0]) >> 2)];
         if (!d)
             return false;
     }
