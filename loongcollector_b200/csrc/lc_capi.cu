@@ -89,6 +89,9 @@ struct lc_engine {
     DevBuf small;  // tickets + counters: [0..3] u32 tickets, +16: u32 n_out, +32: u64 total, +64: u64 counters[2]
     void* h_small = nullptr; // pinned mirror of `small`
     std::unordered_map<uint64_t, void*> blobs; // regex id -> device blob
+    // copy pipeline of the host-pointer entry points
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_h2d, ev_comp;
 };
 
 namespace {
@@ -146,6 +149,21 @@ int prep_desc(lc_engine* e, size_t n0, size_t n1, size_t n2, DescPlan& plan) {
     plan.r[0] = e->desc.as<uint64_t>();
     plan.r[1] = plan.r[0] + n0 + 1;
     plan.r[2] = plan.r[1] + n1 + 1;
+    return LC_OK;
+}
+
+int ensure_copy_streams(lc_engine* e, int nchunks) {
+    if (!e->s_h2d)
+        CU_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+    if (!e->s_d2h)
+        CU_TRY(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+    while ((int)e->ev_h2d.size() < nchunks) {
+        cudaEvent_t a, b;
+        CU_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        e->ev_h2d.push_back(a);
+        e->ev_comp.push_back(b);
+    }
     return LC_OK;
 }
 
@@ -219,6 +237,14 @@ void lc_engine_destroy(lc_engine_t* e) {
         cudaFree(kv.second);
     if (e->h_small)
         cudaFreeHost(e->h_small);
+    for (cudaEvent_t ev : e->ev_h2d)
+        cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_comp)
+        cudaEventDestroy(ev);
+    if (e->s_h2d)
+        cudaStreamDestroy(e->s_h2d);
+    if (e->s_d2h)
+        cudaStreamDestroy(e->s_d2h);
     if (e->stream)
         cudaStreamDestroy(e->stream);
     delete e;
@@ -524,19 +550,78 @@ int lc_regex_parse(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, ui
     CU_TRY(e->out_a.ensure(n));
     CU_TRY(e->out_b.ensure(n * G * 4 + 4));
     CU_TRY(e->out_c.ensure(n * G * 4 + 4));
-    CU_TRY(cudaMemcpyAsync(e->in.p, base, base_len, cudaMemcpyHostToDevice, e->stream));
-    CU_TRY(cudaMemcpyAsync(e->ev_off.p, ev_off, n * 4, cudaMemcpyHostToDevice, e->stream));
-    CU_TRY(cudaMemcpyAsync(e->ev_len.p, ev_len, n * 4, cudaMemcpyHostToDevice, e->stream));
-    rc = lc_regex_parse_dev(e, re, e->in.as<uint8_t>(), base_len, e->ev_off.as<uint32_t>(),
-                            e->ev_len.as<uint32_t>(), n, nkeys, e->out_a.as<uint8_t>(), e->out_b.as<uint32_t>(),
-                            e->out_c.as<uint32_t>());
+    // Large batches are pipelined: the arena is cut into chunks of whole events; all H2D copies are queued up front
+    // on a copy stream, each chunk's kernels run on the engine stream as soon as its bytes have landed, and its
+    // result tables travel back on a third stream while later chunks are still being uploaded (PCIe is full duplex).
+    const uint64_t kChunkBytes = 48ull << 20;
+    uint64_t nchunks = (base_len + kChunkBytes - 1) / kChunkBytes;
+    if (nchunks > 64)
+        nchunks = 64;
+    if (nchunks < 2 || n < nchunks * 1024) {
+        CU_TRY(cudaMemcpyAsync(e->in.p, base, base_len, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->ev_off.p, ev_off, n * 4, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->ev_len.p, ev_len, n * 4, cudaMemcpyHostToDevice, e->stream));
+        rc = lc_regex_parse_dev(e, re, e->in.as<uint8_t>(), base_len, e->ev_off.as<uint32_t>(),
+                                e->ev_len.as<uint32_t>(), n, nkeys, e->out_a.as<uint8_t>(), e->out_b.as<uint32_t>(),
+                                e->out_c.as<uint32_t>());
+        if (rc)
+            return rc;
+        CU_TRY(cudaMemcpyAsync(status, e->out_a.p, n, cudaMemcpyDeviceToHost, e->stream));
+        if (G) {
+            CU_TRY(cudaMemcpyAsync(cap_off, e->out_b.p, n * G * 4, cudaMemcpyDeviceToHost, e->stream));
+            CU_TRY(cudaMemcpyAsync(cap_len, e->out_c.p, n * G * 4, cudaMemcpyDeviceToHost, e->stream));
+        }
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        return LC_OK;
+    }
+    rc = ensure_copy_streams(e, (int)nchunks);
     if (rc)
         return rc;
-    CU_TRY(cudaMemcpyAsync(status, e->out_a.p, n, cudaMemcpyDeviceToHost, e->stream));
-    if (G) {
-        CU_TRY(cudaMemcpyAsync(cap_off, e->out_b.p, n * G * 4, cudaMemcpyDeviceToHost, e->stream));
-        CU_TRY(cudaMemcpyAsync(cap_len, e->out_c.p, n * G * 4, cudaMemcpyDeviceToHost, e->stream));
+    // event ranges per chunk (equal event counts) and the byte span each one touches
+    std::vector<uint64_t> first(nchunks + 1), lo(nchunks), hi(nchunks);
+    for (uint64_t c = 0; c <= nchunks; ++c)
+        first[c] = n * c / nchunks;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        uint64_t l = ~0ull, h = 0;
+        for (uint64_t i = first[c]; i < first[c + 1]; ++i) {
+            uint64_t o = ev_off[i], en = o + ev_len[i];
+            l = o < l ? o : l;
+            h = en > h ? en : h;
+        }
+        if (h > base_len)
+            return fail(LC_ERR_INVALID_ARG, "lc_regex_parse: event beyond base_len");
+        lo[c] = l == ~0ull ? 0 : (l & ~15ull);
+        hi[c] = h;
     }
+    uint8_t* d_in = e->in.as<uint8_t>();
+    uint32_t* d_off = e->ev_off.as<uint32_t>();
+    uint32_t* d_len = e->ev_len.as<uint32_t>();
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        uint64_t i0 = first[c], cnt = first[c + 1] - first[c];
+        if (hi[c] > lo[c])
+            CU_TRY(cudaMemcpyAsync(d_in + lo[c], base + lo[c], hi[c] - lo[c], cudaMemcpyHostToDevice, e->s_h2d));
+        CU_TRY(cudaMemcpyAsync(d_off + i0, ev_off + i0, cnt * 4, cudaMemcpyHostToDevice, e->s_h2d));
+        CU_TRY(cudaMemcpyAsync(d_len + i0, ev_len + i0, cnt * 4, cudaMemcpyHostToDevice, e->s_h2d));
+        CU_TRY(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
+    }
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        uint64_t i0 = first[c], cnt = first[c + 1] - first[c];
+        CU_TRY(cudaStreamWaitEvent(e->stream, e->ev_h2d[c], 0));
+        rc = lc_regex_parse_dev(e, re, d_in, base_len, d_off + i0, d_len + i0, cnt, nkeys, e->out_a.as<uint8_t>() + i0,
+                                e->out_b.as<uint32_t>() + i0 * G, e->out_c.as<uint32_t>() + i0 * G);
+        if (rc)
+            return rc;
+        CU_TRY(cudaEventRecord(e->ev_comp[c], e->stream));
+        CU_TRY(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[c], 0));
+        CU_TRY(cudaMemcpyAsync(status + i0, e->out_a.as<uint8_t>() + i0, cnt, cudaMemcpyDeviceToHost, e->s_d2h));
+        if (G) {
+            CU_TRY(cudaMemcpyAsync(cap_off + i0 * G, e->out_b.as<uint32_t>() + i0 * G, cnt * G * 4,
+                                   cudaMemcpyDeviceToHost, e->s_d2h));
+            CU_TRY(cudaMemcpyAsync(cap_len + i0 * G, e->out_c.as<uint32_t>() + i0 * G, cnt * G * 4,
+                                   cudaMemcpyDeviceToHost, e->s_d2h));
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(e->s_d2h));
     CU_TRY(cudaStreamSynchronize(e->stream));
     return LC_OK;
 }

@@ -322,3 +322,19 @@ def test_regex_kernel_variants_agree(variant, monkeypatch):
             _check_parse(e, pattern, lines)
     finally:
         e.close()
+
+
+def test_regex_parse_pipelined_host_path_full_size(eng):
+    """> 96 MB through the host-pointer API takes the chunked H2D / kernel / D2H pipeline; every row is checked."""
+    lc = _lc()
+    from loongcollector_b200 import synth
+    buf, off, ln = synth.nginx_lines(600000, seed=4242, line_bytes=256)
+    rx = lc.Regex(synth.NGINX_PATTERN)
+    st, co, cl = eng.regex_parse(rx, buf, off, ln, 10)
+    est, eco, ecl = orc.regex_parse_batch(orc.Regex(synth.NGINX_PATTERN), buf, off, ln, 10)
+    assert np.array_equal(st, est) and np.array_equal(co, eco) and np.array_equal(cl, ecl)
+    # ragged natural-length lines, same path
+    buf, off, ln = synth.nginx_lines(700000, seed=4243, line_bytes=None)
+    st, co, cl = eng.regex_parse(rx, buf, off, ln, 10)
+    est, eco, ecl = orc.regex_parse_batch(orc.Regex(synth.NGINX_PATTERN), buf, off, ln, 10)
+    assert np.array_equal(st, est) and np.array_equal(co, eco) and np.array_equal(cl, ecl)
