@@ -128,6 +128,26 @@ def profile_traffic():
     return None
 
 
+def job_throughput(bytes_local, ms_local, world, device="cpu"):
+    """Whole-job MB/s under weak scaling: every rank parses its own shard, the job finishes when the slowest
+    rank does -> sum of the shard bytes / max over ranks of the step time.  Uses the default process group
+    (NCCL on GPUs, gloo in the CPU tests); no data-path collective, just this 2-number reduction."""
+    import torch
+    t = torch.tensor([float(ms_local)], dtype=torch.float64, device=device)
+    b = torch.tensor([float(bytes_local)], dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    return float(b.item()) / (ms * 1e-3) / 1e6, ms
+
+
+def shard_seed(rank):
+    """Shards are independent event groups: rank r generates (and owns) its own lines."""
+    return 20260922 + rank
+
+
 def make_workload(n_lines, seed):
     from loongcollector_b200 import synth
     return synth.nginx_lines(n_lines, seed=seed, line_bytes=LINE_BYTES)
@@ -223,7 +243,7 @@ def run_ours(args):
     nkeys = len(synth.NGINX_KEYS)
 
     n = args.lines
-    buf, off, ln = make_workload(n, 20260922 + rank)
+    buf, off, ln = make_workload(n, shard_seed(rank))
     in_bytes = int(buf.size)
     # pinned host arena (the SourceBuffer stand-in) + pinned result tables
     L = lc.lib()
@@ -290,15 +310,8 @@ def run_ours(args):
     st = d_status.cpu().numpy()
     ok_lines = int((st == 0).sum())
 
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    tk = torch.tensor([kern_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tk, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    kern_ms = float(tk.item())
-    ms_per_step = total_ms / args.steps
-    value = in_bytes * world / (ms_per_step * 1e-3) / 1e6
+    value, ms_per_step = job_throughput(in_bytes, total_ms / args.steps, world, dev)
+    _, kern_ms = job_throughput(in_bytes, kern_ms, world, dev)
 
     # ---- end-to-end through the host-pointer C-ABI (pinned host arena in, result tables out)
     e2e = None
@@ -319,12 +332,10 @@ def run_ours(args):
             step_host()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / e_steps
-        te = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dt = float(te.item())
+        e2e_value, e2e_ms = job_throughput(in_bytes, dt * 1e3, world, dev)
+        dt = e2e_ms * 1e-3
         assert np.array_equal(h_status, st), "host-API result differs from device-API result"
-        e2e = {"value": in_bytes * world / dt / 1e6, "unit": UNIT,
+        e2e = {"value": e2e_value, "unit": UNIT,
                "h2d_bytes_per_step": int(in_bytes + 8 * n), "d2h_bytes_per_step": int(n * (1 + 8 * G)),
                "ms_per_step": dt * 1e3, "steps": e_steps}
 
