@@ -33,7 +33,7 @@ _ALNUM = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789"
 
 
 def _rand_word(rng, n):
-    return "".join(rng.choice(_ALNUM) for _ in range(n))
+    return "".join(rng.choices(_ALNUM, k=n))
 
 
 def _nginx_line(rng, target_len=None, bad=False):
@@ -117,16 +117,10 @@ def _assemble(pool, n, seed):
         off = (np.arange(n, dtype=np.int64) * lens[0])
         ln = np.full(n, lens[0] - 1, np.int64)
     else:
-        pool_buf = np.frombuffer(b"".join(pool), np.uint8)
-        pool_off = np.zeros(len(pool), np.int64)
-        pool_off[1:] = np.cumsum(lens[:-1])
         l = lens[idx]
         off = np.zeros(n, np.int64)
         off[1:] = np.cumsum(l[:-1])
-        total = int(off[-1] + l[-1]) if n else 0
-        # gather: positions of every output byte in the pool buffer
-        src = np.repeat(pool_off[idx] - off, l) + np.arange(total, dtype=np.int64)
-        buf = pool_buf[src]
+        buf = np.frombuffer(b"".join(map(pool.__getitem__, idx.tolist())), np.uint8)
         ln = l - 1
     return np.ascontiguousarray(buf), off.astype(np.uint32), ln.astype(np.uint32)
 

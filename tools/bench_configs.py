@@ -34,6 +34,7 @@ def timeit(fn, steps=5, warmup=2):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--only", default="", help="comma list of configs to run (c1,c3,c4,c5); default all")
     args = ap.parse_args()
     import torch
     import loongcollector_b200 as lc
@@ -146,6 +147,44 @@ def main():
     out.append({"config": "C4 ProcessorParseDelimiterNative -> ProcessorParseRegexNative chain, %d CSV lines" % n4,
                 "MBps": cb.size / dt / 1e6, "lines_per_s": n4 / dt, "roofline_frac": alg / dt / 1e9 / peak,
                 "cpu_oracle_1thread_MBps": cpu, "ms": dt * 1e3})
+    # ------------------------------------------------------------------ C5: Zipf 64 B - 8 KB, nginx + apache patterns
+    n5 = int((1 << 20) * args.scale)
+    zb, zoff, zlen, zkind = synth.zipf_mixed_lines(n5)
+    d_z = dput(zb)
+    pats = [(synth.NGINX_PATTERN, ~zkind), (synth.APACHE_PATTERN, zkind)]
+    work = []
+    for pat, sel in pats:
+        r = lc.Regex(pat)
+        o_, l_ = np.ascontiguousarray(zoff[sel]), np.ascontiguousarray(zlen[sel])
+        m = o_.size
+        work.append((r, dput(o_.view(np.int32)), dput(l_.view(np.int32)), m,
+                     torch.empty(m, dtype=torch.uint8, device=dev),
+                     torch.empty(m * r.ngroups, dtype=torch.int32, device=dev),
+                     torch.empty(m * r.ngroups, dtype=torch.int32, device=dev), pat, o_, l_))
+
+    def c5():
+        for r, do, dl, m, s_, co_, cl_, _, _, _ in work:
+            eng.regex_parse_dev(r, d_z.data_ptr(), zb.size, do.data_ptr(), dl.data_ptr(), m, r.ngroups, s_.data_ptr(),
+                                co_.data_ptr(), cl_.data_ptr())
+
+    dt = timeit(c5, steps=3, warmup=1)
+    alg = 0
+    t_cpu = 0.0
+    cpu_bytes = 0
+    for r, do, dl, m, s_, co_, cl_, pat, o_, l_ in work:
+        alg += int(l_.astype(np.int64).sum()) + m * (8 + 8 * r.ngroups + 1)
+        ns = min(m, 4096)
+        t0 = time.perf_counter()
+        est, eco, ecl = orc.regex_parse_batch(orc.Regex(pat), zb, o_[:ns], l_[:ns], r.ngroups)
+        t_cpu += time.perf_counter() - t0
+        cpu_bytes += int(l_[:ns].astype(np.int64).sum())
+        assert np.array_equal(s_[:ns].cpu().numpy(), est)
+        assert np.array_equal(co_.view(m, r.ngroups)[:ns].cpu().numpy().view(np.uint32), eco)
+        assert np.array_equal(cl_.view(m, r.ngroups)[:ns].cpu().numpy().view(np.uint32), ecl)
+    out.append({"config": "C5 mixed nginx+apache regex, Zipf 64 B-8 KB lines, %d lines (%.0f B avg)" %
+                          (n5, zb.size / n5), "MBps": zb.size / dt / 1e6, "lines_per_s": n5 / dt,
+                "roofline_frac": alg / dt / 1e9 / peak, "cpu_oracle_1thread_MBps": cpu_bytes / t_cpu / 1e6,
+                "ms": dt * 1e3})
     for o in out:
         print(json.dumps(o))
     eng.close()
