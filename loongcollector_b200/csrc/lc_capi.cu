@@ -445,9 +445,16 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
                     slot_bytes = (size_t)32 * lck::fast_slot_pitch(h->ngroups) * 4;
                 size_t budget = smem_max - blob_bytes - 1024;
                 uint32_t warps = (uint32_t)(budget / ((size_t)lab_words * 128 + slot_bytes));
-                if (warps < 4) { // very long average lines: keep 4 warps and let long events use the global slab
-                    warps = 4;
-                    lab_words = (uint32_t)((budget / 4 - slot_bytes) / 128);
+                // Long lines: labels in shared memory would leave a handful of resident warps (measured: 20x
+                // slower).  Keep >= kMinWarps warps resident and let events that do not fit keep their labels in
+                // the global slab instead (L2-resident while in flight; +1 B of traffic per input byte worst case).
+                const uint32_t kMinWarps = 20;
+                if (warps < kMinWarps) {
+                    warps = kMinWarps;
+                    size_t per_warp = budget / kMinWarps;
+                    lab_words = per_warp > slot_bytes + 8 * 128 ? (uint32_t)((per_warp - slot_bytes) / 128) : 8;
+                    while (warps > 4 && (size_t)warps * ((size_t)lab_words * 128 + slot_bytes) > budget)
+                        --warps;
                 }
                 if (warps > 32)
                     warps = 32;
@@ -462,6 +469,11 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
             // global label slab for events longer than the shared-memory budget: start small, remember what worked
             uint64_t full = base_len / per + 2 * n + 1024;
             uint64_t scratch_words = std::max<uint64_t>(e->scratch_hint, std::min<uint64_t>(full, 16ull << 20));
+            if (h->mode == LC_MODE_TWOPASS && (mx + 15) / per + 2 > lab_words) {
+                // some events spill: provision the upper bound of what ALL events could need (no retry runs)
+                uint64_t bound = (hs->counters[1] + 16 * n) / per + 2 * n + 1024;
+                scratch_words = std::max(scratch_words, bound);
+            }
             for (int attempt = 0; attempt < 8; ++attempt) {
                 if (h->mode == LC_MODE_TWOPASS)
                     CU_TRY(e->lab.ensure(scratch_words * 4));
