@@ -84,7 +84,7 @@ struct lc_engine {
     uint64_t scratch_hint = 0;
     // staging / workspace (grow-only)
     DevBuf in, ev_off, ev_len, out_a, out_b, out_c, out_d, out_e;
-    DevBuf lines_off, lines_len, flags, state, cnt, pos, lab_sizes, lab_off, lab;
+    DevBuf lines_off, lines_len, flags, state, cnt, pos, lab_sizes, lab_off, lab, order;
     DevBuf desc;   // look-back descriptors (3 regions)
     DevBuf small;  // tickets + counters: [0..3] u32 tickets, +16: u32 n_out, +32: u64 total, +64: u64 counters[2]
     void* h_small = nullptr; // pinned mirror of `small`
@@ -230,7 +230,7 @@ void lc_engine_destroy(lc_engine_t* e) {
         cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->in, &e->ev_off, &e->ev_len, &e->out_a, &e->out_b, &e->out_c, &e->out_d, &e->out_e,
                       &e->lines_off, &e->lines_len, &e->flags, &e->state, &e->cnt, &e->pos, &e->lab_sizes,
-                      &e->lab_off, &e->lab, &e->desc, &e->small};
+                      &e->lab_off, &e->lab, &e->order, &e->desc, &e->small};
     for (DevBuf* b : bufs)
         b->release();
     for (auto& kv : e->blobs)
@@ -474,6 +474,15 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
                 uint64_t bound = (hs->counters[1] + 16 * n) / per + 2 * n + 1024;
                 scratch_words = std::max(scratch_words, bound);
             }
+            // ragged batch: visit events in descending length-bucket order (a warp costs its longest line)
+            const uint32_t* d_order = nullptr;
+            if (h->mode == LC_MODE_TWOPASS && mx > 2 * avg + 64 && n >= 4096) {
+                CU_TRY(e->order.ensure(n * 4 + 256));
+                uint32_t* hist = e->order.as<uint32_t>() + n;
+                lck::launch_length_order(d_ev_len, n, hist, e->order.as<uint32_t>(), e->stream);
+                e->launches += 3;
+                d_order = e->order.as<uint32_t>();
+            }
             for (int attempt = 0; attempt < 8; ++attempt) {
                 if (h->mode == LC_MODE_TWOPASS)
                     CU_TRY(e->lab.ensure(scratch_words * 4));
@@ -484,18 +493,18 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
                     er = lck::launch_regex_fast2(d_vblob, blob_bytes, multi, h->ngroups, d_base, d_ev_off, d_ev_len, n,
                                                  nkeys, d_status, d_cap_off, d_cap_len, lab_words, threads, grid,
                                                  e->lab.as<uint32_t>(), scratch_words, &ds->bump, &ds->overflow,
-                                                 &ds->next_batch, e->stream);
+                                                 &ds->next_batch, d_order, e->stream);
                 } else if (variant == V_FAST) {
                     const bool multi = reinterpret_cast<const LcFastHeader*>(vb.data())->reserved[0] != 0;
                     er = lck::launch_regex_twopass_fast(d_vblob, blob_bytes, multi, h->ngroups, d_base, d_ev_off,
                                                         d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len, lab_words,
                                                         threads, grid, e->lab.as<uint32_t>(), scratch_words, &ds->bump,
-                                                        &ds->overflow, &ds->next_batch, e->stream);
+                                                        &ds->overflow, &ds->next_batch, d_order, e->stream);
                 } else {
                     er = lck::launch_regex_parse_fast(d_vblob, blob_bytes, h->rev_label_bytes, h->ngroups, d_base,
                                                       d_ev_off, d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len,
                                                       lab_words, threads, grid, e->lab.as<uint32_t>(), scratch_words,
-                                                      &ds->bump, &ds->overflow, &ds->next_batch, e->stream);
+                                                      &ds->bump, &ds->overflow, &ds->next_batch, d_order, e->stream);
                 }
                 e->launches++;
                 if (er)

@@ -218,6 +218,68 @@ void launch_len_stats(const uint32_t* d_ev_len, uint64_t n, unsigned long long* 
     len_stats_kernel<<<grid, 256, 0, st>>>(d_ev_len, n, d_out);
 }
 
+// Ragged batches: events are visited in descending length-bucket order so that the 32 lanes of a warp walk lines
+// of similar length (a warp costs as much as its longest line).  bucket = 2*floor(log2(len)) + next bit.
+__device__ __forceinline__ uint32_t len_bucket(uint32_t len) {
+    if (len < 2)
+        return len;
+    uint32_t lg = 31 - __clz(len);
+    return 2 * lg + ((len >> (lg - 1)) & 1);
+}
+__global__ void __launch_bounds__(256)
+    bucket_hist_kernel(const uint32_t* __restrict__ ev_len, uint64_t n, uint32_t* __restrict__ hist /* [64] */) {
+    __shared__ uint32_t sh[64];
+    if (threadIdx.x < 64)
+        sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh[len_bucket(ev_len[i])], 1u);
+    __syncthreads();
+    if (threadIdx.x < 64 && sh[threadIdx.x])
+        atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void bucket_scan_kernel(uint32_t* hist /* [64] in: counts, out: start cursor, longest bucket first */) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t run = 0;
+        for (int b = 63; b >= 0; --b) {
+            uint32_t c = hist[b];
+            hist[b] = run;
+            run += c;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+    bucket_fill_kernel(const uint32_t* __restrict__ ev_len, uint64_t n, uint32_t* __restrict__ cursor,
+                       uint32_t* __restrict__ order) {
+    // block-local ranking keeps the global atomics to one per (block, bucket)
+    __shared__ uint32_t cnt[64], basep[64];
+    if (threadIdx.x < 64)
+        cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t b = 0, r = 0;
+    if (i < n) {
+        b = len_bucket(ev_len[i]);
+        r = atomicAdd(&cnt[b], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && cnt[threadIdx.x])
+        basep[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]);
+    __syncthreads();
+    if (i < n)
+        order[basep[b] + r] = (uint32_t)i;
+}
+void launch_length_order(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_hist64, uint32_t* d_order,
+                         cudaStream_t st) {
+    if (!n)
+        return;
+    cudaMemsetAsync(d_hist64, 0, 64 * sizeof(uint32_t), st);
+    unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 1184);
+    bucket_hist_kernel<<<grid, 256, 0, st>>>(d_ev_len, n, d_hist64);
+    bucket_scan_kernel<<<1, 32, 0, st>>>(d_hist64);
+    bucket_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ev_len, n, d_hist64, d_order);
+}
+
 // One thread per event; tables read through the read-only path from global memory.
 __global__ void __launch_bounds__(128)
     regex_parse_basic_kernel(const void* __restrict__ blob, uint32_t mode, uint32_t G, const uint8_t* __restrict__ base,
@@ -508,7 +570,7 @@ __global__ void __launch_bounds__(1024, 1)
                               uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
                               uint32_t* __restrict__ cap_len, uint32_t lab_words, uint32_t slot_pitch,
                               uint32_t* __restrict__ scratch, unsigned long long scratch_words,
-                              unsigned long long* bump, uint32_t* overflow, unsigned long long* next_batch) {
+                              unsigned long long* bump, uint32_t* overflow, unsigned long long* next_batch, const uint32_t* __restrict__ order) {
     extern __shared__ uint4 smem[];
     for (uint32_t k = threadIdx.x; k < blob_bytes / 16; k += blockDim.x)
         smem[k] = __ldg(blob + k);
@@ -533,9 +595,9 @@ __global__ void __launch_bounds__(1024, 1)
         batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
         if (batch >= n)
             break;
-        const uint64_t i = batch + lane;
-        if (i >= n)
+        if (batch + lane >= n)
             continue;
+        const uint64_t i = order ? order[batch + lane] : batch + lane;
         const uint32_t off = ev_off[i], len = ev_len[i];
         for (uint32_t k = 0; k < 2 * G; ++k)
             slots[k] = LC_SLOT_UNSET;
@@ -578,7 +640,7 @@ int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, bool
                               uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
                               uint32_t lab_words, uint32_t threads, uint32_t grid, uint32_t* d_scratch,
                               uint64_t scratch_words, unsigned long long* d_bump, uint32_t* d_overflow,
-                              unsigned long long* d_next_batch, cudaStream_t st) {
+                              unsigned long long* d_next_batch, const uint32_t* d_order, cudaStream_t st) {
     if (!n)
         return 0;
     const uint32_t slot_pitch = fast_slot_pitch(ngroups);
@@ -589,7 +651,7 @@ int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, bool
         return (int)er;
     k<<<grid, threads, smem, st>>>((const uint4*)d_fast_blob, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
                                    d_cap_off, d_cap_len, lab_words, slot_pitch, d_scratch, scratch_words, d_bump,
-                                   d_overflow, d_next_batch);
+                                   d_overflow, d_next_batch, d_order);
     return (int)cudaGetLastError();
 }
 
@@ -768,7 +830,7 @@ __global__ void __launch_bounds__(1024, 1)
                        uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
                        uint32_t* __restrict__ cap_len, uint32_t lab_words, uint32_t slot_pitch /* halfwords */,
                        uint32_t* __restrict__ scratch, unsigned long long scratch_words, unsigned long long* bump,
-                       uint32_t* overflow, unsigned long long* next_batch) {
+                       uint32_t* overflow, unsigned long long* next_batch, const uint32_t* __restrict__ order) {
     extern __shared__ uint4 smem[];
     for (uint32_t k = threadIdx.x; k < blob_bytes / 16; k += blockDim.x)
         smem[k] = __ldg(blob + k);
@@ -795,9 +857,9 @@ __global__ void __launch_bounds__(1024, 1)
         batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
         if (batch >= n)
             break;
-        const uint64_t i = batch + lane;
-        if (i >= n)
+        if (batch + lane >= n)
             continue;
+        const uint64_t i = order ? order[batch + lane] : batch + lane;
         const uint32_t off = ev_off[i], len = ev_len[i];
         for (uint32_t k = 0; k < 2 * G; ++k)
             slots[k] = LC_SLOT16_UNSET;
@@ -841,7 +903,7 @@ int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, uint
                        uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t lab_words,
                        uint32_t threads, uint32_t grid, uint32_t* d_scratch, uint64_t scratch_words,
                        unsigned long long* d_bump, uint32_t* d_overflow, unsigned long long* d_next_batch,
-                       cudaStream_t st) {
+                       const uint32_t* d_order, cudaStream_t st) {
     if (!n)
         return 0;
     const uint32_t slot_pitch = fast2_slot_pitch(ngroups);
@@ -852,7 +914,7 @@ int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, uint
         return (int)er;
     k<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
                                    d_cap_off, d_cap_len, lab_words, slot_pitch, d_scratch, scratch_words, d_bump,
-                                   d_overflow, d_next_batch);
+                                   d_overflow, d_next_batch, d_order);
     return (int)cudaGetLastError();
 }
 
@@ -864,7 +926,7 @@ __global__ void __launch_bounds__(1024, 1)
                             uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
                             uint32_t* __restrict__ cap_len, uint32_t lab_words /* per thread, in smem */,
                             uint32_t* __restrict__ scratch, unsigned long long scratch_words,
-                            unsigned long long* bump, uint32_t* overflow, unsigned long long* next_batch) {
+                            unsigned long long* bump, uint32_t* overflow, unsigned long long* next_batch, const uint32_t* __restrict__ order) {
     extern __shared__ uint4 smem[];
     // stage the automaton
     for (uint32_t k = threadIdx.x; k < blob_bytes / 16; k += blockDim.x)
@@ -881,9 +943,9 @@ __global__ void __launch_bounds__(1024, 1)
     batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
     if (batch >= n)
         break;
-    const uint64_t i = batch + lane;
-    if (i >= n)
+    if (batch + lane >= n)
         continue;
+    const uint64_t i = order ? order[batch + lane] : batch + lane;
     const uint32_t off = ev_off[i], len = ev_len[i];
     // aligned view of the arena: byte loads go through 32-bit words of the 4-byte aligned base
     const uint32_t mis = (uint32_t)((uintptr_t)base & 3u);
@@ -939,7 +1001,7 @@ int launch_regex_parse_fast(const void* d_blob, uint32_t blob_bytes, uint32_t re
                             uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
                             uint32_t lab_words, uint32_t threads, uint32_t grid, uint32_t* d_scratch,
                             uint64_t scratch_words, unsigned long long* d_bump, uint32_t* d_overflow,
-                            unsigned long long* d_next_batch, cudaStream_t st) {
+                            unsigned long long* d_next_batch, const uint32_t* d_order, cudaStream_t st) {
     if (!n)
         return 0;
     size_t smem = blob_bytes + (size_t)(threads / 32) * lab_words * 32 * 4;
@@ -952,11 +1014,11 @@ int launch_regex_parse_fast(const void* d_blob, uint32_t blob_bytes, uint32_t re
     if (rev_label_bytes == 2)
         k16<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, ngroups, d_base, d_ev_off, d_ev_len, n, nkeys,
                                          d_status, d_cap_off, d_cap_len, lab_words, d_scratch, scratch_words, d_bump,
-                                         d_overflow, d_next_batch);
+                                         d_overflow, d_next_batch, d_order);
     else
         k8<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, ngroups, d_base, d_ev_off, d_ev_len, n, nkeys,
                                         d_status, d_cap_off, d_cap_len, lab_words, d_scratch, scratch_words, d_bump,
-                                        d_overflow, d_next_batch);
+                                        d_overflow, d_next_batch, d_order);
     return (int)cudaGetLastError();
 }
 

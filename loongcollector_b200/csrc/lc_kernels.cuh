@@ -39,6 +39,10 @@ void launch_label_sizes(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_sizes,
 // d_out[0] = max(ev_len), d_out[1] = sum(ev_len); d_out must be zeroed by the caller
 void launch_len_stats(const uint32_t* d_ev_len, uint64_t n, unsigned long long* d_out, cudaStream_t st);
 
+// order[] = event indices sorted by descending length bucket (d_hist64: 64-word scratch); 3 launches
+void launch_length_order(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_hist64, uint32_t* d_order,
+                         cudaStream_t st);
+
 // a3 fast path: persistent kernel, automaton staged in shared memory.  Labels of events needing
 // <= lab_words 32-bit words stay in shared memory, longer events bump-allocate from d_scratch.
 // d_bump, d_overflow and d_next_batch must be zeroed by the caller.  Dynamic shared memory =
@@ -48,7 +52,7 @@ int launch_regex_parse_fast(const void* d_blob, uint32_t blob_bytes, uint32_t re
                             uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
                             uint32_t lab_words, uint32_t threads, uint32_t grid, uint32_t* d_scratch,
                             uint64_t scratch_words, unsigned long long* d_bump, uint32_t* d_overflow,
-                            unsigned long long* d_next_batch, cudaStream_t st);
+                            unsigned long long* d_next_batch, const uint32_t* d_order, cudaStream_t st);
 
 // a3 fastest path: two-pass automaton in the host-built fast layout (LcFastHeader).  Shared memory per block =
 // blob + labels (threads/32 * lab_words * 128 B) + capture slots (threads * slot_pitch * 4 B).
@@ -61,7 +65,7 @@ int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, bool
                               uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
                               uint32_t lab_words, uint32_t threads, uint32_t grid, uint32_t* d_scratch,
                               uint64_t scratch_words, unsigned long long* d_bump, uint32_t* d_overflow,
-                              unsigned long long* d_next_batch, cudaStream_t st);
+                              unsigned long long* d_next_batch, const uint32_t* d_order, cudaStream_t st);
 
 // a3 stride-2 path (LcFast2Header): labels take (len + 15) / 8 + 1 words, capture slots are u16.
 // Only valid when every event is shorter than 65535 bytes.
@@ -74,7 +78,7 @@ int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, uint
                        uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t lab_words,
                        uint32_t threads, uint32_t grid, uint32_t* d_scratch, uint64_t scratch_words,
                        unsigned long long* d_bump, uint32_t* d_overflow, unsigned long long* d_next_batch,
-                       cudaStream_t st);
+                       const uint32_t* d_order, cudaStream_t st);
 
 // anchored prefix probe, one bool per event
 void launch_prefix_match(const void* d_blob, const uint8_t* d_base, const uint32_t* d_ev_off,
