@@ -82,6 +82,7 @@ struct lc_engine {
     bool force_basic_regex = false;   // env LC_B200_REGEX_KERNEL=basic   (tables in global memory)
     int regex_variant = 0; // env LC_B200_REGEX_KERNEL: 0 auto, 1 "fast" (stride-1), 2 "fast2" (stride-2), 3 "generic"
     uint64_t scratch_hint = 0;
+    bool length_order = false; // env LC_B200_LENGTH_ORDER=1
     // staging / workspace (grow-only)
     DevBuf in, ev_off, ev_len, out_a, out_b, out_c, out_d, out_e;
     DevBuf lines_off, lines_len, flags, state, cnt, pos, lab_sizes, lab_off, lab, order;
@@ -214,6 +215,8 @@ int lc_engine_create(int device, lc_engine_t** out) {
     {
         const char* k = getenv("LC_B200_REGEX_KERNEL");
         e->force_basic_regex = k && !strcmp(k, "basic");
+        const char* lo = getenv("LC_B200_LENGTH_ORDER");
+        e->length_order = lo && !strcmp(lo, "1");
         e->regex_variant = !k ? 0 : (!strcmp(k, "fast") ? 1 : (!strcmp(k, "fast2") ? 2 : (!strcmp(k, "generic") ? 3 : 0)));
     }
     CU_TRY(e->small.ensure(sizeof(Small)));
@@ -476,7 +479,9 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
             }
             // ragged batch: visit events in descending length-bucket order (a warp costs its longest line)
             const uint32_t* d_order = nullptr;
-            if (h->mode == LC_MODE_TWOPASS && mx > 2 * avg + 64 && n >= 4096) {
+            // (measured on C5, Zipf 64 B-8 KB: -7 %, the scattered visiting order costs more L2 locality than the
+            //  balanced warps win -- kept opt-in: LC_B200_LENGTH_ORDER=1)
+            if (e->length_order && h->mode == LC_MODE_TWOPASS && mx > 2 * avg + 64 && n >= 4096) {
                 CU_TRY(e->order.ensure(n * 4 + 256));
                 uint32_t* hist = e->order.as<uint32_t>() + n;
                 lck::launch_length_order(d_ev_len, n, hist, e->order.as<uint32_t>(), e->stream);

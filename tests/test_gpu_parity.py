@@ -338,3 +338,23 @@ def test_regex_parse_pipelined_host_path_full_size(eng):
     st, co, cl = eng.regex_parse(rx, buf, off, ln, 10)
     est, eco, ecl = orc.regex_parse_batch(orc.Regex(synth.NGINX_PATTERN), buf, off, ln, 10)
     assert np.array_equal(st, est) and np.array_equal(co, eco) and np.array_equal(cl, ecl)
+
+
+def test_regex_ragged_batch_long_lines_and_length_order(monkeypatch):
+    """Zipf-like ragged batch: lines beyond the shared-memory label budget keep their labels in the global slab;
+    the opt-in length-bucket visiting order must not change any result."""
+    lc = _lc()
+    from loongcollector_b200 import synth
+    buf, off, ln, kind = synth.zipf_mixed_lines(6000, seed=99, pool=600)
+    rx = lc.Regex(synth.NGINX_PATTERN)
+    o = orc.Regex(synth.NGINX_PATTERN)
+    sel = ~kind
+    est, eco, ecl = orc.regex_parse_batch(o, buf, off[sel], ln[sel], 10)
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LC_B200_LENGTH_ORDER", flag)
+        e = lc.Engine(0)
+        try:
+            st, co, cl = e.regex_parse(rx, buf, off[sel], ln[sel], 10)
+        finally:
+            e.close()
+        assert np.array_equal(st, est) and np.array_equal(co, eco) and np.array_equal(cl, ecl), flag
