@@ -850,6 +850,11 @@ __global__ void __launch_bounds__(1024, 1)
                       (size_t)threadIdx.x * slot_pitch;
     uint8_t* slots_m2 = reinterpret_cast<uint8_t*>(slots) - 2;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // results leave through a per-warp staging area (the warp's label words, free once the walk is done) so that
+    // the capture tables are written with fully coalesced 128-byte stores instead of 32 scattered rows
+    const uint32_t pitch = G | 1u;
+    const bool coop = order == nullptr && G > 0 && (size_t)lab_words * 32 >= (size_t)2 * 32 * pitch;
+    uint32_t* stg = lab_base + (size_t)wid * lab_words * 32;
     for (;;) {
         unsigned long long batch = 0;
         if (lane == 0)
@@ -857,43 +862,72 @@ __global__ void __launch_bounds__(1024, 1)
         batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
         if (batch >= n)
             break;
-        if (batch + lane >= n)
-            continue;
-        const uint64_t i = order ? order[batch + lane] : batch + lane;
-        const uint32_t off = ev_off[i], len = ev_len[i];
-        for (uint32_t k = 0; k < 2 * G; ++k)
-            slots[k] = LC_SLOT16_UNSET;
-        const uint8_t* s = base + off;
-        const uint64_t a16 = (uint64_t)(uintptr_t)s;
-        const uint32_t mis16 = (uint32_t)(a16 & 15u);
-        const uint4* chunks = reinterpret_cast<const uint4*>(a16 - mis16);
-        const uint32_t need = (len + mis16) / 8 + 1; // label words: one byte per byte pair
-        bool ok;
-        if (need <= lab_words) {
-            LabSmemB lab{lab_base + (size_t)wid * lab_words * 32 + lane};
-            ok = fast2_event<MULTI>(v, t, s, chunks, mis16, len, lab, slots_m2);
-        } else {
-            unsigned long long at = atomicAdd(bump, (unsigned long long)need);
-            if (at + need > scratch_words) {
-                atomicExch(overflow, 1u);
-                ok = false;
-            } else {
-                LabGlobalB lab{scratch + at};
+        const bool valid = batch + lane < n;
+        const uint64_t i = valid ? (order ? order[batch + lane] : batch + lane) : 0;
+        uint32_t off = 0, len = 0;
+        uint8_t st = 1;
+        if (valid) {
+            off = ev_off[i];
+            len = ev_len[i];
+            for (uint32_t k = 0; k < 2 * G; ++k)
+                slots[k] = LC_SLOT16_UNSET;
+            const uint8_t* s = base + off;
+            const uint64_t a16 = (uint64_t)(uintptr_t)s;
+            const uint32_t mis16 = (uint32_t)(a16 & 15u);
+            const uint4* chunks = reinterpret_cast<const uint4*>(a16 - mis16);
+            const uint32_t need = (len + mis16) / 8 + 1; // label words: one byte per byte pair
+            bool ok;
+            if (need <= lab_words) {
+                LabSmemB lab{lab_base + (size_t)wid * lab_words * 32 + lane};
                 ok = fast2_event<MULTI>(v, t, s, chunks, mis16, len, lab, slots_m2);
+            } else {
+                unsigned long long at = atomicAdd(bump, (unsigned long long)need);
+                if (at + need > scratch_words) {
+                    atomicExch(overflow, 1u);
+                    ok = false;
+                } else {
+                    LabGlobalB lab{scratch + at};
+                    ok = fast2_event<MULTI>(v, t, s, chunks, mis16, len, lab, slots_m2);
+                }
             }
+            st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
+            status[i] = st;
         }
-        uint8_t st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
-        status[i] = st;
-        uint32_t* co = cap_off + i * G;
-        uint32_t* cl = cap_len + i * G;
-        for (uint32_t g = 0; g < G; ++g) {
-            uint32_t o = 0, l = 0;
-            if (st == 0) {
-                lc_slots16_to_cap(slots, g, len, &o, &l);
-                o += off;
+        if (coop) {
+            __syncwarp();
+            if (valid)
+                for (uint32_t g = 0; g < G; ++g) {
+                    uint32_t o = 0, l = 0;
+                    if (st == 0) {
+                        lc_slots16_to_cap(slots, g, len, &o, &l);
+                        o += off;
+                    }
+                    stg[lane * pitch + g] = o;
+                    stg[32 * pitch + lane * pitch + g] = l;
+                }
+            __syncwarp();
+            const uint64_t left = n - batch;
+            const uint32_t total = (uint32_t)(left < 32 ? left : 32) * G;
+            uint32_t* go = cap_off + batch * G;
+            uint32_t* gl = cap_len + batch * G;
+            for (uint32_t j = lane; j < total; j += 32) {
+                const uint32_t line = j / G, k = j - line * G;
+                go[j] = stg[line * pitch + k];
+                gl[j] = stg[32 * pitch + line * pitch + k];
             }
-            co[g] = o;
-            cl[g] = l;
+            __syncwarp();
+        } else if (valid) {
+            uint32_t* co = cap_off + i * G;
+            uint32_t* cl = cap_len + i * G;
+            for (uint32_t g = 0; g < G; ++g) {
+                uint32_t o = 0, l = 0;
+                if (st == 0) {
+                    lc_slots16_to_cap(slots, g, len, &o, &l);
+                    o += off;
+                }
+                co[g] = o;
+                cl[g] = l;
+            }
         }
     }
 }
