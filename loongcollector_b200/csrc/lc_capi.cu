@@ -475,6 +475,8 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
             if (h->mode == LC_MODE_TWOPASS && (mx + 15) / per + 2 > lab_words) {
                 // some events spill: provision the upper bound of what ALL events could need (no retry runs)
                 uint64_t bound = (hs->counters[1] + 16 * n) / per + 2 * n + 1024;
+                if (variant == V_FAST2) // checkpointed blocks: 2 B per (lab_words * 8)-byte block of a long event
+                    bound = 4 * n + hs->counters[1] / 32 + 1024;
                 scratch_words = std::max(scratch_words, bound);
             }
             // ragged batch: visit events in descending length-bucket order (a warp costs its longest line)

@@ -709,6 +709,83 @@ struct LabGlobalB {
             lc_fast2_pair_slow(v, idx >> 8, idx & 0xFFu, (POS), reinterpret_cast<uint16_t*>(slots_m2 + 2));            \
     }
 
+// One 16-byte chunk of the reverse pass: 8 byte pairs, highest first.  Pairs are restricted to [qlo, Qe).
+// STORE: label words go to lab word index wbase (+1); partial chunks store single label bytes.
+template <bool STORE, class Lab>
+__device__ __forceinline__ void fast2_rev_chunk(const Fast2Dev& t, const uint4 vv, uint32_t lo, uint32_t qlo,
+                                                uint32_t Qe, uint32_t& row, Lab lab, uint32_t wbase) {
+    uint32_t P;
+    if (lo >= qlo && lo + 16 <= Qe) {
+        uint32_t lw;
+        LC2_REV_PAIR(vv.w, 1)
+        lw = P;
+        LC2_REV_PAIR(vv.w, 0)
+        lw = lw * 256 + P;
+        LC2_REV_PAIR(vv.z, 1)
+        lw = lw * 256 + P;
+        LC2_REV_PAIR(vv.z, 0)
+        lw = lw * 256 + P;
+        if (STORE)
+            lab.st(wbase + 1, lw);
+        LC2_REV_PAIR(vv.y, 1)
+        lw = P;
+        LC2_REV_PAIR(vv.y, 0)
+        lw = lw * 256 + P;
+        LC2_REV_PAIR(vv.x, 1)
+        lw = lw * 256 + P;
+        LC2_REV_PAIR(vv.x, 0)
+        lw = lw * 256 + P;
+        if (STORE)
+            lab.st(wbase, lw);
+    } else {
+        const uint32_t wd[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+        for (int pi = 7; pi >= 0; --pi) {
+            const uint32_t q = lo + 2 * pi;
+            if (q >= qlo && q < Qe) {
+                LC2_REV_PAIR(wd[pi >> 1], pi & 1)
+                if (STORE)
+                    lab.stb(wbase * 4 + pi, P);
+            }
+        }
+    }
+}
+
+// One 16-byte chunk of the forward walk: pairs restricted to [qlo, Qf); labels at word index wbase (+1).
+template <bool MULTI, class Lab>
+__device__ __forceinline__ void fast2_fwd_chunk(const LcFast2View& v, const Fast2Dev& t, uint32_t lo, uint32_t mis,
+                                                uint32_t qlo, uint32_t Qf, uint32_t& e, Lab lab, uint32_t wbase,
+                                                uint8_t* slots_m2) {
+    const uint32_t pos0 = lo - mis;
+    if (lo >= qlo && lo + 16 <= Qf) {
+        uint32_t lw = lab.ld(wbase);
+        LC2_FWD_PAIR(0, pos0 + 0)
+        LC2_FWD_PAIR(1, pos0 + 2)
+        LC2_FWD_PAIR(2, pos0 + 4)
+        LC2_FWD_PAIR(3, pos0 + 6)
+        lw = lab.ld(wbase + 1);
+        LC2_FWD_PAIR(0, pos0 + 8)
+        LC2_FWD_PAIR(1, pos0 + 10)
+        LC2_FWD_PAIR(2, pos0 + 12)
+        LC2_FWD_PAIR(3, pos0 + 14)
+    } else {
+#pragma unroll
+        for (int wi = 0; wi < 2; ++wi) {
+            const uint32_t q0 = lo + wi * 8;
+            if (q0 + 8 <= qlo || q0 >= Qf)
+                continue;
+            const uint32_t lw = lab.ld(wbase + wi);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t q = q0 + 2 * k;
+                if (q >= qlo && q < Qf)
+                    LC2_FWD_PAIR(k, q - mis)
+            }
+        }
+    }
+}
+
+// Whole event with all labels resident (`lab` holds (n + mis) / 8 + 1 words).
 template <bool MULTI, class Lab>
 __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev& t, const uint8_t* __restrict__ s,
                                             const uint4* __restrict__ chunks, uint32_t mis, uint32_t n, Lab lab,
@@ -732,42 +809,10 @@ __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev
         const int c_hi = (int)((Qe - 1) >> 4), c_lo = (int)(qlo >> 4);
         uint4 nxt = __ldg(chunks + c_hi);
         for (int qc = c_hi; qc >= c_lo; --qc) {
-            const uint32_t lo = (uint32_t)qc * 16;
             const uint4 vv = nxt;
             if (qc > c_lo)
                 nxt = __ldg(chunks + qc - 1);
-            uint32_t P;
-            if (lo >= qlo && lo + 16 <= Qe) {
-                uint32_t lw;
-                LC2_REV_PAIR(vv.w, 1)
-                lw = P;
-                LC2_REV_PAIR(vv.w, 0)
-                lw = lw * 256 + P;
-                LC2_REV_PAIR(vv.z, 1)
-                lw = lw * 256 + P;
-                LC2_REV_PAIR(vv.z, 0)
-                lw = lw * 256 + P;
-                lab.st(qc * 2 + 1, lw);
-                LC2_REV_PAIR(vv.y, 1)
-                lw = P;
-                LC2_REV_PAIR(vv.y, 0)
-                lw = lw * 256 + P;
-                LC2_REV_PAIR(vv.x, 1)
-                lw = lw * 256 + P;
-                LC2_REV_PAIR(vv.x, 0)
-                lw = lw * 256 + P;
-                lab.st(qc * 2, lw);
-            } else {
-                const uint32_t wd[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-                for (int pi = 7; pi >= 0; --pi) {
-                    const uint32_t q = lo + 2 * pi;
-                    if (q >= qlo && q < Qe) {
-                        LC2_REV_PAIR(wd[pi >> 1], pi & 1)
-                        lab.stb(q >> 1, P);
-                    }
-                }
-            }
+            fast2_rev_chunk<true>(t, vv, (uint32_t)qc * 16, qlo, Qe, row, lab, (uint32_t)qc * 2);
             if (row == 0)
                 return false;
         }
@@ -787,36 +832,88 @@ __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev
         e = lc_fast2_single(v, 0, d, 0, reinterpret_cast<uint16_t*>(slots_m2 + 2));
     if (Qf > qlo) {
         const int c_lo = (int)(qlo >> 4), c_hi = (int)((Qf - 1) >> 4);
-        for (int qc = c_lo; qc <= c_hi; ++qc) {
-            const uint32_t lo = (uint32_t)qc * 16;
-            const uint32_t pos0 = lo - mis;
-            if (lo >= qlo && lo + 16 <= Qf) {
-                uint32_t lw = lab.ld(qc * 2);
-                LC2_FWD_PAIR(0, pos0 + 0)
-                LC2_FWD_PAIR(1, pos0 + 2)
-                LC2_FWD_PAIR(2, pos0 + 4)
-                LC2_FWD_PAIR(3, pos0 + 6)
-                lw = lab.ld(qc * 2 + 1);
-                LC2_FWD_PAIR(0, pos0 + 8)
-                LC2_FWD_PAIR(1, pos0 + 10)
-                LC2_FWD_PAIR(2, pos0 + 12)
-                LC2_FWD_PAIR(3, pos0 + 14)
-            } else {
-#pragma unroll
-                for (int wi = 0; wi < 2; ++wi) {
-                    const uint32_t q0 = lo + wi * 8;
-                    if (q0 + 8 <= qlo || q0 >= Qf)
-                        continue;
-                    const uint32_t lw = lab.ld(qc * 2 + wi);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t q = q0 + 2 * k;
-                        if (q >= qlo && q < Qf)
-                            LC2_FWD_PAIR(k, q - mis)
-                    }
-                }
-            }
+        for (int qc = c_lo; qc <= c_hi; ++qc)
+            fast2_fwd_chunk<MULTI>(v, t, (uint32_t)qc * 16, mis, qlo, Qf, e, lab, (uint32_t)qc * 2, slots_m2);
+    }
+    if (!(Q & 1))
+        (void)lc_fast2_single(v, e & 0xFFu, t.rev_start, n, reinterpret_cast<uint16_t*>(slots_m2 + 2));
+    return true;
+}
+
+// Long event: its labels would not fit the thread's shared-memory area.  Checkpointed evaluation keeps the
+// footprint constant: (1) one reverse pass without label stores records the reverse state at every block
+// boundary (2 bytes per block, in the global slab); (2) block by block, left to right, the reverse pass is re-run
+// over just that block from its checkpoint to regenerate the block's labels in shared memory, followed by the
+// forward walk over the block.  1.5x the look-ups of the resident variant, but full occupancy and no label
+// traffic to HBM.  KC = chunks (16 B) per block, 2 * KC <= lab_words.
+template <bool MULTI, class Lab>
+__device__ __forceinline__ bool fast2_event_blocked(const LcFast2View& v, const Fast2Dev& t,
+                                                    const uint8_t* __restrict__ s, const uint4* __restrict__ chunks,
+                                                    uint32_t mis, uint32_t n, Lab lab, uint32_t KC,
+                                                    uint16_t* __restrict__ ck, uint8_t* slots_m2) {
+    const uint32_t Q = n + mis;
+    const uint32_t qlo = mis + (mis & 1);
+    const uint32_t Qe = Q & ~1u;
+    const uint32_t Qf = (Q + 1) & ~1u;
+    const uint32_t ncls = v.h->ncls, nrev = v.h->nrev;
+    const uint32_t nb = (Q >> 4) / KC + 1; // blocks 0 .. nb-1 cover chunks [j*KC, (j+1)*KC)
+    uint32_t d = t.rev_start;
+    uint32_t peel_label = 0;
+    if ((Q & 1) && n) {
+        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * s[n - 1]) >> 2)];
+        if (!d)
+            return false;
+        peel_label = v.pid[d * nrev + t.rev_start];
+    }
+    uint32_t row = d * t.row_bytes;
+    ck[nb] = (uint16_t)row; // state entering the top block
+    // ---- pass 1: reverse over the whole event, checkpoints only
+    if (Qe > qlo) {
+        const int c_hi = (int)((Qe - 1) >> 4), c_lo = (int)(qlo >> 4);
+        uint4 nxt = __ldg(chunks + c_hi);
+        for (int qc = c_hi; qc >= c_lo; --qc) {
+            const uint4 vv = nxt;
+            if (qc > c_lo)
+                nxt = __ldg(chunks + qc - 1);
+            fast2_rev_chunk<false>(t, vv, (uint32_t)qc * 16, qlo, Qe, row, lab, 0);
+            if (row == 0)
+                return false;
+            if ((uint32_t)qc % KC == 0)
+                ck[(uint32_t)qc / KC] = (uint16_t)row; // state at the lower edge of block qc / KC
         }
+    }
+    d = row / t.row_bytes;
+    if ((mis & 1) && n) {
+        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * s[0]) >> 2)];
+        if (!d)
+            return false;
+    }
+    if (v.fwd1[d] == LC_NONE_ENTRY)
+        return false;
+    uint32_t e = 0;
+    if (mis & 1)
+        e = lc_fast2_single(v, 0, d, 0, reinterpret_cast<uint16_t*>(slots_m2 + 2));
+    // ---- pass 2: per block, regenerate labels then walk forward
+    const int rc_hi = Qe > qlo ? (int)((Qe - 1) >> 4) : -1, rc_lo = (int)(qlo >> 4);
+    const int fc_hi = Qf > qlo ? (int)((Qf - 1) >> 4) : -1, fc_lo = (int)(qlo >> 4);
+    for (uint32_t j = 0; j < nb; ++j) {
+        const int b_lo = (int)(j * KC), b_hi = (int)((j + 1) * KC) - 1;
+        const uint32_t wshift = j * KC * 2; // label words of this block start at 0
+        // reverse over the block from the state at its upper edge
+        int c1 = b_hi < rc_hi ? b_hi : rc_hi, c0 = b_lo > rc_lo ? b_lo : rc_lo;
+        if (c1 >= c0) {
+            uint32_t r2 = (b_hi < rc_hi) ? ck[j + 1] : ck[nb];
+            for (int qc = c1; qc >= c0; --qc)
+                fast2_rev_chunk<true>(t, __ldg(chunks + qc), (uint32_t)qc * 16, qlo, Qe, r2, lab,
+                                      (uint32_t)qc * 2 - wshift);
+        }
+        // the peeled top pair (Q-1, Q) belongs to the block that holds chunk (Q-1) >> 4
+        if ((Q & 1) && n && (int)((Q - 1) >> 4) >= b_lo && (int)((Q - 1) >> 4) <= b_hi)
+            lab.stb(((Q - 1) >> 1) - wshift * 4, peel_label);
+        c1 = b_hi < fc_hi ? b_hi : fc_hi;
+        c0 = b_lo > fc_lo ? b_lo : fc_lo;
+        for (int qc = c0; qc <= c1; ++qc)
+            fast2_fwd_chunk<MULTI>(v, t, (uint32_t)qc * 16, mis, qlo, Qf, e, lab, (uint32_t)qc * 2 - wshift, slots_m2);
     }
     if (!(Q & 1))
         (void)lc_fast2_single(v, e & 0xFFu, t.rev_start, n, reinterpret_cast<uint16_t*>(slots_m2 + 2));
@@ -881,13 +978,18 @@ __global__ void __launch_bounds__(1024, 1)
                 LabSmemB lab{lab_base + (size_t)wid * lab_words * 32 + lane};
                 ok = fast2_event<MULTI>(v, t, s, chunks, mis16, len, lab, slots_m2);
             } else {
-                unsigned long long at = atomicAdd(bump, (unsigned long long)need);
-                if (at + need > scratch_words) {
+                // long event: checkpointed blocks, labels stay in shared memory, 2 B per block in the global slab
+                const uint32_t KC = lab_words / 2;
+                const uint32_t nb = ((len + mis16) >> 4) / KC + 1;
+                const unsigned long long ckw = (nb + 2) / 2 + 1;
+                unsigned long long at = atomicAdd(bump, ckw);
+                if (at + ckw > scratch_words) {
                     atomicExch(overflow, 1u);
                     ok = false;
                 } else {
-                    LabGlobalB lab{scratch + at};
-                    ok = fast2_event<MULTI>(v, t, s, chunks, mis16, len, lab, slots_m2);
+                    LabSmemB lab{lab_base + (size_t)wid * lab_words * 32 + lane};
+                    ok = fast2_event_blocked<MULTI>(v, t, s, chunks, mis16, len, lab, KC,
+                                                    reinterpret_cast<uint16_t*>(scratch + at), slots_m2);
                 }
             }
             st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
