@@ -106,11 +106,15 @@ def _apache_line(rng, target_len=None):
     return line
 
 
+def pool_index(pool_n, n, seed):
+    """The pool entry each of the n output lines/records was sampled from (same draw as _assemble)."""
+    return np.random.default_rng(seed).integers(0, pool_n, size=n)
+
+
 def _assemble(pool, n, seed):
     """Sample n entries from a pool of byte strings (each already ending with '\\n') into one buffer."""
     lens = np.array([len(p) for p in pool], np.int64)
-    rs = np.random.default_rng(seed)
-    idx = rs.integers(0, len(pool), size=n)
+    idx = pool_index(len(pool), n, seed)
     if np.all(lens == lens[0]):
         mat = np.frombuffer(b"".join(pool), np.uint8).reshape(len(pool), lens[0])
         buf = mat[idx].reshape(-1)
@@ -138,9 +142,8 @@ def newline_lines(n, line_bytes=512, seed=DEFAULT_SEED):
     return np.ascontiguousarray(buf), off, ln
 
 
-def nginx_lines(n, seed=DEFAULT_SEED, line_bytes=256, bad_fraction=0.01, pool=16384):
-    """C2: nginx access-log lines for NGINX_PATTERN.  line_bytes includes the '\\n' (None = natural length);
-    bad_fraction of the lines deliberately do not match."""
+def nginx_pool(n, seed=DEFAULT_SEED, line_bytes=256, bad_fraction=0.01, pool=16384):
+    """The distinct template lines nginx_lines() samples from (each ends with '\\n')."""
     rng = random.Random(seed)
     pool_n = max(8, min(n, pool))
     tl = None if line_bytes is None else line_bytes - 1
@@ -148,7 +151,13 @@ def nginx_lines(n, seed=DEFAULT_SEED, line_bytes=256, bad_fraction=0.01, pool=16
     for k in range(pool_n):
         bad = rng.random() < bad_fraction
         lines.append((_nginx_line(rng, tl, bad) + "\n").encode("ascii"))
-    return _assemble(lines, n, seed + 1)
+    return lines
+
+
+def nginx_lines(n, seed=DEFAULT_SEED, line_bytes=256, bad_fraction=0.01, pool=16384):
+    """C2: nginx access-log lines for NGINX_PATTERN.  line_bytes includes the '\\n' (None = natural length);
+    bad_fraction of the lines deliberately do not match.  Line i is pool entry pool_index(len(pool), n, seed + 1)[i]."""
+    return _assemble(nginx_pool(n, seed, line_bytes, bad_fraction, pool), n, seed + 1)
 
 
 def java_stack_records(n_records, seed=DEFAULT_SEED, mean_frames=20, unmatched_fraction=0.005, pool=4096):

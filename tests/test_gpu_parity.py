@@ -358,3 +358,68 @@ def test_regex_ragged_batch_long_lines_and_length_order(monkeypatch):
         finally:
             e.close()
         assert np.array_equal(st, est) and np.array_equal(co, eco) and np.array_equal(cl, ecl), flag
+
+
+# ------------------------------------------------------------------------------------------- BASELINE full sizes
+def test_full_size_c2_every_row_bit_exact(eng):
+    """C2 at BASELINE size (4 Mi x 256 B): the lines are samples of a 16 Ki-line pool, so the oracle's result on the
+    pool expands to the exact expected table of the whole batch -- every status / offset / length is compared."""
+    import torch
+    lc = _lc()
+    from loongcollector_b200 import synth
+    n = 4 * 1024 * 1024
+    buf, off, ln = synth.nginx_lines(n)
+    pool = synth.nginx_pool(n)
+    idx = synth.pool_index(len(pool), n, synth.DEFAULT_SEED + 1)
+    pbuf, poff, plen = _events([p[:-1] for p in pool])
+    o = orc.Regex(synth.NGINX_PATTERN)
+    pst, pco, pcl = orc.regex_parse_batch(o, pbuf, poff, plen, 10)
+    exp_st = pst[idx]
+    rel = (pco.astype(np.int64) - poff[:, None].astype(np.int64)) * (pst == 0)[:, None]
+    exp_co = ((rel[idx] + off[:, None].astype(np.int64)) * (exp_st == 0)[:, None]).astype(np.uint32)
+    exp_cl = pcl[idx]
+    rx = lc.Regex(synth.NGINX_PATTERN)
+    G = rx.ngroups
+    d_buf = torch.from_numpy(buf).cuda()
+    d_off = torch.from_numpy(off.view(np.int32)).cuda()
+    d_len = torch.from_numpy(ln.view(np.int32)).cuda()
+    d_st = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_co = torch.empty(n * G, dtype=torch.int32, device="cuda")
+    d_cl = torch.empty(n * G, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    eng.regex_parse_dev(rx, d_buf.data_ptr(), buf.size, d_off.data_ptr(), d_len.data_ptr(), n, 10, d_st.data_ptr(),
+                        d_co.data_ptr(), d_cl.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_st.cpu().numpy(), exp_st)
+    assert np.array_equal(d_co.cpu().numpy().view(np.uint32).reshape(n, G), exp_co)
+    assert np.array_equal(d_cl.cpu().numpy().view(np.uint32).reshape(n, G), exp_cl)
+    # size-independent properties: captures are ordered, disjoint and inside their line
+    co = exp_co.astype(np.int64)
+    ok = exp_st == 0
+    assert np.all(co[ok, 0] >= off[ok]) and np.all(co[ok, -1] + exp_cl[ok, -1] <= off[ok].astype(np.int64) + ln[ok])
+    assert np.all(co[ok, 1:] >= co[ok, :-1] + exp_cl[ok, :-1])
+
+
+def test_full_size_c1_split(eng):
+    """C1 at BASELINE size (1 Mi x 512 B): the line table is known in closed form."""
+    from loongcollector_b200 import synth
+    n = 1 << 20
+    buf, off, ln = synth.newline_lines(n, 512)
+    g_off, g_len = eng.split_lines(buf, cap=n + 8)
+    assert np.array_equal(g_off, off) and np.array_equal(g_len, ln)
+
+
+def test_full_size_c3_multiline_records(eng):
+    """C3 at BASELINE size (1 Mi Java records, ~1.8 KB): with a start pattern only, every record is one event that
+    begins at a record start and runs to the byte before the next one; counters follow in closed form."""
+    lc = _lc()
+    from loongcollector_b200 import synth
+    nrec = 1 << 20
+    buf, nlines, _ = synth.java_stack_records(nrec)
+    start = lc.Regex(synth.JAVA_START_PATTERN)
+    off, ln, fl, ctr = eng.multiline_split(buf, start, None, None, False, cap=nrec + 8)
+    assert off.size == nrec and ctr.tolist() == [nrec, nlines, 0]
+    # record k starts where record k-1 ended + 1 ('\n'); the last one keeps the trailing '\n' (reference quirk)
+    ends = off.astype(np.int64) + ln
+    assert off[0] == 0 and np.array_equal(off[1:], ends[:-1] + 1) and ends[-1] == buf.size
+    assert np.all(buf[off] == ord("[")) and np.all(fl[:-1] == 2) and fl[-1] == 3
