@@ -105,6 +105,15 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
                        const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
                        uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len);
 
+/* Boolean whole-value match == BoostRegexMatch(buf, size, reg, exception) without captures
+ * (core/common/StringTools.cpp:213-236), the arithmetic of ProcessorFilterNative::IsMatched
+ * (core/plugin/processor/ProcessorFilterNative.cpp:258-275): out_match[i] = 1 iff regex_match holds.
+ * Only the reverse pass of the automaton runs. */
+int lc_regex_match(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, uint64_t base_len,
+                   const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n, uint8_t* out_match);
+int lc_regex_match_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
+                       const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint8_t* d_out_match);
+
 /* Anchored prefix probe == BoostRegexSearch / regex_search(match_continuous) (StringTools.cpp:263-288),
  * one boolean per event. */
 int lc_regex_prefix_match(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, uint64_t base_len,

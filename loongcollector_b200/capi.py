@@ -61,6 +61,8 @@ def lib():
     L.lc_regex_parse.argtypes = parse_args
     L.lc_regex_parse_dev.argtypes = parse_args
     L.lc_regex_prefix_match.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
+    L.lc_regex_match.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
+    L.lc_regex_match_dev.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
     ml_args = [vp, vp, u64, vp, vp, vp, i32, vp, vp, vp, u64, C.POINTER(u64), vp]
     L.lc_multiline_split.argtypes = ml_args
     L.lc_multiline_split_dev.argtypes = ml_args
@@ -193,6 +195,14 @@ class Engine:
         out = np.empty(ev_off.size, np.uint8)
         _check(lib().lc_regex_prefix_match(self._h, rx._h, _p(a), a.size, _p(ev_off), _p(ev_len), ev_off.size,
                                            _p(out)))
+        return out.astype(bool)
+
+    def regex_match(self, rx, base, ev_off, ev_len):
+        a = _u8(base)
+        ev_off = np.ascontiguousarray(ev_off, np.uint32)
+        ev_len = np.ascontiguousarray(ev_len, np.uint32)
+        out = np.empty(ev_off.size, np.uint8)
+        _check(lib().lc_regex_match(self._h, rx._h, _p(a), a.size, _p(ev_off), _p(ev_len), ev_off.size, _p(out)))
         return out.astype(bool)
 
     def multiline_split(self, buf, start, cont, end, discard, cap=None):

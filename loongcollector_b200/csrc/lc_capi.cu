@@ -378,9 +378,53 @@ int lc_split_lines(lc_engine_t* e, const uint8_t* buf, uint64_t len, uint8_t spl
 }
 
 // ------------------------------------------------------------------------------------------------ regex parse
+static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
+                                const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                                uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, bool bool_only);
+
 int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
                        const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
                        uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len) {
+    return regex_parse_dev_impl(e, re, d_base, base_len, d_ev_off, d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len,
+                                false);
+}
+
+int lc_regex_match_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
+                       const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint8_t* d_out_match) {
+    return regex_parse_dev_impl(e, re, d_base, base_len, d_ev_off, d_ev_len, n, 0, d_out_match, nullptr, nullptr, true);
+}
+
+int lc_regex_match(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, uint64_t base_len,
+                   const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n, uint8_t* out_match) {
+    if (!e || !re || (n && (!ev_off || !ev_len || !out_match)) || (base_len && !base))
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_match: bad arguments");
+    int rc = check_regex_usable(re, "lc_regex_match");
+    if (rc)
+        return rc;
+    if (n == 0)
+        return LC_OK;
+    rc = bind(e);
+    if (rc)
+        return rc;
+    CU_TRY(e->in.ensure(base_len + 16));
+    CU_TRY(e->ev_off.ensure(n * 4));
+    CU_TRY(e->ev_len.ensure(n * 4));
+    CU_TRY(e->out_a.ensure(n));
+    CU_TRY(cudaMemcpyAsync(e->in.p, base, base_len, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->ev_off.p, ev_off, n * 4, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->ev_len.p, ev_len, n * 4, cudaMemcpyHostToDevice, e->stream));
+    rc = lc_regex_match_dev(e, re, e->in.as<uint8_t>(), base_len, e->ev_off.as<uint32_t>(), e->ev_len.as<uint32_t>(), n,
+                            e->out_a.as<uint8_t>());
+    if (rc)
+        return rc;
+    CU_TRY(cudaMemcpyAsync(out_match, e->out_a.p, n, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return LC_OK;
+}
+
+static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
+                                const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                                uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, bool bool_only) {
     if (!e || !re)
         return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_dev: bad arguments");
     int rc = check_regex_usable(re, "lc_regex_parse");
@@ -425,6 +469,14 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
             variant = V_FAST;
         const std::vector<uint8_t>& vb =
             variant == V_FAST2 ? re->res.fast2_blob : (variant == V_FAST ? re->res.fast_blob : re->res.blob);
+        bool convert_status = false;
+        if (bool_only && variant != V_FAST2) { // these kernels always write captures: give them scratch tables
+            CU_TRY(e->out_d.ensure(n * h->ngroups * 4 + 4));
+            CU_TRY(e->out_e.ensure(n * h->ngroups * 4 + 4));
+            d_cap_off = e->out_d.as<uint32_t>();
+            d_cap_len = e->out_e.as<uint32_t>();
+            convert_status = true;
+        }
         const uint32_t blob_bytes = (uint32_t)vb.size();
         if (blob_bytes + 4096 <= smem_max) {
             const void* d_vblob = d_blob;
@@ -517,12 +569,21 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
                 if (er)
                     return fail(LC_ERR_CUDA,
                                 std::string("regex kernel launch: ") + cudaGetErrorString((cudaError_t)er));
-                if (h->mode != LC_MODE_TWOPASS)
+                if (h->mode != LC_MODE_TWOPASS) {
+                    if (convert_status) {
+                        lck::launch_status_to_bool(d_status, n, e->stream);
+                        e->launches++;
+                    }
                     return LC_OK;
+                }
                 CU_TRY(cudaMemcpyAsync(&hs->overflow, &ds->overflow, 4, cudaMemcpyDeviceToHost, e->stream));
                 CU_TRY(cudaStreamSynchronize(e->stream));
                 if (!hs->overflow) {
                     e->scratch_hint = scratch_words;
+                    if (convert_status) {
+                        lck::launch_status_to_bool(d_status, n, e->stream);
+                        e->launches++;
+                    }
                     return LC_OK;
                 }
                 scratch_words = scratch_words < full ? std::min<uint64_t>(full, scratch_words * 4) : scratch_words * 2;
@@ -551,9 +612,19 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
         d_lab_off = e->lab_off.as<uint64_t>();
         d_lab = e->lab.as<uint16_t>();
     }
+    if (bool_only) {
+        CU_TRY(e->out_d.ensure(n * h->ngroups * 4 + 4));
+        CU_TRY(e->out_e.ensure(n * h->ngroups * 4 + 4));
+        d_cap_off = e->out_d.as<uint32_t>();
+        d_cap_len = e->out_e.as<uint32_t>();
+    }
     lck::launch_regex_parse_basic(d_blob, h->mode, h->ngroups, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
                                   d_cap_off, d_cap_len, d_lab_off, d_lab, e->stream);
     e->launches++;
+    if (bool_only) {
+        lck::launch_status_to_bool(d_status, n, e->stream);
+        e->launches++;
+    }
     CU_TRY(cudaGetLastError());
     return LC_OK;
 }

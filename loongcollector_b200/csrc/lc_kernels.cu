@@ -280,6 +280,17 @@ void launch_length_order(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_hist6
     bucket_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ev_len, n, d_hist64, d_order);
 }
 
+// lc_regex_match on the kernels that always produce captures: parse status (0 ok, 2 keys mismatch = matched) -> bool
+__global__ void status_to_bool_kernel(uint8_t* __restrict__ st, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        st[i] = st[i] != 1 ? 1 : 0;
+}
+void launch_status_to_bool(uint8_t* d_status, uint64_t n, cudaStream_t st) {
+    if (n)
+        status_to_bool_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_status, n);
+}
+
 // One thread per event; tables read through the read-only path from global memory.
 __global__ void __launch_bounds__(128)
     regex_parse_basic_kernel(const void* __restrict__ blob, uint32_t mode, uint32_t G, const uint8_t* __restrict__ base,
@@ -789,7 +800,7 @@ __device__ __forceinline__ void fast2_fwd_chunk(const LcFast2View& v, const Fast
 template <bool MULTI, class Lab>
 __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev& t, const uint8_t* __restrict__ s,
                                             const uint4* __restrict__ chunks, uint32_t mis, uint32_t n, Lab lab,
-                                            uint8_t* slots_m2 /* slot area - 2 bytes */) {
+                                            uint8_t* slots_m2 /* slot area - 2 bytes */, bool bool_only) {
     const uint32_t Q = n + mis;
     const uint32_t qlo = mis + (mis & 1);      // first even position whose pair lies inside the event
     const uint32_t Qe = Q & ~1u;               // reverse pairs cover [qlo, Qe)
@@ -827,6 +838,8 @@ __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev
     // ---- forward; d == label of position mis
     if (v.fwd1[d] == LC_NONE_ENTRY)
         return false;
+    if (bool_only)
+        return true; // regex_match as a boolean needs no captures: the reverse pass decides
     uint32_t e = 0; // forward entry; byte 0 = current walker
     if (mis & 1)
         e = lc_fast2_single(v, 0, d, 0, reinterpret_cast<uint16_t*>(slots_m2 + 2));
@@ -850,7 +863,7 @@ template <bool MULTI, class Lab>
 __device__ __forceinline__ bool fast2_event_blocked(const LcFast2View& v, const Fast2Dev& t,
                                                     const uint8_t* __restrict__ s, const uint4* __restrict__ chunks,
                                                     uint32_t mis, uint32_t n, Lab lab, uint32_t KC,
-                                                    uint16_t* __restrict__ ck, uint8_t* slots_m2) {
+                                                    uint16_t* __restrict__ ck, uint8_t* slots_m2, bool bool_only) {
     const uint32_t Q = n + mis;
     const uint32_t qlo = mis + (mis & 1);
     const uint32_t Qe = Q & ~1u;
@@ -890,6 +903,8 @@ __device__ __forceinline__ bool fast2_event_blocked(const LcFast2View& v, const 
     }
     if (v.fwd1[d] == LC_NONE_ENTRY)
         return false;
+    if (bool_only)
+        return true;
     uint32_t e = 0;
     if (mis & 1)
         e = lc_fast2_single(v, 0, d, 0, reinterpret_cast<uint16_t*>(slots_m2 + 2));
@@ -949,8 +964,9 @@ __global__ void __launch_bounds__(1024, 1)
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // results leave through a per-warp staging area (the warp's label words, free once the walk is done) so that
     // the capture tables are written with fully coalesced 128-byte stores instead of 32 scattered rows
+    const bool bool_only = cap_off == nullptr; // lc_regex_match: status[i] = 1 match / 0 no match, no captures
     const uint32_t pitch = G | 1u;
-    const bool coop = order == nullptr && G > 0 && (size_t)lab_words * 32 >= (size_t)2 * 32 * pitch;
+    const bool coop = !bool_only && order == nullptr && G > 0 && (size_t)lab_words * 32 >= (size_t)2 * 32 * pitch;
     uint32_t* stg = lab_base + (size_t)wid * lab_words * 32;
     for (;;) {
         unsigned long long batch = 0;
@@ -976,7 +992,7 @@ __global__ void __launch_bounds__(1024, 1)
             bool ok;
             if (need <= lab_words) {
                 LabSmemB lab{lab_base + (size_t)wid * lab_words * 32 + lane};
-                ok = fast2_event<MULTI>(v, t, s, chunks, mis16, len, lab, slots_m2);
+                ok = fast2_event<MULTI>(v, t, s, chunks, mis16, len, lab, slots_m2, bool_only);
             } else {
                 // long event: checkpointed blocks, labels stay in shared memory, 2 B per block in the global slab
                 const uint32_t KC = lab_words / 2;
@@ -989,12 +1005,14 @@ __global__ void __launch_bounds__(1024, 1)
                 } else {
                     LabSmemB lab{lab_base + (size_t)wid * lab_words * 32 + lane};
                     ok = fast2_event_blocked<MULTI>(v, t, s, chunks, mis16, len, lab, KC,
-                                                    reinterpret_cast<uint16_t*>(scratch + at), slots_m2);
+                                                    reinterpret_cast<uint16_t*>(scratch + at), slots_m2, bool_only);
                 }
             }
             st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
-            status[i] = st;
+            status[i] = bool_only ? (ok ? 1 : 0) : st;
         }
+        if (bool_only)
+            continue;
         if (coop) {
             __syncwarp();
             if (valid)

@@ -80,6 +80,9 @@ int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, uint
                        unsigned long long* d_bump, uint32_t* d_overflow, unsigned long long* d_next_batch,
                        const uint32_t* d_order, cudaStream_t st);
 
+// parse status -> boolean (1 = the whole value matched)
+void launch_status_to_bool(uint8_t* d_status, uint64_t n, cudaStream_t st);
+
 // anchored prefix probe, one bool per event
 void launch_prefix_match(const void* d_blob, const uint8_t* d_base, const uint32_t* d_ev_off,
                          const uint32_t* d_ev_len, uint64_t n, uint8_t* d_out, cudaStream_t st);

@@ -680,7 +680,258 @@ void ProcessorParseDelimiterNative::Process(PipelineEventGroup& group) {
     events.resize(wIdx);
 }
 
+// ------------------------------------------------------------------------------------------------ filter
+const std::string ProcessorFilterNative::sName = "processor_filter_regex_native";
+
+ProcessorFilterNative::~ProcessorFilterNative() {
+    for (auto& l : mLeaves)
+        delete l.reg;
+}
+
+static std::string Lower(std::string s) {
+    for (auto& c : s)
+        if (c >= 'A' && c <= 'Z')
+            c = (char)(c + 32);
+    return s;
+}
+
+// ParseExpressionFromJSON (:380-425): returns node index or -1
+int ProcessorFilterNative::ParseExpression(const Json::Value& v, std::string& err) {
+    if (!v.isObject())
+        return -1;
+    if (v["operator"].isString() && v["operands"].isArray()) {
+        std::string op = Lower(v["operator"].asString());
+        const Json::Value& ops = v["operands"];
+        if (op == "not" && ops.size() == 1) {
+            int c = ParseExpression(ops[0], err);
+            if (c < 0)
+                return -1;
+            Node n;
+            n.op = 1;
+            n.left = c;
+            mNodes.push_back(n);
+            return (int)mNodes.size() - 1;
+        }
+        if ((op == "and" || op == "or") && ops.size() == 2) {
+            int l = ParseExpression(ops[0], err);
+            int r = ParseExpression(ops[1], err);
+            if (l < 0 || r < 0)
+                return -1;
+            Node n;
+            n.op = op == "and" ? 2 : 3;
+            n.left = l;
+            n.right = r;
+            mNodes.push_back(n);
+            return (int)mNodes.size() - 1;
+        }
+        return -1;
+    }
+    if ((v["key"].isString() && v["exp"].isString()) || !v["type"].isString()) {
+        if (Lower(v["type"].asString()) != "regex")
+            return -1;
+        Leaf leaf;
+        leaf.key = v["key"].asString();
+        leaf.reg = new CompiledRegex;
+        if (!leaf.reg->Compile(v["exp"].asString(), err)) {
+            delete leaf.reg;
+            return -1;
+        }
+        mLeaves.push_back(leaf);
+        Node n;
+        n.op = 0;
+        n.leaf = (int)mLeaves.size() - 1;
+        mNodes.push_back(n);
+        return (int)mNodes.size() - 1;
+    }
+    return -1;
+}
+
+bool ProcessorFilterNative::Init(const Json::Value& config) {
+    std::string err;
+    if (config.isMember("ConditionExp")) {
+        if (!config["ConditionExp"].isObject())
+            return Fail("object param ConditionExp is not of type object");
+        mRoot = ParseExpression(config["ConditionExp"], err);
+        if (mRoot < 0)
+            return Fail("object param ConditionExp is not valid " + err);
+        mFilterMode = Mode::EXPRESSION_MODE;
+    }
+    auto addRule = [&](const std::string& key, const std::string& pattern) -> bool {
+        Leaf leaf;
+        leaf.key = key;
+        leaf.reg = new CompiledRegex;
+        if (!leaf.reg->Compile(pattern, err)) {
+            delete leaf.reg;
+            return false;
+        }
+        mLeaves.push_back(leaf);
+        return true;
+    };
+    if (mFilterMode == Mode::BYPASS_MODE && config.isMember("FilterKey") && config.isMember("FilterRegex")) {
+        const Json::Value &ks = config["FilterKey"], &rs = config["FilterRegex"];
+        if (!ks.isArray() || !rs.isArray() || ks.size() != rs.size())
+            return Fail("param FilterKey and FilterRegex does not have the same size");
+        for (size_t i = 0; i < ks.size(); ++i)
+            if (!addRule(ks[i].asString(), rs[i].asString()))
+                return Fail("value in list param FilterRegex is not a usable regex: " + err);
+        if (ks.size())
+            mFilterMode = Mode::RULE_MODE;
+    }
+    if (mFilterMode == Mode::BYPASS_MODE && config.isMember("Include") && config["Include"].isObject()) {
+        for (const auto& k : config["Include"].getMemberNames())
+            if (!addRule(k, config["Include"][k].asString()))
+                return Fail("value in map param Include is not a usable regex: " + err);
+        if (!mLeaves.empty())
+            mFilterMode = Mode::RULE_MODE;
+    }
+    GetBool(config, "DiscardingNonUTF8", mDiscardingNonUTF8);
+    return true;
+}
+
+bool ProcessorFilterNative::Eval(int node, const std::vector<std::vector<uint8_t>>& leafResult, size_t ev) const {
+    const Node& n = mNodes[node];
+    switch (n.op) {
+        case 0:
+            return leafResult[n.leaf][ev] != 0;
+        case 1:
+            return !Eval(n.left, leafResult, ev);
+        case 2:
+            return Eval(n.left, leafResult, ev) && Eval(n.right, leafResult, ev);
+        default:
+            return Eval(n.left, leafResult, ev) || Eval(n.right, leafResult, ev);
+    }
+}
+
+// ProcessorFilterNative::noneUtf8 (:297-378): blank every byte that starts an invalid sequence; true if any
+static bool BlankNoneUtf8(std::string& s, bool modify) {
+    bool bad = false;
+    size_t i = 0, n = s.size();
+    auto cont = [&](size_t k) { return k < n && ((unsigned char)s[k] & 0xC0) == 0x80; };
+    while (i < n) {
+        unsigned char c = (unsigned char)s[i];
+        size_t step = 1;
+        bool inv = false;
+        if ((c & 0x80) == 0) {
+        } else if ((c & 0xE0) == 0xC0) {
+            if (!cont(i + 1)) {
+                inv = true;
+            } else {
+                uint32_t u = ((c & 0x1Fu) << 6) | ((unsigned char)s[i + 1] & 0x3Fu);
+                inv = !(u >= 0x80 && u <= 0x7FF);
+                step = 2;
+            }
+        } else if ((c & 0xF0) == 0xE0) {
+            if (!cont(i + 1) || !cont(i + 2)) {
+                inv = true;
+            } else {
+                uint32_t u = (((c & 0x0Fu) << 12) | (((unsigned char)s[i + 1] & 0x3Fu) << 6) |
+                              ((unsigned char)s[i + 2] & 0x3Fu)) &
+                             0xFFFFu;
+                inv = !(u >= 0x800);
+                step = 3;
+            }
+        } else if ((c & 0xF8) == 0xF0) {
+            if (!cont(i + 1) || !cont(i + 2) || !cont(i + 3)) {
+                inv = true;
+            } else {
+                uint32_t u = ((c & 0x07u) << 18) | (((unsigned char)s[i + 1] & 0x3Fu) << 12) |
+                             (((unsigned char)s[i + 2] & 0x3Fu) << 6) | ((unsigned char)s[i + 3] & 0x3Fu);
+                inv = !(u >= 0x10000 && u <= 0x10FFFF);
+                step = 4;
+            }
+        } else {
+            inv = true;
+        }
+        if (inv) {
+            if (!modify)
+                return true;
+            s[i] = ' ';
+            bad = true;
+            i += 1;
+        } else {
+            i += step;
+        }
+    }
+    return bad;
+}
+
+void ProcessorFilterNative::Process(PipelineEventGroup& group) {
+    if (group.GetEvents().empty())
+        return;
+    EventsContainer& events = group.MutableEvents();
+    const size_t ne = events.size();
+    // one batched boolean regex_match per leaf over the events that carry its key
+    std::vector<std::vector<uint8_t>> leafResult(mLeaves.size(), std::vector<uint8_t>(ne, 0));
+    for (size_t li = 0; li < mLeaves.size(); ++li) {
+        FlatBatch batch;
+        for (size_t i = 0; i < ne; ++i) {
+            if (!IsSupportedEvent(events[i]))
+                continue;
+            const LogEvent& ev = events[i].Cast<LogEvent>();
+            if (ev.HasContent(mLeaves[li].key))
+                batch.Add(i, ev.GetContent(mLeaves[li].key));
+        }
+        batch.Finish(*group.GetSourceBuffer());
+        const size_t nb = batch.eventIndex.size();
+        if (!nb)
+            continue;
+        std::vector<uint8_t> m(nb);
+        Check(lc_regex_match(Engine(), mLeaves[li].reg->get(), batch.base, batch.baseLen, batch.off.data(),
+                             batch.len.data(), nb, m.data()),
+              "lc_regex_match");
+        for (size_t b = 0; b < nb; ++b)
+            leafResult[li][batch.eventIndex[b]] = m[b];
+    }
+    size_t wIdx = 0;
+    for (size_t rIdx = 0; rIdx < ne; ++rIdx) {
+        bool res = true;
+        if (IsSupportedEvent(events[rIdx])) {
+            LogEvent& ev = events[rIdx].Cast<LogEvent>();
+            if (mFilterMode == Mode::EXPRESSION_MODE) {
+                res = !ev.Empty() && Eval(mRoot, leafResult, rIdx);
+            } else if (mFilterMode == Mode::RULE_MODE) {
+                res = !ev.Empty();
+                for (size_t li = 0; res && li < mLeaves.size(); ++li)
+                    res = leafResult[li][rIdx] != 0; // a missing key left its slot at 0
+            }
+            if (res && mDiscardingNonUTF8) {
+                std::vector<std::pair<StringView, StringView>> renamed;
+                SourceBuffer& sb = *group.GetSourceBuffer();
+                // contents are visited in place; keys needing repair are re-added after the walk (:190-211)
+                std::vector<LogEvent::Content> snapshot = ev.RawContents();
+                for (auto& c : snapshot) {
+                    if (!c.second)
+                        continue;
+                    StringView key = c.first.first, val = c.first.second;
+                    std::string v = val.to_string();
+                    if (BlankNoneUtf8(v, true)) {
+                        StringBuffer vb = sb.CopyString(v);
+                        val = StringView(vb.data, vb.size);
+                        ev.SetContentNoCopy(key, val);
+                    }
+                    std::string k = key.to_string();
+                    if (BlankNoneUtf8(k, true)) {
+                        StringBuffer kb = sb.CopyString(k);
+                        renamed.emplace_back(StringView(kb.data, kb.size), val);
+                        ev.DelContent(key);
+                    }
+                }
+                for (auto& r : renamed)
+                    ev.SetContentNoCopy(r.first, r.second);
+            }
+        }
+        if (res) {
+            if (wIdx != rIdx)
+                events[wIdx] = std::move(events[rIdx]);
+            ++wIdx;
+        }
+    }
+    events.resize(wIdx);
+}
+
 Processor* CreateProcessor(const std::string& type) {
+    if (type == ProcessorFilterNative::sName)
+        return new ProcessorFilterNative;
     if (type == ProcessorSplitLogStringNative::sName)
         return new ProcessorSplitLogStringNative;
     if (type == ProcessorSplitMultilineLogStringNative::sName)

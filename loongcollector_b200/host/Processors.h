@@ -162,6 +162,41 @@ private:
     bool mSourceKeyOverwritten = false;
 };
 
+// First "next" row: regex include / exclude filter.  Every regex leaf of the rule / expression is
+// evaluated for the whole group with one batched boolean regex_match on the GPU; the and/or/not tree and the
+// non-UTF8 blanking stay on the host.  core/plugin/processor/ProcessorFilterNative.cpp:30-275,380-488
+class ProcessorFilterNative : public Processor {
+public:
+    static const std::string sName;
+    const std::string& Name() const override { return sName; }
+    bool Init(const Json::Value& config) override;
+    void Process(PipelineEventGroup& group) override;
+    using Processor::Process;
+    bool mDiscardingNonUTF8 = false;
+    ~ProcessorFilterNative() override;
+
+protected:
+    bool IsSupportedEvent(const PipelineEventPtr& e) const override { return e.Is<LogEvent>(); }
+
+private:
+    enum class Mode { BYPASS_MODE, EXPRESSION_MODE, RULE_MODE };
+    struct Leaf {
+        std::string key;
+        CompiledRegex* reg;
+    };
+    struct Node { // expression tree; leaf >= 0 indexes mLeaves
+        int op = 0; // 0 leaf, 1 not, 2 and, 3 or
+        int leaf = -1;
+        int left = -1, right = -1;
+    };
+    int ParseExpression(const Json::Value& v, std::string& err);
+    bool Eval(int node, const std::vector<std::vector<uint8_t>>& leafResult, size_t ev) const;
+    Mode mFilterMode = Mode::BYPASS_MODE;
+    std::vector<Leaf> mLeaves;
+    std::vector<Node> mNodes;
+    int mRoot = -1;
+};
+
 // Factory by plugin type name (the names the reference registers, PluginRegistry.cpp:183-200).
 Processor* CreateProcessor(const std::string& type);
 

@@ -188,6 +188,14 @@ void orc_regex_parse_batch(orc_matcher* m, const uint8_t* base, const uint32_t* 
     }
 }
 
+/* BoostRegexMatch(buffer, size, reg, exception) as used by ProcessorFilterNative::IsMatched
+ * (core/plugin/processor/ProcessorFilterNative.cpp:258-275, core/common/StringTools.cpp:213-236): boolean per event. */
+void orc_regex_match_batch(orc_matcher* m, const uint8_t* base, const uint32_t* ev_off, const uint32_t* ev_len,
+                           uint64_t n, uint8_t* out) {
+    for (uint64_t i = 0; i < n; ++i)
+        out[i] = (uint8_t)orc_regex_full_match(m, base + ev_off[i], ev_len[i], NULL, NULL);
+}
+
 /* ------------------------------------------------------------------ split */
 /* ProcessorSplitLogStringNative::ProcessEvent + GetNextLine (:127-174): pieces between split chars;
  * empty pieces kept; a trailing split char yields no extra empty piece (loop stops at begin >= size).

@@ -61,6 +61,8 @@ def lib():
     L.orc_regex_parse_batch.restype = None
     L.orc_regex_parse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_regex_match_batch.restype = None
+    L.orc_regex_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.orc_split_lines.restype = C.c_uint64
     L.orc_split_lines.argtypes = [C.c_void_p, C.c_uint64, C.c_uint8, C.c_void_p, C.c_void_p, C.c_uint64]
     L.orc_multiline_split.restype = C.c_uint64
@@ -187,6 +189,15 @@ def regex_parse_batch(rx: Regex, base, ev_off, ev_len, nkeys: int, matcher=None)
     lib().orc_regex_parse_batch(matcher or rx._m, _ptr(a), _ptr(ev_off), _ptr(ev_len), n, nkeys, _ptr(status),
                                 _ptr(co), _ptr(cl))
     return status, co, cl
+
+
+def regex_match_batch(rx: Regex, base, ev_off, ev_len):
+    a = _as_u8(base)
+    ev_off = np.ascontiguousarray(ev_off, np.uint32)
+    ev_len = np.ascontiguousarray(ev_len, np.uint32)
+    out = np.zeros(ev_off.size, np.uint8)
+    lib().orc_regex_match_batch(rx._m, _ptr(a), _ptr(ev_off), _ptr(ev_len), ev_off.size, _ptr(out))
+    return out.astype(bool)
 
 
 def delim_parse_batch(base, ev_off, ev_len, sep: bytes, quote: int, nkeys: int, extend: bool, allow_short: bool,
@@ -675,8 +686,150 @@ class ProcessorParseDelimiterNative:
         return True
 
 
+def _none_utf8(data: bytes, modify: bool):
+    """ProcessorFilterNative::noneUtf8 (ProcessorFilterNative.cpp:297-378): returns (has_invalid, sanitised) where
+    every byte that starts an invalid sequence is replaced by a blank (only that byte; scanning resumes after it)."""
+    b = bytearray(data)
+    i, n, bad = 0, len(b), False
+
+    def cont(k):
+        return k < n and (b[k] & 0xC0) == 0x80
+
+    while i < n:
+        c = b[i]
+        step = 1
+        inv = False
+        if c & 0x80 == 0:
+            pass
+        elif c & 0xE0 == 0xC0:
+            if i + 1 >= n or not cont(i + 1):
+                inv = True
+            else:
+                u = ((c & 0x1F) << 6) | (b[i + 1] & 0x3F)
+                inv = not (0x80 <= u <= 0x7FF)
+                step = 2
+        elif c & 0xF0 == 0xE0:
+            if i + 2 >= n or not cont(i + 1) or not cont(i + 2):
+                inv = True
+            else:
+                u = (((c & 0x0F) << 12) | ((b[i + 1] & 0x3F) << 6) | (b[i + 2] & 0x3F)) & 0xFFFF
+                inv = not (u >= 0x800)
+                step = 3
+        elif c & 0xF8 == 0xF0:
+            if i + 3 >= n or not cont(i + 1) or not cont(i + 2) or not cont(i + 3):
+                inv = True
+            else:
+                u = ((c & 0x07) << 18) | ((b[i + 1] & 0x3F) << 12) | ((b[i + 2] & 0x3F) << 6) | (b[i + 3] & 0x3F)
+                inv = not (0x10000 <= u <= 0x10FFFF)
+                step = 4
+        else:
+            inv = True
+        if inv:
+            if not modify:
+                return True, data
+            b[i] = 0x20
+            bad = True
+            i += 1
+        else:
+            i += step
+    return bad, bytes(b)
+
+
+class ProcessorFilterNative:
+    """core/plugin/processor/ProcessorFilterNative.cpp:30-275,380-488 -- the first "next" row of SURVEY.md 8(f)."""
+    name = "processor_filter_regex_native"
+
+    def __init__(self, cfg):
+        self.mode = "bypass"
+        self.exp = None
+        self.rule = None
+        ce = cfg.get("ConditionExp")
+        if ce is not None:
+            if not isinstance(ce, dict):
+                raise ValueError("object param ConditionExp is not of type object")
+            self.exp = self._parse(ce)
+            if self.exp is None:
+                raise ValueError("object param ConditionExp is not valid")
+            self.mode = "expression"
+        if self.mode == "bypass":
+            keys = cfg.get("FilterKey") or []
+            regs = cfg.get("FilterRegex") or []
+            if len(keys) != len(regs):
+                raise ValueError("param FilterKey and FilterRegex does not have the same size")
+            if keys:
+                self.rule = [(_b(k), Regex(r)) for k, r in zip(keys, regs)]
+                self.mode = "rule"
+        if self.mode == "bypass":
+            inc = cfg.get("Include") or {}
+            if inc:
+                self.rule = [(_b(k), Regex(inc[k])) for k in sorted(inc)]
+                self.mode = "rule"
+        d = cfg.get("DiscardingNonUTF8", False)
+        self.discard_non_utf8 = d if isinstance(d, bool) else False
+
+    def _parse(self, v):
+        if not isinstance(v, dict):
+            return None
+        if isinstance(v.get("operator"), str) and isinstance(v.get("operands"), list):
+            op = v["operator"].lower()
+            ops = v["operands"]
+            if op == "not" and len(ops) == 1:
+                c = self._parse(ops[0])
+                return ("not", c) if c else None
+            if op in ("and", "or") and len(ops) == 2:
+                l, r = self._parse(ops[0]), self._parse(ops[1])
+                return (op, l, r) if l and r else None
+            return None
+        if (isinstance(v.get("key"), str) and isinstance(v.get("exp"), str)) or not isinstance(v.get("type"), str):
+            t = v.get("type", "")
+            if not isinstance(t, str) or t.lower() != "regex":
+                return None
+            return ("regex", _b(v.get("key", "")), Regex(v.get("exp", "")))
+        return None
+
+    def _eval(self, node, e: Event):
+        if node[0] == "regex":
+            if not e.has(node[1]):
+                return False
+            return node[2].full_match(e.get(node[1])) is not None
+        if node[0] == "not":
+            return not self._eval(node[1], e)
+        if node[0] == "and":
+            return self._eval(node[1], e) and self._eval(node[2], e)
+        return self._eval(node[1], e) or self._eval(node[2], e)
+
+    def process(self, g: Group):
+        if not g.events:
+            return
+        g.events = [e for e in g.events if self._event(e)]
+
+    def _event(self, e: Event):
+        if e.type != LOG:
+            return True
+        res = True
+        if self.mode == "expression":
+            res = e.size() > 0 and self._eval(self.exp, e)
+        elif self.mode == "rule":
+            res = e.size() > 0 and all(e.has(k) and rx.full_match(e.get(k)) is not None for k, rx in self.rule)
+        if res and self.discard_non_utf8:
+            renamed = []
+            for c in e.contents:
+                if not c[2]:
+                    continue
+                bad, fixed = _none_utf8(c[1], True)
+                if bad:
+                    c[1] = fixed
+                badk, fixedk = _none_utf8(c[0], True)
+                if badk:
+                    renamed.append((fixedk, c[1]))
+                    c[2] = False
+            for k, v in renamed:
+                e.set(k, v)
+        return res
+
+
 PROCESSORS = {
     p.name: p
     for p in (ProcessorSplitLogStringNative, ProcessorSplitMultilineLogStringNative, ProcessorParseRegexNative,
-              ProcessorParseDelimiterNative)
+              ProcessorParseDelimiterNative, ProcessorFilterNative)
 }

@@ -423,3 +423,16 @@ def test_full_size_c3_multiline_records(eng):
     ends = off.astype(np.int64) + ln
     assert off[0] == 0 and np.array_equal(off[1:], ends[:-1] + 1) and ends[-1] == buf.size
     assert np.all(buf[off] == ord("[")) and np.all(fl[:-1] == 2) and fl[-1] == 3
+
+
+def test_regex_match_boolean_matches_oracle(eng):
+    """lc_regex_match (ProcessorFilterNative's arithmetic): reverse pass only, one boolean per value."""
+    lc = _lc()
+    rng = random.Random(31)
+    lines = _noise_lines(rng, 2000) + _nginx_lines(rng, 1500) + [b"100", b"2008-08-08", b"192.168.1.1", b"x" * 3000]
+    base, off, ln = _events(lines)
+    ip = r"((2[0-4]\d|25[0-5]|[01]?\d\d?)\.){3}(2[0-4]\d|25[0-5]|[01]?\d\d?)"
+    for p in PATTERNS[:6] + [r"\d+", r"20\d{1,2}-\d{1,2}-\d{1,2}", r"\S+", ip, r".*value1", r"^no-agent$"]:
+        got = eng.regex_match(lc.Regex(p), base, off, ln)
+        want = orc.regex_match_batch(orc.Regex(p), base, off, ln)
+        assert np.array_equal(got, want), p
