@@ -703,7 +703,7 @@ int ProcessorFilterNative::ParseExpression(const Json::Value& v, std::string& er
         std::string op = Lower(v["operator"].asString());
         const Json::Value& ops = v["operands"];
         if (op == "not" && ops.size() == 1) {
-            int c = ParseExpression(ops[0], err);
+            int c = ParseExpression(ops[(size_t)0], err);
             if (c < 0)
                 return -1;
             Node n;
@@ -713,8 +713,8 @@ int ProcessorFilterNative::ParseExpression(const Json::Value& v, std::string& er
             return (int)mNodes.size() - 1;
         }
         if ((op == "and" || op == "or") && ops.size() == 2) {
-            int l = ParseExpression(ops[0], err);
-            int r = ParseExpression(ops[1], err);
+            int l = ParseExpression(ops[(size_t)0], err);
+            int r = ParseExpression(ops[(size_t)1], err);
             if (l < 0 || r < 0)
                 return -1;
             Node n;
