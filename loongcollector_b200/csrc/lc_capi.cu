@@ -503,7 +503,9 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
                 // Long lines: labels in shared memory would leave a handful of resident warps (measured: 20x
                 // slower).  Keep >= kMinWarps warps resident and let events that do not fit keep their labels in
                 // the global slab instead (L2-resident while in flight; +1 B of traffic per input byte worst case).
-                const uint32_t kMinWarps = 20;
+                // The stride-2 kernel evaluates oversized events in checkpointed blocks (labels of one block only),
+                // so it can afford the full 32 warps; the others keep whole-event labels in the global slab.
+                const uint32_t kMinWarps = variant == V_FAST2 ? 32 : 20;
                 if (warps < kMinWarps) {
                     warps = kMinWarps;
                     size_t per_warp = budget / kMinWarps;

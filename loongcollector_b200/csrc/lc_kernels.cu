@@ -918,9 +918,13 @@ __device__ __forceinline__ bool fast2_event_blocked(const LcFast2View& v, const 
         int c1 = b_hi < rc_hi ? b_hi : rc_hi, c0 = b_lo > rc_lo ? b_lo : rc_lo;
         if (c1 >= c0) {
             uint32_t r2 = (b_hi < rc_hi) ? ck[j + 1] : ck[nb];
-            for (int qc = c1; qc >= c0; --qc)
-                fast2_rev_chunk<true>(t, __ldg(chunks + qc), (uint32_t)qc * 16, qlo, Qe, r2, lab,
-                                      (uint32_t)qc * 2 - wshift);
+            uint4 nxt = __ldg(chunks + c1);
+            for (int qc = c1; qc >= c0; --qc) {
+                const uint4 vv = nxt;
+                if (qc > c0)
+                    nxt = __ldg(chunks + qc - 1);
+                fast2_rev_chunk<true>(t, vv, (uint32_t)qc * 16, qlo, Qe, r2, lab, (uint32_t)qc * 2 - wshift);
+            }
         }
         // the peeled top pair (Q-1, Q) belongs to the block that holds chunk (Q-1) >> 4
         if ((Q & 1) && n && (int)((Q - 1) >> 4) >= b_lo && (int)((Q - 1) >> 4) <= b_hi)
