@@ -35,11 +35,15 @@ __device__ __forceinline__ uint32_t match16(uint4 v, uint32_t splat) {
     return m;
 }
 
+// Each thread owns ROWS consecutive 16-byte chunks (64 contiguous bytes for ROWS = 4): one 64-bit newline mask,
+// ONE block scan and ONE look-back per 16 KiB tile.  A warp's loads cover 2 KiB of contiguous memory, so every
+// 128-byte line is fetched once (two lanes x four loads share it through L1).
 template <int THREADS, int ROWS>
 __global__ void __launch_bounds__(THREADS)
     split_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
                  uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap, volatile uint64_t* desc,
                  uint32_t* ticket, uint32_t ntiles, uint32_t* n_out) {
+    static_assert(ROWS == 4, "one 64-bit mask per thread");
     __shared__ uint64_t s_scan[THREADS / 32 + 1];
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_prefix;
@@ -50,75 +54,65 @@ __global__ void __launch_bounds__(THREADS)
     const uint32_t tile = s_tile;
     const uint4* vbuf = reinterpret_cast<const uint4*>(buf - shift);
     const uint64_t total_v = (uint64_t)len + shift; // virtual length including the alignment lead-in
-    const uint64_t chunk0 = (uint64_t)tile * THREADS * ROWS;
+    const uint64_t chunk0 = ((uint64_t)tile * THREADS + tid) * ROWS;
+    const uint64_t vpos0 = chunk0 * 16;
 
-    uint32_t mask[ROWS];
-    uint64_t pay[ROWS];
+    uint4 v[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-        uint64_t chunk = chunk0 + (uint64_t)r * THREADS + tid;
-        uint64_t vpos = chunk * 16;
+        v[r] = make_uint4(0, 0, 0, 0);
+        if (vpos0 + (uint64_t)r * 16 < total_v)
+            v[r] = __ldg(vbuf + chunk0 + r);
+    }
+    uint64_t mask = 0;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const uint64_t vpos = vpos0 + (uint64_t)r * 16;
         uint32_t m = 0;
         if (vpos < total_v) {
-            uint4 v = __ldg(vbuf + chunk);
-            m = match16(v, splat);
+            m = match16(v[r], splat);
             if (vpos == 0 && shift) // alignment lead-in bytes in front of the buffer (shift < 16)
                 m &= ~((1u << shift) - 1u);
-            uint64_t rem = total_v - vpos;
+            const uint64_t rem = total_v - vpos;
             if (rem < 16)
                 m &= (1u << rem) - 1u;
         }
-        mask[r] = m;
-        uint32_t last = m ? (uint32_t)(vpos + (31 - __clz(m)) + 1 - shift) : 0u;
-        pay[r] = OpCountMax::make(__popc(m), last);
+        mask |= (uint64_t)m << (16 * r);
     }
-
-    uint64_t excl[ROWS], rowpre[ROWS];
-    uint64_t carry = OpCountMax::identity();
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        uint64_t tot;
-        excl[r] = block_exclusive_scan<OpCountMax, THREADS>(pay[r], tot, s_scan);
-        rowpre[r] = carry;
-        carry = OpCountMax::combine(carry, tot);
-    }
+    const uint32_t last = mask ? (uint32_t)(vpos0 + (63 - __clzll((long long)mask)) + 1 - shift) : 0u;
+    const uint64_t pay = OpCountMax::make(__popcll(mask), last);
+    uint64_t tot;
+    const uint64_t excl = block_exclusive_scan<OpCountMax, THREADS>(pay, tot, s_scan);
     if (tid < 32) {
-        uint64_t p = lookback<OpCountMax>(desc, tile, carry);
+        uint64_t p = lookback<OpCountMax>(desc, tile, tot);
         if (tid == 0)
             s_prefix = p;
     }
     __syncthreads();
-    const uint64_t tile_prefix = s_prefix;
-
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        uint64_t pre = OpCountMax::combine(tile_prefix, OpCountMax::combine(rowpre[r], excl[r]));
-        uint32_t k = OpCountMax::count(pre);
-        uint32_t start = OpCountMax::maxv(pre);
-        uint32_t m = mask[r];
-        uint64_t vpos = (chunk0 + (uint64_t)r * THREADS + tid) * 16;
-        while (m) {
-            int b = __ffs(m) - 1;
-            m &= m - 1;
-            uint32_t p = (uint32_t)(vpos + b - shift);
+    const uint64_t pre = OpCountMax::combine(s_prefix, excl);
+    uint32_t k = OpCountMax::count(pre);
+    uint32_t start = OpCountMax::maxv(pre);
+    while (mask) {
+        const int b = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        const uint32_t p = (uint32_t)(vpos0 + b - shift);
+        if (k < cap) {
+            out_off[k] = start;
+            out_len[k] = p - start;
+        }
+        ++k;
+        start = p + 1;
+    }
+    if (tile == ntiles - 1 && tid == THREADS - 1) {
+        // inclusive total of the whole buffer: the unterminated last piece, if any
+        if (start < len) {
             if (k < cap) {
                 out_off[k] = start;
-                out_len[k] = p - start;
+                out_len[k] = len - start;
             }
             ++k;
-            start = p + 1;
         }
-        if (tile == ntiles - 1 && r == ROWS - 1 && tid == THREADS - 1) {
-            // inclusive total of the whole buffer: the unterminated last piece, if any
-            if (start < len) {
-                if (k < cap) {
-                    out_off[k] = start;
-                    out_len[k] = len - start;
-                }
-                ++k;
-            }
-            *n_out = k;
-        }
+        *n_out = k;
     }
 }
 
@@ -1604,8 +1598,19 @@ __global__ void __launch_bounds__(128)
             int state = 0; // 0 INITIAL 1 QUOTE 2 DATA 3 DOUBLE_QUOTE
             int dq = 0;
             int fs = begIdx, fe = begIdx;
-            for (int32_t k = begIdx; k < endIdx && ok; ++k) {
-                uint8_t c = v[k];
+            // bytes are consumed as 16-byte aligned chunks (one LDG.128 per 16 bytes instead of 16 byte loads)
+            const uint32_t mis = (uint32_t)((uintptr_t)v & 15u);
+            const uint4* chunks = reinterpret_cast<const uint4*>(v - mis);
+            const uint32_t qb = (uint32_t)begIdx + mis, qe = (uint32_t)endIdx + mis;
+            for (uint32_t qc = qb >> 4; qc <= ((qe - 1) >> 4) && ok; ++qc) {
+                const uint4 vv = __ldg(chunks + qc);
+                const uint32_t wd[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+                for (int bi = 0; bi < 16; ++bi) {
+                    const uint32_t q = qc * 16 + bi;
+                    if (q < qb || q >= qe || !ok)
+                        continue;
+                    const uint8_t c = (uint8_t)(wd[bi >> 2] >> (8 * (bi & 3)));
                 if (c == sep) {
                     if (state == 1) {
                         fe++;
@@ -1645,6 +1650,7 @@ __global__ void __launch_bounds__(128)
                     } else {
                         fe++;
                     }
+                }
                 }
             }
             if (ok) {
