@@ -550,8 +550,10 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
                 CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof(Small) - offsetof(Small, overflow), e->stream));
                 int er;
                 if (variant == V_FAST2) {
-                    const bool multi = reinterpret_cast<const LcFast2Header*>(vb.data())->has_multi != 0;
-                    er = lck::launch_regex_fast2(d_vblob, blob_bytes, multi, h->ngroups, d_base, d_ev_off, d_ev_len, n,
+                    const LcFast2Header* f2h = reinterpret_cast<const LcFast2Header*>(vb.data());
+                    const bool multi = f2h->has_multi != 0;
+                    er = lck::launch_regex_fast2(d_vblob, blob_bytes, multi, f2h->pair_shift == 2, h->ngroups, d_base,
+                                                 d_ev_off, d_ev_len, n,
                                                  nkeys, d_status, d_cap_off, d_cap_len, lab_words, threads, grid,
                                                  e->lab.as<uint32_t>(), scratch_words, &ds->bump, &ds->overflow,
                                                  &ds->next_batch, d_order, e->stream);

@@ -153,8 +153,7 @@ LC_HD void lc_slots_to_cap(const uint32_t* slots, uint32_t g, uint32_t n, uint32
 // The kernel's unrolled middle section is a specialisation of exactly these statements.
 struct LcFast2View {
     const LcFast2Header* h;
-    const uint16_t* cls_hi;
-    const uint16_t* cls_lo;
+    const uint8_t* cls;
     const uint8_t* t2; // byte addressed (u32 entries)
     const uint8_t* pid;
     const uint8_t* pair_l;
@@ -169,8 +168,7 @@ LC_HD LcFast2View lc_fast2_view(const void* blob) {
     const LcFast2Header* h = (const LcFast2Header*)blob;
     LcFast2View v;
     v.h = h;
-    v.cls_hi = (const uint16_t*)(b + h->off_cls_hi);
-    v.cls_lo = (const uint16_t*)(b + h->off_cls_lo);
+    v.cls = b + h->off_cls;
     v.t2 = b + h->off_t2;
     v.pid = b + h->off_pid;
     v.pair_l = b + h->off_pair_l;
@@ -226,14 +224,14 @@ LC_HD bool lc_fast2_event(const LcFast2View& v, const uint8_t* s, uint32_t mis, 
     uint32_t q = Q;
     if ((q & 1) && q > mis) { // byte q-1 is the first slot of the pair (q-1, q): second slot is the end position
         --q;
-        d = v.rev1[d * ncls + v.cls_lo[s[q - mis]] / 4];
+        d = v.rev1[d * ncls + v.cls[s[q - mis]]];
         if (!d)
             return false;
         lab[q / 2] = v.pid[d * nrev + start];
     }
     while (q >= mis + 2) { // full byte pair (q-2, q-1)
         q -= 2;
-        const uint32_t addr = d * row_bytes + (uint32_t)v.cls_hi[s[q + 1 - mis]] + v.cls_lo[s[q - mis]];
+        const uint32_t addr = d * row_bytes + ((uint32_t)v.cls[s[q + 1 - mis]] * ncls + v.cls[s[q - mis]]) * 4;
         const uint32_t e = *(const uint32_t*)(v.t2 + addr);
         lab[q / 2] = (uint8_t)(e >> 16);
         d = (e & 0xFFFFu) / row_bytes;
@@ -242,7 +240,7 @@ LC_HD bool lc_fast2_event(const LcFast2View& v, const uint8_t* s, uint32_t mis, 
     }
     if (q > mis) { // one byte left: it sits in the second slot of a pair whose first slot precedes the event
         --q;
-        d = v.rev1[d * ncls + v.cls_lo[s[q - mis]] / 4];
+        d = v.rev1[d * ncls + v.cls[s[q - mis]]];
         if (!d)
             return false;
     }
@@ -255,9 +253,10 @@ LC_HD bool lc_fast2_event(const LcFast2View& v, const uint8_t* s, uint32_t mis, 
         w = lc_fast2_single(v, w, d, 0, slots);
         ++q;
     }
+    const uint32_t pshift = v.h->pair_shift, f2row = v.h->f2_row;
     while (q + 1 <= Q) {
-        const uint32_t P = lab[q / 2];
-        const uint32_t e = v.f2[w * 256 + P];
+        const uint32_t P = lab[q / 2] >> pshift; // labels hold pair_id << pair_shift
+        const uint32_t e = v.f2[w * f2row + P];
         const uint32_t sa = (e >> 8) & 0x7Fu, sb = (e >> 16) & 0x7Fu;
         if (e & LC_FAST2_ACT_MULTI) {
             lc_fast2_pair_slow(v, w, P, q - mis, slots);

@@ -668,11 +668,10 @@ int launch_regex_twopass_fast(const void* d_fast_blob, uint32_t blob_bytes, bool
 //                       entry bytes 1,2 -> up to two predicated 16-bit STS into the thread's capture slots
 // Pairs are aligned on even addresses; an odd first byte / odd end position is peeled as a single step.
 struct Fast2Dev {
-    const uint8_t* cls_hi; // byte addressed u16 tables
-    const uint8_t* cls_lo;
-    const uint8_t* t2;     // byte addressed u32 entries
-    const uint32_t* f2;
-    uint32_t rev_start, row_bytes;
+    const uint8_t* cls; // byte -> class (u8, conflict-free for ASCII)
+    const uint8_t* t2;  // byte addressed u32 entries
+    const uint8_t* f2;  // byte addressed u32 entries
+    uint32_t rev_start, row_bytes, ncls;
 };
 
 struct LabSmemB { // label words interleaved [word][lane]; byte-level access for peeled / partial chunks
@@ -692,26 +691,27 @@ struct LabGlobalB {
 
 #define LC2_REV_PAIR(X, HI)                                                                                           \
     {                                                                                                                  \
-        const uint32_t b1 = __byte_perm((X), 0, (HI) ? 0x4443 : 0x4441);                                               \
-        const uint32_t b0 = __byte_perm((X), 0, (HI) ? 0x4442 : 0x4440);                                               \
-        const uint32_t off = *reinterpret_cast<const uint16_t*>(t.cls_hi + 2 * b1) +                                   \
-                             *reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * b0);                                    \
-        const uint32_t e2 = *reinterpret_cast<const uint32_t*>(t.t2 + row + off);                                      \
+        const uint32_t c1 = t.cls[__byte_perm((X), 0, (HI) ? 0x4443 : 0x4441)];                                        \
+        const uint32_t c0 = t.cls[__byte_perm((X), 0, (HI) ? 0x4442 : 0x4440)];                                        \
+        const uint32_t e2 = *reinterpret_cast<const uint32_t*>(t.t2 + row + ((c1 * t.ncls + c0) << 2));               \
         row = e2 & 0xFFFFu;                                                                                            \
         P = e2 >> 16;                                                                                                  \
     }
 
+// COMPACT: labels hold pair_id * 4 and PRMT(entry, labels) is the byte offset of the next entry (256-byte rows);
+// otherwise PRMT gives the entry index in 256-entry rows.
 #define LC2_FWD_PAIR(K, POS)                                                                                          \
     {                                                                                                                  \
-        const uint32_t idx = __byte_perm(e, lw, 0x3304 + (K)); /* walker << 8 | pair id */                             \
-        e = t.f2[idx];                                                                                                 \
+        const uint32_t idx = __byte_perm(e, lw, 0x3304 + (K)); /* walker << 8 | label */                               \
+        e = *reinterpret_cast<const uint32_t*>(t.f2 + (COMPACT ? idx : idx * 4));                                      \
         const uint32_t sa = (e >> 8) & 0x7Fu, sb = (e >> 16) & 0x7Fu;                                                  \
         if (sa)                                                                                                        \
             *reinterpret_cast<uint16_t*>(slots_m2 + sa) = (uint16_t)(POS);                                             \
         if (sb)                                                                                                        \
             *reinterpret_cast<uint16_t*>(slots_m2 + sb) = (uint16_t)((POS) + 1);                                       \
         if (MULTI && (e & LC_FAST2_ACT_MULTI))                                                                         \
-            lc_fast2_pair_slow(v, idx >> 8, idx & 0xFFu, (POS), reinterpret_cast<uint16_t*>(slots_m2 + 2));            \
+            lc_fast2_pair_slow(v, idx >> 8, (idx & 0xFFu) >> (COMPACT ? 2 : 0), (POS),                                 \
+                               reinterpret_cast<uint16_t*>(slots_m2 + 2));                                             \
     }
 
 // One 16-byte chunk of the reverse pass: 8 byte pairs, highest first.  Pairs are restricted to [qlo, Qe).
@@ -757,7 +757,7 @@ __device__ __forceinline__ void fast2_rev_chunk(const Fast2Dev& t, const uint4 v
 }
 
 // One 16-byte chunk of the forward walk: pairs restricted to [qlo, Qf); labels at word index wbase (+1).
-template <bool MULTI, class Lab>
+template <bool MULTI, bool COMPACT, class Lab>
 __device__ __forceinline__ void fast2_fwd_chunk(const LcFast2View& v, const Fast2Dev& t, uint32_t lo, uint32_t mis,
                                                 uint32_t qlo, uint32_t Qf, uint32_t& e, Lab lab, uint32_t wbase,
                                                 uint8_t* slots_m2) {
@@ -791,7 +791,7 @@ __device__ __forceinline__ void fast2_fwd_chunk(const LcFast2View& v, const Fast
 }
 
 // Whole event with all labels resident (`lab` holds (n + mis) / 8 + 1 words).
-template <bool MULTI, class Lab>
+template <bool MULTI, bool COMPACT, class Lab>
 __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev& t, const uint8_t* __restrict__ s,
                                             const uint4* __restrict__ chunks, uint32_t mis, uint32_t n, Lab lab,
                                             uint8_t* slots_m2 /* slot area - 2 bytes */, bool bool_only) {
@@ -804,7 +804,7 @@ __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev
     // ---- reverse: peel the byte whose pair partner is the end position
     if ((Q & 1) && n) {
         const uint32_t b = s[n - 1];
-        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * b) >> 2)];
+        d = v.rev1[d * ncls + t.cls[b]];
         if (!d)
             return false;
         lab.stb((Q - 1) >> 1, v.pid[d * nrev + t.rev_start]);
@@ -825,7 +825,7 @@ __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev
     d = row / t.row_bytes;
     // the first byte sits in the second slot of a pair whose first slot precedes the event
     if ((mis & 1) && n) {
-        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * s[0]) >> 2)];
+        d = v.rev1[d * ncls + t.cls[s[0]]];
         if (!d)
             return false;
     }
@@ -840,7 +840,7 @@ __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev
     if (Qf > qlo) {
         const int c_lo = (int)(qlo >> 4), c_hi = (int)((Qf - 1) >> 4);
         for (int qc = c_lo; qc <= c_hi; ++qc)
-            fast2_fwd_chunk<MULTI>(v, t, (uint32_t)qc * 16, mis, qlo, Qf, e, lab, (uint32_t)qc * 2, slots_m2);
+            fast2_fwd_chunk<MULTI, COMPACT>(v, t, (uint32_t)qc * 16, mis, qlo, Qf, e, lab, (uint32_t)qc * 2, slots_m2);
     }
     if (!(Q & 1))
         (void)lc_fast2_single(v, e & 0xFFu, t.rev_start, n, reinterpret_cast<uint16_t*>(slots_m2 + 2));
@@ -853,7 +853,7 @@ __device__ __forceinline__ bool fast2_event(const LcFast2View& v, const Fast2Dev
 // over just that block from its checkpoint to regenerate the block's labels in shared memory, followed by the
 // forward walk over the block.  1.5x the look-ups of the resident variant, but full occupancy and no label
 // traffic to HBM.  KC = chunks (16 B) per block, 2 * KC <= lab_words.
-template <bool MULTI, class Lab>
+template <bool MULTI, bool COMPACT, class Lab>
 __device__ __forceinline__ bool fast2_event_blocked(const LcFast2View& v, const Fast2Dev& t,
                                                     const uint8_t* __restrict__ s, const uint4* __restrict__ chunks,
                                                     uint32_t mis, uint32_t n, Lab lab, uint32_t KC,
@@ -867,7 +867,7 @@ __device__ __forceinline__ bool fast2_event_blocked(const LcFast2View& v, const 
     uint32_t d = t.rev_start;
     uint32_t peel_label = 0;
     if ((Q & 1) && n) {
-        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * s[n - 1]) >> 2)];
+        d = v.rev1[d * ncls + t.cls[s[n - 1]]];
         if (!d)
             return false;
         peel_label = v.pid[d * nrev + t.rev_start];
@@ -891,7 +891,7 @@ __device__ __forceinline__ bool fast2_event_blocked(const LcFast2View& v, const 
     }
     d = row / t.row_bytes;
     if ((mis & 1) && n) {
-        d = v.rev1[d * ncls + (*reinterpret_cast<const uint16_t*>(t.cls_lo + 2 * s[0]) >> 2)];
+        d = v.rev1[d * ncls + t.cls[s[0]]];
         if (!d)
             return false;
     }
@@ -926,14 +926,14 @@ __device__ __forceinline__ bool fast2_event_blocked(const LcFast2View& v, const 
         c1 = b_hi < fc_hi ? b_hi : fc_hi;
         c0 = b_lo > fc_lo ? b_lo : fc_lo;
         for (int qc = c0; qc <= c1; ++qc)
-            fast2_fwd_chunk<MULTI>(v, t, (uint32_t)qc * 16, mis, qlo, Qf, e, lab, (uint32_t)qc * 2 - wshift, slots_m2);
+            fast2_fwd_chunk<MULTI, COMPACT>(v, t, (uint32_t)qc * 16, mis, qlo, Qf, e, lab, (uint32_t)qc * 2 - wshift, slots_m2);
     }
     if (!(Q & 1))
         (void)lc_fast2_single(v, e & 0xFFu, t.rev_start, n, reinterpret_cast<uint16_t*>(slots_m2 + 2));
     return true;
 }
 
-template <bool MULTI>
+template <bool MULTI, bool COMPACT>
 __global__ void __launch_bounds__(1024, 1)
     regex_fast2_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, const uint8_t* __restrict__ base,
                        const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
@@ -947,10 +947,10 @@ __global__ void __launch_bounds__(1024, 1)
     __syncthreads();
     const LcFast2View v = lc_fast2_view(smem);
     Fast2Dev t;
-    t.cls_hi = reinterpret_cast<const uint8_t*>(v.cls_hi);
-    t.cls_lo = reinterpret_cast<const uint8_t*>(v.cls_lo);
+    t.cls = v.cls;
     t.t2 = v.t2;
-    t.f2 = v.f2;
+    t.f2 = reinterpret_cast<const uint8_t*>(v.f2);
+    t.ncls = v.h->ncls;
     t.rev_start = v.h->rev_start;
     t.row_bytes = v.h->row_bytes;
     const uint32_t G = v.h->ngroups;
@@ -990,7 +990,7 @@ __global__ void __launch_bounds__(1024, 1)
             bool ok;
             if (need <= lab_words) {
                 LabSmemB lab{lab_base + (size_t)wid * lab_words * 32 + lane};
-                ok = fast2_event<MULTI>(v, t, s, chunks, mis16, len, lab, slots_m2, bool_only);
+                ok = fast2_event<MULTI, COMPACT>(v, t, s, chunks, mis16, len, lab, slots_m2, bool_only);
             } else {
                 // long event: checkpointed blocks, labels stay in shared memory, 2 B per block in the global slab
                 const uint32_t KC = lab_words / 2;
@@ -1002,7 +1002,7 @@ __global__ void __launch_bounds__(1024, 1)
                     ok = false;
                 } else {
                     LabSmemB lab{lab_base + (size_t)wid * lab_words * 32 + lane};
-                    ok = fast2_event_blocked<MULTI>(v, t, s, chunks, mis16, len, lab, KC,
+                    ok = fast2_event_blocked<MULTI, COMPACT>(v, t, s, chunks, mis16, len, lab, KC,
                                                     reinterpret_cast<uint16_t*>(scratch + at), slots_m2, bool_only);
                 }
             }
@@ -1050,7 +1050,8 @@ __global__ void __launch_bounds__(1024, 1)
     }
 }
 
-int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, uint32_t ngroups, const uint8_t* d_base,
+int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, bool compact, uint32_t ngroups,
+                       const uint8_t* d_base,
                        const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
                        uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t lab_words,
                        uint32_t threads, uint32_t grid, uint32_t* d_scratch, uint64_t scratch_words,
@@ -1060,7 +1061,8 @@ int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, uint
         return 0;
     const uint32_t slot_pitch = fast2_slot_pitch(ngroups);
     size_t smem = fast2_smem_bytes(blob_bytes, ngroups, lab_words, threads);
-    auto k = multi ? regex_fast2_kernel<true> : regex_fast2_kernel<false>;
+    auto k = compact ? (multi ? regex_fast2_kernel<true, true> : regex_fast2_kernel<false, true>)
+                     : (multi ? regex_fast2_kernel<true, false> : regex_fast2_kernel<false, false>);
     cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (er != cudaSuccess)
         return (int)er;

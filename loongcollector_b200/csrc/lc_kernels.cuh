@@ -73,7 +73,8 @@ inline uint32_t fast2_slot_pitch(uint32_t ngroups) { return ((ngroups + 1) | 1u)
 inline size_t fast2_smem_bytes(uint32_t blob_bytes, uint32_t ngroups, uint32_t lab_words, uint32_t threads) {
     return (size_t)blob_bytes + (size_t)(threads / 32) * lab_words * 128 + (size_t)threads * fast2_slot_pitch(ngroups) * 2;
 }
-int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, uint32_t ngroups, const uint8_t* d_base,
+int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, bool compact, uint32_t ngroups,
+                       const uint8_t* d_base,
                        const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
                        uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t lab_words,
                        uint32_t threads, uint32_t grid, uint32_t* d_scratch, uint64_t scratch_words,

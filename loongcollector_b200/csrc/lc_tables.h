@@ -104,18 +104,22 @@ struct LcFastHeader {
 // ---- "fast2 blob": stride-2 layout of the same two-pass automaton.  Two input bytes are consumed per dependent
 // look-up and ONE label byte is stored per byte pair, which halves both the dependency chain and the
 // shared-memory footprint per in-flight line.  Pairs are aligned on even addresses.
-//   cls_hi u16 [256]                  class(b) * ncls * 4      } byte offset of (c1, c0) inside a t2 row
-//   cls_lo u16 [256]                  class(b) * 4             }
+//   cls    u8  [256]                  byte -> class.  64 words: ASCII text never bank-conflicts (bytes b, b+128 share
+//                                     a bank); the row offset (c1 * ncls + c0) * 4 is computed arithmetically.
 //   t2     u32 [nrev][ncls*ncls]      reverse pair step from state D over bytes (b1 = later, b0 = earlier):
 //                                     entry = next_state * row_bytes (bits 0..15, the byte offset of its row,
-//                                     row_bytes = ncls*ncls*4) | pair_id << 16.  addr' = (t2[addr] & 0xFFFF) + off.
-//   pid    u8  [nrev][nrev]           pair id of (label(q), label(q+1)); 0 = impossible
-//   pair_l u8  [npairs][2]            inverse of pid
+//                                     row_bytes = ncls*ncls*4) | (pair_id << pair_shift) << 16.
+//   pid    u8  [nrev][nrev]           (pair id << pair_shift) of (label(q), label(q+1)); 0 = impossible
+//   pair_l u8  [npairs][2]            inverse of pid (indexed by the plain pair id)
 //   rev1   u8  [nrev][ncls]           single reverse step by class (peeled first / last byte)
-//   f2     u32 [nw][256]              forward pair step: byte0 = next walker after both steps, byte1 = slot set by
+//   f2     u32 [nw][f2_row]           forward pair step: byte0 = next walker after both steps, byte1 = slot set by
 //                                     the 1st step, byte2 = slot set by the 2nd step (2*slot + 2, 0 = none; bit 7 of
 //                                     byte1 = some step sets several slots -> slow path via pair_l + fwd1 + masks),
-//                                     byte3 = 0.  index of the next look-up = PRMT(entry, labels) = walker << 8 | pair.
+//                                     byte3 = 0.
+//                                     compact layout (npairs <= 63: pair_shift = 2, f2_row = 64): labels hold
+//                                     pair_id * 4 and PRMT(entry, labels) = walker << 8 | pair_id * 4 is directly the
+//                                     BYTE offset of the next entry (256-byte rows);
+//                                     wide layout (pair_shift = 0, f2_row = 256): PRMT gives the entry INDEX.
 //   fwd1   u32 [nw][nrev]             single forward step: next walker | action id << 16 (LC_NONE_ENTRY = no path)
 //   masks  u64 [nact]
 #define LC_FAST2_MAGIC 0x4C434632u /* 'LCF2' */
@@ -131,8 +135,8 @@ struct LcFast2Header {
     uint32_t npairs;
     uint32_t nact;
     uint32_t row_bytes; // ncls * ncls * 4
-    uint32_t off_cls_hi;
-    uint32_t off_cls_lo;
+    uint32_t off_cls;
+    uint32_t pair_shift; // 2 = compact f2 layout, 0 = wide
     uint32_t off_t2;
     uint32_t off_pid;
     uint32_t off_pair_l;
@@ -141,7 +145,8 @@ struct LcFast2Header {
     uint32_t off_fwd1;
     uint32_t off_masks;
     uint32_t has_multi;
-    uint32_t reserved[4];
+    uint32_t f2_row; // entries per f2 row (64 or 256)
+    uint32_t reserved[3];
 };
 
 #ifdef __cplusplus

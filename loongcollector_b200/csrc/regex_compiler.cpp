@@ -1555,11 +1555,13 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                 fh.npairs = npairs;
                 fh.nact = (uint32_t)actions.size();
                 fh.row_bytes = ncl * ncl * 4;
-                std::vector<uint16_t> cls_hi(256), cls_lo(256);
-                for (int b = 0; b < 256; ++b) {
-                    cls_hi[b] = (uint16_t)(byte_class[b] * ncl * 4);
-                    cls_lo[b] = (uint16_t)(byte_class[b] * 4);
-                }
+                std::vector<uint8_t> cls(byte_class, byte_class + 256);
+                const uint32_t pshift = npairs <= 63 ? 2u : 0u;
+                const uint32_t f2row = pshift ? 64u : 256u;
+                fh.pair_shift = pshift;
+                fh.f2_row = f2row;
+                for (auto& x : pid)
+                    x = (uint8_t)(x << pshift);
                 std::vector<uint32_t> t2((size_t)nD * ncl * ncl, 0);
                 for (int D = 1; D < nD; ++D)
                     for (uint32_t c1 = 0; c1 < ncl; ++c1) {
@@ -1571,7 +1573,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                             if (!La)
                                 continue;
                             t2[((size_t)D * ncl + c1) * ncl + c0] =
-                                (La * fh.row_bytes) | ((uint32_t)pid[(size_t)La * nD + Lb] << 16);
+                                (La * fh.row_bytes) | ((uint32_t)pid[(size_t)La * nD + Lb] << 16); // pid is pre-shifted
                         }
                     }
                 std::vector<uint8_t> rev1((size_t)nD * ncl, 0);
@@ -1591,7 +1593,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                         ++bit;
                     return 2u * (uint32_t)bit + 2u;
                 };
-                std::vector<uint32_t> f2((size_t)nw * 256, 0);
+                std::vector<uint32_t> f2((size_t)nw * f2row, 0);
                 for (int w = 0; w < nw; ++w)
                     for (uint32_t P = 1; P < npairs; ++P) {
                         uint32_t La = pair_l[2 * P], Lb = pair_l[2 * P + 1];
@@ -1606,9 +1608,9 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                         uint32_t sa = slot_code(LC_ENTRY_ACT(e1)), sb = slot_code(LC_ENTRY_ACT(e2));
                         if (sa == kMulti || sb == kMulti) {
                             fh.has_multi = 1;
-                            f2[(size_t)w * 256 + P] = w2 | LC_FAST2_ACT_MULTI;
+                            f2[(size_t)w * f2row + P] = w2 | LC_FAST2_ACT_MULTI;
                         } else {
-                            f2[(size_t)w * 256 + P] = w2 | (sa << 8) | (sb << 16);
+                            f2[(size_t)w * f2row + P] = w2 | (sa << 8) | (sb << 16);
                         }
                     }
                 std::vector<uint32_t> fwd1((size_t)nw * nD, LC_NONE_ENTRY);
@@ -1616,8 +1618,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                     for (int D = 0; D < nD; ++D)
                         fwd1[(size_t)w * nD + D] = fwd[(size_t)w * fwd_cols + D];
                 std::vector<uint8_t> fb(sizeof fh, 0);
-                put(fb, fh.off_cls_hi, cls_hi);
-                put(fb, fh.off_cls_lo, cls_lo);
+                put(fb, fh.off_cls, cls);
                 put(fb, fh.off_t2, t2);
                 put(fb, fh.off_pid, pid);
                 put(fb, fh.off_pair_l, pair_l);
