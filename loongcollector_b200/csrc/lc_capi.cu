@@ -80,9 +80,11 @@ struct lc_engine {
     int smem_per_block_optin = 0;
     int smem_per_sm = 0;
     bool force_basic_regex = false;   // env LC_B200_REGEX_KERNEL=basic   (tables in global memory)
-    int regex_variant = 0; // env LC_B200_REGEX_KERNEL: 0 auto, 1 "fast" (stride-1), 2 "fast2" (stride-2), 3 "generic"
+    int regex_variant = 0; // env LC_B200_REGEX_KERNEL: 0 auto, 1 "fast" (stride-1), 2 "fast2" (stride-2), 3 "generic",
+                           // 4 "tdfa" (single pass)
     uint64_t scratch_hint = 0;
     bool length_order = false; // env LC_B200_LENGTH_ORDER=1
+    uint32_t max_warps = 32;   // env LC_B200_MAX_WARPS (tuning knob: resident warps per block of the regex kernels)
     // staging / workspace (grow-only)
     DevBuf in, ev_off, ev_len, out_a, out_b, out_c, out_d, out_e;
     DevBuf lines_off, lines_len, flags, state, cnt, pos, lab_sizes, lab_off, lab, order;
@@ -101,7 +103,9 @@ cudaError_t engine_blob(lc_engine* e, const lc_regex* r, const void** out, int l
     *out = nullptr;
     if (!r)
         return cudaSuccess;
-    const std::vector<uint8_t>& src = layout == 2 ? r->res.fast2_blob : (layout == 1 ? r->res.fast_blob : r->res.blob);
+    const std::vector<uint8_t>& src = layout == 3   ? r->res.tdfa_blob
+                                      : layout == 2 ? r->res.fast2_blob
+                                                    : (layout == 1 ? r->res.fast_blob : r->res.blob);
     const uint64_t key = r->id * 4 + (uint64_t)layout;
     auto it = e->blobs.find(key);
     if (it != e->blobs.end()) {
@@ -215,9 +219,12 @@ int lc_engine_create(int device, lc_engine_t** out) {
     {
         const char* k = getenv("LC_B200_REGEX_KERNEL");
         e->force_basic_regex = k && !strcmp(k, "basic");
+        const char* mw = getenv("LC_B200_MAX_WARPS");
+        if (mw && atoi(mw) >= 4 && atoi(mw) <= 32)
+            e->max_warps = (uint32_t)atoi(mw);
         const char* lo = getenv("LC_B200_LENGTH_ORDER");
         e->length_order = lo && !strcmp(lo, "1");
-        e->regex_variant = !k ? 0 : (!strcmp(k, "fast") ? 1 : (!strcmp(k, "fast2") ? 2 : (!strcmp(k, "generic") ? 3 : 0)));
+        e->regex_variant = !k ? 0 : (!strcmp(k, "fast") ? 1 : (!strcmp(k, "fast2") ? 2 : (!strcmp(k, "generic") ? 3 : (!strcmp(k, "tdfa") ? 4 : 0))));
     }
     CU_TRY(e->small.ensure(sizeof(Small)));
     CU_TRY(cudaMallocHost(&e->h_small, sizeof(Small)));
@@ -444,6 +451,41 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
     Small* hs = (Small*)e->h_small;
     const bool force_basic = e->force_basic_regex;
     const size_t smem_max = (size_t)e->smem_per_block_optin;
+    // ---- single-pass tagged DFA: the preferred kernel whenever the pattern's TDFA fits shared memory
+    if (!force_basic && (e->regex_variant == 0 || e->regex_variant == 4) && !re->res.tdfa_blob.empty()) {
+        const LcTdfaHeader* th = reinterpret_cast<const LcTdfaHeader*>(re->res.tdfa_blob.data());
+        const uint32_t tb = (uint32_t)re->res.tdfa_blob.size();
+        uint32_t warps = e->max_warps;
+        while (warps > 4 && lck::tdfa_smem_bytes(tb, th->nregs, warps * 32) > smem_max)
+            warps -= 4;
+        bool usable = lck::tdfa_smem_bytes(tb, th->nregs, warps * 32) <= smem_max;
+        if (usable && base_len >= 65535) { // capture registers are 16-bit: every event must be < 65535 bytes
+            CU_TRY(cudaMemsetAsync(ds->counters, 0, sizeof ds->counters, e->stream));
+            lck::launch_len_stats(d_ev_len, n, ds->counters, e->stream);
+            e->launches++;
+            CU_TRY(cudaMemcpyAsync(hs->counters, ds->counters, sizeof ds->counters, cudaMemcpyDeviceToHost,
+                                   e->stream));
+            CU_TRY(cudaStreamSynchronize(e->stream));
+            usable = hs->counters[0] < 65535;
+        }
+        if (usable) {
+            const void* d_tblob;
+            CU_TRY(engine_blob(e, re, &d_tblob, 3));
+            const uint32_t threads = warps * 32;
+            const uint64_t need_blocks = (n + threads - 1) / threads;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(need_blocks, (uint64_t)e->num_sms);
+            const uint32_t* d_order = nullptr;
+            CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof(Small) - offsetof(Small, overflow), e->stream));
+            int er = lck::launch_regex_tdfa(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off, d_ev_len, n,
+                                            nkeys, d_status, bool_only ? nullptr : d_cap_off,
+                                            bool_only ? nullptr : d_cap_len, threads, grid, &ds->next_batch, d_order,
+                                            e->stream);
+            e->launches++;
+            if (er)
+                return fail(LC_ERR_CUDA, std::string("regex kernel launch: ") + cudaGetErrorString((cudaError_t)er));
+            return LC_OK;
+        }
+    }
     if (!force_basic) {
         // ---- pick the kernel variant: stride-2 layout > stride-1 fast layout > generic shared-memory interpreter
         uint64_t mx = 0, avg = base_len / n + 1;
@@ -513,8 +555,8 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
                     while (warps > 4 && (size_t)warps * ((size_t)lab_words * 128 + slot_bytes) > budget)
                         --warps;
                 }
-                if (warps > 32)
-                    warps = 32;
+                if (warps > e->max_warps)
+                    warps = e->max_warps;
                 threads = warps * 32;
                 blocks_per_sm = 1;
                 if (warps <= 16 && 2 * (blob_bytes + (size_t)warps * (lab_words * 128 + slot_bytes) + 1024) <=

@@ -284,3 +284,83 @@ LC_HD void lc_slots16_to_cap(const uint16_t* slots, uint32_t g, uint32_t n, uint
         *len = e - b;
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Single-pass tagged DFA (lc_tables.h: LcTdfaHeader): reference (loop) formulation; the kernel's unrolled middle
+// section is a specialisation of exactly these statements.
+struct LcTdfaView {
+    const LcTdfaHeader* h;
+    const uint8_t* cls;
+    const uint8_t* t2; // byte addressed (u32 entries)
+    const uint32_t* t1;
+    const uint32_t* eof;
+    const uint16_t* ops;
+};
+
+LC_HD LcTdfaView lc_tdfa_view(const void* blob) {
+    const uint8_t* b = (const uint8_t*)blob;
+    const LcTdfaHeader* h = (const LcTdfaHeader*)blob;
+    LcTdfaView v;
+    v.h = h;
+    v.cls = b + h->off_cls;
+    v.t2 = b + h->off_t2;
+    v.t1 = (const uint32_t*)(b + h->off_t1);
+    v.eof = (const uint32_t*)(b + h->off_eof);
+    v.ops = (const uint16_t*)(b + h->off_ops);
+    return v;
+}
+
+LC_HD void lc_tdfa_run_ops(const LcTdfaView& v, uint32_t list, uint32_t pos, uint16_t* regs) {
+    const uint16_t* p = v.ops + list;
+    const uint32_t cnt = p[0];
+    for (uint32_t k = 1; k <= cnt; ++k) {
+        const uint32_t op = p[k], dst = op >> 8, src = op & 0xFFu;
+        regs[dst] = src == LC_TDFA_SRC_POS ? (uint16_t)pos : src == LC_TDFA_SRC_UNSET ? (uint16_t)LC_SLOT16_UNSET : regs[src];
+    }
+}
+
+// one byte from `state` at position pos; returns the next state (0 = dead)
+LC_HD uint32_t lc_tdfa_single(const LcTdfaView& v, uint32_t state, uint32_t byte, uint32_t pos, uint16_t* regs) {
+    const uint32_t e = v.t1[state * v.h->ncls + v.cls[byte]];
+    if (e >> 16)
+        lc_tdfa_run_ops(v, e >> 16, pos, regs);
+    return e & 0xFFFFu;
+}
+
+// s = first byte of the event; `mis` = virtual index of that byte (address & 15 on the device; pairs are aligned
+// on even virtual indices).  regs: h->nregs u16 entries, the first 2 * ngroups preset to LC_SLOT16_UNSET; on a
+// match they hold the capture boundaries.  n must be < 65535.
+LC_HD bool lc_tdfa_event(const LcTdfaView& v, const uint8_t* s, uint32_t mis, uint32_t n, uint16_t* regs) {
+    const uint32_t ncls = v.h->ncls, row_bytes = v.h->row_bytes;
+    uint32_t st = v.h->start;
+    uint32_t pos = 0;
+    if ((mis & 1) && n) {
+        st = lc_tdfa_single(v, st, s[0], 0, regs);
+        pos = 1;
+    }
+    while (pos + 2 <= n) {
+        const uint32_t c0 = v.cls[s[pos]], c1 = v.cls[s[pos + 1]];
+        const uint32_t e = *(const uint32_t*)(v.t2 + st * row_bytes + (c0 * ncls + c1) * 4);
+        if (e & LC_TDFA_SLOW) {
+            const uint32_t s1 = lc_tdfa_single(v, st, s[pos], pos, regs);
+            (void)lc_tdfa_single(v, s1, s[pos + 1], pos + 1, regs);
+        } else {
+            const uint32_t sa = (e >> 16) & 0x7Fu, sb = (e >> 24) & 0x7Fu;
+            if (sa)
+                regs[(sa - 2) / 2] = (uint16_t)pos;
+            if (sb)
+                regs[(sb - 2) / 2] = (uint16_t)(pos + 1);
+        }
+        st = (e & 0xFFFFu) / row_bytes;
+        pos += 2;
+    }
+    if (pos < n) {
+        st = lc_tdfa_single(v, st, s[pos], pos, regs);
+        ++pos;
+    }
+    const uint32_t fin = v.eof[st];
+    if (fin == LC_NONE_ENTRY)
+        return false;
+    lc_tdfa_run_ops(v, fin, n, regs);
+    return true;
+}

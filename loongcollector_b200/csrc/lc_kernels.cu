@@ -1072,6 +1072,211 @@ int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, bool
     return (int)cudaGetLastError();
 }
 
+// ---- single-pass tagged-DFA kernel (lc_tables.h: LcTdfaHeader) ----------------------------------------------
+// One forward pass, two input bytes per dependent look-up, no labels: per byte pair
+//   c0 = cls[b0] ; c1 = cls[b1] ; e = t2[row + (c0 * ncls + c1) * 4] ; row = e & 0xFFFF           (the chain)
+//   bytes 2,3 of e -> up to two predicated 16-bit STS into the thread's register file in shared memory
+// The per-line state is the register file alone (2 * groups + spares halfwords), so all 32 warps stay resident
+// whatever the line length, and the input is read exactly once.
+struct TdfaDev {
+    const uint8_t* cls;
+    const uint8_t* t2;
+    uint32_t row_bytes, ncls;
+};
+
+#define LCT_PAIR(X, HI, POS)                                                                                           \
+    {                                                                                                                  \
+        const uint32_t b0 = __byte_perm((X), 0, (HI) ? 0x4442 : 0x4440), b1 = __byte_perm((X), 0, (HI) ? 0x4443 : 0x4441); \
+        const uint32_t c0 = t.cls[b0], c1 = t.cls[b1];                                                                 \
+        const uint32_t prow = row;                                                                                     \
+        const uint32_t e = *reinterpret_cast<const uint32_t*>(t.t2 + row + ((c0 * t.ncls + c1) << 2));                \
+        row = e & 0xFFFFu;                                                                                             \
+        const uint32_t sa = (e >> 16) & 0x7Fu, sb = e >> 24;                                                           \
+        if (sa)                                                                                                        \
+            *reinterpret_cast<uint16_t*>(regs_m2 + sa) = (uint16_t)(POS);                                              \
+        if (sb)                                                                                                        \
+            *reinterpret_cast<uint16_t*>(regs_m2 + sb) = (uint16_t)((POS) + 1);                                        \
+        if (SLOW && (e & LC_TDFA_SLOW)) {                                                                              \
+            uint16_t* rg = reinterpret_cast<uint16_t*>(regs_m2 + 2);                                                   \
+            const uint32_t s1 = lc_tdfa_single(v, prow / t.row_bytes, b0, (POS), rg);                                  \
+            (void)lc_tdfa_single(v, s1, b1, (POS) + 1, rg);                                                            \
+        }                                                                                                              \
+    }
+
+// One 16-byte chunk: the byte pairs at virtual positions [lo, lo + 16) restricted to [qlo, Qe).
+template <bool SLOW>
+__device__ __forceinline__ void tdfa_chunk(const LcTdfaView& v, const TdfaDev& t, const uint4 vv, uint32_t lo,
+                                           uint32_t mis, uint32_t qlo, uint32_t Qe, uint32_t& row, uint8_t* regs_m2) {
+    const uint32_t pos0 = lo - mis;
+    if (lo >= qlo && lo + 16 <= Qe) {
+        LCT_PAIR(vv.x, 0, pos0 + 0)
+        LCT_PAIR(vv.x, 1, pos0 + 2)
+        LCT_PAIR(vv.y, 0, pos0 + 4)
+        LCT_PAIR(vv.y, 1, pos0 + 6)
+        LCT_PAIR(vv.z, 0, pos0 + 8)
+        LCT_PAIR(vv.z, 1, pos0 + 10)
+        LCT_PAIR(vv.w, 0, pos0 + 12)
+        LCT_PAIR(vv.w, 1, pos0 + 14)
+    } else {
+        const uint32_t wd[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+        for (int pi = 0; pi < 8; ++pi) {
+            const uint32_t q = lo + 2 * pi;
+            if (q >= qlo && q < Qe)
+                LCT_PAIR(wd[pi >> 1], pi & 1, q - mis)
+        }
+    }
+}
+
+template <bool SLOW>
+__device__ __forceinline__ bool tdfa_event(const LcTdfaView& v, const TdfaDev& t, const uint8_t* __restrict__ s,
+                                           const uint4* __restrict__ chunks, uint32_t mis, uint32_t n,
+                                           uint8_t* regs_m2) {
+    const uint32_t Q = n + mis;
+    const uint32_t qlo = mis + (mis & 1); // first even virtual position whose pair lies inside the event
+    const uint32_t Qe = Q & ~1u;          // pairs cover [qlo, Qe)
+    uint16_t* rg = reinterpret_cast<uint16_t*>(regs_m2 + 2);
+    uint32_t st = v.h->start;
+    if ((mis & 1) && n) // odd first byte: single step
+        st = lc_tdfa_single(v, st, s[0], 0, rg);
+    uint32_t row = st * t.row_bytes;
+    if (Qe > qlo) {
+        const int c_lo = (int)(qlo >> 4), c_hi = (int)((Qe - 1) >> 4);
+        uint4 nxt = __ldg(chunks + c_lo);
+        for (int qc = c_lo; qc <= c_hi; ++qc) {
+            const uint4 vv = nxt;
+            if (qc < c_hi)
+                nxt = __ldg(chunks + qc + 1);
+            tdfa_chunk<SLOW>(v, t, vv, (uint32_t)qc * 16, mis, qlo, Qe, row, regs_m2);
+            if (row == 0)
+                return false;
+        }
+    }
+    st = row / t.row_bytes;
+    if ((Q & 1) && Q - 1 >= qlo) // odd last byte
+        st = lc_tdfa_single(v, st, s[n - 1], n - 1, rg);
+    const uint32_t fin = v.eof[st];
+    if (fin == LC_NONE_ENTRY)
+        return false;
+    lc_tdfa_run_ops(v, fin, n, rg);
+    return true;
+}
+
+template <bool SLOW>
+__global__ void __launch_bounds__(1024, 1)
+    regex_tdfa_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, const uint8_t* __restrict__ base,
+                      const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
+                      uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
+                      uint32_t* __restrict__ cap_len, uint32_t reg_pitch /* halfwords */,
+                      unsigned long long* next_batch, const uint32_t* __restrict__ order) {
+    extern __shared__ uint4 smem[];
+    for (uint32_t k = threadIdx.x; k < blob_bytes / 16; k += blockDim.x)
+        smem[k] = __ldg(blob + k);
+    __syncthreads();
+    const LcTdfaView v = lc_tdfa_view(smem);
+    TdfaDev t;
+    t.cls = v.cls;
+    t.t2 = v.t2;
+    t.ncls = v.h->ncls;
+    t.row_bytes = v.h->row_bytes;
+    const uint32_t G = v.h->ngroups;
+    // shared memory: [blob][register files: threads x reg_pitch halfwords]
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint16_t* wregs = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(smem) + blob_bytes) +
+                      (size_t)wid * 32 * reg_pitch; // this warp's 32 register files
+    uint16_t* regs = wregs + (size_t)lane * reg_pitch;
+    uint8_t* regs_m2 = reinterpret_cast<uint8_t*>(regs) - 2;
+    const bool bool_only = cap_off == nullptr; // lc_regex_match: status[i] = 1 match / 0 no match, no captures
+    for (;;) {
+        unsigned long long batch = 0;
+        if (lane == 0)
+            batch = atomicAdd(next_batch, 32ull);
+        batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+        if (batch >= n)
+            break;
+        const bool valid = batch + lane < n;
+        const uint64_t i = valid ? (order ? order[batch + lane] : batch + lane) : 0;
+        uint32_t off = 0, len = 0;
+        uint32_t st = 1;
+        if (valid) {
+            off = ev_off[i];
+            len = ev_len[i];
+            for (uint32_t k = 0; k < G; ++k)
+                reinterpret_cast<uint32_t*>(regs)[k] = 0xFFFFFFFFu; // home registers = LC_SLOT16_UNSET
+            const uint8_t* s = base + off;
+            const uint64_t a16 = (uint64_t)(uintptr_t)s;
+            const uint32_t mis16 = (uint32_t)(a16 & 15u);
+            const uint4* chunks = reinterpret_cast<const uint4*>(a16 - mis16);
+            const bool ok = tdfa_event<SLOW>(v, t, s, chunks, mis16, len, regs_m2);
+            st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
+            status[i] = bool_only ? (ok ? 1 : 0) : (uint8_t)st;
+        }
+        if (bool_only || G == 0)
+            continue;
+        if (order == nullptr) {
+            // coalesced result rows: element j of the batch's [32][G] tables is produced by lane j % 32 straight
+            // from the owning line's register file (one 32-bit LDS = begin | end << 16)
+            __syncwarp();
+            const uint64_t left = n - batch;
+            const uint32_t total = (uint32_t)(left < 32 ? left : 32) * G;
+            uint32_t* go = cap_off + batch * G;
+            uint32_t* gl = cap_len + batch * G;
+            for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const uint32_t line = j < total ? j / G : 0, g = j - line * G;
+                const uint32_t l_off = __shfl_sync(0xFFFFFFFFu, off, line);
+                const uint32_t l_len = __shfl_sync(0xFFFFFFFFu, len, line);
+                const uint32_t l_st = __shfl_sync(0xFFFFFFFFu, st, line);
+                if (j < total) {
+                    uint32_t o = 0, l = 0;
+                    if (l_st == 0) {
+                        const uint32_t be = reinterpret_cast<const uint32_t*>(wregs + (size_t)line * reg_pitch)[g];
+                        const uint32_t b = be & 0xFFFFu, en = be >> 16;
+                        if (b == LC_SLOT16_UNSET || en == LC_SLOT16_UNSET || en < b) {
+                            o = l_off + l_len;
+                        } else {
+                            o = l_off + b;
+                            l = en - b;
+                        }
+                    }
+                    go[j] = o;
+                    gl[j] = l;
+                }
+            }
+            __syncwarp();
+        } else if (valid) {
+            uint32_t* co = cap_off + i * G;
+            uint32_t* cl = cap_len + i * G;
+            for (uint32_t g = 0; g < G; ++g) {
+                uint32_t o = 0, l = 0;
+                if (st == 0) {
+                    lc_slots16_to_cap(regs, g, len, &o, &l);
+                    o += off;
+                }
+                co[g] = o;
+                cl[g] = l;
+            }
+        }
+    }
+}
+
+int launch_regex_tdfa(const void* d_blob, uint32_t blob_bytes, bool slow, uint32_t nregs, const uint8_t* d_base,
+                      const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                      uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t threads, uint32_t grid,
+                      unsigned long long* d_next_batch, const uint32_t* d_order, cudaStream_t st) {
+    if (!n)
+        return 0;
+    const uint32_t reg_pitch = tdfa_reg_pitch(nregs);
+    size_t smem = tdfa_smem_bytes(blob_bytes, nregs, threads);
+    auto k = slow ? regex_tdfa_kernel<true> : regex_tdfa_kernel<false>;
+    cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (er != cudaSuccess)
+        return (int)er;
+    k<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
+                                   d_cap_off, d_cap_len, reg_pitch, d_next_batch, d_order);
+    return (int)cudaGetLastError();
+}
+
 template <class LabT>
 __global__ void __launch_bounds__(1024, 1)
     regex_parse_smem_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, uint32_t G,

@@ -149,8 +149,50 @@ struct LcFast2Header {
     uint32_t reserved[3];
 };
 
+// ---- "tdfa blob": single forward pass, stride 2.  The priority-ordered NFA thread list is determinised together
+// with the capture bookkeeping (a tagged DFA with leftmost-first / Perl disambiguation): a state is the ordered list
+// of live threads, each with a map tag -> register; a transition may set registers to the current position.  The
+// scheme never needs register copies while scanning: an inherited value keeps its register, a new value takes the
+// tag's home register (= the tag index) when no live thread still refers to it, else a spare.  Only the end-of-input
+// action moves the winner's values to the home registers.  No reverse pass, no labels: half the look-ups of the
+// two-pass layouts and a per-line footprint of just the register file.
+//   cls   u8  [256]                byte -> class
+//   t2    u32 [nstates][ncls*ncls] pair step over bytes (b0 = earlier, b1 = later), indexed (c0 * ncls + c1):
+//                                  bits 0..15 = next_state * row_bytes (row_bytes = ncls*ncls*4; state 0 = dead),
+//                                  bits 16..22 = register set by the 1st step at position p   (2*reg + 2, 0 = none),
+//                                  bit  23     = slow path (some step sets more than one register),
+//                                  bits 24..30 = register set by the 2nd step at position p+1 (2*reg + 2, 0 = none).
+//   t1    u32 [nstates][ncls]      single step: next state | op-list index << 16 (peeled bytes and the slow path)
+//   eof   u32 [nstates]            end of input: op-list index of the winning thread, LC_NONE_ENTRY = no match
+//   ops   u16 []                   op lists: [count, op...], op = dst << 8 | src ; src 0xFF = current position,
+//                                  0xFE = unset, else a register (copy).  List 0 is empty.
+#define LC_TDFA_MAGIC 0x4C435444u /* 'LCTD' */
+#define LC_TDFA_SLOW 0x00800000u
+#define LC_TDFA_SRC_POS 0xFFu
+#define LC_TDFA_SRC_UNSET 0xFEu
+#define LC_TDFA_MAX_REGS 62u
+struct LcTdfaHeader {
+    uint32_t magic;
+    uint32_t total_bytes;
+    uint32_t ngroups;
+    uint32_t nstates;
+    uint32_t ncls;
+    uint32_t nregs; // 2 * ngroups home registers + spares
+    uint32_t start;
+    uint32_t row_bytes;
+    uint32_t off_cls;
+    uint32_t off_t2;
+    uint32_t off_t1;
+    uint32_t off_eof;
+    uint32_t off_ops;
+    uint32_t has_slow;
+    uint32_t max_threads; // diagnostics
+    uint32_t reserved[1];
+};
+
 #ifdef __cplusplus
 static_assert(sizeof(LcFast2Header) % 16 == 0, "fast2 header must keep 16B alignment");
+static_assert(sizeof(LcTdfaHeader) % 16 == 0, "tdfa header must keep 16B alignment");
 static_assert(sizeof(LcFastHeader) % 16 == 0, "fast header must keep 16B alignment");
 static_assert(sizeof(LcRegexHeader) % 16 == 0, "header must keep 16B alignment of what follows");
 #endif

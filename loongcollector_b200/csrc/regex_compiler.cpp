@@ -1633,6 +1633,239 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                 res.fast2_blob.swap(fb);
             }
         }
+
+        // ---- single-pass tagged DFA (see lc_tables.h: LcTdfaHeader).  Determinises the priority-ordered thread
+        // list of the backtracking search: thread order = priority, the first thread to reach a walker owns it,
+        // and the first thread (in order) that can take MATCH at end of input is the boost/Perl answer.
+        [&]() {
+            const uint32_t ncl = (uint32_t)nclasses;
+            const uint32_t T = 2 * res.ngroups;
+            const uint64_t row_bytes = (uint64_t)ncl * ncl * 4;
+            if (T > LC_TDFA_MAX_REGS || row_bytes > 65535)
+                return;
+            const size_t max_states = (size_t)(65535 / row_bytes); // next_state * row_bytes must fit 16 bits
+            struct TThread {
+                int w;
+                std::vector<int16_t> reg; // tag -> register, -1 = unset
+            };
+            struct TState {
+                int pk;
+                std::vector<TThread> th;
+            };
+            std::vector<TState> states(1); // 0 = dead
+            std::map<std::vector<int16_t>, uint32_t> ids;
+            auto key_of = [&](const TState& st) {
+                std::vector<int16_t> k;
+                k.reserve(1 + st.th.size() * (T + 1));
+                k.push_back((int16_t)st.pk);
+                for (auto& th : st.th) {
+                    k.push_back((int16_t)th.w);
+                    k.insert(k.end(), th.reg.begin(), th.reg.end());
+                }
+                return k;
+            };
+            bool ok = true;
+            auto intern = [&](TState&& st) -> uint32_t {
+                if (st.th.empty())
+                    return 0;
+                auto k = key_of(st);
+                auto it = ids.find(k);
+                if (it != ids.end())
+                    return it->second;
+                if (states.size() >= max_states || states.size() >= 4096) {
+                    ok = false;
+                    return 0;
+                }
+                uint32_t id = (uint32_t)states.size();
+                ids.emplace(std::move(k), id);
+                states.push_back(std::move(st));
+                return id;
+            };
+            std::vector<uint16_t> ops = {0}; // list 0 = empty
+            std::map<std::vector<uint16_t>, uint32_t> op_ids;
+            op_ids[std::vector<uint16_t>()] = 0;
+            auto op_list = [&](const std::vector<uint16_t>& lst) -> uint32_t {
+                auto it = op_ids.find(lst);
+                if (it != op_ids.end())
+                    return it->second;
+                if (ops.size() + lst.size() + 1 > 65535) {
+                    ok = false;
+                    return 0;
+                }
+                uint32_t id = (uint32_t)ops.size();
+                ops.push_back((uint16_t)lst.size());
+                ops.insert(ops.end(), lst.begin(), lst.end());
+                op_ids[lst] = id;
+                return id;
+            };
+            {
+                TState st0;
+                st0.pk = 0; // K_EDGE (or the single collapsed kind)
+                st0.th.push_back({0, std::vector<int16_t>(T, (int16_t)-1)});
+                intern(std::move(st0));
+            }
+            std::vector<uint32_t> t1;                     // [state][class] next | oplist << 16
+            std::vector<std::vector<uint8_t>> sets;       // [state][class] registers set by the step
+            std::vector<uint32_t> eof;
+            uint32_t nregs = T, max_threads = 1;
+            for (size_t s = 0; s < states.size() && ok; ++s) {
+                t1.resize((s + 1) * ncl, 0);
+                sets.resize((s + 1) * ncl);
+                eof.resize(s + 1, LC_NONE_ENTRY);
+                if (s == 0)
+                    continue;
+                const TState cur = states[s]; // copy: `states` grows
+                max_threads = std::max<uint32_t>(max_threads, (uint32_t)cur.th.size());
+                // end of input: the first thread that can take MATCH wins
+                for (size_t i = 0; i < cur.th.size() && eof[s] == LC_NONE_ENTRY; ++i)
+                    for (auto& cd : cand[cur.th[i].w]) {
+                        if (cd.target >= 0 || !asserts_hold(cd.asserts, cur.pk, K_EDGE))
+                            continue;
+                        std::vector<uint16_t> lst;
+                        for (uint32_t t = 0; t < T; ++t) {
+                            int r = cur.th[i].reg[t];
+                            if (cd.saves >> t & 1)
+                                lst.push_back((uint16_t)(t << 8 | LC_TDFA_SRC_POS));
+                            else if (r < 0)
+                                lst.push_back((uint16_t)(t << 8 | LC_TDFA_SRC_UNSET));
+                            else if ((uint32_t)r != t)
+                                lst.push_back((uint16_t)(t << 8 | (uint32_t)r));
+                        }
+                        eof[s] = op_list(lst);
+                        break;
+                    }
+                for (uint32_t c = 0; c < ncl && ok; ++c) {
+                    const int nk = class_kind[c];
+                    struct NT {
+                        int w, parent;
+                        uint64_t saves;
+                    };
+                    std::vector<NT> nts;
+                    std::vector<char> taken(nw, 0);
+                    for (size_t i = 0; i < cur.th.size(); ++i)
+                        for (auto& cd : cand[cur.th[i].w]) {
+                            if (cd.target < 0 || taken[cd.target])
+                                continue;
+                            if (cd.asserts && !asserts_hold(cd.asserts, cur.pk, nk))
+                                continue;
+                            if (!walker_has(cd.target, (int)c))
+                                continue;
+                            taken[cd.target] = 1;
+                            nts.push_back({cd.target, (int)i, cd.saves});
+                        }
+                    if (nts.empty())
+                        continue;
+                    if (nts.size() > 64) {
+                        ok = false;
+                        break;
+                    }
+                    // registers still referenced by inherited values
+                    std::vector<char> used(256, 0);
+                    uint64_t set_tags = 0;
+                    for (auto& nt : nts) {
+                        set_tags |= nt.saves;
+                        for (uint32_t t = 0; t < T; ++t)
+                            if (!(nt.saves >> t & 1)) {
+                                int r = cur.th[nt.parent].reg[t];
+                                if (r >= 0)
+                                    used[r] = 1;
+                            }
+                    }
+                    std::vector<int16_t> alloc(T, (int16_t)-1);
+                    std::vector<uint8_t> setregs;
+                    for (uint32_t t = 0; t < T; ++t)
+                        if (set_tags >> t & 1) {
+                            uint32_t r = t;
+                            if (used[r]) {
+                                r = T;
+                                while (r < 255 && used[r])
+                                    ++r;
+                            }
+                            if (r >= LC_TDFA_MAX_REGS) {
+                                ok = false;
+                                break;
+                            }
+                            used[r] = 1;
+                            alloc[t] = (int16_t)r;
+                            setregs.push_back((uint8_t)r);
+                            nregs = std::max(nregs, r + 1);
+                        }
+                    if (!ok)
+                        break;
+                    TState nx;
+                    nx.pk = ctx_full ? nk : 0;
+                    for (auto& nt : nts) {
+                        TThread th;
+                        th.w = nt.w;
+                        th.reg = cur.th[nt.parent].reg;
+                        for (uint32_t t = 0; t < T; ++t)
+                            if (nt.saves >> t & 1)
+                                th.reg[t] = alloc[t];
+                        nx.th.push_back(std::move(th));
+                    }
+                    uint32_t to = intern(std::move(nx));
+                    if (!ok)
+                        break;
+                    std::vector<uint16_t> lst;
+                    for (uint8_t r : setregs)
+                        lst.push_back((uint16_t)((uint32_t)r << 8 | LC_TDFA_SRC_POS));
+                    uint32_t ol = op_list(lst);
+                    t1[s * ncl + c] = to | (ol << 16);
+                    sets[s * ncl + c] = setregs;
+                }
+            }
+            if (!ok)
+                return;
+            const uint32_t ns = (uint32_t)states.size();
+            LcTdfaHeader th;
+            memset(&th, 0, sizeof th);
+            th.magic = LC_TDFA_MAGIC;
+            th.ngroups = res.ngroups;
+            th.nstates = ns;
+            th.ncls = ncl;
+            th.nregs = nregs;
+            th.start = 1;
+            th.row_bytes = (uint32_t)row_bytes;
+            th.max_threads = max_threads;
+            std::vector<uint32_t> t2((size_t)ns * ncl * ncl, 0);
+            for (uint32_t s = 1; s < ns; ++s)
+                for (uint32_t c0 = 0; c0 < ncl; ++c0) {
+                    uint32_t s1 = t1[(size_t)s * ncl + c0] & 0xFFFFu;
+                    if (!s1)
+                        continue;
+                    const auto& A = sets[(size_t)s * ncl + c0];
+                    for (uint32_t c1 = 0; c1 < ncl; ++c1) {
+                        uint32_t s2 = t1[(size_t)s1 * ncl + c1] & 0xFFFFu;
+                        if (!s2)
+                            continue;
+                        const auto& B = sets[(size_t)s1 * ncl + c1];
+                        uint32_t e = s2 * (uint32_t)row_bytes;
+                        if (A.size() > 1 || B.size() > 1) {
+                            e |= LC_TDFA_SLOW;
+                            th.has_slow = 1;
+                        } else {
+                            if (!A.empty())
+                                e |= (2u * A[0] + 2u) << 16;
+                            if (!B.empty())
+                                e |= (2u * B[0] + 2u) << 24;
+                        }
+                        t2[((size_t)s * ncl + c0) * ncl + c1] = e;
+                    }
+                }
+            std::vector<uint8_t> cls(byte_class, byte_class + 256);
+            std::vector<uint8_t> tb(sizeof th, 0);
+            put(tb, th.off_cls, cls);
+            put(tb, th.off_t2, t2);
+            put(tb, th.off_t1, t1);
+            put(tb, th.off_eof, eof);
+            put(tb, th.off_ops, ops);
+            while (tb.size() % 16)
+                tb.push_back(0);
+            th.total_bytes = (uint32_t)tb.size();
+            memcpy(tb.data(), &th, sizeof th);
+            if (tb.size() <= max_table_bytes)
+                res.tdfa_blob.swap(tb);
+        }();
     } catch (const Invalid& e) {
         res.valid = false;
         res.supported = false;

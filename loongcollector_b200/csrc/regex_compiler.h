@@ -24,6 +24,7 @@ struct CompileResult {
     std::vector<uint8_t> blob; // LcRegexHeader + arrays (lc_tables.h); empty unless supported
     std::vector<uint8_t> fast_blob; // LcFastHeader + kernel-ready tables; empty when the fast layout does not apply
     std::vector<uint8_t> fast2_blob; // LcFast2Header + stride-2 tables; empty when that layout does not apply
+    std::vector<uint8_t> tdfa_blob;  // LcTdfaHeader + single-pass tagged-DFA tables; empty when the TDFA is too large
     // diagnostics
     uint32_t n_insts = 0, n_walkers = 0, n_rev = 0, n_prefix = 0;
 };

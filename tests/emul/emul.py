@@ -36,6 +36,9 @@ def lib():
         L.emul_full_match.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p]
         L.emul_full_match_fast2.restype = C.c_int
         L.emul_full_match_fast2.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.emul_full_match_tdfa.restype = C.c_int
+        L.emul_full_match_tdfa.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.emul_tdfa_info.argtypes = [C.c_void_p, C.c_void_p]
         L.emul_fast2_bytes.restype = C.c_uint32
         L.emul_fast2_bytes.argtypes = [C.c_void_p]
         L.emul_fast_bytes.restype = C.c_uint32
@@ -84,6 +87,24 @@ class EmulRegex:
         if rc == 0:
             return None
         return [(int(co[g]), int(cl[g])) for g in range(self.ngroups)]
+
+    def full_match_tdfa(self, data: bytes, mis: int = 0):
+        """single-pass tagged DFA; returns 'n/a' when the pattern has no tdfa layout"""
+        co = np.zeros(max(self.ngroups, 1), np.uint32)
+        cl = np.zeros(max(self.ngroups, 1), np.uint32)
+        rc = lib().emul_full_match_tdfa(self._h, data, len(data), mis, co.ctypes.data_as(C.c_void_p),
+                                        cl.ctypes.data_as(C.c_void_p))
+        if rc < 0:
+            return "n/a"
+        if rc == 0:
+            return None
+        return [(int(co[g]), int(cl[g])) for g in range(self.ngroups)]
+
+    @property
+    def tdfa_info(self):
+        info = np.zeros(6, np.uint32)
+        lib().emul_tdfa_info(self._h, info.ctypes.data_as(C.c_void_p))
+        return dict(zip(("states", "classes", "regs", "max_threads", "has_slow", "bytes"), (int(x) for x in info)))
 
     @property
     def fast2_bytes(self):

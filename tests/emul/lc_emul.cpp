@@ -65,6 +65,34 @@ int emul_full_match_fast2(const EmulRegex* e, const uint8_t* s, uint32_t n, uint
         lc_slots16_to_cap(slots, g, n, cap_off + g, cap_len + g);
     return 1;
 }
+// single-pass tagged DFA: returns -1 when the pattern has no tdfa blob
+int emul_full_match_tdfa(const EmulRegex* e, const uint8_t* s, uint32_t n, uint32_t mis, uint32_t* cap_off,
+                         uint32_t* cap_len) {
+    if (e->r.tdfa_blob.empty())
+        return -1;
+    LcTdfaView v = lc_tdfa_view(e->r.tdfa_blob.data());
+    uint16_t regs[64];
+    for (uint32_t k = 0; k < 64; ++k)
+        regs[k] = LC_SLOT16_UNSET;
+    if (!lc_tdfa_event(v, s, mis, n, regs))
+        return 0;
+    for (uint32_t g = 0; g < v.h->ngroups; ++g)
+        lc_slots16_to_cap(regs, g, n, cap_off + g, cap_len + g);
+    return 1;
+}
+// info[0..5] = states, classes, registers, max threads per state, has_slow, table bytes
+void emul_tdfa_info(const EmulRegex* e, uint32_t* info) {
+    memset(info, 0, 6 * sizeof(uint32_t));
+    if (e->r.tdfa_blob.empty())
+        return;
+    const LcTdfaHeader* h = (const LcTdfaHeader*)e->r.tdfa_blob.data();
+    info[0] = h->nstates;
+    info[1] = h->ncls;
+    info[2] = h->nregs;
+    info[3] = h->max_threads;
+    info[4] = h->has_slow;
+    info[5] = h->total_bytes;
+}
 uint32_t emul_fast2_bytes(const EmulRegex* e) { return (uint32_t)e->r.fast2_blob.size(); }
 uint32_t emul_fast_bytes(const EmulRegex* e) { return (uint32_t)e->r.fast_blob.size(); }
 

@@ -309,7 +309,7 @@ def test_delim_matches_oracle(eng, sep, quote, extend, allow_short):
 
 
 # ------------------------------------------------------------------------------------------- kernel variants
-@pytest.mark.parametrize("variant", ["basic", "generic", "fast", "fast2"])
+@pytest.mark.parametrize("variant", ["basic", "generic", "fast", "fast2", "tdfa"])
 def test_regex_kernel_variants_agree(variant, monkeypatch):
     """The baseline (tables in global memory) and generic (smem interpreter) kernels stay parity-checked too."""
     lc = _lc()
@@ -320,6 +320,11 @@ def test_regex_kernel_variants_agree(variant, monkeypatch):
         lines = _noise_lines(rng, 1500) + _nginx_lines(rng, 1500) + [b"x" * 5000, b"[" + b"y" * 3000 + b"] [z] q"]
         for pattern in PATTERNS[:6]:
             _check_parse(e, pattern, lines)
+        # one event beyond the 16-bit capture registers of the stride-2 / single-pass kernels: they must hand the
+        # whole batch to a kernel with 32-bit slots
+        huge = lines[:200] + [b"GET /" + b"a" * 70000 + b" 200", b"k=" + b"v" * 66000]
+        for pattern in (PATTERNS[0], r"(\w+) /(\w+) (\d+)", r"(\w)=(.*)"):
+            _check_parse(e, pattern, huge)
     finally:
         e.close()
 

@@ -117,7 +117,7 @@ def py_caps(m, n):
 @pytest.mark.parametrize("seed", range(8))
 def test_random_patterns_agree_with_pcre2_and_python(seed):
     rng = random.Random(20260922 + seed)
-    checked = n_sup = n_two = 0
+    checked = n_sup = n_two = n_tdfa = 0
     for _ in range(400):
         pat = gen(rng)
         try:
@@ -142,6 +142,9 @@ def test_random_patterns_agree_with_pcre2_and_python(seed):
             s = rand_input(rng, ALPHA)
             want = o.full_match(s)
             got = e.full_match(s)
+            td = e.full_match_tdfa(s, rng.randint(0, 15))
+            assert td == "n/a" or td == got, ("tdfa", pat, s, td, got)
+            n_tdfa += td != "n/a"
             if _bol_at_end_corner(pat, s):
                 # boost (and Python) let a mid-pattern '^' match at END of input after a trailing newline;
                 # PCRE2 does not.  The engine follows boost; only Python can arbitrate this corner.
@@ -162,6 +165,7 @@ def test_random_patterns_agree_with_pcre2_and_python(seed):
                 assert (pr.match(s) is not None) == e.prefix_match(s), (pat, s)
             checked += 1
     assert checked > 2000 and n_sup > 100
+    assert n_tdfa > checked // 2  # the single-pass layout must cover most patterns
 
 
 def test_random_crlf_line_anchors_agree_with_pcre2_anycrlf():
