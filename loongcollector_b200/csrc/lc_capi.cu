@@ -81,7 +81,7 @@ struct lc_engine {
     int smem_per_sm = 0;
     bool force_basic_regex = false;   // env LC_B200_REGEX_KERNEL=basic   (tables in global memory)
     int regex_variant = 0; // env LC_B200_REGEX_KERNEL: 0 auto, 1 "fast" (stride-1), 2 "fast2" (stride-2), 3 "generic",
-                           // 4 "tdfa" (single pass)
+                           // 4 "tdfa" (single pass, staged input), 5 "tdfa_direct" (single pass, per-lane loads)
     uint64_t scratch_hint = 0;
     bool length_order = false; // env LC_B200_LENGTH_ORDER=1
     uint32_t max_warps = 32;   // env LC_B200_MAX_WARPS (tuning knob: resident warps per block of the regex kernels)
@@ -224,7 +224,7 @@ int lc_engine_create(int device, lc_engine_t** out) {
             e->max_warps = (uint32_t)atoi(mw);
         const char* lo = getenv("LC_B200_LENGTH_ORDER");
         e->length_order = lo && !strcmp(lo, "1");
-        e->regex_variant = !k ? 0 : (!strcmp(k, "fast") ? 1 : (!strcmp(k, "fast2") ? 2 : (!strcmp(k, "generic") ? 3 : (!strcmp(k, "tdfa") ? 4 : 0))));
+        e->regex_variant = !k ? 0 : (!strcmp(k, "fast") ? 1 : (!strcmp(k, "fast2") ? 2 : (!strcmp(k, "generic") ? 3 : (!strcmp(k, "tdfa") ? 4 : (!strcmp(k, "tdfa_direct") ? 5 : 0)))));
     }
     CU_TRY(e->small.ensure(sizeof(Small)));
     CU_TRY(cudaMallocHost(&e->h_small, sizeof(Small)));
@@ -452,13 +452,19 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
     const bool force_basic = e->force_basic_regex;
     const size_t smem_max = (size_t)e->smem_per_block_optin;
     // ---- single-pass tagged DFA: the preferred kernel whenever the pattern's TDFA fits shared memory
-    if (!force_basic && (e->regex_variant == 0 || e->regex_variant == 4) && !re->res.tdfa_blob.empty()) {
+    if (!force_basic && (e->regex_variant == 0 || e->regex_variant == 4 || e->regex_variant == 5) &&
+        !re->res.tdfa_blob.empty()) {
         const LcTdfaHeader* th = reinterpret_cast<const LcTdfaHeader*>(re->res.tdfa_blob.data());
         const uint32_t tb = (uint32_t)re->res.tdfa_blob.size();
+        const bool staged = e->regex_variant != 5;
+        auto smem_need = [&](uint32_t warps) {
+            return staged ? lck::tdfa_staged_smem_bytes(tb, th->nregs, warps * 32)
+                          : lck::tdfa_smem_bytes(tb, th->nregs, warps * 32);
+        };
         uint32_t warps = e->max_warps;
-        while (warps > 4 && lck::tdfa_smem_bytes(tb, th->nregs, warps * 32) > smem_max)
-            warps -= 4;
-        bool usable = lck::tdfa_smem_bytes(tb, th->nregs, warps * 32) <= smem_max;
+        while (warps > 4 && smem_need(warps) > smem_max)
+            warps -= 2;
+        bool usable = smem_need(warps) <= smem_max;
         if (usable && base_len >= 65535) { // capture registers are 16-bit: every event must be < 65535 bytes
             CU_TRY(cudaMemsetAsync(ds->counters, 0, sizeof ds->counters, e->stream));
             lck::launch_len_stats(d_ev_len, n, ds->counters, e->stream);
@@ -474,11 +480,17 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
             const uint32_t threads = warps * 32;
             const uint64_t need_blocks = (n + threads - 1) / threads;
             const uint32_t grid = (uint32_t)std::min<uint64_t>(need_blocks, (uint64_t)e->num_sms);
-            const uint32_t* d_order = nullptr;
             CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof(Small) - offsetof(Small, overflow), e->stream));
-            int er = lck::launch_regex_tdfa(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off, d_ev_len, n,
+            int er;
+            if (staged)
+                er = lck::launch_regex_tdfa_staged(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off,
+                                                   d_ev_len, n, nkeys, d_status, bool_only ? nullptr : d_cap_off,
+                                                   bool_only ? nullptr : d_cap_len, threads, grid, &ds->next_batch,
+                                                   e->stream);
+            else
+                er = lck::launch_regex_tdfa(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off, d_ev_len, n,
                                             nkeys, d_status, bool_only ? nullptr : d_cap_off,
-                                            bool_only ? nullptr : d_cap_len, threads, grid, &ds->next_batch, d_order,
+                                            bool_only ? nullptr : d_cap_len, threads, grid, &ds->next_batch, nullptr,
                                             e->stream);
             e->launches++;
             if (er)

@@ -343,15 +343,15 @@ LC_HD bool lc_tdfa_event(const LcTdfaView& v, const uint8_t* s, uint32_t mis, ui
         const uint32_t e = *(const uint32_t*)(v.t2 + st * row_bytes + (c0 * ncls + c1) * 4);
         if (e & LC_TDFA_SLOW) {
             const uint32_t s1 = lc_tdfa_single(v, st, s[pos], pos, regs);
-            (void)lc_tdfa_single(v, s1, s[pos + 1], pos + 1, regs);
+            st = lc_tdfa_single(v, s1, s[pos + 1], pos + 1, regs);
         } else {
             const uint32_t sa = (e >> 16) & 0x7Fu, sb = (e >> 24) & 0x7Fu;
             if (sa)
                 regs[(sa - 2) / 2] = (uint16_t)pos;
             if (sb)
                 regs[(sb - 2) / 2] = (uint16_t)(pos + 1);
+            st = (e & 0xFFFFu) / row_bytes;
         }
-        st = (e & 0xFFFFu) / row_bytes;
         pos += 2;
     }
     if (pos < n) {

@@ -1099,7 +1099,7 @@ struct TdfaDev {
         if (SLOW && (e & LC_TDFA_SLOW)) {                                                                              \
             uint16_t* rg = reinterpret_cast<uint16_t*>(regs_m2 + 2);                                                   \
             const uint32_t s1 = lc_tdfa_single(v, prow / t.row_bytes, b0, (POS), rg);                                  \
-            (void)lc_tdfa_single(v, s1, b1, (POS) + 1, rg);                                                            \
+            row = lc_tdfa_single(v, s1, b1, (POS) + 1, rg) * t.row_bytes;                                              \
         }                                                                                                              \
     }
 
@@ -1274,6 +1274,300 @@ int launch_regex_tdfa(const void* d_blob, uint32_t blob_bytes, bool slow, uint32
         return (int)er;
     k<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
                                    d_cap_off, d_cap_len, reg_pitch, d_next_batch, d_order);
+    return (int)cudaGetLastError();
+}
+
+// ---- staged single-pass kernel: the same automaton as regex_tdfa_kernel, fed through shared memory -----------
+// Why: with one line per lane, a per-lane 16-byte LDG touches 32 different 128-byte lines, i.e. 32 L1 tag
+// wavefronts for 512 bytes -- measured to cost more than the automaton's own look-ups.  Here the warp fetches its
+// 32 lines COOPERATIVELY: one cp.async (LDGSTS) instruction moves 4 full 128-byte lines (8 lanes x 16 B each, 4
+// wavefronts) straight into a per-warp staging tile laid out [chunk][(line + chunk) mod 32] in 16-byte units; the
+// rotation makes both the 16-byte async writes and the later per-lane LDS.128 reads bank-conflict free.  Lanes
+// then consume their own line from the tile.  All hot-loop accesses use 32-bit shared-window addresses: the class
+// table sits on a 256-byte boundary (address = PRMT(byte, base)), and the pair table's row offsets are rebased to
+// absolute addresses while the automaton is staged, so a pair step is
+//   PRMT PRMT LDS.U8 LDS.U8 IMAD LEA LDS LOP  + two predicated STS.U16 for capture boundaries.
+#define LCT_STAGE_CHUNKS 8u /* 16-byte chunks per line per stage: 128 B = one L1 line per 8-lane group */
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8_v(uint32_t a) { // mutable data (staging tile)
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64_v(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128_v(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts_u64(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+struct TdfaAbs {
+    uint32_t cls;       // absolute shared address of the class table (256-byte aligned)
+    uint32_t t2;        // absolute shared address of row 0 (= the dead state)
+    uint32_t ncls;
+    uint32_t row_bytes;
+    uint32_t inv_row;   // ceil(2^32 / row_bytes): state = umulhi(row - t2, inv_row)
+};
+
+#define LCS_PAIR(X, HI, POS)                                                                                           \
+    {                                                                                                                  \
+        const uint32_t c0 = lds_u8(__byte_perm((X), t.cls, (HI) ? 0x7652 : 0x7650));                                   \
+        const uint32_t c1 = lds_u8(__byte_perm((X), t.cls, (HI) ? 0x7653 : 0x7651));                                   \
+        const uint32_t e = lds_u32(row + ((c0 * t.ncls + c1) << 2));                                                   \
+        row = e & 0xFFFFu;                                                                                             \
+        const uint32_t sa = e & 0x7F0000u, sb = e >> 24;                                                               \
+        if (sa)                                                                                                        \
+            sts_u16(regs_m2 + __umulhi(sa, 0x10000u), (POS));                                                          \
+        if (sb)                                                                                                        \
+            sts_u16(regs_m2 + sb, (POS) + 1);                                                                          \
+    }
+
+// Out-of-line redo of one chunk whose fast pass met an entry that sets several registers in one step: single steps
+// with full op lists over the same pairs, from the state at chunk entry.  Re-executing the single-register sets
+// in order on top of the fast pass leaves exactly the sequential result.
+__device__ __noinline__ uint32_t tdfa_chunk_slow(const LcTdfaView v, uint32_t st, uint4 vv, uint32_t lo,
+                                                 uint32_t mis, uint32_t qlo, uint32_t Qe, uint16_t* rg) {
+    const uint32_t wd[4] = {vv.x, vv.y, vv.z, vv.w};
+    for (uint32_t pi = 0; pi < 8; ++pi) {
+        const uint32_t q = lo + 2 * pi;
+        if (q >= qlo && q < Qe) {
+            const uint32_t w = wd[pi >> 1] >> ((pi & 1) * 16);
+            st = lc_tdfa_single(v, st, w & 0xFFu, q - mis, rg);
+            st = lc_tdfa_single(v, st, (w >> 8) & 0xFFu, q + 1 - mis, rg);
+        }
+    }
+    return st;
+}
+
+template <bool SLOW>
+__global__ void __launch_bounds__(1024, 1)
+    regex_tdfa_staged_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, const uint8_t* __restrict__ base,
+                             const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
+                             uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
+                             uint32_t* __restrict__ cap_len, uint32_t reg_pitch /* halfwords */,
+                             unsigned long long* next_batch) {
+    extern __shared__ uint4 smem[];
+    // carve-out: [pad][cls 256 B @ 256-aligned][blob][register files][line info: warps x 32 x 8 B][tiles: warps x 4 KB]
+    const uint32_t s0abs = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t cls_abs = (s0abs + 255u) & ~255u;
+    uint8_t* g_cls = reinterpret_cast<uint8_t*>(smem) + (cls_abs - s0abs);
+    uint4* g_blob = reinterpret_cast<uint4*>(g_cls + 256);
+    for (uint32_t k = threadIdx.x; k < blob_bytes / 16; k += blockDim.x)
+        g_blob[k] = __ldg(blob + k);
+    __syncthreads();
+    const LcTdfaView v = lc_tdfa_view(g_blob);
+    TdfaAbs t;
+    t.cls = cls_abs;
+    asm volatile("" : "+r"(t.cls)); // keep it in a vector register: PRMT then takes the selector as an immediate
+    t.t2 = cls_abs + 256 + v.h->off_t2;
+    t.ncls = v.h->ncls;
+    t.row_bytes = v.h->row_bytes;
+    t.inv_row = (uint32_t)((0x100000000ull + t.row_bytes - 1) / t.row_bytes);
+    if (t.t2 + (v.h->nstates + 1) * t.row_bytes > 65535u)
+        __trap(); // rows could not be addressed with 16 bits: the host must not select this kernel
+    for (uint32_t k = threadIdx.x; k < 64; k += blockDim.x)
+        reinterpret_cast<uint32_t*>(g_cls)[k] = reinterpret_cast<const uint32_t*>(v.cls)[k];
+    {
+        uint32_t* t2w = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(g_blob) + v.h->off_t2);
+        const uint32_t nent = (v.h->nstates + 1) * t.ncls * t.ncls;
+        for (uint32_t k = threadIdx.x; k < nent; k += blockDim.x)
+            t2w[k] += t.t2; // rebase: low 16 bits = absolute shared address of the next row
+    }
+    __syncthreads();
+    const uint32_t G = v.h->ngroups;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint8_t* g_regs0 = reinterpret_cast<uint8_t*>(g_blob) + blob_bytes;
+    uint16_t* wregs = reinterpret_cast<uint16_t*>(g_regs0) + (size_t)wid * 32 * reg_pitch;
+    uint16_t* regs = wregs + (size_t)lane * reg_pitch;
+    const uint32_t regs_abs = (uint32_t)__cvta_generic_to_shared(regs);
+    const uint32_t regs_m2 = regs_abs - 2;
+    const uint32_t info_abs = (uint32_t)__cvta_generic_to_shared(g_regs0 + (size_t)blockDim.x * reg_pitch * 2) + wid * 256;
+    const uint32_t tile_abs = (uint32_t)__cvta_generic_to_shared(g_regs0 + (size_t)blockDim.x * reg_pitch * 2) +
+                              nwarps * 256 + wid * (LCT_STAGE_CHUNKS * 512);
+    const uint4* gbase128 = reinterpret_cast<const uint4*>((uintptr_t)base & ~(uintptr_t)127);
+    const uint32_t base_mis = (uint32_t)((uintptr_t)base & 127);
+    const bool bool_only = cap_off == nullptr;
+    const uint32_t dead = t.t2, sink = t.t2 + v.h->sink * t.row_bytes;
+    for (;;) {
+        unsigned long long batch = 0;
+        if (lane == 0)
+            batch = atomicAdd(next_batch, 32ull);
+        batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+        if (batch >= n)
+            break;
+        const bool valid = batch + lane < n;
+        const uint64_t i = batch + lane;
+        uint32_t off = 0, len = 0, mis = 0, nch = 0, cfirst = 0, g0 = 0;
+        if (valid) {
+            off = ev_off[i];
+            len = ev_len[i];
+            const uint64_t a = (uint64_t)base_mis + off; // byte offset from gbase128
+            mis = (uint32_t)(a & 127);
+            g0 = (uint32_t)((a - mis) >> 4);
+            nch = (mis + len + 15) >> 4;
+            cfirst = mis >> 4;
+            for (uint32_t k = 0; k < G; ++k)
+                reinterpret_cast<uint32_t*>(regs)[k] = 0xFFFFFFFFu; // home registers = LC_SLOT16_UNSET
+        }
+        sts_u64(info_abs + lane * 8, g0, nch | (cfirst << 16));
+        const uint32_t max_nch = __reduce_max_sync(0xFFFFFFFFu, nch);
+        const uint32_t Q = len + mis;
+        const uint32_t qlo = mis + (mis & 1);
+        const uint32_t Qe = Q & ~1u;
+        const uint32_t c_last = (Q & 1) && Q - 1 >= qlo ? (Q - 1) >> 4 : 0xFFFFFFFFu; // chunk of the odd last byte
+        uint16_t* rg = regs;
+        uint32_t row = t.t2 + v.h->start * t.row_bytes;
+        __syncwarp();
+        for (uint32_t s0 = 0; s0 < max_nch; s0 += LCT_STAGE_CHUNKS) {
+            // ---- cooperative fetch: instruction r moves chunks s0..s0+7 of lines r, r+8, r+16, r+24
+            {
+                const uint32_t q = lane & 7, cidx = s0 + q;
+#pragma unroll
+                for (uint32_t r = 0; r < 8; ++r) {
+                    const uint32_t line = (lane >> 3) * 8 + r;
+                    const uint2 inf = lds_u64_v(info_abs + line * 8);
+                    const uint32_t l_nch = inf.y & 0xFFFFu, l_first = inf.y >> 16;
+                    if (cidx >= l_first && cidx < l_nch)
+                        cp_async_16(tile_abs + ((q * 32 + ((line + q) & 31)) << 4), gbase128 + inf.x + cidx);
+                }
+                cp_async_wait_all();
+            }
+            __syncwarp();
+            // ---- every lane walks its own line through the tile
+            if (valid && row != dead) {
+                for (uint32_t q = 0; q < LCT_STAGE_CHUNKS; ++q) {
+                    const uint32_t qc = s0 + q;
+                    if (qc < cfirst || qc >= nch)
+                        continue;
+                    const uint32_t caddr = tile_abs + ((q * 32 + ((lane + q) & 31)) << 4);
+                    const uint32_t lo = qc * 16;
+                    if (qc == cfirst && (mis & 1) && len) { // odd first byte: single step from the start state
+                        const uint32_t st1 = lc_tdfa_single(v, v.h->start, lds_u8_v(caddr + (mis & 15)), 0, rg);
+                        row = t.t2 + st1 * t.row_bytes;
+                    }
+                    if (Qe > qlo && lo < Qe && lo + 16 > qlo) {
+                        const uint4 vv = lds_u128_v(caddr);
+                        const uint32_t row_in = row;
+                        const uint32_t pos0 = lo - mis;
+                        if (lo >= qlo && lo + 16 <= Qe) {
+                            LCS_PAIR(vv.x, 0, pos0 + 0)
+                            LCS_PAIR(vv.x, 1, pos0 + 2)
+                            LCS_PAIR(vv.y, 0, pos0 + 4)
+                            LCS_PAIR(vv.y, 1, pos0 + 6)
+                            LCS_PAIR(vv.z, 0, pos0 + 8)
+                            LCS_PAIR(vv.z, 1, pos0 + 10)
+                            LCS_PAIR(vv.w, 0, pos0 + 12)
+                            LCS_PAIR(vv.w, 1, pos0 + 14)
+                        } else {
+                            const uint32_t wd[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+                            for (int pi = 0; pi < 8; ++pi) {
+                                const uint32_t qq = lo + 2 * pi;
+                                if (qq >= qlo && qq < Qe)
+                                    LCS_PAIR(wd[pi >> 1], pi & 1, qq - mis)
+                            }
+                        }
+                        if (SLOW && row == sink) // some step set several registers: redo this chunk step by step
+                            row = t.t2 + t.row_bytes * tdfa_chunk_slow(v, __umulhi(row_in - t.t2, t.inv_row), vv, lo,
+                                                                       mis, qlo, Qe, rg);
+                    }
+                    if (qc == c_last) { // odd last byte
+                        const uint32_t st1 = lc_tdfa_single(v, __umulhi(row - t.t2, t.inv_row),
+                                                            lds_u8_v(caddr + ((Q - 1) & 15)), len - 1, rg);
+                        row = t.t2 + st1 * t.row_bytes;
+                    }
+                    if (row == dead)
+                        break;
+                }
+            }
+            __syncwarp();
+        }
+        uint32_t st = 1;
+        if (valid) {
+            bool ok = false;
+            const uint32_t fin = v.eof[__umulhi(row - t.t2, t.inv_row)];
+            if (fin != LC_NONE_ENTRY) {
+                lc_tdfa_run_ops(v, fin, len, rg);
+                ok = true;
+            }
+            st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
+            status[i] = bool_only ? (ok ? 1 : 0) : (uint8_t)st;
+        }
+        if (bool_only || G == 0)
+            continue;
+        // coalesced result rows: element j of the batch's [32][G] tables is produced by lane j % 32 straight from
+        // the owning line's register file (one 32-bit LDS = begin | end << 16)
+        __syncwarp();
+        const uint64_t left = n - batch;
+        const uint32_t total = (uint32_t)(left < 32 ? left : 32) * G;
+        uint32_t* go = cap_off + batch * G;
+        uint32_t* gl = cap_len + batch * G;
+        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const uint32_t line = j < total ? j / G : 0, g = j - line * G;
+            const uint32_t l_off = __shfl_sync(0xFFFFFFFFu, off, line);
+            const uint32_t l_len = __shfl_sync(0xFFFFFFFFu, len, line);
+            const uint32_t l_st = __shfl_sync(0xFFFFFFFFu, st, line);
+            if (j < total) {
+                uint32_t o = 0, l = 0;
+                if (l_st == 0) {
+                    const uint32_t be = reinterpret_cast<const volatile uint32_t*>(wregs + (size_t)line * reg_pitch)[g];
+                    const uint32_t b = be & 0xFFFFu, en = be >> 16;
+                    if (b == LC_SLOT16_UNSET || en == LC_SLOT16_UNSET || en < b) {
+                        o = l_off + l_len;
+                    } else {
+                        o = l_off + b;
+                        l = en - b;
+                    }
+                }
+                go[j] = o;
+                gl[j] = l;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow, uint32_t nregs, const uint8_t* d_base,
+                             const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
+                             uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t threads,
+                             uint32_t grid, unsigned long long* d_next_batch, cudaStream_t st) {
+    if (!n)
+        return 0;
+    const uint32_t reg_pitch = tdfa_reg_pitch(nregs);
+    size_t smem = tdfa_staged_smem_bytes(blob_bytes, nregs, threads);
+    auto k = slow ? regex_tdfa_staged_kernel<true> : regex_tdfa_staged_kernel<false>;
+    cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (er != cudaSuccess)
+        return (int)er;
+    k<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
+                                   d_cap_off, d_cap_len, reg_pitch, d_next_batch);
     return (int)cudaGetLastError();
 }
 

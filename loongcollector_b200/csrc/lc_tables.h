@@ -160,7 +160,9 @@ struct LcFast2Header {
 //   t2    u32 [nstates][ncls*ncls] pair step over bytes (b0 = earlier, b1 = later), indexed (c0 * ncls + c1):
 //                                  bits 0..15 = next_state * row_bytes (row_bytes = ncls*ncls*4; state 0 = dead),
 //                                  bits 16..22 = register set by the 1st step at position p   (2*reg + 2, 0 = none),
-//                                  bit  23     = slow path (some step sets more than one register),
+//                                  bit  23     = slow path (some step sets more than one register): such entries
+//                                                lead to the absorbing SINK row (index nstates) instead of the real
+//                                                next state, which only the single-step tables can produce,
 //                                  bits 24..30 = register set by the 2nd step at position p+1 (2*reg + 2, 0 = none).
 //   t1    u32 [nstates][ncls]      single step: next state | op-list index << 16 (peeled bytes and the slow path)
 //   eof   u32 [nstates]            end of input: op-list index of the winning thread, LC_NONE_ENTRY = no match
@@ -171,6 +173,7 @@ struct LcFast2Header {
 #define LC_TDFA_SRC_POS 0xFFu
 #define LC_TDFA_SRC_UNSET 0xFEu
 #define LC_TDFA_MAX_REGS 62u
+#define LC_TDFA_REBASE_ROOM 4096u /* t2 must start below this shared-memory address (header + cls + carve-out) */
 struct LcTdfaHeader {
     uint32_t magic;
     uint32_t total_bytes;
@@ -187,7 +190,7 @@ struct LcTdfaHeader {
     uint32_t off_ops;
     uint32_t has_slow;
     uint32_t max_threads; // diagnostics
-    uint32_t reserved[1];
+    uint32_t sink;        // index of the slow-path sink row (= nstates; t2 has nstates + 1 rows)
 };
 
 #ifdef __cplusplus

@@ -1641,9 +1641,12 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
             const uint32_t ncl = (uint32_t)nclasses;
             const uint32_t T = 2 * res.ngroups;
             const uint64_t row_bytes = (uint64_t)ncl * ncl * 4;
-            if (T > LC_TDFA_MAX_REGS || row_bytes > 65535)
+            if (T > LC_TDFA_MAX_REGS || row_bytes > 16384)
                 return;
-            const size_t max_states = (size_t)(65535 / row_bytes); // next_state * row_bytes must fit 16 bits
+            // next_state * row_bytes must fit 16 bits even after the kernel rebases the rows to absolute
+            // shared-memory addresses (the tables sit within the first LC_TDFA_REBASE_ROOM bytes of the window)
+            // (one row is reserved for the slow-path sink)
+            const size_t max_states = (size_t)((65535 - LC_TDFA_REBASE_ROOM) / row_bytes) - 1;
             struct TThread {
                 int w;
                 std::vector<int16_t> reg; // tag -> register, -1 = unset
@@ -1827,7 +1830,12 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
             th.start = 1;
             th.row_bytes = (uint32_t)row_bytes;
             th.max_threads = max_threads;
-            std::vector<uint32_t> t2((size_t)ns * ncl * ncl, 0);
+            // row ns = the slow-path sink: entries whose steps set several registers lead there and it absorbs
+            // every byte pair, so a kernel can test for it once per 16-byte chunk and redo that chunk step by step
+            th.sink = ns;
+            std::vector<uint32_t> t2((size_t)(ns + 1) * ncl * ncl, 0);
+            for (uint32_t k = 0; k < ncl * ncl; ++k)
+                t2[(size_t)ns * ncl * ncl + k] = ns * (uint32_t)row_bytes | LC_TDFA_SLOW;
             for (uint32_t s = 1; s < ns; ++s)
                 for (uint32_t c0 = 0; c0 < ncl; ++c0) {
                     uint32_t s1 = t1[(size_t)s * ncl + c0] & 0xFFFFu;
@@ -1841,7 +1849,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                         const auto& B = sets[(size_t)s1 * ncl + c1];
                         uint32_t e = s2 * (uint32_t)row_bytes;
                         if (A.size() > 1 || B.size() > 1) {
-                            e |= LC_TDFA_SLOW;
+                            e = ns * (uint32_t)row_bytes | LC_TDFA_SLOW;
                             th.has_slow = 1;
                         } else {
                             if (!A.empty())

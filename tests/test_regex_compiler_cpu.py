@@ -190,6 +190,8 @@ def test_random_crlf_line_anchors_agree_with_pcre2_anycrlf():
             if _bol_at_end_corner(pat, s) or b"\r\n" in s:
                 continue  # boost never anchors BETWEEN \r and \n; PCRE2 does -- see test_boost_crlf_unit
             assert e.full_match(s) == o.full_match(s), (pat, s)
+            td = e.full_match_tdfa(s, rng.randint(0, 127))
+            assert td == "n/a" or td == e.full_match(s), ("tdfa", pat, s)
             assert e.prefix_match(s) == o.prefix_match(s), (pat, s)
             n += 1
     assert n > 500
@@ -213,3 +215,38 @@ def test_boost_crlf_unit():
     assert e.full_match(b"a\n\rb") == []
     e = EmulRegex(r"a\n^")
     assert e.full_match(b"a\n") == []            # '^' at end of input after a trailing separator (boost, Python)
+
+
+def test_tdfa_layout_on_benchmark_patterns_and_corners():
+    """The single-pass tagged DFA (the headline kernel's tables) against the oracle on realistic lines, at both
+    pair alignments, plus the corners its register scheme must get right: empty groups (two boundaries in one
+    step -> slow path), optional groups left unset, captures inside repeats (last iteration wins) and
+    alternations whose losing branch wrote a register first."""
+    from loongcollector_b200 import synth
+    rng = random.Random(5)
+    for pat in (synth.NGINX_PATTERN, synth.APACHE_PATTERN, synth.CSV_URL_PATTERN):
+        e, o = EmulRegex(pat), orc.Regex(pat)
+        info = e.tdfa_info
+        assert info["states"] > 1 and info["regs"] >= 2 * e.ngroups, (pat, info)
+        buf, off, ln = synth.nginx_lines(300, seed=rng.randint(0, 1 << 30), line_bytes=None)
+        lines = [bytes(buf[a:a + b]) for a, b in zip(off, ln)]
+        lines += [l[:rng.randint(0, len(l))] for l in lines[:60]] + [l.replace(b'"-"', b'""') for l in lines[:60]]
+        for l in lines:
+            want = o.full_match(l)
+            for mis in (0, 1, 14, 15, 77):
+                assert e.full_match_tdfa(l, mis) == want, (pat, l, mis)
+    corners = [
+        (r"(a*)(b*)(c*)", [b"", b"a", b"b", b"c", b"abc", b"aacc", b"bb"]),
+        (r"(?:(a)|(b)|(c))*", [b"", b"a", b"ab", b"abc", b"cba", b"aab"]),
+        (r"(a|ab)(c|bcd)(d*)", [b"abcd", b"acd", b"abcdd", b"ac"]),
+        (r"(\d+)-(\d+)?(x|yy)*(.*?)(\s.*|)", [b"1-2xyy z", b"12-", b"1-xx", b"3-4yyx\tq"]),
+        (r'"([^"]*)" "([^"]*)"', [b'"" ""', b'"a" ""', b'"" "b"', b'"ab" "cd"']),
+        (r"(\S+\]) (x*)", [b"a]b] xx", b"]]] ", b"a] x"]),
+        (r"^(\w+)\b.(\w+)$", [b"ab cd", b"ab,cd", b"a\nb"]),
+    ]
+    for pat, inputs in corners:
+        e, o = EmulRegex(pat), orc.Regex(pat)
+        assert e.tdfa_info["states"] > 1, pat
+        for s in inputs:
+            for mis in (0, 1):
+                assert e.full_match_tdfa(s, mis) == o.full_match(s), (pat, s, mis)
