@@ -1304,6 +1304,11 @@ __device__ __forceinline__ uint32_t lds_u8_v(uint32_t a) { // mutable data (stag
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u32_v(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint2 lds_u64_v(uint32_t a) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
@@ -1350,19 +1355,52 @@ struct TdfaAbs {
 
 // Out-of-line redo of one chunk whose fast pass met an entry that sets several registers in one step: single steps
 // with full op lists over the same pairs, from the state at chunk entry.  Re-executing the single-register sets
-// in order on top of the fast pass leaves exactly the sequential result.
-__device__ __noinline__ uint32_t tdfa_chunk_slow(const LcTdfaView v, uint32_t st, uint4 vv, uint32_t lo,
-                                                 uint32_t mis, uint32_t qlo, uint32_t Qe, uint16_t* rg) {
+// in order on top of the fast pass leaves exactly the sequential result.  Returns the state after the chunk.
+__device__ __noinline__ uint32_t tdfa_chunk_slow(const LcTdfaView v, uint32_t st, uint4 vv, uint32_t pos0,
+                                                 uint16_t* rg) {
     const uint32_t wd[4] = {vv.x, vv.y, vv.z, vv.w};
     for (uint32_t pi = 0; pi < 8; ++pi) {
-        const uint32_t q = lo + 2 * pi;
-        if (q >= qlo && q < Qe) {
-            const uint32_t w = wd[pi >> 1] >> ((pi & 1) * 16);
-            st = lc_tdfa_single(v, st, w & 0xFFu, q - mis, rg);
-            st = lc_tdfa_single(v, st, (w >> 8) & 0xFFu, q + 1 - mis, rg);
-        }
+        const uint32_t w = wd[pi >> 1] >> ((pi & 1) * 16);
+        st = lc_tdfa_single(v, st, w & 0xFFu, pos0 + 2 * pi, rg);
+        st = lc_tdfa_single(v, st, (w >> 8) & 0xFFu, pos0 + 2 * pi + 1, rg);
     }
     return st;
+}
+
+// A chunk that is not fully covered by byte pairs of the line (its first and/or last chunk): optional odd first
+// byte, the pairs inside [qlo, Qe), optional odd last byte.  At most two calls per line.  caddr = shared address
+// of the chunk in the tile, lo = index of its first byte in the line's 16-byte aligned frame.
+__device__ __noinline__ uint32_t tdfa_partial_chunk(const LcTdfaView v, const TdfaAbs t, uint32_t row, uint32_t caddr,
+                                                    uint32_t lo, uint32_t mis, uint32_t len, uint32_t regs_m2,
+                                                    uint16_t* rg, uint32_t sink) {
+    const uint32_t Q = len + mis, qlo = mis + (mis & 1), Qe = Q & ~1u;
+    if (lo == 0 && (mis & 1)) { // odd first byte (frame index mis lies in chunk 0): single step from the start state
+        const uint32_t st1 = lc_tdfa_single(v, v.h->start, lds_u8_v(caddr + mis), 0, rg);
+        row = t.t2 + st1 * t.row_bytes;
+    }
+    const uint32_t a = lo > qlo ? lo : qlo, b = lo + 16 < Qe ? lo + 16 : Qe;
+    for (uint32_t q = a; q < b; q += 2) {
+        const uint32_t b0 = lds_u8_v(caddr + (q - lo)), b1 = lds_u8_v(caddr + (q - lo) + 1);
+        const uint32_t e = lds_u32(row + ((lds_u8(t.cls | b0) * t.ncls + lds_u8(t.cls | b1)) << 2));
+        const uint32_t nrow = e & 0xFFFFu;
+        if (nrow == sink) {
+            const uint32_t s1 = lc_tdfa_single(v, __umulhi(row - t.t2, t.inv_row), b0, q - mis, rg);
+            row = t.t2 + t.row_bytes * lc_tdfa_single(v, s1, b1, q + 1 - mis, rg);
+        } else {
+            const uint32_t sa = (e >> 16) & 0x7Fu, sb = e >> 24;
+            if (sa)
+                sts_u16(regs_m2 + sa, q - mis);
+            if (sb)
+                sts_u16(regs_m2 + sb, q + 1 - mis);
+            row = nrow;
+        }
+    }
+    if ((Q & 1) && Q - 1 >= qlo && ((Q - 1) >> 4) == (lo >> 4)) { // odd last byte
+        const uint32_t st1 = lc_tdfa_single(v, __umulhi(row - t.t2, t.inv_row), lds_u8_v(caddr + ((Q - 1) & 15)),
+                                            len - 1, rg);
+        row = t.t2 + st1 * t.row_bytes;
+    }
+    return row;
 }
 
 template <bool SLOW>
@@ -1401,19 +1439,28 @@ __global__ void __launch_bounds__(1024, 1)
     }
     __syncthreads();
     const uint32_t G = v.h->ngroups;
+    const uint32_t invG = G ? 0xFFFFFFFFu / G + 1 : 0; // umulhi(j, invG) == j / G for j < 65536
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint8_t* g_regs0 = reinterpret_cast<uint8_t*>(g_blob) + blob_bytes;
     uint16_t* wregs = reinterpret_cast<uint16_t*>(g_regs0) + (size_t)wid * 32 * reg_pitch;
     uint16_t* regs = wregs + (size_t)lane * reg_pitch;
+    const uint32_t wregs_abs = (uint32_t)__cvta_generic_to_shared(wregs);
     const uint32_t regs_abs = (uint32_t)__cvta_generic_to_shared(regs);
     const uint32_t regs_m2 = regs_abs - 2;
-    const uint32_t info_abs = (uint32_t)__cvta_generic_to_shared(g_regs0 + (size_t)blockDim.x * reg_pitch * 2) + wid * 256;
-    const uint32_t tile_abs = (uint32_t)__cvta_generic_to_shared(g_regs0 + (size_t)blockDim.x * reg_pitch * 2) +
-                              nwarps * 256 + wid * (LCT_STAGE_CHUNKS * 512);
-    const uint4* gbase128 = reinterpret_cast<const uint4*>((uintptr_t)base & ~(uintptr_t)127);
-    const uint32_t base_mis = (uint32_t)((uintptr_t)base & 127);
+    const uint32_t aux_abs = (uint32_t)__cvta_generic_to_shared(g_regs0 + (size_t)blockDim.x * reg_pitch * 2);
+    const uint32_t info_abs = aux_abs + wid * 256;
+    const uint32_t tile_abs = aux_abs + nwarps * 256 + wid * (LCT_STAGE_CHUNKS * 512);
+    const uint4* gbase16 = reinterpret_cast<const uint4*>((uintptr_t)base & ~(uintptr_t)15);
+    const uint32_t base_mis = (uint32_t)((uintptr_t)base & 15);
     const bool bool_only = cap_off == nullptr;
     const uint32_t dead = t.t2, sink = t.t2 + v.h->sink * t.row_bytes;
+    uint16_t* rg = regs;
+    // loader role of this lane: chunk column q of lines L0 + r (r = 0..7); tile slot of (chunk q, line) is
+    // q * 512 + ((line ^ q) << 4): the XOR keeps the 8 writers of a line and the 32 readers of a row on distinct banks
+    const uint32_t ld_q = lane & 7, ld_L0 = (lane >> 3) * 8;
+    const uint32_t ld_info = info_abs + ld_L0 * 8;
+    const uint32_t ld_dst = tile_abs + (ld_q << 9) + (ld_L0 << 4);
+    const uint32_t rd_lane16 = lane << 4;
     for (;;) {
         unsigned long long batch = 0;
         if (lane == 0)
@@ -1423,87 +1470,66 @@ __global__ void __launch_bounds__(1024, 1)
             break;
         const bool valid = batch + lane < n;
         const uint64_t i = batch + lane;
-        uint32_t off = 0, len = 0, mis = 0, nch = 0, cfirst = 0, g0 = 0;
+        uint32_t off = 0, len = 0, mis = 0, nch = 0, g0 = 0;
         if (valid) {
             off = ev_off[i];
             len = ev_len[i];
-            const uint64_t a = (uint64_t)base_mis + off; // byte offset from gbase128
-            mis = (uint32_t)(a & 127);
-            g0 = (uint32_t)((a - mis) >> 4);
-            nch = (mis + len + 15) >> 4;
-            cfirst = mis >> 4;
+            const uint64_t a = (uint64_t)base_mis + off; // byte offset from gbase16
+            mis = (uint32_t)(a & 15);
+            g0 = (uint32_t)(a >> 4);
+            nch = len ? (mis + len + 15) >> 4 : 0;
             for (uint32_t k = 0; k < G; ++k)
                 reinterpret_cast<uint32_t*>(regs)[k] = 0xFFFFFFFFu; // home registers = LC_SLOT16_UNSET
         }
-        sts_u64(info_abs + lane * 8, g0, nch | (cfirst << 16));
+        sts_u64(info_abs + lane * 8, g0, nch);
         const uint32_t max_nch = __reduce_max_sync(0xFFFFFFFFu, nch);
-        const uint32_t Q = len + mis;
-        const uint32_t qlo = mis + (mis & 1);
-        const uint32_t Qe = Q & ~1u;
-        const uint32_t c_last = (Q & 1) && Q - 1 >= qlo ? (Q - 1) >> 4 : 0xFFFFFFFFu; // chunk of the odd last byte
-        uint16_t* rg = regs;
+        // frame of the line: byte j of the line sits at frame index mis + j; pairs cover the even-aligned [qlo, Qe)
+        const uint32_t Q = len + mis, qlo = mis + (mis & 1), Qe = Q & ~1u;
+        const uint32_t kf_lo = (qlo + 15) >> 4, kf_hi = Qe >> 4; // fully paired chunks: [kf_lo, kf_hi)
+        const uint32_t k_tail = len ? (Q - 1) >> 4 : 0;
+        const bool has_head = len && !(kf_lo == 0 && kf_hi > 0);        // chunk 0 is not fully paired
+        const bool has_tail = len && k_tail >= kf_hi && !(has_head && k_tail == 0);
         uint32_t row = t.t2 + v.h->start * t.row_bytes;
         __syncwarp();
         for (uint32_t s0 = 0; s0 < max_nch; s0 += LCT_STAGE_CHUNKS) {
             // ---- cooperative fetch: instruction r moves chunks s0..s0+7 of lines r, r+8, r+16, r+24
             {
-                const uint32_t q = lane & 7, cidx = s0 + q;
+                const uint32_t cidx = s0 + ld_q;
 #pragma unroll
                 for (uint32_t r = 0; r < 8; ++r) {
-                    const uint32_t line = (lane >> 3) * 8 + r;
-                    const uint2 inf = lds_u64_v(info_abs + line * 8);
-                    const uint32_t l_nch = inf.y & 0xFFFFu, l_first = inf.y >> 16;
-                    if (cidx >= l_first && cidx < l_nch)
-                        cp_async_16(tile_abs + ((q * 32 + ((line + q) & 31)) << 4), gbase128 + inf.x + cidx);
+                    const uint2 inf = lds_u64_v(ld_info + r * 8);
+                    if (cidx < inf.y)
+                        cp_async_16(ld_dst + (((r ^ ld_q)) << 4), gbase16 + inf.x + cidx);
                 }
                 cp_async_wait_all();
             }
             __syncwarp();
             // ---- every lane walks its own line through the tile
-            if (valid && row != dead) {
-                for (uint32_t q = 0; q < LCT_STAGE_CHUNKS; ++q) {
-                    const uint32_t qc = s0 + q;
-                    if (qc < cfirst || qc >= nch)
-                        continue;
-                    const uint32_t caddr = tile_abs + ((q * 32 + ((lane + q) & 31)) << 4);
-                    const uint32_t lo = qc * 16;
-                    if (qc == cfirst && (mis & 1) && len) { // odd first byte: single step from the start state
-                        const uint32_t st1 = lc_tdfa_single(v, v.h->start, lds_u8_v(caddr + (mis & 15)), 0, rg);
-                        row = t.t2 + st1 * t.row_bytes;
-                    }
-                    if (Qe > qlo && lo < Qe && lo + 16 > qlo) {
-                        const uint4 vv = lds_u128_v(caddr);
-                        const uint32_t row_in = row;
-                        const uint32_t pos0 = lo - mis;
-                        if (lo >= qlo && lo + 16 <= Qe) {
-                            LCS_PAIR(vv.x, 0, pos0 + 0)
-                            LCS_PAIR(vv.x, 1, pos0 + 2)
-                            LCS_PAIR(vv.y, 0, pos0 + 4)
-                            LCS_PAIR(vv.y, 1, pos0 + 6)
-                            LCS_PAIR(vv.z, 0, pos0 + 8)
-                            LCS_PAIR(vv.z, 1, pos0 + 10)
-                            LCS_PAIR(vv.w, 0, pos0 + 12)
-                            LCS_PAIR(vv.w, 1, pos0 + 14)
-                        } else {
-                            const uint32_t wd[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-                            for (int pi = 0; pi < 8; ++pi) {
-                                const uint32_t qq = lo + 2 * pi;
-                                if (qq >= qlo && qq < Qe)
-                                    LCS_PAIR(wd[pi >> 1], pi & 1, qq - mis)
-                            }
-                        }
-                        if (SLOW && row == sink) // some step set several registers: redo this chunk step by step
-                            row = t.t2 + t.row_bytes * tdfa_chunk_slow(v, __umulhi(row_in - t.t2, t.inv_row), vv, lo,
-                                                                       mis, qlo, Qe, rg);
-                    }
-                    if (qc == c_last) { // odd last byte
-                        const uint32_t st1 = lc_tdfa_single(v, __umulhi(row - t.t2, t.inv_row),
-                                                            lds_u8_v(caddr + ((Q - 1) & 15)), len - 1, rg);
-                        row = t.t2 + st1 * t.row_bytes;
-                    }
-                    if (row == dead)
-                        break;
+            if (row != dead) {
+                if (has_head && s0 == 0)
+                    row = tdfa_partial_chunk(v, t, row, tile_abs + rd_lane16, 0, mis, len, regs_m2, rg, sink);
+                const uint32_t ka = kf_lo > s0 ? kf_lo : s0;
+                const uint32_t kb = kf_hi < s0 + LCT_STAGE_CHUNKS ? kf_hi : s0 + LCT_STAGE_CHUNKS;
+                for (uint32_t k = ka; k < kb; ++k) {
+                    const uint32_t q = k & 7;
+                    const uint4 vv = lds_u128_v(tile_abs + (q << 9) + (rd_lane16 ^ (q << 4)));
+                    const uint32_t pos0 = k * 16 - mis;
+                    const uint32_t row_in = row;
+                    LCS_PAIR(vv.x, 0, pos0 + 0)
+                    LCS_PAIR(vv.x, 1, pos0 + 2)
+                    LCS_PAIR(vv.y, 0, pos0 + 4)
+                    LCS_PAIR(vv.y, 1, pos0 + 6)
+                    LCS_PAIR(vv.z, 0, pos0 + 8)
+                    LCS_PAIR(vv.z, 1, pos0 + 10)
+                    LCS_PAIR(vv.w, 0, pos0 + 12)
+                    LCS_PAIR(vv.w, 1, pos0 + 14)
+                    if (SLOW && row == sink) // some step set several registers: redo this chunk step by step
+                        row = t.t2 + t.row_bytes * tdfa_chunk_slow(v, __umulhi(row_in - t.t2, t.inv_row), vv, pos0, rg);
+                }
+                if (has_tail && k_tail - s0 < LCT_STAGE_CHUNKS) {
+                    const uint32_t q = k_tail & 7;
+                    row = tdfa_partial_chunk(v, t, row, tile_abs + (q << 9) + (rd_lane16 ^ (q << 4)), k_tail * 16, mis,
+                                             len, regs_m2, rg, sink);
                 }
             }
             __syncwarp();
@@ -1522,33 +1548,30 @@ __global__ void __launch_bounds__(1024, 1)
         if (bool_only || G == 0)
             continue;
         // coalesced result rows: element j of the batch's [32][G] tables is produced by lane j % 32 straight from
-        // the owning line's register file (one 32-bit LDS = begin | end << 16)
+        // the owning line's register file (one 32-bit LDS = begin | end << 16); the line's (off, len) travel
+        // through the info slots
+        sts_u64(info_abs + lane * 8, off, st == 0 ? len : 0xFFFFFFFFu);
         __syncwarp();
         const uint64_t left = n - batch;
         const uint32_t total = (uint32_t)(left < 32 ? left : 32) * G;
         uint32_t* go = cap_off + batch * G;
         uint32_t* gl = cap_len + batch * G;
-        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            const uint32_t line = j < total ? j / G : 0, g = j - line * G;
-            const uint32_t l_off = __shfl_sync(0xFFFFFFFFu, off, line);
-            const uint32_t l_len = __shfl_sync(0xFFFFFFFFu, len, line);
-            const uint32_t l_st = __shfl_sync(0xFFFFFFFFu, st, line);
-            if (j < total) {
-                uint32_t o = 0, l = 0;
-                if (l_st == 0) {
-                    const uint32_t be = reinterpret_cast<const volatile uint32_t*>(wregs + (size_t)line * reg_pitch)[g];
-                    const uint32_t b = be & 0xFFFFu, en = be >> 16;
-                    if (b == LC_SLOT16_UNSET || en == LC_SLOT16_UNSET || en < b) {
-                        o = l_off + l_len;
-                    } else {
-                        o = l_off + b;
-                        l = en - b;
-                    }
+        for (uint32_t j = lane; j < total; j += 32) {
+            const uint32_t line = G == 1 ? j : __umulhi(j, invG), g = j - line * G; // (2^32 / 1 does not fit invG)
+            const uint2 inf = lds_u64_v(info_abs + line * 8);
+            uint32_t o = 0, l = 0;
+            if (inf.y != 0xFFFFFFFFu) {
+                const uint32_t be = lds_u32_v(wregs_abs + line * reg_pitch * 2 + g * 4);
+                const uint32_t b = be & 0xFFFFu, en = be >> 16;
+                if (b == LC_SLOT16_UNSET || en == LC_SLOT16_UNSET || en < b) {
+                    o = inf.x + inf.y;
+                } else {
+                    o = inf.x + b;
+                    l = en - b;
                 }
-                go[j] = o;
-                gl[j] = l;
             }
+            go[j] = o;
+            gl[j] = l;
         }
         __syncwarp();
     }
