@@ -1340,6 +1340,9 @@ struct TdfaAbs {
     uint32_t inv_row;   // ceil(2^32 / row_bytes): state = umulhi(row - t2, inv_row)
 };
 
+// (Tried and measured slower on C2: a power-of-two row pitch with the address formed as row | index * 4 -- the same
+// class pair of different states then always shares a bank; and storing both boundary fields under one predicate --
+// two instructions fewer per pair but more shared-memory wavefronts.)
 #define LCS_PAIR(X, HI, POS)                                                                                           \
     {                                                                                                                  \
         const uint32_t c0 = lds_u8(__byte_perm((X), t.cls, (HI) ? 0x7652 : 0x7650));                                   \
@@ -1403,6 +1406,9 @@ __device__ __noinline__ uint32_t tdfa_partial_chunk(const LcTdfaView v, const Td
     return row;
 }
 
+// (Tile fill alternatives measured on C2 and dropped: cp.async.ca instead of .cg -2 %; LDG.128 into registers followed
+// by STS.128 -- 8x fewer shared-memory wavefronts than LDGSTS, which writes one 16-byte wavefront per lane -- but
+// -10 %: the loads stall the issuing warp and the extra live registers spill under the 64-register cap.)
 template <bool SLOW>
 __global__ void __launch_bounds__(1024, 1)
     regex_tdfa_staged_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, const uint8_t* __restrict__ base,
@@ -1411,7 +1417,8 @@ __global__ void __launch_bounds__(1024, 1)
                              uint32_t* __restrict__ cap_len, uint32_t reg_pitch /* halfwords */,
                              unsigned long long* next_batch) {
     extern __shared__ uint4 smem[];
-    // carve-out: [pad][cls 256 B @ 256-aligned][blob][register files][line info: warps x 32 x 8 B][tiles: warps x 4 KB]
+    // carve-out: [pad][class table, 256 B @ 256-aligned][blob][16 B][register files][line info: warps x 32 x 8 B]
+    // [tiles: warps x 4 KB]
     const uint32_t s0abs = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t cls_abs = (s0abs + 255u) & ~255u;
     uint8_t* g_cls = reinterpret_cast<uint8_t*>(smem) + (cls_abs - s0abs);
@@ -1422,18 +1429,17 @@ __global__ void __launch_bounds__(1024, 1)
     const LcTdfaView v = lc_tdfa_view(g_blob);
     TdfaAbs t;
     t.cls = cls_abs;
-    asm volatile("" : "+r"(t.cls)); // keep it in a vector register: PRMT then takes the selector as an immediate
     t.t2 = cls_abs + 256 + v.h->off_t2;
     t.ncls = v.h->ncls;
     t.row_bytes = v.h->row_bytes;
     t.inv_row = (uint32_t)((0x100000000ull + t.row_bytes - 1) / t.row_bytes);
     if (t.t2 + (v.h->nstates + 1) * t.row_bytes > 65535u)
         __trap(); // rows could not be addressed with 16 bits: the host must not select this kernel
-    for (uint32_t k = threadIdx.x; k < 64; k += blockDim.x)
-        reinterpret_cast<uint32_t*>(g_cls)[k] = reinterpret_cast<const uint32_t*>(v.cls)[k];
+    for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x)
+        g_cls[k] = v.cls[k];
     {
         uint32_t* t2w = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(g_blob) + v.h->off_t2);
-        const uint32_t nent = (v.h->nstates + 1) * t.ncls * t.ncls;
+        const uint32_t nent = (v.h->nstates + 1) * (t.row_bytes / 4);
         for (uint32_t k = threadIdx.x; k < nent; k += blockDim.x)
             t2w[k] += t.t2; // rebase: low 16 bits = absolute shared address of the next row
     }
@@ -1441,15 +1447,18 @@ __global__ void __launch_bounds__(1024, 1)
     const uint32_t G = v.h->ngroups;
     const uint32_t invG = G ? 0xFFFFFFFFu / G + 1 : 0; // umulhi(j, invG) == j / G for j < 65536
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    uint8_t* g_regs0 = reinterpret_cast<uint8_t*>(g_blob) + blob_bytes;
+    uint8_t* g_regs0 = reinterpret_cast<uint8_t*>(g_blob) + blob_bytes + 16; // (+16: no-op slot of the first thread)
     uint16_t* wregs = reinterpret_cast<uint16_t*>(g_regs0) + (size_t)wid * 32 * reg_pitch;
     uint16_t* regs = wregs + (size_t)lane * reg_pitch;
-    const uint32_t wregs_abs = (uint32_t)__cvta_generic_to_shared(wregs);
     const uint32_t regs_abs = (uint32_t)__cvta_generic_to_shared(regs);
     const uint32_t regs_m2 = regs_abs - 2;
     const uint32_t aux_abs = (uint32_t)__cvta_generic_to_shared(g_regs0 + (size_t)blockDim.x * reg_pitch * 2);
     const uint32_t info_abs = aux_abs + wid * 256;
     const uint32_t tile_abs = aux_abs + nwarps * 256 + wid * (LCT_STAGE_CHUNKS * 512);
+    // bounce the class-table address through shared memory so that it lives in a per-thread register: with a
+    // uniform-register operand PRMT cannot take its selector as an immediate (one extra MOV per look-up)
+    sts_u64(info_abs + lane * 8, cls_abs, 0);
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t.cls) : "r"(info_abs + lane * 8) : "memory");
     const uint4* gbase16 = reinterpret_cast<const uint4*>((uintptr_t)base & ~(uintptr_t)15);
     const uint32_t base_mis = (uint32_t)((uintptr_t)base & 15);
     const bool bool_only = cap_off == nullptr;
@@ -1499,7 +1508,7 @@ __global__ void __launch_bounds__(1024, 1)
                 for (uint32_t r = 0; r < 8; ++r) {
                     const uint2 inf = lds_u64_v(ld_info + r * 8);
                     if (cidx < inf.y)
-                        cp_async_16(ld_dst + (((r ^ ld_q)) << 4), gbase16 + inf.x + cidx);
+                        cp_async_16(ld_dst + ((r ^ ld_q) << 4), gbase16 + inf.x + cidx);
                 }
                 cp_async_wait_all();
             }
@@ -1554,14 +1563,15 @@ __global__ void __launch_bounds__(1024, 1)
         __syncwarp();
         const uint64_t left = n - batch;
         const uint32_t total = (uint32_t)(left < 32 ? left : 32) * G;
-        uint32_t* go = cap_off + batch * G;
-        uint32_t* gl = cap_len + batch * G;
-        for (uint32_t j = lane; j < total; j += 32) {
+        uint32_t* go = cap_off + batch * G + lane;
+        uint32_t* gl = cap_len + batch * G + lane;
+        const uint32_t wbase = regs_m2 + 2 - lane * reg_pitch * 2; // register file of the warp's line 0
+        for (uint32_t j = lane; j < total; j += 32, go += 32, gl += 32) {
             const uint32_t line = G == 1 ? j : __umulhi(j, invG), g = j - line * G; // (2^32 / 1 does not fit invG)
             const uint2 inf = lds_u64_v(info_abs + line * 8);
             uint32_t o = 0, l = 0;
             if (inf.y != 0xFFFFFFFFu) {
-                const uint32_t be = lds_u32_v(wregs_abs + line * reg_pitch * 2 + g * 4);
+                const uint32_t be = lds_u32_v(wbase + line * reg_pitch * 2 + g * 4);
                 const uint32_t b = be & 0xFFFFu, en = be >> 16;
                 if (b == LC_SLOT16_UNSET || en == LC_SLOT16_UNSET || en < b) {
                     o = inf.x + inf.y;
@@ -1570,8 +1580,8 @@ __global__ void __launch_bounds__(1024, 1)
                     l = en - b;
                 }
             }
-            go[j] = o;
-            gl[j] = l;
+            *go = o;
+            *gl = l;
         }
         __syncwarp();
     }

@@ -95,7 +95,8 @@ int launch_regex_tdfa(const void* d_blob, uint32_t blob_bytes, bool slow, uint32
 // staged variant: lines are fetched cooperatively (cp.async, 4 full 128-byte lines per instruction) into a per-warp
 // 4 KB tile; carve-out = 512 B (aligned class table) + blob + register files + 256 B line info and 4 KB tile per warp
 inline size_t tdfa_staged_smem_bytes(uint32_t blob_bytes, uint32_t nregs, uint32_t threads) {
-    return 512 + (size_t)blob_bytes + (size_t)threads * tdfa_reg_pitch(nregs) * 2 + (size_t)(threads / 32) * (256 + 4096);
+    return 512 + (size_t)blob_bytes + 16 + (size_t)threads * tdfa_reg_pitch(nregs) * 2 +
+           (size_t)(threads / 32) * (256 + 4096);
 }
 int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow, uint32_t nregs, const uint8_t* d_base,
                              const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,

@@ -157,8 +157,9 @@ struct LcFast2Header {
 // action moves the winner's values to the home registers.  No reverse pass, no labels: half the look-ups of the
 // two-pass layouts and a per-line footprint of just the register file.
 //   cls   u8  [256]                byte -> class
-//   t2    u32 [nstates][ncls*ncls] pair step over bytes (b0 = earlier, b1 = later), indexed (c0 * ncls + c1):
-//                                  bits 0..15 = next_state * row_bytes (row_bytes = ncls*ncls*4; state 0 = dead),
+//   t2    u32 [nstates+1][row_bytes/4] pair step over bytes (b0 = earlier, b1 = later), indexed (c0 * ncls + c1):
+//                                  bits 0..15 = next_state * row_bytes (row_bytes = (ncls*ncls | 1) * 4: an odd word
+//                                  pitch spreads the states over the shared-memory banks; state 0 = dead),
 //                                  bits 16..22 = register set by the 1st step at position p   (2*reg + 2, 0 = none),
 //                                  bit  23     = slow path (some step sets more than one register): such entries
 //                                                lead to the absorbing SINK row (index nstates) instead of the real
@@ -173,7 +174,7 @@ struct LcFast2Header {
 #define LC_TDFA_SRC_POS 0xFFu
 #define LC_TDFA_SRC_UNSET 0xFEu
 #define LC_TDFA_MAX_REGS 62u
-#define LC_TDFA_REBASE_ROOM 4096u /* t2 must start below this shared-memory address (header + cls + carve-out) */
+#define LC_TDFA_REBASE_ROOM 2048u /* window base + class table + blob header precede the (row-aligned) pair table */
 struct LcTdfaHeader {
     uint32_t magic;
     uint32_t total_bytes;

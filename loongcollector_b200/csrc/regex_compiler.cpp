@@ -1640,13 +1640,19 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
         [&]() {
             const uint32_t ncl = (uint32_t)nclasses;
             const uint32_t T = 2 * res.ngroups;
-            const uint64_t row_bytes = (uint64_t)ncl * ncl * 4;
+            // NB: the row pitch is deliberately NOT rounded to a power of two (measured: with 512-byte rows the same
+            // class pair of different states always shares a bank and the look-ups conflict; -4 % on C2)
+            // Instead the pitch is an ODD number of words, so that the same class pair of different states falls
+            // into different banks.
+            const uint64_t row_bytes = (uint64_t)((ncl * ncl) | 1u) * 4;
             if (T > LC_TDFA_MAX_REGS || row_bytes > 16384)
                 return;
             // next_state * row_bytes must fit 16 bits even after the kernel rebases the rows to absolute
-            // shared-memory addresses (the tables sit within the first LC_TDFA_REBASE_ROOM bytes of the window)
-            // (one row is reserved for the slow-path sink)
-            const size_t max_states = (size_t)((65535 - LC_TDFA_REBASE_ROOM) / row_bytes) - 1;
+            // shared-memory addresses: the pair table starts on a row_bytes boundary within the first
+            // LC_TDFA_REBASE_ROOM + row_bytes bytes of the window, and one more row is the slow-path sink
+            if ((65535 - LC_TDFA_REBASE_ROOM) / row_bytes < 4)
+                return;
+            const size_t max_states = (size_t)((65535 - LC_TDFA_REBASE_ROOM) / row_bytes) - 2;
             struct TThread {
                 int w;
                 std::vector<int16_t> reg; // tag -> register, -1 = unset
@@ -1833,9 +1839,10 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
             // row ns = the slow-path sink: entries whose steps set several registers lead there and it absorbs
             // every byte pair, so a kernel can test for it once per 16-byte chunk and redo that chunk step by step
             th.sink = ns;
-            std::vector<uint32_t> t2((size_t)(ns + 1) * ncl * ncl, 0);
+            const size_t rw = (size_t)row_bytes / 4; // words per row
+            std::vector<uint32_t> t2((size_t)(ns + 1) * rw, 0);
             for (uint32_t k = 0; k < ncl * ncl; ++k)
-                t2[(size_t)ns * ncl * ncl + k] = ns * (uint32_t)row_bytes | LC_TDFA_SLOW;
+                t2[(size_t)ns * rw + k] = ns * (uint32_t)row_bytes | LC_TDFA_SLOW;
             for (uint32_t s = 1; s < ns; ++s)
                 for (uint32_t c0 = 0; c0 < ncl; ++c0) {
                     uint32_t s1 = t1[(size_t)s * ncl + c0] & 0xFFFFu;
@@ -1857,7 +1864,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                             if (!B.empty())
                                 e |= (2u * B[0] + 2u) << 24;
                         }
-                        t2[((size_t)s * ncl + c0) * ncl + c1] = e;
+                        t2[(size_t)s * rw + c0 * ncl + c1] = e;
                     }
                 }
             std::vector<uint8_t> cls(byte_class, byte_class + 256);

@@ -115,3 +115,13 @@ int emul_full_match(const EmulRegex* e, const uint8_t* s, uint32_t n, uint32_t* 
     return 1;
 }
 }
+
+extern "C" {
+// copies the tdfa blob (diagnostics / table inspection in tests); returns its size
+uint32_t emul_tdfa_blob(const EmulRegex* e, uint8_t* out, uint32_t cap) {
+    uint32_t n = (uint32_t)e->r.tdfa_blob.size();
+    if (out && cap >= n)
+        memcpy(out, e->r.tdfa_blob.data(), n);
+    return n;
+}
+}
