@@ -465,7 +465,7 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
         while (warps > 4 && smem_need(warps) > smem_max)
             warps -= 2;
         bool usable = smem_need(warps) <= smem_max;
-        if (usable && base_len >= 65535) { // capture registers are 16-bit: every event must be < 65535 bytes
+        if (usable && !staged && base_len >= 65535) { // capture registers are 16-bit: every event must be < 65535 bytes
             CU_TRY(cudaMemsetAsync(ds->counters, 0, sizeof ds->counters, e->stream));
             lck::launch_len_stats(d_ev_len, n, ds->counters, e->stream);
             e->launches++;
@@ -486,7 +486,7 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
                 er = lck::launch_regex_tdfa_staged(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off,
                                                    d_ev_len, n, nkeys, d_status, bool_only ? nullptr : d_cap_off,
                                                    bool_only ? nullptr : d_cap_len, threads, grid, &ds->next_batch,
-                                                   e->stream);
+                                                   &ds->overflow, e->stream);
             else
                 er = lck::launch_regex_tdfa(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off, d_ev_len, n,
                                             nkeys, d_status, bool_only ? nullptr : d_cap_off,
@@ -495,7 +495,14 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
             e->launches++;
             if (er)
                 return fail(LC_ERR_CUDA, std::string("regex kernel launch: ") + cudaGetErrorString((cudaError_t)er));
-            return LC_OK;
+            if (!staged || base_len < 65535)
+                return LC_OK;
+            // the kernel itself reports events too long for its 16-bit capture registers (no length pre-pass)
+            CU_TRY(cudaMemcpyAsync(&hs->overflow, &ds->overflow, 4, cudaMemcpyDeviceToHost, e->stream));
+            CU_TRY(cudaStreamSynchronize(e->stream));
+            if (!hs->overflow)
+                return LC_OK;
+            // fall through: redo the whole call on a kernel with 32-bit slots
         }
     }
     if (!force_basic) {

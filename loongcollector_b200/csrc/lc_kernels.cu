@@ -1415,7 +1415,7 @@ __global__ void __launch_bounds__(1024, 1)
                              const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
                              uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
                              uint32_t* __restrict__ cap_len, uint32_t reg_pitch /* halfwords */,
-                             unsigned long long* next_batch) {
+                             unsigned long long* next_batch, uint32_t* overflow) {
     extern __shared__ uint4 smem[];
     // carve-out: [pad][class table, 256 B @ 256-aligned][blob][16 B][register files][line info: warps x 32 x 8 B]
     // [tiles: warps x 4 KB]
@@ -1483,6 +1483,10 @@ __global__ void __launch_bounds__(1024, 1)
         if (valid) {
             off = ev_off[i];
             len = ev_len[i];
+            if (len >= 65535u) { // capture registers are 16-bit: tell the host to redo the call with 32-bit slots
+                atomicExch(overflow, 1u);
+                len = 0;
+            }
             const uint64_t a = (uint64_t)base_mis + off; // byte offset from gbase16
             mis = (uint32_t)(a & 15);
             g0 = (uint32_t)(a >> 4);
@@ -1590,7 +1594,7 @@ __global__ void __launch_bounds__(1024, 1)
 int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow, uint32_t nregs, const uint8_t* d_base,
                              const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
                              uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t threads,
-                             uint32_t grid, unsigned long long* d_next_batch, cudaStream_t st) {
+                             uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow, cudaStream_t st) {
     if (!n)
         return 0;
     const uint32_t reg_pitch = tdfa_reg_pitch(nregs);
@@ -1600,7 +1604,7 @@ int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow,
     if (er != cudaSuccess)
         return (int)er;
     k<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
-                                   d_cap_off, d_cap_len, reg_pitch, d_next_batch);
+                                   d_cap_off, d_cap_len, reg_pitch, d_next_batch, d_overflow);
     return (int)cudaGetLastError();
 }
 

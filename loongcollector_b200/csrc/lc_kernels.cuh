@@ -82,7 +82,8 @@ int launch_regex_fast2(const void* d_blob, uint32_t blob_bytes, bool multi, bool
                        const uint32_t* d_order, cudaStream_t st);
 
 // a3 single-pass tagged-DFA path (LcTdfaHeader): no labels; per thread only nregs u16 registers in shared memory.
-// Only valid when every event is shorter than 65535 bytes.
+// Only valid when every event is shorter than 65535 bytes (the staged kernel raises *d_overflow otherwise and the
+// host repeats the call on a kernel with 32-bit slots; the direct kernel relies on a host-side length check).
 inline uint32_t tdfa_reg_pitch(uint32_t nregs) { return (((nregs + 1) / 2) | 1u) * 2; } // halfwords; odd WORD pitch
 inline size_t tdfa_smem_bytes(uint32_t blob_bytes, uint32_t nregs, uint32_t threads) {
     return (size_t)blob_bytes + (size_t)threads * tdfa_reg_pitch(nregs) * 2;
@@ -101,7 +102,7 @@ inline size_t tdfa_staged_smem_bytes(uint32_t blob_bytes, uint32_t nregs, uint32
 int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow, uint32_t nregs, const uint8_t* d_base,
                              const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
                              uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t threads,
-                             uint32_t grid, unsigned long long* d_next_batch, cudaStream_t st);
+                             uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow, cudaStream_t st);
 
 // parse status -> boolean (1 = the whole value matched)
 void launch_status_to_bool(uint8_t* d_status, uint64_t n, cudaStream_t st);
