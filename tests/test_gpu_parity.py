@@ -309,7 +309,7 @@ def test_delim_matches_oracle(eng, sep, quote, extend, allow_short):
 
 
 # ------------------------------------------------------------------------------------------- kernel variants
-@pytest.mark.parametrize("variant", ["basic", "generic", "fast", "fast2", "tdfa"])
+@pytest.mark.parametrize("variant", ["basic", "generic", "fast", "fast2", "tdfa", "tdfa_direct"])
 def test_regex_kernel_variants_agree(variant, monkeypatch):
     """The baseline (tables in global memory) and generic (smem interpreter) kernels stay parity-checked too."""
     lc = _lc()
