@@ -242,6 +242,7 @@ public:
     void SetMetadata(EventGroupMetaKey key, const std::string& val);
     StringView GetMetadata(EventGroupMetaKey key) const;
     bool HasMetadata(EventGroupMetaKey key) const { return mMetadata.count(key) != 0; }
+    void DelMetadata(EventGroupMetaKey key) { mMetadata.erase(key); }
     const GroupMetadata& GetAllMetadata() const { return mMetadata; }
     void SetTag(const std::string& key, const std::string& val);
 

@@ -929,7 +929,304 @@ void ProcessorFilterNative::Process(PipelineEventGroup& group) {
     events.resize(wIdx);
 }
 
+// ------------------------------------------------------------------------------------------------ merge multiline
+const std::string ProcessorMergeMultilineLogNative::sName = "processor_merge_multiline_log_native";
+const std::string ProcessorMergeMultilineLogNative::PartLogFlag = "P";
+
+bool ProcessorMergeMultilineLogNative::Init(const Json::Value& config) {
+    GetString(config, "SourceKey", mSourceKey);
+    std::string mergeType;
+    if (!GetString(config, "MergeType", mergeType))
+        return Fail("mandatory string param MergeType is missing");
+    if (mergeType == "flag") {
+        mMergeType = MergeType::BY_FLAG;
+        return true;
+    }
+    if (mergeType != "regex")
+        return Fail("string param MergeType is not valid");
+    std::string err;
+    if (!mMultiline.Init(config, err))
+        return Fail(err);
+    struct {
+        const std::string* pattern;
+        CompiledRegex* reg;
+        bool* has;
+    } regs[] = {{&mMultiline.mStartPattern, &mStartReg, &mHasStart},
+                {&mMultiline.mContinuePattern, &mContinueReg, &mHasContinue},
+                {&mMultiline.mEndPattern, &mEndReg, &mHasEnd}};
+    for (auto& r : regs) {
+        std::string p = *r.pattern;
+        if (!p.empty() && EndsWith(p, "$"))
+            p.pop_back();
+        while (!p.empty() && EndsWith(p, ".*"))
+            p.resize(p.size() - 2);
+        if (p.empty())
+            continue;
+        if (!r.reg->Compile(p, err))
+            return Fail("multiline pattern: " + err); // outside the automaton subset: never approximated
+        *r.has = true;
+    }
+    if (!mHasStart && !mHasEnd && mHasContinue)
+        mHasContinue = false;
+    else if (mHasStart && mHasContinue && mHasEnd)
+        mHasContinue = false;
+    return true;
+}
+
+std::vector<std::pair<std::string, uint64_t>> ProcessorMergeMultilineLogNative::Counters() const {
+    return {{"merged_events_total", mMergedEventsTotal.GetValue()},
+            {"unmatched_events_total", mUnmatchedEventsTotal.GetValue()}};
+}
+
+void ProcessorMergeMultilineLogNative::Process(PipelineEventGroup& group) {
+    if (group.GetEvents().empty())
+        return;
+    if (mMergeType == MergeType::BY_REGEX) {
+        MergeLogsByRegex(group);
+    } else if (group.HasMetadata(EventGroupMetaKey::HAS_PART_LOG)) {
+        MergeLogsByFlag(group);
+        group.DelMetadata(EventGroupMetaKey::HAS_PART_LOG);
+    }
+}
+
+// :320-346.  The reference joins the values IN PLACE (it writes the line break over the byte that follows the target
+// value and memmoves the next values down); that is only sound when the values lie in event order inside one
+// arena chunk with nothing else in between, which is what the splitters produce.  Same here when that holds (values
+// adjacent, at most one separator byte apart), else the joined value is built in a fresh arena allocation -- the
+// resulting content is identical.
+void ProcessorMergeMultilineLogNative::MergeEvents(PipelineEventGroup& group, std::vector<LogEvent*>& logEvents,
+                                                   bool insertLineBreak) {
+    if (logEvents.empty())
+        return;
+    mMergedEventsTotal.Add(logEvents.size());
+    if (logEvents.size() == 1) {
+        logEvents.clear();
+        return;
+    }
+    LogEvent* target = logEvents[0];
+    StringView targetValue = target->GetContent(mSourceKey);
+    size_t total = targetValue.size();
+    bool inPlace = true;
+    const char* end = targetValue.data() + targetValue.size();
+    for (size_t i = 1; i < logEvents.size(); ++i) {
+        StringView cur = logEvents[i]->GetContent(mSourceKey);
+        total += cur.size() + (insertLineBreak ? 1 : 0);
+        const char* dst = end + (insertLineBreak ? 1 : 0);
+        // adjacent values only (at most the one separator byte the splitter left between them): anything else
+        // in the gap -- e.g. another content of the target event -- must not be overwritten
+        if (cur.data() < dst || cur.data() > end + 1)
+            inPlace = false;
+        end = dst + cur.size();
+    }
+    size_t chunkSize = 0;
+    SourceBuffer& sb = *group.GetSourceBuffer();
+    if (inPlace && !sb.ChunkContaining(targetValue.data(), total, &chunkSize))
+        inPlace = false;
+    char* begin;
+    if (inPlace) {
+        begin = const_cast<char*>(targetValue.data());
+    } else {
+        StringBuffer b = sb.AllocateStringBuffer(total);
+        begin = b.data;
+        memcpy(begin, targetValue.data(), targetValue.size());
+    }
+    char* w = begin + targetValue.size();
+    for (size_t i = 1; i < logEvents.size(); ++i) {
+        if (insertLineBreak)
+            *w++ = '\n';
+        StringView cur = logEvents[i]->GetContent(mSourceKey);
+        memmove(w, cur.data(), cur.size());
+        w += cur.size();
+    }
+    // the key view must outlive the call: reuse the stored key of the target's content
+    StringView key;
+    for (auto& c : target->RawContents())
+        if (c.second && c.first.first == StringView(mSourceKey))
+            key = c.first.first;
+    target->SetContentNoCopy(key, StringView(begin, (size_t)(w - begin)));
+    logEvents.clear();
+}
+
+// :348-385 (alarms / log lines are not produced by this engine)
+void ProcessorMergeMultilineLogNative::HandleUnmatchLogs(EventsContainer& logEvents, size_t& newSize, size_t begin,
+                                                         size_t end) {
+    mUnmatchedEventsTotal.Add(end - begin + 1);
+    if (mMultiline.mUnmatchedContentTreatment == MultilineOptions::UnmatchedContentTreatment::DISCARD)
+        return;
+    for (size_t i = begin; i <= end; ++i)
+        logEvents[newSize++] = std::move(logEvents[i]);
+}
+
+// :116-159
+void ProcessorMergeMultilineLogNative::MergeLogsByFlag(PipelineEventGroup& group) {
+    EventsContainer& sourceEvents = group.MutableEvents();
+    size_t size = 0, begin = 0;
+    std::vector<LogEvent*> events;
+    bool isPartialLog = false;
+    for (size_t cur = 0; cur < sourceEvents.size(); ++cur) {
+        if (!IsSupportedEvent(sourceEvents[cur])) {
+            if (events.empty())
+                begin = cur;
+            for (size_t i = begin; i < sourceEvents.size(); ++i)
+                sourceEvents[size++] = std::move(sourceEvents[i]);
+            sourceEvents.resize(size);
+            return;
+        }
+        LogEvent* sourceEvent = &sourceEvents[cur].Cast<LogEvent>();
+        if (sourceEvent->Empty())
+            continue;
+        events.emplace_back(sourceEvent);
+        if (isPartialLog) {
+            if (!sourceEvent->HasContent(PartLogFlag)) {
+                MergeEvents(group, events, false);
+                sourceEvents[size++] = std::move(sourceEvents[begin]);
+                begin = cur + 1;
+                isPartialLog = false;
+            }
+        } else if (sourceEvent->HasContent(PartLogFlag)) {
+            sourceEvent->DelContent(PartLogFlag);
+            isPartialLog = true;
+        } else {
+            MergeEvents(group, events, false);
+            sourceEvents[size++] = std::move(sourceEvents[begin]);
+            begin = cur + 1;
+        }
+    }
+    if (isPartialLog) {
+        MergeEvents(group, events, false);
+        sourceEvents[size++] = std::move(sourceEvents[begin]);
+    }
+    sourceEvents.resize(size);
+}
+
+// :161-318.  BoostRegexSearch(match_continuous) of every (event, pattern) pair is a pure function of the value, so all
+// probes are evaluated up front on the GPU and the walk below only reads flags.
+void ProcessorMergeMultilineLogNative::MergeLogsByRegex(PipelineEventGroup& group) {
+    EventsContainer& sourceEvents = group.MutableEvents();
+    const size_t ne = sourceEvents.size();
+    std::vector<uint8_t> mS(ne, 0), mC(ne, 0), mE(ne, 0);
+    {
+        FlatBatch batch;
+        for (size_t i = 0; i < ne; ++i) {
+            if (!IsSupportedEvent(sourceEvents[i]))
+                break; // the walk stops at the first unsupported event
+            const LogEvent& ev = sourceEvents[i].Cast<LogEvent>();
+            if (ev.Empty())
+                continue;
+            if (!ev.HasContent(mSourceKey))
+                break;
+            batch.Add(i, ev.GetContent(mSourceKey));
+        }
+        batch.Finish(*group.GetSourceBuffer());
+        const size_t nb = batch.eventIndex.size();
+        struct {
+            bool has;
+            CompiledRegex* reg;
+            std::vector<uint8_t>* dst;
+        } probes[] = {{mHasStart, &mStartReg, &mS}, {mHasContinue, &mContinueReg, &mC}, {mHasEnd, &mEndReg, &mE}};
+        std::vector<uint8_t> m(nb);
+        for (auto& p : probes) {
+            if (!p.has || !nb)
+                continue;
+            Check(lc_regex_prefix_match(Engine(), p.reg->get(), batch.base, batch.baseLen, batch.off.data(),
+                                        batch.len.data(), nb, m.data()),
+                  "lc_regex_prefix_match");
+            for (size_t b = 0; b < nb; ++b)
+                (*p.dst)[batch.eventIndex[b]] = m[b];
+        }
+    }
+    const bool S = mHasStart, C = mHasContinue, E = mHasEnd;
+    size_t begin = 0, newSize = 0;
+    std::vector<LogEvent*> events;
+    bool isPartialLog = !S && !C && E; // only an end pattern: stick to the partial state
+    for (size_t cur = 0; cur < ne; ++cur) {
+        bool stop = !IsSupportedEvent(sourceEvents[cur]);
+        LogEvent* sourceEvent = stop ? nullptr : &sourceEvents[cur].Cast<LogEvent>();
+        if (!stop && sourceEvent->Empty())
+            continue;
+        if (!stop && !sourceEvent->HasContent(mSourceKey))
+            stop = true;
+        if (stop) {
+            if (events.empty())
+                begin = cur;
+            for (size_t i = begin; i < ne; ++i)
+                sourceEvents[newSize++] = std::move(sourceEvents[i]);
+            sourceEvents.resize(newSize);
+            return;
+        }
+        if (!isPartialLog) {
+            const bool first = S ? mS[cur] : mC[cur];
+            if (first) {
+                events.emplace_back(sourceEvent);
+                begin = cur;
+                isPartialLog = true;
+            } else if (E && !S && C && mE[cur]) {
+                begin = cur; // continue + end: the line matches the end pattern rather than the continue pattern
+                mMergedEventsTotal.Add(1);
+                sourceEvents[newSize++] = std::move(sourceEvents[begin]);
+            } else {
+                HandleUnmatchLogs(sourceEvents, newSize, cur, cur);
+            }
+            continue;
+        }
+        if (C && mC[cur]) {
+            events.emplace_back(sourceEvent);
+            continue;
+        }
+        if (E) {
+            events.emplace_back(sourceEvent);
+            if (C) {
+                if (mE[cur]) {
+                    MergeEvents(group, events, true);
+                    sourceEvents[newSize++] = std::move(sourceEvents[begin]);
+                } else {
+                    HandleUnmatchLogs(sourceEvents, newSize, begin, cur);
+                    events.clear();
+                }
+                isPartialLog = false;
+            } else if (mE[cur]) {
+                MergeEvents(group, events, true);
+                sourceEvents[newSize++] = std::move(sourceEvents[begin]);
+                if (S)
+                    isPartialLog = false;
+                else
+                    begin = cur + 1; // only an end pattern: the next record starts right away
+            }
+        } else if (!C) { // start only
+            if (!mS[cur]) {
+                events.emplace_back(sourceEvent);
+            } else {
+                MergeEvents(group, events, true);
+                sourceEvents[newSize++] = std::move(sourceEvents[begin]);
+                begin = cur;
+                events.emplace_back(sourceEvent);
+            }
+        } else { // start + continue, and the line is not a continuation
+            MergeEvents(group, events, true);
+            sourceEvents[newSize++] = std::move(sourceEvents[begin]);
+            if (!mS[cur]) {
+                HandleUnmatchLogs(sourceEvents, newSize, cur, cur);
+                isPartialLog = false;
+            } else {
+                begin = cur;
+                events.emplace_back(sourceEvent);
+            }
+        }
+    }
+    if (isPartialLog && begin < ne) {
+        if (!E) {
+            MergeEvents(group, events, true);
+            sourceEvents[newSize++] = std::move(sourceEvents[begin]);
+        } else {
+            HandleUnmatchLogs(sourceEvents, newSize, begin, ne - 1);
+        }
+    }
+    sourceEvents.resize(newSize);
+}
+
 Processor* CreateProcessor(const std::string& type) {
+    if (type == ProcessorMergeMultilineLogNative::sName)
+        return new ProcessorMergeMultilineLogNative;
     if (type == ProcessorFilterNative::sName)
         return new ProcessorFilterNative;
     if (type == ProcessorSplitLogStringNative::sName)

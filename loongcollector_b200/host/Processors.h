@@ -197,6 +197,40 @@ private:
     int mRoot = -1;
 };
 
+// Second "next" row: merges already-split LogEvents of a group back into records -- by the docker
+// partial-log flag or by start / continue / end patterns.  The anchored prefix probes of every event are evaluated for
+// the whole group with one batched lc_regex_prefix_match per pattern; the sequential merge walk (which needs the
+// event objects and joins the values in place in the arena) stays on the host.
+// core/plugin/processor/inner/ProcessorMergeMultilineLogNative.cpp:33-420
+class ProcessorMergeMultilineLogNative : public Processor {
+public:
+    enum class MergeType { BY_REGEX, BY_FLAG };
+    static const std::string sName;
+    static const std::string PartLogFlag;
+    const std::string& Name() const override { return sName; }
+    bool Init(const Json::Value& config) override;
+    void Process(PipelineEventGroup& group) override;
+    using Processor::Process;
+    std::vector<std::pair<std::string, uint64_t>> Counters() const override;
+    std::string mSourceKey = "content";
+    MergeType mMergeType = MergeType::BY_REGEX;
+    MultilineOptions mMultiline;
+    Counter mMergedEventsTotal, mUnmatchedEventsTotal;
+
+protected:
+    bool IsSupportedEvent(const PipelineEventPtr& e) const override { return e.Is<LogEvent>(); }
+
+private:
+    void MergeLogsByFlag(PipelineEventGroup& group);
+    void MergeLogsByRegex(PipelineEventGroup& group);
+    void MergeEvents(PipelineEventGroup& group, std::vector<LogEvent*>& logEvents, bool insertLineBreak);
+    void HandleUnmatchLogs(EventsContainer& logEvents, size_t& newSize, size_t begin, size_t end);
+    // the *RegPtr members of MultilineOptions (MultilineOptions.cpp:125-160,196-215): compiled from the pattern
+    // with its trailing '$' / ".*" removed; unset when that is empty or dropped by the combination rules
+    CompiledRegex mStartReg, mContinueReg, mEndReg;
+    bool mHasStart = false, mHasContinue = false, mHasEnd = false;
+};
+
 // Factory by plugin type name (the names the reference registers, PluginRegistry.cpp:183-200).
 Processor* CreateProcessor(const std::string& type);
 

@@ -446,6 +446,26 @@ class MultilineOptions:
         self.is_multiline = has["StartPattern"] or has["EndPattern"]
         t = _last_segment(cfg, "Multiline.UnmatchedContentTreatment", "single_line")
         self.discard = (t == "discard")
+        # The *RegPtr members (used by ProcessorMergeMultilineLogNative): compiled from the TRIMMED pattern
+        # (trailing '$' and '.*' removed, ParseRegex :196-215), null when the trimmed pattern is empty, and the
+        # continue pattern is dropped when it is the only one or when all three are given (:125-160).
+        self.start_reg = self._trim(self.start) if has["StartPattern"] else None
+        self.cont_reg = self._trim(self.cont) if has["ContinuePattern"] else None
+        self.end_reg = self._trim(self.end) if has["EndPattern"] else None
+        if self.start_reg is None and self.end_reg is None and self.cont_reg is not None:
+            self.cont_reg = None
+        elif self.start_reg is not None and self.cont_reg is not None and self.end_reg is not None:
+            self.cont_reg = None
+        self.ignore_warning = bool(cfg.get("IgnoringUnmatchWarning", False))
+
+    @staticmethod
+    def _trim(pattern):
+        p = pattern
+        if p.endswith("$"):
+            p = p[:-1]
+        while p.endswith(".*"):
+            p = p[:-2]
+        return p
 
     @staticmethod
     def _parse_regex(pattern):
@@ -828,8 +848,162 @@ class ProcessorFilterNative:
         return res
 
 
+class ProcessorMergeMultilineLogNative:
+    """SURVEY.md 8(f) rank 2.  core/plugin/processor/inner/ProcessorMergeMultilineLogNative.cpp:33-420:
+    merges already-split LogEvents of a group back into records, by the docker partial-log flag ("P" content,
+    :116-159) or by the start / continue / end patterns (anchored prefix probes, :161-318)."""
+    name = "processor_merge_multiline_log_native"
+    PART_LOG_FLAG = b"P"
+
+    def __init__(self, cfg):
+        self.source_key = _b(cfg.get("SourceKey", "content"))
+        mt = cfg.get("MergeType")
+        if mt == "flag":
+            self.by_flag = True
+            self.opts = None
+        elif mt == "regex":
+            self.by_flag = False
+            self.opts = MultilineOptions(cfg)
+            self.start = Regex(self.opts.start_reg) if self.opts.start_reg is not None else None
+            self.cont = Regex(self.opts.cont_reg) if self.opts.cont_reg is not None else None
+            self.end = Regex(self.opts.end_reg) if self.opts.end_reg is not None else None
+        else:
+            raise ValueError("MergeType")  # Init returns false (:52-74)
+        self.counters = {"merged_events": 0, "unmatched_events": 0}
+
+    def process(self, g: Group):
+        if not g.events:
+            return
+        if not self.by_flag:
+            self._by_regex(g)
+        elif "has.part.log" in g.metadata:
+            self._by_flag(g)
+            del g.metadata["has.part.log"]
+
+    # MergeEvents (:320-346): the target keeps its other contents; values are joined in place
+    def _merge(self, evs, line_break):
+        if not evs:
+            return
+        self.counters["merged_events"] += len(evs)
+        if len(evs) > 1:
+            sep = b"\n" if line_break else b""
+            evs[0].set(self.source_key, sep.join(e.get(self.source_key) for e in evs))
+        evs.clear()
+
+    # HandleUnmatchLogs (:348-385)
+    def _unmatched(self, src, out, begin, end):
+        self.counters["unmatched_events"] += end - begin + 1
+        if self.opts.discard:
+            return
+        out.extend(src[begin:end + 1])
+
+    def _by_flag(self, g: Group):
+        src, out, evs = g.events, [], []
+        partial, begin = False, 0
+        for cur, e in enumerate(src):
+            if e.type != LOG:
+                if not evs:
+                    begin = cur
+                out.extend(src[begin:])
+                g.events = out
+                return
+            if e.size() == 0:
+                continue
+            evs.append(e)
+            if partial:
+                if not e.has(self.PART_LOG_FLAG):
+                    self._merge(evs, False)
+                    out.append(src[begin])
+                    begin = cur + 1
+                    partial = False
+            elif e.has(self.PART_LOG_FLAG):
+                e.delete(self.PART_LOG_FLAG)
+                partial = True
+            else:
+                self._merge(evs, False)
+                out.append(src[begin])
+                begin = cur + 1
+        if partial:
+            self._merge(evs, False)
+            out.append(src[begin])
+        g.events = out
+
+    def _by_regex(self, g: Group):
+        S, C, E = self.start, self.cont, self.end
+        src, out, evs = g.events, [], []
+        begin = 0
+        partial = S is None and C is None and E is not None
+        for cur, e in enumerate(src):
+            if e.type != LOG or (e.size() != 0 and not e.has(self.source_key)):
+                if not evs:
+                    begin = cur
+                out.extend(src[begin:])
+                g.events = out
+                return
+            if e.size() == 0:
+                continue
+            val = e.get(self.source_key)
+            if not partial:
+                first = S if S is not None else C
+                if first.prefix_match(val):
+                    evs.append(e)
+                    begin = cur
+                    partial = True
+                elif E is not None and S is None and C is not None and E.prefix_match(val):
+                    begin = cur
+                    self.counters["merged_events"] += 1
+                    out.append(src[begin])
+                else:
+                    self._unmatched(src, out, cur, cur)
+                continue
+            if C is not None and C.prefix_match(val):
+                evs.append(e)
+                continue
+            if E is not None:
+                evs.append(e)
+                if C is not None:
+                    if E.prefix_match(val):
+                        self._merge(evs, True)
+                        out.append(src[begin])
+                    else:
+                        self._unmatched(src, out, begin, cur)
+                        evs.clear()
+                    partial = False
+                elif E.prefix_match(val):
+                    self._merge(evs, True)
+                    out.append(src[begin])
+                    if S is not None:
+                        partial = False
+                    else:
+                        begin = cur + 1
+            elif C is None:
+                if not S.prefix_match(val):
+                    evs.append(e)
+                else:
+                    self._merge(evs, True)
+                    out.append(src[begin])
+                    begin = cur
+                    evs.append(e)
+            else:
+                self._merge(evs, True)
+                out.append(src[begin])
+                if not S.prefix_match(val):
+                    self._unmatched(src, out, cur, cur)
+                    partial = False
+                else:
+                    begin = cur
+                    evs.append(e)
+        if partial and begin < len(src):
+            if E is None:
+                self._merge(evs, True)
+                out.append(src[begin])
+            else:
+                self._unmatched(src, out, begin, len(src) - 1)
+        g.events = out
+
+
 PROCESSORS = {
     p.name: p
     for p in (ProcessorSplitLogStringNative, ProcessorSplitMultilineLogStringNative, ProcessorParseRegexNative,
-              ProcessorParseDelimiterNative, ProcessorFilterNative)
+              ProcessorParseDelimiterNative, ProcessorFilterNative, ProcessorMergeMultilineLogNative)
 }

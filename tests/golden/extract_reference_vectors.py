@@ -28,6 +28,7 @@ FILES = {
     "multiline": "ProcessorSplitMultilineLogStringNativeUnittest.cpp",
     "regex": "ProcessorParseRegexNativeUnittest.cpp",
     "delimiter": "ProcessorParseDelimiterNativeUnittest.cpp",
+    "merge": "ProcessorMergeMultilineLogNativeUnittest.cpp",
 }
 
 PROC_TYPES = {
@@ -35,6 +36,7 @@ PROC_TYPES = {
     "ProcessorSplitMultilineLogStringNative": "processor_split_multiline_log_string_native",
     "ProcessorParseRegexNative": "processor_parse_regex_native",
     "ProcessorParseDelimiterNative": "processor_parse_delimiter_native",
+    "ProcessorMergeMultilineLogNative": "processor_merge_multiline_log_native",
 }
 
 BUILTIN_CONSTS = {
@@ -276,6 +278,8 @@ def extract_file(kind, path):
             return {"input": in_json, "pipeline": [], "metadata": dict(pending_meta), "counters": []}
 
         pending_meta = {}
+        group_no = 0
+        pre_events = []
         last_case = None
         cur_emitted = False
         enable_meta = False
@@ -348,6 +352,8 @@ def extract_file(kind, path):
                 if "make_shared" in " ".join(ids) or ids[:1] == ["PipelineEventGroup"]:
                     if ids[:1] == ["PipelineEventGroup"]:
                         pending_meta = {}
+                        group_no += 1
+                        pre_events = []
                     continue
                 if "FromJsonString" in ids:
                     idx = ids.index("FromJsonString")
@@ -362,8 +368,21 @@ def extract_file(kind, path):
                                 break
                         e += 1
                     val, _ = ev.expr(st[k + 2:e] + [("op", ";")], 0)
-                    cur = new_case(val)
+                    if cur is not None and not cur["pipeline"] and cur.get("_group") == group_no:
+                        cur.setdefault("more_inputs", []).append(val)  # a second FromJsonString on the same group
+                    else:
+                        cur = new_case(val)
+                        cur["_group"] = group_no
+                        if pre_events:
+                            cur["pre_inputs"] = list(pre_events)
+                            pre_events = []
                     cur_emitted = False
+                    continue
+                if "AddMetricEvent" in ids:
+                    if cur is not None and not cur["pipeline"] and cur.get("_group") == group_no:
+                        cur.setdefault("more_inputs", []).append("__metric__")
+                    else:
+                        pre_events.append("__metric__")  # added before the group's first FromJsonString
                     continue
                 # Init
                 if "Init" in ids and "config" in ids:
@@ -445,6 +464,15 @@ def extract_file(kind, path):
     for c in cases:
         try:
             c["input"] = json.loads(c["input"], strict=False)
+            c.pop("_group", None)
+            metric = {"name": "", "timestamp": 0, "type": 2, "value": {"type": "unknown"}}
+            if c.get("pre_inputs"):
+                c["input"]["events"] = [metric] * len(c.pop("pre_inputs")) + c["input"]["events"]
+            for more in c.pop("more_inputs", []):
+                # what eventGroup.AddMetricEvent() serialises to (core/models/MetricEvent.cpp ToJson, empty event)
+                extra = [{"name": "", "timestamp": 0, "type": 2, "value": {"type": "unknown"}}] if more == "__metric__" \
+                    else json.loads(more, strict=False)["events"]
+                c["input"]["events"] = c["input"]["events"] + extra
             if c["expected"] is not None and c["expected"] != "__unchecked__":
                 c["expected"] = json.loads(c["expected"], strict=False)
             if not c["pipeline"]:

@@ -33,7 +33,7 @@ def load_cases(kind):
 
 def all_cases():
     out = []
-    for k in ("split", "multiline", "regex", "delimiter", "filter"):
+    for k in ("split", "multiline", "regex", "delimiter", "filter", "merge"):
         out.extend(load_cases(k))
     return out
 

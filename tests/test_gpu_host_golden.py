@@ -27,3 +27,70 @@ def test_host_processors_match_reference_fixture(fn):
 
     n = run_cases_of_function(BY_FN[fn], make, run, lambda p: p.counters())
     assert n > 0
+
+
+def test_merge_multiline_random_groups_match_oracle():
+    """ProcessorMergeMultilineLogNative on random groups: every supported pattern combination, both unmatched
+    treatments, the flag mode, empty events, events without the source key and unsupported events in the middle --
+    the host class (batched GPU probes + host walk) against the oracle restatement, contents and counters."""
+    import json
+    import random
+
+    import loongcollector_b200 as lc
+    from oracle import oracle as orc
+
+    rng = random.Random(20240607)
+    words = ["S1 begin", "S2", "  cont a", "  cont", "E done", "Eof", "noise", "x", "", "S", "E"]
+    combos = [("S.*", "", ""), ("S.*", r"\s+cont.*", ""), ("S\\d?.*", "", "E.*"), ("", r"\s+cont", "E\\w+"),
+              ("", "", "E.*$"), ("S.*", r"\s+cont.*", "E.*")]
+    name = "processor_merge_multiline_log_native"
+    checked = 0
+    for start, cont, end in combos:
+        for treat in ("single_line", "discard"):
+            cfg = {"MergeType": "regex", "UnmatchedContentTreatment": treat}
+            if start:
+                cfg["StartPattern"] = start
+            if cont:
+                cfg["ContinuePattern"] = cont
+            if end:
+                cfg["EndPattern"] = end
+            host, ora = lc.HostProcessor(name, cfg), orc.PROCESSORS[name](cfg)
+            for _ in range(12):
+                evs = []
+                for _ in range(rng.randint(0, 40)):
+                    r = rng.random()
+                    if r < 0.03:
+                        evs.append({"name": "", "timestamp": 0, "type": 2, "value": {"type": "unknown"}})
+                    elif r < 0.06:
+                        evs.append({"type": 1, "timestamp": 7, "timestampNanosecond": 0})
+                    elif r < 0.08:
+                        evs.append({"type": 1, "timestamp": 7, "timestampNanosecond": 0, "contents": {"other": "v"}})
+                    else:
+                        evs.append({"type": 1, "timestamp": 7, "timestampNanosecond": 0,
+                                    "contents": {"content": rng.choice(words), "tag": "t%d" % rng.randint(0, 3)}})
+                root = {"events": evs} if evs else None
+                got = host.process(json.loads(json.dumps(root)), True)
+                g = orc.Group.from_json(json.loads(json.dumps(root)))
+                ora.process(g)
+                assert json.dumps(got, sort_keys=True) == json.dumps(g.to_json(True), sort_keys=True), (cfg, root)
+                checked += 1
+            hc = host.counters()
+            assert hc["merged_events_total"] == ora.counters["merged_events"], cfg
+            assert hc["unmatched_events_total"] == ora.counters["unmatched_events"], cfg
+    # flag mode: docker partial logs
+    cfg = {"MergeType": "flag"}
+    host, ora = lc.HostProcessor(name, cfg), orc.PROCESSORS[name](cfg)
+    for _ in range(30):
+        evs = []
+        for _ in range(rng.randint(1, 30)):
+            c = {"content": rng.choice(words)}
+            if rng.random() < 0.4:
+                c["P"] = ""
+            evs.append({"type": 1, "timestamp": 7, "timestampNanosecond": 0, "contents": c})
+        root = {"events": evs, "metadata": {"has.part.log": "P"}} if rng.random() < 0.8 else {"events": evs}
+        got = host.process(json.loads(json.dumps(root)), True)
+        g = orc.Group.from_json(json.loads(json.dumps(root)))
+        ora.process(g)
+        assert json.dumps(got, sort_keys=True) == json.dumps(g.to_json(True), sort_keys=True), root
+        checked += 1
+    assert checked > 150
