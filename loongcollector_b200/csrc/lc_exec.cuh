@@ -5,6 +5,7 @@
 // library only ever calls these from device code.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include "lc_tables.h"
 
@@ -362,5 +363,121 @@ LC_HD bool lc_tdfa_event(const LcTdfaView& v, const uint8_t* s, uint32_t mis, ui
     if (fin == LC_NONE_ENTRY)
         return false;
     lc_tdfa_run_ops(v, fin, n, regs);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Delimiter quote FSM (DelimiterModeFsmParser::ParseDelimiterLine, zero-copy variant,
+// core/parser/DelimiterModeFsmParser.cpp:260-294) with run skipping: per 16-byte aligned chunk the separator and
+// quote positions are found with byte-wise SIMD compares; only those "special" bytes go through the state
+// machine, every run of ordinary bytes between them is one step (the ordinary-byte transition is idempotent:
+// INITIAL -> DATA, QUOTE / DATA stay, DOUBLE_QUOTE is an error).  Exactly the per-byte machine otherwise.
+//   v = line base; [begin, end) = trimmed range; push(field_start, field_len, doubled_quotes) receives every column.
+// Reads the aligned 16-byte chunks that contain bytes of [begin, end) (like the kernel's other loaders).
+LC_HD uint32_t lc_eq_mask16(const uint32_t w[4], uint32_t splat) {
+    uint32_t m = 0;
+    for (int k = 0; k < 4; ++k) {
+#if defined(__CUDA_ARCH__)
+        const uint32_t eq = __vcmpeq4(w[k], splat) & 0x01010101u;
+#else
+        uint32_t x = w[k] ^ splat, eq = 0;
+        for (int b = 0; b < 4; ++b)
+            if (((x >> (8 * b)) & 0xFFu) == 0)
+                eq |= 1u << (8 * b);
+#endif
+        m |= (((eq * 0x01020408u) >> 24) & 0xFu) << (4 * k);
+    }
+    return m;
+}
+
+template <class Push>
+LC_HD bool lc_delim_fsm(const uint8_t* v, int32_t begin, int32_t end, uint8_t sep, uint8_t quote, Push& push) {
+    int state = 0; // 0 INITIAL 1 QUOTE 2 DATA 3 DOUBLE_QUOTE
+    int dq = 0;
+    int fs = begin, fe = begin;
+    const uint32_t sep_splat = sep * 0x01010101u, quote_splat = quote * 0x01010101u;
+    const uint32_t mis = (uint32_t)((uintptr_t)v & 15u);
+    const uint8_t* abase = v - mis;
+    const uint32_t qb = (uint32_t)begin + mis, qe = (uint32_t)end + mis; // range in the aligned frame
+    uint32_t cur = qb;                                                   // next unprocessed byte
+    for (uint32_t qc = qb >> 4; end > begin && qc <= ((qe - 1) >> 4); ++qc) {
+        uint32_t w[4];
+#if defined(__CUDA_ARCH__)
+        const uint4 vv = __ldg(reinterpret_cast<const uint4*>(abase) + qc);
+        w[0] = vv.x, w[1] = vv.y, w[2] = vv.z, w[3] = vv.w;
+#else
+        memcpy(w, abase + (size_t)qc * 16, 16);
+#endif
+        const uint32_t q0 = qc * 16;
+        uint32_t ms = lc_eq_mask16(w, sep_splat), mq = lc_eq_mask16(w, quote_splat);
+        uint32_t special = ms | mq;
+        if (q0 < qb)
+            special &= ~((1u << (qb - q0)) - 1u);
+        if (qe - q0 < 16)
+            special &= (1u << (qe - q0)) - 1u;
+        const uint32_t chunk_end = qe - q0 < 16 ? qe : q0 + 16;
+        for (;;) {
+            uint32_t next = chunk_end;
+            int b = -1;
+            if (special) {
+#if defined(__CUDA_ARCH__)
+                b = __ffs((int)special) - 1;
+#else
+                b = __builtin_ctz(special);
+#endif
+                special &= special - 1;
+                next = q0 + (uint32_t)b;
+            }
+            const uint32_t gap = next - cur; // run of ordinary bytes
+            if (gap) {
+                if (state == 3)
+                    return false;
+                if (state == 0)
+                    state = 2;
+                fe += (int)gap;
+            }
+            if (b < 0) {
+                cur = chunk_end;
+                break;
+            }
+            cur = next + 1;
+            if (ms >> b & 1) { // separator
+                if (state == 1) {
+                    fe++;
+                } else if (state == 3) {
+                    state = 0;
+                    dq--;
+                    push((uint32_t)fs, (uint32_t)(fe - fs), (uint32_t)dq);
+                    dq = 0;
+                    fe += 2;
+                    fs = fe;
+                } else {
+                    state = 0;
+                    push((uint32_t)fs, (uint32_t)(fe - fs), (uint32_t)dq);
+                    dq = 0;
+                    fs = ++fe;
+                }
+            } else { // quote (a byte equal to both counts as the separator, as in the per-byte machine)
+                if (state == 0) {
+                    state = 1;
+                    fs++;
+                } else if (state == 1) {
+                    state = 3;
+                    dq++;
+                    fe++;
+                } else if (state == 2) {
+                    return false;
+                } else {
+                    state = 1;
+                    fe++;
+                }
+            }
+        }
+    }
+    if (state == 3)
+        dq--;
+    if (state == 1)
+        return false;
+    push((uint32_t)fs, (uint32_t)(fe - fs), (uint32_t)dq);
     return true;
 }

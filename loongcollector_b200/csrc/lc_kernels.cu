@@ -2131,74 +2131,9 @@ __global__ void __launch_bounds__(128)
     } else {
         const bool use_quote = cfg.sep_len == 1 && cfg.quote != cfg.sep[0];
         if (use_quote) {
-            // DelimiterModeFsmParser::ParseDelimiterLine (zero-copy variant, :260-294)
-            const uint8_t sep = cfg.sep[0], quote = cfg.quote;
-            int state = 0; // 0 INITIAL 1 QUOTE 2 DATA 3 DOUBLE_QUOTE
-            int dq = 0;
-            int fs = begIdx, fe = begIdx;
-            // bytes are consumed as 16-byte aligned chunks (one LDG.128 per 16 bytes instead of 16 byte loads)
-            const uint32_t mis = (uint32_t)((uintptr_t)v & 15u);
-            const uint4* chunks = reinterpret_cast<const uint4*>(v - mis);
-            const uint32_t qb = (uint32_t)begIdx + mis, qe = (uint32_t)endIdx + mis;
-            for (uint32_t qc = qb >> 4; qc <= ((qe - 1) >> 4) && ok; ++qc) {
-                const uint4 vv = __ldg(chunks + qc);
-                const uint32_t wd[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-                for (int bi = 0; bi < 16; ++bi) {
-                    const uint32_t q = qc * 16 + bi;
-                    if (q < qb || q >= qe || !ok)
-                        continue;
-                    const uint8_t c = (uint8_t)(wd[bi >> 2] >> (8 * (bi & 3)));
-                if (c == sep) {
-                    if (state == 1) {
-                        fe++;
-                    } else if (state == 3) {
-                        state = 0;
-                        dq--;
-                        push(fs, fe - fs, dq);
-                        dq = 0;
-                        fe += 2;
-                        fs = fe;
-                    } else {
-                        state = 0;
-                        push(fs, fe - fs, dq);
-                        dq = 0;
-                        fs = ++fe;
-                    }
-                } else if (c == quote) {
-                    if (state == 0) {
-                        state = 1;
-                        fs++;
-                    } else if (state == 1) {
-                        state = 3;
-                        dq++;
-                        fe++;
-                    } else if (state == 2) {
-                        ok = false;
-                    } else {
-                        state = 1;
-                        fe++;
-                    }
-                } else {
-                    if (state == 0) {
-                        state = 2;
-                        fe++;
-                    } else if (state == 3) {
-                        ok = false;
-                    } else {
-                        fe++;
-                    }
-                }
-                }
-            }
-            if (ok) {
-                if (state == 3)
-                    dq--;
-                if (state == 1)
-                    ok = false;
-                else
-                    push(fs, fe - fs, dq);
-            }
+            // DelimiterModeFsmParser::ParseDelimiterLine (zero-copy variant, :260-294), run-skipping formulation:
+            // only separators and quotes step the state machine, runs of ordinary bytes are one step (lc_exec.cuh)
+            ok = lc_delim_fsm(v, begIdx, endIdx, cfg.sep[0], cfg.quote, push);
         } else {
             // ProcessorParseDelimiterNative::SplitString (:366-409)
             const uint32_t d = cfg.sep_len;

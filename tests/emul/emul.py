@@ -39,6 +39,9 @@ def lib():
         L.emul_full_match_tdfa.restype = C.c_int
         L.emul_full_match_tdfa.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.emul_tdfa_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.emul_delim_fsm.restype = C.c_int64
+        L.emul_delim_fsm.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint8, C.c_uint8, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int64]
         L.emul_fast2_bytes.restype = C.c_uint32
         L.emul_fast2_bytes.argtypes = [C.c_void_p]
         L.emul_fast_bytes.restype = C.c_uint32
@@ -119,3 +122,17 @@ class EmulRegex:
             lib().emul_free(self._h)
         except Exception:
             pass
+
+
+def delim_fsm(buf: np.ndarray, line_off: int, begin: int, end: int, sep: int, quote: int, cap: int = 64):
+    """Run-skipping delimiter FSM of the kernels on the line starting at buf[line_off] (buf must keep 16 spare
+    bytes on both sides of the line).  Returns None on an FSM error, else the list of (off, len, dq) columns."""
+    fo = np.zeros(cap, np.uint32)
+    fl = np.zeros(cap, np.uint32)
+    fd = np.zeros(cap, np.uint32)
+    n = lib().emul_delim_fsm(buf.ctypes.data + line_off, begin, end, sep, quote, fo.ctypes.data_as(C.c_void_p),
+                             fl.ctypes.data_as(C.c_void_p), fd.ctypes.data_as(C.c_void_p), cap)
+    if n < 0:
+        return None
+    k = min(int(n), cap)
+    return int(n), list(zip(fo[:k].tolist(), fl[:k].tolist(), fd[:k].tolist()))

@@ -125,3 +125,22 @@ uint32_t emul_tdfa_blob(const EmulRegex* e, uint8_t* out, uint32_t cap) {
     return n;
 }
 }
+
+extern "C" {
+// run-skipping delimiter FSM of the kernels (lc_exec.cuh: lc_delim_fsm); same contract as the oracle's orc_delim_fsm:
+// returns the column count or -1 on an FSM error; writes at most cap columns.  `line` must sit in a buffer with 16
+// readable bytes before and after it (aligned 16-byte chunks are read).
+int64_t emul_delim_fsm(const uint8_t* line, int32_t begin, int32_t end, uint8_t sep, uint8_t quote, uint32_t* f_off,
+                       uint32_t* f_len, uint32_t* f_dq, int64_t cap) {
+    int64_t n = 0;
+    auto push = [&](uint32_t o, uint32_t l, uint32_t dq) {
+        if (n < cap) {
+            f_off[n] = o;
+            f_len[n] = l;
+            f_dq[n] = dq;
+        }
+        ++n;
+    };
+    return lc_delim_fsm(line, begin, end, sep, quote, push) ? n : -1;
+}
+}
