@@ -2087,20 +2087,46 @@ void launch_ml_emit(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t*
 }
 
 // ================================================================================================ delimiter
+// STAGED (max_fields <= kDelimStagedMaxFields): the [32 lines][max_fields] blocks of f_off / f_len / f_dq that a warp
+// produces are contiguous in the output tables, so they are assembled in shared memory (row pitch max_fields | 1:
+// conflict-free for the per-line pushes) and leave as fully coalesced 128-byte stores, zero padding included; the
+// direct variant writes every record with a 4-byte store into its line's row (32 different rows per warp
+// instruction).
+constexpr uint32_t kDelimStagedMaxFields = 32;
+template <bool STAGED>
 __global__ void __launch_bounds__(128)
     delim_kernel(DelimConfig cfg, const uint8_t* __restrict__ base, const uint32_t* __restrict__ ev_off,
                  const uint32_t* __restrict__ ev_len, uint64_t n, uint8_t* __restrict__ status,
                  uint32_t* __restrict__ nfields, uint32_t* __restrict__ f_off, uint32_t* __restrict__ f_len,
                  uint32_t* __restrict__ f_dq) {
+    extern __shared__ uint32_t s_rows[]; // STAGED: [warp][3][32][pitch]
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-        return;
+    const uint32_t MF = cfg.max_fields;
+    const uint32_t lane = threadIdx.x & 31, pitch = MF | 1u;
+    uint32_t* fo;
+    uint32_t* fl;
+    uint32_t* fd;
+    uint32_t* wrows = nullptr;
+    if (STAGED) {
+        wrows = s_rows + (size_t)(threadIdx.x >> 5) * 3 * 32 * pitch;
+        fo = wrows + lane * pitch;
+        fl = fo + 32 * pitch;
+        fd = fl + 32 * pitch;
+        for (uint32_t k = 0; k < MF; ++k) {
+            fo[k] = 0;
+            fl[k] = 0;
+            fd[k] = 0;
+        }
+    } else {
+        if (i >= n)
+            return;
+        fo = f_off + i * MF;
+        fl = f_len + i * MF;
+        fd = f_dq + i * MF;
+    }
+    if (i < n) {
     const uint32_t eo = ev_off[i];
     const uint8_t* v = base + eo;
-    const uint32_t MF = cfg.max_fields;
-    uint32_t* fo = f_off + i * MF;
-    uint32_t* fl = f_len + i * MF;
-    uint32_t* fd = f_dq + i * MF;
     uint32_t nf = 0; // columns counted
     uint8_t st;
     // trim (:226-238)
@@ -2183,10 +2209,31 @@ __global__ void __launch_bounds__(128)
     }
     status[i] = st;
     nfields[i] = nf;
-    for (uint32_t k = (st == 1 || st == 2) ? 0 : (nf < MF ? nf : MF); k < MF; ++k) {
+    // rows of failed / blank lines are zero; so are the unused columns (STAGED rows start out zeroed)
+    for (uint32_t k = (st == 1 || st == 2) ? 0 : (nf < MF ? nf : MF); k < MF && (!STAGED || st == 1 || st == 2); ++k) {
         fo[k] = 0;
         fl[k] = 0;
         fd[k] = 0;
+    }
+    }
+    if (STAGED) {
+        __syncwarp();
+        const uint64_t i0 = i - lane; // first line of this warp
+        if (i0 < n) {
+            const uint64_t left = n - i0;
+            const uint32_t total = (uint32_t)(left < 32 ? left : 32) * MF;
+            const uint32_t invMF = MF > 1 ? 0xFFFFFFFFu / MF + 1 : 0;
+            uint32_t* go = f_off + i0 * MF;
+            uint32_t* gl = f_len + i0 * MF;
+            uint32_t* gd = f_dq + i0 * MF;
+            for (uint32_t j = lane; j < total; j += 32) {
+                const uint32_t line = MF > 1 ? __umulhi(j, invMF) : j, k = j - line * MF;
+                const uint32_t at = line * pitch + k;
+                go[j] = wrows[at];
+                gl[j] = wrows[32 * pitch + at];
+                gd[j] = wrows[64 * pitch + at];
+            }
+        }
     }
 }
 
@@ -2195,8 +2242,18 @@ void launch_delim(const DelimConfig& cfg, const uint8_t* d_base, const uint32_t*
                   uint32_t* d_f_dq, cudaStream_t st) {
     if (!n)
         return;
-    delim_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cfg, d_base, d_ev_off, d_ev_len, n, d_status, d_nfields,
-                                                              d_f_off, d_f_len, d_f_dq);
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    static const bool direct = getenv("LC_B200_DELIM_DIRECT") != nullptr; // A/B knob
+    if (!direct && cfg.max_fields && cfg.max_fields <= kDelimStagedMaxFields) {
+        const size_t smem = (size_t)4 * 3 * 32 * (cfg.max_fields | 1u) * sizeof(uint32_t);
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(delim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        delim_kernel<true><<<grid, 128, smem, st>>>(cfg, d_base, d_ev_off, d_ev_len, n, d_status, d_nfields, d_f_off,
+                                                    d_f_len, d_f_dq);
+    } else {
+        delim_kernel<false><<<grid, 128, 0, st>>>(cfg, d_base, d_ev_off, d_ev_len, n, d_status, d_nfields, d_f_off,
+                                                  d_f_len, d_f_dq);
+    }
 }
 
 } // namespace lck
