@@ -35,15 +35,19 @@ __device__ __forceinline__ uint32_t match16(uint4 v, uint32_t splat) {
     return m;
 }
 
-// Each thread owns ROWS consecutive 16-byte chunks (64 contiguous bytes for ROWS = 4): one 64-bit newline mask,
-// ONE block scan and ONE look-back per 16 KiB tile.  A warp's loads cover 2 KiB of contiguous memory, so every
-// 128-byte line is fetched once (two lanes x four loads share it through L1).
-template <int THREADS, int ROWS>
+// Each thread owns SEGS x 64 contiguous bytes (4 x 16-byte chunks and one 64-bit newline mask per segment): ONE
+// block scan and ONE look-back per tile of THREADS x SEGS x 64 bytes.  A warp's loads cover contiguous memory, so
+// every 128-byte line is fetched once (lanes share it through L1).  Tiles are deliberately LARGE (1024 threads,
+// 64 KiB): the block waits at a barrier while its first warp walks back over the descriptors of unfinished
+// predecessors, and that walk gets longer with the number of tiles in flight (measured on C1: 16 KiB tiles 1.64,
+// 32 KiB 1.73, 64 KiB 1.87 TB/s; 128 KiB = 2 segments per thread 1.75 TB/s, the 57 registers leave one block per
+// SM; one tile per WARP, no barrier at all, 1.15 TB/s).
+template <int THREADS, int SEGS>
 __global__ void __launch_bounds__(THREADS)
     split_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
                  uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap, volatile uint64_t* desc,
                  uint32_t* ticket, uint32_t ntiles, uint32_t* n_out) {
-    static_assert(ROWS == 4, "one 64-bit mask per thread");
+    constexpr int ROWS = 4 * SEGS;
     __shared__ uint64_t s_scan[THREADS / 32 + 1];
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_prefix;
@@ -64,23 +68,29 @@ __global__ void __launch_bounds__(THREADS)
         if (vpos0 + (uint64_t)r * 16 < total_v)
             v[r] = __ldg(vbuf + chunk0 + r);
     }
-    uint64_t mask = 0;
+    uint64_t mask[SEGS];
+    uint64_t pay = OpCountMax::identity();
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const uint64_t vpos = vpos0 + (uint64_t)r * 16;
-        uint32_t m = 0;
-        if (vpos < total_v) {
-            m = match16(v[r], splat);
-            if (vpos == 0 && shift) // alignment lead-in bytes in front of the buffer (shift < 16)
-                m &= ~((1u << shift) - 1u);
-            const uint64_t rem = total_v - vpos;
-            if (rem < 16)
-                m &= (1u << rem) - 1u;
+    for (int sg = 0; sg < SEGS; ++sg) {
+        uint64_t mk = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint64_t vpos = vpos0 + (uint64_t)(sg * 4 + r) * 16;
+            uint32_t m = 0;
+            if (vpos < total_v) {
+                m = match16(v[sg * 4 + r], splat);
+                if (vpos == 0 && shift) // alignment lead-in bytes in front of the buffer (shift < 16)
+                    m &= ~((1u << shift) - 1u);
+                const uint64_t rem = total_v - vpos;
+                if (rem < 16)
+                    m &= (1u << rem) - 1u;
+            }
+            mk |= (uint64_t)m << (16 * r);
         }
-        mask |= (uint64_t)m << (16 * r);
+        mask[sg] = mk;
+        const uint32_t last = mk ? (uint32_t)(vpos0 + sg * 64 + (63 - __clzll((long long)mk)) + 1 - shift) : 0u;
+        pay = OpCountMax::combine(pay, OpCountMax::make(__popcll(mk), last));
     }
-    const uint32_t last = mask ? (uint32_t)(vpos0 + (63 - __clzll((long long)mask)) + 1 - shift) : 0u;
-    const uint64_t pay = OpCountMax::make(__popcll(mask), last);
     uint64_t tot;
     const uint64_t excl = block_exclusive_scan<OpCountMax, THREADS>(pay, tot, s_scan);
     if (tid < 32) {
@@ -92,16 +102,20 @@ __global__ void __launch_bounds__(THREADS)
     const uint64_t pre = OpCountMax::combine(s_prefix, excl);
     uint32_t k = OpCountMax::count(pre);
     uint32_t start = OpCountMax::maxv(pre);
-    while (mask) {
-        const int b = __ffsll((long long)mask) - 1;
-        mask &= mask - 1;
-        const uint32_t p = (uint32_t)(vpos0 + b - shift);
-        if (k < cap) {
-            out_off[k] = start;
-            out_len[k] = p - start;
+#pragma unroll
+    for (int sg = 0; sg < SEGS; ++sg) {
+        uint64_t mk = mask[sg];
+        while (mk) {
+            const int b = __ffsll((long long)mk) - 1;
+            mk &= mk - 1;
+            const uint32_t p = (uint32_t)(vpos0 + sg * 64 + b - shift);
+            if (k < cap) {
+                out_off[k] = start;
+                out_len[k] = p - start;
+            }
+            ++k;
+            start = p + 1;
         }
-        ++k;
-        start = p + 1;
     }
     if (tile == ntiles - 1 && tid == THREADS - 1) {
         // inclusive total of the whole buffer: the unterminated last piece, if any
@@ -119,10 +133,23 @@ __global__ void __launch_bounds__(THREADS)
 void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
                   uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out, cudaStream_t st) {
     uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
-    uint32_t ntiles = split_tiles(len, shift);
     uint32_t splat = split_char * 0x01010101u;
-    split_kernel<kSplitThreads, kSplitRows><<<ntiles, kSplitThreads, 0, st>>>(
-        d_buf, len, shift, splat, d_off, d_len, cap, (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out);
+    static const int cfg = [] {
+        const char* e = getenv("LC_B200_SPLIT_TILE_KB"); // A/B knob: 16, 64 or 128 (descriptors are sized for 16)
+        int t = e ? atoi(e) : 64;
+        return (t == 16 || t == 128) ? t : 64;
+    }();
+    const uint64_t tile_bytes = (uint64_t)cfg * 1024;
+    uint32_t ntiles = (uint32_t)((len + shift + tile_bytes - 1) / tile_bytes);
+    if (cfg == 128)
+        split_kernel<1024, 2><<<ntiles, 1024, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
+                                                        (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out);
+    else if (cfg == 64)
+        split_kernel<1024, 1><<<ntiles, 1024, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
+                                                        (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out);
+    else
+        split_kernel<256, 1><<<ntiles, 256, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
+                                                      (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out);
 }
 
 // ================================================================================================ sums

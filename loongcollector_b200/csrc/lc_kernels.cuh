@@ -6,9 +6,8 @@
 
 namespace lck {
 
-constexpr int kSplitThreads = 256;
-constexpr int kSplitRows = 4;
-constexpr uint32_t kSplitTileBytes = kSplitThreads * kSplitRows * 16; // 16 KiB of input per tile
+// smallest split tile (16 KiB): look-back descriptors are sized for it; the kernel normally runs 128 KiB tiles
+constexpr uint32_t kSplitTileBytes = 256 * 4 * 16;
 
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 4;
