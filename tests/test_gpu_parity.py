@@ -441,3 +441,89 @@ def test_regex_match_boolean_matches_oracle(eng):
         got = eng.regex_match(lc.Regex(p), base, off, ln)
         want = orc.regex_match_batch(orc.Regex(p), base, off, ln)
         assert np.array_equal(got, want), p
+
+
+# ------------------------------------------------------------------------------------------- unaligned arenas
+@pytest.mark.parametrize("shift", [1, 7, 16, 77])
+def test_dev_entry_points_with_unaligned_base(eng, shift):
+    """*_dev entry points take an arena that is already in HBM; nothing says it starts on a 16-byte boundary (a
+    SourceBuffer value can start anywhere inside its chunk).  Every kernel that reads aligned 16-byte chunks has to
+    fold the misalignment of `base` itself into its addressing -- checked here for split, regex parse (single-pass
+    and two-pass kernels), multiline and delimiter."""
+    import torch
+    lc = _lc()
+    from loongcollector_b200 import synth
+    dev = torch.device("cuda", 0)
+
+    def shifted(buf):
+        t = torch.zeros(buf.size + shift + 64, dtype=torch.uint8, device=dev)
+        t[shift:shift + buf.size] = torch.from_numpy(np.ascontiguousarray(buf)).to(dev)
+        return t, t.data_ptr() + shift
+
+    def dput(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    # split + regex parse over natural-length nginx lines
+    buf, off, ln = synth.nginx_lines(5000, seed=shift, line_bytes=None)
+    keep, ptr = shifted(buf)
+    n = off.size
+    d_off = torch.empty(n + 8, dtype=torch.int32, device=dev)
+    d_len = torch.empty(n + 8, dtype=torch.int32, device=dev)
+    got_n = eng.split_lines_dev(ptr, buf.size, 10, d_off.data_ptr(), d_len.data_ptr(), n + 8)
+    assert got_n == n
+    assert np.array_equal(d_off[:n].cpu().numpy().view(np.uint32), off)
+    assert np.array_equal(d_len[:n].cpu().numpy().view(np.uint32), ln)
+    o = orc.Regex(synth.NGINX_PATTERN)
+    est, eco, ecl = orc.regex_parse_batch(o, buf, off, ln, 10)
+    rx = lc.Regex(synth.NGINX_PATTERN)
+    G = rx.ngroups
+    for variant in ("tdfa", "fast2", "generic"):
+        os.environ["LC_B200_REGEX_KERNEL"] = variant
+        try:
+            e2 = lc.Engine(0)
+            st = torch.empty(n, dtype=torch.uint8, device=dev)
+            co = torch.empty(n * G, dtype=torch.int32, device=dev)
+            cl = torch.empty(n * G, dtype=torch.int32, device=dev)
+            e2.regex_parse_dev(rx, ptr, buf.size, d_off.data_ptr(), d_len.data_ptr(), n, 10, st.data_ptr(),
+                               co.data_ptr(), cl.data_ptr())
+            e2.sync()
+            assert np.array_equal(st.cpu().numpy(), est), variant
+            assert np.array_equal(co.cpu().numpy().view(np.uint32).reshape(n, G), eco), variant
+            assert np.array_equal(cl.cpu().numpy().view(np.uint32).reshape(n, G), ecl), variant
+            e2.close()
+        finally:
+            os.environ.pop("LC_B200_REGEX_KERNEL", None)
+    # multiline
+    jb, _, _ = synth.java_stack_records(400, seed=shift)
+    keep2, jptr = shifted(jb)
+    s = lc.Regex(synth.JAVA_START_PATTERN)
+    e_off, e_len, e_fl, ectr = orc.multiline_split(jb, orc.Regex(synth.JAVA_START_PATTERN), None, None, False)
+    cap = e_off.size + 8
+    m_off = torch.empty(cap, dtype=torch.int32, device=dev)
+    m_len = torch.empty(cap, dtype=torch.int32, device=dev)
+    m_fl = torch.empty(cap, dtype=torch.uint8, device=dev)
+    k, ctr = eng.multiline_split_dev(jptr, jb.size, s, None, None, False, m_off.data_ptr(), m_len.data_ptr(),
+                                     m_fl.data_ptr(), cap)
+    assert k == e_off.size and ctr.tolist() == ectr.tolist()
+    assert np.array_equal(m_off[:k].cpu().numpy().view(np.uint32), e_off)
+    assert np.array_equal(m_len[:k].cpu().numpy().view(np.uint32), e_len)
+    assert np.array_equal(m_fl[:k].cpu().numpy(), e_fl)
+    # delimiter
+    cb, c_off, c_len = synth.csv_lines(3000, seed=shift)
+    keep3, cptr = shifted(cb)
+    MF = 11
+    want = orc.delim_parse_batch(cb, c_off, c_len, b",", ord('"'), 10, True, True, MF)
+    nn = c_off.size
+    d_co, d_cl = dput(c_off.view(np.int32)), dput(c_len.view(np.int32))
+    st4 = torch.empty(nn, dtype=torch.uint8, device=dev)
+    nf4 = torch.empty(nn, dtype=torch.int32, device=dev)
+    fo4 = torch.empty(nn * MF, dtype=torch.int32, device=dev)
+    fl4 = torch.empty(nn * MF, dtype=torch.int32, device=dev)
+    fd4 = torch.empty(nn * MF, dtype=torch.int32, device=dev)
+    eng.delim_parse_dev(cptr, cb.size, d_co.data_ptr(), d_cl.data_ptr(), nn, b",", ord('"'), 10, True, True, MF,
+                        st4.data_ptr(), nf4.data_ptr(), fo4.data_ptr(), fl4.data_ptr(), fd4.data_ptr())
+    eng.sync()
+    got = (st4.cpu().numpy(), nf4.cpu().numpy().view(np.uint32), fo4.cpu().numpy().view(np.uint32).reshape(nn, MF),
+           fl4.cpu().numpy().view(np.uint32).reshape(nn, MF), fd4.cpu().numpy().view(np.uint32).reshape(nn, MF))
+    for g, w, name in zip(got, want, ("status", "nfields", "f_off", "f_len", "f_dq")):
+        assert np.array_equal(g, w), name
