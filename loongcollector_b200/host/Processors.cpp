@@ -1135,93 +1135,107 @@ void ProcessorMergeMultilineLogNative::MergeLogsByRegex(PipelineEventGroup& grou
                 (*p.dst)[batch.eventIndex[b]] = m[b];
         }
     }
+    // The walk as a decision table: what a value does depends only on (which patterns exist, whether a record is
+    // open, the three probe flags).  Decide() is that pure function; the loop below just executes its verdicts.
+    enum class Act {
+        OPEN,             // the value starts a record
+        ALONE,            // continue + end mode, no record open, the value matches the end pattern: a record by itself
+        UNMATCHED,        // no record open and nothing matches
+        APPEND,           // joins the open record, which stays open
+        APPEND_CLOSE,     // joins the open record and completes it
+        APPEND_FAIL,      // joins the open record, which thereby fails as a whole (continue + end, end not matched)
+        CLOSE_OPEN,       // the open record is complete WITHOUT this value, which starts the next one
+        CLOSE_UNMATCHED,  // the open record is complete without this value, which matches nothing
+    };
     const bool S = mHasStart, C = mHasContinue, E = mHasEnd;
-    size_t begin = 0, newSize = 0;
-    std::vector<LogEvent*> events;
-    bool isPartialLog = !S && !C && E; // only an end pattern: stick to the partial state
+    auto Decide = [S, C, E](bool open, bool mS, bool mC, bool mE) -> Act {
+        if (!open) {
+            if (S ? mS : mC)
+                return Act::OPEN;
+            return (!S && C && E && mE) ? Act::ALONE : Act::UNMATCHED;
+        }
+        if (C && mC)
+            return Act::APPEND;
+        if (E) {
+            if (C)
+                return mE ? Act::APPEND_CLOSE : Act::APPEND_FAIL;
+            return mE ? Act::APPEND_CLOSE : Act::APPEND;
+        }
+        if (!C)
+            return mS ? Act::CLOSE_OPEN : Act::APPEND;
+        return mS ? Act::CLOSE_OPEN : Act::CLOSE_UNMATCHED;
+    };
+    size_t head = 0;  // index of the first event of the open record
+    size_t kept = 0;  // events written back so far
+    std::vector<LogEvent*> record;
+    bool open = !S && !C && E; // with only an end pattern every value belongs to a record
+    auto Complete = [&]() {   // the open record becomes one event (the head event carries the joined value)
+        MergeEvents(group, record, true);
+        sourceEvents[kept++] = std::move(sourceEvents[head]);
+    };
     for (size_t cur = 0; cur < ne; ++cur) {
-        bool stop = !IsSupportedEvent(sourceEvents[cur]);
-        LogEvent* sourceEvent = stop ? nullptr : &sourceEvents[cur].Cast<LogEvent>();
-        if (!stop && sourceEvent->Empty())
+        LogEvent* ev = IsSupportedEvent(sourceEvents[cur]) ? &sourceEvents[cur].Cast<LogEvent>() : nullptr;
+        if (ev && ev->Empty())
             continue;
-        if (!stop && !sourceEvent->HasContent(mSourceKey))
-            stop = true;
-        if (stop) {
-            if (events.empty())
-                begin = cur;
-            for (size_t i = begin; i < ne; ++i)
-                sourceEvents[newSize++] = std::move(sourceEvents[i]);
-            sourceEvents.resize(newSize);
+        if (!ev || !ev->HasContent(mSourceKey)) {
+            // an unsupported event or one without the source key ends the walk: everything from the head of the
+            // open record (or from here) is kept as it is
+            if (record.empty())
+                head = cur;
+            for (size_t i = head; i < ne; ++i)
+                sourceEvents[kept++] = std::move(sourceEvents[i]);
+            sourceEvents.resize(kept);
             return;
         }
-        if (!isPartialLog) {
-            const bool first = S ? mS[cur] : mC[cur];
-            if (first) {
-                events.emplace_back(sourceEvent);
-                begin = cur;
-                isPartialLog = true;
-            } else if (E && !S && C && mE[cur]) {
-                begin = cur; // continue + end: the line matches the end pattern rather than the continue pattern
+        switch (Decide(open, mS[cur] != 0, mC[cur] != 0, mE[cur] != 0)) {
+            case Act::OPEN:
+                record.push_back(ev);
+                head = cur;
+                open = true;
+                break;
+            case Act::ALONE:
                 mMergedEventsTotal.Add(1);
-                sourceEvents[newSize++] = std::move(sourceEvents[begin]);
-            } else {
-                HandleUnmatchLogs(sourceEvents, newSize, cur, cur);
-            }
-            continue;
-        }
-        if (C && mC[cur]) {
-            events.emplace_back(sourceEvent);
-            continue;
-        }
-        if (E) {
-            events.emplace_back(sourceEvent);
-            if (C) {
-                if (mE[cur]) {
-                    MergeEvents(group, events, true);
-                    sourceEvents[newSize++] = std::move(sourceEvents[begin]);
-                } else {
-                    HandleUnmatchLogs(sourceEvents, newSize, begin, cur);
-                    events.clear();
-                }
-                isPartialLog = false;
-            } else if (mE[cur]) {
-                MergeEvents(group, events, true);
-                sourceEvents[newSize++] = std::move(sourceEvents[begin]);
-                if (S)
-                    isPartialLog = false;
+                sourceEvents[kept++] = std::move(sourceEvents[cur]);
+                break;
+            case Act::UNMATCHED:
+                HandleUnmatchLogs(sourceEvents, kept, cur, cur);
+                break;
+            case Act::APPEND:
+                record.push_back(ev);
+                break;
+            case Act::APPEND_CLOSE:
+                record.push_back(ev);
+                Complete();
+                if (S || C)
+                    open = false;
                 else
-                    begin = cur + 1; // only an end pattern: the next record starts right away
-            }
-        } else if (!C) { // start only
-            if (!mS[cur]) {
-                events.emplace_back(sourceEvent);
-            } else {
-                MergeEvents(group, events, true);
-                sourceEvents[newSize++] = std::move(sourceEvents[begin]);
-                begin = cur;
-                events.emplace_back(sourceEvent);
-            }
-        } else { // start + continue, and the line is not a continuation
-            MergeEvents(group, events, true);
-            sourceEvents[newSize++] = std::move(sourceEvents[begin]);
-            if (!mS[cur]) {
-                HandleUnmatchLogs(sourceEvents, newSize, cur, cur);
-                isPartialLog = false;
-            } else {
-                begin = cur;
-                events.emplace_back(sourceEvent);
-            }
+                    head = cur + 1; // only an end pattern: the next record starts right away
+                break;
+            case Act::APPEND_FAIL:
+                record.clear();
+                HandleUnmatchLogs(sourceEvents, kept, head, cur);
+                open = false;
+                break;
+            case Act::CLOSE_OPEN:
+                Complete();
+                head = cur;
+                record.push_back(ev);
+                break;
+            case Act::CLOSE_UNMATCHED:
+                Complete();
+                HandleUnmatchLogs(sourceEvents, kept, cur, cur);
+                open = false;
+                break;
         }
     }
-    if (isPartialLog && begin < ne) {
-        if (!E) {
-            MergeEvents(group, events, true);
-            sourceEvents[newSize++] = std::move(sourceEvents[begin]);
-        } else {
-            HandleUnmatchLogs(sourceEvents, newSize, begin, ne - 1);
-        }
+    // a record still open at the end of the group: complete when there is no end pattern to wait for, else unmatched
+    if (open && head < ne) {
+        if (!E)
+            Complete();
+        else
+            HandleUnmatchLogs(sourceEvents, kept, head, ne - 1);
     }
-    sourceEvents.resize(newSize);
+    sourceEvents.resize(kept);
 }
 
 Processor* CreateProcessor(const std::string& type) {
