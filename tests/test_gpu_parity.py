@@ -527,3 +527,56 @@ def test_dev_entry_points_with_unaligned_base(eng, shift):
            fl4.cpu().numpy().view(np.uint32).reshape(nn, MF), fd4.cpu().numpy().view(np.uint32).reshape(nn, MF))
     for g, w, name in zip(got, want, ("status", "nfields", "f_off", "f_len", "f_dq")):
         assert np.array_equal(g, w), name
+
+
+def test_regex_every_length_at_every_alignment(eng):
+    """The staged single-pass kernel decomposes a line into an optional head chunk, fully paired 16-byte chunks and
+    an optional tail chunk (odd first / last byte peeled) in the line's own 16-byte frame: every line length 0..100
+    at every start alignment 0..15, matching and non-matching, through the device entry point."""
+    import torch
+    lc = _lc()
+    rng = random.Random(1234)
+    dev = torch.device("cuda", 0)
+    patterns = [r"(\w*)-(\d*)(x?)(.*)", r"([a-z]+)(?: (\d+))*", r'"([^"]*)" "([^"]*)"(.*)', r"(a|ab)(c|bcd)*(d*)(.*)"]
+    alpha = 'ab cd-12x"'
+    pieces, offs, lens = [], [], []
+    at = 0
+    for length in range(0, 101):
+        for align in range(16):
+            pad = (align - at) % 16
+            pieces.append(b"#" * pad)
+            at += pad
+            kind = rng.random()
+            if kind < 0.4:
+                body = ("ab-%s%s" % ("1" * rng.randint(0, 3), "x" * rng.randint(0, 1))).encode()
+            elif kind < 0.6:
+                body = b'"' + b"q" * rng.randint(0, 5) + b'" "' + b"r" * rng.randint(0, 5) + b'"'
+            else:
+                body = b""
+            line = (body + "".join(rng.choice(alpha) for _ in range(length)).encode())[:length]
+            pieces.append(line)
+            offs.append(at)
+            lens.append(len(line))
+            at += len(line)
+    base = np.frombuffer(b"".join(pieces) + b"#" * 32, np.uint8)
+    off = np.array(offs, np.uint32)
+    ln = np.array(lens, np.uint32)
+    n = off.size
+    d_base = torch.from_numpy(base.copy()).to(dev)
+    d_off = torch.from_numpy(off.view(np.int32).copy()).to(dev)
+    d_len = torch.from_numpy(ln.view(np.int32).copy()).to(dev)
+    for pattern in patterns:
+        rx, o = lc.Regex(pattern), orc.Regex(pattern)
+        G = rx.ngroups
+        est, eco, ecl = orc.regex_parse_batch(o, base, off, ln, G)
+        st = torch.empty(n, dtype=torch.uint8, device=dev)
+        co = torch.empty(n * G, dtype=torch.int32, device=dev)
+        cl = torch.empty(n * G, dtype=torch.int32, device=dev)
+        eng.regex_parse_dev(rx, d_base.data_ptr(), base.size, d_off.data_ptr(), d_len.data_ptr(), n, G, st.data_ptr(),
+                            co.data_ptr(), cl.data_ptr())
+        eng.sync()
+        bad = np.nonzero(st.cpu().numpy() != est)[0]
+        assert bad.size == 0, (pattern, [(int(ln[i]), int(off[i]) % 16) for i in bad[:5]])
+        assert np.array_equal(co.cpu().numpy().view(np.uint32).reshape(n, G), eco), pattern
+        assert np.array_equal(cl.cpu().numpy().view(np.uint32).reshape(n, G), ecl), pattern
+        assert 0 < int((est == 0).sum()) < n, pattern  # both verdicts occur
