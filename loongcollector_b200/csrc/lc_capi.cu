@@ -83,7 +83,7 @@ struct lc_engine {
     int regex_variant = 0; // env LC_B200_REGEX_KERNEL: 0 auto, 1 "fast" (stride-1), 2 "fast2" (stride-2), 3 "generic",
                            // 4 "tdfa" (single pass, staged input), 5 "tdfa_direct" (single pass, per-lane loads)
     uint64_t scratch_hint = 0;
-    bool length_order = false; // env LC_B200_LENGTH_ORDER=1
+    int length_order = -1; // env LC_B200_LENGTH_ORDER: 1 = always order ragged batches by length, 0 = never, unset = auto
     uint32_t max_warps = 32;   // env LC_B200_MAX_WARPS (tuning knob: resident warps per block of the regex kernels)
     // staging / workspace (grow-only)
     DevBuf in, ev_off, ev_len, out_a, out_b, out_c, out_d, out_e;
@@ -223,7 +223,7 @@ int lc_engine_create(int device, lc_engine_t** out) {
         if (mw && atoi(mw) >= 4 && atoi(mw) <= 32)
             e->max_warps = (uint32_t)atoi(mw);
         const char* lo = getenv("LC_B200_LENGTH_ORDER");
-        e->length_order = lo && !strcmp(lo, "1");
+        e->length_order = !lo ? -1 : (!strcmp(lo, "1") ? 1 : 0);
         e->regex_variant = !k ? 0 : (!strcmp(k, "fast") ? 1 : (!strcmp(k, "fast2") ? 2 : (!strcmp(k, "generic") ? 3 : (!strcmp(k, "tdfa") ? 4 : (!strcmp(k, "tdfa_direct") ? 5 : 0)))));
     }
     CU_TRY(e->small.ensure(sizeof(Small)));
@@ -480,13 +480,33 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
             const uint32_t threads = warps * 32;
             const uint64_t need_blocks = (n + threads - 1) / threads;
             const uint32_t grid = (uint32_t)std::min<uint64_t>(need_blocks, (uint64_t)e->num_sms);
+            // Ragged batches of long lines: a warp costs its longest line, so visit the events by descending length
+            // bucket.  Only looked at when the mean length makes the pre-pass (one small kernel + a sync) negligible;
+            // LC_B200_LENGTH_ORDER=1 forces it, =0 disables it.
+            const uint32_t* d_order = nullptr;
+            if (staged && n >= 4096 && e->length_order != 0 && (e->length_order == 1 || base_len / n >= 1024)) {
+                CU_TRY(cudaMemsetAsync(ds->counters, 0, sizeof ds->counters, e->stream));
+                lck::launch_len_stats(d_ev_len, n, ds->counters, e->stream);
+                e->launches++;
+                CU_TRY(cudaMemcpyAsync(hs->counters, ds->counters, sizeof ds->counters, cudaMemcpyDeviceToHost,
+                                       e->stream));
+                CU_TRY(cudaStreamSynchronize(e->stream));
+                const uint64_t mx = hs->counters[0], avg = hs->counters[1] / n + 1;
+                if (mx > avg + avg / 2 + 64) {
+                    CU_TRY(e->order.ensure(n * 4 + 256));
+                    uint32_t* hist = e->order.as<uint32_t>() + n;
+                    lck::launch_length_order(d_ev_len, n, hist, e->order.as<uint32_t>(), e->stream);
+                    e->launches += 3;
+                    d_order = e->order.as<uint32_t>();
+                }
+            }
             CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof(Small) - offsetof(Small, overflow), e->stream));
             int er;
             if (staged)
                 er = lck::launch_regex_tdfa_staged(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off,
                                                    d_ev_len, n, nkeys, d_status, bool_only ? nullptr : d_cap_off,
                                                    bool_only ? nullptr : d_cap_len, threads, grid, &ds->next_batch,
-                                                   &ds->overflow, e->stream);
+                                                   &ds->overflow, d_order, e->stream);
             else
                 er = lck::launch_regex_tdfa(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off, d_ev_len, n,
                                             nkeys, d_status, bool_only ? nullptr : d_cap_off,
@@ -598,7 +618,7 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
             const uint32_t* d_order = nullptr;
             // (measured on C5, Zipf 64 B-8 KB: -7 %, the scattered visiting order costs more L2 locality than the
             //  balanced warps win -- kept opt-in: LC_B200_LENGTH_ORDER=1)
-            if (e->length_order && h->mode == LC_MODE_TWOPASS && mx > 2 * avg + 64 && n >= 4096) {
+            if (e->length_order == 1 && h->mode == LC_MODE_TWOPASS && mx > 2 * avg + 64 && n >= 4096) {
                 CU_TRY(e->order.ensure(n * 4 + 256));
                 uint32_t* hist = e->order.as<uint32_t>() + n;
                 lck::launch_length_order(d_ev_len, n, hist, e->order.as<uint32_t>(), e->stream);

@@ -1442,7 +1442,7 @@ __global__ void __launch_bounds__(1024, 1)
                              const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
                              uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
                              uint32_t* __restrict__ cap_len, uint32_t reg_pitch /* halfwords */,
-                             unsigned long long* next_batch, uint32_t* overflow) {
+                             unsigned long long* next_batch, uint32_t* overflow, const uint32_t* __restrict__ order) {
     extern __shared__ uint4 smem[];
     // carve-out: [pad][class table, 256 B @ 256-aligned][blob][16 B][register files][line info: warps x 32 x 8 B]
     // [tiles: warps x 4 KB]
@@ -1505,7 +1505,9 @@ __global__ void __launch_bounds__(1024, 1)
         if (batch >= n)
             break;
         const bool valid = batch + lane < n;
-        const uint64_t i = batch + lane;
+        // ragged batches: `order` lists the events by descending length bucket, so that the 32 lines of a warp are of
+        // similar length (a warp costs its longest line)
+        const uint64_t i = (order && valid) ? order[batch + lane] : batch + lane;
         uint32_t off = 0, len = 0, mis = 0, nch = 0, g0 = 0;
         if (valid) {
             off = ev_off[i];
@@ -1587,6 +1589,22 @@ __global__ void __launch_bounds__(1024, 1)
         }
         if (bool_only || G == 0)
             continue;
+        if (order) { // rows of the batch are scattered: every lane writes its own
+            if (valid) {
+                uint32_t* co = cap_off + i * G;
+                uint32_t* cl = cap_len + i * G;
+                for (uint32_t g = 0; g < G; ++g) {
+                    uint32_t o = 0, l = 0;
+                    if (st == 0) {
+                        lc_slots16_to_cap(regs, g, len, &o, &l);
+                        o += off;
+                    }
+                    co[g] = o;
+                    cl[g] = l;
+                }
+            }
+            continue;
+        }
         // coalesced result rows: element j of the batch's [32][G] tables is produced by lane j % 32 straight from
         // the owning line's register file (one 32-bit LDS = begin | end << 16); the line's (off, len) travel
         // through the info slots
@@ -1621,7 +1639,8 @@ __global__ void __launch_bounds__(1024, 1)
 int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow, uint32_t nregs, const uint8_t* d_base,
                              const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
                              uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t threads,
-                             uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow, cudaStream_t st) {
+                             uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow,
+                             const uint32_t* d_order, cudaStream_t st) {
     if (!n)
         return 0;
     const uint32_t reg_pitch = tdfa_reg_pitch(nregs);
@@ -1631,7 +1650,7 @@ int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow,
     if (er != cudaSuccess)
         return (int)er;
     k<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
-                                   d_cap_off, d_cap_len, reg_pitch, d_next_batch, d_overflow);
+                                   d_cap_off, d_cap_len, reg_pitch, d_next_batch, d_overflow, d_order);
     return (int)cudaGetLastError();
 }
 

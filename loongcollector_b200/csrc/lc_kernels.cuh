@@ -101,7 +101,8 @@ inline size_t tdfa_staged_smem_bytes(uint32_t blob_bytes, uint32_t nregs, uint32
 int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow, uint32_t nregs, const uint8_t* d_base,
                              const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
                              uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t threads,
-                             uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow, cudaStream_t st);
+                             uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow,
+                             const uint32_t* d_order /* or nullptr */, cudaStream_t st);
 
 // parse status -> boolean (1 = the whole value matched)
 void launch_status_to_bool(uint8_t* d_status, uint64_t n, cudaStream_t st);
