@@ -1002,6 +1002,75 @@ class ProcessorMergeMultilineLogNative:
         g.events = out
 
 
+# ----------------------------------------------------------------------------- SLS wire format (next row, rank 4)
+# Restates core/protobuf/sls/LogGroupSerializer.cpp:33-143,232-262 (hand-rolled protobuf writer) and the LOG-event
+# path of SLSEventGroupSerializer::Serialize (core/collection_pipeline/serializer/SLSSerializer.cpp:162-269,377-395).
+SLS_MIN_LOG_TIME = 1 << 28  # AddLogTime clamps so that the varint always takes 5 bytes (:108-117)
+SLS_MAX_LOG_GROUP_SIZE = 10 * 1024 * 1024  # max_send_log_group_size (FlusherSLS.cpp:61)
+_SLS_TOPIC, _SLS_SOURCE, _SLS_UUID = b"__topic__", b"__source__", b"__machine_uuid__"
+
+
+def _sls_varint(v: int) -> bytes:
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def _sls_string(b: bytes) -> bytes:
+    return _sls_varint(len(b)) + b
+
+
+def _sls_pair(tag: int, key: bytes, val: bytes) -> bytes:
+    """Contents (field 2 of Log) / LogTags (field 6 of LogGroup): nested {Key = 1, Value = 2}"""
+    inner = b"\x0a" + _sls_string(key) + b"\x12" + _sls_string(val)
+    return bytes([tag]) + _sls_varint(len(inner)) + inner
+
+
+def sls_serialize_logs(events, enable_ns: bool):
+    """The `Logs` fields (field 1) of the LogGroup for a list of (time, ns or None, [(key, value), ...]); events
+    without contents are skipped (LogEvent::Empty).  Returns (bytes, offsets of each emitted record)."""
+    out = bytearray()
+    offs = []
+    for t, ns, contents in events:
+        if not contents:
+            continue
+        body = b"\x08" + _sls_varint(max(int(t) & 0xFFFFFFFF, SLS_MIN_LOG_TIME))
+        for k, v in contents:
+            body += _sls_pair(0x12, k, v)
+        if enable_ns and ns is not None:
+            body += b"\x25" + int(ns).to_bytes(4, "little")
+        offs.append(len(out))
+        out += b"\x0a" + _sls_varint(len(body)) + body
+    return bytes(out), offs
+
+
+def sls_serialize_group(g: "Group", enable_ns: bool = False):
+    """SLSEventGroupSerializer::Serialize for a group of LOG events: (bytes, None) or (None, error message)."""
+    if not g.events:
+        return None, "empty event group"
+    evs = [(e.timestamp, e.ns, e.live()) for e in g.events]
+    logs, _ = sls_serialize_logs(evs, enable_ns)
+    if not logs:
+        return None, "all empty logs"
+    tail = bytearray()
+    for k in sorted(g.tags, key=lambda x: _b(x)):  # SizedMap wraps a std::map: key order
+        kb, vb = _b(k), _b(g.tags[k])
+        if kb == _SLS_TOPIC:
+            tail += b"\x1a" + _sls_string(vb)
+        elif kb == _SLS_SOURCE:
+            tail += b"\x22" + _sls_string(vb)
+        elif kb == _SLS_UUID:
+            tail += b"\x2a" + _sls_string(vb)
+        else:
+            tail += _sls_pair(0x32, kb, vb)
+    if len(logs) + len(tail) > SLS_MAX_LOG_GROUP_SIZE:
+        return None, "log group exceeds size limit"
+    return logs + bytes(tail), None
+
+
 PROCESSORS = {
     p.name: p
     for p in (ProcessorSplitLogStringNative, ProcessorSplitMultilineLogStringNative, ProcessorParseRegexNative,
