@@ -147,6 +147,22 @@ int lc_delim_parse_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len,
                        uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* d_status,
                        uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len, uint32_t* d_f_dq);
 
+/* ---- f4 (next row): SLSEventGroupSerializer::Serialize for LOG events
+ *          (core/collection_pipeline/serializer/SLSSerializer.cpp:254-269,377-395 over the writer of
+ *           core/protobuf/sls/LogGroupSerializer.cpp:33-143,232-262)
+ * Emits the `Logs` fields (field 1 of sls_logs::LogGroup), concatenated in event order.  Event i owns the contents
+ * entries [ent_begin[i], ent_begin[i+1]) (m = ent_begin[n] entries in all); entry k is the key
+ * base[ent_koff[k], +ent_klen[k]) and the value base[ent_voff[k], +ent_vlen[k]).  Events without entries are skipped
+ * (LogEvent::Empty); Time below 2^28 is raised to 2^28 (the reference keeps the varint at 5 bytes);
+ * ev_time_ns may be NULL, and ev_time_ns[i] == LC_SLS_NO_NS means "no Time_ns field" (nanoseconds disabled or not
+ * set).  *out_len receives the total size; if it exceeds out_cap nothing is written and LC_ERR_CAPACITY is returned.
+ * The group-level fields (Topic, Source, MachineUUID, LogTags) are a few bytes appended by the caller. */
+#define LC_SLS_NO_NS 0xFFFFFFFFu
+int lc_sls_serialize_logs(lc_engine_t* e, const uint8_t* base, uint64_t base_len, uint64_t n, const uint32_t* ev_time,
+                          const uint32_t* ev_time_ns, const uint64_t* ent_begin, const uint32_t* ent_koff,
+                          const uint32_t* ent_klen, const uint32_t* ent_voff, const uint32_t* ent_vlen, uint8_t* out,
+                          uint64_t out_cap, uint64_t* out_len);
+
 #ifdef __cplusplus
 }
 #endif

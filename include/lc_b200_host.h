@@ -25,6 +25,11 @@ char* lc_host_processor_process(lc_host_processor_t* p, const char* group_json, 
 char* lc_host_processor_counters(const lc_host_processor_t* p);
 void lc_host_string_free(char* s);
 
+/* SLSEventGroupSerializer::Serialize (core/collection_pipeline/serializer/SLSSerializer.cpp:162-252) of the LOG
+ * group described by group_json; enable_ns = GlobalConfig::mEnableTimestampNanosecond.  Returns the malloc'd wire
+ * bytes (free with lc_host_string_free) and their length, or NULL + *err_out = the reference's error message. */
+char* lc_host_sls_serialize(const char* group_json, int enable_ns, unsigned long long* len_out, char** err_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,7 @@ def lib():
     dl_args = [vp, vp, u64, vp, vp, u64, vp, u32, u8, u32, i32, i32, u32, vp, vp, vp, vp, vp]
     L.lc_delim_parse.argtypes = dl_args
     L.lc_delim_parse_dev.argtypes = dl_args
+    L.lc_sls_serialize_logs.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, u64, C.POINTER(u64)]
     _LIB = L
     return L
 
@@ -234,6 +235,33 @@ class Engine:
         return status, nf, fo, fl, fd
 
     # ---- device-pointer API (ints = device addresses) ---------------------------------------------
+    def sls_serialize_logs(self, events, enable_ns=True):
+        """events: list of (time, ns or None, [(key bytes, value bytes), ...]) -> the LogGroup's `Logs` fields (bytes).
+        Packs the keys and values into one arena the way LogEvent contents alias the SourceBuffer."""
+        arena = bytearray()
+        koff, klen, voff, vlen, begin, times, nss = [], [], [], [], [0], [], []
+        for t, ns, contents in events:
+            for k, v in contents:
+                koff.append(len(arena))
+                klen.append(len(k))
+                arena += k
+                voff.append(len(arena))
+                vlen.append(len(v))
+                arena += v
+            begin.append(len(koff))
+            times.append(int(t) & 0xFFFFFFFF)
+            nss.append(0xFFFFFFFF if (ns is None or not enable_ns) else int(ns))
+        n = len(times)
+        base = np.frombuffer(bytes(arena), np.uint8) if arena else np.zeros(1, np.uint8)
+        a32 = lambda x: np.array(x if x else [0], np.uint32)  # noqa: E731
+        need = C.c_uint64(0)
+        cap = len(arena) + 32 * len(koff) + 16 * n + 64
+        out = np.zeros(max(cap, 1), np.uint8)
+        _check(lib().lc_sls_serialize_logs(self._h, _p(base), len(arena), n, _p(a32(times)), _p(a32(nss)),
+                                           _p(np.array(begin, np.uint64)), _p(a32(koff)), _p(a32(klen)),
+                                           _p(a32(voff)), _p(a32(vlen)), _p(out), cap, C.byref(need)))
+        return bytes(out[:need.value])
+
     def split_lines_dev(self, d_buf, length, split_char, d_off, d_len, cap):
         n = C.c_uint64(0)
         _check(lib().lc_split_lines_dev(self._h, _p(d_buf), length, split_char, _p(d_off), _p(d_len), cap,
@@ -314,3 +342,23 @@ class HostProcessor:
                 lib().lc_host_processor_destroy(self._h)
         except Exception:
             pass
+
+
+def host_sls_serialize(group, enable_ns=False):
+    """SLSEventGroupSerializer::Serialize of the C++ host layer on a JSON event group: (bytes, None) or (None, error)."""
+    import json
+    L = lib()
+    L.lc_host_sls_serialize.restype = C.c_void_p
+    L.lc_host_sls_serialize.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_void_p)]
+    L.lc_host_string_free.argtypes = [C.c_void_p]
+    err = C.c_void_p()
+    n = C.c_ulonglong(0)
+    out = L.lc_host_sls_serialize(json.dumps(group).encode("utf-8"), int(bool(enable_ns)), C.byref(n), C.byref(err))
+    if not out:
+        msg = C.string_at(err.value).decode() if err.value else "unknown error"
+        if err.value:
+            L.lc_host_string_free(err)
+        return None, msg
+    data = C.string_at(out, n.value)
+    L.lc_host_string_free(out)
+    return data, None

@@ -1030,4 +1030,79 @@ int lc_delim_parse(lc_engine_t* e, const uint8_t* base, uint64_t base_len, const
     return LC_OK;
 }
 
+int lc_sls_serialize_logs(lc_engine_t* e, const uint8_t* base, uint64_t base_len, uint64_t n, const uint32_t* ev_time,
+                          const uint32_t* ev_time_ns, const uint64_t* ent_begin, const uint32_t* ent_koff,
+                          const uint32_t* ent_klen, const uint32_t* ent_voff, const uint32_t* ent_vlen, uint8_t* out,
+                          uint64_t out_cap, uint64_t* out_len) {
+    if (!e || !out_len || (n && (!ev_time || !ent_begin)) || (base_len && !base))
+        return fail(LC_ERR_INVALID_ARG, "lc_sls_serialize_logs: bad arguments");
+    *out_len = 0;
+    if (n == 0)
+        return LC_OK;
+    const uint64_t m = ent_begin[n];
+    if (m && (!ent_koff || !ent_klen || !ent_voff || !ent_vlen))
+        return fail(LC_ERR_INVALID_ARG, "lc_sls_serialize_logs: bad arguments");
+    if (base_len >= 0xFFFFFFF0ull || n >= (1ull << 30) || m >= (1ull << 31))
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB, < 2^30 events and < 2^31 contents per call");
+    int rc = bind(e);
+    if (rc)
+        return rc;
+    // workspace: in = arena, ev_off/ev_len = key spans, out_b/out_c = value spans, lines_off/lines_len = time / ns,
+    // pos = ent_begin, lab_sizes / cnt = record / body sizes, lab_off = record offsets, out_d = the wire bytes
+    CU_TRY(e->in.ensure(base_len + 16));
+    CU_TRY(e->ev_off.ensure(m * 4 + 4));
+    CU_TRY(e->ev_len.ensure(m * 4 + 4));
+    CU_TRY(e->out_b.ensure(m * 4 + 4));
+    CU_TRY(e->out_c.ensure(m * 4 + 4));
+    CU_TRY(e->lines_off.ensure(n * 4));
+    CU_TRY(e->lines_len.ensure(n * 4));
+    CU_TRY(e->pos.ensure((n + 1) * 8));
+    CU_TRY(e->lab_sizes.ensure(n * 4));
+    CU_TRY(e->cnt.ensure(n * 4));
+    CU_TRY(e->lab_off.ensure(n * 8));
+    DescPlan plan;
+    rc = prep_desc(e, 0, 0, lck::scan_tiles(n), plan);
+    if (rc)
+        return rc;
+    Small* ds = e->small.as<Small>();
+    Small* hs = (Small*)e->h_small;
+    CU_TRY(cudaMemcpyAsync(e->in.p, base, base_len, cudaMemcpyHostToDevice, e->stream));
+    if (m) {
+        CU_TRY(cudaMemcpyAsync(e->ev_off.p, ent_koff, m * 4, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->ev_len.p, ent_klen, m * 4, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->out_b.p, ent_voff, m * 4, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->out_c.p, ent_vlen, m * 4, cudaMemcpyHostToDevice, e->stream));
+    }
+    CU_TRY(cudaMemcpyAsync(e->lines_off.p, ev_time, n * 4, cudaMemcpyHostToDevice, e->stream));
+    if (ev_time_ns)
+        CU_TRY(cudaMemcpyAsync(e->lines_len.p, ev_time_ns, n * 4, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(e->pos.p, ent_begin, (n + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    const uint32_t* d_ns = ev_time_ns ? e->lines_len.as<uint32_t>() : nullptr;
+    lck::launch_sls_sizes(e->pos.as<uint64_t>(), e->ev_len.as<uint32_t>(), e->out_c.as<uint32_t>(), d_ns, n,
+                          e->lab_sizes.as<uint32_t>(), e->cnt.as<uint32_t>(), e->stream);
+    lck::launch_exclusive_sum(e->lab_sizes.as<uint32_t>(), n, e->lab_off.as<uint64_t>(), &ds->total, plan.r[2],
+                              &ds->tickets[2], e->stream);
+    e->launches += 2;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(&hs->total, &ds->total, 8, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    *out_len = hs->total;
+    if (hs->total > out_cap)
+        return fail(LC_ERR_CAPACITY, "lc_sls_serialize_logs: output capacity too small");
+    if (hs->total == 0)
+        return LC_OK;
+    if (!out)
+        return fail(LC_ERR_INVALID_ARG, "lc_sls_serialize_logs: bad arguments");
+    CU_TRY(e->out_d.ensure(hs->total));
+    lck::launch_sls_emit(e->in.as<uint8_t>(), e->lines_off.as<uint32_t>(), d_ns, e->pos.as<uint64_t>(),
+                         e->ev_off.as<uint32_t>(), e->ev_len.as<uint32_t>(), e->out_b.as<uint32_t>(),
+                         e->out_c.as<uint32_t>(), n, e->lab_off.as<uint64_t>(), e->cnt.as<uint32_t>(),
+                         e->out_d.as<uint8_t>(), e->stream);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, e->out_d.p, hs->total, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return LC_OK;
+}
+
 } // extern "C"

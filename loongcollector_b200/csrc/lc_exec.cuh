@@ -481,3 +481,92 @@ LC_HD bool lc_delim_fsm(const uint8_t* v, int32_t begin, int32_t end, uint8_t se
     push((uint32_t)fs, (uint32_t)(fe - fs), (uint32_t)dq);
     return true;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// SLS wire format of LOG events (next row): the hand-rolled protobuf writer of
+// core/protobuf/sls/LogGroupSerializer.cpp:33-143,232-262 as size and emit functions over spans of the arena.
+//   Log record = 0x0A varint(body) body ; body = 0x08 varint5(max(time, 2^28)) { 0x12 varint(pair) pair }* [0x25 ns:4]
+//   pair       = 0x0A varint(klen) key 0x12 varint(vlen) value
+LC_HD uint32_t lc_varint_size(uint32_t v) { return v < (1u << 7) ? 1 : v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5; }
+
+LC_HD uint32_t lc_put_varint(uint8_t* p, uint32_t v) {
+    uint32_t n = 0;
+    while (v >= 0x80u) {
+        p[n++] = (uint8_t)(v | 0x80u);
+        v >>= 7;
+    }
+    p[n++] = (uint8_t)v;
+    return n;
+}
+
+// GetLogContentSize (:232-237) without the tag + length prefix
+LC_HD uint32_t lc_sls_pair_inner(uint32_t klen, uint32_t vlen) {
+    return 1 + lc_varint_size(klen) + klen + 1 + lc_varint_size(vlen) + vlen;
+}
+
+// GetLogSize (:239-253): body = size inside the Logs field, return = with tag and length prefix; 0 entries -> 0, 0
+LC_HD uint32_t lc_sls_log_size(const uint32_t* klen, const uint32_t* vlen, uint64_t e0, uint64_t e1, bool has_ns,
+                               uint32_t* body_out) {
+    if (e0 == e1) {
+        *body_out = 0;
+        return 0;
+    }
+    uint32_t body = 1 + 5 + (has_ns ? 1 + 4 : 0);
+    for (uint64_t k = e0; k < e1; ++k) {
+        const uint32_t in = lc_sls_pair_inner(klen[k], vlen[k]);
+        body += 1 + lc_varint_size(in) + in;
+    }
+    *body_out = body;
+    return 1 + lc_varint_size(body) + body;
+}
+
+// Writes one Log record at `out` (which has room for lc_sls_log_size bytes).  Called by all `nlanes` cooperating
+// lanes with identical arguments except `lane`: lane 0 writes the tags / lengths, every lane copies its share of the
+// key and value bytes.
+LC_HD void lc_sls_emit_log(uint8_t* out, const uint8_t* base, uint32_t time, bool has_ns, uint32_t ns,
+                           const uint32_t* koff, const uint32_t* klen, const uint32_t* voff, const uint32_t* vlen,
+                           uint64_t e0, uint64_t e1, uint32_t body, uint32_t lane, uint32_t nlanes) {
+    uint32_t at = 0;
+    uint8_t hdr[16];
+    uint32_t h = 0;
+    hdr[h++] = 0x0A;
+    h += lc_put_varint(hdr + h, body);
+    hdr[h++] = 0x08;
+    h += lc_put_varint(hdr + h, time < (1u << 28) ? (1u << 28) : time); // always 5 bytes
+    if (lane == 0)
+        for (uint32_t j = 0; j < h; ++j)
+            out[j] = hdr[j];
+    at = h;
+    for (uint64_t k = e0; k < e1; ++k) {
+        const uint32_t kl = klen[k], vl = vlen[k];
+        h = 0;
+        hdr[h++] = 0x12;
+        h += lc_put_varint(hdr + h, lc_sls_pair_inner(kl, vl));
+        hdr[h++] = 0x0A;
+        h += lc_put_varint(hdr + h, kl);
+        if (lane == 0)
+            for (uint32_t j = 0; j < h; ++j)
+                out[at + j] = hdr[j];
+        at += h;
+        for (uint32_t j = lane; j < kl; j += nlanes)
+            out[at + j] = base[koff[k] + j];
+        at += kl;
+        h = 0;
+        hdr[h++] = 0x12;
+        h += lc_put_varint(hdr + h, vl);
+        if (lane == 0)
+            for (uint32_t j = 0; j < h; ++j)
+                out[at + j] = hdr[j];
+        at += h;
+        for (uint32_t j = lane; j < vl; j += nlanes)
+            out[at + j] = base[voff[k] + j];
+        at += vl;
+    }
+    if (has_ns && lane == 0) {
+        out[at] = 0x25;
+        out[at + 1] = (uint8_t)ns;
+        out[at + 2] = (uint8_t)(ns >> 8);
+        out[at + 3] = (uint8_t)(ns >> 16);
+        out[at + 4] = (uint8_t)(ns >> 24);
+    }
+}

@@ -2302,4 +2302,56 @@ void launch_delim(const DelimConfig& cfg, const uint8_t* d_base, const uint32_t*
     }
 }
 
+// ================================================================================================ SLS serialise
+// Next row: the `Logs` fields of an sls_logs::LogGroup written straight from spans of the
+// arena (lc_exec.cuh: lc_sls_log_size / lc_sls_emit_log).  sizes -> exclusive_sum_kernel -> emit.
+__global__ void __launch_bounds__(256)
+    sls_size_kernel(const uint64_t* __restrict__ ent_begin, const uint32_t* __restrict__ klen,
+                    const uint32_t* __restrict__ vlen, const uint32_t* __restrict__ ev_ns, uint64_t n,
+                    uint32_t* __restrict__ rec_size, uint32_t* __restrict__ body_size) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    uint32_t body;
+    rec_size[i] = lc_sls_log_size(klen, vlen, ent_begin[i], ent_begin[i + 1], ev_ns && ev_ns[i] != 0xFFFFFFFFu, &body);
+    body_size[i] = body;
+}
+
+// one warp per event: lane 0 writes tags and lengths, all lanes copy the key / value bytes
+__global__ void __launch_bounds__(256)
+    sls_emit_kernel(const uint8_t* __restrict__ base, const uint32_t* __restrict__ ev_time,
+                    const uint32_t* __restrict__ ev_ns, const uint64_t* __restrict__ ent_begin,
+                    const uint32_t* __restrict__ koff, const uint32_t* __restrict__ klen,
+                    const uint32_t* __restrict__ voff, const uint32_t* __restrict__ vlen, uint64_t n,
+                    const uint64_t* __restrict__ rec_off, const uint32_t* __restrict__ body_size,
+                    uint8_t* __restrict__ out) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n)
+        return;
+    const uint64_t e0 = ent_begin[i], e1 = ent_begin[i + 1];
+    if (e0 == e1)
+        return; // LogEvent::Empty: skipped (SLSSerializer.cpp:383-385)
+    const bool has_ns = ev_ns && ev_ns[i] != 0xFFFFFFFFu;
+    lc_sls_emit_log(out + rec_off[i], base, ev_time[i], has_ns, has_ns ? ev_ns[i] : 0u, koff, klen, voff, vlen, e0, e1,
+                    body_size[i], threadIdx.x & 31, 32);
+}
+
+void launch_sls_sizes(const uint64_t* d_ent_begin, const uint32_t* d_klen, const uint32_t* d_vlen,
+                      const uint32_t* d_ev_ns, uint64_t n, uint32_t* d_rec_size, uint32_t* d_body_size,
+                      cudaStream_t st) {
+    if (n)
+        sls_size_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ent_begin, d_klen, d_vlen, d_ev_ns, n,
+                                                                     d_rec_size, d_body_size);
+}
+
+void launch_sls_emit(const uint8_t* d_base, const uint32_t* d_ev_time, const uint32_t* d_ev_ns,
+                     const uint64_t* d_ent_begin, const uint32_t* d_koff, const uint32_t* d_klen,
+                     const uint32_t* d_voff, const uint32_t* d_vlen, uint64_t n, const uint64_t* d_rec_off,
+                     const uint32_t* d_body_size, uint8_t* d_out, cudaStream_t st) {
+    if (n)
+        sls_emit_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d_base, d_ev_time, d_ev_ns, d_ent_begin,
+                                                                          d_koff, d_klen, d_voff, d_vlen, n, d_rec_off,
+                                                                          d_body_size, d_out);
+}
+
 } // namespace lck

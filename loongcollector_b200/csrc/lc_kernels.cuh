@@ -144,4 +144,14 @@ void launch_delim(const DelimConfig& cfg, const uint8_t* d_base, const uint32_t*
                   uint64_t n, uint8_t* d_status, uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len,
                   uint32_t* d_f_dq, cudaStream_t st);
 
+// next row (rank 4): SLS wire format of LOG events.  ev_ns may be null; 0xFFFFFFFF = no nanosecond part.
+// rec_size[i] = bytes of event i's Log record (0 = empty event, skipped); body_size[i] = bytes inside its Logs field.
+void launch_sls_sizes(const uint64_t* d_ent_begin, const uint32_t* d_klen, const uint32_t* d_vlen,
+                      const uint32_t* d_ev_ns, uint64_t n, uint32_t* d_rec_size, uint32_t* d_body_size,
+                      cudaStream_t st);
+void launch_sls_emit(const uint8_t* d_base, const uint32_t* d_ev_time, const uint32_t* d_ev_ns,
+                     const uint64_t* d_ent_begin, const uint32_t* d_koff, const uint32_t* d_klen,
+                     const uint32_t* d_voff, const uint32_t* d_vlen, uint64_t n, const uint64_t* d_rec_off,
+                     const uint32_t* d_body_size, uint8_t* d_out, cudaStream_t st);
+
 } // namespace lck

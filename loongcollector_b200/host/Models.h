@@ -245,6 +245,7 @@ public:
     void DelMetadata(EventGroupMetaKey key) { mMetadata.erase(key); }
     const GroupMetadata& GetAllMetadata() const { return mMetadata; }
     void SetTag(const std::string& key, const std::string& val);
+    const std::map<StringView, StringView>& GetTags() const { return mTags; }
 
     Json::Value ToJson(bool enableEventMeta = false) const;
     bool FromJson(const Json::Value& root);

@@ -1238,6 +1238,134 @@ void ProcessorMergeMultilineLogNative::MergeLogsByRegex(PipelineEventGroup& grou
     sourceEvents.resize(kept);
 }
 
+// ------------------------------------------------------------------------------------------------ SLS serialise
+namespace {
+void PutVarint(std::string& out, uint32_t v) {
+    while (v >= 0x80u) {
+        out.push_back((char)(v | 0x80u));
+        v >>= 7;
+    }
+    out.push_back((char)v);
+}
+void PutString(std::string& out, StringView s) {
+    PutVarint(out, (uint32_t)s.size());
+    out.append(s.data(), s.size());
+}
+} // namespace
+
+bool SLSEventGroupSerializer::Serialize(PipelineEventGroup& group, std::string& res, std::string& errorMsg) const {
+    const EventsContainer& events = group.GetEvents();
+    if (events.empty()) {
+        errorMsg = "empty event group";
+        return false;
+    }
+    if (!events[0].Is<LogEvent>()) {
+        errorMsg = "unsupported event type in event group"; // metric / span / raw groups: not built yet
+        return false;
+    }
+    // flatten the contents of every event into entry tables over the arena
+    const size_t n = events.size();
+    std::vector<uint32_t> evTime(n), evNs(n, LC_SLS_NO_NS);
+    std::vector<uint64_t> entBegin(n + 1, 0);
+    std::vector<const char*> kPtr, vPtr;
+    std::vector<uint32_t> kLen, vLen;
+    for (size_t i = 0; i < n; ++i) {
+        const LogEvent& e = events[i].Cast<LogEvent>();
+        evTime[i] = (uint32_t)e.GetTimestamp();
+        if (mEnableTimestampNanosecond && e.GetTimestampNanosecond())
+            evNs[i] = e.GetTimestampNanosecond().value();
+        for (auto& c : e.RawContents()) {
+            if (!c.second)
+                continue;
+            kPtr.push_back(c.first.first.data());
+            kLen.push_back((uint32_t)c.first.first.size());
+            vPtr.push_back(c.first.second.data());
+            vLen.push_back((uint32_t)c.first.second.size());
+        }
+        entBegin[i + 1] = kPtr.size();
+    }
+    const size_t m = kPtr.size();
+    if (m == 0) {
+        errorMsg = "all empty logs";
+        return false;
+    }
+    // one span of the arena if all keys and values live in the same chunk, else a packed copy
+    const char* lo = kPtr[0];
+    const char* hi = kPtr[0] + kLen[0];
+    for (size_t k = 0; k < m; ++k) {
+        lo = std::min(lo, std::min(kPtr[k], vPtr[k]));
+        hi = std::max(hi, std::max(kPtr[k] + kLen[k], vPtr[k] + vLen[k]));
+    }
+    std::vector<uint32_t> kOff(m), vOff(m);
+    std::vector<uint8_t> packed;
+    const uint8_t* base;
+    uint64_t baseLen;
+    size_t chunkSize = 0;
+    if ((uint64_t)(hi - lo) < 0xFFFFFFF0ull && group.GetSourceBuffer()->ChunkContaining(lo, (size_t)(hi - lo), &chunkSize)) {
+        base = reinterpret_cast<const uint8_t*>(lo);
+        baseLen = (uint64_t)(hi - lo);
+        for (size_t k = 0; k < m; ++k) {
+            kOff[k] = (uint32_t)(kPtr[k] - lo);
+            vOff[k] = (uint32_t)(vPtr[k] - lo);
+        }
+    } else {
+        size_t total = 0;
+        for (size_t k = 0; k < m; ++k)
+            total += (size_t)kLen[k] + vLen[k];
+        packed.resize(total + 1);
+        size_t at = 0;
+        for (size_t k = 0; k < m; ++k) {
+            kOff[k] = (uint32_t)at;
+            memcpy(packed.data() + at, kPtr[k], kLen[k]);
+            at += kLen[k];
+            vOff[k] = (uint32_t)at;
+            memcpy(packed.data() + at, vPtr[k], vLen[k]);
+            at += vLen[k];
+        }
+        base = packed.data();
+        baseLen = total;
+    }
+    // group-level fields in tag (map) order, :203-213,239-249
+    std::string tail;
+    for (auto& tag : group.GetTags()) {
+        if (tag.first == StringView("__topic__")) {
+            tail.push_back(0x1A);
+            PutString(tail, tag.second);
+        } else if (tag.first == StringView("__source__")) {
+            tail.push_back(0x22);
+            PutString(tail, tag.second);
+        } else if (tag.first == StringView("__machine_uuid__")) {
+            tail.push_back(0x2A);
+            PutString(tail, tag.second);
+        } else {
+            std::string inner;
+            inner.push_back(0x0A);
+            PutString(inner, tag.first);
+            inner.push_back(0x12);
+            PutString(inner, tag.second);
+            tail.push_back(0x32);
+            PutVarint(tail, (uint32_t)inner.size());
+            tail += inner;
+        }
+    }
+    uint64_t need = 0;
+    int rc = lc_sls_serialize_logs(Engine(), base, baseLen, n, evTime.data(), evNs.data(), entBegin.data(), kOff.data(),
+                                   kLen.data(), vOff.data(), vLen.data(), nullptr, 0, &need);
+    if (rc != LC_OK && rc != LC_ERR_CAPACITY)
+        Check(rc, "lc_sls_serialize_logs");
+    if ((int64_t)(need + tail.size()) > (int64_t)mMaxSendLogGroupSize) {
+        errorMsg = "log group exceeds size limit\tgroup size: " + ToString(need + tail.size())
+                   + "\tsize limit: " + ToString((uint64_t)mMaxSendLogGroupSize);
+        return false;
+    }
+    res.resize(need);
+    Check(lc_sls_serialize_logs(Engine(), base, baseLen, n, evTime.data(), evNs.data(), entBegin.data(), kOff.data(),
+                                kLen.data(), vOff.data(), vLen.data(), reinterpret_cast<uint8_t*>(&res[0]), need, &need),
+          "lc_sls_serialize_logs");
+    res += tail;
+    return true;
+}
+
 Processor* CreateProcessor(const std::string& type) {
     if (type == ProcessorMergeMultilineLogNative::sName)
         return new ProcessorMergeMultilineLogNative;

@@ -231,6 +231,17 @@ private:
     bool mHasStart = false, mHasContinue = false, mHasEnd = false;
 };
 
+// Fourth "next" row: the SLS wire format of a group of LOG events.  Mirrors
+// SLSEventGroupSerializer::Serialize (core/collection_pipeline/serializer/SLSSerializer.cpp:162-252): the `Logs`
+// fields -- all the bytes that scale with the data -- are written on the GPU straight from the arena spans of the
+// events' contents (lc_sls_serialize_logs); Topic / Source / MachineUUID / LogTags are appended here.
+class SLSEventGroupSerializer {
+public:
+    bool mEnableTimestampNanosecond = false;      // GlobalConfig::mEnableTimestampNanosecond
+    int32_t mMaxSendLogGroupSize = 10 * 1024 * 1024; // flag max_send_log_group_size (FlusherSLS.cpp:61)
+    bool Serialize(PipelineEventGroup& group, std::string& res, std::string& errorMsg) const;
+};
+
 // Factory by plugin type name (the names the reference registers, PluginRegistry.cpp:183-200).
 Processor* CreateProcessor(const std::string& type);
 

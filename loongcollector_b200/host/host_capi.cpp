@@ -83,4 +83,38 @@ char* lc_host_processor_counters(const lc_host_processor_t* p) {
 }
 
 void lc_host_string_free(char* s) { free(s); }
+
+char* lc_host_sls_serialize(const char* group_json, int enable_ns, unsigned long long* len_out, char** err_out) {
+    if (err_out)
+        *err_out = nullptr;
+    if (len_out)
+        *len_out = 0;
+    try {
+        PipelineEventGroup group(std::make_shared<SourceBuffer>());
+        if (group_json && strcmp(group_json, "null") != 0 && !group.FromJsonString(group_json)) {
+            if (err_out)
+                *err_out = dup("group is not valid JSON");
+            return nullptr;
+        }
+        SLSEventGroupSerializer ser;
+        ser.mEnableTimestampNanosecond = enable_ns != 0;
+        std::string res, err;
+        if (!ser.Serialize(group, res, err)) {
+            if (err_out)
+                *err_out = dup(err);
+            return nullptr;
+        }
+        char* p = (char*)malloc(res.size() + 1);
+        memcpy(p, res.data(), res.size());
+        p[res.size()] = 0;
+        if (len_out)
+            *len_out = res.size();
+        return p;
+    } catch (const std::exception& e) {
+        if (err_out)
+            *err_out = dup(std::string("Serialize threw: ") + e.what());
+        return nullptr;
+    }
+}
+
 }

@@ -42,6 +42,8 @@ def lib():
         L.emul_delim_fsm.restype = C.c_int64
         L.emul_delim_fsm.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint8, C.c_uint8, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64]
+        L.emul_sls_serialize_logs.restype = C.c_uint64
+        L.emul_sls_serialize_logs.argtypes = [C.c_void_p] + [C.c_uint64] + [C.c_void_p] * 8 + [C.c_uint64]
         L.emul_fast2_bytes.restype = C.c_uint32
         L.emul_fast2_bytes.argtypes = [C.c_void_p]
         L.emul_fast_bytes.restype = C.c_uint32
@@ -136,3 +138,29 @@ def delim_fsm(buf: np.ndarray, line_off: int, begin: int, end: int, sep: int, qu
         return None
     k = min(int(n), cap)
     return int(n), list(zip(fo[:k].tolist(), fl[:k].tolist(), fd[:k].tolist()))
+
+
+def sls_serialize_logs(events, enable_ns=True):
+    """Host build of the kernels' SLS size / emit functions; same packing as capi.Engine.sls_serialize_logs."""
+    arena = bytearray()
+    koff, klen, voff, vlen, begin, times, nss = [], [], [], [], [0], [], []
+    for t, ns, contents in events:
+        for k, v in contents:
+            koff.append(len(arena))
+            klen.append(len(k))
+            arena += k
+            voff.append(len(arena))
+            vlen.append(len(v))
+            arena += v
+        begin.append(len(koff))
+        times.append(int(t) & 0xFFFFFFFF)
+        nss.append(0xFFFFFFFF if (ns is None or not enable_ns) else int(ns))
+    base = np.frombuffer(bytes(arena), np.uint8) if arena else np.zeros(1, np.uint8)
+    a32 = lambda x: np.array(x if x else [0], np.uint32)  # noqa: E731
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    arrs = [a32(times), a32(nss), np.array(begin, np.uint64), a32(koff), a32(klen), a32(voff), a32(vlen)]
+    cap = len(arena) + 32 * len(koff) + 16 * len(times) + 64
+    out = np.zeros(cap, np.uint8)
+    total = lib().emul_sls_serialize_logs(p(base), len(times), *[p(a) for a in arrs], p(out), cap)
+    assert total <= cap
+    return bytes(out[:total])

@@ -144,3 +144,31 @@ int64_t emul_delim_fsm(const uint8_t* line, int32_t begin, int32_t end, uint8_t 
     return lc_delim_fsm(line, begin, end, sep, quote, push) ? n : -1;
 }
 }
+
+extern "C" {
+// SLS wire format, host build of the kernels' size / emit functions (lc_exec.cuh), one "lane".  Returns the total
+// size; writes when out_cap suffices.  Same contract as lc_sls_serialize_logs.
+uint64_t emul_sls_serialize_logs(const uint8_t* base, uint64_t n, const uint32_t* ev_time, const uint32_t* ev_ns,
+                                 const uint64_t* ent_begin, const uint32_t* koff, const uint32_t* klen,
+                                 const uint32_t* voff, const uint32_t* vlen, uint8_t* out, uint64_t out_cap) {
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t body;
+        total += lc_sls_log_size(klen, vlen, ent_begin[i], ent_begin[i + 1], ev_ns && ev_ns[i] != 0xFFFFFFFFu, &body);
+    }
+    if (total > out_cap)
+        return total;
+    uint64_t at = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t body;
+        const bool has_ns = ev_ns && ev_ns[i] != 0xFFFFFFFFu;
+        const uint32_t sz = lc_sls_log_size(klen, vlen, ent_begin[i], ent_begin[i + 1], has_ns, &body);
+        if (!sz)
+            continue;
+        lc_sls_emit_log(out + at, base, ev_time[i], has_ns, has_ns ? ev_ns[i] : 0u, koff, klen, voff, vlen,
+                        ent_begin[i], ent_begin[i + 1], body, 0, 1);
+        at += sz;
+    }
+    return total;
+}
+}

@@ -109,3 +109,26 @@ def test_logs_are_byte_identical_to_protobuf_runtime():
         got, offs = orc.sls_serialize_logs(events, enable_ns=True)
         assert got == m.SerializeToString()
         assert len(offs) == len(m.Logs) and all(got[o] == 0x0A for o in offs)
+
+
+def _random_events(rng, n_max=40):
+    events = []
+    for _ in range(rng.randint(0, n_max)):
+        t = rng.choice([0, 5, (1 << 28) - 1, 1 << 28, 1234567890, 0xFFFFFFFF])
+        ns = rng.choice([None, 0, 1, 999999999])
+        contents = [(bytes(rng.randrange(256) for _ in range(rng.choice([0, 1, 7, 127, 128, 300]))),
+                     bytes(rng.randrange(256) for _ in range(rng.choice([0, 3, 127, 128, 200, 17000]))))
+                    for _ in range(rng.choice([0, 0, 1, 2, 6, 11]))]
+        events.append((t, ns, contents))
+    return events
+
+
+def test_kernel_size_and_emit_functions_on_the_host():
+    """csrc/lc_exec.cuh: lc_sls_log_size / lc_sls_emit_log (the arithmetic of the sls kernels) compiled for the host."""
+    from tests.emul import emul
+    rng = random.Random(7)
+    for _ in range(200):
+        events = _random_events(rng)
+        for enable_ns in (True, False):
+            want, _ = orc.sls_serialize_logs(events, enable_ns)
+            assert emul.sls_serialize_logs(events, enable_ns) == want
