@@ -250,3 +250,74 @@ def test_tdfa_layout_on_benchmark_patterns_and_corners():
         for s in inputs:
             for mis in (0, 1):
                 assert e.full_match_tdfa(s, mis) == o.full_match(s), (pat, s, mis)
+
+
+def _tdfa_blob(e):
+    import ctypes as C
+    import struct
+
+    import numpy as np
+    from tests.emul.emul import lib
+    L = lib()
+    L.emul_tdfa_blob.restype = C.c_uint32
+    L.emul_tdfa_blob.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    n = L.emul_tdfa_blob(e._h, None, 0)
+    if not n:
+        return None, None
+    buf = np.zeros(n, np.uint8)
+    L.emul_tdfa_blob(e._h, buf.ctypes.data_as(C.c_void_p), n)
+    b = buf.tobytes()
+    names = ("magic total ngroups nstates ncls nregs start row_bytes off_cls off_t2 off_t1 off_eof off_ops has_slow "
+             "max_threads sink").split()
+    return dict(zip(names, struct.unpack("<16I", b[:64]))), b
+
+
+def test_tdfa_table_invariants_the_kernel_relies_on():
+    """Structural facts the staged kernel assumes about every single-pass blob (lc_tables.h: LcTdfaHeader): rows fit
+    16-bit offsets even after rebasing, the row pitch is an odd word count, the dead row and the sink row absorb, every
+    entry points at a row start, register fields name existing registers, slow entries lead to the sink, and the
+    op lists stay inside the pool."""
+    import numpy as np
+    rng = random.Random(31)
+    seen = slow = 0
+    pats = [gen(rng) for _ in range(500)] + [r"(\w+) (\d+)", r'"([^"]*)" "([^"]*)"', r"(?:(a)|(b)|(c))*x"]
+    from loongcollector_b200 import synth
+    pats += [synth.NGINX_PATTERN, synth.APACHE_PATTERN, synth.JAVA_START_PATTERN, synth.CSV_URL_PATTERN]
+    for pat in pats:
+        e = EmulRegex(pat)
+        if not e.supported:
+            continue
+        h, b = _tdfa_blob(e)
+        if h is None:
+            continue
+        seen += 1
+        ns, ncl, rb = h["nstates"], h["ncls"], h["row_bytes"]
+        assert h["magic"] == 0x4C435444 and h["total"] == len(b) and h["sink"] == ns and h["start"] == 1
+        assert rb == ((ncl * ncl) | 1) * 4 and (rb // 4) % 2 == 1
+        assert (ns + 2) * rb + 2048 <= 65535 and h["nregs"] <= 62 and h["nregs"] >= 2 * h["ngroups"]
+        t2 = np.frombuffer(b[h["off_t2"]:h["off_t2"] + (ns + 1) * rb], np.uint32).reshape(ns + 1, rb // 4)
+        used = t2[:, :ncl * ncl]
+        nxt = used & 0xFFFF
+        assert np.all(nxt % rb == 0) and np.all(nxt // rb <= ns)
+        assert np.all(t2[0] == 0)                                       # dead row absorbs, no actions
+        assert np.all(used[ns] == (ns * rb | 0x00800000))               # sink row absorbs
+        is_slow = (used & 0x00800000) != 0
+        assert np.all((nxt[is_slow] // rb) == ns)                       # slow entries lead to the sink ...
+        assert np.all((used[is_slow] & 0x7F7F0000) == 0)                # ... and carry no register fields
+        assert bool(is_slow[:ns].any()) == bool(h["has_slow"])
+        slow += int(h["has_slow"])
+        for shift in (16, 24):
+            f = (used[:ns] >> shift) & 0x7F
+            f = f[(f != 0) & ~is_slow[:ns]]
+            assert np.all(f % 2 == 0) and np.all((f - 2) // 2 < h["nregs"])
+        t1 = np.frombuffer(b[h["off_t1"]:h["off_t1"] + ns * ncl * 4], np.uint32)
+        ops = np.frombuffer(b[h["off_ops"]:], np.uint16)
+        eof = np.frombuffer(b[h["off_eof"]:h["off_eof"] + ns * 4], np.uint32)
+        assert np.all((t1 & 0xFFFF) < ns)
+        for lst in list(t1 >> 16) + [x for x in eof if x != 0xFFFFFFFF]:
+            lst = int(lst)
+            assert lst < ops.size and lst + 1 + int(ops[lst]) <= ops.size
+            for op in ops[lst + 1:lst + 1 + int(ops[lst])]:
+                dst, src = int(op) >> 8, int(op) & 0xFF
+                assert dst < h["nregs"] and (src in (0xFF, 0xFE) or src < h["nregs"])
+    assert seen > 100 and slow > 5
