@@ -40,8 +40,8 @@ LINE_BYTES = 256
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lines", type=int, default=LINES_PER_GPU, help="lines per GPU (default: the C2 size)")
     ap.add_argument("--cpu-sample-lines", type=int, default=131072)
