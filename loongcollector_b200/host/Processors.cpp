@@ -1057,46 +1057,48 @@ void ProcessorMergeMultilineLogNative::HandleUnmatchLogs(EventsContainer& logEve
         logEvents[newSize++] = std::move(logEvents[i]);
 }
 
-// :116-159
+// :116-159.  A record is a run of parts: every part but the last carries the "P" content (the container runtime's
+// partial-line marker); a part without it completes the run, and so does the end of the group.  The first part loses
+// its marker, the joined value lands in the first part, and the output slot takes the event that FOLLOWS the previous
+// record (an empty event there survives in place of the joined one -- the reference's behaviour, kept).
 void ProcessorMergeMultilineLogNative::MergeLogsByFlag(PipelineEventGroup& group) {
-    EventsContainer& sourceEvents = group.MutableEvents();
-    size_t size = 0, begin = 0;
-    std::vector<LogEvent*> events;
-    bool isPartialLog = false;
-    for (size_t cur = 0; cur < sourceEvents.size(); ++cur) {
-        if (!IsSupportedEvent(sourceEvents[cur])) {
-            if (events.empty())
-                begin = cur;
-            for (size_t i = begin; i < sourceEvents.size(); ++i)
-                sourceEvents[size++] = std::move(sourceEvents[i]);
-            sourceEvents.resize(size);
+    EventsContainer& all = group.MutableEvents();
+    const size_t n = all.size();
+    size_t kept = 0;  // events written back so far
+    size_t head = 0;  // index right after the previous record
+    bool open = false; // the previous part carried the marker
+    std::vector<LogEvent*> parts;
+    auto Complete = [&](size_t next) {
+        MergeEvents(group, parts, false);
+        all[kept++] = std::move(all[head]);
+        head = next;
+        open = false;
+    };
+    for (size_t cur = 0; cur < n; ++cur) {
+        if (!IsSupportedEvent(all[cur])) {
+            // ends the walk: the open run (or, without one, everything from here) is kept as it is
+            if (parts.empty())
+                head = cur;
+            for (size_t i = head; i < n; ++i)
+                all[kept++] = std::move(all[i]);
+            all.resize(kept);
             return;
         }
-        LogEvent* sourceEvent = &sourceEvents[cur].Cast<LogEvent>();
-        if (sourceEvent->Empty())
+        LogEvent* part = &all[cur].Cast<LogEvent>();
+        if (part->Empty())
             continue;
-        events.emplace_back(sourceEvent);
-        if (isPartialLog) {
-            if (!sourceEvent->HasContent(PartLogFlag)) {
-                MergeEvents(group, events, false);
-                sourceEvents[size++] = std::move(sourceEvents[begin]);
-                begin = cur + 1;
-                isPartialLog = false;
-            }
-        } else if (sourceEvent->HasContent(PartLogFlag)) {
-            sourceEvent->DelContent(PartLogFlag);
-            isPartialLog = true;
-        } else {
-            MergeEvents(group, events, false);
-            sourceEvents[size++] = std::move(sourceEvents[begin]);
-            begin = cur + 1;
+        parts.push_back(part);
+        const bool marked = part->HasContent(PartLogFlag);
+        if (!marked) {
+            Complete(cur + 1);
+        } else if (!open) {
+            part->DelContent(PartLogFlag);
+            open = true;
         }
     }
-    if (isPartialLog) {
-        MergeEvents(group, events, false);
-        sourceEvents[size++] = std::move(sourceEvents[begin]);
-    }
-    sourceEvents.resize(size);
+    if (open)
+        Complete(n);
+    all.resize(kept);
 }
 
 // :161-318.  BoostRegexSearch(match_continuous) of every (event, pattern) pair is a pure function of the value, so all
