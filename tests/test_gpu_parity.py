@@ -580,3 +580,19 @@ def test_regex_every_length_at_every_alignment(eng):
         assert np.array_equal(co.cpu().numpy().view(np.uint32).reshape(n, G), eco), pattern
         assert np.array_equal(cl.cpu().numpy().view(np.uint32).reshape(n, G), ecl), pattern
         assert 0 < int((est == 0).sum()) < n, pattern  # both verdicts occur
+
+
+def test_regex_assertions_inside_the_pattern(eng):
+    """Word boundaries and line anchors in the middle of a pattern: the single-pass tables carry the kind of the
+    previous byte in the state (no kernel-side context logic), values contain embedded line separators."""
+    rng = random.Random(77)
+    patterns = [r"(\w+)\b.(\w+)\b(.*)", r"(.*)\bat\b(.*)", r"(a+)$.^(b+)(.*)", r"(\S+)$\s^(\S+)(?:$\s^(\S+))?",
+                r"^(\w+) (\w+)$", r"(.*?)\b(\d+)\b(.*)"]
+    # (no \\r: boost treats \\r\\n as one separator, the PCRE2 oracle does not -- tests/test_regex_compiler_cpu.py pins that
+    #  corner on the CPU tier; a trailing separator is avoided for the mid-pattern '^' corner described there)
+    alpha = "ab at 12\n_-"
+    lines = [b"ab cd ef", b"x at y", b"aa\nbb tail", b"w1\nw2\nw3", b"foo 12 bar", b"at", b""]
+    for _ in range(3000):
+        lines.append("".join(rng.choice(alpha) for _ in range(rng.randint(0, 40))).encode().rstrip(b"\n"))
+    for pattern in patterns:
+        _check_parse(eng, pattern, lines)
