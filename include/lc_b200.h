@@ -10,9 +10,13 @@
  * Conventions
  *  - "base" is the contiguous SourceBuffer allocation holding the group's bytes
  *    (core/common/memory/SourceBuffer.h:98-131,156-181); every offset is u32 relative to base.
- *  - Host-pointer entry points (no suffix) copy base + the event table to the GPU, run the kernels and
- *    copy the results back before returning.  *_dev entry points take DEVICE pointers and a CUDA stream
- *    and never touch host memory (used when the arena is already resident in HBM).
+ *  - Host-pointer entry points (no suffix) validate the event table against base_len (LC_ERR_INVALID_ARG), copy
+ *    base + the event table to the GPU, run the kernels and copy the results back before returning.
+ *    *_dev entry points take DEVICE pointers (arena already resident in HBM) and queue their kernels on the
+ *    engine's current stream -- lc_engine_stream(), replaceable with lc_engine_set_stream().  The regex / delimiter
+ *    *_dev calls never wait for the device (results are valid once the stream has drained: lc_engine_sync or the
+ *    caller's own event); the split / multiline *_dev calls return a count and therefore synchronise.  *_dev
+ *    callers guarantee ev_off[i] + ev_len[i] <= base_len (device tables are not re-read on the host).
  *  - One lc_engine per (GPU, host thread): mirrors the reference's per-thread regex copies
  *    (ProcessorParseRegexNative.cpp:64-67,255-257).  An engine is not thread-safe; regexes are immutable
  *    after compilation and may be shared between engines.
@@ -65,8 +69,11 @@ int lc_engine_create(int device, lc_engine_t** out);
 void lc_engine_destroy(lc_engine_t* e);
 /* Blocks until all work queued on the engine's stream is complete. */
 int lc_engine_sync(lc_engine_t* e);
-/* CUDA stream (cudaStream_t) owned by the engine, for callers that enqueue their own work. */
+/* CUDA stream (cudaStream_t) the engine queues its work on, for callers that enqueue their own work. */
 void* lc_engine_stream(lc_engine_t* e);
+/* Makes the engine queue on the caller's stream (cudaStream_t; NULL = back to the engine's own).  Drains the
+ * previous stream first: the engine's workspace is re-used from call to call and ordered by the stream. */
+int lc_engine_set_stream(lc_engine_t* e, void* stream);
 /* Number of kernel launches issued by this engine so far (bench.py's gpu_launches). */
 uint64_t lc_engine_launch_count(const lc_engine_t* e);
 /* Pinned host memory helpers (a SourceBuffer arena allocated here is DMA-able without staging). */
@@ -104,6 +111,34 @@ int lc_regex_parse(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, ui
 int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
                        const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
                        uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len);
+
+/* Same, with the event table read in place from a strided table: event i = (d_ev_off[i * ev_stride],
+ * d_ev_len[i * ev_stride]).  Lets one processor's output feed the next without a gather -- e.g. column k of
+ * lc_delim_parse_dev's [n][max_fields] tables (d_f_off + k, d_f_len + k, stride max_fields) is the event table of
+ * the regex that parses that column (the delimiter -> regex chain of a pipeline, BASELINE config C4). */
+int lc_regex_parse_strided_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
+                               const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint32_t ev_stride, uint64_t n,
+                               uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len);
+
+/* Several patterns evaluated in ONE grid (BASELINE config C5 "multi-pattern"; north_star: "evaluate every log line
+ * in the batch in one grid").  The reference runs one ProcessorParseRegexNative per pattern, each holding its own
+ * boost::regex (ProcessorParseRegexNative.cpp:64-67), and a line parsed by pattern p sees exactly RegexLogLineParser
+ * of that instance (:186-253).  Here all automata are resident in shared memory together and every line is tried on
+ * the patterns in array order until one matches (== regex_match of `(?:p0)|(?:p1)|...`, groups numbered per
+ * pattern); with sel != NULL line i is tried on pattern sel[i] only (LC_MULTI_ANY = on all, in order).
+ * which[i] = index of the pattern that matched or LC_MULTI_NONE; status[i] as LC_REGEX_* for that pattern's nkeys;
+ * rows of cap_off / cap_len are [n][row_pitch] (row_pitch >= the largest group count), columns beyond the matching
+ * pattern's groups and rows of unmatched lines are zero.  1..8 patterns. */
+#define LC_MULTI_NONE 0xFFu
+#define LC_MULTI_ANY 0xFFu
+int lc_regex_parse_multi(lc_engine_t* e, const lc_regex_t* const* res, uint32_t npat, const uint32_t* nkeys,
+                         const uint8_t* base, uint64_t base_len, const uint32_t* ev_off, const uint32_t* ev_len,
+                         uint64_t n, const uint8_t* sel, uint8_t* which, uint8_t* status, uint32_t row_pitch,
+                         uint32_t* cap_off, uint32_t* cap_len);
+int lc_regex_parse_multi_dev(lc_engine_t* e, const lc_regex_t* const* res, uint32_t npat, const uint32_t* nkeys,
+                             const uint8_t* d_base, uint64_t base_len, const uint32_t* d_ev_off,
+                             const uint32_t* d_ev_len, uint64_t n, const uint8_t* d_sel, uint8_t* d_which,
+                             uint8_t* d_status, uint32_t row_pitch, uint32_t* d_cap_off, uint32_t* d_cap_len);
 
 /* Boolean whole-value match == BoostRegexMatch(buf, size, reg, exception) without captures
  * (core/common/StringTools.cpp:213-236), the arithmetic of ProcessorFilterNative::IsMatched

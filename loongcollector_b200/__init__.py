@@ -7,3 +7,4 @@ library has not been built, and every compute call fails if no CUDA device is us
 from .capi import (Engine, HostProcessor, LcError, Regex, device_count, lib, version, LC_ML_IS_LAST,  # noqa: F401
                    LC_ML_MATCHED)
 from ._build import build  # noqa: F401
+from . import capi  # noqa: F401

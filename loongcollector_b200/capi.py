@@ -60,6 +60,11 @@ def lib():
     parse_args = [vp, vp, vp, u64, vp, vp, u64, u32, vp, vp, vp]
     L.lc_regex_parse.argtypes = parse_args
     L.lc_regex_parse_dev.argtypes = parse_args
+    L.lc_engine_set_stream.argtypes = [vp, vp]
+    L.lc_regex_parse_strided_dev.argtypes = [vp, vp, vp, u64, vp, vp, u32, u64, u32, vp, vp, vp]
+    multi_args = [vp, vp, u32, vp, vp, u64, vp, vp, u64, vp, vp, vp, u32, vp, vp]
+    L.lc_regex_parse_multi.argtypes = multi_args
+    L.lc_regex_parse_multi_dev.argtypes = multi_args
     L.lc_regex_prefix_match.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
     L.lc_regex_match.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
     L.lc_regex_match_dev.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
@@ -188,6 +193,46 @@ class Engine:
         _check(lib().lc_regex_parse(self._h, rx._h, _p(a), a.size, _p(ev_off), _p(ev_len), n, nkeys, _p(status),
                                     _p(co), _p(cl)))
         return status, co, cl
+
+    @staticmethod
+    def _multi_handles(rxs, nkeys):
+        arr = (C.c_void_p * len(rxs))(*[r._h.value if isinstance(r._h, C.c_void_p) else r._h for r in rxs])
+        nk = np.ascontiguousarray(nkeys, np.uint32)
+        assert nk.size == len(rxs)
+        return arr, nk
+
+    def regex_parse_multi(self, rxs, nkeys, base, ev_off, ev_len, sel=None, row_pitch=None):
+        """First-match-wins over several patterns in one grid; returns (which, status, cap_off, cap_len)."""
+        a = _u8(base)
+        ev_off = np.ascontiguousarray(ev_off, np.uint32)
+        ev_len = np.ascontiguousarray(ev_len, np.uint32)
+        n = ev_off.size
+        G = int(row_pitch if row_pitch is not None else max(r.ngroups for r in rxs))
+        arr, nk = self._multi_handles(rxs, nkeys)
+        which = np.empty(n, np.uint8)
+        status = np.empty(n, np.uint8)
+        co = np.empty((n, G), np.uint32)
+        cl = np.empty((n, G), np.uint32)
+        if sel is not None:
+            sel = np.ascontiguousarray(sel, np.uint8)
+        _check(lib().lc_regex_parse_multi(self._h, arr, len(rxs), _p(nk), _p(a), a.size, _p(ev_off), _p(ev_len), n,
+                                          _p(sel), _p(which), _p(status), G, _p(co), _p(cl)))
+        return which, status, co, cl
+
+    def regex_parse_multi_dev(self, rxs, nkeys, d_base, base_len, d_ev_off, d_ev_len, n, d_sel, d_which, d_status,
+                              row_pitch, d_cap_off, d_cap_len):
+        arr, nk = self._multi_handles(rxs, nkeys)
+        _check(lib().lc_regex_parse_multi_dev(self._h, arr, len(rxs), _p(nk), _p(d_base), base_len, _p(d_ev_off),
+                                              _p(d_ev_len), n, _p(d_sel), _p(d_which), _p(d_status), row_pitch,
+                                              _p(d_cap_off), _p(d_cap_len)))
+
+    def regex_parse_strided_dev(self, rx, d_base, base_len, d_ev_off, d_ev_len, ev_stride, n, nkeys, d_status,
+                                d_cap_off, d_cap_len):
+        _check(lib().lc_regex_parse_strided_dev(self._h, rx._h, _p(d_base), base_len, _p(d_ev_off), _p(d_ev_len),
+                                                ev_stride, n, nkeys, _p(d_status), _p(d_cap_off), _p(d_cap_len)))
+
+    def set_stream(self, stream):
+        _check(lib().lc_engine_set_stream(self._h, _p(stream) if stream else None))
 
     def regex_prefix_match(self, rx, base, ev_off, ev_len):
         a = _u8(base)

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <string>
 #include <unordered_map>
@@ -64,6 +65,10 @@ struct DevBuf {
 
 std::atomic<uint64_t> g_regex_ids{1};
 
+// engines alive in this process: lc_regex_free() tells each of them to drop its device copies of the tables
+std::mutex g_engines_mu;
+std::vector<lc_engine*> g_engines;
+
 } // namespace
 
 struct lc_regex {
@@ -74,7 +79,8 @@ struct lc_regex {
 
 struct lc_engine {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // the stream every call of this engine is queued on
+    cudaStream_t own_stream = nullptr; // created with the engine; `stream` unless lc_engine_set_stream replaced it
     uint64_t launches = 0;
     int num_sms = 148;
     int smem_per_block_optin = 0;
@@ -85,13 +91,16 @@ struct lc_engine {
     uint64_t scratch_hint = 0;
     int length_order = -1; // env LC_B200_LENGTH_ORDER: 1 = always order ragged batches by length, 0 = never, unset = auto
     uint32_t max_warps = 32;   // env LC_B200_MAX_WARPS (tuning knob: resident warps per block of the regex kernels)
+    bool multi_split = false;  // env LC_B200_MULTI_SPLIT=1: lc_regex_parse_multi launches one pattern at a time (test knob)
     // staging / workspace (grow-only)
     DevBuf in, ev_off, ev_len, out_a, out_b, out_c, out_d, out_e;
     DevBuf lines_off, lines_len, flags, state, cnt, pos, lab_sizes, lab_off, lab, order;
     DevBuf desc;   // look-back descriptors (3 regions)
     DevBuf small;  // tickets + counters: [0..3] u32 tickets, +16: u32 n_out, +32: u64 total, +64: u64 counters[2]
     void* h_small = nullptr; // pinned mirror of `small`
-    std::unordered_map<uint64_t, void*> blobs; // regex id -> device blob
+    std::unordered_map<uint64_t, void*> blobs; // regex id * 4 + layout -> device blob
+    std::mutex freed_mu;
+    std::vector<uint64_t> freed_ids; // regexes freed since the last call (their blobs are released lazily)
     // copy pipeline of the host-pointer entry points
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> ev_h2d, ev_comp;
@@ -107,6 +116,26 @@ cudaError_t engine_blob(lc_engine* e, const lc_regex* r, const void** out, int l
                                       : layout == 2 ? r->res.fast2_blob
                                                     : (layout == 1 ? r->res.fast_blob : r->res.blob);
     const uint64_t key = r->id * 4 + (uint64_t)layout;
+    {
+        // device tables of regexes freed since the last call (lc_regex_free): released here, on the engine's own
+        // thread, after the stream has drained
+        std::vector<uint64_t> dead;
+        {
+            std::lock_guard<std::mutex> lk(e->freed_mu);
+            dead.swap(e->freed_ids);
+        }
+        if (!dead.empty()) {
+            cudaStreamSynchronize(e->stream);
+            for (uint64_t id : dead)
+                for (uint64_t l = 0; l < 4; ++l) {
+                    auto f = e->blobs.find(id * 4 + l);
+                    if (f != e->blobs.end()) {
+                        cudaFree(f->second);
+                        e->blobs.erase(f);
+                    }
+                }
+        }
+    }
     auto it = e->blobs.find(key);
     if (it != e->blobs.end()) {
         *out = it->second;
@@ -117,8 +146,10 @@ cudaError_t engine_blob(lc_engine* e, const lc_regex* r, const void** out, int l
     if (er != cudaSuccess)
         return er;
     er = cudaMemcpyAsync(d, src.data(), src.size(), cudaMemcpyHostToDevice, e->stream);
-    if (er != cudaSuccess)
+    if (er != cudaSuccess) {
+        cudaFree(d);
         return er;
+    }
     e->blobs[key] = d;
     *out = d;
     return cudaSuccess;
@@ -132,7 +163,7 @@ struct Small {
     uint64_t total;
     unsigned long long bump;
     unsigned long long next_batch;
-    uint64_t pad1[1];
+    unsigned long long total_chars; // un-truncated split-char count of the last split
     unsigned long long counters[2];
 };
 
@@ -169,6 +200,19 @@ int ensure_copy_streams(lc_engine* e, int nchunks) {
         e->ev_h2d.push_back(a);
         e->ev_comp.push_back(b);
     }
+    return LC_OK;
+}
+
+// host-pointer entry points: every event must lie inside [0, base_len) -- a bad table would make the kernels read
+// (or, for the serialiser, write) outside the staged arena
+int check_events(const uint32_t* off, const uint32_t* len, uint64_t n, uint64_t base_len, const char* what) {
+    uint64_t hi = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t en = (uint64_t)off[i] + len[i];
+        hi = en > hi ? en : hi;
+    }
+    if (hi > base_len)
+        return fail(LC_ERR_INVALID_ARG, std::string(what) + ": event beyond base_len");
     return LC_OK;
 }
 
@@ -212,7 +256,8 @@ int lc_engine_create(int device, lc_engine_t** out) {
         return fail(LC_ERR_CUDA, "out of host memory");
     e->device = device;
     CU_TRY(cudaSetDevice(device));
-    CU_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
     CU_TRY(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device));
     CU_TRY(cudaDeviceGetAttribute(&e->smem_per_block_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CU_TRY(cudaDeviceGetAttribute(&e->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
@@ -222,12 +267,18 @@ int lc_engine_create(int device, lc_engine_t** out) {
         const char* mw = getenv("LC_B200_MAX_WARPS");
         if (mw && atoi(mw) >= 4 && atoi(mw) <= 32)
             e->max_warps = (uint32_t)atoi(mw);
+        const char* msp = getenv("LC_B200_MULTI_SPLIT");
+        e->multi_split = msp && !strcmp(msp, "1");
         const char* lo = getenv("LC_B200_LENGTH_ORDER");
         e->length_order = !lo ? -1 : (!strcmp(lo, "1") ? 1 : 0);
         e->regex_variant = !k ? 0 : (!strcmp(k, "fast") ? 1 : (!strcmp(k, "fast2") ? 2 : (!strcmp(k, "generic") ? 3 : (!strcmp(k, "tdfa") ? 4 : (!strcmp(k, "tdfa_direct") ? 5 : 0)))));
     }
     CU_TRY(e->small.ensure(sizeof(Small)));
     CU_TRY(cudaMallocHost(&e->h_small, sizeof(Small)));
+    {
+        std::lock_guard<std::mutex> lk(g_engines_mu);
+        g_engines.push_back(e);
+    }
     *out = e;
     return LC_OK;
 }
@@ -235,6 +286,10 @@ int lc_engine_create(int device, lc_engine_t** out) {
 void lc_engine_destroy(lc_engine_t* e) {
     if (!e)
         return;
+    {
+        std::lock_guard<std::mutex> lk(g_engines_mu);
+        g_engines.erase(std::remove(g_engines.begin(), g_engines.end(), e), g_engines.end());
+    }
     cudaSetDevice(e->device);
     if (e->stream)
         cudaStreamSynchronize(e->stream);
@@ -255,8 +310,8 @@ void lc_engine_destroy(lc_engine_t* e) {
         cudaStreamDestroy(e->s_h2d);
     if (e->s_d2h)
         cudaStreamDestroy(e->s_d2h);
-    if (e->stream)
-        cudaStreamDestroy(e->stream);
+    if (e->own_stream)
+        cudaStreamDestroy(e->own_stream);
     delete e;
 }
 
@@ -269,6 +324,15 @@ int lc_engine_sync(lc_engine_t* e) {
 }
 
 void* lc_engine_stream(lc_engine_t* e) { return e ? (void*)e->stream : nullptr; }
+
+int lc_engine_set_stream(lc_engine_t* e, void* stream) {
+    if (!e)
+        return fail(LC_ERR_INVALID_ARG, "engine is NULL");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaStreamSynchronize(e->stream)); // workspace reuse is ordered by the stream: drain the old one first
+    e->stream = stream ? (cudaStream_t)stream : e->own_stream;
+    return LC_OK;
+}
 uint64_t lc_engine_launch_count(const lc_engine_t* e) { return e ? e->launches : 0; }
 
 void* lc_host_alloc(size_t bytes) {
@@ -303,7 +367,18 @@ int lc_regex_compile(const char* pattern, size_t len, lc_regex_t** out) {
     return LC_OK;
 }
 
-void lc_regex_free(lc_regex_t* r) { delete r; }
+void lc_regex_free(lc_regex_t* r) {
+    if (!r)
+        return;
+    {
+        std::lock_guard<std::mutex> lk(g_engines_mu);
+        for (lc_engine* e : g_engines) {
+            std::lock_guard<std::mutex> lk2(e->freed_mu);
+            e->freed_ids.push_back(r->id);
+        }
+    }
+    delete r;
+}
 const char* lc_regex_error(const lc_regex_t* r) { return r ? r->res.error.c_str() : ""; }
 uint32_t lc_regex_ngroups(const lc_regex_t* r) { return r ? r->res.ngroups : 0; }
 
@@ -343,12 +418,14 @@ int lc_split_lines_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, uint8
     Small* ds = e->small.as<Small>();
     uint32_t cap32 = cap > 0x3FFFFFFFull ? 0x3FFFFFFFu : (uint32_t)cap;
     lck::launch_split(d_buf, (uint32_t)len, split_char, d_out_off, d_out_len, cap32, plan.r[0], &ds->tickets[0],
-                      &ds->n_out, e->stream);
+                      &ds->n_out, &ds->total_chars, e->stream);
     e->launches++;
     CU_TRY(cudaGetLastError());
     Small* hs = (Small*)e->h_small;
-    CU_TRY(cudaMemcpyAsync(&hs->n_out, &ds->n_out, 4, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
+    if (hs->total_chars >= (1ull << 30) - 1)
+        return fail(LC_ERR_TOO_LARGE, "more than 2^30 pieces in one call");
     *n_out = hs->n_out;
     if (*n_out > cap)
         return fail(LC_ERR_CAPACITY, "lc_split_lines: output capacity too small");
@@ -385,20 +462,34 @@ int lc_split_lines(lc_engine_t* e, const uint8_t* buf, uint64_t len, uint8_t spl
 }
 
 // ------------------------------------------------------------------------------------------------ regex parse
+// span_bytes: bytes of the arena this batch's events cover (== base_len for a whole-arena call; the chunked host path
+// passes the chunk's own span so that per-batch heuristics see the batch, not the arena).  ev_stride: distance in
+// elements between consecutive entries of d_ev_off / d_ev_len (1 = dense tables).
 static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
-                                const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
-                                uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, bool bool_only);
+                                uint64_t span_bytes, const uint32_t* d_ev_off, const uint32_t* d_ev_len,
+                                uint32_t ev_stride, uint64_t n, uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off,
+                                uint32_t* d_cap_len, bool bool_only);
 
 int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
                        const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
                        uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len) {
-    return regex_parse_dev_impl(e, re, d_base, base_len, d_ev_off, d_ev_len, n, nkeys, d_status, d_cap_off, d_cap_len,
-                                false);
+    return regex_parse_dev_impl(e, re, d_base, base_len, base_len, d_ev_off, d_ev_len, 1, n, nkeys, d_status, d_cap_off,
+                                d_cap_len, false);
+}
+
+int lc_regex_parse_strided_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
+                               const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint32_t ev_stride, uint64_t n,
+                               uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len) {
+    if (ev_stride == 0)
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_strided_dev: ev_stride must be >= 1");
+    return regex_parse_dev_impl(e, re, d_base, base_len, base_len, d_ev_off, d_ev_len, ev_stride, n, nkeys, d_status,
+                                d_cap_off, d_cap_len, false);
 }
 
 int lc_regex_match_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
                        const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint8_t* d_out_match) {
-    return regex_parse_dev_impl(e, re, d_base, base_len, d_ev_off, d_ev_len, n, 0, d_out_match, nullptr, nullptr, true);
+    return regex_parse_dev_impl(e, re, d_base, base_len, base_len, d_ev_off, d_ev_len, 1, n, 0, d_out_match, nullptr,
+                                nullptr, true);
 }
 
 int lc_regex_match(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, uint64_t base_len,
@@ -410,6 +501,9 @@ int lc_regex_match(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, ui
         return rc;
     if (n == 0)
         return LC_OK;
+    rc = check_events(ev_off, ev_len, n, base_len, "lc_regex_match");
+    if (rc)
+        return rc;
     rc = bind(e);
     if (rc)
         return rc;
@@ -429,9 +523,25 @@ int lc_regex_match(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, ui
     return LC_OK;
 }
 
+// gathers a strided event table into the engine's dense scratch tables (the two-pass fall-back kernels take dense
+// tables only)
+static int densify_events(lc_engine_t* e, const uint32_t*& d_ev_off, const uint32_t*& d_ev_len, uint32_t ev_stride,
+                          uint64_t n) {
+    CU_TRY(e->lines_off.ensure(n * 4));
+    CU_TRY(e->lines_len.ensure(n * 4));
+    CU_TRY(cudaMemcpy2DAsync(e->lines_off.p, 4, d_ev_off, (size_t)ev_stride * 4, 4, n, cudaMemcpyDeviceToDevice,
+                             e->stream));
+    CU_TRY(cudaMemcpy2DAsync(e->lines_len.p, 4, d_ev_len, (size_t)ev_stride * 4, 4, n, cudaMemcpyDeviceToDevice,
+                             e->stream));
+    d_ev_off = e->lines_off.as<uint32_t>();
+    d_ev_len = e->lines_len.as<uint32_t>();
+    return LC_OK;
+}
+
 static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_base, uint64_t base_len,
-                                const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
-                                uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, bool bool_only) {
+                                uint64_t span_bytes, const uint32_t* d_ev_off, const uint32_t* d_ev_len,
+                                uint32_t ev_stride, uint64_t n, uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off,
+                                uint32_t* d_cap_len, bool bool_only) {
     if (!e || !re)
         return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_dev: bad arguments");
     int rc = check_regex_usable(re, "lc_regex_parse");
@@ -451,12 +561,14 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
     Small* hs = (Small*)e->h_small;
     const bool force_basic = e->force_basic_regex;
     const size_t smem_max = (size_t)e->smem_per_block_optin;
-    // ---- single-pass tagged DFA: the preferred kernel whenever the pattern's TDFA fits shared memory
+    // ---- single-pass tagged DFA: the preferred kernel whenever the pattern's TDFA fits shared memory.  Nothing on
+    // this path waits for the device: ragged-batch ordering is decided by a device-side flag and events too long for
+    // the 16-bit capture registers are redone by a follow-up kernel that exits at once when there was none.
     if (!force_basic && (e->regex_variant == 0 || e->regex_variant == 4 || e->regex_variant == 5) &&
         !re->res.tdfa_blob.empty()) {
         const LcTdfaHeader* th = reinterpret_cast<const LcTdfaHeader*>(re->res.tdfa_blob.data());
         const uint32_t tb = (uint32_t)re->res.tdfa_blob.size();
-        const bool staged = e->regex_variant != 5;
+        const bool staged = e->regex_variant != 5 || ev_stride != 1;
         auto smem_need = [&](uint32_t warps) {
             return staged ? lck::tdfa_staged_smem_bytes(tb, th->nregs, warps * 32)
                           : lck::tdfa_smem_bytes(tb, th->nregs, warps * 32);
@@ -465,7 +577,7 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
         while (warps > 4 && smem_need(warps) > smem_max)
             warps -= 2;
         bool usable = smem_need(warps) <= smem_max;
-        if (usable && !staged && base_len >= 65535) { // capture registers are 16-bit: every event must be < 65535 bytes
+        if (usable && !staged && base_len >= 65535) { // A/B kernel without the long-event hand-over: host-side check
             CU_TRY(cudaMemsetAsync(ds->counters, 0, sizeof ds->counters, e->stream));
             lck::launch_len_stats(d_ev_len, n, ds->counters, e->stream);
             e->launches++;
@@ -481,32 +593,29 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
             const uint64_t need_blocks = (n + threads - 1) / threads;
             const uint32_t grid = (uint32_t)std::min<uint64_t>(need_blocks, (uint64_t)e->num_sms);
             // Ragged batches of long lines: a warp costs its longest line, so visit the events by descending length
-            // bucket.  Only looked at when the mean length makes the pre-pass (one small kernel + a sync) negligible;
-            // LC_B200_LENGTH_ORDER=1 forces it, =0 disables it.
+            // bucket.  Only built when the mean length makes the three small pre-pass kernels negligible; the scan
+            // kernel leaves a flag saying whether the lengths really are ragged, which the regex kernel reads.
+            // LC_B200_LENGTH_ORDER=1 forces the pre-pass, =0 disables it.
             const uint32_t* d_order = nullptr;
-            if (staged && n >= 4096 && e->length_order != 0 && (e->length_order == 1 || base_len / n >= 1024)) {
-                CU_TRY(cudaMemsetAsync(ds->counters, 0, sizeof ds->counters, e->stream));
-                lck::launch_len_stats(d_ev_len, n, ds->counters, e->stream);
-                e->launches++;
-                CU_TRY(cudaMemcpyAsync(hs->counters, ds->counters, sizeof ds->counters, cudaMemcpyDeviceToHost,
-                                       e->stream));
-                CU_TRY(cudaStreamSynchronize(e->stream));
-                const uint64_t mx = hs->counters[0], avg = hs->counters[1] / n + 1;
-                if (mx > avg + avg / 2 + 64) {
-                    CU_TRY(e->order.ensure(n * 4 + 256));
-                    uint32_t* hist = e->order.as<uint32_t>() + n;
-                    lck::launch_length_order(d_ev_len, n, hist, e->order.as<uint32_t>(), e->stream);
-                    e->launches += 3;
-                    d_order = e->order.as<uint32_t>();
-                }
+            const uint32_t* d_order_flag = nullptr;
+            if (staged && ev_stride == 1 && n >= 4096 && e->length_order != 0 &&
+                (e->length_order == 1 || span_bytes / n >= 1024)) {
+                CU_TRY(e->order.ensure(n * 4 + 512));
+                uint32_t* hist = e->order.as<uint32_t>() + n;
+                lck::launch_length_order(d_ev_len, n, hist, e->order.as<uint32_t>(), e->stream);
+                e->launches += 3;
+                d_order = e->order.as<uint32_t>();
+                d_order_flag = e->length_order == 1 ? nullptr : hist + 64;
             }
-            CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof(Small) - offsetof(Small, overflow), e->stream));
+            CU_TRY(cudaMemsetAsync(&ds->overflow, 0, offsetof(Small, total_chars) - offsetof(Small, overflow),
+                                   e->stream));
             int er;
             if (staged)
                 er = lck::launch_regex_tdfa_staged(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off,
-                                                   d_ev_len, n, nkeys, d_status, bool_only ? nullptr : d_cap_off,
-                                                   bool_only ? nullptr : d_cap_len, threads, grid, &ds->next_batch,
-                                                   &ds->overflow, d_order, e->stream);
+                                                   d_ev_len, ev_stride, n, nkeys, d_status,
+                                                   bool_only ? nullptr : d_cap_off, bool_only ? nullptr : d_cap_len,
+                                                   threads, grid, &ds->next_batch, &ds->overflow, d_order,
+                                                   d_order_flag, e->stream);
             else
                 er = lck::launch_regex_tdfa(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off, d_ev_len, n,
                                             nkeys, d_status, bool_only ? nullptr : d_cap_off,
@@ -515,19 +624,29 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
             e->launches++;
             if (er)
                 return fail(LC_ERR_CUDA, std::string("regex kernel launch: ") + cudaGetErrorString((cudaError_t)er));
-            if (!staged || base_len < 65535)
-                return LC_OK;
-            // the kernel itself reports events too long for its 16-bit capture registers (no length pre-pass)
-            CU_TRY(cudaMemcpyAsync(&hs->overflow, &ds->overflow, 4, cudaMemcpyDeviceToHost, e->stream));
-            CU_TRY(cudaStreamSynchronize(e->stream));
-            if (!hs->overflow)
-                return LC_OK;
-            // fall through: redo the whole call on a kernel with 32-bit slots
+            if (staged && base_len >= 65535) {
+                lck::TdfaMultiArgs ma;
+                memset(&ma, 0, sizeof ma);
+                ma.blob[0] = d_tblob;
+                ma.blob_bytes[0] = tb;
+                ma.nkeys[0] = nkeys;
+                ma.npat = 1;
+                lck::launch_regex_tdfa_long(ma, d_base, d_ev_off, d_ev_len, ev_stride, n, nullptr, nullptr, d_status,
+                                            d_cap_off, d_cap_len, th->ngroups, &ds->overflow, bool_only, e->stream);
+                e->launches++;
+                CU_TRY(cudaGetLastError());
+            }
+            return LC_OK;
         }
+    }
+    if (ev_stride != 1) {
+        rc = densify_events(e, d_ev_off, d_ev_len, ev_stride, n);
+        if (rc)
+            return rc;
     }
     if (!force_basic) {
         // ---- pick the kernel variant: stride-2 layout > stride-1 fast layout > generic shared-memory interpreter
-        uint64_t mx = 0, avg = base_len / n + 1;
+        uint64_t mx = 0, avg = span_bytes / n + 1;
         if (h->mode == LC_MODE_TWOPASS) {
             // size the per-thread label area from the actual length distribution: cover the longest event when
             // the batch is near-uniform, else ~1.25x the mean (longer events spill to the global slab)
@@ -605,7 +724,7 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
             uint64_t need_blocks = (n + threads - 1) / threads;
             uint32_t grid = (uint32_t)std::min<uint64_t>(need_blocks, (uint64_t)e->num_sms * blocks_per_sm);
             // global label slab for events longer than the shared-memory budget: start small, remember what worked
-            uint64_t full = base_len / per + 2 * n + 1024;
+            uint64_t full = span_bytes / per + 2 * n + 1024;
             uint64_t scratch_words = std::max<uint64_t>(e->scratch_hint, std::min<uint64_t>(full, 16ull << 20));
             if (h->mode == LC_MODE_TWOPASS && (mx + 15) / per + 2 > lab_words) {
                 // some events spill: provision the upper bound of what ALL events could need (no retry runs)
@@ -619,7 +738,7 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
             // (measured on C5, Zipf 64 B-8 KB: -7 %, the scattered visiting order costs more L2 locality than the
             //  balanced warps win -- kept opt-in: LC_B200_LENGTH_ORDER=1)
             if (e->length_order == 1 && h->mode == LC_MODE_TWOPASS && mx > 2 * avg + 64 && n >= 4096) {
-                CU_TRY(e->order.ensure(n * 4 + 256));
+                CU_TRY(e->order.ensure(n * 4 + 512));
                 uint32_t* hist = e->order.as<uint32_t>() + n;
                 lck::launch_length_order(d_ev_len, n, hist, e->order.as<uint32_t>(), e->stream);
                 e->launches += 3;
@@ -628,7 +747,7 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
             for (int attempt = 0; attempt < 8; ++attempt) {
                 if (h->mode == LC_MODE_TWOPASS)
                     CU_TRY(e->lab.ensure(scratch_words * 4));
-                CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof(Small) - offsetof(Small, overflow), e->stream));
+                CU_TRY(cudaMemsetAsync(&ds->overflow, 0, offsetof(Small, total_chars) - offsetof(Small, overflow), e->stream));
                 int er;
                 if (variant == V_FAST2) {
                     const LcFast2Header* f2h = reinterpret_cast<const LcFast2Header*>(vb.data());
@@ -714,6 +833,83 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
     return LC_OK;
 }
 
+} // extern "C"
+
+// Pipelined host-pointer batch: the arena is cut into chunks of whole events; chunk c's bytes and event table go up on a
+// copy stream, its kernels run on the engine stream as soon as they have landed, and its result tables travel back on
+// a third stream while later chunks are still being uploaded (PCIe is full duplex).  `run(c, i0, cnt, span)` queues
+// the chunk's kernels; `down(c, i0, cnt)` queues its D2H copies on s_d2h.  Event ranges are validated chunk by chunk
+// right before their upload is queued, so the check overlaps the copies of the previous chunks.
+template <class Run, class Down>
+static int pipelined_events(lc_engine_t* e, const uint8_t* base, uint64_t base_len, const uint32_t* ev_off,
+                            const uint32_t* ev_len, uint64_t n, uint64_t nchunks, const char* what, Run run, Down down) {
+    int rc = ensure_copy_streams(e, (int)nchunks);
+    if (rc)
+        return rc;
+    uint8_t* d_in = e->in.as<uint8_t>();
+    uint32_t* d_off = e->ev_off.as<uint32_t>();
+    uint32_t* d_len = e->ev_len.as<uint32_t>();
+    // every exit path drains the copy streams: they read and write caller buffers
+    auto drain = [&](int code) {
+        cudaStreamSynchronize(e->s_h2d);
+        cudaStreamSynchronize(e->stream);
+        cudaStreamSynchronize(e->s_d2h);
+        return code;
+    };
+    // the engine stream may still be reading the workspace on behalf of an earlier asynchronous call
+    cudaEvent_t ev0 = e->ev_comp[0];
+    if (cudaEventRecord(ev0, e->stream) != cudaSuccess || cudaStreamWaitEvent(e->s_h2d, ev0, 0) != cudaSuccess)
+        return fail(LC_ERR_CUDA, "stream ordering failed");
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const uint64_t i0 = n * c / nchunks, i1 = n * (c + 1) / nchunks, cnt = i1 - i0;
+        uint64_t lo = ~0ull, hi = 0;
+        for (uint64_t i = i0; i < i1; ++i) {
+            const uint64_t o = ev_off[i], en = o + ev_len[i];
+            lo = o < lo ? o : lo;
+            hi = en > hi ? en : hi;
+        }
+        if (hi > base_len)
+            return drain(fail(LC_ERR_INVALID_ARG, std::string(what) + ": event beyond base_len"));
+        lo = lo == ~0ull ? 0 : (lo & ~15ull);
+#define LC_PIPE_TRY(expr)                                                                                              \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess)                                                                                         \
+            return drain(fail(LC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)));                        \
+    } while (0)
+        if (hi > lo)
+            LC_PIPE_TRY(cudaMemcpyAsync(d_in + lo, base + lo, hi - lo, cudaMemcpyHostToDevice, e->s_h2d));
+        LC_PIPE_TRY(cudaMemcpyAsync(d_off + i0, ev_off + i0, cnt * 4, cudaMemcpyHostToDevice, e->s_h2d));
+        LC_PIPE_TRY(cudaMemcpyAsync(d_len + i0, ev_len + i0, cnt * 4, cudaMemcpyHostToDevice, e->s_h2d));
+        LC_PIPE_TRY(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
+        LC_PIPE_TRY(cudaStreamWaitEvent(e->stream, e->ev_h2d[c], 0));
+        rc = run(c, i0, cnt, hi > lo ? hi - lo : 0);
+        if (rc)
+            return drain(rc);
+        LC_PIPE_TRY(cudaEventRecord(e->ev_comp[c], e->stream));
+        LC_PIPE_TRY(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[c], 0));
+        rc = down(c, i0, cnt);
+        if (rc)
+            return drain(rc);
+#undef LC_PIPE_TRY
+    }
+    CU_TRY(cudaStreamSynchronize(e->s_d2h));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return LC_OK;
+}
+
+static uint64_t pipeline_chunks(uint64_t base_len, uint64_t n) {
+    const uint64_t kChunkBytes = 48ull << 20;
+    uint64_t nchunks = (base_len + kChunkBytes - 1) / kChunkBytes;
+    if (nchunks > 64)
+        nchunks = 64;
+    if (nchunks < 2 || n < nchunks * 1024)
+        return 1;
+    return nchunks;
+}
+
+extern "C" {
+
 int lc_regex_parse(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, uint64_t base_len,
                    const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n, uint32_t nkeys, uint8_t* status,
                    uint32_t* cap_off, uint32_t* cap_len) {
@@ -724,32 +920,35 @@ int lc_regex_parse(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, ui
         return rc;
     if (n == 0)
         return LC_OK;
+    const uint32_t G = re->res.ngroups;
+    if (G && (!cap_off || !cap_len))
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_parse: bad arguments");
+    if (base_len >= 0xFFFFFFF0ull || n >= (1ull << 30))
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB and < 2^30 events per call");
     rc = bind(e);
     if (rc)
         return rc;
-    const uint32_t G = re->res.ngroups;
     CU_TRY(e->in.ensure(base_len + 16));
     CU_TRY(e->ev_off.ensure(n * 4));
     CU_TRY(e->ev_len.ensure(n * 4));
     CU_TRY(e->out_a.ensure(n));
     CU_TRY(e->out_b.ensure(n * G * 4 + 4));
     CU_TRY(e->out_c.ensure(n * G * 4 + 4));
-    // Large batches are pipelined: the arena is cut into chunks of whole events; all H2D copies are queued up front
-    // on a copy stream, each chunk's kernels run on the engine stream as soon as its bytes have landed, and its
-    // result tables travel back on a third stream while later chunks are still being uploaded (PCIe is full duplex).
-    const uint64_t kChunkBytes = 48ull << 20;
-    uint64_t nchunks = (base_len + kChunkBytes - 1) / kChunkBytes;
-    if (nchunks > 64)
-        nchunks = 64;
-    if (nchunks < 2 || n < nchunks * 1024) {
+    const uint64_t nchunks = pipeline_chunks(base_len, n);
+    if (nchunks == 1) {
+        rc = check_events(ev_off, ev_len, n, base_len, "lc_regex_parse");
+        if (rc)
+            return rc;
         CU_TRY(cudaMemcpyAsync(e->in.p, base, base_len, cudaMemcpyHostToDevice, e->stream));
         CU_TRY(cudaMemcpyAsync(e->ev_off.p, ev_off, n * 4, cudaMemcpyHostToDevice, e->stream));
         CU_TRY(cudaMemcpyAsync(e->ev_len.p, ev_len, n * 4, cudaMemcpyHostToDevice, e->stream));
         rc = lc_regex_parse_dev(e, re, e->in.as<uint8_t>(), base_len, e->ev_off.as<uint32_t>(),
                                 e->ev_len.as<uint32_t>(), n, nkeys, e->out_a.as<uint8_t>(), e->out_b.as<uint32_t>(),
                                 e->out_c.as<uint32_t>());
-        if (rc)
+        if (rc) {
+            cudaStreamSynchronize(e->stream);
             return rc;
+        }
         CU_TRY(cudaMemcpyAsync(status, e->out_a.p, n, cudaMemcpyDeviceToHost, e->stream));
         if (G) {
             CU_TRY(cudaMemcpyAsync(cap_off, e->out_b.p, n * G * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -758,45 +957,13 @@ int lc_regex_parse(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, ui
         CU_TRY(cudaStreamSynchronize(e->stream));
         return LC_OK;
     }
-    rc = ensure_copy_streams(e, (int)nchunks);
-    if (rc)
-        return rc;
-    // event ranges per chunk (equal event counts) and the byte span each one touches
-    std::vector<uint64_t> first(nchunks + 1), lo(nchunks), hi(nchunks);
-    for (uint64_t c = 0; c <= nchunks; ++c)
-        first[c] = n * c / nchunks;
-    for (uint64_t c = 0; c < nchunks; ++c) {
-        uint64_t l = ~0ull, h = 0;
-        for (uint64_t i = first[c]; i < first[c + 1]; ++i) {
-            uint64_t o = ev_off[i], en = o + ev_len[i];
-            l = o < l ? o : l;
-            h = en > h ? en : h;
-        }
-        if (h > base_len)
-            return fail(LC_ERR_INVALID_ARG, "lc_regex_parse: event beyond base_len");
-        lo[c] = l == ~0ull ? 0 : (l & ~15ull);
-        hi[c] = h;
-    }
     uint8_t* d_in = e->in.as<uint8_t>();
-    uint32_t* d_off = e->ev_off.as<uint32_t>();
-    uint32_t* d_len = e->ev_len.as<uint32_t>();
-    for (uint64_t c = 0; c < nchunks; ++c) {
-        uint64_t i0 = first[c], cnt = first[c + 1] - first[c];
-        if (hi[c] > lo[c])
-            CU_TRY(cudaMemcpyAsync(d_in + lo[c], base + lo[c], hi[c] - lo[c], cudaMemcpyHostToDevice, e->s_h2d));
-        CU_TRY(cudaMemcpyAsync(d_off + i0, ev_off + i0, cnt * 4, cudaMemcpyHostToDevice, e->s_h2d));
-        CU_TRY(cudaMemcpyAsync(d_len + i0, ev_len + i0, cnt * 4, cudaMemcpyHostToDevice, e->s_h2d));
-        CU_TRY(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
-    }
-    for (uint64_t c = 0; c < nchunks; ++c) {
-        uint64_t i0 = first[c], cnt = first[c + 1] - first[c];
-        CU_TRY(cudaStreamWaitEvent(e->stream, e->ev_h2d[c], 0));
-        rc = lc_regex_parse_dev(e, re, d_in, base_len, d_off + i0, d_len + i0, cnt, nkeys, e->out_a.as<uint8_t>() + i0,
-                                e->out_b.as<uint32_t>() + i0 * G, e->out_c.as<uint32_t>() + i0 * G);
-        if (rc)
-            return rc;
-        CU_TRY(cudaEventRecord(e->ev_comp[c], e->stream));
-        CU_TRY(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[c], 0));
+    auto run = [&](uint64_t, uint64_t i0, uint64_t cnt, uint64_t span) {
+        return regex_parse_dev_impl(e, re, d_in, base_len, span, e->ev_off.as<uint32_t>() + i0,
+                                    e->ev_len.as<uint32_t>() + i0, 1, cnt, nkeys, e->out_a.as<uint8_t>() + i0,
+                                    e->out_b.as<uint32_t>() + i0 * G, e->out_c.as<uint32_t>() + i0 * G, false);
+    };
+    auto down = [&](uint64_t, uint64_t i0, uint64_t cnt) {
         CU_TRY(cudaMemcpyAsync(status + i0, e->out_a.as<uint8_t>() + i0, cnt, cudaMemcpyDeviceToHost, e->s_d2h));
         if (G) {
             CU_TRY(cudaMemcpyAsync(cap_off + i0 * G, e->out_b.as<uint32_t>() + i0 * G, cnt * G * 4,
@@ -804,10 +971,183 @@ int lc_regex_parse(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, ui
             CU_TRY(cudaMemcpyAsync(cap_len + i0 * G, e->out_c.as<uint32_t>() + i0 * G, cnt * G * 4,
                                    cudaMemcpyDeviceToHost, e->s_d2h));
         }
+        return (int)LC_OK;
+    };
+    return pipelined_events(e, base, base_len, ev_off, ev_len, n, nchunks, "lc_regex_parse", run, down);
+}
+
+// ------------------------------------------------------------------------------------------------ multi-pattern
+int lc_regex_parse_multi_dev(lc_engine_t* e, const lc_regex_t* const* res, uint32_t npat, const uint32_t* nkeys,
+                             const uint8_t* d_base, uint64_t base_len, const uint32_t* d_ev_off,
+                             const uint32_t* d_ev_len, uint64_t n, const uint8_t* d_sel, uint8_t* d_which,
+                             uint8_t* d_status, uint32_t row_pitch, uint32_t* d_cap_off, uint32_t* d_cap_len) {
+    if (!e || !res || !nkeys || npat == 0 || npat > lck::LC_MULTI_MAX)
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_multi_dev: bad arguments (1..8 patterns)");
+    int rc;
+    uint32_t gmax = 0, max_nregs = 0;
+    bool slow = false;
+    for (uint32_t p = 0; p < npat; ++p) {
+        if (!res[p])
+            return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_multi_dev: NULL pattern");
+        if ((rc = check_regex_usable(res[p], "lc_regex_parse_multi")))
+            return rc;
+        if (res[p]->res.tdfa_blob.empty())
+            return fail(LC_ERR_REGEX_UNSUPPORTED,
+                        "lc_regex_parse_multi: pattern " + std::to_string(p) +
+                            " has no single-pass tables (too many states / registers); parse it with lc_regex_parse");
+        const LcTdfaHeader* th = reinterpret_cast<const LcTdfaHeader*>(res[p]->res.tdfa_blob.data());
+        gmax = std::max(gmax, th->ngroups);
+        max_nregs = std::max(max_nregs, th->nregs);
+        slow = slow || th->has_slow != 0;
     }
-    CU_TRY(cudaStreamSynchronize(e->s_d2h));
-    CU_TRY(cudaStreamSynchronize(e->stream));
+    if (row_pitch < gmax)
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_multi_dev: row_pitch smaller than the largest group count");
+    if (n == 0)
+        return LC_OK;
+    if (base_len >= 0xFFFFFFF0ull || n >= (1ull << 30))
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB and < 2^30 events per call");
+    rc = bind(e);
+    if (rc)
+        return rc;
+    Small* ds = e->small.as<Small>();
+    const size_t smem_max = (size_t)e->smem_per_block_optin;
+    lck::TdfaMultiArgs all;
+    memset(&all, 0, sizeof all);
+    all.npat = npat;
+    for (uint32_t p = 0; p < npat; ++p) {
+        CU_TRY(engine_blob(e, res[p], &all.blob[p], 3));
+        all.blob_bytes[p] = (uint32_t)res[p]->res.tdfa_blob.size();
+        all.nkeys[p] = nkeys[p];
+    }
+    // ragged batches: same device-side decision as the single-pattern path
+    const uint32_t* d_order = nullptr;
+    const uint32_t* d_order_flag = nullptr;
+    if (n >= 4096 && e->length_order != 0 && (e->length_order == 1 || base_len / n >= 1024)) {
+        CU_TRY(e->order.ensure(n * 4 + 512));
+        uint32_t* hist = e->order.as<uint32_t>() + n;
+        lck::launch_length_order(d_ev_len, n, hist, e->order.as<uint32_t>(), e->stream);
+        e->launches += 3;
+        d_order = e->order.as<uint32_t>();
+        d_order_flag = e->length_order == 1 ? nullptr : hist + 64;
+    }
+    // Group consecutive patterns whose tables fit shared memory together (and below shared address 64 Ki: the pair
+    // tables are addressed with 16 bits).  One group = one launch; normally everything is one group.
+    uint32_t p0 = 0;
+    bool first = true;
+    while (p0 < npat) {
+        lck::TdfaMultiArgs ga;
+        memset(&ga, 0, sizeof ga);
+        uint32_t warps = 0;
+        uint32_t p1 = p0;
+        while (p1 < npat) {
+            lck::TdfaMultiArgs tryg = ga;
+            tryg.blob[tryg.npat] = all.blob[p1];
+            tryg.blob_bytes[tryg.npat] = all.blob_bytes[p1];
+            tryg.nkeys[tryg.npat] = all.nkeys[p1];
+            tryg.npat++;
+            // last pair table must end below 64 Ki (LC_TDFA_REBASE_ROOM covers the window base and static shared memory)
+            const bool addressable = LC_TDFA_REBASE_ROOM + lck::tdfa_multi_table_bytes(tryg) <= 65535u;
+            uint32_t w = e->max_warps;
+            while (w > 4 && lck::tdfa_multi_smem_bytes(tryg, max_nregs, w * 32) > smem_max)
+                w -= 2;
+            const bool fits = lck::tdfa_multi_smem_bytes(tryg, max_nregs, w * 32) <= smem_max && w >= 16;
+            if (tryg.npat > 1 && (!(addressable && fits) || e->multi_split))
+                break;
+            if (tryg.npat == 1 && lck::tdfa_multi_smem_bytes(tryg, max_nregs, w * 32) > smem_max)
+                return fail(LC_ERR_REGEX_UNSUPPORTED, "lc_regex_parse_multi: tables do not fit shared memory");
+            ga = tryg;
+            warps = w;
+            ++p1;
+        }
+        const uint32_t threads = warps * 32;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((n + threads - 1) / threads, (uint64_t)e->num_sms);
+        CU_TRY(cudaMemsetAsync(&ds->next_batch, 0, sizeof ds->next_batch, e->stream));
+        if (first)
+            CU_TRY(cudaMemsetAsync(&ds->overflow, 0, sizeof ds->overflow, e->stream));
+        int er = lck::launch_regex_tdfa_multi(ga, p0, !first, slow, max_nregs, d_base, d_ev_off, d_ev_len, n, d_sel,
+                                              d_which, d_status, d_cap_off, d_cap_len, row_pitch, threads, grid,
+                                              &ds->next_batch, &ds->overflow, d_order, d_order_flag, e->stream);
+        e->launches++;
+        if (er)
+            return fail(LC_ERR_CUDA, std::string("regex kernel launch: ") + cudaGetErrorString((cudaError_t)er));
+        first = false;
+        p0 = p1;
+    }
+    if (base_len >= 65535) {
+        lck::launch_regex_tdfa_long(all, d_base, d_ev_off, d_ev_len, 1, n, d_sel, d_which, d_status, d_cap_off,
+                                    d_cap_len, row_pitch, &ds->overflow, false, e->stream);
+        e->launches++;
+        CU_TRY(cudaGetLastError());
+    }
     return LC_OK;
+}
+
+int lc_regex_parse_multi(lc_engine_t* e, const lc_regex_t* const* res, uint32_t npat, const uint32_t* nkeys,
+                         const uint8_t* base, uint64_t base_len, const uint32_t* ev_off, const uint32_t* ev_len,
+                         uint64_t n, const uint8_t* sel, uint8_t* which, uint8_t* status, uint32_t row_pitch,
+                         uint32_t* cap_off, uint32_t* cap_len) {
+    if (!e || !res || !nkeys || (n && (!ev_off || !ev_len || !status || !which)) || (base_len && !base) ||
+        (n && row_pitch && (!cap_off || !cap_len)))
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_multi: bad arguments");
+    if (n == 0)
+        return LC_OK;
+    if (base_len >= 0xFFFFFFF0ull || n >= (1ull << 30))
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB and < 2^30 events per call");
+    int rc = bind(e);
+    if (rc)
+        return rc;
+    const uint64_t G = row_pitch;
+    CU_TRY(e->in.ensure(base_len + 16));
+    CU_TRY(e->ev_off.ensure(n * 4));
+    CU_TRY(e->ev_len.ensure(n * 4));
+    CU_TRY(e->out_a.ensure(n));
+    CU_TRY(e->out_b.ensure(n * G * 4 + 4));
+    CU_TRY(e->out_c.ensure(n * G * 4 + 4));
+    CU_TRY(e->out_d.ensure(n));
+    CU_TRY(e->flags.ensure(n));
+    if (sel) {
+        for (uint64_t i = 0; i < n; ++i)
+            if (sel[i] != 0xFFu && sel[i] >= npat)
+                return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_multi: selector names a pattern that does not exist");
+        CU_TRY(cudaMemcpyAsync(e->flags.p, sel, n, cudaMemcpyHostToDevice, e->stream));
+    }
+    const uint8_t* d_sel = sel ? e->flags.as<uint8_t>() : nullptr;
+    uint8_t* d_in = e->in.as<uint8_t>();
+    const uint64_t nchunks = pipeline_chunks(base_len, n);
+    auto run = [&](uint64_t, uint64_t i0, uint64_t cnt, uint64_t) {
+        return lc_regex_parse_multi_dev(e, res, npat, nkeys, d_in, base_len, e->ev_off.as<uint32_t>() + i0,
+                                        e->ev_len.as<uint32_t>() + i0, cnt, d_sel ? d_sel + i0 : nullptr,
+                                        e->out_d.as<uint8_t>() + i0, e->out_a.as<uint8_t>() + i0, row_pitch,
+                                        e->out_b.as<uint32_t>() + i0 * G, e->out_c.as<uint32_t>() + i0 * G);
+    };
+    auto down_on = [&](cudaStream_t st, uint64_t i0, uint64_t cnt) {
+        CU_TRY(cudaMemcpyAsync(status + i0, e->out_a.as<uint8_t>() + i0, cnt, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(which + i0, e->out_d.as<uint8_t>() + i0, cnt, cudaMemcpyDeviceToHost, st));
+        if (G) {
+            CU_TRY(cudaMemcpyAsync(cap_off + i0 * G, e->out_b.as<uint32_t>() + i0 * G, cnt * G * 4,
+                                   cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(cap_len + i0 * G, e->out_c.as<uint32_t>() + i0 * G, cnt * G * 4,
+                                   cudaMemcpyDeviceToHost, st));
+        }
+        return (int)LC_OK;
+    };
+    if (nchunks == 1) {
+        rc = check_events(ev_off, ev_len, n, base_len, "lc_regex_parse_multi");
+        if (rc)
+            return rc;
+        CU_TRY(cudaMemcpyAsync(e->in.p, base, base_len, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->ev_off.p, ev_off, n * 4, cudaMemcpyHostToDevice, e->stream));
+        CU_TRY(cudaMemcpyAsync(e->ev_len.p, ev_len, n * 4, cudaMemcpyHostToDevice, e->stream));
+        rc = run(0, 0, n, base_len);
+        if (!rc)
+            rc = down_on(e->stream, 0, n);
+        cudaError_t er = cudaStreamSynchronize(e->stream);
+        if (!rc && er != cudaSuccess)
+            return fail(LC_ERR_CUDA, cudaGetErrorString(er));
+        return rc;
+    }
+    auto down = [&](uint64_t, uint64_t i0, uint64_t cnt) { return down_on(e->s_d2h, i0, cnt); };
+    return pipelined_events(e, base, base_len, ev_off, ev_len, n, nchunks, "lc_regex_parse_multi", run, down);
 }
 
 int lc_regex_prefix_match(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, uint64_t base_len,
@@ -819,6 +1159,9 @@ int lc_regex_prefix_match(lc_engine_t* e, const lc_regex_t* re, const uint8_t* b
         return rc;
     if (n == 0)
         return LC_OK;
+    rc = check_events(ev_off, ev_len, n, base_len, "lc_regex_prefix_match");
+    if (rc)
+        return rc;
     rc = bind(e);
     if (rc)
         return rc;
@@ -882,11 +1225,13 @@ int lc_multiline_split_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, c
             return rc;
         lck::launch_split(d_buf, (uint32_t)len, '\n', e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(),
                           (uint32_t)(lcap > 0x3FFFFFFFull ? 0x3FFFFFFFull : lcap), plan.r[0], &ds->tickets[0],
-                          &ds->n_out, e->stream);
+                          &ds->n_out, &ds->total_chars, e->stream);
         e->launches++;
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemcpyAsync(&hs->n_out, &ds->n_out, 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, e->stream));
         CU_TRY(cudaStreamSynchronize(e->stream));
+        if (hs->total_chars >= (1ull << 30) - 2)
+            return fail(LC_ERR_TOO_LARGE, "more than 2^30 lines in one call");
         n = hs->n_out;
         if (n <= lcap)
             break;
@@ -1000,7 +1345,10 @@ int lc_delim_parse(lc_engine_t* e, const uint8_t* base, uint64_t base_len, const
         return fail(LC_ERR_INVALID_ARG, "lc_delim_parse: bad arguments");
     if (n == 0)
         return LC_OK;
-    int rc = bind(e);
+    int rc = check_events(ev_off, ev_len, n, base_len, "lc_delim_parse");
+    if (rc)
+        return rc;
+    rc = bind(e);
     if (rc)
         return rc;
     size_t fbytes = (size_t)n * max_fields * 4;
@@ -1044,7 +1392,17 @@ int lc_sls_serialize_logs(lc_engine_t* e, const uint8_t* base, uint64_t base_len
         return fail(LC_ERR_INVALID_ARG, "lc_sls_serialize_logs: bad arguments");
     if (base_len >= 0xFFFFFFF0ull || n >= (1ull << 30) || m >= (1ull << 31))
         return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB, < 2^30 events and < 2^31 contents per call");
-    int rc = bind(e);
+    for (uint64_t i = 0; i < n; ++i)
+        if (ent_begin[i] > ent_begin[i + 1])
+            return fail(LC_ERR_INVALID_ARG, "lc_sls_serialize_logs: ent_begin must be non-decreasing");
+    if (ent_begin[0] != 0)
+        return fail(LC_ERR_INVALID_ARG, "lc_sls_serialize_logs: ent_begin[0] must be 0");
+    int rc = check_events(ent_koff, ent_klen, m, base_len, "lc_sls_serialize_logs (keys)");
+    if (!rc)
+        rc = check_events(ent_voff, ent_vlen, m, base_len, "lc_sls_serialize_logs (values)");
+    if (rc)
+        return rc;
+    rc = bind(e);
     if (rc)
         return rc;
     // workspace: in = arena, ev_off/ev_len = key spans, out_b/out_c = value spans, lines_off/lines_len = time / ns,

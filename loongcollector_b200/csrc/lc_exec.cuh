@@ -311,17 +311,21 @@ LC_HD LcTdfaView lc_tdfa_view(const void* blob) {
     return v;
 }
 
-LC_HD void lc_tdfa_run_ops(const LcTdfaView& v, uint32_t list, uint32_t pos, uint16_t* regs) {
+// RegT = uint16_t (events shorter than 65535 bytes: the shared-memory register files of the kernels) or uint32_t
+// (the long-event kernel); "unset" is the all-ones value of RegT.
+template <class RegT>
+LC_HD void lc_tdfa_run_ops(const LcTdfaView& v, uint32_t list, uint32_t pos, RegT* regs) {
     const uint16_t* p = v.ops + list;
     const uint32_t cnt = p[0];
     for (uint32_t k = 1; k <= cnt; ++k) {
         const uint32_t op = p[k], dst = op >> 8, src = op & 0xFFu;
-        regs[dst] = src == LC_TDFA_SRC_POS ? (uint16_t)pos : src == LC_TDFA_SRC_UNSET ? (uint16_t)LC_SLOT16_UNSET : regs[src];
+        regs[dst] = src == LC_TDFA_SRC_POS ? (RegT)pos : src == LC_TDFA_SRC_UNSET ? (RegT)~(RegT)0 : regs[src];
     }
 }
 
 // one byte from `state` at position pos; returns the next state (0 = dead)
-LC_HD uint32_t lc_tdfa_single(const LcTdfaView& v, uint32_t state, uint32_t byte, uint32_t pos, uint16_t* regs) {
+template <class RegT>
+LC_HD uint32_t lc_tdfa_single(const LcTdfaView& v, uint32_t state, uint32_t byte, uint32_t pos, RegT* regs) {
     const uint32_t e = v.t1[state * v.h->ncls + v.cls[byte]];
     if (e >> 16)
         lc_tdfa_run_ops(v, e >> 16, pos, regs);
@@ -330,8 +334,9 @@ LC_HD uint32_t lc_tdfa_single(const LcTdfaView& v, uint32_t state, uint32_t byte
 
 // s = first byte of the event; `mis` = virtual index of that byte (address & 15 on the device; pairs are aligned
 // on even virtual indices).  regs: h->nregs u16 entries, the first 2 * ngroups preset to LC_SLOT16_UNSET; on a
-// match they hold the capture boundaries.  n must be < 65535.
-LC_HD bool lc_tdfa_event(const LcTdfaView& v, const uint8_t* s, uint32_t mis, uint32_t n, uint16_t* regs) {
+// match they hold the capture boundaries.  n must be < 65535 for RegT = uint16_t.
+template <class RegT>
+LC_HD bool lc_tdfa_event(const LcTdfaView& v, const uint8_t* s, uint32_t mis, uint32_t n, RegT* regs) {
     const uint32_t ncls = v.h->ncls, row_bytes = v.h->row_bytes;
     uint32_t st = v.h->start;
     uint32_t pos = 0;
@@ -348,9 +353,9 @@ LC_HD bool lc_tdfa_event(const LcTdfaView& v, const uint8_t* s, uint32_t mis, ui
         } else {
             const uint32_t sa = (e >> 16) & 0x7Fu, sb = (e >> 24) & 0x7Fu;
             if (sa)
-                regs[(sa - 2) / 2] = (uint16_t)pos;
+                regs[(sa - 2) / 2] = (RegT)pos;
             if (sb)
-                regs[(sb - 2) / 2] = (uint16_t)(pos + 1);
+                regs[(sb - 2) / 2] = (RegT)(pos + 1);
             st = (e & 0xFFFFu) / row_bytes;
         }
         pos += 2;

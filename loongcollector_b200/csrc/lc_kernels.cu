@@ -46,7 +46,7 @@ template <int THREADS, int SEGS>
 __global__ void __launch_bounds__(THREADS)
     split_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
                  uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap, volatile uint64_t* desc,
-                 uint32_t* ticket, uint32_t ntiles, uint32_t* n_out) {
+                 uint32_t* ticket, uint32_t ntiles, uint32_t* n_out, unsigned long long* total_chars) {
     constexpr int ROWS = 4 * SEGS;
     __shared__ uint64_t s_scan[THREADS / 32 + 1];
     __shared__ uint32_t s_tile;
@@ -95,8 +95,11 @@ __global__ void __launch_bounds__(THREADS)
     const uint64_t excl = block_exclusive_scan<OpCountMax, THREADS>(pay, tot, s_scan);
     if (tid < 32) {
         uint64_t p = lookback<OpCountMax>(desc, tile, tot);
-        if (tid == 0)
+        if (tid == 0) {
             s_prefix = p;
+            if (OpCountMax::count(tot)) // un-truncated count (the payload keeps 30 bits): > 2^30 pieces is an error
+                atomicAdd(total_chars, (unsigned long long)OpCountMax::count(tot));
+        }
     }
     __syncthreads();
     const uint64_t pre = OpCountMax::combine(s_prefix, excl);
@@ -131,7 +134,8 @@ __global__ void __launch_bounds__(THREADS)
 }
 
 void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
-                  uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out, cudaStream_t st) {
+                  uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
+                  unsigned long long* d_total, cudaStream_t st) {
     uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
     uint32_t splat = split_char * 0x01010101u;
     static const int cfg = [] {
@@ -143,13 +147,13 @@ void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32
     uint32_t ntiles = (uint32_t)((len + shift + tile_bytes - 1) / tile_bytes);
     if (cfg == 128)
         split_kernel<1024, 2><<<ntiles, 1024, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
-                                                        (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out);
+                                                        (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out, d_total);
     else if (cfg == 64)
         split_kernel<1024, 1><<<ntiles, 1024, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
-                                                        (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out);
+                                                        (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out, d_total);
     else
         split_kernel<256, 1><<<ntiles, 256, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
-                                                      (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out);
+                                                      (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out, d_total);
 }
 
 // ================================================================================================ sums
@@ -259,14 +263,22 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x < 64 && sh[threadIdx.x])
         atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
-__global__ void bucket_scan_kernel(uint32_t* hist /* [64] in: counts, out: start cursor, longest bucket first */) {
+__global__ void bucket_scan_kernel(uint32_t* hist /* [64] in: counts, out: start cursor, longest bucket first;
+                                                       [64] out: 1 = ragged batch (lengths span > 2 adjacent buckets) */) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         uint32_t run = 0;
+        int lo = 64, hi = -1;
         for (int b = 63; b >= 0; --b) {
             uint32_t c = hist[b];
+            if (c) {
+                lo = b;
+                if (hi < 0)
+                    hi = b;
+            }
             hist[b] = run;
             run += c;
         }
+        hist[64] = (hi - lo >= 2) ? 1u : 0u;
     }
 }
 __global__ void __launch_bounds__(256)
@@ -294,7 +306,7 @@ void launch_length_order(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_hist6
                          cudaStream_t st) {
     if (!n)
         return;
-    cudaMemsetAsync(d_hist64, 0, 64 * sizeof(uint32_t), st);
+    cudaMemsetAsync(d_hist64, 0, 65 * sizeof(uint32_t), st);
     unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 1184);
     bucket_hist_kernel<<<grid, 256, 0, st>>>(d_ev_len, n, d_hist64);
     bucket_scan_kernel<<<1, 32, 0, st>>>(d_hist64);
@@ -1436,13 +1448,106 @@ __device__ __noinline__ uint32_t tdfa_partial_chunk(const LcTdfaView v, const Td
 // (Tile fill alternatives measured on C2 and dropped: cp.async.ca instead of .cg -2 %; LDG.128 into registers followed
 // by STS.128 -- 8x fewer shared-memory wavefronts than LDGSTS, which writes one 16-byte wavefront per lane -- but
 // -10 %: the loads stall the issuing warp and the extra live registers spill under the 64-register cap.)
+//
+// The warp's 32 lines (one per lane; line = frame of `len` bytes starting `mis` bytes into its first 16-byte chunk,
+// chunk list published in the warp's info slots as {first chunk index, chunk count}) walk through automaton `t`
+// stage by stage: cooperative fetch of 8 chunks per line into the tile, then every lane consumes its own line.
+// Lanes whose `row` is `dead` on entry (or becomes dead) only help fetching.  Returns the final row.
+struct TdfaLoader {
+    const uint4* gbase16; // 16-byte aligned base of the arena
+    uint32_t ld_q;        // loader role: chunk column of lines ld_L0 + r (r = 0..7)
+    uint32_t ld_info;     // info slots of those lines
+    uint32_t ld_dst;      // tile slot of (chunk ld_q, line ld_L0)
+    uint32_t tile_abs;    // this warp's 4 KB tile
+    uint32_t rd_lane16;   // lane << 4
+};
+
+template <bool SLOW>
+__device__ __forceinline__ uint32_t tdfa_walk_lines(const LcTdfaView& v, const TdfaAbs& t, const TdfaLoader& L,
+                                                    uint32_t dead, uint32_t sink, uint32_t row, uint32_t len,
+                                                    uint32_t mis, uint32_t max_nch, uint32_t regs_m2, uint16_t* rg) {
+    // frame of the line: byte j of the line sits at frame index mis + j; pairs cover the even-aligned [qlo, Qe)
+    const uint32_t Q = len + mis, qlo = mis + (mis & 1), Qe = Q & ~1u;
+    const uint32_t kf_lo = (qlo + 15) >> 4, kf_hi = Qe >> 4; // fully paired chunks: [kf_lo, kf_hi)
+    const uint32_t k_tail = len ? (Q - 1) >> 4 : 0;
+    const bool has_head = len && !(kf_lo == 0 && kf_hi > 0);        // chunk 0 is not fully paired
+    const bool has_tail = len && k_tail >= kf_hi && !(has_head && k_tail == 0);
+    const uint32_t tile_abs = L.tile_abs, rd_lane16 = L.rd_lane16;
+    for (uint32_t s0 = 0; s0 < max_nch; s0 += LCT_STAGE_CHUNKS) {
+        // ---- cooperative fetch: instruction r moves chunks s0..s0+7 of lines r, r+8, r+16, r+24
+        {
+            const uint32_t cidx = s0 + L.ld_q;
+#pragma unroll
+            for (uint32_t r = 0; r < 8; ++r) {
+                const uint2 inf = lds_u64_v(L.ld_info + r * 8);
+                if (cidx < inf.y)
+                    cp_async_16(L.ld_dst + ((r ^ L.ld_q) << 4), L.gbase16 + inf.x + cidx);
+            }
+            cp_async_wait_all();
+        }
+        __syncwarp();
+        // ---- every lane walks its own line through the tile
+        if (row != dead) {
+            if (has_head && s0 == 0)
+                row = tdfa_partial_chunk(v, t, row, tile_abs + rd_lane16, 0, mis, len, regs_m2, rg, sink);
+            const uint32_t ka = kf_lo > s0 ? kf_lo : s0;
+            const uint32_t kb = kf_hi < s0 + LCT_STAGE_CHUNKS ? kf_hi : s0 + LCT_STAGE_CHUNKS;
+            for (uint32_t k = ka; k < kb; ++k) {
+                const uint32_t q = k & 7;
+                const uint4 vv = lds_u128_v(tile_abs + (q << 9) + (rd_lane16 ^ (q << 4)));
+                const uint32_t pos0 = k * 16 - mis;
+                const uint32_t row_in = row;
+                LCS_PAIR(vv.x, 0, pos0 + 0)
+                LCS_PAIR(vv.x, 1, pos0 + 2)
+                LCS_PAIR(vv.y, 0, pos0 + 4)
+                LCS_PAIR(vv.y, 1, pos0 + 6)
+                LCS_PAIR(vv.z, 0, pos0 + 8)
+                LCS_PAIR(vv.z, 1, pos0 + 10)
+                LCS_PAIR(vv.w, 0, pos0 + 12)
+                LCS_PAIR(vv.w, 1, pos0 + 14)
+                if (SLOW && row == sink) // some step set several registers: redo this chunk step by step
+                    row = t.t2 + t.row_bytes * tdfa_chunk_slow(v, __umulhi(row_in - t.t2, t.inv_row), vv, pos0, rg);
+            }
+            if (has_tail && k_tail - s0 < LCT_STAGE_CHUNKS) {
+                const uint32_t q = k_tail & 7;
+                row = tdfa_partial_chunk(v, t, row, tile_abs + (q << 9) + (rd_lane16 ^ (q << 4)), k_tail * 16, mis,
+                                         len, regs_m2, rg, sink);
+            }
+        }
+        __syncwarp();
+    }
+    return row;
+}
+
+// Stages one automaton: class table at the 256-byte aligned shared address cls_abs, blob right behind it; pair-table
+// entries are rebased so that their low 16 bits are the ABSOLUTE shared address of the next row.  All threads call;
+// the caller synchronises afterwards.
+__device__ __forceinline__ void tdfa_stage_blob(uint8_t* g_cls, uint32_t cls_abs, const uint4* __restrict__ blob,
+                                                uint32_t blob_bytes) {
+    uint4* g_blob = reinterpret_cast<uint4*>(g_cls + 256);
+    for (uint32_t k = threadIdx.x; k < blob_bytes / 16; k += blockDim.x)
+        g_blob[k] = __ldg(blob + k);
+    __syncthreads();
+    const LcTdfaView v = lc_tdfa_view(g_blob);
+    const uint32_t t2 = cls_abs + 256 + v.h->off_t2;
+    if (t2 + (v.h->nstates + 1) * v.h->row_bytes > 65535u)
+        __trap(); // rows could not be addressed with 16 bits: the host must not select this kernel
+    for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x)
+        g_cls[k] = v.cls[k];
+    uint32_t* t2w = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(g_blob) + v.h->off_t2);
+    const uint32_t nent = (v.h->nstates + 1) * (v.h->row_bytes / 4);
+    for (uint32_t k = threadIdx.x; k < nent; k += blockDim.x)
+        t2w[k] += t2;
+}
+
 template <bool SLOW>
 __global__ void __launch_bounds__(1024, 1)
     regex_tdfa_staged_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, const uint8_t* __restrict__ base,
-                             const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
-                             uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
-                             uint32_t* __restrict__ cap_len, uint32_t reg_pitch /* halfwords */,
-                             unsigned long long* next_batch, uint32_t* overflow, const uint32_t* __restrict__ order) {
+                             const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len,
+                             uint32_t ev_stride, uint64_t n, uint32_t nkeys, uint8_t* __restrict__ status,
+                             uint32_t* __restrict__ cap_off, uint32_t* __restrict__ cap_len,
+                             uint32_t reg_pitch /* halfwords */, unsigned long long* next_batch, uint32_t* overflow,
+                             const uint32_t* __restrict__ order, const uint32_t* __restrict__ order_flag) {
     extern __shared__ uint4 smem[];
     // carve-out: [pad][class table, 256 B @ 256-aligned][blob][16 B][register files][line info: warps x 32 x 8 B]
     // [tiles: warps x 4 KB]
@@ -1450,8 +1555,7 @@ __global__ void __launch_bounds__(1024, 1)
     const uint32_t cls_abs = (s0abs + 255u) & ~255u;
     uint8_t* g_cls = reinterpret_cast<uint8_t*>(smem) + (cls_abs - s0abs);
     uint4* g_blob = reinterpret_cast<uint4*>(g_cls + 256);
-    for (uint32_t k = threadIdx.x; k < blob_bytes / 16; k += blockDim.x)
-        g_blob[k] = __ldg(blob + k);
+    tdfa_stage_blob(g_cls, cls_abs, blob, blob_bytes);
     __syncthreads();
     const LcTdfaView v = lc_tdfa_view(g_blob);
     TdfaAbs t;
@@ -1460,17 +1564,6 @@ __global__ void __launch_bounds__(1024, 1)
     t.ncls = v.h->ncls;
     t.row_bytes = v.h->row_bytes;
     t.inv_row = (uint32_t)((0x100000000ull + t.row_bytes - 1) / t.row_bytes);
-    if (t.t2 + (v.h->nstates + 1) * t.row_bytes > 65535u)
-        __trap(); // rows could not be addressed with 16 bits: the host must not select this kernel
-    for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x)
-        g_cls[k] = v.cls[k];
-    {
-        uint32_t* t2w = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(g_blob) + v.h->off_t2);
-        const uint32_t nent = (v.h->nstates + 1) * (t.row_bytes / 4);
-        for (uint32_t k = threadIdx.x; k < nent; k += blockDim.x)
-            t2w[k] += t.t2; // rebase: low 16 bits = absolute shared address of the next row
-    }
-    __syncthreads();
     const uint32_t G = v.h->ngroups;
     const uint32_t invG = G ? 0xFFFFFFFFu / G + 1 : 0; // umulhi(j, invG) == j / G for j < 65536
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1486,17 +1579,22 @@ __global__ void __launch_bounds__(1024, 1)
     // uniform-register operand PRMT cannot take its selector as an immediate (one extra MOV per look-up)
     sts_u64(info_abs + lane * 8, cls_abs, 0);
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t.cls) : "r"(info_abs + lane * 8) : "memory");
-    const uint4* gbase16 = reinterpret_cast<const uint4*>((uintptr_t)base & ~(uintptr_t)15);
     const uint32_t base_mis = (uint32_t)((uintptr_t)base & 15);
     const bool bool_only = cap_off == nullptr;
     const uint32_t dead = t.t2, sink = t.t2 + v.h->sink * t.row_bytes;
     uint16_t* rg = regs;
+    if (order && order_flag && *order_flag == 0) // the length pre-pass found a uniform batch: natural order
+        order = nullptr;
     // loader role of this lane: chunk column q of lines L0 + r (r = 0..7); tile slot of (chunk q, line) is
     // q * 512 + ((line ^ q) << 4): the XOR keeps the 8 writers of a line and the 32 readers of a row on distinct banks
-    const uint32_t ld_q = lane & 7, ld_L0 = (lane >> 3) * 8;
-    const uint32_t ld_info = info_abs + ld_L0 * 8;
-    const uint32_t ld_dst = tile_abs + (ld_q << 9) + (ld_L0 << 4);
-    const uint32_t rd_lane16 = lane << 4;
+    TdfaLoader L;
+    L.gbase16 = reinterpret_cast<const uint4*>((uintptr_t)base & ~(uintptr_t)15);
+    L.ld_q = lane & 7;
+    const uint32_t ld_L0 = (lane >> 3) * 8;
+    L.ld_info = info_abs + ld_L0 * 8;
+    L.ld_dst = tile_abs + (L.ld_q << 9) + (ld_L0 << 4);
+    L.tile_abs = tile_abs;
+    L.rd_lane16 = lane << 4;
     for (;;) {
         unsigned long long batch = 0;
         if (lane == 0)
@@ -1510,9 +1608,9 @@ __global__ void __launch_bounds__(1024, 1)
         const uint64_t i = (order && valid) ? order[batch + lane] : batch + lane;
         uint32_t off = 0, len = 0, mis = 0, nch = 0, g0 = 0;
         if (valid) {
-            off = ev_off[i];
-            len = ev_len[i];
-            if (len >= 65535u) { // capture registers are 16-bit: tell the host to redo the call with 32-bit slots
+            off = ev_off[i * ev_stride];
+            len = ev_len[i * ev_stride];
+            if (len >= 65535u) { // capture registers are 16-bit: regex_tdfa_long_kernel redoes this event afterwards
                 atomicExch(overflow, 1u);
                 len = 0;
             }
@@ -1525,57 +1623,9 @@ __global__ void __launch_bounds__(1024, 1)
         }
         sts_u64(info_abs + lane * 8, g0, nch);
         const uint32_t max_nch = __reduce_max_sync(0xFFFFFFFFu, nch);
-        // frame of the line: byte j of the line sits at frame index mis + j; pairs cover the even-aligned [qlo, Qe)
-        const uint32_t Q = len + mis, qlo = mis + (mis & 1), Qe = Q & ~1u;
-        const uint32_t kf_lo = (qlo + 15) >> 4, kf_hi = Qe >> 4; // fully paired chunks: [kf_lo, kf_hi)
-        const uint32_t k_tail = len ? (Q - 1) >> 4 : 0;
-        const bool has_head = len && !(kf_lo == 0 && kf_hi > 0);        // chunk 0 is not fully paired
-        const bool has_tail = len && k_tail >= kf_hi && !(has_head && k_tail == 0);
         uint32_t row = t.t2 + v.h->start * t.row_bytes;
         __syncwarp();
-        for (uint32_t s0 = 0; s0 < max_nch; s0 += LCT_STAGE_CHUNKS) {
-            // ---- cooperative fetch: instruction r moves chunks s0..s0+7 of lines r, r+8, r+16, r+24
-            {
-                const uint32_t cidx = s0 + ld_q;
-#pragma unroll
-                for (uint32_t r = 0; r < 8; ++r) {
-                    const uint2 inf = lds_u64_v(ld_info + r * 8);
-                    if (cidx < inf.y)
-                        cp_async_16(ld_dst + ((r ^ ld_q) << 4), gbase16 + inf.x + cidx);
-                }
-                cp_async_wait_all();
-            }
-            __syncwarp();
-            // ---- every lane walks its own line through the tile
-            if (row != dead) {
-                if (has_head && s0 == 0)
-                    row = tdfa_partial_chunk(v, t, row, tile_abs + rd_lane16, 0, mis, len, regs_m2, rg, sink);
-                const uint32_t ka = kf_lo > s0 ? kf_lo : s0;
-                const uint32_t kb = kf_hi < s0 + LCT_STAGE_CHUNKS ? kf_hi : s0 + LCT_STAGE_CHUNKS;
-                for (uint32_t k = ka; k < kb; ++k) {
-                    const uint32_t q = k & 7;
-                    const uint4 vv = lds_u128_v(tile_abs + (q << 9) + (rd_lane16 ^ (q << 4)));
-                    const uint32_t pos0 = k * 16 - mis;
-                    const uint32_t row_in = row;
-                    LCS_PAIR(vv.x, 0, pos0 + 0)
-                    LCS_PAIR(vv.x, 1, pos0 + 2)
-                    LCS_PAIR(vv.y, 0, pos0 + 4)
-                    LCS_PAIR(vv.y, 1, pos0 + 6)
-                    LCS_PAIR(vv.z, 0, pos0 + 8)
-                    LCS_PAIR(vv.z, 1, pos0 + 10)
-                    LCS_PAIR(vv.w, 0, pos0 + 12)
-                    LCS_PAIR(vv.w, 1, pos0 + 14)
-                    if (SLOW && row == sink) // some step set several registers: redo this chunk step by step
-                        row = t.t2 + t.row_bytes * tdfa_chunk_slow(v, __umulhi(row_in - t.t2, t.inv_row), vv, pos0, rg);
-                }
-                if (has_tail && k_tail - s0 < LCT_STAGE_CHUNKS) {
-                    const uint32_t q = k_tail & 7;
-                    row = tdfa_partial_chunk(v, t, row, tile_abs + (q << 9) + (rd_lane16 ^ (q << 4)), k_tail * 16, mis,
-                                             len, regs_m2, rg, sink);
-                }
-            }
-            __syncwarp();
-        }
+        row = tdfa_walk_lines<SLOW>(v, t, L, dead, sink, row, len, mis, max_nch, regs_m2, rg);
         uint32_t st = 1;
         if (valid) {
             bool ok = false;
@@ -1637,10 +1687,10 @@ __global__ void __launch_bounds__(1024, 1)
 }
 
 int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow, uint32_t nregs, const uint8_t* d_base,
-                             const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
-                             uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t threads,
-                             uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow,
-                             const uint32_t* d_order, cudaStream_t st) {
+                             const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint32_t ev_stride, uint64_t n,
+                             uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
+                             uint32_t threads, uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow,
+                             const uint32_t* d_order, const uint32_t* d_order_flag, cudaStream_t st) {
     if (!n)
         return 0;
     const uint32_t reg_pitch = tdfa_reg_pitch(nregs);
@@ -1649,9 +1699,294 @@ int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow,
     cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (er != cudaSuccess)
         return (int)er;
-    k<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, d_base, d_ev_off, d_ev_len, n, nkeys, d_status,
-                                   d_cap_off, d_cap_len, reg_pitch, d_next_batch, d_overflow, d_order);
+    k<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, d_base, d_ev_off, d_ev_len, ev_stride, n, nkeys,
+                                   d_status, d_cap_off, d_cap_len, reg_pitch, d_next_batch, d_overflow, d_order,
+                                   d_order_flag);
     return (int)cudaGetLastError();
+}
+
+// ---- several patterns in one grid (BASELINE config C5 "multi-pattern") ---------------------------------------
+// All automata are co-resident in shared memory (each with its own 256-byte aligned class table; every pair table
+// must end below shared address 64 Ki, which the host checks).  Per 32-line batch the patterns are tried in array
+// order: lanes whose line has not matched yet (and whose selector, if any, names this pattern) walk it, the others
+// only help fetching the tiles.  First match wins == what `(?:p0)|(?:p1)|...` would return under regex_match, with
+// the capture groups numbered per pattern.  which[i] = index of the matching pattern or 0xFF.
+// RESUME (patterns that do not fit together are spread over several launches): which[] holds the result of the
+// earlier launches; lines matched there are left alone, p_base = index of this launch's first pattern.
+struct TdfaPatS {
+    uint32_t cls, t2, ncls, row_bytes, inv_row, start_row, sink, G, nkeys, blob_off;
+};
+
+template <bool SLOW, bool RESUME>
+__global__ void __launch_bounds__(1024, 1)
+    regex_tdfa_multi_kernel(TdfaMultiArgs a, uint32_t p_base, const uint8_t* __restrict__ base,
+                            const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint64_t n,
+                            const uint8_t* __restrict__ sel, uint8_t* __restrict__ which, uint8_t* __restrict__ status,
+                            uint32_t* __restrict__ cap_off, uint32_t* __restrict__ cap_len, uint32_t gpitch,
+                            uint32_t reg_pitch /* halfwords */, unsigned long long* next_batch, uint32_t* overflow,
+                            const uint32_t* __restrict__ order, const uint32_t* __restrict__ order_flag) {
+    extern __shared__ uint4 smem[];
+    __shared__ TdfaPatS pats[LC_MULTI_MAX];
+    const uint32_t s0abs = (uint32_t)__cvta_generic_to_shared(smem);
+    uint32_t cursor = (s0abs + 255u) & ~255u;
+    uint8_t* const smem_b = reinterpret_cast<uint8_t*>(smem);
+    const uint32_t P = a.npat;
+    for (uint32_t p = 0; p < P; ++p) {
+        uint8_t* g_cls = smem_b + (cursor - s0abs);
+        tdfa_stage_blob(g_cls, cursor, reinterpret_cast<const uint4*>(a.blob[p]), a.blob_bytes[p]);
+        if (threadIdx.x == 0) {
+            const LcTdfaView v = lc_tdfa_view(g_cls + 256);
+            TdfaPatS ps;
+            ps.cls = cursor;
+            ps.t2 = cursor + 256 + v.h->off_t2;
+            ps.ncls = v.h->ncls;
+            ps.row_bytes = v.h->row_bytes;
+            ps.inv_row = (uint32_t)((0x100000000ull + ps.row_bytes - 1) / ps.row_bytes);
+            ps.start_row = ps.t2 + v.h->start * ps.row_bytes;
+            ps.sink = ps.t2 + v.h->sink * ps.row_bytes;
+            ps.G = v.h->ngroups;
+            ps.nkeys = a.nkeys[p];
+            ps.blob_off = cursor + 256 - s0abs;
+            pats[p] = ps;
+        }
+        cursor += 256 + ((a.blob_bytes[p] + 255u) & ~255u);
+    }
+    __syncthreads();
+    const uint32_t invG = gpitch ? 0xFFFFFFFFu / gpitch + 1 : 0;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint8_t* g_regs0 = smem_b + (cursor - s0abs) + 16;
+    uint16_t* wregs = reinterpret_cast<uint16_t*>(g_regs0) + (size_t)wid * 32 * reg_pitch;
+    uint16_t* regs = wregs + (size_t)lane * reg_pitch;
+    const uint32_t regs_abs = (uint32_t)__cvta_generic_to_shared(regs);
+    const uint32_t regs_m2 = regs_abs - 2;
+    const uint32_t aux_abs = (uint32_t)__cvta_generic_to_shared(g_regs0 + (size_t)blockDim.x * reg_pitch * 2);
+    const uint32_t info_abs = aux_abs + wid * 256;
+    const uint32_t tile_abs = aux_abs + nwarps * 256 + wid * (LCT_STAGE_CHUNKS * 512);
+    const uint32_t pats_abs = (uint32_t)__cvta_generic_to_shared(pats);
+    const uint32_t base_mis = (uint32_t)((uintptr_t)base & 15);
+    if (order && order_flag && *order_flag == 0)
+        order = nullptr;
+    TdfaLoader L;
+    L.gbase16 = reinterpret_cast<const uint4*>((uintptr_t)base & ~(uintptr_t)15);
+    L.ld_q = lane & 7;
+    const uint32_t ld_L0 = (lane >> 3) * 8;
+    L.ld_info = info_abs + ld_L0 * 8;
+    L.ld_dst = tile_abs + (L.ld_q << 9) + (ld_L0 << 4);
+    L.tile_abs = tile_abs;
+    L.rd_lane16 = lane << 4;
+    for (;;) {
+        unsigned long long batch = 0;
+        if (lane == 0)
+            batch = atomicAdd(next_batch, 32ull);
+        batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+        if (batch >= n)
+            break;
+        const bool valid = batch + lane < n;
+        const uint64_t i = (order && valid) ? order[batch + lane] : batch + lane;
+        uint32_t off = 0, len = 0, mis = 0, nch = 0, g0 = 0, selp = 0xFFu;
+        bool open = valid; // still looking for a matching pattern
+        bool skip_out = false;
+        if (valid) {
+            off = ev_off[i];
+            len = ev_len[i];
+            if (len >= 65535u) { // regex_tdfa_long_kernel handles this event (all patterns) afterwards
+                atomicExch(overflow, 1u);
+                len = 0;
+                open = false;
+            }
+            if (sel)
+                selp = sel[i];
+            if (RESUME && which[i] != 0xFFu) {
+                open = false;
+                skip_out = true;
+            }
+            const uint64_t ab = (uint64_t)base_mis + off;
+            mis = (uint32_t)(ab & 15);
+            g0 = (uint32_t)(ab >> 4);
+            nch = len ? (mis + len + 15) >> 4 : 0;
+        }
+        uint32_t st = 1, wh = 0xFFu, Gw = 0;
+        for (uint32_t p = 0; p < P; ++p) {
+            const bool act = open && (selp == 0xFFu || selp == p_base + p);
+            if (!__any_sync(0xFFFFFFFFu, act))
+                continue;
+            // this pattern's parameters, through volatile loads so that they live in per-thread registers (PRMT with
+            // an immediate selector needs a non-uniform operand, see regex_tdfa_staged_kernel)
+            TdfaAbs t;
+            uint32_t start_row, sink, Gp, nkp, blob_off;
+            {
+                const uint32_t pa = pats_abs + p * (uint32_t)sizeof(TdfaPatS);
+                asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t.cls) : "r"(pa) : "memory");
+                t.t2 = lds_u32_v(pa + 4);
+                t.ncls = lds_u32_v(pa + 8);
+                t.row_bytes = lds_u32_v(pa + 12);
+                t.inv_row = lds_u32_v(pa + 16);
+                start_row = lds_u32_v(pa + 20);
+                sink = lds_u32_v(pa + 24);
+                Gp = lds_u32_v(pa + 28);
+                nkp = lds_u32_v(pa + 32);
+                blob_off = lds_u32_v(pa + 36);
+            }
+            const LcTdfaView v = lc_tdfa_view(smem_b + blob_off);
+            const uint32_t dead = t.t2;
+            if (act)
+                for (uint32_t k = 0; k < Gp; ++k)
+                    reinterpret_cast<uint32_t*>(regs)[k] = 0xFFFFFFFFu;
+            const uint32_t nch_p = act ? nch : 0;
+            sts_u64(info_abs + lane * 8, g0, nch_p);
+            const uint32_t max_nch = __reduce_max_sync(0xFFFFFFFFu, nch_p);
+            uint32_t row = act ? start_row : dead;
+            __syncwarp();
+            row = tdfa_walk_lines<SLOW>(v, t, L, dead, sink, row, len, mis, max_nch, regs_m2, regs);
+            if (act) {
+                const uint32_t fin = v.eof[__umulhi(row - t.t2, t.inv_row)];
+                if (fin != LC_NONE_ENTRY) {
+                    lc_tdfa_run_ops(v, fin, len, regs);
+                    open = false;
+                    wh = p_base + p;
+                    Gw = Gp;
+                    st = Gp + 1 <= nkp ? 2 : 0;
+                }
+            }
+            __syncwarp();
+        }
+        if (valid && !skip_out) {
+            status[i] = (uint8_t)st;
+            which[i] = (uint8_t)wh;
+        }
+        if (gpitch == 0)
+            continue;
+        if (order) {
+            if (valid && !skip_out) {
+                uint32_t* co = cap_off + i * gpitch;
+                uint32_t* cl = cap_len + i * gpitch;
+                for (uint32_t g = 0; g < gpitch; ++g) {
+                    uint32_t o = 0, l = 0;
+                    if (st == 0 && g < Gw) {
+                        lc_slots16_to_cap(regs, g, len, &o, &l);
+                        o += off;
+                    }
+                    co[g] = o;
+                    cl[g] = l;
+                }
+            }
+            continue;
+        }
+        // coalesced rows of gpitch entries; info = {off, len | G << 16} of a matched line, 0xFFFFFFFF = zero row,
+        // 0xFFFFFFFE = row owned by an earlier launch (left alone)
+        sts_u64(info_abs + lane * 8, off, skip_out ? 0xFFFFFFFEu : (st == 0 ? (len | (Gw << 16)) : 0xFFFFFFFFu));
+        __syncwarp();
+        const uint64_t left = n - batch;
+        const uint32_t total = (uint32_t)(left < 32 ? left : 32) * gpitch;
+        uint32_t* go = cap_off + batch * gpitch + lane;
+        uint32_t* gl = cap_len + batch * gpitch + lane;
+        const uint32_t wbase = regs_m2 + 2 - lane * reg_pitch * 2;
+        for (uint32_t j = lane; j < total; j += 32, go += 32, gl += 32) {
+            const uint32_t line = gpitch == 1 ? j : __umulhi(j, invG), g = j - line * gpitch;
+            const uint2 inf = lds_u64_v(info_abs + line * 8);
+            if (inf.y == 0xFFFFFFFEu)
+                continue;
+            uint32_t o = 0, l = 0;
+            if (inf.y != 0xFFFFFFFFu && g < (inf.y >> 16)) {
+                const uint32_t ln = inf.y & 0xFFFFu;
+                const uint32_t be = lds_u32_v(wbase + line * reg_pitch * 2 + g * 4);
+                const uint32_t b = be & 0xFFFFu, en = be >> 16;
+                if (b == LC_SLOT16_UNSET || en == LC_SLOT16_UNSET || en < b) {
+                    o = inf.x + ln;
+                } else {
+                    o = inf.x + b;
+                    l = en - b;
+                }
+            }
+            *go = o;
+            *gl = l;
+        }
+        __syncwarp();
+    }
+}
+
+int launch_regex_tdfa_multi(const TdfaMultiArgs& a, uint32_t p_base, bool resume, bool slow, uint32_t max_nregs,
+                            const uint8_t* d_base, const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n,
+                            const uint8_t* d_sel, uint8_t* d_which, uint8_t* d_status, uint32_t* d_cap_off,
+                            uint32_t* d_cap_len, uint32_t gpitch, uint32_t threads, uint32_t grid,
+                            unsigned long long* d_next_batch, uint32_t* d_overflow, const uint32_t* d_order,
+                            const uint32_t* d_order_flag, cudaStream_t st) {
+    if (!n)
+        return 0;
+    const uint32_t reg_pitch = tdfa_reg_pitch(max_nregs);
+    size_t smem = tdfa_multi_smem_bytes(a, max_nregs, threads);
+    auto k = resume ? (slow ? regex_tdfa_multi_kernel<true, true> : regex_tdfa_multi_kernel<false, true>)
+                    : (slow ? regex_tdfa_multi_kernel<true, false> : regex_tdfa_multi_kernel<false, false>);
+    cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (er != cudaSuccess)
+        return (int)er;
+    k<<<grid, threads, smem, st>>>(a, p_base, d_base, d_ev_off, d_ev_len, n, d_sel, d_which, d_status, d_cap_off,
+                                   d_cap_len, gpitch, reg_pitch, d_next_batch, d_overflow, d_order, d_order_flag);
+    return (int)cudaGetLastError();
+}
+
+// ---- events of 65535 bytes or more: 32-bit capture registers, tables read from global memory ------------------
+// Launched unconditionally behind the staged kernels (which skip such events and raise *overflow); returns at once
+// when no event was that long, so the common case costs one empty launch and NO host round trip.  One thread per
+// long event, bytes fetched directly; patterns tried in order as in regex_tdfa_multi_kernel (npat = 1, which ==
+// nullptr: the single-pattern entry points).
+__global__ void __launch_bounds__(128)
+    regex_tdfa_long_kernel(TdfaMultiArgs a, const uint8_t* __restrict__ base, const uint32_t* __restrict__ ev_off,
+                           const uint32_t* __restrict__ ev_len, uint32_t ev_stride, uint64_t n,
+                           const uint8_t* __restrict__ sel, uint8_t* __restrict__ which, uint8_t* __restrict__ status,
+                           uint32_t* __restrict__ cap_off, uint32_t* __restrict__ cap_len, uint32_t gpitch,
+                           const uint32_t* __restrict__ overflow, int bool_only) {
+    if (*overflow == 0)
+        return;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t len = ev_len[i * ev_stride];
+        if (len < 65535u)
+            continue;
+        const uint32_t off = ev_off[i * ev_stride];
+        const uint8_t* s = base + off;
+        uint32_t regs[LC_TDFA_MAX_REGS + 2];
+        uint32_t st = 1, wh = 0xFFu, Gw = 0;
+        const uint32_t selp = sel ? sel[i] : 0xFFu;
+        for (uint32_t p = 0; p < a.npat && wh == 0xFFu; ++p) {
+            if (selp != 0xFFu && selp != p)
+                continue;
+            const LcTdfaView v = lc_tdfa_view(a.blob[p]);
+            for (uint32_t k = 0; k < 2 * v.h->ngroups; ++k)
+                regs[k] = 0xFFFFFFFFu;
+            if (lc_tdfa_event<uint32_t>(v, s, 0, len, regs)) {
+                wh = p;
+                Gw = v.h->ngroups;
+                st = Gw + 1 <= a.nkeys[p] ? 2 : 0;
+            }
+        }
+        if (bool_only) {
+            status[i] = wh != 0xFFu ? 1 : 0;
+            continue;
+        }
+        status[i] = (uint8_t)st;
+        if (which)
+            which[i] = (uint8_t)wh;
+        for (uint32_t g = 0; g < gpitch; ++g) {
+            uint32_t o = 0, l = 0;
+            if (st == 0 && g < Gw) {
+                lc_slots_to_cap(regs, g, len, &o, &l);
+                o += off;
+            }
+            cap_off[i * gpitch + g] = o;
+            cap_len[i * gpitch + g] = l;
+        }
+    }
+}
+
+void launch_regex_tdfa_long(const TdfaMultiArgs& a, const uint8_t* d_base, const uint32_t* d_ev_off,
+                            const uint32_t* d_ev_len, uint32_t ev_stride, uint64_t n, const uint8_t* d_sel,
+                            uint8_t* d_which, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
+                            uint32_t gpitch, const uint32_t* d_overflow, bool bool_only, cudaStream_t st) {
+    if (!n)
+        return;
+    unsigned grid = (unsigned)std::min<uint64_t>((n + 127) / 128, 1184);
+    regex_tdfa_long_kernel<<<grid, 128, 0, st>>>(a, d_base, d_ev_off, d_ev_len, ev_stride, n, d_sel, d_which, d_status,
+                                                 d_cap_off, d_cap_len, gpitch, d_overflow, bool_only ? 1 : 0);
 }
 
 template <class LabT>

@@ -19,8 +19,11 @@ inline uint32_t split_tiles(uint64_t len, uint32_t shift) {
 inline uint32_t scan_tiles(uint64_t n) { return (uint32_t)((n + kScanTile - 1) / kScanTile); }
 
 // a1: newline split.  desc: >= split_tiles() u64 (zeroed), ticket: u32 (zeroed), n_out: u32 device counter.
+// d_total: u64 device counter (zeroed) that receives the un-truncated number of split chars (the look-back payload
+// keeps 30 bits of count: the caller reports LC_ERR_TOO_LARGE beyond that).
 void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
-                  uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out, cudaStream_t st);
+                  uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
+                  unsigned long long* d_total, cudaStream_t st);
 
 // exclusive sum of u32 -> u64 (out has n entries; *d_total receives the grand total)
 void launch_exclusive_sum(const uint32_t* d_in, uint64_t n, uint64_t* d_out, uint64_t* d_total, uint64_t* d_desc,
@@ -38,7 +41,8 @@ void launch_label_sizes(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_sizes,
 // d_out[0] = max(ev_len), d_out[1] = sum(ev_len); d_out must be zeroed by the caller
 void launch_len_stats(const uint32_t* d_ev_len, uint64_t n, unsigned long long* d_out, cudaStream_t st);
 
-// order[] = event indices sorted by descending length bucket (d_hist64: 64-word scratch); 3 launches
+// order[] = event indices sorted by descending length bucket (d_hist64: 64-word scratch + 1 flag word); 3 launches.
+// d_hist64[64] = 1 when the lengths span more than two adjacent buckets (a ragged batch: use the order), else 0.
 void launch_length_order(const uint32_t* d_ev_len, uint64_t n, uint32_t* d_hist64, uint32_t* d_order,
                          cudaStream_t st);
 
@@ -99,10 +103,41 @@ inline size_t tdfa_staged_smem_bytes(uint32_t blob_bytes, uint32_t nregs, uint32
            (size_t)(threads / 32) * (256 + 4096);
 }
 int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow, uint32_t nregs, const uint8_t* d_base,
-                             const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
-                             uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t threads,
-                             uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow,
-                             const uint32_t* d_order /* or nullptr */, cudaStream_t st);
+                             const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint32_t ev_stride /* elements */,
+                             uint64_t n, uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
+                             uint32_t threads, uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow,
+                             const uint32_t* d_order /* or nullptr */, const uint32_t* d_order_flag /* or nullptr */,
+                             cudaStream_t st);
+
+// several patterns in one grid: all tagged-DFA blobs co-resident in shared memory, tried per line in array order
+constexpr uint32_t LC_MULTI_MAX = 8;
+struct TdfaMultiArgs {
+    const void* blob[LC_MULTI_MAX]; // device tdfa blobs
+    uint32_t blob_bytes[LC_MULTI_MAX];
+    uint32_t nkeys[LC_MULTI_MAX];
+    uint32_t npat;
+};
+inline size_t tdfa_multi_table_bytes(const TdfaMultiArgs& a) {
+    size_t t = 256;
+    for (uint32_t p = 0; p < a.npat; ++p)
+        t += 256 + ((a.blob_bytes[p] + 255u) & ~255u);
+    return t;
+}
+inline size_t tdfa_multi_smem_bytes(const TdfaMultiArgs& a, uint32_t max_nregs, uint32_t threads) {
+    return tdfa_multi_table_bytes(a) + 16 + (size_t)threads * tdfa_reg_pitch(max_nregs) * 2 +
+           (size_t)(threads / 32) * (256 + 4096);
+}
+int launch_regex_tdfa_multi(const TdfaMultiArgs& a, uint32_t p_base, bool resume, bool slow, uint32_t max_nregs,
+                            const uint8_t* d_base, const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n,
+                            const uint8_t* d_sel, uint8_t* d_which, uint8_t* d_status, uint32_t* d_cap_off,
+                            uint32_t* d_cap_len, uint32_t gpitch, uint32_t threads, uint32_t grid,
+                            unsigned long long* d_next_batch, uint32_t* d_overflow, const uint32_t* d_order,
+                            const uint32_t* d_order_flag, cudaStream_t st);
+// events >= 65535 bytes (skipped by the staged kernels, which raise *d_overflow): 32-bit registers, no-op otherwise
+void launch_regex_tdfa_long(const TdfaMultiArgs& a, const uint8_t* d_base, const uint32_t* d_ev_off,
+                            const uint32_t* d_ev_len, uint32_t ev_stride, uint64_t n, const uint8_t* d_sel,
+                            uint8_t* d_which, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len,
+                            uint32_t gpitch, const uint32_t* d_overflow, bool bool_only, cudaStream_t st);
 
 // parse status -> boolean (1 = the whole value matched)
 void launch_status_to_bool(uint8_t* d_status, uint64_t n, cudaStream_t st);

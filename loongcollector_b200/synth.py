@@ -192,6 +192,44 @@ def java_stack_records(n_records, seed=DEFAULT_SEED, mean_frames=20, unmatched_f
 
 def csv_lines(n, seed=DEFAULT_SEED, pool=16384):
     """C4: CSV lines, 10 fields, ~160 B, 5 % quoted fields, 0.5 % doubled quotes; field 3 is url-like."""
+    return _assemble(csv_pool(n, seed, pool), n, seed + 1)
+
+
+CSV_KEYS = ["ip", "f1", "f2", "url", "f4", "f5", "f6", "f7", "f8", "f9"]
+CSV_URL_PATTERN = r"(/[^?]*)\?k=(\w+)"
+
+
+def zipf_mixed_lines(n, seed=DEFAULT_SEED, s=1.1, lo=64, hi=8192, pool=8192):
+    """C5: 50/50 nginx (NGINX_PATTERN) and apache (APACHE_PATTERN) lines, length ~ Zipf(s) clipped to [lo, hi].
+    Returns (buffer, off, len, is_apache[n] bool)."""
+    lines, kinds = zipf_mixed_pool(n, seed, s, lo, hi, pool)
+    buf, off, ln = _assemble(lines, n, seed + 1)
+    idx = pool_index(len(lines), n, seed + 1)
+    return buf, off, ln, kinds[idx]
+
+
+def zipf_mixed_pool(n, seed=DEFAULT_SEED, s=1.1, lo=64, hi=8192, pool=8192):
+    """The distinct template lines zipf_mixed_lines() samples from (each ends with '\\n') and their kinds; line i of
+    zipf_mixed_lines(n, seed, ...) is pool entry pool_index(len(pool), n, seed + 1)[i]."""
+    rng = random.Random(seed)
+    rs = np.random.default_rng(seed + 3)
+    pool_n = max(8, min(n, pool))
+    lens = np.clip(lo - 1 + rs.zipf(s, size=pool_n), lo, hi)
+    lines, kinds = [], []
+    for k in range(pool_n):
+        L = int(lens[k])
+        if rng.random() < 0.5:
+            base = _nginx_line(rng, max(L - 1, 120))
+            kinds.append(0)
+        else:
+            base = _apache_line(rng, max(L - 1, 120))
+            kinds.append(1)
+        lines.append((base + "\n").encode("ascii"))
+    return lines, np.array(kinds, bool)
+
+
+def csv_pool(n, seed=DEFAULT_SEED, pool=16384):
+    """The distinct template lines csv_lines() samples from (same construction; index = pool_index(.., seed + 1))."""
     rng = random.Random(seed)
     pool_n = max(8, min(n, pool))
     lines = []
@@ -211,32 +249,4 @@ def csv_lines(n, seed=DEFAULT_SEED, pool=16384):
                 c = '"' + c + ',x"'
             cells.append(c)
         lines.append((",".join(cells) + "\n").encode("ascii"))
-    return _assemble(lines, n, seed + 1)
-
-
-CSV_KEYS = ["ip", "f1", "f2", "url", "f4", "f5", "f6", "f7", "f8", "f9"]
-CSV_URL_PATTERN = r"(/[^?]*)\?k=(\w+)"
-
-
-def zipf_mixed_lines(n, seed=DEFAULT_SEED, s=1.1, lo=64, hi=8192, pool=8192):
-    """C5: 50/50 nginx (NGINX_PATTERN) and apache (APACHE_PATTERN) lines, length ~ Zipf(s) clipped to [lo, hi].
-    Returns (buffer, off, len, is_apache[n] bool)."""
-    rng = random.Random(seed)
-    rs = np.random.default_rng(seed + 3)
-    pool_n = max(8, min(n, pool))
-    lens = np.clip(lo - 1 + rs.zipf(s, size=pool_n), lo, hi)
-    # Zipf(1.1) is extremely heavy-tailed: rescale ranks into [lo, hi] by log so the clip does not dominate
-    lens = np.clip((lo * np.power(hi / lo, rs.random(pool_n) ** 3)).astype(np.int64), lo, hi) if False else lens
-    lines, kinds = [], []
-    for k in range(pool_n):
-        L = int(lens[k])
-        if rng.random() < 0.5:
-            base = _nginx_line(rng, max(L - 1, 120))
-            kinds.append(0)
-        else:
-            base = _apache_line(rng, max(L - 1, 120))
-            kinds.append(1)
-        lines.append((base + "\n").encode("ascii"))
-    buf, off, ln = _assemble(lines, n, seed + 1)
-    idx = np.random.default_rng(seed + 1).integers(0, pool_n, size=n)
-    return buf, off, ln, np.array(kinds, bool)[idx]
+    return lines
