@@ -112,6 +112,18 @@ int lc_regex_parse_dev(lc_engine_t* e, const lc_regex_t* re, const uint8_t* d_ba
                        const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint64_t n, uint32_t nkeys,
                        uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len);
 
+/* Batched event groups -- Processor::Process(std::vector<PipelineEventGroup>&) (Processor.h:31): the arenas of many
+ * groups (<= 512 KB each, LogFileReader.cpp:97) go up back to back into ONE packed device arena and are parsed by one
+ * launch sequence, instead of one launch + six copies + one sync per group.  Span k = the bytes
+ * [span_ptr[k], + span_len[k]) of one group's SourceBuffer chunk (DMA-able without staging when it was allocated
+ * with lc_host_alloc); it lands at [span_dst[k], + span_len[k]) of the packed arena (16-byte aligned, ascending,
+ * non-overlapping, below packed_len).  Events [span_first_ev[k], span_first_ev[k+1]) belong to span k; ev_off[] and
+ * the returned cap_off[] are relative to the PACKED arena (host address = span_ptr[k] + (off - span_dst[k])). */
+int lc_regex_parse_packed(lc_engine_t* e, const lc_regex_t* re, uint64_t nspans, const uint8_t* const* span_ptr,
+                          const uint32_t* span_len, const uint32_t* span_dst, const uint64_t* span_first_ev,
+                          uint64_t packed_len, const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n,
+                          uint32_t nkeys, uint8_t* status, uint32_t* cap_off, uint32_t* cap_len);
+
 /* Same, with the event table read in place from a strided table: event i = (d_ev_off[i * ev_stride],
  * d_ev_len[i * ev_stride]).  Lets one processor's output feed the next without a gather -- e.g. column k of
  * lc_delim_parse_dev's [n][max_fields] tables (d_f_off + k, d_f_len + k, stride max_fields) is the event table of

@@ -7,6 +7,7 @@
  */
 #ifndef LC_B200_HOST_H
 #define LC_B200_HOST_H
+#include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -29,6 +30,24 @@ void lc_host_string_free(char* s);
  * group described by group_json; enable_ns = GlobalConfig::mEnableTimestampNanosecond.  Returns the malloc'd wire
  * bytes (free with lc_host_string_free) and their length, or NULL + *err_out = the reference's error message. */
 char* lc_host_sls_serialize(const char* group_json, int enable_ns, unsigned long long* len_out, char** err_out);
+
+/* Makes every SourceBuffer chunk created from now on pinned (lc_host_alloc): a group's arena is then DMA-able in
+ * place -- the integration's replacement of SourceBuffer's `new char[]` (core/common/memory/SourceBuffer.h:98-131). */
+void lc_host_use_pinned_arenas(int on);
+
+/* End-to-end run at the plugin boundary (bench.py's `e2e`).  Builds event groups of <= group_bytes from the line
+ * table (one arena chunk per group, one LogEvent {"content": line} per line: the state the reader + split processor
+ * leave, LogFileReader.cpp:97) and times `reps` repetitions of
+ *   mode 0: ProcessorInstance::Process with ONE group per call (a ProcessorRunner thread popping groups),
+ *   mode 1: ProcessorInstance::Process(std::vector<PipelineEventGroup>&) with ALL groups (batched override).
+ * data[line_off[i] + line_len[i]] must be readable (the separator byte travels with the line).  Groups are rebuilt,
+ * untimed, before every repetition.  seconds_out[reps] = wall time of the Process calls of each repetition.
+ * stats_out[12] = groups, in events, out events, live contents, content checksum (sum of key.size*131 +
+ * value.size*31 + first value byte), arena bytes, then ProcessorInstance's counters: in events, out events, in
+ * bytes, out bytes, process ns, process ms (summed over all repetitions).  Returns 0, or 1 + *err_out. */
+int lc_host_bench_plugin(const char* type, const char* config_json, const uint8_t* data, const uint32_t* line_off,
+                         const uint32_t* line_len, uint64_t n_lines, uint32_t group_bytes, int mode, int reps,
+                         double* seconds_out, uint64_t stats_out[12], char** err_out);
 
 #ifdef __cplusplus
 }

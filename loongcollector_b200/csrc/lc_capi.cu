@@ -976,6 +976,116 @@ int lc_regex_parse(lc_engine_t* e, const lc_regex_t* re, const uint8_t* base, ui
     return pipelined_events(e, base, base_len, ev_off, ev_len, n, nchunks, "lc_regex_parse", run, down);
 }
 
+// Batched event groups: span k (one group's arena bytes, ideally pinned: lc_host_alloc) is uploaded to
+// [span_dst[k], + span_len[k]) of ONE packed device arena; the event table addresses the packed arena.  Chunks of
+// ~32 MB of whole spans flow through the same three-stream pipeline as lc_regex_parse.
+int lc_regex_parse_packed(lc_engine_t* e, const lc_regex_t* re, uint64_t nspans, const uint8_t* const* span_ptr,
+                          const uint32_t* span_len, const uint32_t* span_dst, const uint64_t* span_first_ev,
+                          uint64_t packed_len, const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n,
+                          uint32_t nkeys, uint8_t* status, uint32_t* cap_off, uint32_t* cap_len) {
+    if (!e || !re || (nspans && (!span_ptr || !span_len || !span_dst || !span_first_ev)) ||
+        (n && (!ev_off || !ev_len || !status)))
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_packed: bad arguments");
+    int rc = check_regex_usable(re, "lc_regex_parse_packed");
+    if (rc)
+        return rc;
+    if (n == 0)
+        return LC_OK;
+    const uint32_t G = re->res.ngroups;
+    if (G && (!cap_off || !cap_len))
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_packed: bad arguments");
+    if (packed_len >= 0xFFFFFFF0ull || n >= (1ull << 30))
+        return fail(LC_ERR_TOO_LARGE, "packed arena must be < 4 GiB and < 2^30 events per call");
+    if (nspans == 0 || span_first_ev[0] != 0 || span_first_ev[nspans] != n)
+        return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_packed: span_first_ev must cover [0, n]");
+    rc = bind(e);
+    if (rc)
+        return rc;
+    CU_TRY(e->in.ensure(packed_len + 16));
+    CU_TRY(e->ev_off.ensure(n * 4));
+    CU_TRY(e->ev_len.ensure(n * 4));
+    CU_TRY(e->out_a.ensure(n));
+    CU_TRY(e->out_b.ensure(n * G * 4 + 4));
+    CU_TRY(e->out_c.ensure(n * G * 4 + 4));
+    // chunk boundaries (in spans): ~32 MB of arena bytes each, at most 64 chunks
+    std::vector<uint64_t> cut{0};
+    {
+        const uint64_t target = std::max<uint64_t>(32ull << 20, packed_len / 64 + 1);
+        uint64_t acc = 0;
+        for (uint64_t k = 0; k < nspans; ++k) {
+            acc += span_len[k];
+            if (acc >= target && k + 1 < nspans) {
+                cut.push_back(k + 1);
+                acc = 0;
+            }
+        }
+        cut.push_back(nspans);
+    }
+    const uint64_t nchunks = cut.size() - 1;
+    rc = ensure_copy_streams(e, (int)nchunks);
+    if (rc)
+        return rc;
+    uint8_t* d_in = e->in.as<uint8_t>();
+    uint32_t* d_off = e->ev_off.as<uint32_t>();
+    uint32_t* d_len = e->ev_len.as<uint32_t>();
+    auto drain = [&](int code) {
+        cudaStreamSynchronize(e->s_h2d);
+        cudaStreamSynchronize(e->stream);
+        cudaStreamSynchronize(e->s_d2h);
+        return code;
+    };
+#define LC_PIPE_TRY(expr)                                                                                              \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess)                                                                                         \
+            return drain(fail(LC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)));                        \
+    } while (0)
+    LC_PIPE_TRY(cudaEventRecord(e->ev_comp[0], e->stream));
+    LC_PIPE_TRY(cudaStreamWaitEvent(e->s_h2d, e->ev_comp[0], 0));
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const uint64_t k0 = cut[c], k1 = cut[c + 1];
+        const uint64_t i0 = span_first_ev[k0], i1 = span_first_ev[k1], cnt = i1 - i0;
+        uint64_t span_bytes = 0;
+        for (uint64_t k = k0; k < k1; ++k) {
+            const uint64_t lo = span_dst[k], hi = lo + span_len[k];
+            if ((lo & 15u) || hi > packed_len || span_first_ev[k] > span_first_ev[k + 1] ||
+                (k + 1 < nspans && hi > span_dst[k + 1]))
+                return drain(fail(LC_ERR_INVALID_ARG, "lc_regex_parse_packed: spans must be 16-byte aligned, ordered "
+                                                      "and inside the packed arena"));
+            for (uint64_t i = span_first_ev[k]; i < span_first_ev[k + 1]; ++i)
+                if (ev_off[i] < lo || (uint64_t)ev_off[i] + ev_len[i] > hi)
+                    return drain(fail(LC_ERR_INVALID_ARG, "lc_regex_parse_packed: event outside its span"));
+            if (span_len[k])
+                LC_PIPE_TRY(cudaMemcpyAsync(d_in + lo, span_ptr[k], span_len[k], cudaMemcpyHostToDevice, e->s_h2d));
+            span_bytes += span_len[k];
+        }
+        if (cnt) {
+            LC_PIPE_TRY(cudaMemcpyAsync(d_off + i0, ev_off + i0, cnt * 4, cudaMemcpyHostToDevice, e->s_h2d));
+            LC_PIPE_TRY(cudaMemcpyAsync(d_len + i0, ev_len + i0, cnt * 4, cudaMemcpyHostToDevice, e->s_h2d));
+        }
+        LC_PIPE_TRY(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
+        if (!cnt)
+            continue;
+        LC_PIPE_TRY(cudaStreamWaitEvent(e->stream, e->ev_h2d[c], 0));
+        rc = regex_parse_dev_impl(e, re, d_in, packed_len, span_bytes, d_off + i0, d_len + i0, 1, cnt, nkeys,
+                                  e->out_a.as<uint8_t>() + i0, e->out_b.as<uint32_t>() + i0 * G,
+                                  e->out_c.as<uint32_t>() + i0 * G, false);
+        if (rc)
+            return drain(rc);
+        LC_PIPE_TRY(cudaEventRecord(e->ev_comp[c], e->stream));
+        LC_PIPE_TRY(cudaStreamWaitEvent(e->s_d2h, e->ev_comp[c], 0));
+        LC_PIPE_TRY(cudaMemcpyAsync(status + i0, e->out_a.as<uint8_t>() + i0, cnt, cudaMemcpyDeviceToHost, e->s_d2h));
+        if (G) {
+            LC_PIPE_TRY(cudaMemcpyAsync(cap_off + i0 * G, e->out_b.as<uint32_t>() + i0 * G, cnt * G * 4,
+                                        cudaMemcpyDeviceToHost, e->s_d2h));
+            LC_PIPE_TRY(cudaMemcpyAsync(cap_len + i0 * G, e->out_c.as<uint32_t>() + i0 * G, cnt * G * 4,
+                                        cudaMemcpyDeviceToHost, e->s_d2h));
+        }
+    }
+#undef LC_PIPE_TRY
+    return drain(LC_OK);
+}
+
 // ------------------------------------------------------------------------------------------------ multi-pattern
 int lc_regex_parse_multi_dev(lc_engine_t* e, const lc_regex_t* const* res, uint32_t npat, const uint32_t* nkeys,
                              const uint8_t* d_base, uint64_t base_len, const uint32_t* d_ev_off,

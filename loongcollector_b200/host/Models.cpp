@@ -32,11 +32,18 @@ void LogEvent::SetContent(StringView key, StringView val) {
 void LogEvent::SetContentNoCopy(StringView key, StringView val) {
     for (auto it = mContents.rbegin(); it != mContents.rend(); ++it)
         if (it->second && it->first.first == key) {
+            mAllocatedContentSize += key.size() + val.size() - it->first.first.size() - it->first.second.size();
             it->first = std::make_pair(key, val);
             return;
         }
     ++mContentCnt;
+    mAllocatedContentSize += key.size() + val.size();
     mContents.emplace_back(std::make_pair(key, val), true);
+}
+
+// LogEvent.cpp:165-167: timestamp + optional nanosecond + the vector header + bytes of the live keys and values
+size_t LogEvent::DataSize() const {
+    return PipelineEvent::DataSize() + sizeof(mContents) + mAllocatedContentSize;
 }
 
 void LogEvent::DelContent(StringView key) {
@@ -44,6 +51,7 @@ void LogEvent::DelContent(StringView key) {
         if (it->second && it->first.first == key) {
             it->second = false;
             --mContentCnt;
+            mAllocatedContentSize -= it->first.first.size() + it->first.second.size();
             return;
         }
 }

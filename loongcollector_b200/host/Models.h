@@ -38,8 +38,17 @@ struct StringBuffer {
 // Chunked bump arena.  Chunks double from 4 KiB up to 128 KiB; a request of at least half the current chunk
 // size gets its own allocation (same growth rule as the reference so that a file read lands in ONE chunk).
 // Every string buffer is NUL-terminated one past its end.
+// Chunks come from operator new[] by default; a process that hands its arenas to the GPU engine installs the
+// engine's pinned allocator (lc_host_alloc / lc_host_free) with SetChunkAllocator so that a group's bytes are
+// DMA-able in place -- the "SourceBuffer zero-copy arena" stays the only copy of the log bytes on the host.
 class SourceBuffer {
 public:
+    using AllocFn = void* (*)(size_t);
+    using FreeFn = void (*)(void*);
+    static void SetChunkAllocator(AllocFn a, FreeFn f) {
+        sAlloc = a;
+        sFree = f;
+    }
     SourceBuffer() = default;
     SourceBuffer(const SourceBuffer&) = delete;
     SourceBuffer& operator=(const SourceBuffer&) = delete;
@@ -73,21 +82,41 @@ public:
     }
 
 private:
+    struct ChunkFree {
+        FreeFn fn; // allocator that was active when the chunk was made (nullptr: operator new[])
+        ChunkFree() : fn(nullptr) {}
+        explicit ChunkFree(FreeFn f) : fn(f) {}
+        void operator()(char* p) const {
+            if (fn)
+                fn(p);
+            else
+                delete[] p;
+        }
+    };
     struct Chunk {
-        std::unique_ptr<char[]> mem;
+        std::unique_ptr<char[], ChunkFree> mem;
         size_t cap = 0, used = 0;
     };
+    static std::unique_ptr<char[], ChunkFree> NewChunk(size_t bytes) {
+        if (sAlloc && sFree) {
+            if (void* p = sAlloc(bytes))
+                return std::unique_ptr<char[], ChunkFree>(static_cast<char*>(p), ChunkFree(sFree));
+        }
+        return std::unique_ptr<char[], ChunkFree>(new char[bytes], ChunkFree());
+    }
+    inline static AllocFn sAlloc = nullptr;
+    inline static FreeFn sFree = nullptr;
     char* Allocate(size_t bytes) {
         if (bytes * 2 >= mNextChunk) { // oversize: own allocation
             Chunk c;
-            c.mem.reset(new char[bytes]);
+            c.mem = NewChunk(bytes);
             c.cap = c.used = bytes;
             mChunks.insert(mChunks.begin(), std::move(c)); // keep the current bump chunk last
             return mChunks.front().mem.get();
         }
         if (mChunks.empty() || mChunks.back().used + bytes > mChunks.back().cap || mChunks.back().cap != mCurCap) {
             Chunk c;
-            c.mem.reset(new char[mNextChunk]);
+            c.mem = NewChunk(mNextChunk);
             c.cap = mNextChunk;
             mCurCap = mNextChunk;
             mChunks.push_back(std::move(c));
@@ -119,6 +148,8 @@ public:
     }
     std::shared_ptr<SourceBuffer>& GetSourceBuffer();
     virtual Json::Value ToJson(bool enableEventMeta) const = 0;
+    // PipelineEvent.h:62 -- what ProcessorInstance's in / out byte counters add up
+    virtual size_t DataSize() const { return sizeof(mTimestamp) + sizeof(mTimestampNanosecond); }
 
 protected:
     PipelineEvent(Type t, PipelineEventGroup* g) : mType(t), mGroup(g) {}
@@ -158,10 +189,12 @@ public:
     std::pair<uint64_t, uint64_t> GetPosition() const { return {mFileOffset, mRawSize}; }
     Json::Value ToJson(bool enableEventMeta) const override;
     bool FromJson(const Json::Value& root);
+    size_t DataSize() const override;
 
 private:
     std::vector<Content> mContents;
     size_t mContentCnt = 0;
+    size_t mAllocatedContentSize = 0;
     uint64_t mFileOffset = 0, mRawSize = 0;
 };
 
@@ -173,6 +206,7 @@ public:
     void SetContent(const std::string& c);
     Json::Value ToJson(bool enableEventMeta) const override;
     bool FromJson(const Json::Value& root);
+    size_t DataSize() const override { return PipelineEvent::DataSize() + mContent.size(); } // RawEvent.cpp:47-49
 
 private:
     StringView mContent;
@@ -246,6 +280,17 @@ public:
     const GroupMetadata& GetAllMetadata() const { return mMetadata; }
     void SetTag(const std::string& key, const std::string& val);
     const std::map<StringView, StringView>& GetTags() const { return mTags; }
+
+    // PipelineEventGroup.cpp:333-339: the events vector header + every event + the tags (SizedMap: header + bytes)
+    size_t DataSize() const {
+        size_t s = sizeof(mEvents);
+        for (const auto& e : mEvents)
+            s += e->DataSize();
+        s += sizeof(mTags);
+        for (const auto& kv : mTags)
+            s += kv.first.size() + kv.second.size();
+        return s;
+    }
 
     Json::Value ToJson(bool enableEventMeta = false) const;
     bool FromJson(const Json::Value& root);

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <stdexcept>
+#include <thread>
 
 namespace logtail {
 
@@ -35,6 +36,70 @@ lc_engine_t* Engine() {
 void Check(int rc, const char* what) {
     if (rc != LC_OK)
         throw std::runtime_error(std::string(what) + ": " + lc_last_error());
+}
+
+// Grow-only pinned host table (lc_host_alloc): result tables land here by DMA without a staging copy.
+template <class T>
+struct PinnedVec {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~PinnedVec() { lc_host_free(p); }
+    T* ensure(size_t n) {
+        if (n > cap) {
+            lc_host_free(p);
+            cap = n + n / 4 + 64;
+            p = static_cast<T*>(lc_host_alloc(cap * sizeof(T)));
+            if (!p) {
+                cap = 0;
+                throw std::runtime_error(std::string("loongcollector_b200: ") + lc_last_error());
+            }
+        }
+        return p;
+    }
+};
+
+struct ThreadScratch {
+    PinnedVec<uint32_t> off, len, capOff, capLen;
+    PinnedVec<uint8_t> status, staging;
+};
+ThreadScratch& Scratch() {
+    static thread_local ThreadScratch s;
+    return s;
+}
+
+// Host threads used for the gather / epilogue of a batched Process call (env LC_B200_HOST_THREADS, default 16, at most
+// the hardware concurrency).  The reference spends this work on its process_thread_count ProcessorRunner threads.
+unsigned HostThreads() {
+    static const unsigned n = [] {
+        const char* e = getenv("LC_B200_HOST_THREADS");
+        unsigned hw = std::thread::hardware_concurrency();
+        unsigned want = e ? (unsigned)atoi(e) : 16u;
+        if (want < 1)
+            want = 1;
+        if (hw && want > hw)
+            want = hw;
+        return want;
+    }();
+    return n;
+}
+
+// fn(begin, end, thread) over [0, n) in contiguous slices
+template <class Fn>
+void ParallelFor(size_t n, size_t minPerThread, Fn fn) {
+    unsigned t = HostThreads();
+    if (minPerThread && n / minPerThread < t)
+        t = (unsigned)std::max<size_t>(1, n / minPerThread);
+    if (t <= 1) {
+        fn((size_t)0, n, 0u);
+        return;
+    }
+    std::vector<std::thread> th;
+    th.reserve(t - 1);
+    for (unsigned k = 1; k < t; ++k)
+        th.emplace_back([&, k] { fn(n * k / t, n * (k + 1) / t, k); });
+    fn((size_t)0, n / t, 0u);
+    for (auto& x : th)
+        x.join();
 }
 
 // Flattens the source values of the events to be parsed into (base, off[], len[]).  If every value lies
@@ -315,9 +380,9 @@ bool ProcessorSplitMultilineLogStringNative::Init(const Json::Value& config) {
 }
 
 std::vector<std::pair<std::string, uint64_t>> ProcessorSplitMultilineLogStringNative::Counters() const {
-    return {{"matched_events", mMatchedEventsTotal.v},
-            {"matched_lines", mMatchedLinesTotal.v},
-            {"unmatched_lines", mUnmatchedLinesTotal.v}};
+    return {{"matched_events", mMatchedEventsTotal.GetValue()},
+            {"matched_lines", mMatchedLinesTotal.GetValue()},
+            {"unmatched_lines", mUnmatchedLinesTotal.GetValue()}};
 }
 
 void ProcessorSplitMultilineLogStringNative::Process(PipelineEventGroup& group) {
@@ -419,86 +484,277 @@ bool ProcessorParseRegexNative::Init(const Json::Value& config) {
 }
 
 std::vector<std::pair<std::string, uint64_t>> ProcessorParseRegexNative::Counters() const {
-    return {{"discarded", mDiscardedEventsTotal.v},
-            {"out_failed", mOutFailedEventsTotal.v},
-            {"out_key_not_found", mOutKeyNotFoundEventsTotal.v},
-            {"out_successful", mOutSuccessfulEventsTotal.v}};
+    return {{"discarded", mDiscardedEventsTotal.GetValue()},
+            {"out_failed", mOutFailedEventsTotal.GetValue()},
+            {"out_key_not_found", mOutKeyNotFoundEventsTotal.GetValue()},
+            {"out_successful", mOutSuccessfulEventsTotal.GetValue()}};
+}
+
+void ProcessorParseRegexNative::AddCounters(const LocalCounters& c) {
+    if (c.discarded)
+        mDiscardedEventsTotal.Add(c.discarded);
+    if (c.failed)
+        mOutFailedEventsTotal.Add(c.failed);
+    if (c.keyNotFound)
+        mOutKeyNotFoundEventsTotal.Add(c.keyNotFound);
+    if (c.successful)
+        mOutSuccessfulEventsTotal.Add(c.successful);
+}
+
+// ProcessEvent (:132-168) with the regex verdict already known.  r == nullptr: the event never reached the engine
+// (unsupported type, source key absent, or whole-line mode).
+bool ProcessorParseRegexNative::FinishEvent(PipelineEventGroup& group, PipelineEventPtr& e, const EventResult* r,
+                                            LocalCounters& c) const {
+    if (!IsSupportedEvent(e)) {
+        ++c.failed;
+        return true;
+    }
+    LogEvent& ev = e.Cast<LogEvent>();
+    if (!ev.HasContent(mSourceKey)) {
+        ++c.keyNotFound;
+        return true;
+    }
+    StringView rawContent = ev.GetContent(mSourceKey);
+    bool ok = true;
+    if (mIsWholeLineMode) {
+        AddLog(ev, mKeys.empty() ? StringView("content") : StringView(mKeys[0]), rawContent);
+    } else if (r->status == LC_REGEX_NOMATCH) {
+        ++c.failed;
+        ok = false;
+    } else if (r->status == LC_REGEX_KEYS_MISMATCH) {
+        ok = false;
+    } else {
+        for (uint32_t k = 0; k < mKeys.size(); ++k)
+            AddLog(ev, mKeys[k], StringView(r->origin + (r->capOff[k] - r->originOff), r->capLen[k]));
+    }
+    if (!ok || !mSourceKeyOverwritten)
+        ev.DelContent(mSourceKey);
+    if (mCommonParserOptions.ShouldAddSourceContent(ok))
+        AddLog(ev, mCommonParserOptions.mRenamedSourceKey, rawContent, false);
+    if (mCommonParserOptions.ShouldAddLegacyUnmatchedRawLog(ok))
+        AddLog(ev, CommonParserOptions::legacyUnmatchedRawLogKey, rawContent, false);
+    if (mCommonParserOptions.ShouldEraseEvent(ok, ev, group.GetAllMetadata())) {
+        ++c.discarded;
+        return false;
+    }
+    ++c.successful;
+    return true;
 }
 
 void ProcessorParseRegexNative::Process(PipelineEventGroup& group) {
     if (group.GetEvents().empty())
         return;
-    EventsContainer& events = group.MutableEvents();
-    // gather the events that reach RegexLogLineParser and run ONE batched regex_match over them
-    FlatBatch batch;
-    if (!mIsWholeLineMode) {
-        for (size_t i = 0; i < events.size(); ++i) {
-            if (!IsSupportedEvent(events[i]))
-                continue;
-            const LogEvent& ev = events[i].Cast<LogEvent>();
-            if (ev.HasContent(mSourceKey))
-                batch.Add(i, ev.GetContent(mSourceKey));
-        }
-        batch.Finish(*group.GetSourceBuffer());
-    }
-    const uint32_t G = mReg.groups();
-    const size_t nb = batch.eventIndex.size();
-    std::vector<uint8_t> status(nb);
-    std::vector<uint32_t> capOff(nb * G + 1), capLen(nb * G + 1);
-    if (nb)
-        Check(lc_regex_parse(Engine(), mReg.get(), batch.base, batch.baseLen, batch.off.data(), batch.len.data(), nb,
-                             (uint32_t)mKeys.size(), status.data(), capOff.data(), capLen.data()),
-              "lc_regex_parse");
+    ProcessBatch(&group, 1);
+}
 
-    size_t wIdx = 0, b = 0;
-    for (size_t rIdx = 0; rIdx < events.size(); ++rIdx) {
-        bool keep = true;
-        PipelineEventPtr& e = events[rIdx];
-        if (!IsSupportedEvent(e)) {
-            mOutFailedEventsTotal.Add(1);
-        } else {
-            LogEvent& ev = e.Cast<LogEvent>();
-            if (!ev.HasContent(mSourceKey)) {
-                mOutKeyNotFoundEventsTotal.Add(1);
-            } else {
-                StringView rawContent = ev.GetContent(mSourceKey);
-                bool ok = true;
-                if (mIsWholeLineMode) {
-                    AddLog(ev, mKeys.empty() ? StringView("content") : StringView(mKeys[0]), rawContent);
-                } else {
-                    uint8_t st = status[b];
-                    if (st == LC_REGEX_NOMATCH) {
-                        mOutFailedEventsTotal.Add(1);
-                        ok = false;
-                    } else if (st == LC_REGEX_KEYS_MISMATCH) {
-                        ok = false;
-                    } else {
-                        for (uint32_t k = 0; k < mKeys.size(); ++k)
-                            AddLog(ev, mKeys[k], batch.View(b, capOff[b * G + k], capLen[b * G + k]));
+void ProcessorParseRegexNative::Process(std::vector<PipelineEventGroup>& groups) {
+    // sub-batches whose packed arena stays well below the 4 GiB / 2^30-event limits of one engine call
+    const uint64_t kMaxBytes = 1ull << 30;
+    size_t g0 = 0;
+    while (g0 < groups.size()) {
+        uint64_t bytes = 0, events = 0;
+        size_t g1 = g0;
+        while (g1 < groups.size()) {
+            uint64_t gb = 0;
+            for (const auto& e : groups[g1].GetEvents())
+                if (e.Is<LogEvent>())
+                    gb += e.Cast<LogEvent>().GetContent(mSourceKey).size() + 16;
+            if (g1 > g0 && (bytes + gb > kMaxBytes || events + groups[g1].GetEvents().size() > (1u << 28)))
+                break;
+            bytes += gb;
+            events += groups[g1].GetEvents().size();
+            ++g1;
+        }
+        ProcessBatch(groups.data() + g0, g1 - g0);
+        g0 = g1;
+    }
+}
+
+// One engine call for `ngroups` groups.  Per group the values to parse normally alias ONE arena chunk (all lines of a
+// file read): that chunk range is the group's span and goes to the GPU in place; a group whose values are scattered
+// over several chunks is packed into pinned staging first.
+void ProcessorParseRegexNative::ProcessBatch(PipelineEventGroup* groups, size_t ngroups) {
+    struct GroupPlan {
+        uint64_t firstEv = 0, nEv = 0; // slice of the flat event table
+        const char* lo = nullptr;      // span = [lo, lo + spanLen) in host memory
+        uint32_t spanLen = 0, spanDst = 0;
+        bool staged = false;
+        uint64_t stagedAt = 0;
+    };
+    std::vector<GroupPlan> plan(ngroups);
+    try {
+        uint64_t nb = 0;
+        if (!mIsWholeLineMode) {
+            // ---- pass 1 (parallel over groups): count the events that reach RegexLogLineParser, find each span
+            ParallelFor(ngroups, 8, [&](size_t a, size_t b, unsigned) {
+                for (size_t g = a; g < b; ++g) {
+                    GroupPlan& p = plan[g];
+                    const char* lo = nullptr;
+                    const char* hi = nullptr;
+                    uint64_t total = 0;
+                    for (const auto& e : groups[g].GetEvents()) {
+                        if (!IsSupportedEvent(e))
+                            continue;
+                        const LogEvent& ev = e.Cast<LogEvent>();
+                        if (!ev.HasContent(mSourceKey))
+                            continue;
+                        StringView v = ev.GetContent(mSourceKey);
+                        if (!p.nEv || v.data() < lo)
+                            lo = v.data();
+                        if (!p.nEv || v.data() + v.size() > hi)
+                            hi = v.data() + v.size();
+                        total += v.size();
+                        ++p.nEv;
                     }
-                    ++b;
+                    if (!p.nEv)
+                        continue;
+                    size_t chunkSize = 0;
+                    if ((uint64_t)(hi - lo) < (1ull << 31) &&
+                        groups[g].GetSourceBuffer()->ChunkContaining(lo, (size_t)(hi - lo), &chunkSize)) {
+                        p.lo = lo;
+                        p.spanLen = (uint32_t)(hi - lo);
+                    } else {
+                        p.staged = true;
+                        p.spanLen = (uint32_t)total;
+                    }
                 }
-                if (!ok || !mSourceKeyOverwritten)
-                    ev.DelContent(mSourceKey);
-                if (mCommonParserOptions.ShouldAddSourceContent(ok))
-                    AddLog(ev, mCommonParserOptions.mRenamedSourceKey, rawContent, false);
-                if (mCommonParserOptions.ShouldAddLegacyUnmatchedRawLog(ok))
-                    AddLog(ev, CommonParserOptions::legacyUnmatchedRawLogKey, rawContent, false);
-                if (mCommonParserOptions.ShouldEraseEvent(ok, ev, group.GetAllMetadata())) {
-                    mDiscardedEventsTotal.Add(1);
-                    keep = false;
-                } else {
-                    mOutSuccessfulEventsTotal.Add(1);
+            });
+            uint64_t dst = 0, stagedBytes = 0;
+            for (auto& p : plan) {
+                p.firstEv = nb;
+                nb += p.nEv;
+                p.spanDst = (uint32_t)dst;
+                dst += ((uint64_t)p.spanLen + 15) & ~15ull;
+                if (p.staged) {
+                    p.stagedAt = stagedBytes;
+                    stagedBytes += ((uint64_t)p.spanLen + 15) & ~15ull;
                 }
             }
+            if (nb) {
+                ThreadScratch& sc = Scratch();
+                const uint32_t G = mReg.groups();
+                uint32_t* off = sc.off.ensure(nb);
+                uint32_t* len = sc.len.ensure(nb);
+                uint8_t* status = sc.status.ensure(nb);
+                uint32_t* capOff = sc.capOff.ensure(nb * G + 1);
+                uint32_t* capLen = sc.capLen.ensure(nb * G + 1);
+                uint8_t* staging = stagedBytes ? sc.staging.ensure(stagedBytes) : nullptr;
+                // ---- pass 2 (parallel): the flat event table in packed-arena coordinates
+                ParallelFor(ngroups, 8, [&](size_t a, size_t b, unsigned) {
+                    for (size_t g = a; g < b; ++g) {
+                        GroupPlan& p = plan[g];
+                        if (!p.nEv)
+                            continue;
+                        uint64_t i = p.firstEv;
+                        uint64_t at = 0;
+                        if (p.staged)
+                            p.lo = reinterpret_cast<const char*>(staging + p.stagedAt);
+                        for (const auto& e : groups[g].GetEvents()) {
+                            if (!IsSupportedEvent(e))
+                                continue;
+                            const LogEvent& ev = e.Cast<LogEvent>();
+                            if (!ev.HasContent(mSourceKey))
+                                continue;
+                            StringView v = ev.GetContent(mSourceKey);
+                            if (p.staged) {
+                                if (v.size())
+                                    memcpy(staging + p.stagedAt + at, v.data(), v.size());
+                                off[i] = p.spanDst + (uint32_t)at;
+                                at += v.size();
+                            } else {
+                                off[i] = p.spanDst + (uint32_t)(v.data() - p.lo);
+                            }
+                            len[i] = (uint32_t)v.size();
+                            ++i;
+                        }
+                    }
+                });
+                std::vector<const uint8_t*> spanPtr(ngroups);
+                std::vector<uint32_t> spanLen(ngroups), spanDst(ngroups);
+                std::vector<uint64_t> spanFirst(ngroups + 1);
+                for (size_t g = 0; g < ngroups; ++g) {
+                    spanPtr[g] = reinterpret_cast<const uint8_t*>(plan[g].lo);
+                    spanLen[g] = plan[g].nEv ? plan[g].spanLen : 0;
+                    spanDst[g] = plan[g].spanDst;
+                    spanFirst[g] = plan[g].firstEv;
+                }
+                spanFirst[ngroups] = nb;
+                Check(lc_regex_parse_packed(Engine(), mReg.get(), ngroups, spanPtr.data(), spanLen.data(),
+                                            spanDst.data(), spanFirst.data(), dst, off, len, nb,
+                                            (uint32_t)mKeys.size(), status, capOff, capLen),
+                      "lc_regex_parse_packed");
+            }
         }
-        if (keep) {
-            if (wIdx != rIdx)
-                events[wIdx] = std::move(events[rIdx]);
-            ++wIdx;
-        }
+        // ---- pass 3 (parallel over groups): the per-event epilogue
+        ThreadScratch& sc = Scratch();
+        const uint32_t G = mReg.groups();
+        std::vector<LocalCounters> local(HostThreads());
+        ParallelFor(ngroups, 8, [&](size_t a, size_t b, unsigned tid) {
+            LocalCounters& c = local[tid];
+            for (size_t g = a; g < b; ++g) {
+                EventsContainer& events = groups[g].MutableEvents();
+                const GroupPlan& p = plan[g];
+                uint64_t i = p.firstEv;
+                uint64_t at = 0;
+                size_t wIdx = 0;
+                for (size_t rIdx = 0; rIdx < events.size(); ++rIdx) {
+                    EventResult r{};
+                    const EventResult* rp = nullptr;
+                    if (!mIsWholeLineMode && IsSupportedEvent(events[rIdx])) {
+                        const LogEvent& ev = events[rIdx].Cast<LogEvent>();
+                        if (ev.HasContent(mSourceKey)) {
+                            StringView v = ev.GetContent(mSourceKey);
+                            r.status = sc.status.p[i];
+                            r.capOff = sc.capOff.p + i * G;
+                            r.capLen = sc.capLen.p + i * G;
+                            r.origin = v.data(); // captures map back onto the ORIGINAL bytes, staged or not
+                            r.originOff = sc.off.p[i];
+                            rp = &r;
+                            ++i;
+                            at += v.size();
+                        }
+                    }
+                    if (FinishEvent(groups[g], events[rIdx], rp, c)) {
+                        if (wIdx != rIdx)
+                            events[wIdx] = std::move(events[rIdx]);
+                        ++wIdx;
+                    }
+                }
+                (void)at;
+                events.resize(wIdx);
+            }
+        });
+        for (const auto& c : local)
+            AddCounters(c);
+    } catch (const std::exception& ex) {
+        EngineFailed(ex.what()); // groups not yet rewritten stay untouched (the reference never throws out of Process)
     }
-    events.resize(wIdx);
+}
+
+// ------------------------------------------------------------------------------------------------ instance wrapper
+void ProcessorInstance::Process(std::vector<PipelineEventGroup>& eventGroupList) {
+    if (eventGroupList.empty())
+        return;
+    // the two DataSize() sweeps run on the host threads of the batch when the call carries many groups (the reference
+    // spreads them over its ProcessorRunner threads, one group per call)
+    auto sweep = [&](Counter& events, Counter& bytes) {
+        ParallelFor(eventGroupList.size(), 64, [&](size_t a, size_t b, unsigned) {
+            uint64_t ev = 0, by = 0;
+            for (size_t g = a; g < b; ++g) {
+                ev += eventGroupList[g].GetEvents().size();
+                by += eventGroupList[g].DataSize();
+            }
+            events.Add(ev);
+            bytes.Add(by);
+        });
+    };
+    sweep(mInEventsTotal, mInSizeBytes);
+    const auto before = std::chrono::steady_clock::now();
+    mPlugin->Process(eventGroupList);
+    const auto ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - before);
+    mTotalProcessTimeNs.Add((uint64_t)ns.count());
+    mTotalProcessTimeMs.Add((uint64_t)(ns.count() / 1000000));
+    sweep(mOutEventsTotal, mOutSizeBytes);
 }
 
 // ------------------------------------------------------------------------------------------------ delimiter
@@ -539,10 +795,10 @@ bool ProcessorParseDelimiterNative::Init(const Json::Value& config) {
 }
 
 std::vector<std::pair<std::string, uint64_t>> ProcessorParseDelimiterNative::Counters() const {
-    return {{"discarded", mDiscardedEventsTotal.v},
-            {"out_failed", mOutFailedEventsTotal.v},
-            {"out_key_not_found", mOutKeyNotFoundEventsTotal.v},
-            {"out_successful", mOutSuccessfulEventsTotal.v}};
+    return {{"discarded", mDiscardedEventsTotal.GetValue()},
+            {"out_failed", mOutFailedEventsTotal.GetValue()},
+            {"out_key_not_found", mOutKeyNotFoundEventsTotal.GetValue()},
+            {"out_successful", mOutSuccessfulEventsTotal.GetValue()}};
 }
 
 void ProcessorParseDelimiterNative::Process(PipelineEventGroup& group) {

@@ -8,6 +8,9 @@
 //   processors ..................... core/plugin/processor/{ProcessorParseRegexNative,ProcessorParseDelimiterNative}.cpp,
 //                                    core/plugin/processor/inner/{ProcessorSplitLogStringNative,ProcessorSplitMultilineLogStringNative}.cpp
 #pragma once
+#include <atomic>
+#include <chrono>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -16,10 +19,12 @@
 
 namespace logtail {
 
+// Process() runs concurrently on the same instance from every ProcessorRunner thread (ProcessorRunner.cpp:48-53):
+// counters are atomic like the reference's (monitor/metric_models/MetricTypes.h, relaxed adds).
 struct Counter {
-    uint64_t v = 0;
-    uint64_t GetValue() const { return v; }
-    void Add(uint64_t d) { v += d; }
+    std::atomic<uint64_t> v{0};
+    uint64_t GetValue() const { return v.load(std::memory_order_relaxed); }
+    void Add(uint64_t d) { v.fetch_add(d, std::memory_order_relaxed); }
 };
 
 class Processor {
@@ -33,6 +38,9 @@ public:
     }
     virtual void Process(PipelineEventGroup& group) = 0;
     const std::string& LastError() const { return mError; }
+    // The reference's Process never throws (per-event failure = counters + policy): an engine failure (CUDA error,
+    // out of memory) leaves the affected groups untouched, is counted here and its text kept in LastError().
+    uint64_t EngineErrors() const { return mEngineErrors.GetValue(); }
     // name -> value of every counter the reference registers for this plugin
     virtual std::vector<std::pair<std::string, uint64_t>> Counters() const { return {}; }
 
@@ -42,7 +50,29 @@ protected:
         mError = msg;
         return false;
     }
+    void EngineFailed(const char* what) {
+        mEngineErrors.Add(1);
+        mError = what;
+    }
     std::string mError;
+    Counter mEngineErrors;
+};
+
+// ProcessorInstance (core/collection_pipeline/plugin/instance/ProcessorInstance.cpp:29-63): the wrapper the pipeline
+// calls -- in / out event and byte counters (two DataSize() sweeps per call) and the wall time spent in the plugin.
+class ProcessorInstance {
+public:
+    explicit ProcessorInstance(Processor* plugin) : mPlugin(plugin) {}
+    const std::string& Name() const { return mPlugin->Name(); }
+    Processor* GetPlugin() { return mPlugin.get(); }
+    bool Init(const Json::Value& config) { return mPlugin->Init(config); }
+    void Process(std::vector<PipelineEventGroup>& eventGroupList);
+    Counter mInEventsTotal, mOutEventsTotal, mInSizeBytes, mOutSizeBytes, mTotalProcessTimeMs;
+    // finer-grained than the reference's millisecond counter (kept in addition to it)
+    Counter mTotalProcessTimeNs;
+
+private:
+    std::unique_ptr<Processor> mPlugin;
 };
 
 struct CommonParserOptions {
@@ -121,7 +151,9 @@ public:
     const std::string& Name() const override { return sName; }
     bool Init(const Json::Value& config) override;
     void Process(PipelineEventGroup& group) override;
-    using Processor::Process;
+    // Batched override of Processor.h:31: the arenas of all groups are packed into one device arena and parsed by
+    // one launch sequence (lc_regex_parse_packed); gather and per-event epilogue run on a few host threads.
+    void Process(std::vector<PipelineEventGroup>& groups) override;
     std::vector<std::pair<std::string, uint64_t>> Counters() const override;
     std::string mSourceKey, mRegex;
     std::vector<std::string> mKeys;
@@ -132,6 +164,20 @@ protected:
     bool IsSupportedEvent(const PipelineEventPtr& e) const override { return e.Is<LogEvent>(); }
 
 private:
+    struct EventResult {
+        uint8_t status;
+        const uint32_t* capOff; // row of the capture tables (offsets relative to `origin - originOff`)
+        const uint32_t* capLen;
+        const char* origin;     // first byte of the source value
+        uint32_t originOff;     // its offset in the table's coordinate system
+    };
+    struct LocalCounters {
+        uint64_t discarded = 0, failed = 0, keyNotFound = 0, successful = 0;
+    };
+    // ProcessEvent epilogue (:135-167) of one event; returns false when the event is to be erased
+    bool FinishEvent(PipelineEventGroup& group, PipelineEventPtr& e, const EventResult* r, LocalCounters& c) const;
+    void ProcessBatch(PipelineEventGroup* groups, size_t ngroups);
+    void AddCounters(const LocalCounters& c);
     bool mSourceKeyOverwritten = false;
     bool mIsWholeLineMode = false;
     CompiledRegex mReg;

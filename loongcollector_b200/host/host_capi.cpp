@@ -7,6 +7,7 @@
 #include <string>
 
 #include "../../include/lc_b200_host.h"
+#include "PluginBench.h"
 #include "Processors.h"
 
 using namespace logtail;
@@ -114,6 +115,73 @@ char* lc_host_sls_serialize(const char* group_json, int enable_ns, unsigned long
         if (err_out)
             *err_out = dup(std::string("Serialize threw: ") + e.what());
         return nullptr;
+    }
+}
+
+
+void lc_host_use_pinned_arenas(int on) {
+    if (on)
+        SourceBuffer::SetChunkAllocator(&lc_host_alloc, &lc_host_free);
+    else
+        SourceBuffer::SetChunkAllocator(nullptr, nullptr);
+}
+
+int lc_host_bench_plugin(const char* type, const char* config_json, const uint8_t* data, const uint32_t* line_off,
+                         const uint32_t* line_len, uint64_t n_lines, uint32_t group_bytes, int mode, int reps,
+                         double* seconds_out, uint64_t stats_out[12], char** err_out) {
+    if (err_out)
+        *err_out = nullptr;
+    try {
+        std::unique_ptr<Processor> p(CreateProcessor(type ? type : ""));
+        if (!p)
+            throw std::runtime_error(std::string("unknown processor type: ") + (type ? type : "(null)"));
+        Json::Value cfg(Json::objectValue);
+        std::string err;
+        const char* cj = config_json ? config_json : "{}";
+        if (!Json::Value::parse(cj, cj + strlen(cj), cfg, err))
+            throw std::runtime_error("config is not valid JSON: " + err);
+        ProcessorInstance inst(p.release());
+        if (!inst.Init(cfg))
+            throw std::runtime_error("Init failed: " + inst.GetPlugin()->LastError());
+        PluginBench bench(data, line_off, line_len, n_lines, group_bytes, 16);
+        PluginBenchResult r = bench.Run(reps, [&](std::vector<PipelineEventGroup>& groups) {
+            if (mode == 1) {
+                inst.Process(groups); // ProcessorInstance::Process(vector<PipelineEventGroup>&), the pipeline's call
+            } else {
+                // one call per group, as a ProcessorRunner thread does with the groups it pops
+                // (ProcessorRunner.cpp:128-143): the vector holds ONE group each time
+                std::vector<PipelineEventGroup> one;
+                for (auto& g : groups) {
+                    one.clear();
+                    one.emplace_back(std::move(g));
+                    inst.Process(one);
+                    g = std::move(one[0]);
+                }
+            }
+        });
+        if (inst.GetPlugin()->EngineErrors())
+            throw std::runtime_error("engine error inside Process: " + inst.GetPlugin()->LastError());
+        for (int k = 0; k < reps && seconds_out; ++k)
+            seconds_out[k] = r.seconds[k];
+        if (stats_out) {
+            stats_out[0] = r.groups;
+            stats_out[1] = r.inEvents;
+            stats_out[2] = r.outEvents;
+            stats_out[3] = r.liveContents;
+            stats_out[4] = r.checksum;
+            stats_out[5] = r.arenaBytes;
+            stats_out[6] = inst.mInEventsTotal.GetValue();
+            stats_out[7] = inst.mOutEventsTotal.GetValue();
+            stats_out[8] = inst.mInSizeBytes.GetValue();
+            stats_out[9] = inst.mOutSizeBytes.GetValue();
+            stats_out[10] = inst.mTotalProcessTimeNs.GetValue();
+            stats_out[11] = inst.mTotalProcessTimeMs.GetValue();
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        if (err_out)
+            *err_out = dup(e.what());
+        return 1;
     }
 }
 
