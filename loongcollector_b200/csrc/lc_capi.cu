@@ -1320,10 +1320,58 @@ int lc_multiline_split_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, c
 
     Small* ds = e->small.as<Small>();
     Small* hs = (Small*)e->h_small;
+    uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
+    static const bool fused = [] {
+        const char* k = getenv("LC_B200_ML_FUSED"); // A/B knob: 0 = the five-kernel formulation
+        return !(k && !strcmp(k, "0"));
+    }();
+    if (fused) {
+        // Two launches, no host round trip in between: (1) split + per-line probes, (2) state scan + counts + slots +
+        // emission; the second reads the line count from device memory.  The line table is sized from an estimate and
+        // the call repeats with the exact size in the rare case it was too small.
+        uint64_t lcap = len / 24 + 4096;
+        for (;;) {
+            if (lcap > len)
+                lcap = len;
+            if (lcap > 0x3FFFFFF0ull)
+                lcap = 0x3FFFFFF0ull;
+            CU_TRY(e->lines_off.ensure((lcap + 1) * 4));
+            CU_TRY(e->lines_len.ensure((lcap + 1) * 4));
+            CU_TRY(e->flags.ensure(lcap + 1));
+            const uint32_t ftiles = lck::ml_fused_tiles(lcap);
+            DescPlan plan;
+            rc = prep_desc(e, lck::split_tiles(len, shift), ftiles, ftiles, plan);
+            if (rc)
+                return rc;
+            lck::launch_split_probe(cfg, d_buf, (uint32_t)len, e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(),
+                                    e->flags.as<uint8_t>(), (uint32_t)lcap, plan.r[0], &ds->tickets[0], &ds->n_out,
+                                    &ds->total_chars, e->stream);
+            lck::launch_ml_fused(cfg, e->flags.as<uint8_t>(), e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(),
+                                 &ds->n_out, (uint32_t)lcap, (uint32_t)len, d_out_off, d_out_len, d_out_flags, cap,
+                                 plan.r[1], plan.r[2], &ds->tickets[1], ds->counters, &ds->total, e->stream);
+            e->launches += 2;
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, e->stream));
+            CU_TRY(cudaStreamSynchronize(e->stream));
+            if (hs->total_chars >= (1ull << 30) - 2)
+                return fail(LC_ERR_TOO_LARGE, "more than 2^30 lines in one call");
+            if (hs->n_out <= lcap)
+                break;
+            lcap = hs->n_out;
+        }
+        *n_out = hs->total;
+        if (counters) {
+            counters[0] += hs->counters[0];
+            counters[1] += hs->n_out;
+            counters[2] += hs->counters[1];
+        }
+        if (*n_out > cap)
+            return fail(LC_ERR_CAPACITY, "lc_multiline_split: output capacity too small");
+        return LC_OK;
+    }
     // 1. line table (grow the workspace until it fits; typical logs fit the first estimate)
     uint64_t lcap = len / 24 + 4096;
     uint64_t n = 0;
-    uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
     for (;;) {
         if (lcap > len)
             lcap = len;

@@ -42,15 +42,39 @@ __device__ __forceinline__ uint32_t match16(uint4 v, uint32_t splat) {
 // predecessors, and that walk gets longer with the number of tiles in flight (measured on C1: 16 KiB tiles 1.64,
 // 32 KiB 1.73, 64 KiB 1.87 TB/s; 128 KiB = 2 segments per thread 1.75 TB/s, the 57 registers leave one block per
 // SM; one tile per WARP, no barrier at all, 1.15 TB/s).
-template <int THREADS, int SEGS>
-__global__ void __launch_bounds__(THREADS)
+// PROBE (multiline, a2): the owner of a line's terminating newline also evaluates the anchored prefix probes of the
+// start / continue / end patterns on the line's head (regex_search + match_continuous, StringTools.cpp:263-288) and
+// writes one flag byte per line -- the line's first bytes were fetched by this pass a moment ago (same tile or the one
+// before: L1 / L2 hits), so the separate probe pass that re-read the first sector of every line is gone.
+struct SplitProbe {
+    const void* bs; // device blobs of the start / continue / end patterns (nullptr = not configured)
+    const void* bc;
+    const void* be;
+    uint8_t* flags; // [line] bit0/1/2 = start / continue / end matches a prefix
+};
+
+__device__ __forceinline__ uint8_t probe_line(const SplitProbe& pr, const uint8_t* __restrict__ s, uint32_t l) {
+    uint8_t f = 0;
+    if (pr.bs && lc_prefix_match(lc_view(pr.bs), s, l))
+        f |= 1;
+    if (pr.bc && lc_prefix_match(lc_view(pr.bc), s, l))
+        f |= 2;
+    if (pr.be && lc_prefix_match(lc_view(pr.be), s, l))
+        f |= 4;
+    return f;
+}
+
+template <int THREADS, int SEGS, int LBW, bool PROBE>
+__global__ void __launch_bounds__(THREADS, (THREADS == 1024 && SEGS == 1) ? 2 : 1)
     split_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
                  uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap, volatile uint64_t* desc,
-                 uint32_t* ticket, uint32_t ntiles, uint32_t* n_out, unsigned long long* total_chars) {
+                 uint32_t* ticket, uint32_t ntiles, uint32_t* n_out, unsigned long long* total_chars, SplitProbe pr) {
     constexpr int ROWS = 4 * SEGS;
     __shared__ uint64_t s_scan[THREADS / 32 + 1];
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_prefix;
+    __shared__ uint64_t s_part[LBW > 1 ? LBW : 1];
+    __shared__ uint32_t s_flag[LBW > 1 ? LBW : 1];
     const int tid = threadIdx.x;
     if (tid == 0)
         s_tile = atomicAdd(ticket, 1u);
@@ -93,16 +117,21 @@ __global__ void __launch_bounds__(THREADS)
     }
     uint64_t tot;
     const uint64_t excl = block_exclusive_scan<OpCountMax, THREADS>(pay, tot, s_scan);
-    if (tid < 32) {
-        uint64_t p = lookback<OpCountMax>(desc, tile, tot);
-        if (tid == 0) {
-            s_prefix = p;
-            if (OpCountMax::count(tot)) // un-truncated count (the payload keeps 30 bits): > 2^30 pieces is an error
-                atomicAdd(total_chars, (unsigned long long)OpCountMax::count(tot));
+    uint64_t tile_prefix;
+    if (LBW > 1) {
+        tile_prefix = lookback_block<OpCountMax, LBW>(desc, tile, tot, s_part, s_flag);
+    } else {
+        if (tid < 32) {
+            uint64_t p = lookback<OpCountMax>(desc, tile, tot);
+            if (tid == 0)
+                s_prefix = p;
         }
+        __syncthreads();
+        tile_prefix = s_prefix;
     }
-    __syncthreads();
-    const uint64_t pre = OpCountMax::combine(s_prefix, excl);
+    if (tid == 0 && OpCountMax::count(tot)) // un-truncated count (the payload keeps 30 bits): > 2^30 pieces is an error
+        atomicAdd(total_chars, (unsigned long long)OpCountMax::count(tot));
+    const uint64_t pre = OpCountMax::combine(tile_prefix, excl);
     uint32_t k = OpCountMax::count(pre);
     uint32_t start = OpCountMax::maxv(pre);
 #pragma unroll
@@ -115,6 +144,8 @@ __global__ void __launch_bounds__(THREADS)
             if (k < cap) {
                 out_off[k] = start;
                 out_len[k] = p - start;
+                if (PROBE)
+                    pr.flags[k] = probe_line(pr, buf + start, p - start);
             }
             ++k;
             start = p + 1;
@@ -126,6 +157,8 @@ __global__ void __launch_bounds__(THREADS)
             if (k < cap) {
                 out_off[k] = start;
                 out_len[k] = len - start;
+                if (PROBE)
+                    pr.flags[k] = probe_line(pr, buf + start, len - start);
             }
             ++k;
         }
@@ -133,9 +166,19 @@ __global__ void __launch_bounds__(THREADS)
     }
 }
 
-void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
-                  uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
-                  unsigned long long* d_total, cudaStream_t st) {
+static int split_lookback_warps() {
+    static const int w = [] {
+        const char* e = getenv("LC_B200_LOOKBACK_WARPS"); // A/B knob: 1 = single-warp walk, 4 (default) = block-wide
+        int t = e ? atoi(e) : 4;
+        return t == 1 ? 1 : 4;
+    }();
+    return w;
+}
+
+template <bool PROBE>
+static void launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
+                              uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
+                              unsigned long long* d_total, const SplitProbe& pr, cudaStream_t st) {
     uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
     uint32_t splat = split_char * 0x01010101u;
     static const int cfg = [] {
@@ -145,15 +188,42 @@ void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32
     }();
     const uint64_t tile_bytes = (uint64_t)cfg * 1024;
     uint32_t ntiles = (uint32_t)((len + shift + tile_bytes - 1) / tile_bytes);
-    if (cfg == 128)
-        split_kernel<1024, 2><<<ntiles, 1024, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
-                                                        (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out, d_total);
-    else if (cfg == 64)
-        split_kernel<1024, 1><<<ntiles, 1024, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
-                                                        (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out, d_total);
-    else
-        split_kernel<256, 1><<<ntiles, 256, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
-                                                      (volatile uint64_t*)d_desc, d_ticket, ntiles, d_n_out, d_total);
+    volatile uint64_t* desc = (volatile uint64_t*)d_desc;
+    const bool wide = split_lookback_warps() > 1;
+#define LC_SPLIT_LAUNCH(T, S, W)                                                                                       \
+    split_kernel<T, S, W, PROBE><<<ntiles, T, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap, desc, d_ticket,    \
+                                                       ntiles, d_n_out, d_total, pr)
+    if (cfg == 128) {
+        if (wide)
+            LC_SPLIT_LAUNCH(1024, 2, 4);
+        else
+            LC_SPLIT_LAUNCH(1024, 2, 1);
+    } else if (cfg == 64) {
+        if (wide)
+            LC_SPLIT_LAUNCH(1024, 1, 4);
+        else
+            LC_SPLIT_LAUNCH(1024, 1, 1);
+    } else {
+        if (wide)
+            LC_SPLIT_LAUNCH(256, 1, 4);
+        else
+            LC_SPLIT_LAUNCH(256, 1, 1);
+    }
+#undef LC_SPLIT_LAUNCH
+}
+
+void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
+                  uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
+                  unsigned long long* d_total, cudaStream_t st) {
+    SplitProbe pr{nullptr, nullptr, nullptr, nullptr};
+    launch_split_impl<false>(d_buf, len, split_char, d_off, d_len, cap, d_desc, d_ticket, d_n_out, d_total, pr, st);
+}
+
+void launch_split_probe(const MlConfig& cfg, const uint8_t* d_buf, uint32_t len, uint32_t* d_off, uint32_t* d_len,
+                        uint8_t* d_flags, uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
+                        unsigned long long* d_total, cudaStream_t st) {
+    SplitProbe pr{cfg.blob_start, cfg.blob_cont, cfg.blob_end, d_flags};
+    launch_split_impl<true>(d_buf, len, '\n', d_off, d_len, cap, d_desc, d_ticket, d_n_out, d_total, pr, st);
 }
 
 // ================================================================================================ sums
@@ -163,7 +233,8 @@ __global__ void __launch_bounds__(THREADS)
                          volatile uint64_t* desc, uint32_t* ticket, uint32_t ntiles) {
     __shared__ uint64_t s_scan[THREADS / 32 + 1];
     __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_prefix;
+    __shared__ uint64_t s_part[4];
+    __shared__ uint32_t s_flag[4];
     const int tid = threadIdx.x;
     if (tid == 0)
         s_tile = atomicAdd(ticket, 1u);
@@ -179,13 +250,7 @@ __global__ void __launch_bounds__(THREADS)
     }
     uint64_t tot;
     uint64_t ex = block_exclusive_scan<OpSum, THREADS>(sum, tot, s_scan);
-    if (tid < 32) {
-        uint64_t p = lookback<OpSum>(desc, tile, tot);
-        if (tid == 0)
-            s_prefix = p;
-    }
-    __syncthreads();
-    uint64_t run = s_prefix + ex;
+    uint64_t run = lookback_block<OpSum, 4>(desc, tile, tot, s_part, s_flag) + ex;
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         if (base + k < n)
@@ -2465,6 +2530,144 @@ void launch_ml_emit(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t*
     ml_emit_kernel<<<(unsigned)((n + 1 + 127) / 128), 128, 0, st>>>(m, d_flags, d_off, d_len, n, total_len, d_state,
                                                                     d_pos, d_out_off, d_out_len, d_out_flags, cap,
                                                                     d_counters);
+}
+
+// ---- fused back half of the multiline split: state scan -> output counts -> output slots -> emission in ONE kernel.
+// Two chained decoupled look-backs per tile (the 2-state transition functions, then the event counts); the per-line
+// state / count / slot arrays of the three-kernel formulation never exist.  The number of lines is read from device
+// memory (the split kernel's counter), so the launch follows the split without a host round trip: the grid covers
+// the line CAPACITY and surplus tiles return at once.  Elements 0..n-1 are lines, element n is the virtual
+// end-of-buffer.
+constexpr int kMlFusedThreads = 512;
+constexpr int kMlFusedItems = 4;
+
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
+    ml_fused_kernel(MlMode m, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ off,
+                    const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_lines, uint32_t line_cap,
+                    uint32_t total_len, uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len,
+                    uint8_t* __restrict__ out_flags, uint64_t cap, volatile uint64_t* desc_state,
+                    volatile uint64_t* desc_sum, uint32_t* ticket, unsigned long long* counters, uint64_t* total_out) {
+    __shared__ uint64_t s_scan[THREADS / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_part[4];
+    __shared__ uint32_t s_flag[4];
+    const int tid = threadIdx.x;
+    if (tid == 0)
+        s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t n = min(*n_lines, line_cap); // (more lines than the table holds: the host repeats the call)
+    if ((uint64_t)tile * THREADS * ITEMS > n)
+        return;
+    const uint64_t base = (uint64_t)tile * THREADS * ITEMS + (uint64_t)tid * ITEMS;
+    uint64_t el[ITEMS];
+    uint32_t fl[ITEMS];
+    uint64_t agg = OpMlState::identity();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint64_t j = base + k;
+        uint64_t e = OpMlState::identity();
+        fl[k] = 0;
+        if (j < n) {
+            fl[k] = flags[j];
+            uint32_t o0, b0, o1, b1;
+            ml_trans(m, fl[k], 0, o0, b0);
+            ml_trans(m, fl[k], 1, o1, b1);
+            const uint32_t l0 = b0 ? (uint32_t)j + b0 : 0u; // (index + 1) of the opening line
+            const uint32_t l1 = b1 ? (uint32_t)j + b1 : 0u;
+            e = OpMlState::make(o0, o1, l0, l1);
+        }
+        el[k] = e;
+        agg = OpMlState::combine(agg, e);
+    }
+    uint64_t tot;
+    const uint64_t ex = block_exclusive_scan<OpMlState, THREADS>(agg, tot, s_scan);
+    const uint64_t pre = lookback_block<OpMlState, 4>(desc_state, tile, tot, s_part, s_flag);
+    uint64_t run = OpMlState::combine(pre, ex);
+    // initial condition (:165-169): End-only mode starts partial with multiStartIndex = line 0
+    const uint32_t s0 = (!m.S && !m.C && m.E) ? 1u : 0u;
+    const uint32_t lb_init = s0 ? 1u : 0u;
+    uint32_t stt[ITEMS], cnt[ITEMS];
+    uint64_t csum = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint64_t j = base + k;
+        stt[k] = 0;
+        cnt[k] = 0;
+        if (j <= n) {
+            const uint32_t s_in = OpMlState::f(run, s0);
+            uint32_t lbp = OpMlState::lb(run, s0);
+            if (!lbp)
+                lbp = lb_init;
+            const uint32_t lb = lbp ? lbp - 1 : 0u; // line index of multiStartIndex (valid only when s_in)
+            stt[k] = (s_in << 31) | lb;
+            MlCountSink sink;
+            sink.discard = m.discard;
+            sink.len = len;
+            sink.n = (uint32_t)n;
+            ml_actions(m, fl[k], s_in, lb, (uint32_t)j, (uint32_t)n, sink);
+            cnt[k] = sink.cnt;
+            csum += sink.cnt;
+        }
+        run = OpMlState::combine(run, el[k]);
+    }
+    uint64_t tot2;
+    const uint64_t ex2 = block_exclusive_scan<OpSum, THREADS>(csum, tot2, s_scan);
+    const uint64_t pre2 = lookback_block<OpSum, 4>(desc_sum, tile, tot2, s_part, s_flag);
+    uint64_t pos = pre2 + ex2;
+    uint32_t me = 0, ul = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint64_t j = base + k;
+        if (j <= n) {
+            MlEmitSink sink;
+            sink.discard = m.discard;
+            sink.off = off;
+            sink.len = len;
+            sink.total_len = total_len;
+            sink.out_off = out_off;
+            sink.out_len = out_len;
+            sink.out_flags = out_flags;
+            sink.cap = cap;
+            sink.pos = pos;
+            sink.n = (uint32_t)n;
+            // begin + content.size() == sourceVal.size() (:174); the end-of-buffer element always passes true
+            sink.is_last = (j == n) ? 1u : ((off[j] + len[j] == total_len) ? 1u : 0u);
+            ml_actions(m, fl[k], stt[k] >> 31, stt[k] & 0x7FFFFFFFu, (uint32_t)j, (uint32_t)n, sink);
+            me += sink.matched_events;
+            ul += sink.unmatch_lines;
+            pos += cnt[k];
+            if (j == n)
+                *total_out = pos;
+        }
+    }
+    for (int d = 16; d; d >>= 1) {
+        me += __shfl_down_sync(0xFFFFFFFFu, me, d);
+        ul += __shfl_down_sync(0xFFFFFFFFu, ul, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (me)
+            atomicAdd(&counters[0], (unsigned long long)me);
+        if (ul)
+            atomicAdd(&counters[1], (unsigned long long)ul);
+    }
+}
+
+uint32_t ml_fused_tiles(uint64_t line_cap) {
+    const uint64_t per = (uint64_t)kMlFusedThreads * kMlFusedItems;
+    return (uint32_t)((line_cap + 1 + per - 1) / per);
+}
+
+void launch_ml_fused(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len,
+                     const uint32_t* d_n_lines, uint32_t line_cap, uint32_t total_len, uint32_t* d_out_off,
+                     uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, uint64_t* d_desc_state,
+                     uint64_t* d_desc_sum, uint32_t* d_ticket, unsigned long long* d_counters, uint64_t* d_total,
+                     cudaStream_t st) {
+    MlMode m{cfg.blob_start != nullptr, cfg.blob_cont != nullptr, cfg.blob_end != nullptr, cfg.discard != 0};
+    ml_fused_kernel<kMlFusedThreads, kMlFusedItems><<<ml_fused_tiles(line_cap), kMlFusedThreads, 0, st>>>(
+        m, d_flags, d_off, d_len, d_n_lines, line_cap, total_len, d_out_off, d_out_len, d_out_flags, cap,
+        (volatile uint64_t*)d_desc_state, (volatile uint64_t*)d_desc_sum, d_ticket, d_counters, d_total);
 }
 
 // ================================================================================================ delimiter

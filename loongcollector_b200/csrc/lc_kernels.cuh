@@ -165,6 +165,19 @@ void launch_ml_emit(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t*
                     uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, unsigned long long* d_counters,
                     cudaStream_t st);
 
+// fused multiline path: split + per-line probes in one pass (flags[line]), then state scan + counts + slots + emission
+// in one kernel that reads the line count from d_n_lines (no host round trip in between).  d_desc_state / d_desc_sum:
+// ml_fused_tiles(line_cap) + 1 zeroed u64 each.
+void launch_split_probe(const MlConfig& cfg, const uint8_t* d_buf, uint32_t len, uint32_t* d_off, uint32_t* d_len,
+                        uint8_t* d_flags, uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
+                        unsigned long long* d_total, cudaStream_t st);
+uint32_t ml_fused_tiles(uint64_t line_cap);
+void launch_ml_fused(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len,
+                     const uint32_t* d_n_lines, uint32_t line_cap, uint32_t total_len, uint32_t* d_out_off,
+                     uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, uint64_t* d_desc_state,
+                     uint64_t* d_desc_sum, uint32_t* d_ticket, unsigned long long* d_counters, uint64_t* d_total,
+                     cudaStream_t st);
+
 // a4: delimiter
 struct DelimConfig {
     uint8_t sep[4];

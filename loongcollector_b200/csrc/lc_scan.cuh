@@ -162,4 +162,69 @@ __device__ __forceinline__ uint64_t lookback(volatile uint64_t* desc, uint32_t t
     return prefix;
 }
 
+// Block-cooperative look-back: ALL threads of the block call (uniform control flow); the first WARPS warps poll
+// WARPS * 32 predecessors per round.  Why: a tile's walk ends at the nearest predecessor that already holds an
+// INCLUSIVE prefix, and every predecessor that is itself still walking only offers its aggregate -- so the faster the
+// tiles retire, the more descriptors a walk has to cross.  With one warp (32 descriptors per ~L2 round trip) the scan
+// saturates near tile_bytes * 32 / round_trip (measured: 64 KiB tiles ~1.9 TB/s, 1024-line tiles of the line-level
+// scans ~45 G lines/s); WARPS = 4 moves that ceiling 4x out.  Returns the exclusive prefix of `tile` to every thread.
+// s_part: WARPS words, s_flag: WARPS words of shared memory.
+template <class Op, int WARPS>
+__device__ __forceinline__ uint64_t lookback_block(volatile uint64_t* desc, uint32_t tile, uint64_t aggregate,
+                                                   uint64_t* s_part, uint32_t* s_flag) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (tile == 0) {
+        if (threadIdx.x == 0)
+            desc[0] = kFlagInclusive | (aggregate & kPayloadMask);
+        return Op::identity();
+    }
+    if (threadIdx.x == 0)
+        desc[tile] = kFlagAggregate | (aggregate & kPayloadMask);
+    uint64_t prefix = Op::identity();
+    int64_t base = (int64_t)tile - 1;
+    for (;;) {
+        if (wid < WARPS) {
+            const int64_t idx = base - (wid * 32 + lane);
+            uint64_t d;
+            if (idx >= 0) {
+                do {
+                    d = ld_desc(desc + idx);
+                } while ((d >> 62) == 0);
+            } else {
+                d = kFlagInclusive | Op::identity();
+            }
+            const unsigned incl = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2);
+            const int stop = incl ? (__ffs(incl) - 1) : 31;
+            uint64_t r = (lane <= stop) ? (d & kPayloadMask) : Op::identity();
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) { // ordered reduction: higher lanes are EARLIER tiles
+                const uint64_t t = shfl_down64(r, s);
+                if (lane + s < 32)
+                    r = Op::combine(t, r);
+            }
+            if (lane == 0) {
+                s_part[wid] = r;
+                s_flag[wid] = incl != 0;
+            }
+        }
+        __syncthreads();
+        uint64_t r = Op::identity();
+        bool found = false;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w)
+            if (!found) {
+                r = Op::combine(s_part[w], r); // warp w + 1 holds earlier tiles than warp w
+                found = s_flag[w] != 0;
+            }
+        prefix = Op::combine(r, prefix);
+        __syncthreads(); // s_part / s_flag are rewritten in the next round
+        if (found)
+            break;
+        base -= WARPS * 32;
+    }
+    if (threadIdx.x == 0)
+        desc[tile] = kFlagInclusive | (Op::combine(prefix, aggregate) & kPayloadMask);
+    return prefix;
+}
+
 } // namespace lcscan
