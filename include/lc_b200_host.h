@@ -31,6 +31,14 @@ void lc_host_string_free(char* s);
  * bytes (free with lc_host_string_free) and their length, or NULL + *err_out = the reference's error message. */
 char* lc_host_sls_serialize(const char* group_json, int enable_ns, unsigned long long* len_out, char** err_out);
 
+/* Loads a dynamic plugin the way the agent does (dlopen, dlsym("processor_interface"), version == 100 --
+ * PluginRegistry.cpp:255-275) and drives it like DynamicCProcessorProxy (.cpp:21-36): init(ins, &config, &context),
+ * process(plugin_state, &group), finalize(plugin_state).  Returns the processed group's JSON ("null" when group_json
+ * is NULL: init / finalize only); NULL + *err_out on any failure.  *version_out / *name_out (malloc'd) report the
+ * interface fields as soon as the symbol resolves. */
+char* lc_host_dynamic_plugin_roundtrip(const char* so_path, const char* config_json, const char* group_json,
+                                       int enable_event_meta, int* version_out, char** name_out, char** err_out);
+
 /* Makes every SourceBuffer chunk created from now on pinned (lc_host_alloc): a group's arena is then DMA-able in
  * place -- the integration's replacement of SourceBuffer's `new char[]` (core/common/memory/SourceBuffer.h:98-131). */
 void lc_host_use_pinned_arenas(int on);

@@ -37,8 +37,39 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + _host_sources() + _host_headers() + [__file__]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + _host_sources() + _host_headers() + [__file__] + \
+        [os.path.join(PLUGIN_DIR, "dynamic_processor.cpp")]
+    if not all(os.path.exists(plugin_path(n)) for n, _ in PLUGINS):
+        return True
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+# dynamic plugins (plugin/dynamic_processor.cpp): one .so per processor, named lib<name>.so as the agent's loader expects
+PLUGIN_DIR = os.path.join(HERE, "plugin")
+PLUGINS = [
+    ("processor_parse_regex_b200", "processor_parse_regex_native"),
+    ("processor_parse_delimiter_b200", "processor_parse_delimiter_native"),
+    ("processor_split_string_b200", "processor_split_string_native"),
+    ("processor_split_multiline_log_string_b200", "processor_split_multiline_log_string_native"),
+]
+
+
+def plugin_path(name):
+    return os.path.join(PLUGIN_DIR, "lib%s.so" % name)
+
+
+def build_plugins(log):
+    gxx = os.environ.get("CXX", "g++")
+    src = os.path.join(PLUGIN_DIR, "dynamic_processor.cpp")
+    for name, ptype in PLUGINS:
+        cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DLC_PLUGIN_NAME=\"%s\"" % name,
+               "-DLC_PLUGIN_TYPE=\"%s\"" % ptype, src, "-o", plugin_path(name), "-L", HERE,
+               "-l:libloongcollector_b200.so", "-Wl,-rpath,$ORIGIN/.."]
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        log.write(" ".join(cmd) + "\n" + p.stdout)
+        if p.returncode != 0:
+            sys.stderr.write(p.stdout)
+            raise RuntimeError("plugin build failed: %s" % name)
 
 
 def build(force=False, verbose=False):
@@ -51,6 +82,8 @@ def build(force=False, verbose=False):
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + p.stdout)
+        if p.returncode == 0:
+            build_plugins(f)
     if verbose or p.returncode != 0:
         sys.stderr.write(p.stdout)
     if p.returncode != 0:

@@ -318,6 +318,14 @@ bool ProcessorSplitLogStringNative::Init(const Json::Value& config) {
 }
 
 void ProcessorSplitLogStringNative::Process(PipelineEventGroup& group) {
+    try {
+        ProcessImpl(group);
+    } catch (const std::exception& ex) {
+        EngineFailed(ex.what()); // the reference's Process never throws: the group stays as it was
+    }
+}
+
+void ProcessorSplitLogStringNative::ProcessImpl(PipelineEventGroup& group) {
     if (group.GetEvents().empty())
         return;
     EventsContainer newEvents;
@@ -386,6 +394,14 @@ std::vector<std::pair<std::string, uint64_t>> ProcessorSplitMultilineLogStringNa
 }
 
 void ProcessorSplitMultilineLogStringNative::Process(PipelineEventGroup& group) {
+    try {
+        ProcessImpl(group);
+    } catch (const std::exception& ex) {
+        EngineFailed(ex.what()); // the reference's Process never throws: the group stays as it was
+    }
+}
+
+void ProcessorSplitMultilineLogStringNative::ProcessImpl(PipelineEventGroup& group) {
     if (group.GetEvents().empty())
         return;
     EventsContainer newEvents;
@@ -802,6 +818,14 @@ std::vector<std::pair<std::string, uint64_t>> ProcessorParseDelimiterNative::Cou
 }
 
 void ProcessorParseDelimiterNative::Process(PipelineEventGroup& group) {
+    try {
+        ProcessImpl(group);
+    } catch (const std::exception& ex) {
+        EngineFailed(ex.what()); // the reference's Process never throws: the group stays as it was
+    }
+}
+
+void ProcessorParseDelimiterNative::ProcessImpl(PipelineEventGroup& group) {
     if (group.GetEvents().empty())
         return;
     EventsContainer& events = group.MutableEvents();
@@ -817,24 +841,58 @@ void ProcessorParseDelimiterNative::Process(PipelineEventGroup& group) {
     const size_t nb = batch.eventIndex.size();
     const bool extend = mOverflowedFieldsTreatment == OverflowedFieldsTreatment::EXTEND;
     const bool useQuote = mSeparator.size() == 1 && mQuote != mSeparator[0];
-    uint32_t MF = (uint32_t)mKeys.size() + 16;
+    // Dense [n][MF] field tables with MF = keys + 16 serve every ordinary line.  A line with more columns than that
+    // (log content is untrusted: one 256 KB line of separators must not size a table for the whole group) is parsed
+    // again on its own, in small sub-batches whose tables hold exactly its columns -- memory stays O(bytes of those
+    // lines), like the reference's per-line vectors (:246-248).
+    const uint32_t MF = (uint32_t)mKeys.size() + 16;
     std::vector<uint8_t> status(nb);
-    std::vector<uint32_t> nf(nb), fo, fl, fd;
-    for (int pass = 0; nb && pass < 2; ++pass) {
-        fo.assign((size_t)nb * MF, 0);
-        fl.assign((size_t)nb * MF, 0);
-        fd.assign((size_t)nb * MF, 0);
+    std::vector<uint32_t> nf(nb), fo((size_t)nb * MF), fl((size_t)nb * MF), fd((size_t)nb * MF);
+    std::vector<uint32_t> wfo, wfl, wfd;
+    std::vector<size_t> wideStart(nb, (size_t)-1);
+    if (nb) {
         Check(lc_delim_parse(Engine(), batch.base, batch.baseLen, batch.off.data(), batch.len.data(), nb,
                              reinterpret_cast<const uint8_t*>(mSeparator.data()), (uint32_t)mSeparator.size(),
                              (uint8_t)mQuote, (uint32_t)mKeys.size(), extend, mAllowingShortenedFields, MF,
                              status.data(), nf.data(), fo.data(), fl.data(), fd.data()),
               "lc_delim_parse");
-        uint32_t mx = 0;
+        std::vector<size_t> over;
         for (size_t i = 0; i < nb; ++i)
-            mx = std::max(mx, nf[i]);
-        if (mx <= MF)
-            break;
-        MF = mx; // a line with more columns than the table holds: rerun (still on the GPU) with room for all
+            if (nf[i] > MF && status[i] != LC_DELIM_PARSE_FAIL && status[i] != LC_DELIM_BLANK)
+                over.push_back(i);
+        const size_t kMaxEntries = 4u << 20; // 48 MB of tables per sub-batch at most (+ one oversize line alone)
+        size_t at = 0;
+        while (at < over.size()) {
+            size_t cnt = 0;
+            uint32_t mx = 0;
+            while (at + cnt < over.size()) {
+                uint32_t m2 = std::max(mx, nf[over[at + cnt]]);
+                if (cnt && (cnt + 1) * (size_t)m2 > kMaxEntries)
+                    break;
+                mx = m2;
+                ++cnt;
+            }
+            std::vector<uint32_t> so(cnt), sl(cnt), snf(cnt), sfo(cnt * (size_t)mx), sfl(cnt * (size_t)mx),
+                sfd(cnt * (size_t)mx);
+            std::vector<uint8_t> sst(cnt);
+            for (size_t k = 0; k < cnt; ++k) {
+                so[k] = batch.off[over[at + k]];
+                sl[k] = batch.len[over[at + k]];
+            }
+            Check(lc_delim_parse(Engine(), batch.base, batch.baseLen, so.data(), sl.data(), cnt,
+                                 reinterpret_cast<const uint8_t*>(mSeparator.data()), (uint32_t)mSeparator.size(),
+                                 (uint8_t)mQuote, (uint32_t)mKeys.size(), extend, mAllowingShortenedFields, mx,
+                                 sst.data(), snf.data(), sfo.data(), sfl.data(), sfd.data()),
+                  "lc_delim_parse");
+            for (size_t k = 0; k < cnt; ++k) {
+                const size_t i = over[at + k];
+                wideStart[i] = wfo.size();
+                wfo.insert(wfo.end(), sfo.begin() + k * (size_t)mx, sfo.begin() + k * (size_t)mx + nf[i]);
+                wfl.insert(wfl.end(), sfl.begin() + k * (size_t)mx, sfl.begin() + k * (size_t)mx + nf[i]);
+                wfd.insert(wfd.end(), sfd.begin() + k * (size_t)mx, sfd.begin() + k * (size_t)mx + nf[i]);
+            }
+            at += cnt;
+        }
     }
 
     size_t wIdx = 0, b = 0;
@@ -859,8 +917,12 @@ void ProcessorParseDelimiterNative::Process(PipelineEventGroup& group) {
                     if (ok) {
                         cols.clear();
                         SourceBuffer& sb = *group.GetSourceBuffer();
+                        const bool wide = wideStart[b] != (size_t)-1;
+                        const uint32_t* ro = wide ? wfo.data() + wideStart[b] : fo.data() + (size_t)b * MF;
+                        const uint32_t* rl = wide ? wfl.data() + wideStart[b] : fl.data() + (size_t)b * MF;
+                        const uint32_t* rd = wide ? wfd.data() + wideStart[b] : fd.data() + (size_t)b * MF;
                         for (uint32_t j = 0; j < nf[b]; ++j) {
-                            uint32_t o = fo[(size_t)b * MF + j], l = fl[(size_t)b * MF + j], dq = fd[(size_t)b * MF + j];
+                            uint32_t o = ro[j], l = rl[j], dq = rd[j];
                             StringView raw = batch.View(b, o, l);
                             if (useQuote && dq) {
                                 // AddFieldWithUnQuote (:83-113): collapse doubled quotes into a fresh arena string
@@ -1112,6 +1174,14 @@ static bool BlankNoneUtf8(std::string& s, bool modify) {
 }
 
 void ProcessorFilterNative::Process(PipelineEventGroup& group) {
+    try {
+        ProcessImpl(group);
+    } catch (const std::exception& ex) {
+        EngineFailed(ex.what()); // the reference's Process never throws: the group stays as it was
+    }
+}
+
+void ProcessorFilterNative::ProcessImpl(PipelineEventGroup& group) {
     if (group.GetEvents().empty())
         return;
     EventsContainer& events = group.MutableEvents();
@@ -1235,6 +1305,14 @@ std::vector<std::pair<std::string, uint64_t>> ProcessorMergeMultilineLogNative::
 }
 
 void ProcessorMergeMultilineLogNative::Process(PipelineEventGroup& group) {
+    try {
+        ProcessImpl(group);
+    } catch (const std::exception& ex) {
+        EngineFailed(ex.what()); // the reference's Process never throws: the group stays as it was
+    }
+}
+
+void ProcessorMergeMultilineLogNative::ProcessImpl(PipelineEventGroup& group) {
     if (group.GetEvents().empty())
         return;
     if (mMergeType == MergeType::BY_REGEX) {

@@ -116,6 +116,7 @@ public:
     const std::string& Name() const override { return sName; }
     bool Init(const Json::Value& config) override;
     void Process(PipelineEventGroup& group) override;
+    void ProcessImpl(PipelineEventGroup& group);
     using Processor::Process;
     std::string mSourceKey = "content";
     char mSplitChar = '\n';
@@ -131,6 +132,7 @@ public:
     const std::string& Name() const override { return sName; }
     bool Init(const Json::Value& config) override;
     void Process(PipelineEventGroup& group) override;
+    void ProcessImpl(PipelineEventGroup& group);
     using Processor::Process;
     std::vector<std::pair<std::string, uint64_t>> Counters() const override;
     std::string mSourceKey = "content";
@@ -190,6 +192,7 @@ public:
     const std::string& Name() const override { return sName; }
     bool Init(const Json::Value& config) override;
     void Process(PipelineEventGroup& group) override;
+    void ProcessImpl(PipelineEventGroup& group);
     using Processor::Process;
     std::vector<std::pair<std::string, uint64_t>> Counters() const override;
     std::string mSourceKey, mSeparator;
@@ -217,6 +220,7 @@ public:
     const std::string& Name() const override { return sName; }
     bool Init(const Json::Value& config) override;
     void Process(PipelineEventGroup& group) override;
+    void ProcessImpl(PipelineEventGroup& group);
     using Processor::Process;
     bool mDiscardingNonUTF8 = false;
     ~ProcessorFilterNative() override;
@@ -256,6 +260,7 @@ public:
     const std::string& Name() const override { return sName; }
     bool Init(const Json::Value& config) override;
     void Process(PipelineEventGroup& group) override;
+    void ProcessImpl(PipelineEventGroup& group);
     using Processor::Process;
     std::vector<std::pair<std::string, uint64_t>> Counters() const override;
     std::string mSourceKey = "content";

@@ -1,4 +1,5 @@
 // host_capi.cpp -- JSON-driven C entry points over the host Processor classes (include/lc_b200_host.h).
+#include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -67,7 +68,10 @@ char* lc_host_processor_process(lc_host_processor_t* p, const char* group_json, 
         PipelineEventGroup group(sb);
         if (!group.FromJsonString(group_json ? group_json : "null"))
             throw std::runtime_error("group JSON does not parse");
+        const uint64_t errs = p->proc->EngineErrors();
         p->proc->Process(group);
+        if (p->proc->EngineErrors() != errs) // Process itself never throws (reference contract); the harness reports it
+            throw std::runtime_error("engine error inside Process: " + p->proc->LastError());
         return dup(group.ToJsonString(enable_event_meta != 0));
     } catch (const std::exception& e) {
         if (err_out)
@@ -118,6 +122,72 @@ char* lc_host_sls_serialize(const char* group_json, int enable_ns, unsigned long
     }
 }
 
+
+// What PluginRegistry::LoadProcessorPlugin + DynamicCProcessorProxy do with a dynamic plugin
+// (PluginRegistry.cpp:218-275, DynamicCProcessorProxy.cpp:21-36), step by step, on the plugin at so_path.
+char* lc_host_dynamic_plugin_roundtrip(const char* so_path, const char* config_json, const char* group_json,
+                                       int enable_event_meta, int* version_out, char** name_out, char** err_out) {
+    struct Iface { // CProcessor.h:23-45
+        int version;
+        const char* name;
+        const char* language;
+        int (*init)(void* ins, void* config, void* context);
+        void (*finalize)(void* state);
+        void (*process)(void* state, void* group);
+    };
+    struct Instance {
+        const Iface* plugin;
+        void* plugin_state;
+    };
+    if (err_out)
+        *err_out = nullptr;
+    void* h = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) {
+        if (err_out)
+            *err_out = dup(std::string("dlopen: ") + dlerror());
+        return nullptr;
+    }
+    char* result = nullptr;
+    try {
+        const Iface* plugin = static_cast<const Iface*>(dlsym(h, "processor_interface"));
+        if (!plugin)
+            throw std::runtime_error("symbol processor_interface not found");
+        if (version_out)
+            *version_out = plugin->version;
+        if (name_out)
+            *name_out = dup(plugin->name ? plugin->name : "");
+        if (plugin->version != 100)
+            throw std::runtime_error("plugin interface version mismatch");
+        Json::Value cfg(Json::objectValue);
+        std::string err;
+        const char* cj = config_json ? config_json : "{}";
+        if (!Json::Value::parse(cj, cj + strlen(cj), cfg, err))
+            throw std::runtime_error("config is not valid JSON: " + err);
+        Instance ins{plugin, reinterpret_cast<void*>(0xdeadbeef)}; // the proxy leaves plugin_state uninitialised
+        int ctx = 0;
+        if (plugin->init(&ins, &cfg, &ctx) != 0) {
+            if (ins.plugin_state != nullptr)
+                throw std::runtime_error("init failed and left plugin_state dangling");
+            throw std::runtime_error("init returned non-zero");
+        }
+        if (group_json) {
+            PipelineEventGroup group(std::make_shared<SourceBuffer>());
+            if (!group.FromJsonString(group_json))
+                throw std::runtime_error("group JSON does not parse");
+            plugin->process(ins.plugin_state, &group);
+            result = dup(group.ToJsonString(enable_event_meta != 0));
+        } else {
+            result = dup("null");
+        }
+        plugin->finalize(ins.plugin_state);
+    } catch (const std::exception& e) {
+        if (err_out)
+            *err_out = dup(e.what());
+        result = nullptr;
+    }
+    dlclose(h);
+    return result;
+}
 
 void lc_host_use_pinned_arenas(int on) {
     if (on)

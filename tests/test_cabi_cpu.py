@@ -69,3 +69,52 @@ def test_host_layer_init_errors():
         lc.HostProcessor("processor_parse_delimiter_native", {"SourceKey": "c", "Separator": "12345", "Keys": ["a"]})
     with pytest.raises(lc.LcError):
         lc.HostProcessor("no_such_processor", {})
+
+
+def _roundtrip(so, cfg, group):
+    import json
+    L = lc.lib()
+    L.lc_host_dynamic_plugin_roundtrip.restype = ctypes.c_void_p
+    L.lc_host_dynamic_plugin_roundtrip.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int,
+                                                   ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_void_p),
+                                                   ctypes.POINTER(ctypes.c_void_p)]
+    L.lc_host_string_free.argtypes = [ctypes.c_void_p]
+    ver, name, err = ctypes.c_int(-1), ctypes.c_void_p(), ctypes.c_void_p()
+    out = L.lc_host_dynamic_plugin_roundtrip(so.encode(), json.dumps(cfg).encode(),
+                                             None if group is None else json.dumps(group).encode(), 1,
+                                             ctypes.byref(ver), ctypes.byref(name), ctypes.byref(err))
+    nm = ctypes.string_at(name.value).decode() if name.value else None
+    er = ctypes.string_at(err.value).decode() if err.value else None
+    res = json.loads(ctypes.string_at(out).decode()) if out else None
+    for p in (out, name.value, err.value):
+        if p:
+            L.lc_host_string_free(p)
+    return ver.value, nm, res, er
+
+
+def test_dynamic_plugins_export_processor_interface_and_init_like_the_agent_loads_them():
+    """lib<name>.so per processor: dlopen + dlsym("processor_interface") + version == 100, then init / finalize the way
+    DynamicCProcessorProxy drives them (CProcessor.h:23-45, PluginRegistry.cpp:255-275).  Init needs no GPU."""
+    from loongcollector_b200 import _build
+    cfgs = {
+        "processor_parse_regex_b200": {"SourceKey": "content", "Regex": r"(\w+)\t(\w+).*", "Keys": ["a", "b"]},
+        "processor_parse_delimiter_b200": {"SourceKey": "content", "Separator": ",", "Keys": ["a", "b"]},
+        "processor_split_string_b200": {},
+        "processor_split_multiline_log_string_b200": {"Multiline": {"StartPattern": r"\d+-.*"}},
+    }
+    for name, ptype in _build.PLUGINS:
+        so = _build.plugin_path(name)
+        assert os.path.exists(so), so
+        raw = ctypes.CDLL(so)
+        assert hasattr(raw, "processor_interface")
+        ver, nm, res, err = _roundtrip(so, cfgs[name], None)
+        assert (ver, nm, res, err) == (100, name, None, None) or (ver, nm, err) == (100, name, None), (name, err)
+    # a config the reference's Init rejects: init returns non-zero and leaves plugin_state NULL
+    ver, nm, res, err = _roundtrip(_build.plugin_path("processor_parse_regex_b200"),
+                                   {"SourceKey": "content", "Regex": "(a", "Keys": ["a"]}, None)
+    assert ver == 100 and res is None and err == "init returned non-zero"
+    # whole-line mode needs no device: the full init -> process -> finalize round trip runs here
+    grp = {"events": [{"type": 1, "timestamp": 3, "timestampNanosecond": 0, "contents": {"content": "l1\nl2"}}]}
+    ver, nm, res, err = _roundtrip(_build.plugin_path("processor_parse_regex_b200"),
+                                   {"SourceKey": "content", "Regex": "(.*)", "Keys": ["msg"]}, grp)
+    assert err is None and res["events"][0]["contents"] == {"msg": "l1\nl2"}

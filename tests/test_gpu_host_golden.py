@@ -94,3 +94,27 @@ def test_merge_multiline_random_groups_match_oracle():
         assert json.dumps(got, sort_keys=True) == json.dumps(g.to_json(True), sort_keys=True), root
         checked += 1
     assert checked > 150
+
+
+@pytest.mark.parametrize("treatment", ["extend", "keep", "discard"])
+def test_delimiter_lines_with_far_more_columns_than_keys(treatment):
+    """Untrusted content: a few lines with hundreds / thousands of columns among ordinary ones.  The host class parses
+    them again on their own (bounded tables, no group-wide re-run) and still produces exactly the reference's events
+    (`__columnN__` keys in extend mode, the joined remainder in keep mode)."""
+    import json
+
+    import loongcollector_b200 as lc
+    from oracle import oracle as orc
+
+    name = "processor_parse_delimiter_native"
+    cfg = {"SourceKey": "content", "Separator": ",", "Quote": '"', "Keys": ["a", "b", "c"],
+           "OverflowedFieldsTreatment": treatment, "KeepingSourceWhenParseFail": True}
+    lines = ["1,2,3", "x,y", ",".join(str(i) for i in range(300)), "p,\"q,r\",s,t", ",".join(["z"] * 5000),
+             "\"a\"\"b\",c", ",".join("\"v%d\"\"w\"" % i for i in range(40)), ""]
+    evs = [{"type": 1, "timestamp": 5, "timestampNanosecond": 0, "contents": {"content": ln}} for ln in lines]
+    root = {"events": evs}
+    host, ora = lc.HostProcessor(name, cfg), orc.PROCESSORS[name](cfg)
+    got = host.process(json.loads(json.dumps(root)), True)
+    g = orc.Group.from_json(json.loads(json.dumps(root)))
+    ora.process(g)
+    assert json.dumps(got, sort_keys=True) == json.dumps(g.to_json(True), sort_keys=True)
