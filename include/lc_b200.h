@@ -178,6 +178,20 @@ int lc_multiline_split_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, c
                            uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, uint64_t* n_out /* host */,
                            uint64_t counters[3] /* host */);
 
+/* ---- f3 (next row): LogFileReader::RemoveLastIncompleteLog (core/file_server/reader/LogFileReader.cpp:1997-2064) for
+ * raw text (RawTextParser::GetLastLine, :2186-2204): how many leading bytes of a freshly read chunk form complete logs.
+ * start / end: MultilineOptions::GetStartPatternReg / GetEndPatternReg or NULL (multiline mode iff one is set).
+ * *keep_bytes = the function's return value ("the number of bytes left, including \n"); *rollback_line_feeds =
+ * rollbackLineFeedCount (left untouched when allow_rollback == 0 or len == 0, like the reference).  The walk back
+ * over the chunk's lines becomes "the last line whose probe flag is set" over the split pass's line table, so a raw
+ * file chunk can go to the GPU before the reader knows where its last complete record ends. */
+int lc_remove_last_incomplete_log(lc_engine_t* e, const uint8_t* buf, uint64_t len, const lc_regex_t* start,
+                                  const lc_regex_t* end, int allow_rollback, uint64_t* keep_bytes,
+                                  int32_t* rollback_line_feeds);
+int lc_remove_last_incomplete_log_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, const lc_regex_t* start,
+                                      const lc_regex_t* end, int allow_rollback, uint64_t* keep_bytes /* host */,
+                                      int32_t* rollback_line_feeds /* host */);
+
 /* ---- a4: ProcessorParseDelimiterNative::ProcessEvent (ProcessorParseDelimiterNative.cpp:206-409)
  *          + DelimiterModeFsmParser::ParseDelimiterLine (core/parser/DelimiterModeFsmParser.cpp:260-294)
  * Per event: trim (:226-238), then the quote FSM (sep_len == 1 && quote != sep[0]) or the multi-char

@@ -65,6 +65,9 @@ def lib():
     multi_args = [vp, vp, u32, vp, vp, u64, vp, vp, u64, vp, vp, vp, u32, vp, vp]
     L.lc_regex_parse_multi.argtypes = multi_args
     L.lc_regex_parse_multi_dev.argtypes = multi_args
+    rl_args = [vp, vp, u64, vp, vp, i32, C.POINTER(u64), C.POINTER(C.c_int32)]
+    L.lc_remove_last_incomplete_log.argtypes = rl_args
+    L.lc_remove_last_incomplete_log_dev.argtypes = rl_args
     L.lc_regex_prefix_match.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
     L.lc_regex_match.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
     L.lc_regex_match_dev.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
@@ -233,6 +236,14 @@ class Engine:
 
     def set_stream(self, stream):
         _check(lib().lc_engine_set_stream(self._h, _p(stream) if stream else None))
+
+    def remove_last_incomplete_log(self, buf, start, end, allow_rollback=True):
+        """LogFileReader::RemoveLastIncompleteLog (raw text) -> (bytes to keep, rollbackLineFeedCount)."""
+        a = _u8(buf)
+        keep, rb = C.c_uint64(0), C.c_int32(0)
+        _check(lib().lc_remove_last_incomplete_log(self._h, _p(a), a.size, _rh(start), _rh(end),
+                                                   int(bool(allow_rollback)), C.byref(keep), C.byref(rb)))
+        return int(keep.value), int(rb.value)
 
     def regex_prefix_match(self, rx, base, ev_off, ev_len):
         a = _u8(base)

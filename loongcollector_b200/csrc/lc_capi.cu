@@ -1466,6 +1466,81 @@ int lc_multiline_split(lc_engine_t* e, const uint8_t* buf, uint64_t len, const l
     return LC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ last incomplete log
+int lc_remove_last_incomplete_log_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, const lc_regex_t* start,
+                                      const lc_regex_t* end, int allow_rollback, uint64_t* keep_bytes,
+                                      int32_t* rollback_line_feeds) {
+    if (!e || !keep_bytes || !rollback_line_feeds || (len && !d_buf))
+        return fail(LC_ERR_INVALID_ARG, "lc_remove_last_incomplete_log_dev: bad arguments");
+    int rc;
+    for (const lc_regex_t* r : {start, end})
+        if (r && (rc = check_regex_usable(r, "lc_remove_last_incomplete_log")))
+            return rc;
+    *keep_bytes = len;
+    if (!allow_rollback || len == 0) // :1999-2001: nothing to do, the caller's count stays as it is
+        return LC_OK;
+    if (len >= 0x7FFFFFF0ull)
+        return fail(LC_ERR_TOO_LARGE, "chunk must be < 2 GiB (the reference's sizes are int32_t)");
+    rc = bind(e);
+    if (rc)
+        return rc;
+    lck::MlConfig cfg;
+    CU_TRY(engine_blob(e, start, &cfg.blob_start));
+    cfg.blob_cont = nullptr;
+    CU_TRY(engine_blob(e, end, &cfg.blob_end));
+    cfg.discard = 0;
+    Small* ds = e->small.as<Small>();
+    Small* hs = (Small*)e->h_small;
+    const uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
+    uint64_t lcap = len / 24 + 4096;
+    for (;;) {
+        if (lcap > len)
+            lcap = len;
+        CU_TRY(e->lines_off.ensure((lcap + 1) * 4));
+        CU_TRY(e->lines_len.ensure((lcap + 1) * 4));
+        CU_TRY(e->flags.ensure(lcap + 1));
+        DescPlan plan;
+        rc = prep_desc(e, lck::split_tiles(len, shift), 0, 0, plan);
+        if (rc)
+            return rc;
+        lck::launch_split_probe(cfg, d_buf, (uint32_t)len, e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(),
+                                e->flags.as<uint8_t>(), (uint32_t)lcap, plan.r[0], &ds->tickets[0], &ds->n_out,
+                                &ds->total_chars, e->stream);
+        lck::launch_last_record(e->flags.as<uint8_t>(), e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(),
+                                &ds->n_out, (uint32_t)lcap, (uint32_t)len, start != nullptr, end != nullptr,
+                                ds->counters, e->stream);
+        e->launches += 2;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        if (hs->n_out <= lcap)
+            break;
+        lcap = hs->n_out;
+    }
+    *keep_bytes = hs->counters[0];
+    *rollback_line_feeds = (int32_t)hs->counters[1];
+    return LC_OK;
+}
+
+int lc_remove_last_incomplete_log(lc_engine_t* e, const uint8_t* buf, uint64_t len, const lc_regex_t* start,
+                                  const lc_regex_t* end, int allow_rollback, uint64_t* keep_bytes,
+                                  int32_t* rollback_line_feeds) {
+    if (!e || !keep_bytes || !rollback_line_feeds || (len && !buf))
+        return fail(LC_ERR_INVALID_ARG, "lc_remove_last_incomplete_log: bad arguments");
+    *keep_bytes = len;
+    if (!allow_rollback || len == 0)
+        return LC_OK;
+    if (len >= 0x7FFFFFF0ull)
+        return fail(LC_ERR_TOO_LARGE, "chunk must be < 2 GiB (the reference's sizes are int32_t)");
+    int rc = bind(e);
+    if (rc)
+        return rc;
+    CU_TRY(e->in.ensure(len + 16));
+    CU_TRY(cudaMemcpyAsync(e->in.p, buf, len, cudaMemcpyHostToDevice, e->stream));
+    return lc_remove_last_incomplete_log_dev(e, e->in.as<uint8_t>(), len, start, end, allow_rollback, keep_bytes,
+                                             rollback_line_feeds);
+}
+
 // ------------------------------------------------------------------------------------------------ delimiter
 int lc_delim_parse_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len, const uint32_t* d_ev_off,
                        const uint32_t* d_ev_len, uint64_t n, const uint8_t* sep, uint32_t sep_len, uint8_t quote,

@@ -2670,6 +2670,88 @@ void launch_ml_fused(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t
         (volatile uint64_t*)d_desc_state, (volatile uint64_t*)d_desc_sum, d_ticket, d_counters, d_total);
 }
 
+// ---- f3 (next row): LogFileReader::RemoveLastIncompleteLog over the line table + probe flags of the split pass --------
+// core/file_server/reader/LogFileReader.cpp:1997-2064 walks the chunk backwards line by line (RawTextParser::GetLastLine,
+// :2186-2204) until a line matches the end pattern (and is newline-terminated) or, without an end pattern, the start
+// pattern.  With flags[line] at hand that walk is "the last line whose flag is set": one block searches the table from
+// the back, 1024 lines per step.  out[0] = bytes to keep, out[1] = rollbackLineFeedCount.
+__global__ void __launch_bounds__(1024)
+    last_record_kernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ off,
+                       const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_lines, uint32_t line_cap,
+                       uint32_t size, int has_start, int has_end, unsigned long long* __restrict__ out) {
+    __shared__ long long s_best;
+    __shared__ int s_any_end;
+    const uint32_t n = min(*n_lines, line_cap);
+    if (threadIdx.x == 0) {
+        s_best = -1;
+        s_any_end = 0;
+    }
+    __syncthreads();
+    long long hit = -1;
+    if (has_start || has_end) {
+        const uint32_t want = has_end ? 4u : 1u;
+        for (long long hi = (long long)n - 1; hi >= 0; hi -= 1024) {
+            const long long j = hi - threadIdx.x;
+            if (j >= 0 && (flags[j] & want)) {
+                // an end line only counts when its newline is inside the chunk ("ensure the end line is complete")
+                if (!has_end || off[j] + len[j] < size)
+                    atomicMax(&s_best, j);
+                else
+                    s_any_end = 1; // foundEnd on the unterminated last line
+            }
+            __syncthreads();
+            hit = s_best;
+            __syncthreads(); // everyone has read s_best before the next step may raise it
+            if (hit >= 0)
+                break;
+        }
+    }
+    if (threadIdx.x != 0)
+        return;
+    // rollback contribution of lines [a, n): one each, except a line that ends at offset 0 (GetLastLine(end == 0))
+    auto rb_from = [&](long long a) -> unsigned long long {
+        if (a >= (long long)n)
+            return 0;
+        unsigned long long c = (unsigned long long)(n - a);
+        if (a == 0 && n > 0 && off[0] + len[0] == 0)
+            --c;
+        return c;
+    };
+    unsigned long long keep, rb;
+    if (hit >= 0 && has_end) {
+        keep = (unsigned long long)off[hit] + len[hit] + 1;
+        rb = rb_from(hit + 1);
+    } else if (hit >= 0) {
+        keep = off[hit];
+        rb = rb_from(hit);
+    } else if (has_end && s_any_end) {
+        keep = 0;
+        rb = rb_from(0);
+    } else if (n == 0) {
+        keep = size;
+        rb = 0;
+    } else {
+        // single-line rollback (or nothing matched): keep everything when the last line is complete
+        const uint32_t L = n - 1, end = off[L] + len[L];
+        if (end != 0 && end < size) {
+            keep = (unsigned long long)end + 1;
+            rb = 0;
+        } else {
+            keep = off[L];
+            rb = end != 0 ? 1 : 0;
+        }
+    }
+    out[0] = keep;
+    out[1] = rb;
+}
+
+void launch_last_record(const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len, const uint32_t* d_n_lines,
+                        uint32_t line_cap, uint32_t size, bool has_start, bool has_end, unsigned long long* d_out,
+                        cudaStream_t st) {
+    last_record_kernel<<<1, 1024, 0, st>>>(d_flags, d_off, d_len, d_n_lines, line_cap, size, has_start ? 1 : 0,
+                                           has_end ? 1 : 0, d_out);
+}
+
 // ================================================================================================ delimiter
 // STAGED (max_fields <= kDelimStagedMaxFields): the [32 lines][max_fields] blocks of f_off / f_len / f_dq that a warp
 // produces are contiguous in the output tables, so they are assembled in shared memory (row pitch max_fields | 1:

@@ -178,6 +178,11 @@ void launch_ml_fused(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t
                      uint64_t* d_desc_sum, uint32_t* d_ticket, unsigned long long* d_counters, uint64_t* d_total,
                      cudaStream_t st);
 
+// f3: last complete record of a chunk from the split pass's line table + flags; d_out[0] = keep bytes, [1] = rollback
+void launch_last_record(const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len, const uint32_t* d_n_lines,
+                        uint32_t line_cap, uint32_t size, bool has_start, bool has_end, unsigned long long* d_out,
+                        cudaStream_t st);
+
 // a4: delimiter
 struct DelimConfig {
     uint8_t sep[4];

@@ -344,6 +344,78 @@ uint64_t orc_multiline_split(const uint8_t* buf, uint64_t len, orc_matcher* star
     return o.n;
 }
 
+/* ------------------------------------------------------------------ last incomplete log (next row f3)
+ * LogFileReader::RemoveLastIncompleteLog (core/file_server/reader/LogFileReader.cpp:1997-2064) over
+ * RawTextParser::GetLastLine (:2186-2204): how many leading bytes of a freshly read chunk form complete logs, and how
+ * many line feeds are rolled back.  start / end = MultilineOptions::GetStartPatternReg / GetEndPatternReg (NULL = not
+ * configured; multiline mode iff one of them is set).  buf[size] must be readable (the reader's buffer is NUL
+ * terminated one past the end, :2521). */
+typedef struct orc_line_info {
+    int32_t begin, end, rollback, full;
+} orc_line_info;
+
+static orc_line_info orc_get_last_line(const uint8_t* buf, int32_t end) { /* :2186-2204 */
+    orc_line_info r = {0, 0, 0, 0};
+    if (end == 0)
+        return r;
+    r.end = end;
+    r.rollback = 1;
+    r.full = 1;
+    for (int32_t b = end; b > 0; --b)
+        if (buf[b - 1] == '\n') {
+            r.begin = b;
+            return r;
+        }
+    r.begin = 0;
+    return r;
+}
+
+int32_t orc_remove_last_incomplete_log(const uint8_t* buf, int32_t size, orc_matcher* start, orc_matcher* end,
+                                       int allow_rollback, int32_t* rollback_out) {
+    int32_t rollback = *rollback_out;
+    if (!allow_rollback || size == 0) /* :1999-2001 (the count is left as the caller initialised it) */
+        return size;
+    int32_t endPs = buf[size - 1] == '\n' ? size - 1 : size;
+    rollback = 0;
+    int foundEnd = 0;
+    if (start || end) { /* IsMultiline() */
+        while (endPs >= 0) {
+            orc_line_info c = orc_get_last_line(buf, endPs);
+            const uint8_t* d = buf + c.begin;
+            uint64_t dl = (uint64_t)(c.end - c.begin);
+            if (end) {
+                if (orc_regex_prefix_match(end, d, dl)) {
+                    foundEnd = 1;
+                    if (buf[c.end] == '\n') {
+                        *rollback_out = rollback;
+                        return c.end + 1;
+                    }
+                }
+            } else if (start && orc_regex_prefix_match(start, d, dl)) {
+                rollback += c.rollback;
+                *rollback_out = rollback;
+                return c.begin;
+            }
+            rollback += c.rollback;
+            endPs = c.begin - 1;
+        }
+    }
+    if (end && foundEnd) {
+        *rollback_out = rollback;
+        return 0;
+    }
+    rollback = 0;
+    endPs = buf[size - 1] == '\n' ? size - 1 : size;
+    orc_line_info c = orc_get_last_line(buf, endPs);
+    if (c.full && buf[c.end] == '\n') {
+        *rollback_out = rollback;
+        return c.end + 1;
+    }
+    rollback += c.rollback;
+    *rollback_out = rollback;
+    return c.begin;
+}
+
 /* ------------------------------------------------------------------ delimiter */
 enum { ST_INITIAL = 0, ST_QUOTE = 1, ST_DATA = 2, ST_DOUBLE_QUOTE = 3 };
 

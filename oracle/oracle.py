@@ -82,6 +82,9 @@ def lib():
     L.orc_delim_parse_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
                                         C.c_uint8, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_remove_last_incomplete_log.restype = C.c_int32
+    L.orc_remove_last_incomplete_log.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.POINTER(C.c_int32)]
     _LIB = L
     return L
 
@@ -139,6 +142,32 @@ class Regex:
                 L.orc_regex_free(self._re)
         except Exception:
             pass
+
+
+def remove_last_incomplete_log(buf, start: Optional["Regex"], end: Optional["Regex"], allow_rollback: bool = True):
+    """LogFileReader::RemoveLastIncompleteLog (raw text): -> (bytes to keep, rollbackLineFeedCount)."""
+    a = _as_u8(buf)
+    padded = np.concatenate([a, np.zeros(1, np.uint8)])  # the reader's buffer is NUL terminated one past the end
+    rb = C.c_int32(0)
+    keep = lib().orc_remove_last_incomplete_log(_ptr(padded), a.size, start._m if start else None,
+                                                end._m if end else None, 1 if allow_rollback else 0, C.byref(rb))
+    return int(keep), int(rb.value)
+
+
+def multiline_regs(cfg: dict):
+    """(start, end) Regex objects a LogFileReader holds for this Multiline config: MultilineOptions::Init
+    (core/file_server/MultilineOptions.cpp:125-160,205-222) -- Continue alone is ignored, patterns are kept with their
+    trailing '$' / '.*' removed, a pattern reduced to nothing is dropped."""
+    def reg(p):
+        if not p:
+            return None
+        if p.endswith("$"):
+            p = p[:-1]
+        while p.endswith(".*"):
+            p = p[:-2]
+        return Regex(p) if p else None
+    start, end = reg(cfg.get("StartPattern")), reg(cfg.get("EndPattern"))
+    return start, end
 
 
 def split_lines(buf, split_char: int = 10):

@@ -596,3 +596,56 @@ def test_regex_assertions_inside_the_pattern(eng):
         lines.append("".join(rng.choice(alpha) for _ in range(rng.randint(0, 40))).encode().rstrip(b"\n"))
     for pattern in patterns:
         _check_parse(eng, pattern, lines)
+
+
+# ------------------------------------------------------------------------------------------- f3: last incomplete log
+def _host_multiline_regs(cfg):
+    """the (start, end) regexes of a reader for this Multiline config (MultilineOptions.cpp:125-160,205-222)"""
+    lc = _lc()
+
+    def reg(p):
+        if not p:
+            return None
+        if p.endswith("$"):
+            p = p[:-1]
+        while p.endswith(".*"):
+            p = p[:-2]
+        return lc.Regex(p) if p else None
+    return reg(cfg.get("StartPattern")), reg(cfg.get("EndPattern"))
+
+
+def test_remove_last_incomplete_log_reference_fixtures(eng):
+    """every case of core/unittest/reader/RemoveLastIncompleteLogUnittest.cpp (raw-text reader)"""
+    with open(os.path.join(HERE, "golden", "ref_rollback.json"), encoding="utf-8") as f:
+        cases = json.load(f)
+    assert len(cases) == 29
+    for c in cases:
+        start, end = _host_multiline_regs(c["config"])
+        if not c["input"]:
+            continue  # size == 0 returns before anything is computed
+        keep, rb = eng.remove_last_incomplete_log(c["input"].encode(), start, end, True)
+        assert (keep, rb) == (c["expect_size"], c["expect_rollback"]), (c["name"], c["title"])
+
+
+@pytest.mark.parametrize("mode", ["", "S", "E", "SE"])
+def test_remove_last_incomplete_log_random_chunks_match_oracle(eng, mode):
+    lc = _lc()
+    rng = random.Random(len(mode) * 31 + 7)
+    s_pat, e_pat = r"Exception", r"\s*\.\.\.\d+ more"
+    start = lc.Regex(s_pat) if "S" in mode else None
+    end = lc.Regex(e_pat) if "E" in mode else None
+    o_start = orc.Regex(s_pat) if "S" in mode else None
+    o_end = orc.Regex(e_pat) if "E" in mode else None
+    pieces = [BEGIN, CONT, END, UNM, b"", b"x"]
+    for trial in range(150):
+        k = rng.randint(0, 12) if trial % 10 else rng.randint(2000, 6000)
+        lines = [rng.choice(pieces) for _ in range(k)]
+        buf = b"\n".join(lines) + (b"\n" if rng.random() < 0.5 else b"")
+        if rng.random() < 0.1:
+            buf = b"\n" * rng.randint(1, 3) + buf
+        if not buf:
+            continue
+        got = eng.remove_last_incomplete_log(buf, start, end, True)
+        want = orc.remove_last_incomplete_log(buf, o_start, o_end, True)
+        assert got == want, (mode, buf[-200:])
+    assert eng.remove_last_incomplete_log(b"a\nb", start, end, False)[0] == 3
