@@ -224,6 +224,22 @@ int lc_sls_serialize_logs(lc_engine_t* e, const uint8_t* base, uint64_t base_len
                           const uint32_t* ent_klen, const uint32_t* ent_voff, const uint32_t* ent_vlen, uint8_t* out,
                           uint64_t out_cap, uint64_t* out_len);
 
+/* Device-fed variant for the regex -> serialise hand-over: the `Logs` fields of the events a ProcessorParseRegexNative
+ * leaves behind, written straight from its DEVICE result tables (status / cap_off / cap_len of lc_regex_parse_dev,
+ * rows of row_pitch entries) and the constant key strings -- no host-side (key, value) span lists, the bytes never
+ * leave the GPU between parsing and the wire format.  Event i with LC_REGEX_OK carries keys[k] -> capture k for
+ * k < nkeys in key order (AddLog per capture, ProcessorParseRegexNative.cpp:249-251; the source key is deleted,
+ * :153-155); a failed event carries the one content fail_key -> the whole line when fail_key != NULL
+ * (KeepingSourceWhenParseFail with RenamedSourceKey, :156-158) and is skipped otherwise (erased,
+ * CommonParserOptions.cpp:99-117).  keys must be distinct.  d_ev_time_ns may be NULL; LC_SLS_NO_NS per event = no
+ * Time_ns.  d_out receives the bytes on the device; *out_len (host) their count; LC_ERR_CAPACITY if > out_cap. */
+int lc_sls_serialize_parsed_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len, const uint32_t* d_ev_off,
+                                const uint32_t* d_ev_len, const uint8_t* d_status, const uint32_t* d_cap_off,
+                                const uint32_t* d_cap_len, uint32_t row_pitch, uint64_t n, const char* const* keys,
+                                const uint32_t* key_lens, uint32_t nkeys, const char* fail_key, uint32_t fail_key_len,
+                                const uint32_t* d_ev_time, const uint32_t* d_ev_time_ns, uint8_t* d_out,
+                                uint64_t out_cap, uint64_t* out_len);
+
 #ifdef __cplusplus
 }
 #endif

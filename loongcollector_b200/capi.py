@@ -68,6 +68,8 @@ def lib():
     rl_args = [vp, vp, u64, vp, vp, i32, C.POINTER(u64), C.POINTER(C.c_int32)]
     L.lc_remove_last_incomplete_log.argtypes = rl_args
     L.lc_remove_last_incomplete_log_dev.argtypes = rl_args
+    L.lc_sls_serialize_parsed_dev.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, u32, u64, vp, vp, u32, C.c_char_p, u32, vp,
+                                              vp, vp, u64, C.POINTER(u64)]
     L.lc_regex_prefix_match.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
     L.lc_regex_match.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
     L.lc_regex_match_dev.argtypes = [vp, vp, vp, u64, vp, vp, u64, vp]
@@ -317,6 +319,18 @@ class Engine:
                                            _p(np.array(begin, np.uint64)), _p(a32(koff)), _p(a32(klen)),
                                            _p(a32(voff)), _p(a32(vlen)), _p(out), cap, C.byref(need)))
         return bytes(out[:need.value])
+
+    def sls_serialize_parsed_dev(self, d_base, base_len, d_ev_off, d_ev_len, d_status, d_cap_off, d_cap_len, row_pitch,
+                                 n, keys, fail_key, d_ev_time, d_ev_time_ns, d_out, out_cap):
+        """keys: list of bytes; fail_key: bytes or None.  Returns the number of wire bytes written to d_out."""
+        arr = (C.c_char_p * max(len(keys), 1))(*keys)
+        kl = np.array([len(k) for k in keys] or [0], np.uint32)
+        need = C.c_uint64(0)
+        _check(lib().lc_sls_serialize_parsed_dev(self._h, _p(d_base), base_len, _p(d_ev_off), _p(d_ev_len),
+                                                 _p(d_status), _p(d_cap_off), _p(d_cap_len), row_pitch, n, arr, _p(kl),
+                                                 len(keys), fail_key, len(fail_key) if fail_key else 0, _p(d_ev_time),
+                                                 _p(d_ev_time_ns), _p(d_out), out_cap, C.byref(need)))
+        return int(need.value)
 
     def split_lines_dev(self, d_buf, length, split_char, d_off, d_len, cap):
         n = C.c_uint64(0)

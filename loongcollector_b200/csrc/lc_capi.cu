@@ -1696,4 +1696,77 @@ int lc_sls_serialize_logs(lc_engine_t* e, const uint8_t* base, uint64_t base_len
     return LC_OK;
 }
 
+int lc_sls_serialize_parsed_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len, const uint32_t* d_ev_off,
+                                const uint32_t* d_ev_len, const uint8_t* d_status, const uint32_t* d_cap_off,
+                                const uint32_t* d_cap_len, uint32_t row_pitch, uint64_t n, const char* const* keys,
+                                const uint32_t* key_lens, uint32_t nkeys, const char* fail_key, uint32_t fail_key_len,
+                                const uint32_t* d_ev_time, const uint32_t* d_ev_time_ns, uint8_t* d_out,
+                                uint64_t out_cap, uint64_t* out_len) {
+    if (!e || !out_len || (n && (!d_base || !d_ev_off || !d_ev_len || !d_status || !d_ev_time)) ||
+        (nkeys && (!keys || !key_lens || !d_cap_off || !d_cap_len)) || nkeys > row_pitch || nkeys > LC_MAX_GROUPS)
+        return fail(LC_ERR_INVALID_ARG, "lc_sls_serialize_parsed_dev: bad arguments");
+    *out_len = 0;
+    if (n == 0)
+        return LC_OK;
+    if (base_len >= 0xFFFFFFF0ull || n >= (1ull << 30))
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB and < 2^30 events per call");
+    for (uint32_t a = 0; a < nkeys; ++a)
+        for (uint32_t b = a + 1; b < nkeys; ++b)
+            if (key_lens[a] == key_lens[b] && !memcmp(keys[a], keys[b], key_lens[a]))
+                return fail(LC_ERR_INVALID_ARG, "lc_sls_serialize_parsed_dev: keys must be distinct (a repeated key "
+                                                "overwrites its earlier content, LogEvent.cpp:83-95)");
+    int rc = bind(e);
+    if (rc)
+        return rc;
+    // constant key strings: [keys..., fail key] back to back + offsets, staged through the engine's key buffer
+    std::vector<uint8_t> kb;
+    std::vector<uint32_t> at(nkeys + 2);
+    for (uint32_t k = 0; k < nkeys; ++k) {
+        at[k] = (uint32_t)kb.size();
+        kb.insert(kb.end(), keys[k], keys[k] + key_lens[k]);
+    }
+    at[nkeys] = (uint32_t)kb.size();
+    if (fail_key)
+        kb.insert(kb.end(), fail_key, fail_key + fail_key_len);
+    at[nkeys + 1] = (uint32_t)kb.size();
+    const size_t at_bytes = at.size() * 4;
+    CU_TRY(e->order.ensure(at_bytes + kb.size() + 16));
+    CU_TRY(cudaMemcpyAsync(e->order.p, at.data(), at_bytes, cudaMemcpyHostToDevice, e->stream));
+    if (!kb.empty())
+        CU_TRY(cudaMemcpyAsync(e->order.as<uint8_t>() + at_bytes, kb.data(), kb.size(), cudaMemcpyHostToDevice,
+                               e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream)); // (pageable sources: their bytes must be on the device before they die)
+    lck::SlsParsedArgs a{d_base, d_ev_off, d_ev_len, d_status, d_cap_off, d_cap_len, row_pitch,
+                         e->order.as<uint8_t>() + at_bytes, e->order.as<uint32_t>(), nkeys, fail_key ? 1u : 0u};
+    CU_TRY(e->lab_sizes.ensure(n * 4));
+    CU_TRY(e->cnt.ensure(n * 4));
+    CU_TRY(e->lab_off.ensure(n * 8));
+    DescPlan plan;
+    rc = prep_desc(e, 0, 0, lck::scan_tiles(n), plan);
+    if (rc)
+        return rc;
+    Small* ds = e->small.as<Small>();
+    Small* hs = (Small*)e->h_small;
+    lck::launch_sls_parsed_sizes(a, d_ev_time_ns, n, e->lab_sizes.as<uint32_t>(), e->cnt.as<uint32_t>(), e->stream);
+    lck::launch_exclusive_sum(e->lab_sizes.as<uint32_t>(), n, e->lab_off.as<uint64_t>(), &ds->total, plan.r[2],
+                              &ds->tickets[2], e->stream);
+    e->launches += 2;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(&hs->total, &ds->total, 8, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    *out_len = hs->total;
+    if (hs->total > out_cap)
+        return fail(LC_ERR_CAPACITY, "lc_sls_serialize_parsed_dev: output capacity too small");
+    if (hs->total == 0)
+        return LC_OK;
+    if (!d_out)
+        return fail(LC_ERR_INVALID_ARG, "lc_sls_serialize_parsed_dev: bad arguments");
+    lck::launch_sls_parsed_emit(a, d_ev_time, d_ev_time_ns, n, e->lab_off.as<uint64_t>(), e->cnt.as<uint32_t>(),
+                                d_out, e->stream);
+    e->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return LC_OK;
+}
+
 } // extern "C"

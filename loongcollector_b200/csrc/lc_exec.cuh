@@ -575,3 +575,72 @@ LC_HD void lc_sls_emit_log(uint8_t* out, const uint8_t* base, uint32_t time, boo
         out[at + 4] = (uint8_t)(ns >> 24);
     }
 }
+
+// ---- the same writer over an abstract contents list (entry k = key bytes + value bytes), so that the contents can come
+// from the regex stage's capture tables instead of host-built span lists.  En: uint32_t klen(k), vlen(k);
+// const uint8_t* key(k), val(k).
+template <class En>
+LC_HD uint32_t lc_sls_log_size_t(const En& en, uint32_t count, bool has_ns, uint32_t* body_out) {
+    if (count == 0) {
+        *body_out = 0;
+        return 0;
+    }
+    uint32_t body = 1 + 5 + (has_ns ? 1 + 4 : 0);
+    for (uint32_t k = 0; k < count; ++k) {
+        const uint32_t in = lc_sls_pair_inner(en.klen(k), en.vlen(k));
+        body += 1 + lc_varint_size(in) + in;
+    }
+    *body_out = body;
+    return 1 + lc_varint_size(body) + body;
+}
+
+template <class En>
+LC_HD void lc_sls_emit_log_t(uint8_t* out, uint32_t time, bool has_ns, uint32_t ns, const En& en, uint32_t count,
+                             uint32_t body, uint32_t lane, uint32_t nlanes) {
+    uint32_t at = 0;
+    uint8_t hdr[16];
+    uint32_t h = 0;
+    hdr[h++] = 0x0A;
+    h += lc_put_varint(hdr + h, body);
+    hdr[h++] = 0x08;
+    h += lc_put_varint(hdr + h, time < (1u << 28) ? (1u << 28) : time); // always 5 bytes
+    if (lane == 0)
+        for (uint32_t j = 0; j < h; ++j)
+            out[j] = hdr[j];
+    at = h;
+    for (uint32_t k = 0; k < count; ++k) {
+        const uint32_t kl = en.klen(k), vl = en.vlen(k);
+        const uint8_t* kp = en.key(k);
+        const uint8_t* vp = en.val(k);
+        h = 0;
+        hdr[h++] = 0x12;
+        h += lc_put_varint(hdr + h, lc_sls_pair_inner(kl, vl));
+        hdr[h++] = 0x0A;
+        h += lc_put_varint(hdr + h, kl);
+        if (lane == 0)
+            for (uint32_t j = 0; j < h; ++j)
+                out[at + j] = hdr[j];
+        at += h;
+        for (uint32_t j = lane; j < kl; j += nlanes)
+            out[at + j] = kp[j];
+        at += kl;
+        h = 0;
+        hdr[h++] = 0x12;
+        h += lc_put_varint(hdr + h, vl);
+        if (lane == 0)
+            for (uint32_t j = 0; j < h; ++j)
+                out[at + j] = hdr[j];
+        at += h;
+        for (uint32_t j = lane; j < vl; j += nlanes)
+            out[at + j] = vp[j];
+        at += vl;
+    }
+    if (has_ns && lane == 0) {
+        out[at] = 0x25;
+        out[at + 1] = (uint8_t)ns;
+        out[at + 2] = (uint8_t)(ns >> 8);
+        out[at + 3] = (uint8_t)(ns >> 16);
+        out[at + 4] = (uint8_t)(ns >> 24);
+    }
+}
+

@@ -2974,4 +2974,91 @@ void launch_sls_emit(const uint8_t* d_base, const uint32_t* d_ev_time, const uin
                                                                           d_body_size, d_out);
 }
 
+// ---- f4, device-fed: Log records of the events a ProcessorParseRegexNative leaves behind, straight from its result
+// tables.  Event i with status OK carries the contents keys[k] -> capture k (k < nkeys, what AddLog stores at
+// ProcessorParseRegexNative.cpp:249-251, the source key deleted at :153-155); a failed event carries the single content
+// fail_key -> the whole line when a fail key is configured (KeepingSourceWhenParseFail + RenamedSourceKey, :156-158)
+// and is otherwise skipped (erased, CommonParserOptions.cpp:99-117).
+struct SlsParsed {
+    const uint8_t* base;
+    const uint32_t* ev_off;
+    const uint32_t* ev_len;
+    const uint8_t* status;
+    const uint32_t* cap_off;
+    const uint32_t* cap_len;
+    uint32_t pitch;
+    const uint8_t* keys;    // device: key bytes back to back
+    const uint32_t* key_at; // device: [nkeys + 2] offsets into keys (entry nkeys = the fail key)
+    uint32_t nkeys;
+    uint32_t has_fail_key;
+};
+
+struct SlsParsedEntries {
+    const SlsParsed& p;
+    uint64_t i;
+    bool ok;
+    __device__ uint32_t klen(uint32_t k) const {
+        const uint32_t q = ok ? k : p.nkeys;
+        return p.key_at[q + 1] - p.key_at[q];
+    }
+    __device__ const uint8_t* key(uint32_t k) const { return p.keys + p.key_at[ok ? k : p.nkeys]; }
+    __device__ uint32_t vlen(uint32_t k) const { return ok ? p.cap_len[i * p.pitch + k] : p.ev_len[i]; }
+    __device__ const uint8_t* val(uint32_t k) const { return p.base + (ok ? p.cap_off[i * p.pitch + k] : p.ev_off[i]); }
+};
+
+__device__ __forceinline__ uint32_t sls_parsed_count(const SlsParsed& p, uint64_t i, bool& ok) {
+    ok = p.status[i] == 0;
+    return ok ? p.nkeys : (p.has_fail_key ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(256)
+    sls_parsed_size_kernel(SlsParsed p, const uint32_t* __restrict__ ev_ns, uint64_t n, uint32_t* __restrict__ rec_size,
+                           uint32_t* __restrict__ body_size) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    bool ok;
+    const uint32_t cnt = sls_parsed_count(p, i, ok);
+    SlsParsedEntries en{p, i, ok};
+    uint32_t body;
+    rec_size[i] = lc_sls_log_size_t(en, cnt, ev_ns && ev_ns[i] != 0xFFFFFFFFu, &body);
+    body_size[i] = body;
+}
+
+__global__ void __launch_bounds__(256)
+    sls_parsed_emit_kernel(SlsParsed p, const uint32_t* __restrict__ ev_time, const uint32_t* __restrict__ ev_ns,
+                           uint64_t n, const uint64_t* __restrict__ rec_off, const uint32_t* __restrict__ body_size,
+                           uint8_t* __restrict__ out) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n)
+        return;
+    bool ok;
+    const uint32_t cnt = sls_parsed_count(p, i, ok);
+    if (!cnt)
+        return;
+    SlsParsedEntries en{p, i, ok};
+    const bool has_ns = ev_ns && ev_ns[i] != 0xFFFFFFFFu;
+    lc_sls_emit_log_t(out + rec_off[i], ev_time[i], has_ns, has_ns ? ev_ns[i] : 0u, en, cnt, body_size[i],
+                      threadIdx.x & 31, 32);
+}
+
+void launch_sls_parsed_sizes(const SlsParsedArgs& a, const uint32_t* d_ev_ns, uint64_t n, uint32_t* d_rec_size,
+                             uint32_t* d_body_size, cudaStream_t st) {
+    if (!n)
+        return;
+    SlsParsed p{a.base, a.ev_off, a.ev_len, a.status, a.cap_off, a.cap_len, a.pitch, a.keys, a.key_at, a.nkeys,
+                a.has_fail_key};
+    sls_parsed_size_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, d_ev_ns, n, d_rec_size, d_body_size);
+}
+
+void launch_sls_parsed_emit(const SlsParsedArgs& a, const uint32_t* d_ev_time, const uint32_t* d_ev_ns, uint64_t n,
+                            const uint64_t* d_rec_off, const uint32_t* d_body_size, uint8_t* d_out, cudaStream_t st) {
+    if (!n)
+        return;
+    SlsParsed p{a.base, a.ev_off, a.ev_len, a.status, a.cap_off, a.cap_len, a.pitch, a.keys, a.key_at, a.nkeys,
+                a.has_fail_key};
+    sls_parsed_emit_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(p, d_ev_time, d_ev_ns, n, d_rec_off,
+                                                                             d_body_size, d_out);
+}
+
 } // namespace lck

@@ -207,4 +207,23 @@ void launch_sls_emit(const uint8_t* d_base, const uint32_t* d_ev_time, const uin
                      const uint32_t* d_voff, const uint32_t* d_vlen, uint64_t n, const uint64_t* d_rec_off,
                      const uint32_t* d_body_size, uint8_t* d_out, cudaStream_t st);
 
+// f4, device-fed: Log records from the regex stage's result tables + constant key strings (all device pointers)
+struct SlsParsedArgs {
+    const uint8_t* base;
+    const uint32_t* ev_off;
+    const uint32_t* ev_len;
+    const uint8_t* status;
+    const uint32_t* cap_off;
+    const uint32_t* cap_len;
+    uint32_t pitch;
+    const uint8_t* keys;
+    const uint32_t* key_at; // [nkeys + 2]
+    uint32_t nkeys;
+    uint32_t has_fail_key;
+};
+void launch_sls_parsed_sizes(const SlsParsedArgs& a, const uint32_t* d_ev_ns, uint64_t n, uint32_t* d_rec_size,
+                             uint32_t* d_body_size, cudaStream_t st);
+void launch_sls_parsed_emit(const SlsParsedArgs& a, const uint32_t* d_ev_time, const uint32_t* d_ev_ns, uint64_t n,
+                            const uint64_t* d_rec_off, const uint32_t* d_body_size, uint8_t* d_out, cudaStream_t st);
+
 } // namespace lck

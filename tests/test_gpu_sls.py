@@ -90,3 +90,57 @@ def test_host_serializer_matches_oracle():
             want, werr = orc.sls_serialize_group(g, ns)
             got, gerr = capi.host_sls_serialize(root, ns)
             assert got == want and (gerr is None) == (werr is None), (root, ns, gerr, werr)
+
+
+@pytest.mark.parametrize("fail_key", [None, b"rawLog"])
+def test_parsed_tables_to_wire_bytes_on_device(eng, fail_key):
+    """regex parse (device tables) -> lc_sls_serialize_parsed_dev: the wire bytes of the parsed events, written from the
+    capture tables + constant keys without any host-built span list; == the oracle's serialiser over the events the
+    oracle's ProcessorParseRegexNative leaves (10 fields per matching line; failed lines erased or kept as rawLog)."""
+    import torch
+
+    import loongcollector_b200 as lc
+    from loongcollector_b200 import synth
+    n = 30000
+    buf, off, ln = synth.nginx_lines(n, seed=9, line_bytes=None, bad_fraction=0.05)
+    rx = lc.Regex(synth.NGINX_PATTERN)
+    keys = [k.encode() for k in synth.NGINX_KEYS]
+    d_buf = torch.from_numpy(buf).cuda()
+    d_off = torch.from_numpy(off.view(np.int32)).cuda()
+    d_len = torch.from_numpy(ln.view(np.int32)).cuda()
+    d_st = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_co = torch.empty(n * 10, dtype=torch.int32, device="cuda")
+    d_cl = torch.empty(n * 10, dtype=torch.int32, device="cuda")
+    times = (1700000000 + np.arange(n)).astype(np.uint32)
+    nss = np.where(np.arange(n) % 3 == 0, 0xFFFFFFFF, np.arange(n) % 1000).astype(np.uint32)
+    d_t = torch.from_numpy(times.view(np.int32)).cuda()
+    d_ns = torch.from_numpy(nss.view(np.int32)).cuda()
+    cap = int(buf.size) * 2 + 64 * n
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    eng.regex_parse_dev(rx, d_buf.data_ptr(), buf.size, d_off.data_ptr(), d_len.data_ptr(), n, 10, d_st.data_ptr(),
+                        d_co.data_ptr(), d_cl.data_ptr())
+    got_len = eng.sls_serialize_parsed_dev(d_buf.data_ptr(), buf.size, d_off.data_ptr(), d_len.data_ptr(),
+                                           d_st.data_ptr(), d_co.data_ptr(), d_cl.data_ptr(), 10, n, keys, fail_key,
+                                           d_t.data_ptr(), d_ns.data_ptr(), d_out.data_ptr(), cap)
+    got = bytes(d_out[:got_len].cpu().numpy())
+    st, co, cl = orc.regex_parse_batch(orc.Regex(synth.NGINX_PATTERN), buf, off, ln, 10)
+    assert (st != 0).sum() > 100
+    events = []
+    for i in range(n):
+        if st[i] == 0:
+            contents = [(keys[g], bytes(buf[co[i, g]:co[i, g] + cl[i, g]])) for g in range(10)]
+        elif fail_key:
+            contents = [(fail_key, bytes(buf[off[i]:off[i] + ln[i]]))]
+        else:
+            contents = []
+        events.append((int(times[i]), None if nss[i] == 0xFFFFFFFF else int(nss[i]), contents))
+    want, _ = orc.sls_serialize_logs(events, True)
+    assert got == want
+    # capacity error reports the needed size
+    from loongcollector_b200 import capi
+    with pytest.raises(lc.LcError) as ei:
+        eng.sls_serialize_parsed_dev(d_buf.data_ptr(), buf.size, d_off.data_ptr(), d_len.data_ptr(), d_st.data_ptr(),
+                                     d_co.data_ptr(), d_cl.data_ptr(), 10, n, keys, fail_key, d_t.data_ptr(),
+                                     d_ns.data_ptr(), d_out.data_ptr(), 100)
+    assert ei.value.code == capi.LC_ERR_CAPACITY
