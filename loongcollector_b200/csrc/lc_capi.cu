@@ -87,7 +87,8 @@ struct lc_engine {
     int smem_per_sm = 0;
     bool force_basic_regex = false;   // env LC_B200_REGEX_KERNEL=basic   (tables in global memory)
     int regex_variant = 0; // env LC_B200_REGEX_KERNEL: 0 auto, 1 "fast" (stride-1), 2 "fast2" (stride-2), 3 "generic",
-                           // 4 "tdfa" (single pass, staged input), 5 "tdfa_direct" (single pass, per-lane loads)
+                           // 4 "tdfa" (single pass, staged input), 5 "tdfa_direct" (single pass, per-lane loads),
+                           // 6 "tdfa_pc" (single pass, producer warps fill the tiles)
     uint64_t scratch_hint = 0;
     int length_order = -1; // env LC_B200_LENGTH_ORDER: 1 = always order ragged batches by length, 0 = never, unset = auto
     uint32_t max_warps = 32;   // env LC_B200_MAX_WARPS (tuning knob: resident warps per block of the regex kernels)
@@ -271,7 +272,7 @@ int lc_engine_create(int device, lc_engine_t** out) {
         e->multi_split = msp && !strcmp(msp, "1");
         const char* lo = getenv("LC_B200_LENGTH_ORDER");
         e->length_order = !lo ? -1 : (!strcmp(lo, "1") ? 1 : 0);
-        e->regex_variant = !k ? 0 : (!strcmp(k, "fast") ? 1 : (!strcmp(k, "fast2") ? 2 : (!strcmp(k, "generic") ? 3 : (!strcmp(k, "tdfa") ? 4 : (!strcmp(k, "tdfa_direct") ? 5 : 0)))));
+        e->regex_variant = !k ? 0 : (!strcmp(k, "fast") ? 1 : (!strcmp(k, "fast2") ? 2 : (!strcmp(k, "generic") ? 3 : (!strcmp(k, "tdfa") ? 4 : (!strcmp(k, "tdfa_direct") ? 5 : (!strcmp(k, "tdfa_pc") ? 6 : 0))))));
     }
     CU_TRY(e->small.ensure(sizeof(Small)));
     CU_TRY(cudaMallocHost(&e->h_small, sizeof(Small)));
@@ -564,8 +565,7 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
     // ---- single-pass tagged DFA: the preferred kernel whenever the pattern's TDFA fits shared memory.  Nothing on
     // this path waits for the device: ragged-batch ordering is decided by a device-side flag and events too long for
     // the 16-bit capture registers are redone by a follow-up kernel that exits at once when there was none.
-    if (!force_basic && (e->regex_variant == 0 || e->regex_variant == 4 || e->regex_variant == 5) &&
-        !re->res.tdfa_blob.empty()) {
+    if (!force_basic && (e->regex_variant == 0 || e->regex_variant >= 4) && !re->res.tdfa_blob.empty()) {
         const LcTdfaHeader* th = reinterpret_cast<const LcTdfaHeader*>(re->res.tdfa_blob.data());
         const uint32_t tb = (uint32_t)re->res.tdfa_blob.size();
         const bool staged = e->regex_variant != 5 || ev_stride != 1;
@@ -610,7 +610,14 @@ static int regex_parse_dev_impl(lc_engine_t* e, const lc_regex_t* re, const uint
             CU_TRY(cudaMemsetAsync(&ds->overflow, 0, offsetof(Small, total_chars) - offsetof(Small, overflow),
                                    e->stream));
             int er;
-            if (staged)
+            if (staged && e->regex_variant == 6 && !d_order &&
+                lck::tdfa_pc_smem_bytes(tb, th->nregs, 1024) <= smem_max)
+                er = lck::launch_regex_tdfa_pc(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off, d_ev_len,
+                                               ev_stride, n, nkeys, d_status, bool_only ? nullptr : d_cap_off,
+                                               bool_only ? nullptr : d_cap_len, 1024,
+                                               (uint32_t)std::min<uint64_t>((n + 895) / 896, (uint64_t)e->num_sms),
+                                               &ds->next_batch, &ds->overflow, e->stream);
+            else if (staged)
                 er = lck::launch_regex_tdfa_staged(d_tblob, tb, th->has_slow != 0, th->nregs, d_base, d_ev_off,
                                                    d_ev_len, ev_stride, n, nkeys, d_status,
                                                    bool_only ? nullptr : d_cap_off, bool_only ? nullptr : d_cap_len,

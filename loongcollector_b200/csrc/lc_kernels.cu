@@ -1447,17 +1447,25 @@ struct TdfaAbs {
 // (Tried and measured slower on C2: a power-of-two row pitch with the address formed as row | index * 4 -- the same
 // class pair of different states then always shares a bank; and storing both boundary fields under one predicate --
 // two instructions fewer per pair but more shared-memory wavefronts.)
+// UNC (A/B knob LC_B200_TDFA_STORE=uncond): both boundary stores are issued unconditionally -- a pair that sets no
+// register writes the position into the thread's no-op slot (offset 0 of regs_m2: the spare halfword in front of its
+// register file) -- which drops the two predicate set-ups per pair.
 #define LCS_PAIR(X, HI, POS)                                                                                           \
     {                                                                                                                  \
         const uint32_t c0 = lds_u8(__byte_perm((X), t.cls, (HI) ? 0x7652 : 0x7650));                                   \
         const uint32_t c1 = lds_u8(__byte_perm((X), t.cls, (HI) ? 0x7653 : 0x7651));                                   \
         const uint32_t e = lds_u32(row + ((c0 * t.ncls + c1) << 2));                                                   \
         row = e & 0xFFFFu;                                                                                             \
-        const uint32_t sa = e & 0x7F0000u, sb = e >> 24;                                                               \
-        if (sa)                                                                                                        \
-            sts_u16(regs_m2 + __umulhi(sa, 0x10000u), (POS));                                                          \
-        if (sb)                                                                                                        \
-            sts_u16(regs_m2 + sb, (POS) + 1);                                                                          \
+        if (UNC) {                                                                                                     \
+            sts_u16(regs_m2 + (SLOW ? ((e >> 16) & 0x7Fu) : __byte_perm(e, 0, 0x4442)), (POS));                        \
+            sts_u16(regs_m2 + (e >> 24), (POS) + 1);                                                                   \
+        } else {                                                                                                       \
+            const uint32_t sa = e & 0x7F0000u, sb = e >> 24;                                                           \
+            if (sa)                                                                                                    \
+                sts_u16(regs_m2 + __umulhi(sa, 0x10000u), (POS));                                                      \
+            if (sb)                                                                                                    \
+                sts_u16(regs_m2 + sb, (POS) + 1);                                                                      \
+        }                                                                                                              \
     }
 
 // Out-of-line redo of one chunk whose fast pass met an entry that sets several registers in one step: single steps
@@ -1525,10 +1533,22 @@ struct TdfaLoader {
     uint32_t ld_dst;      // tile slot of (chunk ld_q, line ld_L0)
     uint32_t tile_abs;    // this warp's 4 KB tile
     uint32_t rd_lane16;   // lane << 4
+    // cooperative fetch of chunks s0..s0+7 of the warp's 32 lines: instruction r moves lines r, r+8, r+16, r+24
+    __device__ __forceinline__ void stage(uint32_t s0) {
+        const uint32_t cidx = s0 + ld_q;
+#pragma unroll
+        for (uint32_t r = 0; r < 8; ++r) {
+            const uint2 inf = lds_u64_v(ld_info + r * 8);
+            if (cidx < inf.y)
+                cp_async_16(ld_dst + ((r ^ ld_q) << 4), gbase16 + inf.x + cidx);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+    }
 };
 
-template <bool SLOW>
-__device__ __forceinline__ uint32_t tdfa_walk_lines(const LcTdfaView& v, const TdfaAbs& t, const TdfaLoader& L,
+template <bool SLOW, bool UNC, class Fetch>
+__device__ __forceinline__ uint32_t tdfa_walk_lines(const LcTdfaView& v, const TdfaAbs& t, Fetch& L,
                                                     uint32_t dead, uint32_t sink, uint32_t row, uint32_t len,
                                                     uint32_t mis, uint32_t max_nch, uint32_t regs_m2, uint16_t* rg) {
     // frame of the line: byte j of the line sits at frame index mis + j; pairs cover the even-aligned [qlo, Qe)
@@ -1539,18 +1559,7 @@ __device__ __forceinline__ uint32_t tdfa_walk_lines(const LcTdfaView& v, const T
     const bool has_tail = len && k_tail >= kf_hi && !(has_head && k_tail == 0);
     const uint32_t tile_abs = L.tile_abs, rd_lane16 = L.rd_lane16;
     for (uint32_t s0 = 0; s0 < max_nch; s0 += LCT_STAGE_CHUNKS) {
-        // ---- cooperative fetch: instruction r moves chunks s0..s0+7 of lines r, r+8, r+16, r+24
-        {
-            const uint32_t cidx = s0 + L.ld_q;
-#pragma unroll
-            for (uint32_t r = 0; r < 8; ++r) {
-                const uint2 inf = lds_u64_v(L.ld_info + r * 8);
-                if (cidx < inf.y)
-                    cp_async_16(L.ld_dst + ((r ^ L.ld_q) << 4), L.gbase16 + inf.x + cidx);
-            }
-            cp_async_wait_all();
-        }
-        __syncwarp();
+        L.stage(s0); // chunks s0..s0+7 of the warp's 32 lines are in the tile when this returns
         // ---- every lane walks its own line through the tile
         if (row != dead) {
             if (has_head && s0 == 0)
@@ -1605,7 +1614,7 @@ __device__ __forceinline__ void tdfa_stage_blob(uint8_t* g_cls, uint32_t cls_abs
         t2w[k] += t2;
 }
 
-template <bool SLOW>
+template <bool SLOW, bool UNC>
 __global__ void __launch_bounds__(1024, 1)
     regex_tdfa_staged_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, const uint8_t* __restrict__ base,
                              const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len,
@@ -1690,7 +1699,7 @@ __global__ void __launch_bounds__(1024, 1)
         const uint32_t max_nch = __reduce_max_sync(0xFFFFFFFFu, nch);
         uint32_t row = t.t2 + v.h->start * t.row_bytes;
         __syncwarp();
-        row = tdfa_walk_lines<SLOW>(v, t, L, dead, sink, row, len, mis, max_nch, regs_m2, rg);
+        row = tdfa_walk_lines<SLOW, UNC>(v, t, L, dead, sink, row, len, mis, max_nch, regs_m2, rg);
         uint32_t st = 1;
         if (valid) {
             bool ok = false;
@@ -1760,13 +1769,282 @@ int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow,
         return 0;
     const uint32_t reg_pitch = tdfa_reg_pitch(nregs);
     size_t smem = tdfa_staged_smem_bytes(blob_bytes, nregs, threads);
-    auto k = slow ? regex_tdfa_staged_kernel<true> : regex_tdfa_staged_kernel<false>;
+    static const bool unc_env = [] {
+        const char* e = getenv("LC_B200_TDFA_STORE");
+        return e && !strcmp(e, "uncond");
+    }();
+    const bool unc = unc_env && reg_pitch > nregs; // the no-op slot is the spare halfword of the neighbouring file
+    auto k = slow ? (unc ? regex_tdfa_staged_kernel<true, true> : regex_tdfa_staged_kernel<true, false>)
+                  : (unc ? regex_tdfa_staged_kernel<false, true> : regex_tdfa_staged_kernel<false, false>);
     cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (er != cudaSuccess)
         return (int)er;
     k<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, d_base, d_ev_off, d_ev_len, ev_stride, n, nkeys,
                                    d_status, d_cap_off, d_cap_len, reg_pitch, d_next_batch, d_overflow, d_order,
                                    d_order_flag);
+    return (int)cudaGetLastError();
+}
+
+// ---- producer / consumer variant of the staged kernel (A/B: LC_B200_REGEX_KERNEL=tdfa_pc) ------------------------------
+// The staged kernel's tile fill is its single largest shared-memory cost: LDGSTS writes one 16-byte wavefront per lane
+// (32 per instruction, ~500 of the ~1270 wavefronts a 32-line batch of 256-byte lines costs, l1tex 85 % busy).  Here the
+// first NP warps of the block only move data: a producer warp takes a consumer's request (stage number + the 32 lines'
+// chunk lists in the consumer's info slots), pulls the 8 x 512 bytes with LDG.128 into registers and writes them with
+// STS.128 -- 4 wavefronts per instruction in the same [chunk][line ^ chunk] layout -- then completes the consumer's
+// `full` mbarrier.  Consumers never touch global input memory and never execute staging instructions; they run the
+// automaton exactly as in the staged kernel (shared tdfa_walk_lines).  Requests travel through one word per consumer
+// and a per-producer bit mask; an idle producer naps (nanosleep) instead of spinning on issue slots.
+constexpr uint32_t kPcProducers = 4;
+constexpr uint32_t kPcExit = 0xFFFFFFFFu;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void sts_u128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+struct TdfaPcFetch {
+    uint32_t tile_abs;   // this consumer's 4 KB tile
+    uint32_t rd_lane16;  // lane << 4
+    uint32_t req_abs;    // request word of this consumer (stage number / kPcExit)
+    uint32_t* req_mask;  // request mask of the producer serving this consumer
+    uint32_t req_bit;
+    uint32_t full_bar;   // mbarrier the producer completes when the tile is filled
+    uint32_t parity;
+    __device__ __forceinline__ void stage(uint32_t s0) {
+        // (all lanes are past their reads of the tile and their writes of the info slots: the walk ends every stage with
+        // __syncwarp, and the batch set-up synchronises before the walk)
+        if ((threadIdx.x & 31) == 0) {
+            asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(req_abs), "r"(s0) : "memory");
+            __threadfence_block();
+            atomicOr(req_mask, req_bit);
+        }
+        mbar_wait(full_bar, parity);
+        parity ^= 1u;
+    }
+};
+
+template <bool SLOW, bool UNC>
+__global__ void __launch_bounds__(1024, 1)
+    regex_tdfa_pc_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, const uint8_t* __restrict__ base,
+                         const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len, uint32_t ev_stride,
+                         uint64_t n, uint32_t nkeys, uint8_t* __restrict__ status, uint32_t* __restrict__ cap_off,
+                         uint32_t* __restrict__ cap_len, uint32_t reg_pitch /* halfwords */,
+                         unsigned long long* next_batch, uint32_t* overflow) {
+    extern __shared__ uint4 smem[];
+    // carve-out: [pad][class table][blob][16 B][register files: consumers][line info: consumers x 256 B]
+    // [tiles: consumers x 4 KB][full barriers: consumers x 8 B][request words: consumers x 4 B][request masks: NP x 4 B]
+    const uint32_t s0abs = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t cls_abs = (s0abs + 255u) & ~255u;
+    uint8_t* g_cls = reinterpret_cast<uint8_t*>(smem) + (cls_abs - s0abs);
+    uint4* g_blob = reinterpret_cast<uint4*>(g_cls + 256);
+    tdfa_stage_blob(g_cls, cls_abs, blob, blob_bytes);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t NC = nwarps - kPcProducers; // consumer warps
+    uint8_t* g_regs0 = reinterpret_cast<uint8_t*>(g_blob) + blob_bytes + 16;
+    uint8_t* g_aux = g_regs0 + (size_t)NC * 32 * reg_pitch * 2;
+    const uint32_t aux_abs = (uint32_t)__cvta_generic_to_shared(g_aux);
+    const uint32_t tiles_abs = aux_abs + NC * 256;
+    const uint32_t bars_abs = tiles_abs + NC * (LCT_STAGE_CHUNKS * 512);
+    const uint32_t reqs_abs = bars_abs + NC * 8;
+    uint32_t* g_masks = reinterpret_cast<uint32_t*>(g_aux + (size_t)NC * 256 + (size_t)NC * (LCT_STAGE_CHUNKS * 512) +
+                                                    (size_t)NC * 8 + (size_t)NC * 4);
+    if (threadIdx.x < NC)
+        mbar_init(bars_abs + threadIdx.x * 8, 1);
+    if (threadIdx.x < kPcProducers)
+        g_masks[threadIdx.x] = 0;
+    __syncthreads();
+    const uint4* gbase16 = reinterpret_cast<const uint4*>((uintptr_t)base & ~(uintptr_t)15);
+
+    if (wid < kPcProducers) {
+        // ------------------------------------------------------------------------------------------------ producer
+        uint32_t live = 0;
+        for (uint32_t c = wid; c < NC; c += kPcProducers)
+            ++live;
+        const uint32_t ld_q = lane & 7, ld_L0 = (lane >> 3) * 8;
+        while (live) {
+            uint32_t mask = 0;
+            if (lane == 0)
+                mask = atomicExch(&g_masks[wid], 0u);
+            mask = __shfl_sync(0xFFFFFFFFu, mask, 0);
+            if (!mask) {
+                __nanosleep(64);
+                continue;
+            }
+            __threadfence_block();
+            while (mask) {
+                const uint32_t b = __ffs((int)mask) - 1;
+                mask &= mask - 1;
+                const uint32_t c = b * kPcProducers + wid;
+                uint32_t s0;
+                asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(s0) : "r"(reqs_abs + c * 4) : "memory");
+                if (s0 == kPcExit) {
+                    --live;
+                    continue;
+                }
+                const uint32_t ld_info = aux_abs + c * 256 + ld_L0 * 8;
+                const uint32_t ld_dst = tiles_abs + c * (LCT_STAGE_CHUNKS * 512) + (ld_q << 9) + (ld_L0 << 4);
+                const uint32_t cidx = s0 + ld_q;
+                uint4 v[8];
+#pragma unroll
+                for (uint32_t r = 0; r < 8; ++r) {
+                    const uint2 inf = lds_u64_v(ld_info + r * 8);
+                    v[r] = make_uint4(0, 0, 0, 0);
+                    if (cidx < inf.y)
+                        v[r] = __ldg(gbase16 + inf.x + cidx);
+                }
+#pragma unroll
+                for (uint32_t r = 0; r < 8; ++r) {
+                    const uint2 inf = lds_u64_v(ld_info + r * 8);
+                    if (cidx < inf.y)
+                        sts_u128(ld_dst + ((r ^ ld_q) << 4), v[r]);
+                }
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(bars_abs + c * 8);
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------------------------------------------- consumer
+    const uint32_t ci = wid - kPcProducers;
+    const LcTdfaView v = lc_tdfa_view(g_blob);
+    TdfaAbs t;
+    t.cls = cls_abs;
+    t.t2 = cls_abs + 256 + v.h->off_t2;
+    t.ncls = v.h->ncls;
+    t.row_bytes = v.h->row_bytes;
+    t.inv_row = (uint32_t)((0x100000000ull + t.row_bytes - 1) / t.row_bytes);
+    const uint32_t G = v.h->ngroups;
+    const uint32_t invG = G ? 0xFFFFFFFFu / G + 1 : 0;
+    uint16_t* wregs = reinterpret_cast<uint16_t*>(g_regs0) + (size_t)ci * 32 * reg_pitch;
+    uint16_t* regs = wregs + (size_t)lane * reg_pitch;
+    const uint32_t regs_abs = (uint32_t)__cvta_generic_to_shared(regs);
+    const uint32_t regs_m2 = regs_abs - 2;
+    const uint32_t info_abs = aux_abs + ci * 256;
+    sts_u64(info_abs + lane * 8, cls_abs, 0);
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t.cls) : "r"(info_abs + lane * 8) : "memory");
+    __syncwarp();
+    const uint32_t base_mis = (uint32_t)((uintptr_t)base & 15);
+    const bool bool_only = cap_off == nullptr;
+    const uint32_t dead = t.t2, sink = t.t2 + v.h->sink * t.row_bytes;
+    uint16_t* rg = regs;
+    TdfaPcFetch L;
+    L.tile_abs = tiles_abs + ci * (LCT_STAGE_CHUNKS * 512);
+    L.rd_lane16 = lane << 4;
+    L.req_abs = reqs_abs + ci * 4;
+    L.req_mask = &g_masks[ci % kPcProducers];
+    L.req_bit = 1u << (ci / kPcProducers);
+    L.full_bar = bars_abs + ci * 8;
+    L.parity = 0;
+    for (;;) {
+        unsigned long long batch = 0;
+        if (lane == 0)
+            batch = atomicAdd(next_batch, 32ull);
+        batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+        if (batch >= n)
+            break;
+        const bool valid = batch + lane < n;
+        const uint64_t i = batch + lane;
+        uint32_t off = 0, len = 0, mis = 0, nch = 0, g0 = 0;
+        if (valid) {
+            off = ev_off[i * ev_stride];
+            len = ev_len[i * ev_stride];
+            if (len >= 65535u) { // regex_tdfa_long_kernel redoes this event afterwards
+                atomicExch(overflow, 1u);
+                len = 0;
+            }
+            const uint64_t a = (uint64_t)base_mis + off;
+            mis = (uint32_t)(a & 15);
+            g0 = (uint32_t)(a >> 4);
+            nch = len ? (mis + len + 15) >> 4 : 0;
+            for (uint32_t k = 0; k < G; ++k)
+                reinterpret_cast<uint32_t*>(regs)[k] = 0xFFFFFFFFu;
+        }
+        sts_u64(info_abs + lane * 8, g0, nch);
+        const uint32_t max_nch = __reduce_max_sync(0xFFFFFFFFu, nch);
+        uint32_t row = t.t2 + v.h->start * t.row_bytes;
+        __syncwarp();
+        row = tdfa_walk_lines<SLOW, UNC>(v, t, L, dead, sink, row, len, mis, max_nch, regs_m2, rg);
+        uint32_t st = 1;
+        if (valid) {
+            bool ok = false;
+            const uint32_t fin = v.eof[__umulhi(row - t.t2, t.inv_row)];
+            if (fin != LC_NONE_ENTRY) {
+                lc_tdfa_run_ops(v, fin, len, rg);
+                ok = true;
+            }
+            st = ok ? (G + 1 <= nkeys ? 2 : 0) : 1;
+            status[i] = bool_only ? (ok ? 1 : 0) : (uint8_t)st;
+        }
+        if (bool_only || G == 0)
+            continue;
+        sts_u64(info_abs + lane * 8, off, st == 0 ? len : 0xFFFFFFFFu);
+        __syncwarp();
+        const uint64_t left = n - batch;
+        const uint32_t total = (uint32_t)(left < 32 ? left : 32) * G;
+        uint32_t* go = cap_off + batch * G + lane;
+        uint32_t* gl = cap_len + batch * G + lane;
+        const uint32_t wbase = regs_m2 + 2 - lane * reg_pitch * 2;
+        for (uint32_t j = lane; j < total; j += 32, go += 32, gl += 32) {
+            const uint32_t line = G == 1 ? j : __umulhi(j, invG), g = j - line * G;
+            const uint2 inf = lds_u64_v(info_abs + line * 8);
+            uint32_t o = 0, l = 0;
+            if (inf.y != 0xFFFFFFFFu) {
+                const uint32_t be = lds_u32_v(wbase + line * reg_pitch * 2 + g * 4);
+                const uint32_t b = be & 0xFFFFu, en = be >> 16;
+                if (b == LC_SLOT16_UNSET || en == LC_SLOT16_UNSET || en < b) {
+                    o = inf.x + inf.y;
+                } else {
+                    o = inf.x + b;
+                    l = en - b;
+                }
+            }
+            *go = o;
+            *gl = l;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { // tell the producer this consumer is done
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(L.req_abs), "r"(kPcExit) : "memory");
+        __threadfence_block();
+        atomicOr(L.req_mask, L.req_bit);
+    }
+}
+
+int launch_regex_tdfa_pc(const void* d_blob, uint32_t blob_bytes, bool slow, uint32_t nregs, const uint8_t* d_base,
+                         const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint32_t ev_stride, uint64_t n,
+                         uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t threads,
+                         uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow, cudaStream_t st) {
+    if (!n)
+        return 0;
+    const uint32_t reg_pitch = tdfa_reg_pitch(nregs);
+    size_t smem = tdfa_pc_smem_bytes(blob_bytes, nregs, threads);
+    static const bool unc_env = [] {
+        const char* e = getenv("LC_B200_TDFA_STORE");
+        return e && !strcmp(e, "uncond");
+    }();
+    const bool unc = unc_env && reg_pitch > nregs;
+    auto k = slow ? (unc ? regex_tdfa_pc_kernel<true, true> : regex_tdfa_pc_kernel<true, false>)
+                  : (unc ? regex_tdfa_pc_kernel<false, true> : regex_tdfa_pc_kernel<false, false>);
+    cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (er != cudaSuccess)
+        return (int)er;
+    k<<<grid, threads, smem, st>>>((const uint4*)d_blob, blob_bytes, d_base, d_ev_off, d_ev_len, ev_stride, n, nkeys,
+                                   d_status, d_cap_off, d_cap_len, reg_pitch, d_next_batch, d_overflow);
     return (int)cudaGetLastError();
 }
 
@@ -1902,7 +2180,7 @@ __global__ void __launch_bounds__(1024, 1)
             const uint32_t max_nch = __reduce_max_sync(0xFFFFFFFFu, nch_p);
             uint32_t row = act ? start_row : dead;
             __syncwarp();
-            row = tdfa_walk_lines<SLOW>(v, t, L, dead, sink, row, len, mis, max_nch, regs_m2, regs);
+            row = tdfa_walk_lines<SLOW, false>(v, t, L, dead, sink, row, len, mis, max_nch, regs_m2, regs);
             if (act) {
                 const uint32_t fin = v.eof[__umulhi(row - t.t2, t.inv_row)];
                 if (fin != LC_NONE_ENTRY) {

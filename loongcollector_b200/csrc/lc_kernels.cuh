@@ -109,6 +109,17 @@ int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow,
                              const uint32_t* d_order /* or nullptr */, const uint32_t* d_order_flag /* or nullptr */,
                              cudaStream_t st);
 
+// producer / consumer variant (A/B): the first 4 warps of the block only fill the other warps' tiles (LDG.128 + STS.128);
+// threads counts ALL warps, consumers = threads / 32 - 4
+inline size_t tdfa_pc_smem_bytes(uint32_t blob_bytes, uint32_t nregs, uint32_t threads) {
+    const size_t nc = threads / 32 - 4;
+    return 512 + (size_t)blob_bytes + 16 + nc * 32 * tdfa_reg_pitch(nregs) * 2 + nc * (256 + 4096 + 8 + 4) + 16 + 64;
+}
+int launch_regex_tdfa_pc(const void* d_blob, uint32_t blob_bytes, bool slow, uint32_t nregs, const uint8_t* d_base,
+                         const uint32_t* d_ev_off, const uint32_t* d_ev_len, uint32_t ev_stride, uint64_t n,
+                         uint32_t nkeys, uint8_t* d_status, uint32_t* d_cap_off, uint32_t* d_cap_len, uint32_t threads,
+                         uint32_t grid, unsigned long long* d_next_batch, uint32_t* d_overflow, cudaStream_t st);
+
 // several patterns in one grid: all tagged-DFA blobs co-resident in shared memory, tried per line in array order
 constexpr uint32_t LC_MULTI_MAX = 8;
 struct TdfaMultiArgs {

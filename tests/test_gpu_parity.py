@@ -309,10 +309,22 @@ def test_delim_matches_oracle(eng, sep, quote, extend, allow_short):
 
 
 # ------------------------------------------------------------------------------------------- kernel variants
-@pytest.mark.parametrize("variant", ["basic", "generic", "fast", "fast2", "tdfa", "tdfa_direct"])
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("variant", ["basic", "generic", "fast", "fast2", "tdfa", "tdfa_direct", "tdfa_pc",
+                                     "tdfa+uncond", "tdfa_pc+uncond"])
 def test_regex_kernel_variants_agree(variant, monkeypatch):
     """The baseline (tables in global memory) and generic (smem interpreter) kernels stay parity-checked too."""
     lc = _lc()
+    if variant.endswith("+uncond"):
+        # boundary stores issued unconditionally (no-op slot); read once per process, so run in a fresh interpreter
+        import subprocess
+        import sys
+        env = dict(os.environ, LC_B200_TDFA_STORE="uncond")
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
+                            "%s::test_regex_kernel_variants_agree[%s]" % (__file__, variant.split("+")[0])], env=env,
+                           capture_output=True, text=True, timeout=280, cwd=os.path.dirname(HERE))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return
     monkeypatch.setenv("LC_B200_REGEX_KERNEL", variant)
     e = lc.Engine(0)
     try:
