@@ -281,7 +281,8 @@ def oracle_plugin_lib():
 
 
 STAT_NAMES = ("groups", "in_events", "out_events", "live_contents", "checksum", "arena_bytes", "ctr_in_events",
-              "ctr_out_events", "ctr_in_bytes", "ctr_out_bytes", "ctr_process_ns", "ctr_process_ms")
+              "ctr_out_events", "ctr_in_bytes", "ctr_out_bytes", "ctr_process_ns", "ctr_process_ms", "gather_ns",
+              "engine_ns", "epilogue_ns", "spare")
 
 
 def regex_plugin_config():
@@ -440,7 +441,7 @@ class C2(Config):
         L.lc_host_use_pinned_arenas(1)
         os.environ.setdefault("LC_B200_DEVICE", str(self.dev.index))
         secs = np.zeros(reps, np.float64)
-        stats = np.zeros(12, np.uint64)
+        stats = np.zeros(16, np.uint64)
         err = ctypes.c_void_p()
         rc = L.lc_host_bench_plugin(b"processor_parse_regex_native", regex_plugin_config(), _vp(self.buf),
                                     _vp(self.off), _vp(self.ln), self.n, GROUP_BYTES, mode, reps, _vp(secs),
@@ -1130,7 +1131,7 @@ def run_ours(args):
                "api": "ProcessorInstance::Process(std::vector<PipelineEventGroup>&) of the B200-backed "
                       "ProcessorParseRegexNative, %d groups of <= %d KB (pinned SourceBuffer arenas), "
                       "LC_B200_HOST_THREADS=%s" % (stats["groups"], GROUP_BYTES // 1024,
-                                                   os.environ.get("LC_B200_HOST_THREADS", "16")),
+                                                   os.environ.get("LC_B200_HOST_THREADS", "default")),
                "per_rank_ms": gather_rank_stats([float(secs.min()) * 1e3, float(np.median(secs)) * 1e3,
                                                  float(secs.max()) * 1e3], world, dev),
                "plugin_stats": stats}

@@ -124,6 +124,16 @@ int lc_regex_parse_packed(lc_engine_t* e, const lc_regex_t* re, uint64_t nspans,
                           uint64_t packed_len, const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n,
                           uint32_t nkeys, uint8_t* status, uint32_t* cap_off, uint32_t* cap_len);
 
+/* Same, handing the spans back as they finish: on_done(ctx, first_span, span_count) is called on the calling thread, in
+ * span order, once the result rows of those spans' events have landed in status / cap_off / cap_len -- later spans are
+ * still being uploaded and parsed meanwhile, so the caller's per-event epilogue overlaps the GPU pipeline. */
+typedef void (*lc_spans_done_fn)(void* ctx, uint64_t first_span, uint64_t span_count);
+int lc_regex_parse_packed_cb(lc_engine_t* e, const lc_regex_t* re, uint64_t nspans, const uint8_t* const* span_ptr,
+                             const uint32_t* span_len, const uint32_t* span_dst, const uint64_t* span_first_ev,
+                             uint64_t packed_len, const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n,
+                             uint32_t nkeys, uint8_t* status, uint32_t* cap_off, uint32_t* cap_len,
+                             lc_spans_done_fn on_done, void* ctx);
+
 /* Same, with the event table read in place from a strided table: event i = (d_ev_off[i * ev_stride],
  * d_ev_len[i * ev_stride]).  Lets one processor's output feed the next without a gather -- e.g. column k of
  * lc_delim_parse_dev's [n][max_fields] tables (d_f_off + k, d_f_len + k, stride max_fields) is the event table of

@@ -52,10 +52,11 @@ void lc_host_use_pinned_arenas(int on);
  * untimed, before every repetition.  seconds_out[reps] = wall time of the Process calls of each repetition.
  * stats_out[12] = groups, in events, out events, live contents, content checksum (sum of key.size*131 +
  * value.size*31 + first value byte), arena bytes, then ProcessorInstance's counters: in events, out events, in
- * bytes, out bytes, process ns, process ms (summed over all repetitions).  Returns 0, or 1 + *err_out. */
+ * bytes, out bytes, process ns, process ms, then the plugin's own phase timers (gather ns, engine-call ns, epilogue ns;
+ * 0 when it has none), one spare -- all summed over the repetitions.  Returns 0, or 1 + *err_out. */
 int lc_host_bench_plugin(const char* type, const char* config_json, const uint8_t* data, const uint32_t* line_off,
                          const uint32_t* line_len, uint64_t n_lines, uint32_t group_bytes, int mode, int reps,
-                         double* seconds_out, uint64_t stats_out[12], char** err_out);
+                         double* seconds_out, uint64_t stats_out[16], char** err_out);
 
 #ifdef __cplusplus
 }

@@ -104,7 +104,7 @@ struct lc_engine {
     std::vector<uint64_t> freed_ids; // regexes freed since the last call (their blobs are released lazily)
     // copy pipeline of the host-pointer entry points
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    std::vector<cudaEvent_t> ev_h2d, ev_comp;
+    std::vector<cudaEvent_t> ev_h2d, ev_comp, ev_d2h;
 };
 
 namespace {
@@ -195,11 +195,13 @@ int ensure_copy_streams(lc_engine* e, int nchunks) {
     if (!e->s_d2h)
         CU_TRY(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
     while ((int)e->ev_h2d.size() < nchunks) {
-        cudaEvent_t a, b;
+        cudaEvent_t a, b, c;
         CU_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
         e->ev_h2d.push_back(a);
         e->ev_comp.push_back(b);
+        e->ev_d2h.push_back(c);
     }
     return LC_OK;
 }
@@ -306,6 +308,8 @@ void lc_engine_destroy(lc_engine_t* e) {
     for (cudaEvent_t ev : e->ev_h2d)
         cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->ev_comp)
+        cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_d2h)
         cudaEventDestroy(ev);
     if (e->s_h2d)
         cudaStreamDestroy(e->s_h2d);
@@ -990,6 +994,15 @@ int lc_regex_parse_packed(lc_engine_t* e, const lc_regex_t* re, uint64_t nspans,
                           const uint32_t* span_len, const uint32_t* span_dst, const uint64_t* span_first_ev,
                           uint64_t packed_len, const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n,
                           uint32_t nkeys, uint8_t* status, uint32_t* cap_off, uint32_t* cap_len) {
+    return lc_regex_parse_packed_cb(e, re, nspans, span_ptr, span_len, span_dst, span_first_ev, packed_len, ev_off, ev_len,
+                                    n, nkeys, status, cap_off, cap_len, nullptr, nullptr);
+}
+
+int lc_regex_parse_packed_cb(lc_engine_t* e, const lc_regex_t* re, uint64_t nspans, const uint8_t* const* span_ptr,
+                             const uint32_t* span_len, const uint32_t* span_dst, const uint64_t* span_first_ev,
+                             uint64_t packed_len, const uint32_t* ev_off, const uint32_t* ev_len, uint64_t n,
+                             uint32_t nkeys, uint8_t* status, uint32_t* cap_off, uint32_t* cap_len,
+                             lc_spans_done_fn on_done, void* ctx) {
     if (!e || !re || (nspans && (!span_ptr || !span_len || !span_dst || !span_first_ev)) ||
         (n && (!ev_off || !ev_len || !status)))
         return fail(LC_ERR_INVALID_ARG, "lc_regex_parse_packed: bad arguments");
@@ -1071,8 +1084,10 @@ int lc_regex_parse_packed(lc_engine_t* e, const lc_regex_t* re, uint64_t nspans,
             LC_PIPE_TRY(cudaMemcpyAsync(d_len + i0, ev_len + i0, cnt * 4, cudaMemcpyHostToDevice, e->s_h2d));
         }
         LC_PIPE_TRY(cudaEventRecord(e->ev_h2d[c], e->s_h2d));
-        if (!cnt)
+        if (!cnt) {
+            LC_PIPE_TRY(cudaEventRecord(e->ev_d2h[c], e->s_d2h));
             continue;
+        }
         LC_PIPE_TRY(cudaStreamWaitEvent(e->stream, e->ev_h2d[c], 0));
         rc = regex_parse_dev_impl(e, re, d_in, packed_len, span_bytes, d_off + i0, d_len + i0, 1, cnt, nkeys,
                                   e->out_a.as<uint8_t>() + i0, e->out_b.as<uint32_t>() + i0 * G,
@@ -1087,6 +1102,14 @@ int lc_regex_parse_packed(lc_engine_t* e, const lc_regex_t* re, uint64_t nspans,
                                         cudaMemcpyDeviceToHost, e->s_d2h));
             LC_PIPE_TRY(cudaMemcpyAsync(cap_len + i0 * G, e->out_c.as<uint32_t>() + i0 * G, cnt * G * 4,
                                         cudaMemcpyDeviceToHost, e->s_d2h));
+        }
+        LC_PIPE_TRY(cudaEventRecord(e->ev_d2h[c], e->s_d2h));
+    }
+    if (on_done) {
+        // hand the chunks back in order as their result tables land, while later chunks are still on the GPU
+        for (uint64_t c = 0; c < nchunks; ++c) {
+            LC_PIPE_TRY(cudaEventSynchronize(e->ev_d2h[c]));
+            on_done(ctx, cut[c], cut[c + 1] - cut[c]);
         }
     }
 #undef LC_PIPE_TRY

@@ -171,6 +171,19 @@ public:
     void SetContentNoCopy(const StringBuffer& key, const StringBuffer& val) {
         SetContentNoCopy(StringView(key.data, key.size), StringView(val.data, val.size));
     }
+    // LogEvent.cpp:159-163: no look-up of an existing key (the caller knows the key is not present)
+    void AppendContentNoCopy(StringView key, StringView val) {
+        ++mContentCnt;
+        mAllocatedContentSize += key.size() + val.size();
+        mContents.emplace_back(std::make_pair(key, val), true);
+    }
+    // one scan instead of HasContent + GetContent: the newest live entry with this key, or nullptr
+    const Content* FindContent(StringView key) const {
+        for (auto it = mContents.rbegin(); it != mContents.rend(); ++it)
+            if (it->second && it->first.first == key)
+                return &*it;
+        return nullptr;
+    }
     void DelContent(StringView key);
     bool Empty() const { return mContentCnt == 0; }
     size_t Size() const { return mContentCnt; }

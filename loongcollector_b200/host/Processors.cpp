@@ -3,7 +3,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <sched.h>
+
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
 
@@ -58,22 +63,29 @@ struct PinnedVec {
     }
 };
 
+} // namespace
+
 struct ThreadScratch {
     PinnedVec<uint32_t> off, len, capOff, capLen;
     PinnedVec<uint8_t> status, staging;
 };
+
+namespace {
 ThreadScratch& Scratch() {
     static thread_local ThreadScratch s;
     return s;
 }
 
-// Host threads used for the gather / epilogue of a batched Process call (env LC_B200_HOST_THREADS, default 16, at most
-// the hardware concurrency).  The reference spends this work on its process_thread_count ProcessorRunner threads.
+// Host threads used for the gather / epilogue of a batched Process call (env LC_B200_HOST_THREADS; default: the CPUs of
+// the process's affinity mask, at most 64).  The reference spends this work on its process_thread_count ProcessorRunner threads.
 unsigned HostThreads() {
     static const unsigned n = [] {
         const char* e = getenv("LC_B200_HOST_THREADS");
         unsigned hw = std::thread::hardware_concurrency();
-        unsigned want = e ? (unsigned)atoi(e) : 16u;
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0)
+            hw = (unsigned)CPU_COUNT(&set); // the CPUs this process may use (e.g. the GPU's NUMA node)
+        unsigned want = e ? (unsigned)atoi(e) : 64u;
         if (want < 1)
             want = 1;
         if (hw && want > hw)
@@ -83,23 +95,96 @@ unsigned HostThreads() {
     return n;
 }
 
+// Persistent worker pool: a batched Process call runs several short parallel regions (gather, one epilogue per engine
+// chunk), so the threads are created once per process, not per region.  One region at a time; a caller that finds the
+// pool busy (another ProcessorRunner thread inside its own batch) simply runs its region on its own thread.
+class HostPool {
+public:
+    using Fn = std::function<void(size_t, size_t, unsigned)>;
+    static HostPool& Get() {
+        static HostPool p(HostThreads());
+        return p;
+    }
+    unsigned Size() const { return mN; }
+    void Run(size_t n, size_t minPerThread, const Fn& fn) {
+        unsigned t = mN;
+        if (minPerThread && n / minPerThread < t)
+            t = (unsigned)std::max<size_t>(1, n / minPerThread);
+        std::unique_lock<std::mutex> busy(mBusy, std::try_to_lock);
+        if (t <= 1 || !busy.owns_lock()) {
+            fn(0, n, 0u);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mMu);
+            mFn = &fn;
+            mTotal = n;
+            mParts = t;
+            mPending = t - 1;
+            ++mGen;
+        }
+        mCv.notify_all();
+        fn(0, n / t, 0u);
+        std::unique_lock<std::mutex> lk(mMu);
+        mDone.wait(lk, [&] { return mPending == 0; });
+        mFn = nullptr;
+    }
+
+private:
+    explicit HostPool(unsigned n) : mN(n ? n : 1) {
+        for (unsigned k = 1; k < mN; ++k)
+            mThreads.emplace_back([this, k] { Work(k); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mMu);
+            mStop = true;
+            ++mGen;
+        }
+        mCv.notify_all();
+        for (auto& t : mThreads)
+            t.join();
+    }
+    void Work(unsigned k) {
+        uint64_t seen = 0;
+        for (;;) {
+            const Fn* fn;
+            size_t total;
+            unsigned parts;
+            {
+                std::unique_lock<std::mutex> lk(mMu);
+                mCv.wait(lk, [&] { return mGen != seen; });
+                seen = mGen;
+                if (mStop)
+                    return;
+                fn = mFn;
+                total = mTotal;
+                parts = mParts;
+            }
+            if (k < parts && fn)
+                (*fn)(total * k / parts, total * (k + 1) / parts, k);
+            if (k < parts) {
+                std::lock_guard<std::mutex> lk(mMu);
+                if (--mPending == 0)
+                    mDone.notify_one();
+            }
+        }
+    }
+    unsigned mN;
+    std::vector<std::thread> mThreads;
+    std::mutex mMu, mBusy;
+    std::condition_variable mCv, mDone;
+    const Fn* mFn = nullptr;
+    size_t mTotal = 0;
+    unsigned mParts = 0, mPending = 0;
+    uint64_t mGen = 0;
+    bool mStop = false;
+};
+
 // fn(begin, end, thread) over [0, n) in contiguous slices
 template <class Fn>
 void ParallelFor(size_t n, size_t minPerThread, Fn fn) {
-    unsigned t = HostThreads();
-    if (minPerThread && n / minPerThread < t)
-        t = (unsigned)std::max<size_t>(1, n / minPerThread);
-    if (t <= 1) {
-        fn((size_t)0, n, 0u);
-        return;
-    }
-    std::vector<std::thread> th;
-    th.reserve(t - 1);
-    for (unsigned k = 1; k < t; ++k)
-        th.emplace_back([&, k] { fn(n * k / t, n * (k + 1) / t, k); });
-    fn((size_t)0, n / t, 0u);
-    for (auto& x : th)
-        x.join();
+    HostPool::Get().Run(n, minPerThread, fn);
 }
 
 // Flattens the source values of the events to be parsed into (base, off[], len[]).  If every value lies
@@ -496,6 +581,11 @@ bool ProcessorParseRegexNative::Init(const Json::Value& config) {
     for (const auto& k : mKeys)
         if (k == mSourceKey)
             mSourceKeyOverwritten = true;
+    mKeysDistinct = true;
+    for (size_t a = 0; a < mKeys.size(); ++a)
+        for (size_t b = a + 1; b < mKeys.size(); ++b)
+            if (mKeys[a] == mKeys[b])
+                mKeysDistinct = false;
     return mCommonParserOptions.Init(config);
 }
 
@@ -503,7 +593,10 @@ std::vector<std::pair<std::string, uint64_t>> ProcessorParseRegexNative::Counter
     return {{"discarded", mDiscardedEventsTotal.GetValue()},
             {"out_failed", mOutFailedEventsTotal.GetValue()},
             {"out_key_not_found", mOutKeyNotFoundEventsTotal.GetValue()},
-            {"out_successful", mOutSuccessfulEventsTotal.GetValue()}};
+            {"out_successful", mOutSuccessfulEventsTotal.GetValue()},
+            {"b200_gather_ns", mGatherNs.GetValue()},
+            {"b200_engine_ns", mEngineNs.GetValue()},
+            {"b200_epilogue_ns", mEpilogueNs.GetValue()}};
 }
 
 void ProcessorParseRegexNative::AddCounters(const LocalCounters& c) {
@@ -519,18 +612,19 @@ void ProcessorParseRegexNative::AddCounters(const LocalCounters& c) {
 
 // ProcessEvent (:132-168) with the regex verdict already known.  r == nullptr: the event never reached the engine
 // (unsupported type, source key absent, or whole-line mode).
-bool ProcessorParseRegexNative::FinishEvent(PipelineEventGroup& group, PipelineEventPtr& e, const EventResult* r,
+bool ProcessorParseRegexNative::FinishEvent(PipelineEventGroup& group, PipelineEventPtr& e,
+                                            const LogEvent::Content* src, const EventResult* r,
                                             LocalCounters& c) const {
     if (!IsSupportedEvent(e)) {
         ++c.failed;
         return true;
     }
     LogEvent& ev = e.Cast<LogEvent>();
-    if (!ev.HasContent(mSourceKey)) {
+    if (!src) {
         ++c.keyNotFound;
         return true;
     }
-    StringView rawContent = ev.GetContent(mSourceKey);
+    StringView rawContent = src->first.second;
     bool ok = true;
     if (mIsWholeLineMode) {
         AddLog(ev, mKeys.empty() ? StringView("content") : StringView(mKeys[0]), rawContent);
@@ -539,6 +633,11 @@ bool ProcessorParseRegexNative::FinishEvent(PipelineEventGroup& group, PipelineE
         ok = false;
     } else if (r->status == LC_REGEX_KEYS_MISMATCH) {
         ok = false;
+    } else if (mKeysDistinct && !mSourceKeyOverwritten && ev.RawContents().size() == 1) {
+        // the event holds nothing but the source key and no key can collide: SetContentNoCopy's look-up per key
+        // (LogEvent.cpp:83-95) would find nothing, so the fields are appended directly (same resulting contents)
+        for (uint32_t k = 0; k < mKeys.size(); ++k)
+            ev.AppendContentNoCopy(mKeys[k], StringView(r->origin + (r->capOff[k] - r->originOff), r->capLen[k]));
     } else {
         for (uint32_t k = 0; k < mKeys.size(); ++k)
             AddLog(ev, mKeys[k], StringView(r->origin + (r->capOff[k] - r->originOff), r->capLen[k]));
@@ -555,6 +654,37 @@ bool ProcessorParseRegexNative::FinishEvent(PipelineEventGroup& group, PipelineE
     }
     ++c.successful;
     return true;
+}
+
+// the epilogue of every event of one group; the group's parsed events own rows firstEv, firstEv + 1, ... of the tables
+void ProcessorParseRegexNative::EpilogueGroup(PipelineEventGroup& group, uint64_t firstEv, const ThreadScratch& sc,
+                                              uint32_t G, LocalCounters& c) const {
+    EventsContainer& events = group.MutableEvents();
+    uint64_t i = firstEv;
+    size_t wIdx = 0;
+    for (size_t rIdx = 0; rIdx < events.size(); ++rIdx) {
+        EventResult r{};
+        const EventResult* rp = nullptr;
+        const LogEvent::Content* src = nullptr;
+        if (IsSupportedEvent(events[rIdx])) {
+            src = events[rIdx].Cast<LogEvent>().FindContent(mSourceKey);
+            if (src && !mIsWholeLineMode) {
+                r.status = sc.status.p[i];
+                r.capOff = sc.capOff.p + i * G;
+                r.capLen = sc.capLen.p + i * G;
+                r.origin = src->first.second.data(); // captures map back onto the ORIGINAL bytes, staged or not
+                r.originOff = sc.off.p[i];
+                rp = &r;
+                ++i;
+            }
+        }
+        if (FinishEvent(group, events[rIdx], src, rp, c)) {
+            if (wIdx != rIdx)
+                events[wIdx] = std::move(events[rIdx]);
+            ++wIdx;
+        }
+    }
+    events.resize(wIdx);
 }
 
 void ProcessorParseRegexNative::Process(PipelineEventGroup& group) {
@@ -598,8 +728,13 @@ void ProcessorParseRegexNative::ProcessBatch(PipelineEventGroup* groups, size_t 
         uint64_t stagedAt = 0;
     };
     std::vector<GroupPlan> plan(ngroups);
+    using Clock = std::chrono::steady_clock;
+    auto since = [](Clock::time_point t0) {
+        return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t0).count();
+    };
     try {
         uint64_t nb = 0;
+        const auto tGather = Clock::now();
         if (!mIsWholeLineMode) {
             // ---- pass 1 (parallel over groups): count the events that reach RegexLogLineParser, find each span
             ParallelFor(ngroups, 8, [&](size_t a, size_t b, unsigned) {
@@ -611,10 +746,10 @@ void ProcessorParseRegexNative::ProcessBatch(PipelineEventGroup* groups, size_t 
                     for (const auto& e : groups[g].GetEvents()) {
                         if (!IsSupportedEvent(e))
                             continue;
-                        const LogEvent& ev = e.Cast<LogEvent>();
-                        if (!ev.HasContent(mSourceKey))
+                        const LogEvent::Content* sc1 = e.Cast<LogEvent>().FindContent(mSourceKey);
+                        if (!sc1)
                             continue;
-                        StringView v = ev.GetContent(mSourceKey);
+                        StringView v = sc1->first.second;
                         if (!p.nEv || v.data() < lo)
                             lo = v.data();
                         if (!p.nEv || v.data() + v.size() > hi)
@@ -668,10 +803,10 @@ void ProcessorParseRegexNative::ProcessBatch(PipelineEventGroup* groups, size_t 
                         for (const auto& e : groups[g].GetEvents()) {
                             if (!IsSupportedEvent(e))
                                 continue;
-                            const LogEvent& ev = e.Cast<LogEvent>();
-                            if (!ev.HasContent(mSourceKey))
+                            const LogEvent::Content* sc2 = e.Cast<LogEvent>().FindContent(mSourceKey);
+                            if (!sc2)
                                 continue;
-                            StringView v = ev.GetContent(mSourceKey);
+                            StringView v = sc2->first.second;
                             if (p.staged) {
                                 if (v.size())
                                     memcpy(staging + p.stagedAt + at, v.data(), v.size());
@@ -695,53 +830,50 @@ void ProcessorParseRegexNative::ProcessBatch(PipelineEventGroup* groups, size_t 
                     spanFirst[g] = plan[g].firstEv;
                 }
                 spanFirst[ngroups] = nb;
-                Check(lc_regex_parse_packed(Engine(), mReg.get(), ngroups, spanPtr.data(), spanLen.data(),
-                                            spanDst.data(), spanFirst.data(), dst, off, len, nb,
-                                            (uint32_t)mKeys.size(), status, capOff, capLen),
+                mGatherNs.Add(since(tGather));
+                // ---- pass 3: the per-event epilogue of a range of groups (parallel over the groups)
+                const uint32_t Gc = mReg.groups();
+                std::vector<LocalCounters> local(HostThreads());
+                uint64_t epilogueNs = 0;
+                auto epilogue = [&](size_t gBegin, size_t gCount) {
+                    const auto t0 = Clock::now();
+                    ParallelFor(gCount, 4, [&](size_t a, size_t b, unsigned tid) {
+                        LocalCounters& c = local[tid];
+                        for (size_t g = gBegin + a; g < gBegin + b; ++g)
+                            EpilogueGroup(groups[g], plan[g].firstEv, sc, Gc, c);
+                    });
+                    epilogueNs += since(t0);
+                };
+                struct Ctx {
+                    decltype(epilogue)* fn;
+                } cbctx{&epilogue};
+                const auto tEngine = Clock::now();
+                Check(lc_regex_parse_packed_cb(
+                          Engine(), mReg.get(), ngroups, spanPtr.data(), spanLen.data(), spanDst.data(),
+                          spanFirst.data(), dst, off, len, nb, (uint32_t)mKeys.size(), status, capOff, capLen,
+                          [](void* ctx, uint64_t first, uint64_t count) {
+                              (*static_cast<Ctx*>(ctx)->fn)((size_t)first, (size_t)count);
+                          },
+                          &cbctx),
                       "lc_regex_parse_packed");
+                mEngineNs.Add(since(tEngine) - epilogueNs); // the call's own share (the epilogue runs inside it)
+                mEpilogueNs.Add(epilogueNs);
+                for (const auto& c : local)
+                    AddCounters(c);
+                return;
             }
         }
-        // ---- pass 3 (parallel over groups): the per-event epilogue
+        // nothing reached the engine (whole-line mode, or no event carries the source key): epilogue only
+        const auto tEpilogue = Clock::now();
         ThreadScratch& sc = Scratch();
-        const uint32_t G = mReg.groups();
         std::vector<LocalCounters> local(HostThreads());
         ParallelFor(ngroups, 8, [&](size_t a, size_t b, unsigned tid) {
-            LocalCounters& c = local[tid];
-            for (size_t g = a; g < b; ++g) {
-                EventsContainer& events = groups[g].MutableEvents();
-                const GroupPlan& p = plan[g];
-                uint64_t i = p.firstEv;
-                uint64_t at = 0;
-                size_t wIdx = 0;
-                for (size_t rIdx = 0; rIdx < events.size(); ++rIdx) {
-                    EventResult r{};
-                    const EventResult* rp = nullptr;
-                    if (!mIsWholeLineMode && IsSupportedEvent(events[rIdx])) {
-                        const LogEvent& ev = events[rIdx].Cast<LogEvent>();
-                        if (ev.HasContent(mSourceKey)) {
-                            StringView v = ev.GetContent(mSourceKey);
-                            r.status = sc.status.p[i];
-                            r.capOff = sc.capOff.p + i * G;
-                            r.capLen = sc.capLen.p + i * G;
-                            r.origin = v.data(); // captures map back onto the ORIGINAL bytes, staged or not
-                            r.originOff = sc.off.p[i];
-                            rp = &r;
-                            ++i;
-                            at += v.size();
-                        }
-                    }
-                    if (FinishEvent(groups[g], events[rIdx], rp, c)) {
-                        if (wIdx != rIdx)
-                            events[wIdx] = std::move(events[rIdx]);
-                        ++wIdx;
-                    }
-                }
-                (void)at;
-                events.resize(wIdx);
-            }
+            for (size_t g = a; g < b; ++g)
+                EpilogueGroup(groups[g], plan[g].firstEv, sc, mReg.groups(), local[tid]);
         });
         for (const auto& c : local)
             AddCounters(c);
+        mEpilogueNs.Add(since(tEpilogue));
     } catch (const std::exception& ex) {
         EngineFailed(ex.what()); // groups not yet rewritten stay untouched (the reference never throws out of Process)
     }

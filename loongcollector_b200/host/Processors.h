@@ -19,6 +19,8 @@
 
 namespace logtail {
 
+struct ThreadScratch; // pinned per-thread tables of the batched paths (Processors.cpp)
+
 // Process() runs concurrently on the same instance from every ProcessorRunner thread (ProcessorRunner.cpp:48-53):
 // counters are atomic like the reference's (monitor/metric_models/MetricTypes.h, relaxed adds).
 struct Counter {
@@ -177,12 +179,21 @@ private:
         uint64_t discarded = 0, failed = 0, keyNotFound = 0, successful = 0;
     };
     // ProcessEvent epilogue (:135-167) of one event; returns false when the event is to be erased
-    bool FinishEvent(PipelineEventGroup& group, PipelineEventPtr& e, const EventResult* r, LocalCounters& c) const;
+    bool FinishEvent(PipelineEventGroup& group, PipelineEventPtr& e, const LogEvent::Content* src, const EventResult* r,
+                     LocalCounters& c) const;
     void ProcessBatch(PipelineEventGroup* groups, size_t ngroups);
+    void EpilogueGroup(PipelineEventGroup& group, uint64_t firstEv, const struct ThreadScratch& sc, uint32_t G,
+                       LocalCounters& c) const;
     void AddCounters(const LocalCounters& c);
     bool mSourceKeyOverwritten = false;
     bool mIsWholeLineMode = false;
+    bool mKeysDistinct = false; // no key repeats: an event that holds only the source key takes the parsed fields as
+                                // plain appends (AppendContentNoCopy) instead of one look-up per key
     CompiledRegex mReg;
+
+public:
+    // wall time of the three phases of the batched path, summed over calls (ns): gather, engine call, epilogue
+    Counter mGatherNs, mEngineNs, mEpilogueNs;
 };
 
 class ProcessorParseDelimiterNative : public Processor {

@@ -198,7 +198,7 @@ void lc_host_use_pinned_arenas(int on) {
 
 int lc_host_bench_plugin(const char* type, const char* config_json, const uint8_t* data, const uint32_t* line_off,
                          const uint32_t* line_len, uint64_t n_lines, uint32_t group_bytes, int mode, int reps,
-                         double* seconds_out, uint64_t stats_out[12], char** err_out) {
+                         double* seconds_out, uint64_t stats_out[16], char** err_out) {
     if (err_out)
         *err_out = nullptr;
     try {
@@ -246,6 +246,15 @@ int lc_host_bench_plugin(const char* type, const char* config_json, const uint8_
             stats_out[9] = inst.mOutSizeBytes.GetValue();
             stats_out[10] = inst.mTotalProcessTimeNs.GetValue();
             stats_out[11] = inst.mTotalProcessTimeMs.GetValue();
+            stats_out[12] = stats_out[13] = stats_out[14] = stats_out[15] = 0;
+            for (auto& kv : inst.GetPlugin()->Counters()) { // phase breakdown of the batched path, when the plugin has one
+                if (kv.first == "b200_gather_ns")
+                    stats_out[12] = kv.second;
+                else if (kv.first == "b200_engine_ns")
+                    stats_out[13] = kv.second;
+                else if (kv.first == "b200_epilogue_ns")
+                    stats_out[14] = kv.second;
+            }
         }
         return 0;
     } catch (const std::exception& e) {
