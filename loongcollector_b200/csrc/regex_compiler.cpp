@@ -122,6 +122,7 @@ enum AssertKind : uint32_t {
     A_BOT = 1u << 2,   // \A \`
     A_EOT = 1u << 3,   // \z \'
     A_WORDB = 1u << 4, // \b
+    A_NWORDB = 1u << 5, // \B
 };
 
 enum NodeKind { N_EMPTY, N_SET, N_CAT, N_ALT, N_REP, N_GROUP, N_ASSERT };
@@ -511,6 +512,9 @@ struct Parser {
             case 'b':
                 ak = A_WORDB;
                 break;
+            case 'B':
+                ak = A_NWORDB;
+                break;
             case 'A':
             case '`':
                 ak = A_BOT;
@@ -542,7 +546,6 @@ struct Parser {
                 nodes[id].kids = items;
                 return id;
             }
-            case 'B':
             case 'Z':
             case '<':
             case '>':
@@ -1016,6 +1019,13 @@ bool asserts_hold(uint32_t mask, int pk, int nk) {
         return false;
     if (mask & A_WORDB) {
         if ((pk == K_WORD) == (nk == K_WORD))
+            return false;
+    }
+    if (mask & A_NWORDB) {
+        // perl_matcher::match_within_word (boost 1.68 perl_matcher_common.hpp): false at either edge of the buffer
+        // (position == last, or position == backstop without match_prev_avail) -- unlike Perl / PCRE, which let \B
+        // hold at an edge next to a non-word character -- else both neighbours are word characters or both are not
+        if (pk == K_EDGE || nk == K_EDGE || (pk == K_WORD) != (nk == K_WORD))
             return false;
     }
     return true;

@@ -599,7 +599,7 @@ def test_regex_assertions_inside_the_pattern(eng):
     previous byte in the state (no kernel-side context logic), values contain embedded line separators."""
     rng = random.Random(77)
     patterns = [r"(\w+)\b.(\w+)\b(.*)", r"(.*)\bat\b(.*)", r"(a+)$.^(b+)(.*)", r"(\S+)$\s^(\S+)(?:$\s^(\S+))?",
-                r"^(\w+) (\w+)$", r"(.*?)\b(\d+)\b(.*)"]
+                r"^(\w+) (\w+)$", r"(.*?)\b(\d+)\b(.*)", r"(\w+)\B(\w)(.*)", r"(.*?)a\Bb(.*)"]
     # (no \\r: boost treats \\r\\n as one separator, the PCRE2 oracle does not -- tests/test_regex_compiler_cpu.py pins that
     #  corner on the CPU tier; a trailing separator is avoided for the mid-pattern '^' corner described there)
     alpha = "ab at 12\n_-"

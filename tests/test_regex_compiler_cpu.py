@@ -49,12 +49,38 @@ def test_multiline_unit_patterns_prefix():
 
 @pytest.mark.parametrize("pattern,why", [
     (r"(a)\1", "back-reference"), (r"a(?=b)", "look-ahead"), (r"(?<=a)b", "look-behind"), (r"(a*)*", "empty"),
-    (r"a++", "possessive"), (r"(?>a)", "atomic"), (r"\Bx", "escape"),
+    (r"a++", "possessive"), (r"(?>a)", "atomic"), (r"\Zx", "escape"), (r"\<x", "escape"),
 ])
 def test_unsupported_is_reported_not_guessed(pattern, why):
     r = EmulRegex(pattern)
     assert not r.supported
     assert why in r.error
+
+
+def test_not_word_boundary_inside_the_value_agrees_with_pcre2_and_python():
+    """\\B (boost: match_within_word).  Away from the edges of the value boost, Perl, PCRE2 and Python agree: both
+    neighbours are word characters or both are not.  AT an edge boost alone says false (perl_matcher_common.hpp:
+    position == last / position == backstop), so a pattern that needs \\B there does not match here either."""
+    rng = random.Random(77)
+    pats = [r"(\w+)\B(\w)(.*)", r"(.*?)a\Bb(.*)", r"([a-z ]*) \B-(\S*)", r"(\w)\B(\w*)\b(.*)", r"x(?:\B|,)y(.*)"]
+    alpha = "ab x-,y_1 "
+    for p in pats:
+        e, o, py = EmulRegex(p), orc.Regex(p), re.compile(p.encode(), re.S | re.M)
+        assert e.supported, (p, e.error)
+        for _ in range(400):
+            v = "".join(rng.choice(alpha) for _ in range(rng.randint(0, 12))).encode()
+            got, want = e.full_match(v), o.full_match(v)
+            m = py.fullmatch(v)
+            assert (got is None) == (want is None) == (m is None), (p, v)
+            if got is not None:
+                assert got == want, (p, v)
+    # the boost-only rule at the edges of the value
+    edge = EmulRegex(r"\B-(.*)")
+    assert edge.supported and edge.full_match(b"-x") is None        # Perl / PCRE2 would match (start, next to '-')
+    assert orc.Regex(r"\B-(.*)").full_match(b"-x") is not None
+    tail = EmulRegex(r"(.*)-\B")
+    assert tail.full_match(b"x-") is None                           # Perl / PCRE2 would match (end, after '-')
+    assert EmulRegex(r"(.*)a\Bb").full_match(b"xab") is not None
 
 
 @pytest.mark.parametrize("pattern", [r"(", r"a)", r"[a", r"*a", r"a{2,1}", "a\\"])
