@@ -118,3 +118,32 @@ def test_delimiter_lines_with_far_more_columns_than_keys(treatment):
     g = orc.Group.from_json(json.loads(json.dumps(root)))
     ora.process(g)
     assert json.dumps(got, sort_keys=True) == json.dumps(g.to_json(True), sort_keys=True)
+
+
+def test_dynamic_plugins_process_groups_like_the_host_classes():
+    """The lib<name>.so dynamic plugins, driven the way DynamicCProcessorProxy drives them (init -> process -> finalize
+    through the exported processor_interface), produce exactly what the class-level processors produce."""
+    import json
+
+    import loongcollector_b200 as lc
+    from loongcollector_b200 import _build
+    from tests.test_cabi_cpu import _roundtrip
+
+    cases = [
+        ("processor_parse_regex_b200", "processor_parse_regex_native",
+         {"SourceKey": "content", "Regex": r"(\w+)\t(\w+).*", "Keys": ["k1", "k2"], "KeepingSourceWhenParseFail": True,
+          "RenamedSourceKey": "rawLog"}, ["value1\tvalue2 tail", "nomatch", "a\tb"]),
+        ("processor_parse_delimiter_b200", "processor_parse_delimiter_native",
+         {"SourceKey": "content", "Separator": ",", "Quote": "'", "Keys": ["a", "b", "c"]},
+         ["1,2,3", "x,'y,z',w", "only"]),
+        ("processor_split_string_b200", "processor_split_string_native", {}, ["l1\nl2\nl3", "single"]),
+        ("processor_split_multiline_log_string_b200", "processor_split_multiline_log_string_native",
+         {"Multiline": {"StartPattern": r"\[\d+\].*"}}, ["[1] a\n  cont\n[2] b\nnoise"]),
+    ]
+    for name, ptype, cfg, values in cases:
+        grp = {"events": [{"type": 1, "timestamp": 9, "timestampNanosecond": 0, "contents": {"content": v}}
+                          for v in values]}
+        ver, nm, got, err = _roundtrip(_build.plugin_path(name), cfg, json.loads(json.dumps(grp)))
+        assert err is None and ver == 100 and nm == name, (name, err)
+        want = lc.HostProcessor(ptype, cfg).process(json.loads(json.dumps(grp)), True)
+        assert json.dumps(got, sort_keys=True) == json.dumps(want, sort_keys=True), name
