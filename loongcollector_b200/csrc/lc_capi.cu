@@ -1594,7 +1594,10 @@ int lc_delim_parse_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len,
     cfg.extend = extend;
     cfg.allow_short = allow_short;
     cfg.max_fields = max_fields;
-    lck::launch_delim(cfg, d_base, d_ev_off, d_ev_len, n, d_status, d_nfields, d_f_off, d_f_len, d_f_dq, e->stream);
+    Small* ds = e->small.as<Small>();
+    CU_TRY(cudaMemsetAsync(&ds->next_batch, 0, sizeof ds->next_batch, e->stream));
+    lck::launch_delim(cfg, d_base, d_ev_off, d_ev_len, n, d_status, d_nfields, d_f_off, d_f_len, d_f_dq,
+                      &ds->next_batch, e->stream);
     e->launches++;
     CU_TRY(cudaGetLastError());
     return LC_OK;

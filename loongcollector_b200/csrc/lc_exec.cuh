@@ -395,16 +395,113 @@ LC_HD uint32_t lc_eq_mask16(const uint32_t w[4], uint32_t splat) {
     return m;
 }
 
+// Resumable form: the machine's registers + one call per 16-byte aligned chunk, so that a kernel can feed the chunks
+// from a staging tile in shared memory stage by stage.  All positions are offsets from the line start `v`; q* are
+// positions in the line's 16-byte aligned frame (frame index = offset + mis).
+struct LcDelimRun {
+    int state; // 0 INITIAL 1 QUOTE 2 DATA 3 DOUBLE_QUOTE
+    int dq;
+    int fs, fe;
+    uint32_t cur; // next unprocessed frame position
+};
+
+LC_HD void lc_delim_start(LcDelimRun& r, int32_t begin, uint32_t mis) {
+    r.state = 0;
+    r.dq = 0;
+    r.fs = r.fe = begin;
+    r.cur = (uint32_t)begin + mis;
+}
+
+// chunk = the 16 bytes at frame positions [q0, q0 + 16), restricted to [qb, qe).  Returns false on a parse error.
+template <class Push>
+LC_HD bool lc_delim_chunk(LcDelimRun& r, const uint32_t w[4], uint32_t q0, uint32_t qb, uint32_t qe, uint32_t sep_splat,
+                          uint32_t quote_splat, Push& push) {
+    uint32_t ms = lc_eq_mask16(w, sep_splat), mq = lc_eq_mask16(w, quote_splat);
+    uint32_t special = ms | mq;
+    if (q0 < qb)
+        special &= ~((1u << (qb - q0)) - 1u);
+    if (qe - q0 < 16)
+        special &= (1u << (qe - q0)) - 1u;
+    const uint32_t chunk_end = qe - q0 < 16 ? qe : q0 + 16;
+    for (;;) {
+        uint32_t next = chunk_end;
+        int b = -1;
+        if (special) {
+#if defined(__CUDA_ARCH__)
+            b = __ffs((int)special) - 1;
+#else
+            b = __builtin_ctz(special);
+#endif
+            special &= special - 1;
+            next = q0 + (uint32_t)b;
+        }
+        const uint32_t gap = next - r.cur; // run of ordinary bytes
+        if (gap) {
+            if (r.state == 3)
+                return false;
+            if (r.state == 0)
+                r.state = 2;
+            r.fe += (int)gap;
+        }
+        if (b < 0) {
+            r.cur = chunk_end;
+            break;
+        }
+        r.cur = next + 1;
+        if (ms >> b & 1) { // separator
+            if (r.state == 1) {
+                r.fe++;
+            } else if (r.state == 3) {
+                r.state = 0;
+                r.dq--;
+                push((uint32_t)r.fs, (uint32_t)(r.fe - r.fs), (uint32_t)r.dq);
+                r.dq = 0;
+                r.fe += 2;
+                r.fs = r.fe;
+            } else {
+                r.state = 0;
+                push((uint32_t)r.fs, (uint32_t)(r.fe - r.fs), (uint32_t)r.dq);
+                r.dq = 0;
+                r.fs = ++r.fe;
+            }
+        } else { // quote (a byte equal to both counts as the separator, as in the per-byte machine)
+            if (r.state == 0) {
+                r.state = 1;
+                r.fs++;
+            } else if (r.state == 1) {
+                r.state = 3;
+                r.dq++;
+                r.fe++;
+            } else if (r.state == 2) {
+                return false;
+            } else {
+                r.state = 1;
+                r.fe++;
+            }
+        }
+    }
+    return true;
+}
+
+// end of line: closes the last column; false = unterminated quote
+template <class Push>
+LC_HD bool lc_delim_finish(LcDelimRun& r, Push& push) {
+    if (r.state == 3)
+        r.dq--;
+    if (r.state == 1)
+        return false;
+    push((uint32_t)r.fs, (uint32_t)(r.fe - r.fs), (uint32_t)r.dq);
+    return true;
+}
+
 template <class Push>
 LC_HD bool lc_delim_fsm(const uint8_t* v, int32_t begin, int32_t end, uint8_t sep, uint8_t quote, Push& push) {
-    int state = 0; // 0 INITIAL 1 QUOTE 2 DATA 3 DOUBLE_QUOTE
-    int dq = 0;
-    int fs = begin, fe = begin;
     const uint32_t sep_splat = sep * 0x01010101u, quote_splat = quote * 0x01010101u;
     const uint32_t mis = (uint32_t)((uintptr_t)v & 15u);
     const uint8_t* abase = v - mis;
     const uint32_t qb = (uint32_t)begin + mis, qe = (uint32_t)end + mis; // range in the aligned frame
-    uint32_t cur = qb;                                                   // next unprocessed byte
+    LcDelimRun r;
+    lc_delim_start(r, begin, mis);
     for (uint32_t qc = qb >> 4; end > begin && qc <= ((qe - 1) >> 4); ++qc) {
         uint32_t w[4];
 #if defined(__CUDA_ARCH__)
@@ -413,78 +510,10 @@ LC_HD bool lc_delim_fsm(const uint8_t* v, int32_t begin, int32_t end, uint8_t se
 #else
         memcpy(w, abase + (size_t)qc * 16, 16);
 #endif
-        const uint32_t q0 = qc * 16;
-        uint32_t ms = lc_eq_mask16(w, sep_splat), mq = lc_eq_mask16(w, quote_splat);
-        uint32_t special = ms | mq;
-        if (q0 < qb)
-            special &= ~((1u << (qb - q0)) - 1u);
-        if (qe - q0 < 16)
-            special &= (1u << (qe - q0)) - 1u;
-        const uint32_t chunk_end = qe - q0 < 16 ? qe : q0 + 16;
-        for (;;) {
-            uint32_t next = chunk_end;
-            int b = -1;
-            if (special) {
-#if defined(__CUDA_ARCH__)
-                b = __ffs((int)special) - 1;
-#else
-                b = __builtin_ctz(special);
-#endif
-                special &= special - 1;
-                next = q0 + (uint32_t)b;
-            }
-            const uint32_t gap = next - cur; // run of ordinary bytes
-            if (gap) {
-                if (state == 3)
-                    return false;
-                if (state == 0)
-                    state = 2;
-                fe += (int)gap;
-            }
-            if (b < 0) {
-                cur = chunk_end;
-                break;
-            }
-            cur = next + 1;
-            if (ms >> b & 1) { // separator
-                if (state == 1) {
-                    fe++;
-                } else if (state == 3) {
-                    state = 0;
-                    dq--;
-                    push((uint32_t)fs, (uint32_t)(fe - fs), (uint32_t)dq);
-                    dq = 0;
-                    fe += 2;
-                    fs = fe;
-                } else {
-                    state = 0;
-                    push((uint32_t)fs, (uint32_t)(fe - fs), (uint32_t)dq);
-                    dq = 0;
-                    fs = ++fe;
-                }
-            } else { // quote (a byte equal to both counts as the separator, as in the per-byte machine)
-                if (state == 0) {
-                    state = 1;
-                    fs++;
-                } else if (state == 1) {
-                    state = 3;
-                    dq++;
-                    fe++;
-                } else if (state == 2) {
-                    return false;
-                } else {
-                    state = 1;
-                    fe++;
-                }
-            }
-        }
+        if (!lc_delim_chunk(r, w, qc * 16, qb, qe, sep_splat, quote_splat, push))
+            return false;
     }
-    if (state == 3)
-        dq--;
-    if (state == 1)
-        return false;
-    push((uint32_t)fs, (uint32_t)(fe - fs), (uint32_t)dq);
-    return true;
+    return lc_delim_finish(r, push);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -3181,13 +3181,207 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// ---- tiled variant for the quote FSM (the common configuration) -----------------------------------------------------
+// Same structure as the staged regex kernel: persistent warps claim 32-line batches, fetch the lines COOPERATIVELY
+// (cp.async, 4 full 128-byte segments per instruction, [chunk][line ^ chunk] tile) instead of every lane pulling its
+// own line with LDG.128 (32 different 128-byte lines per instruction), and each lane then streams its line out of the
+// tile through the resumable run-skipping FSM (lc_delim_chunk).  Only the trimmed range is fetched: the lane first looks
+// at the last 16 bytes of its line for trailing blanks / CRs (:226-238); leading blanks are skipped in the stream.
+// Field records are assembled in the per-warp row block in shared memory and leave as coalesced 128-byte stores, as
+// in delim_kernel<true>.  Shared memory per warp: 256 B line info + 4 KB tile + 3 x 32 x (max_fields | 1) words.
+__global__ void __launch_bounds__(1024, 1)
+    delim_tiled_kernel(DelimConfig cfg, const uint8_t* __restrict__ base, const uint32_t* __restrict__ ev_off,
+                       const uint32_t* __restrict__ ev_len, uint64_t n, uint8_t* __restrict__ status,
+                       uint32_t* __restrict__ nfields, uint32_t* __restrict__ f_off, uint32_t* __restrict__ f_len,
+                       uint32_t* __restrict__ f_dq, unsigned long long* next_batch) {
+    extern __shared__ uint4 smem[];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t MF = cfg.max_fields, pitch = MF | 1u;
+    const uint32_t s0abs = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t info_abs = s0abs + wid * 256;
+    const uint32_t tile_abs = s0abs + nwarps * 256 + wid * (LCT_STAGE_CHUNKS * 512);
+    uint32_t* wrows = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(smem) + (size_t)nwarps * (256 + 4096)) +
+                      (size_t)wid * 3 * 32 * pitch;
+    uint32_t* fo = wrows + lane * pitch;
+    uint32_t* fl = fo + 32 * pitch;
+    uint32_t* fd = fl + 32 * pitch;
+    const uint32_t base_mis = (uint32_t)((uintptr_t)base & 15);
+    TdfaLoader L;
+    L.gbase16 = reinterpret_cast<const uint4*>((uintptr_t)base & ~(uintptr_t)15);
+    L.ld_q = lane & 7;
+    const uint32_t ld_L0 = (lane >> 3) * 8;
+    L.ld_info = info_abs + ld_L0 * 8;
+    L.ld_dst = tile_abs + (L.ld_q << 9) + (ld_L0 << 4);
+    L.tile_abs = tile_abs;
+    L.rd_lane16 = lane << 4;
+    const uint32_t sep_splat = cfg.sep[0] * 0x01010101u, quote_splat = cfg.quote * 0x01010101u;
+    const uint32_t invMF = MF > 1 ? 0xFFFFFFFFu / MF + 1 : 0;
+    for (;;) {
+        unsigned long long batch = 0;
+        if (lane == 0)
+            batch = atomicAdd(next_batch, 32ull);
+        batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+        if (batch >= n)
+            break;
+        const bool valid = batch + lane < n;
+        const uint64_t i = batch + lane;
+        uint32_t eo = 0, mis = 0, g0 = 0, nch = 0;
+        int32_t endIdx = 0;
+        if (valid) {
+            eo = ev_off[i];
+            endIdx = (int32_t)ev_len[i];
+            const uint64_t a = (uint64_t)base_mis + eo;
+            mis = (uint32_t)(a & 15);
+            g0 = (uint32_t)(a >> 4);
+            // trailing ' ' / '\r' (:226-232): look at the chunks of the tail, last one first
+            while (endIdx > 0) {
+                const uint32_t qlast = mis + (uint32_t)endIdx - 1; // frame position of the last byte
+                const uint4 vv = __ldg(L.gbase16 + g0 + (qlast >> 4));
+                const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+                uint32_t blank = lc_eq_mask16(w, 0x20202020u) | lc_eq_mask16(w, 0x0D0D0D0Du);
+                const uint32_t hi = qlast & 15u;                         // last byte's slot in this chunk
+                const uint32_t lo = (qlast & ~15u) >= mis ? 0u : mis;    // first slot of the chunk that belongs to the line
+                uint32_t inside = ((hi == 15u) ? 0xFFFFu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                const uint32_t keep = ~blank & inside;                   // non-blank bytes of the line in this chunk
+                if (keep) {
+                    endIdx = (int32_t)((qlast & ~15u) + (31 - __clz(keep)) + 1 - mis);
+                    break;
+                }
+                endIdx = (int32_t)((qlast & ~15u) + lo) - (int32_t)mis; // the whole part was blank: go on with the chunk before
+            }
+            nch = endIdx > 0 ? (mis + (uint32_t)endIdx + 15) >> 4 : 0;
+            for (uint32_t k = 0; k < MF; ++k) {
+                fo[k] = 0;
+                fl[k] = 0;
+                fd[k] = 0;
+            }
+        }
+        sts_u64(info_abs + lane * 8, g0, nch);
+        const uint32_t max_nch = __reduce_max_sync(0xFFFFFFFFu, nch);
+        uint32_t nf = 0;
+        auto push = [&](uint32_t o, uint32_t l, uint32_t dq) {
+            if (nf < MF) {
+                fo[nf] = eo + o;
+                fl[nf] = l;
+                fd[nf] = dq;
+            }
+            ++nf;
+        };
+        bool ok = true, started = false;
+        LcDelimRun run;
+        run.state = run.dq = run.fs = run.fe = 0;
+        run.cur = 0;
+        const uint32_t qe = mis + (uint32_t)endIdx;
+        uint32_t qb = mis; // becomes the frame position of the first non-blank byte
+        const bool parse = valid && endIdx > 0;
+        __syncwarp();
+        for (uint32_t s0 = 0; s0 < max_nch; s0 += LCT_STAGE_CHUNKS) {
+            L.stage(s0);
+            if (parse && ok) {
+                const uint32_t kb = nch < s0 + LCT_STAGE_CHUNKS ? nch : s0 + LCT_STAGE_CHUNKS;
+                for (uint32_t k = s0; k < kb; ++k) {
+                    const uint32_t q = k & 7;
+                    const uint4 vv = lds_u128_v(tile_abs + (q << 9) + (L.rd_lane16 ^ (q << 4)));
+                    const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+                    const uint32_t q0 = k * 16;
+                    if (!started) {
+                        // leading ' ' (:233-238): the first byte that is not a blank starts the record
+                        uint32_t nb = ~lc_eq_mask16(w, 0x20202020u) & 0xFFFFu;
+                        if (q0 < qb)
+                            nb &= ~((1u << (qb - q0)) - 1u);
+                        if (qe - q0 < 16)
+                            nb &= (1u << (qe - q0)) - 1u;
+                        if (!nb)
+                            continue;
+                        qb = q0 + (uint32_t)(__ffs((int)nb) - 1);
+                        lc_delim_start(run, (int32_t)(qb - mis), mis);
+                        started = true;
+                        if (cfg.nkeys == 0) { // nothing to parse into: the line fails once it is known not to be blank
+                            ok = false;
+                            break;
+                        }
+                    }
+                    if (!lc_delim_chunk(run, w, q0, qb, qe, sep_splat, quote_splat, push)) {
+                        ok = false;
+                        break;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (valid) {
+            uint8_t st;
+            if (endIdx <= 0 || !started) {
+                st = 2; // empty / all-blank value (:220-224,239-242)
+            } else if (cfg.nkeys == 0) {
+                st = 1;
+                nf = 0;
+            } else {
+                if (ok)
+                    ok = lc_delim_finish(run, push);
+                if (!ok) {
+                    st = 1;
+                    nf = 0;
+                } else {
+                    uint32_t cols = nf;
+                    if (!cfg.extend && cols > cfg.nkeys)
+                        cols = cfg.nkeys + 1; // overflow columns are joined into one (:258-275)
+                    st = (cols == 0 || (!cfg.allow_short && cols < cfg.nkeys)) ? 3 : 0;
+                }
+            }
+            status[i] = st;
+            nfields[i] = (st == 2) ? 0u : nf;
+            if (st == 1 || st == 2) // rows of failed / blank lines are zero
+                for (uint32_t k = 0; k < MF; ++k) {
+                    fo[k] = 0;
+                    fl[k] = 0;
+                    fd[k] = 0;
+                }
+        }
+        __syncwarp();
+        const uint64_t left = n - batch;
+        const uint32_t total = (uint32_t)(left < 32 ? left : 32) * MF;
+        uint32_t* go = f_off + batch * MF;
+        uint32_t* gl = f_len + batch * MF;
+        uint32_t* gd = f_dq + batch * MF;
+        for (uint32_t j = lane; j < total; j += 32) {
+            const uint32_t line = MF > 1 ? __umulhi(j, invMF) : j, k = j - line * MF;
+            const uint32_t at = line * pitch + k;
+            go[j] = wrows[at];
+            gl[j] = wrows[32 * pitch + at];
+            gd[j] = wrows[64 * pitch + at];
+        }
+        __syncwarp();
+    }
+}
+
 void launch_delim(const DelimConfig& cfg, const uint8_t* d_base, const uint32_t* d_ev_off, const uint32_t* d_ev_len,
                   uint64_t n, uint8_t* d_status, uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len,
-                  uint32_t* d_f_dq, cudaStream_t st) {
+                  uint32_t* d_f_dq, unsigned long long* d_next_batch /* zeroed, or nullptr */, cudaStream_t st) {
     if (!n)
         return;
     const unsigned grid = (unsigned)((n + 127) / 128);
     static const bool direct = getenv("LC_B200_DELIM_DIRECT") != nullptr; // A/B knob
+    static const bool no_tiled = getenv("LC_B200_DELIM_NO_TILE") != nullptr; // A/B knob
+    const bool use_quote = cfg.sep_len == 1 && cfg.quote != cfg.sep[0];
+    if (!direct && !no_tiled && use_quote && d_next_batch && cfg.max_fields && cfg.max_fields <= kDelimStagedMaxFields) {
+        // persistent tiled kernel: as many warps per block as the per-warp tile + row block allow
+        int dev = 0, smem_max = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const size_t per_warp = 256 + 4096 + (size_t)3 * 32 * (cfg.max_fields | 1u) * 4;
+        uint32_t warps = (uint32_t)std::min<size_t>(32, (size_t)smem_max / per_warp);
+        if (warps >= 8) {
+            const size_t smem = per_warp * warps;
+            cudaFuncSetAttribute(delim_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const uint64_t need = (n + warps * 32 - 1) / (warps * 32);
+            const unsigned g = (unsigned)std::min<uint64_t>(need, (uint64_t)sms);
+            delim_tiled_kernel<<<g, warps * 32, smem, st>>>(cfg, d_base, d_ev_off, d_ev_len, n, d_status, d_nfields,
+                                                            d_f_off, d_f_len, d_f_dq, d_next_batch);
+            return;
+        }
+    }
     if (!direct && cfg.max_fields && cfg.max_fields <= kDelimStagedMaxFields) {
         const size_t smem = (size_t)4 * 3 * 32 * (cfg.max_fields | 1u) * sizeof(uint32_t);
         if (smem > 48 * 1024)

@@ -204,9 +204,10 @@ struct DelimConfig {
     int allow_short;
     uint32_t max_fields;
 };
+// d_next_batch: zeroed u64 batch counter of the persistent tiled kernel (quote-FSM mode); nullptr = thread-per-line
 void launch_delim(const DelimConfig& cfg, const uint8_t* d_base, const uint32_t* d_ev_off, const uint32_t* d_ev_len,
                   uint64_t n, uint8_t* d_status, uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len,
-                  uint32_t* d_f_dq, cudaStream_t st);
+                  uint32_t* d_f_dq, unsigned long long* d_next_batch, cudaStream_t st);
 
 // next row (rank 4): SLS wire format of LOG events.  ev_ns may be null; 0xFFFFFFFF = no nanosecond part.
 // rec_size[i] = bytes of event i's Log record (0 = empty event, skipped); body_size[i] = bytes inside its Logs field.

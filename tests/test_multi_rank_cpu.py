@@ -20,6 +20,8 @@ def _worker(rank, world, port, q):
     buf, off, ln = bench.make_workload(2048, bench.shard_seed(rank))
     ms_local = 10.0 * (rank + 1)  # rank 1 is the slow one
     value, ms = bench.job_throughput(buf.size, ms_local, world, "cpu")
+    stats = bench.gather_rank_stats([ms_local - 1, ms_local, ms_local + 2], world, "cpu")
+    assert stats == [[9.0, 10.0, 12.0], [19.0, 20.0, 22.0]], stats  # every rank sees every rank's min / med / max
     q.put((rank, int(buf.size), int(np.frombuffer(buf.tobytes(), np.uint8)[:4096].astype(np.uint64).sum()), value, ms))
     dist.barrier()
     dist.destroy_process_group()
