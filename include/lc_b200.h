@@ -218,6 +218,16 @@ int lc_delim_parse_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len,
                        uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* d_status,
                        uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len, uint32_t* d_f_dq);
 
+/* Same, with a column tap for processor chains (ProcessorParseDelimiterNative -> ProcessorParseRegexNative on one
+ * column, BASELINE config C4): the (offset, length) of column tap_col of every line are ALSO written to the dense
+ * tables d_tap_off / d_tap_len -- exactly the event table lc_regex_parse_dev needs for that column, so the next stage
+ * reads 8 bytes per line instead of striding through the [n][max_fields] tables (rows of failed lines are (0, 0)). */
+int lc_delim_parse_tap_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len, const uint32_t* d_ev_off,
+                           const uint32_t* d_ev_len, uint64_t n, const uint8_t* sep, uint32_t sep_len, uint8_t quote,
+                           uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* d_status,
+                           uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len, uint32_t* d_f_dq,
+                           uint32_t tap_col, uint32_t* d_tap_off, uint32_t* d_tap_len);
+
 /* ---- f4 (next row): SLSEventGroupSerializer::Serialize for LOG events
  *          (core/collection_pipeline/serializer/SLSSerializer.cpp:254-269,377-395 over the writer of
  *           core/protobuf/sls/LogGroupSerializer.cpp:33-143,232-262)

@@ -79,6 +79,7 @@ def lib():
     dl_args = [vp, vp, u64, vp, vp, u64, vp, u32, u8, u32, i32, i32, u32, vp, vp, vp, vp, vp]
     L.lc_delim_parse.argtypes = dl_args
     L.lc_delim_parse_dev.argtypes = dl_args
+    L.lc_delim_parse_tap_dev.argtypes = dl_args + [u32, vp, vp]
     L.lc_sls_serialize_logs.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, u64, C.POINTER(u64)]
     _LIB = L
     return L
@@ -351,11 +352,12 @@ class Engine:
         return n.value, ctr
 
     def delim_parse_dev(self, d_base, base_len, d_ev_off, d_ev_len, n, sep: bytes, quote, nkeys, extend, allow_short,
-                        max_fields, d_status, d_nf, d_fo, d_fl, d_fd):
+                        max_fields, d_status, d_nf, d_fo, d_fl, d_fd, tap_col=None, d_tap_off=None, d_tap_len=None):
         sp = np.frombuffer(sep, np.uint8)
-        _check(lib().lc_delim_parse_dev(self._h, _p(d_base), base_len, _p(d_ev_off), _p(d_ev_len), n, _p(sp),
-                                        len(sep), quote, nkeys, int(bool(extend)), int(bool(allow_short)), max_fields,
-                                        _p(d_status), _p(d_nf), _p(d_fo), _p(d_fl), _p(d_fd)))
+        _check(lib().lc_delim_parse_tap_dev(self._h, _p(d_base), base_len, _p(d_ev_off), _p(d_ev_len), n, _p(sp),
+                                            len(sep), quote, nkeys, int(bool(extend)), int(bool(allow_short)),
+                                            max_fields, _p(d_status), _p(d_nf), _p(d_fo), _p(d_fl), _p(d_fd),
+                                            0xFFFFFFFF if tap_col is None else tap_col, _p(d_tap_off), _p(d_tap_len)))
 
 
 class HostProcessor:

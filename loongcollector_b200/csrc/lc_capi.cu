@@ -219,6 +219,23 @@ int check_events(const uint32_t* off, const uint32_t* len, uint64_t n, uint64_t 
     return LC_OK;
 }
 
+// first-byte filter + empty-line verdict of pattern slot p for the fused split + probe pass (prefix DFA of the blob)
+void fill_probe_slot(lck::MlConfig& cfg, int p, const lc_regex* r) {
+    memset(cfg.first[p], 0, sizeof cfg.first[p]);
+    if (!r)
+        return;
+    const uint8_t* b = r->res.blob.data();
+    const LcRegexHeader* h = reinterpret_cast<const LcRegexHeader*>(b);
+    const uint8_t* cls = b + h->off_byte_class;
+    const uint16_t* pre_next = reinterpret_cast<const uint16_t*>(b + h->off_pre_next);
+    const uint8_t* pre_acc = b + h->off_pre_acc;
+    for (uint32_t c = 0; c < 256; ++c)
+        if (pre_next[h->pre_start * h->nclasses + cls[c]] != LC_PREFIX_DEAD)
+            cfg.first[p][c >> 5] |= 1u << (c & 31);
+    if (pre_acc[h->pre_start])
+        cfg.empty_flags |= 1u << p;
+}
+
 int check_regex_usable(const lc_regex* r, const char* what) {
     if (!r->res.supported)
         return fail(r->res.valid ? LC_ERR_REGEX_UNSUPPORTED : LC_ERR_REGEX_INVALID,
@@ -1343,10 +1360,14 @@ int lc_multiline_split_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, c
     if (rc)
         return rc;
     lck::MlConfig cfg;
+    memset(&cfg, 0, sizeof cfg);
     CU_TRY(engine_blob(e, start, &cfg.blob_start));
     CU_TRY(engine_blob(e, cont, &cfg.blob_cont));
     CU_TRY(engine_blob(e, end, &cfg.blob_end));
     cfg.discard = discard_unmatched;
+    fill_probe_slot(cfg, 0, start);
+    fill_probe_slot(cfg, 1, cont);
+    fill_probe_slot(cfg, 2, end);
 
     Small* ds = e->small.as<Small>();
     Small* hs = (Small*)e->h_small;
@@ -1515,10 +1536,13 @@ int lc_remove_last_incomplete_log_dev(lc_engine_t* e, const uint8_t* d_buf, uint
     if (rc)
         return rc;
     lck::MlConfig cfg;
+    memset(&cfg, 0, sizeof cfg);
     CU_TRY(engine_blob(e, start, &cfg.blob_start));
     cfg.blob_cont = nullptr;
     CU_TRY(engine_blob(e, end, &cfg.blob_end));
     cfg.discard = 0;
+    fill_probe_slot(cfg, 0, start);
+    fill_probe_slot(cfg, 2, end);
     Small* ds = e->small.as<Small>();
     Small* hs = (Small*)e->h_small;
     const uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
@@ -1576,7 +1600,18 @@ int lc_delim_parse_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len,
                        const uint32_t* d_ev_len, uint64_t n, const uint8_t* sep, uint32_t sep_len, uint8_t quote,
                        uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* d_status,
                        uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len, uint32_t* d_f_dq) {
-    if (!e || !sep || sep_len < 1 || sep_len > 4 || max_fields == 0)
+    return lc_delim_parse_tap_dev(e, d_base, base_len, d_ev_off, d_ev_len, n, sep, sep_len, quote, nkeys, extend,
+                                  allow_short, max_fields, d_status, d_nfields, d_f_off, d_f_len, d_f_dq, 0xFFFFFFFFu,
+                                  nullptr, nullptr);
+}
+
+int lc_delim_parse_tap_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len, const uint32_t* d_ev_off,
+                           const uint32_t* d_ev_len, uint64_t n, const uint8_t* sep, uint32_t sep_len, uint8_t quote,
+                           uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* d_status,
+                           uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len, uint32_t* d_f_dq,
+                           uint32_t tap_col, uint32_t* d_tap_off, uint32_t* d_tap_len) {
+    if (!e || !sep || sep_len < 1 || sep_len > 4 || max_fields == 0 || ((d_tap_off == nullptr) != (d_tap_len == nullptr)) ||
+        (d_tap_off && tap_col >= max_fields))
         return fail(LC_ERR_INVALID_ARG, "lc_delim_parse_dev: bad arguments (separator must be 1..4 bytes)");
     if (n == 0)
         return LC_OK;
@@ -1594,6 +1629,9 @@ int lc_delim_parse_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_len,
     cfg.extend = extend;
     cfg.allow_short = allow_short;
     cfg.max_fields = max_fields;
+    cfg.tap_col = tap_col;
+    cfg.tap_off = d_tap_off;
+    cfg.tap_len = d_tap_len;
     Small* ds = e->small.as<Small>();
     CU_TRY(cudaMemsetAsync(&ds->next_batch, 0, sizeof ds->next_batch, e->stream));
     lck::launch_delim(cfg, d_base, d_ev_off, d_ev_len, n, d_status, d_nfields, d_f_off, d_f_len, d_f_dq,

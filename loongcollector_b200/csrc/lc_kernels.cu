@@ -13,6 +13,8 @@
 //   delimiter  core/plugin/processor/ProcessorParseDelimiterNative.cpp:219-409, core/parser/DelimiterModeFsmParser.cpp:49-294
 #include "lc_kernels.cuh"
 
+#include <string.h>
+
 #include <algorithm>
 
 #include "lc_exec.cuh"
@@ -42,81 +44,155 @@ __device__ __forceinline__ uint32_t match16(uint4 v, uint32_t splat) {
 // predecessors, and that walk gets longer with the number of tiles in flight (measured on C1: 16 KiB tiles 1.64,
 // 32 KiB 1.73, 64 KiB 1.87 TB/s; 128 KiB = 2 segments per thread 1.75 TB/s, the 57 registers leave one block per
 // SM; one tile per WARP, no barrier at all, 1.15 TB/s).
-// PROBE (multiline, a2): the owner of a line's terminating newline also evaluates the anchored prefix probes of the
-// start / continue / end patterns on the line's head (regex_search + match_continuous, StringTools.cpp:263-288) and
-// writes one flag byte per line -- the line's first bytes were fetched by this pass a moment ago (same tile or the one
-// before: L1 / L2 hits), so the separate probe pass that re-read the first sector of every line is gone.
+// PROBE (multiline, a2): the anchored prefix probes of the start / continue / end patterns (regex_search +
+// match_continuous, StringTools.cpp:263-288) are evaluated by the same pass that finds the lines -- a line's first bytes
+// were fetched a moment ago (same tile or the one before: L1 / L2 hits), so the separate probe pass that re-read the
+// first sector of every line is gone.  A line's owner (the thread that holds its terminating newline) only applies a
+// first-byte filter: most lines cannot start a match of any pattern and get flags = 0 at once.  Candidates go to a
+// queue in shared memory and are probed DENSELY, one thread per queued line, after the tile's lines are written --
+// otherwise a warp in which a single lane owns a 35-step start line would idle its other 31 lanes for 35 steps.
 struct SplitProbe {
-    const void* bs; // device blobs of the start / continue / end patterns (nullptr = not configured)
-    const void* bc;
-    const void* be;
-    uint8_t* flags; // [line] bit0/1/2 = start / continue / end matches a prefix
+    const void* blob[3];   // device blobs of the start / continue / end patterns (nullptr = not configured)
+    uint32_t first[3][8];  // per pattern: bit b set <=> a line whose first byte is b can match (prefix DFA, host-built)
+    uint32_t empty_flags;  // flags of an empty line (patterns that match the empty prefix)
+    uint8_t* flags;        // [line] bit0/1/2 = start / continue / end matches a prefix
 };
+constexpr uint32_t kProbeQueue = 4096;
 
 __device__ __forceinline__ uint8_t probe_line(const SplitProbe& pr, const uint8_t* __restrict__ s, uint32_t l) {
     uint8_t f = 0;
-    if (pr.bs && lc_prefix_match(lc_view(pr.bs), s, l))
-        f |= 1;
-    if (pr.bc && lc_prefix_match(lc_view(pr.bc), s, l))
-        f |= 2;
-    if (pr.be && lc_prefix_match(lc_view(pr.be), s, l))
-        f |= 4;
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        if (pr.blob[p] && lc_prefix_match(lc_view(pr.blob[p]), s, l))
+            f |= (uint8_t)(1u << p);
     return f;
 }
+// which patterns may match a non-empty line whose first byte is b
+__device__ __forceinline__ uint32_t probe_first(const SplitProbe& pr, uint32_t b) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        m |= ((pr.first[p][b >> 5] >> (b & 31)) & 1u) << p;
+    return m;
+}
 
-template <int THREADS, int SEGS, int LBW, bool PROBE>
-__global__ void __launch_bounds__(THREADS, (THREADS == 1024 && SEGS == 1) ? 2 : 1)
+// bit 7 of every byte of w that equals the splat byte (exact, no cross-byte borrows)
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t splat) {
+    const uint32_t x = w ^ splat;
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+// 16 input bytes -> 16-bit mask of the bytes equal to the splat byte
+__device__ __forceinline__ uint32_t match16b(uint4 v, uint32_t splat) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) // bits 7 / 15 / 23 / 31 -> one nibble (the partial products never collide)
+        m |= ((((eq_bytes(w[k], splat) >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * k);
+    return m;
+}
+
+// Each thread owns 64 contiguous bytes (4 x 16-byte chunks, one 64-bit newline mask): ONE block scan and ONE look-back
+// per 64 KiB tile.  The pass is bound by instruction issue and barrier waits, not by HBM (ncu: dram 25 %, issue 42 %,
+// 20 stall cycles per issue at barriers), so the code is kept lean: byte compares without the emulated SIMD-video
+// instructions, range checks only in the last tile, a 32-bit shuffle scan for the counts, and the "start of my first
+// line" taken from the nearest previous thread that holds a newline (ballot + one shuffle) instead of a max-scan.
+template <int THREADS, int LBW, bool PROBE>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 2 : 1)
     split_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
                  uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap, volatile uint64_t* desc,
                  uint32_t* ticket, uint32_t ntiles, uint32_t* n_out, unsigned long long* total_chars, SplitProbe pr) {
-    constexpr int ROWS = 4 * SEGS;
-    __shared__ uint64_t s_scan[THREADS / 32 + 1];
-    __shared__ uint32_t s_tile;
+    constexpr int NW = THREADS / 32;
+    __shared__ uint32_t s_cnt[NW];   // per warp: newline count, then its exclusive prefix inside the tile
+    __shared__ uint32_t s_last[NW];  // per warp: end (offset + 1) of its last newline, 0 = none
+    __shared__ uint32_t s_start[NW]; // per warp: start of the line that is open when the warp's bytes begin (0 = none in tile)
+    __shared__ uint32_t s_tile, s_tot, s_tlast;
     __shared__ uint64_t s_prefix;
     __shared__ uint64_t s_part[LBW > 1 ? LBW : 1];
     __shared__ uint32_t s_flag[LBW > 1 ? LBW : 1];
-    const int tid = threadIdx.x;
-    if (tid == 0)
+    __shared__ uint32_t s_qn;
+    __shared__ uint32_t s_q[PROBE ? kProbeQueue : 1];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
         s_tile = atomicAdd(ticket, 1u);
+        s_qn = 0;
+    }
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint4* vbuf = reinterpret_cast<const uint4*>(buf - shift);
     const uint64_t total_v = (uint64_t)len + shift; // virtual length including the alignment lead-in
-    const uint64_t chunk0 = ((uint64_t)tile * THREADS + tid) * ROWS;
+    const uint64_t chunk0 = ((uint64_t)tile * THREADS + tid) * 4;
     const uint64_t vpos0 = chunk0 * 16;
+    const bool full = ((uint64_t)(tile + 1) * THREADS * 64 <= total_v) && !(tile == 0 && shift);
 
-    uint4 v[ROWS];
+    uint64_t mk = 0;
+    if (full) {
+        uint4 v[4];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        v[r] = make_uint4(0, 0, 0, 0);
-        if (vpos0 + (uint64_t)r * 16 < total_v)
+        for (int r = 0; r < 4; ++r)
             v[r] = __ldg(vbuf + chunk0 + r);
-    }
-    uint64_t mask[SEGS];
-    uint64_t pay = OpCountMax::identity();
 #pragma unroll
-    for (int sg = 0; sg < SEGS; ++sg) {
-        uint64_t mk = 0;
+        for (int r = 0; r < 4; ++r)
+            mk |= (uint64_t)match16b(v[r], splat) << (16 * r);
+    } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const uint64_t vpos = vpos0 + (uint64_t)(sg * 4 + r) * 16;
-            uint32_t m = 0;
+            const uint64_t vpos = vpos0 + (uint64_t)r * 16;
             if (vpos < total_v) {
-                m = match16(v[sg * 4 + r], splat);
+                uint32_t m = match16b(__ldg(vbuf + chunk0 + r), splat);
                 if (vpos == 0 && shift) // alignment lead-in bytes in front of the buffer (shift < 16)
                     m &= ~((1u << shift) - 1u);
                 const uint64_t rem = total_v - vpos;
                 if (rem < 16)
                     m &= (1u << rem) - 1u;
+                mk |= (uint64_t)m << (16 * r);
             }
-            mk |= (uint64_t)m << (16 * r);
         }
-        mask[sg] = mk;
-        const uint32_t last = mk ? (uint32_t)(vpos0 + sg * 64 + (63 - __clzll((long long)mk)) + 1 - shift) : 0u;
-        pay = OpCountMax::combine(pay, OpCountMax::make(__popcll(mk), last));
     }
-    uint64_t tot;
-    const uint64_t excl = block_exclusive_scan<OpCountMax, THREADS>(pay, tot, s_scan);
+    const uint32_t cnt = __popcll(mk);
+    const uint32_t last = mk ? (uint32_t)(vpos0 + (63 - __clzll((long long)mk)) + 1 - shift) : 0u;
+    // ---- counts: inclusive warp scan; starts: nearest previous holder of a newline
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d)
+            inc += t;
+    }
+    const uint32_t has = __ballot_sync(0xFFFFFFFFu, mk != 0);
+    const uint32_t below = has & ((1u << lane) - 1u);
+    const uint32_t prev_last = __shfl_sync(0xFFFFFFFFu, last, below ? 31 - __clz(below) : 0);
+    const uint32_t warp_last = __shfl_sync(0xFFFFFFFFu, last, has ? 31 - __clz(has) : 0);
+    if (lane == 31) {
+        s_cnt[wid] = inc;
+        s_last[wid] = has ? warp_last : 0u;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t c = lane < NW ? s_cnt[lane] : 0u;
+        const uint32_t wl = lane < NW ? s_last[lane] : 0u;
+        uint32_t ci = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ci, d);
+            if (lane >= d)
+                ci += t;
+        }
+        const uint32_t whas = __ballot_sync(0xFFFFFFFFu, c != 0);
+        const uint32_t wbelow = whas & ((1u << lane) - 1u);
+        const uint32_t st = __shfl_sync(0xFFFFFFFFu, wl, wbelow ? 31 - __clz(wbelow) : 0);
+        const uint32_t tl = __shfl_sync(0xFFFFFFFFu, wl, whas ? 31 - __clz(whas) : 0);
+        if (lane < NW) {
+            s_cnt[lane] = ci - c; // exclusive prefix of the warp inside the tile
+            s_start[lane] = wbelow ? st : 0u;
+        }
+        const uint32_t totv = __shfl_sync(0xFFFFFFFFu, ci, NW - 1);
+        if (lane == 0) {
+            s_tot = totv;
+            s_tlast = whas ? tl : 0u;
+        }
+    }
+    __syncthreads();
+    const uint64_t tot = OpCountMax::make(s_tot, s_tlast);
     uint64_t tile_prefix;
     if (LBW > 1) {
         tile_prefix = lookback_block<OpCountMax, LBW>(desc, tile, tot, s_part, s_flag);
@@ -129,27 +205,33 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 1024 && SEGS == 1) ? 2 : 
         __syncthreads();
         tile_prefix = s_prefix;
     }
-    if (tid == 0 && OpCountMax::count(tot)) // un-truncated count (the payload keeps 30 bits): > 2^30 pieces is an error
-        atomicAdd(total_chars, (unsigned long long)OpCountMax::count(tot));
-    const uint64_t pre = OpCountMax::combine(tile_prefix, excl);
-    uint32_t k = OpCountMax::count(pre);
-    uint32_t start = OpCountMax::maxv(pre);
-#pragma unroll
-    for (int sg = 0; sg < SEGS; ++sg) {
-        uint64_t mk = mask[sg];
-        while (mk) {
-            const int b = __ffsll((long long)mk) - 1;
-            mk &= mk - 1;
-            const uint32_t p = (uint32_t)(vpos0 + sg * 64 + b - shift);
-            if (k < cap) {
-                out_off[k] = start;
-                out_len[k] = p - start;
-                if (PROBE)
-                    pr.flags[k] = probe_line(pr, buf + start, p - start);
+    if (tid == 0 && s_tot) // un-truncated count (the payload keeps 30 bits): > 2^30 pieces is an error
+        atomicAdd(total_chars, (unsigned long long)s_tot);
+    uint32_t k = (OpCountMax::count(tile_prefix) + s_cnt[wid] + (inc - cnt)) & 0x3FFFFFFFu;
+    uint32_t start = below ? prev_last : (s_start[wid] ? s_start[wid] : OpCountMax::maxv(tile_prefix));
+    while (mk) {
+        const int b = __ffsll((long long)mk) - 1;
+        mk &= mk - 1;
+        const uint32_t p = (uint32_t)(vpos0 + b - shift);
+        if (k < cap) {
+            out_off[k] = start;
+            out_len[k] = p - start;
+            if (PROBE) {
+                const uint32_t ll = p - start;
+                const uint32_t cand = ll ? probe_first(pr, buf[start]) : 0u;
+                if (!cand) {
+                    pr.flags[k] = ll ? 0 : (uint8_t)pr.empty_flags;
+                } else {
+                    const uint32_t q = atomicAdd(&s_qn, 1u);
+                    if (q < kProbeQueue)
+                        s_q[q] = k;
+                    else
+                        pr.flags[k] = probe_line(pr, buf + start, ll); // queue full: probe in place
+                }
             }
-            ++k;
-            start = p + 1;
         }
+        ++k;
+        start = p + 1;
     }
     if (tile == ntiles - 1 && tid == THREADS - 1) {
         // inclusive total of the whole buffer: the unterminated last piece, if any
@@ -164,13 +246,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 1024 && SEGS == 1) ? 2 : 
         }
         *n_out = k;
     }
+    if (PROBE) {
+        __syncthreads(); // the queue is complete and this tile's line table entries are visible to the block
+        const uint32_t qn = min(s_qn, kProbeQueue);
+        for (uint32_t q = tid; q < qn; q += THREADS) {
+            const uint32_t kk = s_q[q];
+            pr.flags[kk] = probe_line(pr, buf + out_off[kk], out_len[kk]);
+        }
+    }
 }
 
 static int split_lookback_warps() {
     static const int w = [] {
-        const char* e = getenv("LC_B200_LOOKBACK_WARPS"); // A/B knob: 1 = single-warp walk, 4 (default) = block-wide
-        int t = e ? atoi(e) : 4;
-        return t == 1 ? 1 : 4;
+        const char* e = getenv("LC_B200_LOOKBACK_WARPS"); // A/B knob: 1 (default) = single-warp walk, 4 = block-wide
+        int t = e ? atoi(e) : 1;                          // (measured on C1: 4 is 4 % slower -- two more barriers per round)
+        return t == 4 ? 4 : 1;
     }();
     return w;
 }
@@ -182,32 +272,27 @@ static void launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_
     uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
     uint32_t splat = split_char * 0x01010101u;
     static const int cfg = [] {
-        const char* e = getenv("LC_B200_SPLIT_TILE_KB"); // A/B knob: 16, 64 or 128 (descriptors are sized for 16)
+        const char* e = getenv("LC_B200_SPLIT_TILE_KB"); // A/B knob: 16 or 64 (descriptors are sized for 16)
         int t = e ? atoi(e) : 64;
-        return (t == 16 || t == 128) ? t : 64;
+        return t == 16 ? 16 : 64;
     }();
     const uint64_t tile_bytes = (uint64_t)cfg * 1024;
     uint32_t ntiles = (uint32_t)((len + shift + tile_bytes - 1) / tile_bytes);
     volatile uint64_t* desc = (volatile uint64_t*)d_desc;
     const bool wide = split_lookback_warps() > 1;
-#define LC_SPLIT_LAUNCH(T, S, W)                                                                                       \
-    split_kernel<T, S, W, PROBE><<<ntiles, T, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap, desc, d_ticket,    \
-                                                       ntiles, d_n_out, d_total, pr)
-    if (cfg == 128) {
+#define LC_SPLIT_LAUNCH(T, W)                                                                                          \
+    split_kernel<T, W, PROBE><<<ntiles, T, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap, desc, d_ticket, ntiles, \
+                                                    d_n_out, d_total, pr)
+    if (cfg == 64) {
         if (wide)
-            LC_SPLIT_LAUNCH(1024, 2, 4);
+            LC_SPLIT_LAUNCH(1024, 4);
         else
-            LC_SPLIT_LAUNCH(1024, 2, 1);
-    } else if (cfg == 64) {
-        if (wide)
-            LC_SPLIT_LAUNCH(1024, 1, 4);
-        else
-            LC_SPLIT_LAUNCH(1024, 1, 1);
+            LC_SPLIT_LAUNCH(1024, 1);
     } else {
         if (wide)
-            LC_SPLIT_LAUNCH(256, 1, 4);
+            LC_SPLIT_LAUNCH(256, 4);
         else
-            LC_SPLIT_LAUNCH(256, 1, 1);
+            LC_SPLIT_LAUNCH(256, 1);
     }
 #undef LC_SPLIT_LAUNCH
 }
@@ -215,14 +300,23 @@ static void launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_
 void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
                   uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
                   unsigned long long* d_total, cudaStream_t st) {
-    SplitProbe pr{nullptr, nullptr, nullptr, nullptr};
+    SplitProbe pr;
+    memset(&pr, 0, sizeof pr);
     launch_split_impl<false>(d_buf, len, split_char, d_off, d_len, cap, d_desc, d_ticket, d_n_out, d_total, pr, st);
 }
 
 void launch_split_probe(const MlConfig& cfg, const uint8_t* d_buf, uint32_t len, uint32_t* d_off, uint32_t* d_len,
                         uint8_t* d_flags, uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
                         unsigned long long* d_total, cudaStream_t st) {
-    SplitProbe pr{cfg.blob_start, cfg.blob_cont, cfg.blob_end, d_flags};
+    SplitProbe pr;
+    memset(&pr, 0, sizeof pr);
+    pr.blob[0] = cfg.blob_start;
+    pr.blob[1] = cfg.blob_cont;
+    pr.blob[2] = cfg.blob_end;
+    for (int p = 0; p < 3; ++p)
+        memcpy(pr.first[p], cfg.first[p], sizeof pr.first[p]);
+    pr.empty_flags = cfg.empty_flags;
+    pr.flags = d_flags;
     launch_split_impl<true>(d_buf, len, '\n', d_off, d_len, cap, d_desc, d_ticket, d_n_out, d_total, pr, st);
 }
 
@@ -2816,8 +2910,17 @@ void launch_ml_emit(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t*
 // memory (the split kernel's counter), so the launch follows the split without a host round trip: the grid covers
 // the line CAPACITY and surplus tiles return at once.  Elements 0..n-1 are lines, element n is the virtual
 // end-of-buffer.
-constexpr int kMlFusedThreads = 512;
-constexpr int kMlFusedItems = 4;
+constexpr int kMlFusedThreads = 256;
+constexpr int kMlFusedItems = 16; // lines per thread: 4096-line tiles, two look-backs per tile
+
+__device__ __forceinline__ uint64_t ml_element(const MlMode& m, uint32_t fl, uint64_t j) {
+    uint32_t o0, b0, o1, b1;
+    ml_trans(m, fl, 0, o0, b0);
+    ml_trans(m, fl, 1, o1, b1);
+    const uint32_t l0 = b0 ? (uint32_t)j + b0 : 0u; // (index + 1) of the opening line
+    const uint32_t l1 = b1 ? (uint32_t)j + b1 : 0u;
+    return OpMlState::make(o0, o1, l0, l1);
+}
 
 template <int THREADS, int ITEMS>
 __global__ void __launch_bounds__(THREADS)
@@ -2826,6 +2929,7 @@ __global__ void __launch_bounds__(THREADS)
                     uint32_t total_len, uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len,
                     uint8_t* __restrict__ out_flags, uint64_t cap, volatile uint64_t* desc_state,
                     volatile uint64_t* desc_sum, uint32_t* ticket, unsigned long long* counters, uint64_t* total_out) {
+    static_assert(ITEMS == 16, "one 16-byte load of flags per thread");
     __shared__ uint64_t s_scan[THREADS / 32 + 1];
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_part[4];
@@ -2839,66 +2943,71 @@ __global__ void __launch_bounds__(THREADS)
     if ((uint64_t)tile * THREADS * ITEMS > n)
         return;
     const uint64_t base = (uint64_t)tile * THREADS * ITEMS + (uint64_t)tid * ITEMS;
-    uint64_t el[ITEMS];
-    uint32_t fl[ITEMS];
-    uint64_t agg = OpMlState::identity();
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const uint64_t j = base + k;
-        uint64_t e = OpMlState::identity();
-        fl[k] = 0;
-        if (j < n) {
-            fl[k] = flags[j];
-            uint32_t o0, b0, o1, b1;
-            ml_trans(m, fl[k], 0, o0, b0);
-            ml_trans(m, fl[k], 1, o1, b1);
-            const uint32_t l0 = b0 ? (uint32_t)j + b0 : 0u; // (index + 1) of the opening line
-            const uint32_t l1 = b1 ? (uint32_t)j + b1 : 0u;
-            e = OpMlState::make(o0, o1, l0, l1);
-        }
-        el[k] = e;
-        agg = OpMlState::combine(agg, e);
+    // the thread's 16 flag bytes (per-line state, counts and slots are recomputed from them in every pass instead of
+    // being kept in 16-entry register arrays)
+    uint32_t fw[4] = {0, 0, 0, 0};
+    if (base + ITEMS <= n) {
+        const uint4 f4 = *reinterpret_cast<const uint4*>(flags + base);
+        fw[0] = f4.x, fw[1] = f4.y, fw[2] = f4.z, fw[3] = f4.w;
+    } else {
+        for (int k = 0; k < ITEMS; ++k)
+            if (base + k < n)
+                fw[k >> 2] |= (uint32_t)flags[base + k] << (8 * (k & 3));
     }
+    auto flag_of = [&](int k) { return (fw[k >> 2] >> (8 * (k & 3))) & 0xFFu; };
+    // ---- pass 1: compose the 2-state transition functions of the thread's lines
+    uint64_t agg = OpMlState::identity();
+#pragma unroll 4
+    for (int k = 0; k < ITEMS; ++k)
+        if (base + k < n)
+            agg = OpMlState::combine(agg, ml_element(m, flag_of(k), base + k));
     uint64_t tot;
     const uint64_t ex = block_exclusive_scan<OpMlState, THREADS>(agg, tot, s_scan);
     const uint64_t pre = lookback_block<OpMlState, 4>(desc_state, tile, tot, s_part, s_flag);
-    uint64_t run = OpMlState::combine(pre, ex);
+    const uint64_t run0 = OpMlState::combine(pre, ex);
     // initial condition (:165-169): End-only mode starts partial with multiStartIndex = line 0
     const uint32_t s0 = (!m.S && !m.C && m.E) ? 1u : 0u;
     const uint32_t lb_init = s0 ? 1u : 0u;
-    uint32_t stt[ITEMS], cnt[ITEMS];
+    // ---- pass 2: output events of the thread's lines (element n = the virtual end-of-buffer)
+    uint64_t run = run0;
     uint64_t csum = 0;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < ITEMS; ++k) {
         const uint64_t j = base + k;
-        stt[k] = 0;
-        cnt[k] = 0;
         if (j <= n) {
             const uint32_t s_in = OpMlState::f(run, s0);
             uint32_t lbp = OpMlState::lb(run, s0);
             if (!lbp)
                 lbp = lb_init;
             const uint32_t lb = lbp ? lbp - 1 : 0u; // line index of multiStartIndex (valid only when s_in)
-            stt[k] = (s_in << 31) | lb;
             MlCountSink sink;
             sink.discard = m.discard;
             sink.len = len;
             sink.n = (uint32_t)n;
-            ml_actions(m, fl[k], s_in, lb, (uint32_t)j, (uint32_t)n, sink);
-            cnt[k] = sink.cnt;
+            const uint32_t fl = j < n ? flag_of(k) : 0u;
+            ml_actions(m, fl, s_in, lb, (uint32_t)j, (uint32_t)n, sink);
             csum += sink.cnt;
+            if (j < n)
+                run = OpMlState::combine(run, ml_element(m, fl, j));
         }
-        run = OpMlState::combine(run, el[k]);
     }
     uint64_t tot2;
     const uint64_t ex2 = block_exclusive_scan<OpSum, THREADS>(csum, tot2, s_scan);
     const uint64_t pre2 = lookback_block<OpSum, 4>(desc_sum, tile, tot2, s_part, s_flag);
+    // ---- pass 3: emission at the exclusive prefix of the counts
     uint64_t pos = pre2 + ex2;
+    run = run0;
     uint32_t me = 0, ul = 0;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < ITEMS; ++k) {
         const uint64_t j = base + k;
         if (j <= n) {
+            const uint32_t s_in = OpMlState::f(run, s0);
+            uint32_t lbp = OpMlState::lb(run, s0);
+            if (!lbp)
+                lbp = lb_init;
+            const uint32_t lb = lbp ? lbp - 1 : 0u;
+            const uint32_t fl = j < n ? flag_of(k) : 0u;
             MlEmitSink sink;
             sink.discard = m.discard;
             sink.off = off;
@@ -2912,12 +3021,14 @@ __global__ void __launch_bounds__(THREADS)
             sink.n = (uint32_t)n;
             // begin + content.size() == sourceVal.size() (:174); the end-of-buffer element always passes true
             sink.is_last = (j == n) ? 1u : ((off[j] + len[j] == total_len) ? 1u : 0u);
-            ml_actions(m, fl[k], stt[k] >> 31, stt[k] & 0x7FFFFFFFu, (uint32_t)j, (uint32_t)n, sink);
+            ml_actions(m, fl, s_in, lb, (uint32_t)j, (uint32_t)n, sink);
             me += sink.matched_events;
             ul += sink.unmatch_lines;
-            pos += cnt[k];
+            pos = sink.pos;
             if (j == n)
                 *total_out = pos;
+            else
+                run = OpMlState::combine(run, ml_element(m, fl, j));
         }
     }
     for (int d = 16; d; d >>= 1) {
@@ -3159,6 +3270,10 @@ __global__ void __launch_bounds__(128)
         fl[k] = 0;
         fd[k] = 0;
     }
+    if (cfg.tap_off && cfg.tap_col < MF) {
+        cfg.tap_off[i] = fo[cfg.tap_col];
+        cfg.tap_len[i] = fl[cfg.tap_col];
+    }
     }
     if (STAGED) {
         __syncwarp();
@@ -3337,6 +3452,10 @@ __global__ void __launch_bounds__(1024, 1)
                     fl[k] = 0;
                     fd[k] = 0;
                 }
+            if (cfg.tap_off && cfg.tap_col < MF) { // dense copy of one column: the chained processor's event table
+                cfg.tap_off[i] = fo[cfg.tap_col];
+                cfg.tap_len[i] = fl[cfg.tap_col];
+            }
         }
         __syncwarp();
         const uint64_t left = n - batch;

@@ -163,6 +163,10 @@ struct MlConfig {
     const void* blob_cont;
     const void* blob_end;
     int discard;
+    // split + probe pass only (host-built from the prefix DFAs): first[p] bit b = a line starting with byte b can
+    // match pattern p; empty_flags = flag bits of an empty line
+    uint32_t first[3][8];
+    uint32_t empty_flags;
 };
 // flags[i] bit0/1/2 = start/continue/end pattern matches a prefix of line i
 void launch_ml_probe(const MlConfig& cfg, const uint8_t* d_buf, const uint32_t* d_off, const uint32_t* d_len,
@@ -203,6 +207,11 @@ struct DelimConfig {
     int extend;
     int allow_short;
     uint32_t max_fields;
+    // optional column tap: the (off, len) of column tap_col of every line also leave as two DENSE tables (the event
+    // table of a processor chained on that column); tap_col >= max_fields or null pointers = no tap
+    uint32_t tap_col;
+    uint32_t* tap_off;
+    uint32_t* tap_len;
 };
 // d_next_batch: zeroed u64 batch counter of the persistent tiled kernel (quote-FSM mode); nullptr = thread-per-line
 void launch_delim(const DelimConfig& cfg, const uint8_t* d_base, const uint32_t* d_ev_off, const uint32_t* d_ev_len,
