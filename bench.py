@@ -687,6 +687,8 @@ class C4(Config):
         self.fo = torch.empty(n * MF, dtype=torch.int32, device=self.dev)
         self.fl = torch.empty(n * MF, dtype=torch.int32, device=self.dev)
         self.fd = torch.empty(n * MF, dtype=torch.int32, device=self.dev)
+        self.to = torch.empty(n, dtype=torch.int32, device=self.dev)
+        self.tl = torch.empty(n, dtype=torch.int32, device=self.dev)
         self.rs = torch.empty(n, dtype=torch.uint8, device=self.dev)
         self.rco = torch.empty(n * self.G, dtype=torch.int32, device=self.dev)
         self.rcl = torch.empty(n * self.G, dtype=torch.int32, device=self.dev)
@@ -695,13 +697,13 @@ class C4(Config):
 
     def step(self):
         n, MF = self.n, self.MF
+        # the delimiter stage also leaves column 3 as a dense (off, len) table: the regex stage's event table
         self.eng.delim_parse_dev(self.d_buf.data_ptr(), self.in_bytes, self.d_off.data_ptr(), self.d_len.data_ptr(), n,
                                  b",", ord('"'), 10, True, True, MF, self.st.data_ptr(), self.nf.data_ptr(),
-                                 self.fo.data_ptr(), self.fl.data_ptr(), self.fd.data_ptr())
-        # column 3 of the delimiter's field tables IS the regex's event table (read in place, stride MF)
-        self.eng.regex_parse_strided_dev(self.rx, self.d_buf.data_ptr(), self.in_bytes, self.fo.data_ptr() + 12,
-                                         self.fl.data_ptr() + 12, MF, n, self.G, self.rs.data_ptr(),
-                                         self.rco.data_ptr(), self.rcl.data_ptr())
+                                 self.fo.data_ptr(), self.fl.data_ptr(), self.fd.data_ptr(), 3, self.to.data_ptr(),
+                                 self.tl.data_ptr())
+        self.eng.regex_parse_dev(self.rx, self.d_buf.data_ptr(), self.in_bytes, self.to.data_ptr(), self.tl.data_ptr(),
+                                 n, self.G, self.rs.data_ptr(), self.rco.data_ptr(), self.rcl.data_ptr())
 
     def finish_setup(self):
         n, MF = self.n, self.MF

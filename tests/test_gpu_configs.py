@@ -250,6 +250,24 @@ def test_full_size_c4_delimiter_regex_chain(eng):
     eng.regex_parse_strided_dev(rx, d_buf.data_ptr(), buf.size, fo4.data_ptr() + 3 * 4, fl4.data_ptr() + 3 * 4, MF, n, G,
                                 rs.data_ptr(), rco_d.data_ptr(), rcl_d.data_ptr())
     eng.sync()
+    # the same chain through the delimiter's dense column tap (what bench.py --config c4 times)
+    to4 = torch.empty(n, dtype=torch.int32, device="cuda")
+    tl4 = torch.empty(n, dtype=torch.int32, device="cuda")
+    st5 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    fo5 = torch.empty(n * MF, dtype=torch.int32, device="cuda")
+    rs2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    rco2 = torch.empty(n * G, dtype=torch.int32, device="cuda")
+    rcl2 = torch.empty(n * G, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    eng.delim_parse_dev(d_buf.data_ptr(), buf.size, d_off.data_ptr(), d_len.data_ptr(), n, b",", ord('"'), 10, True,
+                        True, MF, st5.data_ptr(), nf4.data_ptr(), fo5.data_ptr(), fl4.data_ptr(), fd4.data_ptr(), 3,
+                        to4.data_ptr(), tl4.data_ptr())
+    eng.regex_parse_dev(rx, d_buf.data_ptr(), buf.size, to4.data_ptr(), tl4.data_ptr(), n, G, rs2.data_ptr(),
+                        rco2.data_ptr(), rcl2.data_ptr())
+    eng.sync()
+    assert torch.equal(to4, fo5.view(n, MF)[:, 3]) and torch.equal(tl4, fl4.view(n, MF)[:, 3])
+    assert torch.equal(st5, st4) and torch.equal(fo5, fo4)
+    assert torch.equal(rs2, rs) and torch.equal(rco2, rco_d) and torch.equal(rcl2, rcl_d)
     assert np.array_equal(st4.cpu().numpy(), e_st)
     assert np.array_equal(nf4.cpu().numpy().view(np.uint32), e_nf)
     assert np.array_equal(fo4.cpu().numpy().view(np.uint32).reshape(n, MF), e_fo)
