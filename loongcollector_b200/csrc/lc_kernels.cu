@@ -1523,6 +1523,9 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
 __device__ __forceinline__ void sts_u64(uint32_t a, uint32_t x, uint32_t y) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void sts_u128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -1687,6 +1690,86 @@ __device__ __forceinline__ uint32_t tdfa_walk_lines(const LcTdfaView& v, const T
     return row;
 }
 
+// ---- software-pipelined tile fill (A/B: LC_B200_TDFA_FETCH=prefetch) ------------------------------------------------
+// The cp.async fill above costs 32 shared-memory wavefronts per instruction (LDGSTS lands one 16-byte wavefront per
+// lane): ~500 of the ~1270 wavefronts a 32-line batch of 256-byte lines needs, on a kernel whose l1tex pipe is 86 %
+// busy.  LDG.128 + STS.128 needs 4 per instruction, but holding a whole stage in registers spills and the loads stall
+// the warp.  Here a stage is 4 chunks (64 bytes per line) and the tile is two 2 KB buffers: while the lanes walk
+// chunk k of stage s out of one buffer, slice k of stage s + 1 travels global -> ONE uint4 register -> the other
+// buffer (LDG before the chunk's work, STS.128 after it), so one load is in flight per lane for the time a chunk takes
+// and nobody waits for it.  Loader role: lane -> chunk column (lane & 3) of line (lane >> 2) * 4 + k; the slot of
+// (chunk q, line) is q * 512 + ((line ^ q) << 4): conflict-free for the 8-lane STS.128 / LDS.128 phases.
+template <bool SLOW, bool UNC>
+__device__ __forceinline__ uint32_t tdfa_walk_lines_pf(const LcTdfaView& v, const TdfaAbs& t, const TdfaLoader& L,
+                                                       uint32_t info_abs, uint32_t dead, uint32_t sink, uint32_t row,
+                                                       uint32_t len, uint32_t mis, uint32_t max_nch, uint32_t regs_m2,
+                                                       uint16_t* rg) {
+    const uint32_t Q = len + mis, qlo = mis + (mis & 1), Qe = Q & ~1u;
+    const uint32_t kf_lo = (qlo + 15) >> 4, kf_hi = Qe >> 4; // fully paired chunks: [kf_lo, kf_hi)
+    const uint32_t k_tail = len ? (Q - 1) >> 4 : 0;
+    const bool has_head = len && !(kf_lo == 0 && kf_hi > 0);
+    const bool has_tail = len && k_tail >= kf_hi && !(has_head && k_tail == 0);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t pq = lane & 3, pL0 = (lane >> 2) * 4;
+    const uint32_t rd16 = L.rd_lane16;
+    if (max_nch == 0)
+        return row;
+    // prologue: stage 0 into buffer 0
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) {
+        const uint32_t line = pL0 + k;
+        const uint2 inf = lds_u64_v(info_abs + line * 8);
+        if (pq < inf.y)
+            sts_u128(L.tile_abs + (pq << 9) + ((line ^ pq) << 4), __ldg(L.gbase16 + inf.x + pq));
+    }
+    uint32_t buf = 0;
+    for (uint32_t s0 = 0; s0 < max_nch; s0 += 4, buf ^= 2048u) {
+        __syncwarp(); // the buffer of this stage is complete, the other one is free
+        const uint32_t cur = L.tile_abs + buf, nxt = L.tile_abs + (buf ^ 2048u);
+        const bool more = s0 + 4 < max_nch;
+#pragma unroll
+        for (uint32_t kk = 0; kk < 4; ++kk) {
+            // ---- slice kk of the next stage: issue the load
+            uint4 pf = make_uint4(0, 0, 0, 0);
+            bool pf_on = false;
+            const uint32_t pline = pL0 + kk;
+            if (more) {
+                const uint2 inf = lds_u64_v(info_abs + pline * 8);
+                pf_on = s0 + 4 + pq < inf.y;
+                if (pf_on)
+                    pf = __ldg(L.gbase16 + inf.x + s0 + 4 + pq);
+            }
+            // ---- this lane's own line: chunk k of the current stage
+            const uint32_t k = s0 + kk;
+            if (row != dead && len) {
+                const uint32_t caddr = cur + (kk << 9) + (rd16 ^ (kk << 4));
+                if (k >= kf_lo && k < kf_hi) {
+                    const uint4 vv = lds_u128_v(caddr);
+                    const uint32_t pos0 = k * 16 - mis;
+                    const uint32_t row_in = row;
+                    LCS_PAIR(vv.x, 0, pos0 + 0)
+                    LCS_PAIR(vv.x, 1, pos0 + 2)
+                    LCS_PAIR(vv.y, 0, pos0 + 4)
+                    LCS_PAIR(vv.y, 1, pos0 + 6)
+                    LCS_PAIR(vv.z, 0, pos0 + 8)
+                    LCS_PAIR(vv.z, 1, pos0 + 10)
+                    LCS_PAIR(vv.w, 0, pos0 + 12)
+                    LCS_PAIR(vv.w, 1, pos0 + 14)
+                    if (SLOW && row == sink)
+                        row = t.t2 + t.row_bytes * tdfa_chunk_slow(v, __umulhi(row_in - t.t2, t.inv_row), vv, pos0, rg);
+                } else if ((k == 0 && has_head) || (k == k_tail && has_tail)) {
+                    row = tdfa_partial_chunk(v, t, row, caddr, k * 16, mis, len, regs_m2, rg, sink);
+                }
+            }
+            // ---- land the prefetched slice in the other buffer
+            if (pf_on)
+                sts_u128(nxt + (pq << 9) + ((pline ^ pq) << 4), pf);
+        }
+    }
+    __syncwarp();
+    return row;
+}
+
 // Stages one automaton: class table at the 256-byte aligned shared address cls_abs, blob right behind it; pair-table
 // entries are rebased so that their low 16 bits are the ABSOLUTE shared address of the next row.  All threads call;
 // the caller synchronises afterwards.
@@ -1708,7 +1791,7 @@ __device__ __forceinline__ void tdfa_stage_blob(uint8_t* g_cls, uint32_t cls_abs
         t2w[k] += t2;
 }
 
-template <bool SLOW, bool UNC>
+template <bool SLOW, bool UNC, bool PF>
 __global__ void __launch_bounds__(1024, 1)
     regex_tdfa_staged_kernel(const uint4* __restrict__ blob, uint32_t blob_bytes, const uint8_t* __restrict__ base,
                              const uint32_t* __restrict__ ev_off, const uint32_t* __restrict__ ev_len,
@@ -1793,7 +1876,10 @@ __global__ void __launch_bounds__(1024, 1)
         const uint32_t max_nch = __reduce_max_sync(0xFFFFFFFFu, nch);
         uint32_t row = t.t2 + v.h->start * t.row_bytes;
         __syncwarp();
-        row = tdfa_walk_lines<SLOW, UNC>(v, t, L, dead, sink, row, len, mis, max_nch, regs_m2, rg);
+        if (PF)
+            row = tdfa_walk_lines_pf<SLOW, UNC>(v, t, L, info_abs, dead, sink, row, len, mis, max_nch, regs_m2, rg);
+        else
+            row = tdfa_walk_lines<SLOW, UNC>(v, t, L, dead, sink, row, len, mis, max_nch, regs_m2, rg);
         uint32_t st = 1;
         if (valid) {
             bool ok = false;
@@ -1868,8 +1954,14 @@ int launch_regex_tdfa_staged(const void* d_blob, uint32_t blob_bytes, bool slow,
         return e && !strcmp(e, "uncond");
     }();
     const bool unc = unc_env && reg_pitch > nregs; // the no-op slot is the spare halfword of the neighbouring file
-    auto k = slow ? (unc ? regex_tdfa_staged_kernel<true, true> : regex_tdfa_staged_kernel<true, false>)
-                  : (unc ? regex_tdfa_staged_kernel<false, true> : regex_tdfa_staged_kernel<false, false>);
+    static const bool pf = [] {
+        const char* e = getenv("LC_B200_TDFA_FETCH");
+        return e && !strcmp(e, "prefetch");
+    }();
+    auto k = pf ? (slow ? regex_tdfa_staged_kernel<true, false, true> : regex_tdfa_staged_kernel<false, false, true>)
+                : (slow ? (unc ? regex_tdfa_staged_kernel<true, true, false> : regex_tdfa_staged_kernel<true, false, false>)
+                        : (unc ? regex_tdfa_staged_kernel<false, true, false>
+                               : regex_tdfa_staged_kernel<false, false, false>));
     cudaError_t er = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (er != cudaSuccess)
         return (int)er;
@@ -1905,9 +1997,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                      : "r"(bar), "r"(parity)
                      : "memory");
     } while (!ok);
-}
-__device__ __forceinline__ void sts_u128(uint32_t a, const uint4& v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 struct TdfaPcFetch {

@@ -311,15 +311,18 @@ def test_delim_matches_oracle(eng, sep, quote, extend, allow_short):
 # ------------------------------------------------------------------------------------------- kernel variants
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize("variant", ["basic", "generic", "fast", "fast2", "tdfa", "tdfa_direct", "tdfa_pc",
-                                     "tdfa+uncond", "tdfa_pc+uncond"])
+                                     "tdfa+uncond", "tdfa_pc+uncond", "tdfa+prefetch"])
 def test_regex_kernel_variants_agree(variant, monkeypatch):
     """The baseline (tables in global memory) and generic (smem interpreter) kernels stay parity-checked too."""
     lc = _lc()
-    if variant.endswith("+uncond"):
-        # boundary stores issued unconditionally (no-op slot); read once per process, so run in a fresh interpreter
+    if "+" in variant:
+        # A/B knobs that are read once per process (unconditional boundary stores / software-pipelined tile fill): run
+        # the base variant in a fresh interpreter with the knob set
         import subprocess
         import sys
-        env = dict(os.environ, LC_B200_TDFA_STORE="uncond")
+        knob = {"uncond": ("LC_B200_TDFA_STORE", "uncond"), "prefetch": ("LC_B200_TDFA_FETCH", "prefetch")}
+        name, val = knob[variant.split("+")[1]]
+        env = dict(os.environ, **{name: val})
         r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
                             "%s::test_regex_kernel_variants_agree[%s]" % (__file__, variant.split("+")[0])], env=env,
                            capture_output=True, text=True, timeout=280, cwd=os.path.dirname(HERE))
