@@ -694,26 +694,11 @@ void ProcessorParseRegexNative::Process(PipelineEventGroup& group) {
 }
 
 void ProcessorParseRegexNative::Process(std::vector<PipelineEventGroup>& groups) {
-    // sub-batches whose packed arena stays well below the 4 GiB / 2^30-event limits of one engine call
-    const uint64_t kMaxBytes = 1ull << 30;
-    size_t g0 = 0;
-    while (g0 < groups.size()) {
-        uint64_t bytes = 0, events = 0;
-        size_t g1 = g0;
-        while (g1 < groups.size()) {
-            uint64_t gb = 0;
-            for (const auto& e : groups[g1].GetEvents())
-                if (e.Is<LogEvent>())
-                    gb += e.Cast<LogEvent>().GetContent(mSourceKey).size() + 16;
-            if (g1 > g0 && (bytes + gb > kMaxBytes || events + groups[g1].GetEvents().size() > (1u << 28)))
-                break;
-            bytes += gb;
-            events += groups[g1].GetEvents().size();
-            ++g1;
-        }
-        ProcessBatch(groups.data() + g0, g1 - g0);
-        g0 = g1;
-    }
+    // sub-batches of at most 2048 groups (<= 512 KB each: <= 1 GiB of arena bytes, far below the 4 GiB / 2^30-event
+    // limits of one engine call); groups that are larger than the reader's 512 KB make ProcessBatch split further
+    const size_t kMaxGroups = 2048;
+    for (size_t g0 = 0; g0 < groups.size(); g0 += kMaxGroups)
+        ProcessBatch(groups.data() + g0, std::min(kMaxGroups, groups.size() - g0));
 }
 
 // One engine call for `ngroups` groups.  Per group the values to parse normally alias ONE arena chunk (all lines of a
@@ -770,6 +755,19 @@ void ProcessorParseRegexNative::ProcessBatch(PipelineEventGroup* groups, size_t 
                     }
                 }
             });
+            {
+                // (oversized batch: groups far larger than the reader's chunks) split and recurse
+                uint64_t bytes = 0, evs = 0;
+                for (auto& p : plan) {
+                    bytes += ((uint64_t)p.spanLen + 15) & ~15ull;
+                    evs += p.nEv;
+                }
+                if (ngroups > 1 && (bytes >= (3ull << 30) || evs >= (1ull << 29))) {
+                    ProcessBatch(groups, ngroups / 2);
+                    ProcessBatch(groups + ngroups / 2, ngroups - ngroups / 2);
+                    return;
+                }
+            }
             uint64_t dst = 0, stagedBytes = 0;
             for (auto& p : plan) {
                 p.firstEv = nb;
