@@ -660,12 +660,12 @@ bool ProcessorParseRegexNative::FinishEvent(PipelineEventGroup& group, PipelineE
 void ProcessorParseRegexNative::EpilogueGroup(PipelineEventGroup& group, uint64_t firstEv, const ThreadScratch& sc,
                                               uint32_t G, LocalCounters& c) const {
     EventsContainer& events = group.MutableEvents();
-    uint64_t i = firstEv;
     size_t wIdx = 0;
     for (size_t rIdx = 0; rIdx < events.size(); ++rIdx) {
         EventResult r{};
         const EventResult* rp = nullptr;
         const LogEvent::Content* src = nullptr;
+        const uint64_t i = firstEv + rIdx; // the event's row of the result tables
         if (IsSupportedEvent(events[rIdx])) {
             src = events[rIdx].Cast<LogEvent>().FindContent(mSourceKey);
             if (src && !mIsWholeLineMode) {
@@ -675,7 +675,6 @@ void ProcessorParseRegexNative::EpilogueGroup(PipelineEventGroup& group, uint64_
                 r.origin = src->first.second.data(); // captures map back onto the ORIGINAL bytes, staged or not
                 r.originOff = sc.off.p[i];
                 rp = &r;
-                ++i;
             }
         }
         if (FinishEvent(group, events[rIdx], src, rp, c)) {
@@ -721,63 +720,13 @@ void ProcessorParseRegexNative::ProcessBatch(PipelineEventGroup* groups, size_t 
         uint64_t nb = 0;
         const auto tGather = Clock::now();
         if (!mIsWholeLineMode) {
-            // ---- pass 1 (parallel over groups): count the events that reach RegexLogLineParser, find each span
-            ParallelFor(ngroups, 8, [&](size_t a, size_t b, unsigned) {
-                for (size_t g = a; g < b; ++g) {
-                    GroupPlan& p = plan[g];
-                    const char* lo = nullptr;
-                    const char* hi = nullptr;
-                    uint64_t total = 0;
-                    for (const auto& e : groups[g].GetEvents()) {
-                        if (!IsSupportedEvent(e))
-                            continue;
-                        const LogEvent::Content* sc1 = e.Cast<LogEvent>().FindContent(mSourceKey);
-                        if (!sc1)
-                            continue;
-                        StringView v = sc1->first.second;
-                        if (!p.nEv || v.data() < lo)
-                            lo = v.data();
-                        if (!p.nEv || v.data() + v.size() > hi)
-                            hi = v.data() + v.size();
-                        total += v.size();
-                        ++p.nEv;
-                    }
-                    if (!p.nEv)
-                        continue;
-                    size_t chunkSize = 0;
-                    if ((uint64_t)(hi - lo) < (1ull << 31) &&
-                        groups[g].GetSourceBuffer()->ChunkContaining(lo, (size_t)(hi - lo), &chunkSize)) {
-                        p.lo = lo;
-                        p.spanLen = (uint32_t)(hi - lo);
-                    } else {
-                        p.staged = true;
-                        p.spanLen = (uint32_t)total;
-                    }
-                }
-            });
-            {
-                // (oversized batch: groups far larger than the reader's chunks) split and recurse
-                uint64_t bytes = 0, evs = 0;
-                for (auto& p : plan) {
-                    bytes += ((uint64_t)p.spanLen + 15) & ~15ull;
-                    evs += p.nEv;
-                }
-                if (ngroups > 1 && (bytes >= (3ull << 30) || evs >= (1ull << 29))) {
-                    ProcessBatch(groups, ngroups / 2);
-                    ProcessBatch(groups + ngroups / 2, ngroups - ngroups / 2);
-                    return;
-                }
-            }
-            uint64_t dst = 0, stagedBytes = 0;
-            for (auto& p : plan) {
-                p.firstEv = nb;
-                nb += p.nEv;
-                p.spanDst = (uint32_t)dst;
-                dst += ((uint64_t)p.spanLen + 15) & ~15ull;
-                if (p.staged) {
-                    p.stagedAt = stagedBytes;
-                    stagedBytes += ((uint64_t)p.spanLen + 15) & ~15ull;
-                }
+            // Rows of the flat event table map 1:1 onto the events of the groups (row = firstEv of the group + index of
+            // the event): an event that does not reach RegexLogLineParser gets an empty row the engine parses for
+            // nothing and the epilogue ignores.  That makes the gather ONE pass over the events.
+            for (size_t g = 0; g < ngroups; ++g) {
+                plan[g].firstEv = nb;
+                plan[g].nEv = groups[g].GetEvents().size();
+                nb += plan[g].nEv;
             }
             if (nb) {
                 ThreadScratch& sc = Scratch();
@@ -787,33 +736,91 @@ void ProcessorParseRegexNative::ProcessBatch(PipelineEventGroup* groups, size_t 
                 uint8_t* status = sc.status.ensure(nb);
                 uint32_t* capOff = sc.capOff.ensure(nb * G + 1);
                 uint32_t* capLen = sc.capLen.ensure(nb * G + 1);
-                uint8_t* staging = stagedBytes ? sc.staging.ensure(stagedBytes) : nullptr;
-                // ---- pass 2 (parallel): the flat event table in packed-arena coordinates
+                // ---- pass 1 (parallel over groups): span = the arena chunk that holds the group's values (the reader's
+                // <= 512 KB buffer); offsets relative to it for now
                 ParallelFor(ngroups, 8, [&](size_t a, size_t b, unsigned) {
                     for (size_t g = a; g < b; ++g) {
                         GroupPlan& p = plan[g];
-                        if (!p.nEv)
-                            continue;
+                        const char* base = nullptr;
+                        size_t chunkSize = 0;
+                        uint64_t total = 0;
                         uint64_t i = p.firstEv;
-                        uint64_t at = 0;
-                        if (p.staged)
-                            p.lo = reinterpret_cast<const char*>(staging + p.stagedAt);
                         for (const auto& e : groups[g].GetEvents()) {
-                            if (!IsSupportedEvent(e))
+                            const LogEvent::Content* src =
+                                IsSupportedEvent(e) ? e.Cast<LogEvent>().FindContent(mSourceKey) : nullptr;
+                            if (!src) {
+                                off[i] = 0;
+                                len[i] = 0;
+                                ++i;
                                 continue;
-                            const LogEvent::Content* sc2 = e.Cast<LogEvent>().FindContent(mSourceKey);
-                            if (!sc2)
-                                continue;
-                            StringView v = sc2->first.second;
-                            if (p.staged) {
+                            }
+                            StringView v = src->first.second;
+                            if (!base && !p.staged) {
+                                base = groups[g].GetSourceBuffer()->ChunkContaining(v.data(), v.size(), &chunkSize);
+                                if (!base || chunkSize >= (1ull << 31))
+                                    p.staged = true;
+                            }
+                            if (!p.staged && !(v.data() >= base && v.data() + v.size() <= base + chunkSize))
+                                p.staged = true;
+                            off[i] = p.staged ? 0u : (uint32_t)(v.data() - base);
+                            len[i] = (uint32_t)v.size();
+                            total += v.size();
+                            ++i;
+                        }
+                        if (p.staged) {
+                            p.spanLen = (uint32_t)total;
+                        } else {
+                            p.lo = base;
+                            p.spanLen = base ? (uint32_t)chunkSize : 0u;
+                        }
+                    }
+                });
+                {
+                    // (oversized batch: groups far larger than the reader's chunks) split and recurse
+                    uint64_t bytes = 0;
+                    for (auto& p : plan)
+                        bytes += ((uint64_t)p.spanLen + 15) & ~15ull;
+                    if (ngroups > 1 && (bytes >= (3ull << 30) || nb >= (1ull << 29))) {
+                        ProcessBatch(groups, ngroups / 2);
+                        ProcessBatch(groups + ngroups / 2, ngroups - ngroups / 2);
+                        return;
+                    }
+                }
+                uint64_t dst = 0, stagedBytes = 0;
+                for (auto& p : plan) {
+                    p.spanDst = (uint32_t)dst;
+                    dst += ((uint64_t)p.spanLen + 15) & ~15ull;
+                    if (p.staged) {
+                        p.stagedAt = stagedBytes;
+                        stagedBytes += ((uint64_t)p.spanLen + 15) & ~15ull;
+                    }
+                }
+                uint8_t* staging = stagedBytes ? sc.staging.ensure(stagedBytes) : nullptr;
+                // ---- pass 2 (parallel): packed-arena coordinates; groups whose values are scattered over several
+                // chunks are packed into pinned staging here
+                ParallelFor(ngroups, 8, [&](size_t a, size_t b, unsigned) {
+                    for (size_t g = a; g < b; ++g) {
+                        GroupPlan& p = plan[g];
+                        uint64_t i = p.firstEv;
+                        if (!p.staged) {
+                            for (uint64_t k = 0; k < p.nEv; ++k)
+                                off[i + k] += p.spanDst;
+                            continue;
+                        }
+                        uint64_t at = 0;
+                        p.lo = reinterpret_cast<const char*>(staging + p.stagedAt);
+                        for (const auto& e : groups[g].GetEvents()) {
+                            const LogEvent::Content* src =
+                                IsSupportedEvent(e) ? e.Cast<LogEvent>().FindContent(mSourceKey) : nullptr;
+                            if (src) {
+                                StringView v = src->first.second;
                                 if (v.size())
                                     memcpy(staging + p.stagedAt + at, v.data(), v.size());
                                 off[i] = p.spanDst + (uint32_t)at;
                                 at += v.size();
                             } else {
-                                off[i] = p.spanDst + (uint32_t)(v.data() - p.lo);
+                                off[i] = p.spanDst;
                             }
-                            len[i] = (uint32_t)v.size();
                             ++i;
                         }
                     }
