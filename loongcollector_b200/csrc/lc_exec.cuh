@@ -296,6 +296,7 @@ struct LcTdfaView {
     const uint32_t* t1;
     const uint32_t* eof;
     const uint16_t* ops;
+    const uint32_t* skip;
 };
 
 LC_HD LcTdfaView lc_tdfa_view(const void* blob) {
@@ -308,7 +309,22 @@ LC_HD LcTdfaView lc_tdfa_view(const void* blob) {
     v.t1 = (const uint32_t*)(b + h->off_t1);
     v.eof = (const uint32_t*)(b + h->off_eof);
     v.ops = (const uint16_t*)(b + h->off_ops);
+    v.skip = (const uint32_t*)(b + h->off_skip);
     return v;
+}
+
+// does the 16-byte chunk w[0..3] hold one of the exit bytes of skip word sk (LC_TDFA_SKIP set)?
+LC_HD bool lc_tdfa_chunk_has_exit(uint32_t sk, const uint32_t w[4]) {
+    const uint32_t n = (sk >> 16) & 3u;
+    uint32_t hit = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t splat = ((sk >> (8 * k)) & 0xFFu) * 0x01010101u;
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t x = w[j] ^ splat;
+            hit |= (x - 0x01010101u) & ~x & 0x80808080u; // some byte of x is zero
+        }
+    }
+    return hit != 0;
 }
 
 // RegT = uint16_t (events shorter than 65535 bytes: the shared-memory register files of the kernels) or uint32_t
@@ -345,6 +361,16 @@ LC_HD bool lc_tdfa_event(const LcTdfaView& v, const uint8_t* s, uint32_t mis, ui
         pos = 1;
     }
     while (pos + 2 <= n) {
+        // run skipping exactly as the kernels do it: at a 16-byte boundary of the line's aligned frame, with a whole
+        // chunk of input left, a skippable state jumps over a chunk that holds none of its exit bytes
+        if (((pos + mis) & 15u) == 0 && pos + 16 <= n && v.skip[st]) {
+            uint32_t w[4];
+            memcpy(w, s + pos, 16);
+            if (!lc_tdfa_chunk_has_exit(v.skip[st], w)) {
+                pos += 16;
+                continue;
+            }
+        }
         const uint32_t c0 = v.cls[s[pos]], c1 = v.cls[s[pos + 1]];
         const uint32_t e = *(const uint32_t*)(v.t2 + st * row_bytes + (c0 * ncls + c1) * 4);
         if (e & LC_TDFA_SLOW) {
@@ -382,14 +408,10 @@ LC_HD bool lc_tdfa_event(const LcTdfaView& v, const uint8_t* s, uint32_t mis, ui
 LC_HD uint32_t lc_eq_mask16(const uint32_t w[4], uint32_t splat) {
     uint32_t m = 0;
     for (int k = 0; k < 4; ++k) {
-#if defined(__CUDA_ARCH__)
-        const uint32_t eq = __vcmpeq4(w[k], splat) & 0x01010101u;
-#else
-        uint32_t x = w[k] ^ splat, eq = 0;
-        for (int b = 0; b < 4; ++b)
-            if (((x >> (8 * b)) & 0xFFu) == 0)
-                eq |= 1u << (8 * b);
-#endif
+        // bit 0 of every byte of w[k] that equals the splat byte: exact zero-byte test of x (no cross-byte borrows);
+        // plain integer ops on both sides (the SIMD-video compare of the GPU is emulated and costs more)
+        const uint32_t x = w[k] ^ splat;
+        const uint32_t eq = (~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u) >> 7;
         m |= (((eq * 0x01020408u) >> 24) & 0xFu) << (4 * k);
     }
     return m;

@@ -256,6 +256,177 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 2 : 1)
     }
 }
 
+// ---- persistent variant: tiles in flight behind the look-back ---------------------------------------------------------
+// ncu of split_kernel<1024>: 35 stall cycles per issued instruction at barriers, DRAM 28 % busy -- a block's life is a
+// chain of exposed latencies (ticket atomic -> loads -> scan barriers -> look-back round trips -> stores) and an SM holds
+// only two such blocks.  Here a block of 512 threads keeps looping over tickets: the ticket of the tile AFTER next is
+// requested and the 32 KiB of the NEXT tile are already on their way into registers while the current tile goes through
+// its scan, look-back and stores, so neither the atomic nor the loads are ever waited for in steady state.
+template <int THREADS, bool PROBE>
+__global__ void __launch_bounds__(THREADS, 2)
+    split_persist_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
+                         uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap,
+                         volatile uint64_t* desc, uint32_t* ticket, uint32_t ntiles, uint32_t* n_out,
+                         unsigned long long* total_chars, SplitProbe pr) {
+    constexpr int NW = THREADS / 32;
+    __shared__ uint32_t s_cnt[NW], s_last[NW], s_start[NW];
+    __shared__ uint32_t s_tick[2], s_tot, s_tlast;
+    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_qn;
+    __shared__ uint32_t s_q[PROBE ? kProbeQueue : 1];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint4* vbuf = reinterpret_cast<const uint4*>(buf - shift);
+    const uint64_t total_v = (uint64_t)len + shift; // virtual length including the alignment lead-in
+    if (tid == 0) {
+        s_tick[0] = atomicAdd(ticket, 1u);
+        s_tick[1] = atomicAdd(ticket, 1u);
+        s_qn = 0;
+    }
+    __syncthreads();
+    uint32_t tile = s_tick[0], nxt = s_tick[1];
+    __syncthreads(); // everyone holds both tickets before the first iteration overwrites slot 0
+    auto load_tile = [&](uint32_t t, uint4* v) {
+        const uint64_t c0 = ((uint64_t)t * THREADS + tid) * 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            v[r] = make_uint4(0, 0, 0, 0);
+            if (t < ntiles && (c0 + r) * 16 < total_v)
+                v[r] = __ldg(vbuf + c0 + r);
+        }
+    };
+    uint4 v[4];
+    load_tile(tile, v);
+    for (uint32_t it = 0; tile < ntiles; ++it) {
+        // the tile after next: its ticket is asked for now and read at the bottom of this iteration
+        if (tid == 0)
+            s_tick[it & 1] = atomicAdd(ticket, 1u);
+        uint4 vn[4];
+        load_tile(nxt, vn);
+        const uint64_t vpos0 = ((uint64_t)tile * THREADS + tid) * 64;
+        const bool full = ((uint64_t)(tile + 1) * THREADS * 64 <= total_v) && !(tile == 0 && shift);
+        uint64_t mk = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint32_t m = match16b(v[r], splat);
+            if (!full) {
+                const uint64_t vpos = vpos0 + (uint64_t)r * 16;
+                if (vpos >= total_v)
+                    m = 0;
+                else {
+                    if (vpos == 0 && shift)
+                        m &= ~((1u << shift) - 1u);
+                    const uint64_t rem = total_v - vpos;
+                    if (rem < 16)
+                        m &= (1u << rem) - 1u;
+                }
+            }
+            mk |= (uint64_t)m << (16 * r);
+        }
+        const uint32_t cnt = __popcll(mk);
+        const uint32_t last = mk ? (uint32_t)(vpos0 + (63 - __clzll((long long)mk)) + 1 - shift) : 0u;
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d)
+                inc += t;
+        }
+        const uint32_t has = __ballot_sync(0xFFFFFFFFu, mk != 0);
+        const uint32_t below = has & ((1u << lane) - 1u);
+        const uint32_t prev_last = __shfl_sync(0xFFFFFFFFu, last, below ? 31 - __clz(below) : 0);
+        const uint32_t warp_last = __shfl_sync(0xFFFFFFFFu, last, has ? 31 - __clz(has) : 0);
+        if (lane == 31) {
+            s_cnt[wid] = inc;
+            s_last[wid] = has ? warp_last : 0u;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t c = lane < NW ? s_cnt[lane] : 0u;
+            const uint32_t wl = lane < NW ? s_last[lane] : 0u;
+            uint32_t ci = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ci, d);
+                if (lane >= d)
+                    ci += t;
+            }
+            const uint32_t whas = __ballot_sync(0xFFFFFFFFu, c != 0);
+            const uint32_t wbelow = whas & ((1u << lane) - 1u);
+            const uint32_t st = __shfl_sync(0xFFFFFFFFu, wl, wbelow ? 31 - __clz(wbelow) : 0);
+            const uint32_t tl = __shfl_sync(0xFFFFFFFFu, wl, whas ? 31 - __clz(whas) : 0);
+            const uint32_t totv = __shfl_sync(0xFFFFFFFFu, ci, NW - 1);
+            if (lane < NW) {
+                s_cnt[lane] = ci - c;
+                s_start[lane] = wbelow ? st : 0u;
+            }
+            // the look-back of this tile: the first warp walks while the others wait at the next barrier
+            const uint64_t p = lookback<OpCountMax>(desc, tile, OpCountMax::make(totv, whas ? tl : 0u));
+            if (lane == 0) {
+                s_prefix = p;
+                s_tot = totv;
+                if (totv)
+                    atomicAdd(total_chars, (unsigned long long)totv);
+            }
+        }
+        __syncthreads();
+        const uint64_t tile_prefix = s_prefix;
+        uint32_t k = (OpCountMax::count(tile_prefix) + s_cnt[wid] + (inc - cnt)) & 0x3FFFFFFFu;
+        uint32_t start = below ? prev_last : (s_start[wid] ? s_start[wid] : OpCountMax::maxv(tile_prefix));
+        while (mk) {
+            const int b = __ffsll((long long)mk) - 1;
+            mk &= mk - 1;
+            const uint32_t p = (uint32_t)(vpos0 + b - shift);
+            if (k < cap) {
+                out_off[k] = start;
+                out_len[k] = p - start;
+                if (PROBE) {
+                    const uint32_t ll = p - start;
+                    const uint32_t cand = ll ? probe_first(pr, buf[start]) : 0u;
+                    if (!cand) {
+                        pr.flags[k] = ll ? 0 : (uint8_t)pr.empty_flags;
+                    } else {
+                        const uint32_t q = atomicAdd(&s_qn, 1u);
+                        if (q < kProbeQueue)
+                            s_q[q] = k;
+                        else
+                            pr.flags[k] = probe_line(pr, buf + start, ll);
+                    }
+                }
+            }
+            ++k;
+            start = p + 1;
+        }
+        if (tile == ntiles - 1 && tid == THREADS - 1) {
+            if (start < len) { // the unterminated last piece, if any
+                if (k < cap) {
+                    out_off[k] = start;
+                    out_len[k] = len - start;
+                    if (PROBE)
+                        pr.flags[k] = probe_line(pr, buf + start, len - start);
+                }
+                ++k;
+            }
+            *n_out = k;
+        }
+        __syncthreads(); // the probe queue is complete, this tile's table entries are visible; s_* may be rewritten
+        if (PROBE) {
+            const uint32_t qn = min(s_qn, kProbeQueue);
+            for (uint32_t q = tid; q < qn; q += THREADS) {
+                const uint32_t kk = s_q[q];
+                pr.flags[kk] = probe_line(pr, buf + out_off[kk], out_len[kk]);
+            }
+            __syncthreads();
+            if (tid == 0)
+                s_qn = 0;
+        }
+        tile = nxt;
+        nxt = s_tick[it & 1];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            v[r] = vn[r];
+    }
+}
+
 static int split_lookback_warps() {
     static const int w = [] {
         const char* e = getenv("LC_B200_LOOKBACK_WARPS"); // A/B knob: 1 (default) = single-warp walk, 4 = block-wide
@@ -276,9 +447,30 @@ static void launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_
         int t = e ? atoi(e) : 64;
         return t == 16 ? 16 : 64;
     }();
+    volatile uint64_t* desc = (volatile uint64_t*)d_desc;
+    static const bool persist = [] {
+        const char* e = getenv("LC_B200_SPLIT_PERSIST"); // A/B knob: 0 = one block per tile
+        return !(e && !strcmp(e, "0"));
+    }();
+    if (persist) {
+        constexpr int T = 512; // 32 KiB tiles (the descriptors are sized for 16 KiB tiles: enough)
+        const uint32_t nt = (uint32_t)(((uint64_t)len + shift + T * 64 - 1) / (T * 64));
+        static int sms = 0, per_sm = 0;
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, split_persist_kernel<T, PROBE>, T, 0);
+            if (per_sm < 1)
+                per_sm = 1;
+        }
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(nt, (uint64_t)sms * per_sm);
+        split_persist_kernel<T, PROBE><<<grid, T, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap, desc, d_ticket,
+                                                          nt, d_n_out, d_total, pr);
+        return;
+    }
     const uint64_t tile_bytes = (uint64_t)cfg * 1024;
     uint32_t ntiles = (uint32_t)((len + shift + tile_bytes - 1) / tile_bytes);
-    volatile uint64_t* desc = (volatile uint64_t*)d_desc;
     const bool wide = split_lookback_warps() > 1;
 #define LC_SPLIT_LAUNCH(T, W)                                                                                          \
     split_kernel<T, W, PROBE><<<ntiles, T, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap, desc, d_ticket, ntiles, \
@@ -1539,6 +1731,7 @@ struct TdfaAbs {
     uint32_t ncls;
     uint32_t row_bytes;
     uint32_t inv_row;   // ceil(2^32 / row_bytes): state = umulhi(row - t2, inv_row)
+    uint32_t skip;      // absolute shared address of the run-skipping table (u32 per state, lc_tables.h)
 };
 
 // (Tried and measured slower on C2: a power-of-two row pitch with the address formed as row | index * 4 -- the same
@@ -1666,6 +1859,16 @@ __device__ __forceinline__ uint32_t tdfa_walk_lines(const LcTdfaView& v, const T
             for (uint32_t k = ka; k < kb; ++k) {
                 const uint32_t q = k & 7;
                 const uint4 vv = lds_u128_v(tile_abs + (q << 9) + (rd_lane16 ^ (q << 4)));
+                {
+                    // run skipping: inside [^"]* / .* / after the line has died the state maps every byte but (at
+                    // most) two back to itself without touching a register -- a chunk without those bytes is a no-op
+                    const uint32_t sk = lds_u32(t.skip + __umulhi(row - t.t2, t.inv_row) * 4);
+                    if (sk) {
+                        const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+                        if (!lc_tdfa_chunk_has_exit(sk, w))
+                            continue;
+                    }
+                }
                 const uint32_t pos0 = k * 16 - mis;
                 const uint32_t row_in = row;
                 LCS_PAIR(vv.x, 0, pos0 + 0)
@@ -1815,6 +2018,7 @@ __global__ void __launch_bounds__(1024, 1)
     t.ncls = v.h->ncls;
     t.row_bytes = v.h->row_bytes;
     t.inv_row = (uint32_t)((0x100000000ull + t.row_bytes - 1) / t.row_bytes);
+    t.skip = cls_abs + 256 + v.h->off_skip;
     const uint32_t G = v.h->ngroups;
     const uint32_t invG = G ? 0xFFFFFFFFu / G + 1 : 0; // umulhi(j, invG) == j / G for j < 65536
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -2111,6 +2315,7 @@ __global__ void __launch_bounds__(1024, 1)
     t.ncls = v.h->ncls;
     t.row_bytes = v.h->row_bytes;
     t.inv_row = (uint32_t)((0x100000000ull + t.row_bytes - 1) / t.row_bytes);
+    t.skip = cls_abs + 256 + v.h->off_skip;
     const uint32_t G = v.h->ngroups;
     const uint32_t invG = G ? 0xFFFFFFFFu / G + 1 : 0;
     uint16_t* wregs = reinterpret_cast<uint16_t*>(g_regs0) + (size_t)ci * 32 * reg_pitch;
@@ -2240,7 +2445,7 @@ int launch_regex_tdfa_pc(const void* d_blob, uint32_t blob_bytes, bool slow, uin
 // RESUME (patterns that do not fit together are spread over several launches): which[] holds the result of the
 // earlier launches; lines matched there are left alone, p_base = index of this launch's first pattern.
 struct TdfaPatS {
-    uint32_t cls, t2, ncls, row_bytes, inv_row, start_row, sink, G, nkeys, blob_off;
+    uint32_t cls, t2, ncls, row_bytes, inv_row, start_row, sink, G, nkeys, blob_off, skip;
 };
 
 template <bool SLOW, bool RESUME>
@@ -2273,6 +2478,7 @@ __global__ void __launch_bounds__(1024, 1)
             ps.G = v.h->ngroups;
             ps.nkeys = a.nkeys[p];
             ps.blob_off = cursor + 256 - s0abs;
+            ps.skip = cursor + 256 + v.h->off_skip;
             pats[p] = ps;
         }
         cursor += 256 + ((a.blob_bytes[p] + 255u) & ~255u);
@@ -2352,6 +2558,7 @@ __global__ void __launch_bounds__(1024, 1)
                 Gp = lds_u32_v(pa + 28);
                 nkp = lds_u32_v(pa + 32);
                 blob_off = lds_u32_v(pa + 36);
+                t.skip = lds_u32_v(pa + 40);
             }
             const LcTdfaView v = lc_tdfa_view(smem_b + blob_off);
             const uint32_t dead = t.t2;
@@ -3400,15 +3607,18 @@ __global__ void __launch_bounds__(1024, 1)
                        uint32_t* __restrict__ f_dq, unsigned long long* next_batch) {
     extern __shared__ uint4 smem[];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t MF = cfg.max_fields, pitch = MF | 1u;
+    // the warp's [32][MF] blocks of f_off / f_len / f_dq are built in shared memory in exactly the global layout (row
+    // pitch MF), so that they leave -- zero padding included -- as plain 16-byte vector copies
+    const uint32_t MF = cfg.max_fields;
+    const uint32_t blk_words = 32 * MF, blk_pad = (blk_words + 3u) & ~3u; // words per table block (16-byte multiple)
     const uint32_t s0abs = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t info_abs = s0abs + wid * 256;
     const uint32_t tile_abs = s0abs + nwarps * 256 + wid * (LCT_STAGE_CHUNKS * 512);
     uint32_t* wrows = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(smem) + (size_t)nwarps * (256 + 4096)) +
-                      (size_t)wid * 3 * 32 * pitch;
-    uint32_t* fo = wrows + lane * pitch;
-    uint32_t* fl = fo + 32 * pitch;
-    uint32_t* fd = fl + 32 * pitch;
+                      (size_t)wid * 3 * blk_pad;
+    uint32_t* fo = wrows + lane * MF;
+    uint32_t* fl = fo + blk_pad;
+    uint32_t* fd = fl + blk_pad;
     const uint32_t base_mis = (uint32_t)((uintptr_t)base & 15);
     TdfaLoader L;
     L.gbase16 = reinterpret_cast<const uint4*>((uintptr_t)base & ~(uintptr_t)15);
@@ -3419,7 +3629,6 @@ __global__ void __launch_bounds__(1024, 1)
     L.tile_abs = tile_abs;
     L.rd_lane16 = lane << 4;
     const uint32_t sep_splat = cfg.sep[0] * 0x01010101u, quote_splat = cfg.quote * 0x01010101u;
-    const uint32_t invMF = MF > 1 ? 0xFFFFFFFFu / MF + 1 : 0;
     for (;;) {
         unsigned long long batch = 0;
         if (lane == 0)
@@ -3429,6 +3638,9 @@ __global__ void __launch_bounds__(1024, 1)
             break;
         const bool valid = batch + lane < n;
         const uint64_t i = batch + lane;
+        // zero the three row blocks (rows of failed / blank lines and unused columns are zero)
+        for (uint32_t k = lane; k < 3 * blk_pad / 4; k += 32)
+            reinterpret_cast<uint4*>(wrows)[k] = make_uint4(0, 0, 0, 0);
         uint32_t eo = 0, mis = 0, g0 = 0, nch = 0;
         int32_t endIdx = 0;
         if (valid) {
@@ -3441,24 +3653,18 @@ __global__ void __launch_bounds__(1024, 1)
             while (endIdx > 0) {
                 const uint32_t qlast = mis + (uint32_t)endIdx - 1; // frame position of the last byte
                 const uint4 vv = __ldg(L.gbase16 + g0 + (qlast >> 4));
-                const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
-                uint32_t blank = lc_eq_mask16(w, 0x20202020u) | lc_eq_mask16(w, 0x0D0D0D0Du);
-                const uint32_t hi = qlast & 15u;                         // last byte's slot in this chunk
-                const uint32_t lo = (qlast & ~15u) >= mis ? 0u : mis;    // first slot of the chunk that belongs to the line
-                uint32_t inside = ((hi == 15u) ? 0xFFFFu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-                const uint32_t keep = ~blank & inside;                   // non-blank bytes of the line in this chunk
+                const uint32_t blank = match16b(vv, 0x20202020u) | match16b(vv, 0x0D0D0D0Du);
+                const uint32_t hi = qlast & 15u;                      // last byte's slot in this chunk
+                const uint32_t lo = (qlast & ~15u) >= mis ? 0u : mis; // first slot of the chunk that belongs to the line
+                const uint32_t inside = ((hi == 15u) ? 0xFFFFu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                const uint32_t keep = ~blank & inside;                // non-blank bytes of the line in this chunk
                 if (keep) {
                     endIdx = (int32_t)((qlast & ~15u) + (31 - __clz(keep)) + 1 - mis);
                     break;
                 }
-                endIdx = (int32_t)((qlast & ~15u) + lo) - (int32_t)mis; // the whole part was blank: go on with the chunk before
+                endIdx = (int32_t)((qlast & ~15u) + lo) - (int32_t)mis; // all blank: go on with the chunk before
             }
             nch = endIdx > 0 ? (mis + (uint32_t)endIdx + 15) >> 4 : 0;
-            for (uint32_t k = 0; k < MF; ++k) {
-                fo[k] = 0;
-                fl[k] = 0;
-                fd[k] = 0;
-            }
         }
         sts_u64(info_abs + lane * 8, g0, nch);
         const uint32_t max_nch = __reduce_max_sync(0xFFFFFFFFu, nch);
@@ -3490,7 +3696,7 @@ __global__ void __launch_bounds__(1024, 1)
                     const uint32_t q0 = k * 16;
                     if (!started) {
                         // leading ' ' (:233-238): the first byte that is not a blank starts the record
-                        uint32_t nb = ~lc_eq_mask16(w, 0x20202020u) & 0xFFFFu;
+                        uint32_t nb = ~match16b(vv, 0x20202020u) & 0xFFFFu;
                         if (q0 < qb)
                             nb &= ~((1u << (qb - q0)) - 1u);
                         if (qe - q0 < 16)
@@ -3503,6 +3709,32 @@ __global__ void __launch_bounds__(1024, 1)
                         if (cfg.nkeys == 0) { // nothing to parse into: the line fails once it is known not to be blank
                             ok = false;
                             break;
+                        }
+                    }
+                    // ---- fast path: a chunk that lies wholly inside the record, holds no quote byte and is entered
+                    // outside a quoted field: only the separators matter and every one of them closes a plain field
+                    // (INITIAL / DATA transitions of the FSM, dq == 0).  Separator flags stay spread over the words
+                    // (bit 7 of each matching byte): no mask compaction, no per-byte state machine.
+                    if (q0 >= qb && q0 + 16 <= qe && (run.state == 0 || run.state == 2)) {
+                        const uint32_t fq = eq_bytes(w[0], quote_splat) | eq_bytes(w[1], quote_splat) |
+                                            eq_bytes(w[2], quote_splat) | eq_bytes(w[3], quote_splat);
+                        if (!fq) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint32_t f = eq_bytes(w[j], sep_splat);
+                                while (f) {
+                                    const uint32_t bit = (uint32_t)__ffs((int)f) - 1;
+                                    f &= f - 1;
+                                    const int lp = (int)(q0 + 4 * j + (bit >> 3)) - (int)mis; // the separator's offset
+                                    push((uint32_t)run.fs, (uint32_t)(lp - run.fs), 0u);
+                                    run.fs = lp + 1;
+                                }
+                            }
+                            run.fe = (int)(q0 + 16) - (int)mis;
+                            run.cur = q0 + 16;
+                            run.state = run.fe > run.fs ? 2 : 0;
+                            run.dq = 0;
+                            continue;
                         }
                     }
                     if (!lc_delim_chunk(run, w, q0, qb, qe, sep_splat, quote_splat, push)) {
@@ -3547,17 +3779,25 @@ __global__ void __launch_bounds__(1024, 1)
             }
         }
         __syncwarp();
+        // ---- the three [lines][MF] blocks leave as 16-byte vector copies (a batch starts at a multiple of 128 * MF
+        // bytes; the table bases are 16-byte aligned allocations)
         const uint64_t left = n - batch;
-        const uint32_t total = (uint32_t)(left < 32 ? left : 32) * MF;
-        uint32_t* go = f_off + batch * MF;
-        uint32_t* gl = f_len + batch * MF;
-        uint32_t* gd = f_dq + batch * MF;
-        for (uint32_t j = lane; j < total; j += 32) {
-            const uint32_t line = MF > 1 ? __umulhi(j, invMF) : j, k = j - line * MF;
-            const uint32_t at = line * pitch + k;
-            go[j] = wrows[at];
-            gl[j] = wrows[32 * pitch + at];
-            gd[j] = wrows[64 * pitch + at];
+        const uint32_t total = (uint32_t)(left < 32 ? left : 32) * MF; // words per table
+        uint32_t* gt[3] = {f_off + batch * MF, f_len + batch * MF, f_dq + batch * MF};
+#pragma unroll
+        for (int tb = 0; tb < 3; ++tb) {
+            const uint32_t* src = wrows + tb * blk_pad;
+            uint32_t* dst = gt[tb];
+            if ((((uintptr_t)dst) & 15u) == 0) {
+                const uint32_t nv = total >> 2;
+                for (uint32_t j = lane; j < nv; j += 32)
+                    reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(src)[j];
+                for (uint32_t j = (nv << 2) + lane; j < total; j += 32)
+                    dst[j] = src[j];
+            } else {
+                for (uint32_t j = lane; j < total; j += 32)
+                    dst[j] = src[j];
+            }
         }
         __syncwarp();
     }
@@ -3578,7 +3818,7 @@ void launch_delim(const DelimConfig& cfg, const uint8_t* d_base, const uint32_t*
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const size_t per_warp = 256 + 4096 + (size_t)3 * 32 * (cfg.max_fields | 1u) * 4;
+        const size_t per_warp = 256 + 4096 + (size_t)3 * ((32 * cfg.max_fields + 3u) & ~3u) * 4;
         uint32_t warps = (uint32_t)std::min<size_t>(32, (size_t)smem_max / per_warp);
         if (warps >= 8) {
             const size_t smem = per_warp * warps;

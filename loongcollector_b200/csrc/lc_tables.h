@@ -169,11 +169,16 @@ struct LcFast2Header {
 //   eof   u32 [nstates]            end of input: op-list index of the winning thread, LC_NONE_ENTRY = no match
 //   ops   u16 []                   op lists: [count, op...], op = dst << 8 | src ; src 0xFF = current position,
 //                                  0xFE = unset, else a register (copy).  List 0 is empty.
+//   skip  u32 [nstates+1]          run skipping: a state that every byte except at most two "exit" bytes maps back to
+//                                  itself without touching a register (the inside of [^"]*, .*, the dead state) can
+//                                  jump over a whole 16-byte chunk that holds none of its exit bytes.
+//                                  0 = not skippable; else LC_TDFA_SKIP | nexits << 16 | exit2 << 8 | exit1.
 #define LC_TDFA_MAGIC 0x4C435444u /* 'LCTD' */
 #define LC_TDFA_SLOW 0x00800000u
 #define LC_TDFA_SRC_POS 0xFFu
 #define LC_TDFA_SRC_UNSET 0xFEu
 #define LC_TDFA_MAX_REGS 62u
+#define LC_TDFA_SKIP 0x80000000u
 #define LC_TDFA_REBASE_ROOM 2048u /* window base + class table + blob header precede the (row-aligned) pair table */
 struct LcTdfaHeader {
     uint32_t magic;
@@ -192,6 +197,8 @@ struct LcTdfaHeader {
     uint32_t has_slow;
     uint32_t max_threads; // diagnostics
     uint32_t sink;        // index of the slow-path sink row (= nstates; t2 has nstates + 1 rows)
+    uint32_t off_skip;
+    uint32_t reserved2[3];
 };
 
 #ifdef __cplusplus

@@ -1878,12 +1878,28 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                     }
                 }
             std::vector<uint8_t> cls(byte_class, byte_class + 256);
+            // run skipping: states whose every byte but at most two loops back without an op (state 0 = dead: always)
+            std::vector<uint32_t> skip(ns + 1, 0);
+            for (uint32_t s = 0; s < ns; ++s) {
+                uint32_t nexit = 0, ex[2] = {0, 0};
+                for (uint32_t b = 0; b < 256 && nexit <= 2; ++b) {
+                    const uint32_t e = s ? t1[(size_t)s * ncl + byte_class[b]] : 0u;
+                    if (e != s) { // another state, or ops on the way
+                        if (nexit < 2)
+                            ex[nexit] = b;
+                        ++nexit;
+                    }
+                }
+                if (nexit <= 2)
+                    skip[s] = LC_TDFA_SKIP | nexit << 16 | ex[1] << 8 | ex[0];
+            }
             std::vector<uint8_t> tb(sizeof th, 0);
             put(tb, th.off_cls, cls);
             put(tb, th.off_t2, t2);
             put(tb, th.off_t1, t1);
             put(tb, th.off_eof, eof);
             put(tb, th.off_ops, ops);
+            put(tb, th.off_skip, skip);
             while (tb.size() % 16)
                 tb.push_back(0);
             th.total_bytes = (uint32_t)tb.size();

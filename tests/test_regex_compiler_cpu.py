@@ -347,3 +347,23 @@ def test_tdfa_table_invariants_the_kernel_relies_on():
                 dst, src = int(op) >> 8, int(op) & 0xFF
                 assert dst < h["nregs"] and (src in (0xFF, 0xFE) or src < h["nregs"])
     assert seen > 100 and slow > 5
+
+
+def test_tdfa_run_skipping_chunks_is_exact():
+    """States that loop on every byte but (at most) two exit bytes jump over whole 16-byte chunks without those bytes
+    (lc_tables.h: skip).  Fields of every length around the chunk size, exit bytes at every slot of a chunk, at every
+    alignment of the line -- against the oracle."""
+    pats = [r'"([^"]*)" (.*)', r'(\w+) "([^\\"]*)" (\d+)', r"\[([^\]]+)\] (.*)", r"(.*)", r'x(.*)y"([^"]*)"']
+    for pat in pats:
+        e, o = EmulRegex(pat), orc.Regex(pat)
+        assert e.supported and e.tdfa_info["states"] > 1, pat
+        cases = []
+        for n in list(range(0, 40)) + [47, 48, 49, 63, 64, 65, 100, 255]:
+            fill = ("ab/c?d=" * 40)[:n]
+            cases += [('"%s" tail %s' % (fill, fill)).encode(), ('GET "%s" 200' % fill).encode(),
+                      ("[%s] rest%s" % (fill, fill)).encode(), ("x%sy\"%s\"" % (fill, fill)).encode(),
+                      ('"%s\\" 1' % fill).encode(), ('"%s' % fill).encode()]
+        for v in cases:
+            want = o.full_match(v)
+            for mis in range(16):
+                assert e.full_match_tdfa(v, mis) == want, (pat, v, mis)
