@@ -664,3 +664,21 @@ def test_remove_last_incomplete_log_random_chunks_match_oracle(eng, mode):
         want = orc.remove_last_incomplete_log(buf, o_start, o_end, True)
         assert got == want, (mode, buf[-200:])
     assert eng.remove_last_incomplete_log(b"a\nb", start, end, False)[0] == 3
+
+
+def test_split_reports_too_large_beyond_2_pow_30_pieces(eng):
+    """The look-back payload keeps 30 bits of piece count: a buffer with more split chars than that must be refused
+    (LC_ERR_TOO_LARGE), not wrapped silently."""
+    import ctypes as C
+
+    import torch
+    lc = _lc()
+    n = (1 << 30) + 4096
+    d = torch.full((n,), 10, dtype=torch.uint8, device="cuda")
+    off = torch.empty(1024, dtype=torch.int32, device="cuda")
+    ln = torch.empty(1024, dtype=torch.int32, device="cuda")
+    got = C.c_uint64(0)
+    rc = lc.lib().lc_split_lines_dev(eng._h, C.c_void_p(d.data_ptr()), n, 10, C.c_void_p(off.data_ptr()),
+                                     C.c_void_p(ln.data_ptr()), 1024, C.byref(got))
+    assert rc == lc.capi.LC_ERR_TOO_LARGE, (rc, got.value)
+    del d
