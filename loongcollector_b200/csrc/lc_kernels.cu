@@ -261,7 +261,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 2 : 1)
 // chain of exposed latencies (ticket atomic -> loads -> scan barriers -> look-back round trips -> stores) and an SM holds
 // only two such blocks.  Here a block of 512 threads keeps looping over tickets: the ticket of the tile AFTER next is
 // requested and the 32 KiB of the NEXT tile are already on their way into registers while the current tile goes through
-// its scan, look-back and stores, so neither the atomic nor the loads are ever waited for in steady state.
+// its scan, look-back and stores, so the loads are never waited for in steady state.  Tiles are assigned statically
+// (block b takes tiles b, b + grid, b + 2 grid, ...; the grid is sized by occupancy so that every block is resident, which
+// is what the look-back's forward progress needs): pre-claimed dynamic tickets would make every tile wait for a tile its
+// own holder has not started yet -- measured: a fully serial chain, 10x slower.
 template <int THREADS, bool PROBE>
 __global__ void __launch_bounds__(THREADS, 2)
     split_persist_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
@@ -270,21 +273,18 @@ __global__ void __launch_bounds__(THREADS, 2)
                          unsigned long long* total_chars, SplitProbe pr) {
     constexpr int NW = THREADS / 32;
     __shared__ uint32_t s_cnt[NW], s_last[NW], s_start[NW];
-    __shared__ uint32_t s_tick[2], s_tot, s_tlast;
+    __shared__ uint32_t s_tot, s_tlast;
     __shared__ uint64_t s_prefix;
     __shared__ uint32_t s_qn;
     __shared__ uint32_t s_q[PROBE ? kProbeQueue : 1];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint4* vbuf = reinterpret_cast<const uint4*>(buf - shift);
     const uint64_t total_v = (uint64_t)len + shift; // virtual length including the alignment lead-in
-    if (tid == 0) {
-        s_tick[0] = atomicAdd(ticket, 1u);
-        s_tick[1] = atomicAdd(ticket, 1u);
+    if (tid == 0)
         s_qn = 0;
-    }
     __syncthreads();
-    uint32_t tile = s_tick[0], nxt = s_tick[1];
-    __syncthreads(); // everyone holds both tickets before the first iteration overwrites slot 0
+    (void)ticket;
+    uint32_t tile = blockIdx.x, nxt = blockIdx.x + gridDim.x;
     auto load_tile = [&](uint32_t t, uint4* v) {
         const uint64_t c0 = ((uint64_t)t * THREADS + tid) * 4;
 #pragma unroll
@@ -296,10 +296,7 @@ __global__ void __launch_bounds__(THREADS, 2)
     };
     uint4 v[4];
     load_tile(tile, v);
-    for (uint32_t it = 0; tile < ntiles; ++it) {
-        // the tile after next: its ticket is asked for now and read at the bottom of this iteration
-        if (tid == 0)
-            s_tick[it & 1] = atomicAdd(ticket, 1u);
+    while (tile < ntiles) {
         uint4 vn[4];
         load_tile(nxt, vn);
         const uint64_t vpos0 = ((uint64_t)tile * THREADS + tid) * 64;
@@ -420,7 +417,7 @@ __global__ void __launch_bounds__(THREADS, 2)
                 s_qn = 0;
         }
         tile = nxt;
-        nxt = s_tick[it & 1];
+        nxt += gridDim.x;
 #pragma unroll
         for (int r = 0; r < 4; ++r)
             v[r] = vn[r];
