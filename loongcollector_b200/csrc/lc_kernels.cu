@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "lc_exec.cuh"
 #include "lc_scan.cuh"
@@ -58,6 +59,79 @@ struct SplitProbe {
     uint8_t* flags;        // [line] bit0/1/2 = start / continue / end matches a prefix
 };
 constexpr uint32_t kProbeQueue = 4096;
+constexpr uint32_t kProbeTable = 2048; // u16 entries of a prefix DFA that is staged in shared memory (states x classes)
+
+// The prefix DFAs of the (up to three) patterns, staged in shared memory by every block of the split + probe pass: a
+// queued line is probed with three DEPENDENT look-ups per byte (byte -> class -> next state), which from global memory
+// costs a few hundred cycles per step and left a 35-step tail on every tile.
+struct ProbeSmem {
+    uint8_t cls[3][256];
+    uint16_t next[3][kProbeTable];
+    uint8_t acc[3][256];
+    uint32_t nc[3], start[3], staged[3];
+};
+
+__device__ __forceinline__ void probe_stage(const SplitProbe& pr, ProbeSmem& ps) {
+    for (int p = 0; p < 3; ++p) {
+        if (!pr.blob[p]) {
+            if (threadIdx.x == 0)
+                ps.staged[p] = 0;
+            continue;
+        }
+        const LcProgView v = lc_view(pr.blob[p]);
+        const uint32_t ns = v.h->pre_nstates, nc = v.h->nclasses;
+        const bool fits = ns * nc <= kProbeTable && ns <= 256;
+        if (threadIdx.x == 0) {
+            ps.nc[p] = nc;
+            ps.start[p] = v.h->pre_start;
+            ps.staged[p] = fits ? 1u : 0u;
+        }
+        if (!fits)
+            continue;
+        for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x)
+            ps.cls[p][k] = v.byte_class[k];
+        for (uint32_t k = threadIdx.x; k < ns * nc; k += blockDim.x)
+            ps.next[p][k] = v.pre_next[k];
+        for (uint32_t k = threadIdx.x; k < ns; k += blockDim.x)
+            ps.acc[p][k] = v.pre_acc[k];
+    }
+}
+
+__device__ __forceinline__ uint8_t probe_line_smem(const SplitProbe& pr, const ProbeSmem& ps,
+                                                   const uint8_t* __restrict__ s, uint32_t l) {
+    uint8_t f = 0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        if (!pr.blob[p])
+            continue;
+        if (!ps.staged[p]) {
+            if (lc_prefix_match(lc_view(pr.blob[p]), s, l))
+                f |= (uint8_t)(1u << p);
+            continue;
+        }
+        const uint32_t nc = ps.nc[p];
+        uint32_t st = ps.start[p];
+        bool hit = false, done = false;
+        for (uint32_t i = 0; i < l; ++i) {
+            const uint32_t e = ps.next[p][st * nc + ps.cls[p][s[i]]];
+            if (e == LC_PREFIX_ACCEPT) {
+                hit = true;
+                done = true;
+                break;
+            }
+            if (e == LC_PREFIX_DEAD) {
+                done = true;
+                break;
+            }
+            st = e;
+        }
+        if (!done)
+            hit = ps.acc[p][st] != 0;
+        if (hit)
+            f |= (uint8_t)(1u << p);
+    }
+    return f;
+}
 
 __device__ __forceinline__ uint8_t probe_line(const SplitProbe& pr, const uint8_t* __restrict__ s, uint32_t l) {
     uint8_t f = 0;
@@ -97,7 +171,7 @@ __device__ __forceinline__ uint32_t match16b(uint4 v, uint32_t splat) {
 // instructions, range checks only in the last tile, a 32-bit shuffle scan for the counts, and the "start of my first
 // line" taken from the nearest previous thread that holds a newline (ballot + one shuffle) instead of a max-scan.
 template <int THREADS, int LBW, bool PROBE>
-__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 2 : 1)
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS)
     split_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
                  uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap, volatile uint64_t* desc,
                  uint32_t* ticket, uint32_t ntiles, uint32_t* n_out, unsigned long long* total_chars, SplitProbe pr) {
@@ -111,11 +185,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 2 : 1)
     __shared__ uint32_t s_flag[LBW > 1 ? LBW : 1];
     __shared__ uint32_t s_qn;
     __shared__ uint32_t s_q[PROBE ? kProbeQueue : 1];
+    __shared__ typename std::conditional<PROBE, ProbeSmem, uint32_t>::type s_probe;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
         s_tile = atomicAdd(ticket, 1u);
         s_qn = 0;
     }
+    if constexpr (PROBE)
+        probe_stage(pr, s_probe);
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint4* vbuf = reinterpret_cast<const uint4*>(buf - shift);
@@ -246,12 +323,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 2 : 1)
         }
         *n_out = k;
     }
-    if (PROBE) {
+    if constexpr (PROBE) {
         __syncthreads(); // the queue is complete and this tile's line table entries are visible to the block
         const uint32_t qn = min(s_qn, kProbeQueue);
         for (uint32_t q = tid; q < qn; q += THREADS) {
             const uint32_t kk = s_q[q];
-            pr.flags[kk] = probe_line(pr, buf + out_off[kk], out_len[kk]);
+            pr.flags[kk] = probe_line_smem(pr, s_probe, buf + out_off[kk], out_len[kk]);
         }
     }
 }
@@ -440,14 +517,14 @@ static void launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_
     uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
     uint32_t splat = split_char * 0x01010101u;
     static const int cfg = [] {
-        const char* e = getenv("LC_B200_SPLIT_TILE_KB"); // A/B knob: 16 or 64 (descriptors are sized for 16)
+        const char* e = getenv("LC_B200_SPLIT_TILE_KB"); // A/B knob: 16, 32 or 64 (descriptors are sized for 16)
         int t = e ? atoi(e) : 64;
-        return t == 16 ? 16 : 64;
+        return (t == 16 || t == 32) ? t : 64;
     }();
     volatile uint64_t* desc = (volatile uint64_t*)d_desc;
     static const bool persist = [] {
-        const char* e = getenv("LC_B200_SPLIT_PERSIST"); // A/B knob: 0 = one block per tile
-        return !(e && !strcmp(e, "0"));
+        const char* e = getenv("LC_B200_SPLIT_PERSIST"); // A/B knob: 1 = persistent prefetching blocks (measured slower:
+        return e && !strcmp(e, "1");                     // C1 0.39 ms vs 0.26 ms -- half the resident threads per SM)
     }();
     if (persist) {
         constexpr int T = 512; // 32 KiB tiles (the descriptors are sized for 16 KiB tiles: enough)
@@ -477,6 +554,8 @@ static void launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_
             LC_SPLIT_LAUNCH(1024, 4);
         else
             LC_SPLIT_LAUNCH(1024, 1);
+    } else if (cfg == 32) {
+        LC_SPLIT_LAUNCH(512, 1);
     } else {
         if (wide)
             LC_SPLIT_LAUNCH(256, 4);
@@ -3716,16 +3795,14 @@ __global__ void __launch_bounds__(1024, 1)
                         const uint32_t fq = eq_bytes(w[0], quote_splat) | eq_bytes(w[1], quote_splat) |
                                             eq_bytes(w[2], quote_splat) | eq_bytes(w[3], quote_splat);
                         if (!fq) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint32_t f = eq_bytes(w[j], sep_splat);
-                                while (f) {
-                                    const uint32_t bit = (uint32_t)__ffs((int)f) - 1;
-                                    f &= f - 1;
-                                    const int lp = (int)(q0 + 4 * j + (bit >> 3)) - (int)mis; // the separator's offset
-                                    push((uint32_t)run.fs, (uint32_t)(lp - run.fs), 0u);
-                                    run.fs = lp + 1;
-                                }
+                            // ONE loop over the chunk's separators (16-bit mask): iteration i closes every lane's i-th
+                            // field of the chunk together (per-word loops ran with 1-2 active lanes: measured)
+                            uint32_t f = match16b(vv, sep_splat);
+                            while (f) {
+                                const int lp = (int)(q0 + (uint32_t)__ffs((int)f) - 1) - (int)mis; // the separator's offset
+                                f &= f - 1;
+                                push((uint32_t)run.fs, (uint32_t)(lp - run.fs), 0u);
+                                run.fs = lp + 1;
                             }
                             run.fe = (int)(q0 + 16) - (int)mis;
                             run.cur = q0 + 16;

@@ -661,7 +661,19 @@ void ProcessorParseRegexNative::EpilogueGroup(PipelineEventGroup& group, uint64_
                                               uint32_t G, LocalCounters& c) const {
     EventsContainer& events = group.MutableEvents();
     size_t wIdx = 0;
-    for (size_t rIdx = 0; rIdx < events.size(); ++rIdx) {
+    const size_t nev = events.size();
+    for (size_t rIdx = 0; rIdx < nev; ++rIdx) {
+        // the walk is bound by cache misses on the event objects and their contents arrays (one heap block each, touched
+        // once): pull the object 16 events ahead and its contents array 8 events ahead
+        if (rIdx + 16 < nev && events[rIdx + 16])
+            __builtin_prefetch(events[rIdx + 16].operator->(), 1, 1);
+        if (rIdx + 8 < nev && IsSupportedEvent(events[rIdx + 8])) {
+            const auto& rc = events[rIdx + 8].Cast<LogEvent>().RawContents();
+            if (!rc.empty()) {
+                __builtin_prefetch(rc.data(), 1, 1);
+                __builtin_prefetch(reinterpret_cast<const char*>(rc.data()) + 256, 1, 1);
+            }
+        }
         EventResult r{};
         const EventResult* rp = nullptr;
         const LogEvent::Content* src = nullptr;
@@ -745,7 +757,17 @@ void ProcessorParseRegexNative::ProcessBatch(PipelineEventGroup* groups, size_t 
                         size_t chunkSize = 0;
                         uint64_t total = 0;
                         uint64_t i = p.firstEv;
-                        for (const auto& e : groups[g].GetEvents()) {
+                        const EventsContainer& gev = groups[g].GetEvents();
+                        for (size_t x = 0; x < gev.size(); ++x) {
+                            const PipelineEventPtr& e = gev[x];
+                            // (cache misses on the event objects and their contents arrays: pull them in ahead)
+                            if (x + 16 < gev.size() && gev[x + 16])
+                                __builtin_prefetch(gev[x + 16].operator->(), 0, 1);
+                            if (x + 8 < gev.size() && IsSupportedEvent(gev[x + 8])) {
+                                const auto& rc = gev[x + 8].Cast<LogEvent>().RawContents();
+                                if (!rc.empty())
+                                    __builtin_prefetch(rc.data(), 0, 1);
+                            }
                             const LogEvent::Content* src =
                                 IsSupportedEvent(e) ? e.Cast<LogEvent>().FindContent(mSourceKey) : nullptr;
                             if (!src) {
