@@ -435,74 +435,75 @@ LC_HD void lc_delim_start(LcDelimRun& r, int32_t begin, uint32_t mis) {
 }
 
 // chunk = the 16 bytes at frame positions [q0, q0 + 16), restricted to [qb, qe).  Returns false on a parse error.
+//
+// Only separators and quotes ("specials") step the machine; the run of ordinary bytes in front of each special is one
+// step.  The step itself is table-driven and branch-free apart from the push: on the GPU the 32 lanes of a warp walk
+// 32 different lines, and a formulation with one code path per (state, byte kind) made the warp execute most paths for
+// every special (ncu: 1-6 active lanes on the hot instructions).  Entry (state * 2 + kind), kind 0 = separator,
+// 1 = quote:  bits 0-1 next state | bits 2-3 fe += | bit 4 push the column first | bit 5 dq-- before the push |
+// bit 6 error | bit 7 fs++ | bit 8 dq++.  After a push: dq = 0 and fs = the new fe.
+//   INITIAL  sep: push, fe+1 -> INITIAL          quote: fs++ -> QUOTE
+//   QUOTE    sep: fe+1 (part of the field)       quote: dq++, fe+1 -> DOUBLE_QUOTE
+//   DATA     sep: push, fe+1 -> INITIAL          quote: error
+//   DQUOTE   sep: dq--, push, fe+2 -> INITIAL    quote: fe+1 -> QUOTE (it was an escaped quote)
+#define LC_DELIM_T(next, dfe, push, dqdec, err, fsinc, dqinc)                                                           \
+    ((uint64_t)((next) | (dfe) << 2 | (push) << 4 | (dqdec) << 5 | (err) << 6 | (fsinc) << 7 | (dqinc) << 8))
 template <class Push>
 LC_HD bool lc_delim_chunk(LcDelimRun& r, const uint32_t w[4], uint32_t q0, uint32_t qb, uint32_t qe, uint32_t sep_splat,
                           uint32_t quote_splat, Push& push) {
-    uint32_t ms = lc_eq_mask16(w, sep_splat), mq = lc_eq_mask16(w, quote_splat);
-    uint32_t special = ms | mq;
+    const uint64_t T_LO = LC_DELIM_T(0, 1, 1, 0, 0, 0, 0) | LC_DELIM_T(1, 0, 0, 0, 0, 1, 0) << 16 |
+                          LC_DELIM_T(1, 1, 0, 0, 0, 0, 0) << 32 | LC_DELIM_T(3, 1, 0, 0, 0, 0, 1) << 48;
+    const uint64_t T_HI = LC_DELIM_T(0, 1, 1, 0, 0, 0, 0) | LC_DELIM_T(2, 0, 0, 0, 1, 0, 0) << 16 |
+                          LC_DELIM_T(0, 2, 1, 1, 0, 0, 0) << 32 | LC_DELIM_T(1, 1, 0, 0, 0, 0, 0) << 48;
+    const uint32_t ms = lc_eq_mask16(w, sep_splat);
+    uint32_t special = ms | lc_eq_mask16(w, quote_splat);
     if (q0 < qb)
         special &= ~((1u << (qb - q0)) - 1u);
     if (qe - q0 < 16)
         special &= (1u << (qe - q0)) - 1u;
     const uint32_t chunk_end = qe - q0 < 16 ? qe : q0 + 16;
-    for (;;) {
-        uint32_t next = chunk_end;
-        int b = -1;
-        if (special) {
+    int state = r.state, dq = r.dq, fs = r.fs, fe = r.fe;
+    uint32_t cur = r.cur, bad = 0;
+    while (special) {
 #if defined(__CUDA_ARCH__)
-            b = __ffs((int)special) - 1;
+        const int b = __ffs((int)special) - 1;
 #else
-            b = __builtin_ctz(special);
+        const int b = __builtin_ctz(special);
 #endif
-            special &= special - 1;
-            next = q0 + (uint32_t)b;
+        special &= special - 1;
+        const uint32_t next = q0 + (uint32_t)b;
+        const uint32_t gap = next - cur; // run of ordinary bytes in front of the special
+        bad |= (gap != 0 && state == 3) ? 1u : 0u;
+        state = (gap != 0 && state == 0) ? 2 : state;
+        fe += (int)gap;
+        cur = next + 1;
+        const uint32_t idx = (uint32_t)state * 2u + (((ms >> b) & 1u) ^ 1u); // a byte equal to both counts as separator
+        const uint32_t e = (uint32_t)((idx < 4 ? T_LO : T_HI) >> ((idx & 3u) * 16u)) & 0xFFFFu;
+        if (e & 0x10u) {
+            dq -= (int)((e >> 5) & 1u);
+            if (!bad)
+                push((uint32_t)fs, (uint32_t)(fe - fs), (uint32_t)dq);
+            dq = 0;
         }
-        const uint32_t gap = next - r.cur; // run of ordinary bytes
-        if (gap) {
-            if (r.state == 3)
-                return false;
-            if (r.state == 0)
-                r.state = 2;
-            r.fe += (int)gap;
-        }
-        if (b < 0) {
-            r.cur = chunk_end;
-            break;
-        }
-        r.cur = next + 1;
-        if (ms >> b & 1) { // separator
-            if (r.state == 1) {
-                r.fe++;
-            } else if (r.state == 3) {
-                r.state = 0;
-                r.dq--;
-                push((uint32_t)r.fs, (uint32_t)(r.fe - r.fs), (uint32_t)r.dq);
-                r.dq = 0;
-                r.fe += 2;
-                r.fs = r.fe;
-            } else {
-                r.state = 0;
-                push((uint32_t)r.fs, (uint32_t)(r.fe - r.fs), (uint32_t)r.dq);
-                r.dq = 0;
-                r.fs = ++r.fe;
-            }
-        } else { // quote (a byte equal to both counts as the separator, as in the per-byte machine)
-            if (r.state == 0) {
-                r.state = 1;
-                r.fs++;
-            } else if (r.state == 1) {
-                r.state = 3;
-                r.dq++;
-                r.fe++;
-            } else if (r.state == 2) {
-                return false;
-            } else {
-                r.state = 1;
-                r.fe++;
-            }
-        }
+        fe += (int)((e >> 2) & 3u);
+        dq += (int)((e >> 8) & 1u);
+        bad |= (e >> 6) & 1u;
+        fs = (e & 0x10u) ? fe : fs + (int)((e >> 7) & 1u);
+        state = (int)(e & 3u);
     }
-    return true;
+    {
+        const uint32_t gap = chunk_end - cur; // ordinary bytes behind the last special of the chunk
+        bad |= (gap != 0 && state == 3) ? 1u : 0u;
+        state = (gap != 0 && state == 0) ? 2 : state;
+        fe += (int)gap;
+        cur = chunk_end;
+    }
+    r.state = state;
+    r.dq = dq;
+    r.fs = fs;
+    r.fe = fe;
+    r.cur = cur;
+    return bad == 0;
 }
 
 // end of line: closes the last column; false = unterminated quote

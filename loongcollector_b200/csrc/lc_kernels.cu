@@ -3787,30 +3787,8 @@ __global__ void __launch_bounds__(1024, 1)
                             break;
                         }
                     }
-                    // ---- fast path: a chunk that lies wholly inside the record, holds no quote byte and is entered
-                    // outside a quoted field: only the separators matter and every one of them closes a plain field
-                    // (INITIAL / DATA transitions of the FSM, dq == 0).  Separator flags stay spread over the words
-                    // (bit 7 of each matching byte): no mask compaction, no per-byte state machine.
-                    if (q0 >= qb && q0 + 16 <= qe && (run.state == 0 || run.state == 2)) {
-                        const uint32_t fq = eq_bytes(w[0], quote_splat) | eq_bytes(w[1], quote_splat) |
-                                            eq_bytes(w[2], quote_splat) | eq_bytes(w[3], quote_splat);
-                        if (!fq) {
-                            // ONE loop over the chunk's separators (16-bit mask): iteration i closes every lane's i-th
-                            // field of the chunk together (per-word loops ran with 1-2 active lanes: measured)
-                            uint32_t f = match16b(vv, sep_splat);
-                            while (f) {
-                                const int lp = (int)(q0 + (uint32_t)__ffs((int)f) - 1) - (int)mis; // the separator's offset
-                                f &= f - 1;
-                                push((uint32_t)run.fs, (uint32_t)(lp - run.fs), 0u);
-                                run.fs = lp + 1;
-                            }
-                            run.fe = (int)(q0 + 16) - (int)mis;
-                            run.cur = q0 + 16;
-                            run.state = run.fe > run.fs ? 2 : 0;
-                            run.dq = 0;
-                            continue;
-                        }
-                    }
+                    // (one code path for every chunk: a separate fast path for quote-free chunks made the warp run
+                    //  both paths for nearly every chunk -- some lane always sits on a partial or quoted chunk)
                     if (!lc_delim_chunk(run, w, q0, qb, qe, sep_splat, quote_splat, push)) {
                         ok = false;
                         break;
