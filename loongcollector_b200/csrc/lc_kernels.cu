@@ -13,10 +13,13 @@
 //   delimiter  core/plugin/processor/ProcessorParseDelimiterNative.cpp:219-409, core/parser/DelimiterModeFsmParser.cpp:49-294
 #include "lc_kernels.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <type_traits>
+#include <vector>
 
 #include "lc_exec.cuh"
 #include "lc_scan.cuh"
@@ -170,12 +173,25 @@ __device__ __forceinline__ uint32_t match16b(uint4 v, uint32_t splat) {
 // 20 stall cycles per issue at barriers), so the code is kept lean: byte compares without the emulated SIMD-video
 // instructions, range checks only in the last tile, a 32-bit shuffle scan for the counts, and the "start of my first
 // line" taken from the nearest previous thread that holds a newline (ballot + one shuffle) instead of a max-scan.
-template <int THREADS, int LBW, bool PROBE>
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// TRACE (debug, LC_B200_SPLIT_TRACE=<file>): thread 0 of every block stamps %globaltimer at the phase boundaries into
+// trace[tile * 8 ..]: 0 block start, 1 ticket known, 2 own loads + masks done, 3 whole block scanned, 4 look-back done,
+// 5 stores issued, 6 end.
+template <int THREADS, int LBW, bool PROBE, bool TRACE = false>
 __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
     split_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
                  uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap, volatile uint64_t* desc,
-                 uint32_t* ticket, uint32_t ntiles, uint32_t* n_out, unsigned long long* total_chars, SplitProbe pr) {
+                 uint32_t* ticket, uint32_t ntiles, uint32_t* n_out, unsigned long long* total_chars, SplitProbe pr,
+                 uint64_t* trace = nullptr) {
     constexpr int NW = THREADS / 32;
+    uint64_t tr[7];
+    if (TRACE)
+        tr[0] = globaltimer_ns();
     __shared__ uint32_t s_cnt[NW];   // per warp: newline count, then its exclusive prefix inside the tile
     __shared__ uint32_t s_last[NW];  // per warp: end (offset + 1) of its last newline, 0 = none
     __shared__ uint32_t s_start[NW]; // per warp: start of the line that is open when the warp's bytes begin (0 = none in tile)
@@ -195,6 +211,8 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
         probe_stage(pr, s_probe);
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (TRACE)
+        tr[1] = globaltimer_ns();
     const uint4* vbuf = reinterpret_cast<const uint4*>(buf - shift);
     const uint64_t total_v = (uint64_t)len + shift; // virtual length including the alignment lead-in
     const uint64_t chunk0 = ((uint64_t)tile * THREADS + tid) * 4;
@@ -227,6 +245,8 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
     }
     const uint32_t cnt = __popcll(mk);
     const uint32_t last = mk ? (uint32_t)(vpos0 + (63 - __clzll((long long)mk)) + 1 - shift) : 0u;
+    if (TRACE)
+        tr[2] = globaltimer_ns() + (cnt >> 31);
     // ---- counts: inclusive warp scan; starts: nearest previous holder of a newline
     uint32_t inc = cnt;
 #pragma unroll
@@ -269,19 +289,24 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
         }
     }
     __syncthreads();
+    if (TRACE)
+        tr[3] = globaltimer_ns();
     const uint64_t tot = OpCountMax::make(s_tot, s_tlast);
     uint64_t tile_prefix;
     if (LBW > 1) {
         tile_prefix = lookback_block<OpCountMax, LBW>(desc, tile, tot, s_part, s_flag);
     } else {
         if (tid < 32) {
-            uint64_t p = lookback<OpCountMax>(desc, tile, tot);
+            uint64_t p = LBW < 0 ? lookback_deep<OpCountMax, (LBW < 0 ? -LBW : 1)>(desc, tile, tot)
+                                 : lookback<OpCountMax>(desc, tile, tot);
             if (tid == 0)
                 s_prefix = p;
         }
         __syncthreads();
         tile_prefix = s_prefix;
     }
+    if (TRACE)
+        tr[4] = globaltimer_ns() + (tile_prefix >> 63);
     if (tid == 0 && s_tot) // un-truncated count (the payload keeps 30 bits): > 2^30 pieces is an error
         atomicAdd(total_chars, (unsigned long long)s_tot);
     uint32_t k = (OpCountMax::count(tile_prefix) + s_cnt[wid] + (inc - cnt)) & 0x3FFFFFFFu;
@@ -323,12 +348,23 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
         }
         *n_out = k;
     }
+    if (TRACE)
+        tr[5] = globaltimer_ns() + (k >> 31);
     if constexpr (PROBE) {
         __syncthreads(); // the queue is complete and this tile's line table entries are visible to the block
         const uint32_t qn = min(s_qn, kProbeQueue);
         for (uint32_t q = tid; q < qn; q += THREADS) {
             const uint32_t kk = s_q[q];
             pr.flags[kk] = probe_line_smem(pr, s_probe, buf + out_off[kk], out_len[kk]);
+        }
+    }
+    if (TRACE) {
+        __syncthreads();
+        tr[6] = globaltimer_ns();
+        if (tid == 0) {
+            for (int q = 0; q < 7; ++q)
+                trace[(uint64_t)tile * 8 + q] = tr[q];
+            trace[(uint64_t)tile * 8 + 7] = blockIdx.x;
         }
     }
 }
@@ -504,8 +540,8 @@ __global__ void __launch_bounds__(THREADS, 2)
 static int split_lookback_warps() {
     static const int w = [] {
         const char* e = getenv("LC_B200_LOOKBACK_WARPS"); // A/B knob: 1 (default) = single-warp walk, 4 = block-wide
-        int t = e ? atoi(e) : 1;                          // (measured on C1: 4 is 4 % slower -- two more barriers per round)
-        return t == 4 ? 4 : 1;
+        int t = e ? atoi(e) : 1;                          // (measured on C1: 4 is 4 % slower -- two more barriers per
+        return t == 4 ? 4 : (t == -8 || t == -4) ? t : 1; // round); -4 / -8 = one warp, 4 / 8 descriptors per lane
     }();
     return w;
 }
@@ -546,12 +582,39 @@ static void launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_
     const uint64_t tile_bytes = (uint64_t)cfg * 1024;
     uint32_t ntiles = (uint32_t)((len + shift + tile_bytes - 1) / tile_bytes);
     const bool wide = split_lookback_warps() > 1;
+    const int deep = split_lookback_warps() < 0 ? -split_lookback_warps() : 0;
 #define LC_SPLIT_LAUNCH(T, W)                                                                                          \
     split_kernel<T, W, PROBE><<<ntiles, T, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap, desc, d_ticket, ntiles, \
                                                     d_n_out, d_total, pr)
+    if (const char* tf = getenv("LC_B200_SPLIT_TRACE")) { // debug: per-tile phase timestamps -> file (blocks the stream)
+        uint64_t* d_tr = nullptr;
+        cudaMalloc(&d_tr, (size_t)ntiles * 64);
+        cudaMemsetAsync(d_tr, 0, (size_t)ntiles * 64, st);
+        if (split_lookback_warps() == -8)
+            split_kernel<1024, -8, PROBE, true><<<ntiles, 1024, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
+                                                                         desc, d_ticket, ntiles, d_n_out, d_total, pr,
+                                                                         d_tr);
+        else
+            split_kernel<1024, 1, PROBE, true><<<ntiles, 1024, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
+                                                                        desc, d_ticket, ntiles, d_n_out, d_total, pr,
+                                                                        d_tr);
+        std::vector<uint64_t> h((size_t)ntiles * 8);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), d_tr, h.size() * 8, cudaMemcpyDeviceToHost);
+        cudaFree(d_tr);
+        if (FILE* f = fopen(tf, "wb")) {
+            fwrite(h.data(), 8, h.size(), f);
+            fclose(f);
+        }
+        return;
+    }
     if (cfg == 64) {
         if (wide)
             LC_SPLIT_LAUNCH(1024, 4);
+        else if (deep == 8)
+            LC_SPLIT_LAUNCH(1024, -8);
+        else if (deep == 4)
+            LC_SPLIT_LAUNCH(1024, -4);
         else
             LC_SPLIT_LAUNCH(1024, 1);
     } else if (cfg == 32) {
@@ -1813,25 +1876,29 @@ struct TdfaAbs {
 // (Tried and measured slower on C2: a power-of-two row pitch with the address formed as row | index * 4 -- the same
 // class pair of different states then always shares a bank; and storing both boundary fields under one predicate --
 // two instructions fewer per pair but more shared-memory wavefronts.)
-// UNC (A/B knob LC_B200_TDFA_STORE=uncond): both boundary stores are issued unconditionally -- a pair that sets no
-// register writes the position into the thread's no-op slot (offset 0 of regs_m2: the spare halfword in front of its
-// register file) -- which drops the two predicate set-ups per pair.
-#define LCS_PAIR(X, HI, POS)                                                                                           \
+// Pair step over the STAGED tables (tdfa_stage_blob re-encodes them for this loop): the class table holds class * 4,
+// a pair-table entry is  next_row_address << 16 | (register of the 2nd step) << 8 | (register of the 1st step)  (register
+// fields = byte offset of the register + 2, 0 = none).  With the row in the HIGH half the address of the next look-up is
+// one LEA.HI -- (entry >> 16) + index -- instead of a mask and an add, one instruction less on the dependent chain of
+// every pair: PRMT PRMT LDS.U8 LDS.U8 IMAD LEA.HI LDS + two predicated STS.U16 for capture boundaries.
+// ROWX = the address of the current row: `row` for the first pair of a chunk, (e_prev >> 16) afterwards.
+// UNC (A/B knob LC_B200_TDFA_STORE=uncond): both boundary stores are issued unconditionally (no-op slot at offset 0).
+#define LCS_PAIR(ROWX, X, HI, POS)                                                                                     \
     {                                                                                                                  \
         const uint32_t c0 = lds_u8(__byte_perm((X), t.cls, (HI) ? 0x7652 : 0x7650));                                   \
         const uint32_t c1 = lds_u8(__byte_perm((X), t.cls, (HI) ? 0x7653 : 0x7651));                                   \
-        const uint32_t e = lds_u32(row + ((c0 * t.ncls + c1) << 2));                                                   \
-        row = e & 0xFFFFu;                                                                                             \
+        const uint32_t e = lds_u32((ROWX) + (c0 * t.ncls + c1));                                                       \
         if (UNC) {                                                                                                     \
-            sts_u16(regs_m2 + (SLOW ? ((e >> 16) & 0x7Fu) : __byte_perm(e, 0, 0x4442)), (POS));                        \
-            sts_u16(regs_m2 + (e >> 24), (POS) + 1);                                                                   \
+            sts_u16(regs_m2 + (e & 0x7Fu), (POS));                                                                     \
+            sts_u16(regs_m2 + ((e >> 8) & 0x7Fu), (POS) + 1);                                                          \
         } else {                                                                                                       \
-            const uint32_t sa = e & 0x7F0000u, sb = e >> 24;                                                           \
+            const uint32_t sa = e & 0x7Fu, sb = e & 0x7F00u;                                                           \
             if (sa)                                                                                                    \
-                sts_u16(regs_m2 + __umulhi(sa, 0x10000u), (POS));                                                      \
+                sts_u16(regs_m2 + sa, (POS));                                                                          \
             if (sb)                                                                                                    \
-                sts_u16(regs_m2 + sb, (POS) + 1);                                                                      \
+                sts_u16(regs_m2 + (sb >> 8), (POS) + 1);                                                               \
         }                                                                                                              \
+        e_prev = e;                                                                                                    \
     }
 
 // Out-of-line redo of one chunk whose fast pass met an entry that sets several registers in one step: single steps
@@ -1862,13 +1929,13 @@ __device__ __noinline__ uint32_t tdfa_partial_chunk(const LcTdfaView v, const Td
     const uint32_t a = lo > qlo ? lo : qlo, b = lo + 16 < Qe ? lo + 16 : Qe;
     for (uint32_t q = a; q < b; q += 2) {
         const uint32_t b0 = lds_u8_v(caddr + (q - lo)), b1 = lds_u8_v(caddr + (q - lo) + 1);
-        const uint32_t e = lds_u32(row + ((lds_u8(t.cls | b0) * t.ncls + lds_u8(t.cls | b1)) << 2));
-        const uint32_t nrow = e & 0xFFFFu;
+        const uint32_t e = lds_u32(row + (lds_u8(t.cls | b0) * t.ncls + lds_u8(t.cls | b1))); // (staged encoding)
+        const uint32_t nrow = e >> 16;
         if (nrow == sink) {
             const uint32_t s1 = lc_tdfa_single(v, __umulhi(row - t.t2, t.inv_row), b0, q - mis, rg);
             row = t.t2 + t.row_bytes * lc_tdfa_single(v, s1, b1, q + 1 - mis, rg);
         } else {
-            const uint32_t sa = (e >> 16) & 0x7Fu, sb = e >> 24;
+            const uint32_t sa = e & 0x7Fu, sb = (e >> 8) & 0x7Fu;
             if (sa)
                 sts_u16(regs_m2 + sa, q - mis);
             if (sb)
@@ -1947,14 +2014,16 @@ __device__ __forceinline__ uint32_t tdfa_walk_lines(const LcTdfaView& v, const T
                 }
                 const uint32_t pos0 = k * 16 - mis;
                 const uint32_t row_in = row;
-                LCS_PAIR(vv.x, 0, pos0 + 0)
-                LCS_PAIR(vv.x, 1, pos0 + 2)
-                LCS_PAIR(vv.y, 0, pos0 + 4)
-                LCS_PAIR(vv.y, 1, pos0 + 6)
-                LCS_PAIR(vv.z, 0, pos0 + 8)
-                LCS_PAIR(vv.z, 1, pos0 + 10)
-                LCS_PAIR(vv.w, 0, pos0 + 12)
-                LCS_PAIR(vv.w, 1, pos0 + 14)
+                uint32_t e_prev;
+                LCS_PAIR(row, vv.x, 0, pos0 + 0)
+                LCS_PAIR(e_prev >> 16, vv.x, 1, pos0 + 2)
+                LCS_PAIR(e_prev >> 16, vv.y, 0, pos0 + 4)
+                LCS_PAIR(e_prev >> 16, vv.y, 1, pos0 + 6)
+                LCS_PAIR(e_prev >> 16, vv.z, 0, pos0 + 8)
+                LCS_PAIR(e_prev >> 16, vv.z, 1, pos0 + 10)
+                LCS_PAIR(e_prev >> 16, vv.w, 0, pos0 + 12)
+                LCS_PAIR(e_prev >> 16, vv.w, 1, pos0 + 14)
+                row = e_prev >> 16;
                 if (SLOW && row == sink) // some step set several registers: redo this chunk step by step
                     row = t.t2 + t.row_bytes * tdfa_chunk_slow(v, __umulhi(row_in - t.t2, t.inv_row), vv, pos0, rg);
             }
@@ -2026,14 +2095,16 @@ __device__ __forceinline__ uint32_t tdfa_walk_lines_pf(const LcTdfaView& v, cons
                     const uint4 vv = lds_u128_v(caddr);
                     const uint32_t pos0 = k * 16 - mis;
                     const uint32_t row_in = row;
-                    LCS_PAIR(vv.x, 0, pos0 + 0)
-                    LCS_PAIR(vv.x, 1, pos0 + 2)
-                    LCS_PAIR(vv.y, 0, pos0 + 4)
-                    LCS_PAIR(vv.y, 1, pos0 + 6)
-                    LCS_PAIR(vv.z, 0, pos0 + 8)
-                    LCS_PAIR(vv.z, 1, pos0 + 10)
-                    LCS_PAIR(vv.w, 0, pos0 + 12)
-                    LCS_PAIR(vv.w, 1, pos0 + 14)
+                    uint32_t e_prev;
+                    LCS_PAIR(row, vv.x, 0, pos0 + 0)
+                    LCS_PAIR(e_prev >> 16, vv.x, 1, pos0 + 2)
+                    LCS_PAIR(e_prev >> 16, vv.y, 0, pos0 + 4)
+                    LCS_PAIR(e_prev >> 16, vv.y, 1, pos0 + 6)
+                    LCS_PAIR(e_prev >> 16, vv.z, 0, pos0 + 8)
+                    LCS_PAIR(e_prev >> 16, vv.z, 1, pos0 + 10)
+                    LCS_PAIR(e_prev >> 16, vv.w, 0, pos0 + 12)
+                    LCS_PAIR(e_prev >> 16, vv.w, 1, pos0 + 14)
+                    row = e_prev >> 16;
                     if (SLOW && row == sink)
                         row = t.t2 + t.row_bytes * tdfa_chunk_slow(v, __umulhi(row_in - t.t2, t.inv_row), vv, pos0, rg);
                 } else if ((k == 0 && has_head) || (k == k_tail && has_tail)) {
@@ -2062,12 +2133,17 @@ __device__ __forceinline__ void tdfa_stage_blob(uint8_t* g_cls, uint32_t cls_abs
     const uint32_t t2 = cls_abs + 256 + v.h->off_t2;
     if (t2 + (v.h->nstates + 1) * v.h->row_bytes > 65535u)
         __trap(); // rows could not be addressed with 16 bits: the host must not select this kernel
+    if (v.h->ncls > 63)
+        __trap(); // class * 4 must fit the byte-wide staged class table
     for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x)
-        g_cls[k] = v.cls[k];
+        g_cls[k] = (uint8_t)(v.cls[k] * 4); // pre-multiplied: c0 * ncls + c1 is then the BYTE offset of the entry
     uint32_t* t2w = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(g_blob) + v.h->off_t2);
     const uint32_t nent = (v.h->nstates + 1) * (v.h->row_bytes / 4);
-    for (uint32_t k = threadIdx.x; k < nent; k += blockDim.x)
-        t2w[k] += t2;
+    for (uint32_t k = threadIdx.x; k < nent; k += blockDim.x) {
+        // blob entry: row offset | reg of step 1 << 16 | slow << 23 | reg of step 2 << 24  ->  the loop's encoding
+        const uint32_t e = t2w[k];
+        t2w[k] = ((e & 0xFFFFu) + t2) << 16 | ((e >> 24) & 0x7Fu) << 8 | ((e >> 16) & 0x7Fu);
+    }
 }
 
 template <bool SLOW, bool UNC, bool PF>

@@ -162,6 +162,65 @@ __device__ __forceinline__ uint64_t lookback(volatile uint64_t* desc, uint32_t t
     return prefix;
 }
 
+// Deep variant: every lane holds D consecutive descriptors (D independent loads in flight), so one L2 round trip covers
+// 32 * D predecessors -- with D = 8 that is more than the tiles that are resident at once (2 x 148 blocks), i.e. the
+// nearest INCLUSIVE prefix is inside the first window.  Lanes do not spin on descriptors that lie beyond the nearest
+// inclusive one; a window is re-polled only while a not-yet-published tile sits in front of it.
+template <class Op, int D>
+__device__ __forceinline__ uint64_t lookback_deep(volatile uint64_t* desc, uint32_t tile, uint64_t aggregate) {
+    const int lane = threadIdx.x & 31;
+    if (tile == 0) {
+        if (lane == 0)
+            desc[0] = kFlagInclusive | (aggregate & kPayloadMask);
+        return Op::identity();
+    }
+    if (lane == 0)
+        desc[tile] = kFlagAggregate | (aggregate & kPayloadMask);
+    uint64_t prefix = Op::identity();
+    int64_t base = (int64_t)tile - 1;
+    for (;;) {
+        uint64_t d[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const int64_t idx = base - (lane * D + j);
+            d[j] = idx >= 0 ? ld_desc(desc + idx) : (kFlagInclusive | Op::identity());
+        }
+        uint64_t r = Op::identity();
+        bool found = false, blocked = false;
+#pragma unroll
+        for (int j = 0; j < D; ++j) { // nearest first; stop at the first inclusive or unpublished descriptor
+            const uint32_t fl = (uint32_t)(d[j] >> 62);
+            if (!found && !blocked) {
+                if (fl == 0) {
+                    blocked = true;
+                } else {
+                    r = Op::combine(d[j] & kPayloadMask, r);
+                    found = fl == 2;
+                }
+            }
+        }
+        const unsigned incl = __ballot_sync(0xFFFFFFFFu, found), blk = __ballot_sync(0xFFFFFFFFu, blocked);
+        const int fi = incl ? (__ffs(incl) - 1) : 32, bi = blk ? (__ffs(blk) - 1) : 32;
+        if (bi < fi)
+            continue; // an unpublished tile in front of the nearest inclusive prefix: poll the window again
+        if (lane > fi)
+            r = Op::identity();
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { // ordered reduction: higher lanes are EARLIER tiles
+            const uint64_t t = shfl_down64(r, s);
+            if (lane + s < 32)
+                r = Op::combine(t, r);
+        }
+        prefix = Op::combine(shfl64(r, 0), prefix);
+        if (incl)
+            break;
+        base -= 32 * D;
+    }
+    if (lane == 0)
+        desc[tile] = kFlagInclusive | (Op::combine(prefix, aggregate) & kPayloadMask);
+    return prefix;
+}
+
 // Block-cooperative look-back: ALL threads of the block call (uniform control flow); the first WARPS warps poll
 // WARPS * 32 predecessors per round.  Why: a tile's walk ends at the nearest predecessor that already holds an
 // INCLUSIVE prefix, and every predecessor that is itself still walking only offers its aggregate -- so the faster the
