@@ -97,6 +97,7 @@ struct lc_engine {
     DevBuf in, ev_off, ev_len, out_a, out_b, out_c, out_d, out_e;
     DevBuf lines_off, lines_len, flags, state, cnt, pos, lab_sizes, lab_off, lab, order;
     DevBuf desc;   // look-back descriptors (3 regions)
+    DevBuf split_scratch; // masks + per-tile counts of the three-pass split (lck::split_scratch_bytes)
     DevBuf small;  // tickets + counters: [0..3] u32 tickets, +16: u32 n_out, +32: u64 total, +64: u64 counters[2]
     void* h_small = nullptr; // pinned mirror of `small`
     std::unordered_map<uint64_t, void*> blobs; // regex id * 4 + layout -> device blob
@@ -315,7 +316,7 @@ void lc_engine_destroy(lc_engine_t* e) {
         cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->in, &e->ev_off, &e->ev_len, &e->out_a, &e->out_b, &e->out_c, &e->out_d, &e->out_e,
                       &e->lines_off, &e->lines_len, &e->flags, &e->state, &e->cnt, &e->pos, &e->lab_sizes,
-                      &e->lab_off, &e->lab, &e->order, &e->desc, &e->small};
+                      &e->lab_off, &e->lab, &e->order, &e->desc, &e->small, &e->split_scratch};
     for (DevBuf* b : bufs)
         b->release();
     for (auto& kv : e->blobs)
@@ -439,9 +440,10 @@ int lc_split_lines_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, uint8
         return rc;
     Small* ds = e->small.as<Small>();
     uint32_t cap32 = cap > 0x3FFFFFFFull ? 0x3FFFFFFFu : (uint32_t)cap;
-    lck::launch_split(d_buf, (uint32_t)len, split_char, d_out_off, d_out_len, cap32, plan.r[0], &ds->tickets[0],
-                      &ds->n_out, &ds->total_chars, e->stream);
-    e->launches++;
+    CU_TRY(e->split_scratch.ensure(lck::split_scratch_bytes(len, false)));
+    e->launches += lck::launch_split(d_buf, (uint32_t)len, split_char, d_out_off, d_out_len, cap32, plan.r[0],
+                                     &ds->tickets[0], &ds->n_out, &ds->total_chars, e->split_scratch.as<uint64_t>(),
+                                     e->stream);
     CU_TRY(cudaGetLastError());
     Small* hs = (Small*)e->h_small;
     CU_TRY(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, e->stream));
@@ -1394,13 +1396,28 @@ int lc_multiline_split_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, c
             rc = prep_desc(e, lck::split_tiles(len, shift), ftiles, ftiles, plan);
             if (rc)
                 return rc;
-            lck::launch_split_probe(cfg, d_buf, (uint32_t)len, e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(),
-                                    e->flags.as<uint8_t>(), (uint32_t)lcap, plan.r[0], &ds->tickets[0], &ds->n_out,
-                                    &ds->total_chars, e->stream);
-            lck::launch_ml_fused(cfg, e->flags.as<uint8_t>(), e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(),
-                                 &ds->n_out, (uint32_t)lcap, (uint32_t)len, d_out_off, d_out_len, d_out_flags, cap,
-                                 plan.r[1], plan.r[2], &ds->tickets[1], ds->counters, &ds->total, e->stream);
-            e->launches += 2;
+            CU_TRY(e->split_scratch.ensure(lck::split_scratch_bytes(len, true)));
+            e->launches += lck::launch_split_probe(cfg, d_buf, (uint32_t)len, e->lines_off.as<uint32_t>(),
+                                                   e->lines_len.as<uint32_t>(), e->flags.as<uint8_t>(), (uint32_t)lcap,
+                                                   plan.r[0], &ds->tickets[0], &ds->n_out, &ds->total_chars,
+                                                   e->split_scratch.as<uint64_t>(), e->stream) - 1;
+            static const bool ml_lookback = [] {
+                const char* v = getenv("LC_B200_ML"); // A/B knob: "lookback" = ml_fused_kernel (two chained look-backs)
+                return v && !strcmp(v, "lookback");
+            }();
+            if (ml_lookback) {
+                lck::launch_ml_fused(cfg, e->flags.as<uint8_t>(), e->lines_off.as<uint32_t>(),
+                                     e->lines_len.as<uint32_t>(), &ds->n_out, (uint32_t)lcap, (uint32_t)len, d_out_off,
+                                     d_out_len, d_out_flags, cap, plan.r[1], plan.r[2], &ds->tickets[1], ds->counters,
+                                     &ds->total, e->stream);
+                e->launches += 2;
+            } else {
+                CU_TRY(e->state.ensure((size_t)lck::ml_pass_tiles(lcap) * 32 + 64));
+                e->launches += 1 + lck::launch_ml_passes(cfg, e->flags.as<uint8_t>(), e->lines_off.as<uint32_t>(),
+                                                         e->lines_len.as<uint32_t>(), &ds->n_out, (uint32_t)lcap,
+                                                         (uint32_t)len, d_out_off, d_out_len, d_out_flags, cap,
+                                                         e->state.as<uint64_t>(), ds->counters, &ds->total, e->stream);
+            }
             CU_TRY(cudaGetLastError());
             CU_TRY(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, e->stream));
             CU_TRY(cudaStreamSynchronize(e->stream));
@@ -1432,10 +1449,12 @@ int lc_multiline_split_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, c
         rc = prep_desc(e, lck::split_tiles(len, shift), 0, 0, plan);
         if (rc)
             return rc;
-        lck::launch_split(d_buf, (uint32_t)len, '\n', e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(),
-                          (uint32_t)(lcap > 0x3FFFFFFFull ? 0x3FFFFFFFull : lcap), plan.r[0], &ds->tickets[0],
-                          &ds->n_out, &ds->total_chars, e->stream);
-        e->launches++;
+        CU_TRY(e->split_scratch.ensure(lck::split_scratch_bytes(len, false)));
+        e->launches += lck::launch_split(d_buf, (uint32_t)len, '\n', e->lines_off.as<uint32_t>(),
+                                         e->lines_len.as<uint32_t>(),
+                                         (uint32_t)(lcap > 0x3FFFFFFFull ? 0x3FFFFFFFull : lcap), plan.r[0],
+                                         &ds->tickets[0], &ds->n_out, &ds->total_chars,
+                                         e->split_scratch.as<uint64_t>(), e->stream);
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaMemcpyAsync(hs, ds, sizeof(Small), cudaMemcpyDeviceToHost, e->stream));
         CU_TRY(cudaStreamSynchronize(e->stream));
@@ -1557,9 +1576,11 @@ int lc_remove_last_incomplete_log_dev(lc_engine_t* e, const uint8_t* d_buf, uint
         rc = prep_desc(e, lck::split_tiles(len, shift), 0, 0, plan);
         if (rc)
             return rc;
-        lck::launch_split_probe(cfg, d_buf, (uint32_t)len, e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(),
-                                e->flags.as<uint8_t>(), (uint32_t)lcap, plan.r[0], &ds->tickets[0], &ds->n_out,
-                                &ds->total_chars, e->stream);
+        CU_TRY(e->split_scratch.ensure(lck::split_scratch_bytes(len, true)));
+        e->launches += lck::launch_split_probe(cfg, d_buf, (uint32_t)len, e->lines_off.as<uint32_t>(),
+                                               e->lines_len.as<uint32_t>(), e->flags.as<uint8_t>(), (uint32_t)lcap,
+                                               plan.r[0], &ds->tickets[0], &ds->n_out, &ds->total_chars,
+                                               e->split_scratch.as<uint64_t>(), e->stream) - 1;
         lck::launch_last_record(e->flags.as<uint8_t>(), e->lines_off.as<uint32_t>(), e->lines_len.as<uint32_t>(),
                                 &ds->n_out, (uint32_t)lcap, (uint32_t)len, start != nullptr, end != nullptr,
                                 ds->counters, e->stream);

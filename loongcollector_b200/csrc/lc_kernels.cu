@@ -56,6 +56,7 @@ __device__ __forceinline__ uint32_t match16(uint4 v, uint32_t splat) {
 // queue in shared memory and are probed DENSELY, one thread per queued line, after the tile's lines are written --
 // otherwise a warp in which a single lane owns a 35-step start line would idle its other 31 lanes for 35 steps.
 struct SplitProbe {
+    uint32_t any_first[8]; // union of first[]: bytes that can start a match of any pattern
     const void* blob[3];   // device blobs of the start / continue / end patterns (nullptr = not configured)
     uint32_t first[3][8];  // per pattern: bit b set <=> a line whose first byte is b can match (prefix DFA, host-built)
     uint32_t empty_flags;  // flags of an empty line (patterns that match the empty prefix)
@@ -369,71 +370,260 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
     }
 }
 
-// ---- persistent variant: tiles in flight behind the look-back ---------------------------------------------------------
-// ncu of split_kernel<1024>: 35 stall cycles per issued instruction at barriers, DRAM 28 % busy -- a block's life is a
-// chain of exposed latencies (ticket atomic -> loads -> scan barriers -> look-back round trips -> stores) and an SM holds
-// only two such blocks.  Here a block of 512 threads keeps looping over tickets: the ticket of the tile AFTER next is
-// requested and the 32 KiB of the NEXT tile are already on their way into registers while the current tile goes through
-// its scan, look-back and stores, so the loads are never waited for in steady state.  Tiles are assigned statically
-// (block b takes tiles b, b + grid, b + 2 grid, ...; the grid is sized by occupancy so that every block is resident, which
-// is what the look-back's forward progress needs): pre-claimed dynamic tickets would make every tile wait for a tile its
-// own holder has not started yet -- measured: a fully serial chain, 10x slower.
-template <int THREADS, bool PROBE>
-__global__ void __launch_bounds__(THREADS, 2)
-    split_persist_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
-                         uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap,
-                         volatile uint64_t* desc, uint32_t* ticket, uint32_t ntiles, uint32_t* n_out,
-                         unsigned long long* total_chars, SplitProbe pr) {
-    constexpr int NW = THREADS / 32;
-    __shared__ uint32_t s_cnt[NW], s_last[NW], s_start[NW];
-    __shared__ uint32_t s_tot, s_tlast;
-    __shared__ uint64_t s_prefix;
-    __shared__ uint32_t s_qn;
-    __shared__ uint32_t s_q[PROBE ? kProbeQueue : 1];
+// ---- three-pass split: masks -> tile scan -> emission ------------------------------------------------------------------
+// What the single-pass kernel above cannot get around (measured with LC_B200_SPLIT_TRACE, three restructurings tried:
+// persistent + prefetched tiles, a scanner warp beside the byte work, two tiles of slack, 256-descriptor walks): lines
+// must be numbered in buffer order, so with a decoupled look-back a tile finishes only after EVERY earlier tile has
+// published its count, and the per-tile service time has a heavy tail (mask work p50 3.5 us, p90 6.7, max 14 us with
+// two 1024-thread blocks on an SM).  296 resident tiles wait for the slowest of them, every generation; all variants
+// ended at 8 us per 64 KiB tile = 2 TB/s.  The order constraint only concerns the NUMBERS, though, not the bytes:
+//   pass 1  split_mask_kernel   reads the buffer once, fully coalesced (one 512-byte row per load instruction), and
+//                               writes one mask bit per byte (len/8 bytes) plus {count, end of last newline} per tile;
+//                               tiles are independent -- no descriptor, no ticket, no waiting;
+//   pass 2  split_scan_kernel   one block turns the per-tile pairs into exclusive prefixes (8 K tiles for 512 MiB);
+//   pass 3  split_emit_kernel   reads the MASKS (1/8 of the bytes, mostly still in L2), numbers the lines of a tile from
+//                               its prefix and writes the table.
+// Traffic: len + 2 * len/8 instead of len; in exchange no pass ever waits for another block.  With per-line probes (the
+// multiline front half) pass 1 also records, per newline, whether the byte after it can start a match of any pattern
+// (a second bit per byte), so that pass 3 neither re-reads line heads from DRAM for the first-byte filter nor probes
+// the ~95 % of lines that cannot match.
+constexpr uint32_t kSplitTileChunks = 4096; // 16-byte chunks per tile (64 KiB, 1024 threads x 4)
+
+__device__ __forceinline__ uint32_t match16c(uint4 v, uint32_t splat) {
+    constexpr uint32_t M0 = (1u << 25) | (1u << 18) | (1u << 11) | (1u << 4), M4 = M0 << 4;
+    // bit 8j+7 of a word's marks times 2^(25+C-7j) lands on bit 32+C+j; all 16 partial products fall on distinct bits,
+    // so the high word of the product holds the word's nibble at C..C+3 exactly (no carries)
+    const uint32_t p0 = (__umulhi(eq_bytes(v.x, splat), M0) & 0x0Fu) | (__umulhi(eq_bytes(v.y, splat), M4) & 0xF0u);
+    const uint32_t p1 = (__umulhi(eq_bytes(v.z, splat), M0) & 0x0Fu) | (__umulhi(eq_bytes(v.w, splat), M4) & 0xF0u);
+    return p0 | (p1 << 8);
+}
+
+template <bool PROBE>
+__global__ void __launch_bounds__(1024, 2)
+    split_mask_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
+                      void* __restrict__ masks /* u16 (PROBE: u32 = newline | candidate << 16) per chunk */,
+                      uint64_t* __restrict__ agg /* [tile] */, uint64_t* __restrict__ wagg /* [tile][warp] */,
+                      SplitProbe pr) {
+    __shared__ uint32_t s_cnt, s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    if (tid == 0)
+        s_cnt = s_last = 0;
+    __syncthreads();
     const uint4* vbuf = reinterpret_cast<const uint4*>(buf - shift);
     const uint64_t total_v = (uint64_t)len + shift; // virtual length including the alignment lead-in
-    if (tid == 0)
-        s_qn = 0;
-    __syncthreads();
-    (void)ticket;
-    uint32_t tile = blockIdx.x, nxt = blockIdx.x + gridDim.x;
-    auto load_tile = [&](uint32_t t, uint4* v) {
-        const uint64_t c0 = ((uint64_t)t * THREADS + tid) * 4;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            v[r] = make_uint4(0, 0, 0, 0);
-            if (t < ntiles && (c0 + r) * 16 < total_v)
-                v[r] = __ldg(vbuf + c0 + r);
-        }
-    };
+    const uint64_t c0 = (uint64_t)tile * kSplitTileChunks + (uint32_t)wid * 128 + lane; // row r: chunk c0 + 32 r
+    const bool full = ((uint64_t)(tile + 1) * kSplitTileChunks * 16 <= total_v) && !(tile == 0 && shift);
     uint4 v[4];
-    load_tile(tile, v);
-    while (tile < ntiles) {
-        uint4 vn[4];
-        load_tile(nxt, vn);
-        const uint64_t vpos0 = ((uint64_t)tile * THREADS + tid) * 64;
-        const bool full = ((uint64_t)(tile + 1) * THREADS * 64 <= total_v) && !(tile == 0 && shift);
-        uint64_t mk = 0;
+    uint32_t m[4];
+    if (full) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            v[r] = __ldg(vbuf + c0 + 32 * r);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            m[r] = match16c(v[r], splat);
+    } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            uint32_t m = match16b(v[r], splat);
-            if (!full) {
-                const uint64_t vpos = vpos0 + (uint64_t)r * 16;
-                if (vpos >= total_v)
-                    m = 0;
-                else {
-                    if (vpos == 0 && shift)
-                        m &= ~((1u << shift) - 1u);
-                    const uint64_t rem = total_v - vpos;
-                    if (rem < 16)
-                        m &= (1u << rem) - 1u;
+            const uint64_t vpos = (c0 + 32 * r) * 16;
+            m[r] = 0;
+            v[r] = make_uint4(0, 0, 0, 0);
+            if (vpos < total_v) {
+                v[r] = __ldg(vbuf + c0 + 32 * r);
+                m[r] = match16c(v[r], splat);
+                if (vpos == 0 && shift) // alignment lead-in bytes in front of the buffer (shift < 16)
+                    m[r] &= ~((1u << shift) - 1u);
+                if (total_v - vpos < 16)
+                    m[r] &= (1u << (total_v - vpos)) - 1u;
+            }
+        }
+    }
+    uint32_t last = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (m[r]) // rows ascend, so the last hit wins
+            last = (uint32_t)((c0 + 32 * r) * 16 + (31 - __clz(m[r])) + 1 - shift);
+    const uint32_t cnt = __popc(m[0] | (m[1] << 16)) + __popc(m[2] | (m[3] << 16));
+    if constexpr (PROBE) {
+        uint32_t* mc = reinterpret_cast<uint32_t*>(masks);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint32_t c16 = 0, mm = m[r];
+            while (mm) {
+                const uint32_t b = __ffs(mm) - 1;
+                mm &= mm - 1;
+                if (b == 15) { // the next byte lives in another chunk: leave the decision to the probe
+                    c16 |= 1u << 15;
+                } else {
+                    const uint32_t i = (b + 1) >> 2;
+                    const uint32_t w = i < 2 ? (i == 0 ? v[r].x : v[r].y) : (i == 2 ? v[r].z : v[r].w);
+                    const uint32_t nb = (w >> (8 * ((b + 1) & 3))) & 0xFFu;
+                    c16 |= ((pr.any_first[nb >> 5] >> (nb & 31)) & 1u) << b;
                 }
             }
-            mk |= (uint64_t)m << (16 * r);
+            mc[c0 + 32 * r] = m[r] | (c16 << 16);
         }
+    } else {
+        uint16_t* m16 = reinterpret_cast<uint16_t*>(masks);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            m16[c0 + 32 * r] = (uint16_t)m[r];
+    }
+    const uint32_t wc = __reduce_add_sync(0xFFFFFFFFu, cnt), wl = __reduce_max_sync(0xFFFFFFFFu, last);
+    if (lane == 0) {
+        wagg[(uint64_t)tile * 32 + wid] = ((uint64_t)wc << 32) | wl; // the warp's 2 KiB: pass 3 needs no block scan
+        if (wc) {
+            atomicAdd(&s_cnt, wc);
+            atomicMax(&s_last, wl);
+        }
+    }
+    __syncthreads();
+    if (tid == 0)
+        agg[tile] = ((uint64_t)s_cnt << 32) | s_last;
+}
+
+// exclusive {sum of counts, max of ends} over the tiles, in tile order.  One block: every thread folds a contiguous run
+// of tiles (independent loads), ONE block scan over the 1024 runs, then the thread writes the prefixes of its run.
+__global__ void __launch_bounds__(1024)
+    split_scan_kernel(const uint64_t* __restrict__ agg, uint32_t ntiles, uint64_t* __restrict__ prefix,
+                      unsigned long long* total_chars) {
+    __shared__ unsigned long long s_c[32];
+    __shared__ uint32_t s_l[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t per = (ntiles + 1023) / 1024;
+    const uint32_t t0 = min((uint32_t)tid * per, ntiles), t1 = min(t0 + per, ntiles);
+    unsigned long long c = 0;
+    uint32_t l = 0;
+#pragma unroll 8
+    for (uint32_t t = t0; t < t1; ++t) { // (independent loads: one round trip per 8 tiles)
+        const uint64_t a = __ldg(agg + t);
+        c += a >> 32;
+        l = max(l, (uint32_t)a);
+    }
+    unsigned long long ic = c;
+    uint32_t il = l;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long tc = shfl_up64(ic, d);
+        const uint32_t tl = __shfl_up_sync(0xFFFFFFFFu, il, d);
+        if (lane >= d) {
+            ic += tc;
+            il = max(il, tl);
+        }
+    }
+    if (lane == 31) {
+        s_c[wid] = ic;
+        s_l[wid] = il;
+    }
+    __syncthreads();
+    unsigned long long pre_c = 0; // totals of the warps before mine
+    uint32_t pre_l = 0;
+    for (int w = 0; w < wid; ++w) {
+        pre_c += s_c[w];
+        pre_l = max(pre_l, s_l[w]);
+    }
+    uint32_t el = __shfl_up_sync(0xFFFFFFFFu, il, 1);
+    if (lane == 0)
+        el = 0;
+    unsigned long long run_c = pre_c + (ic - c);
+    uint32_t run_l = max(pre_l, el);
+    for (uint32_t t = t0; t < t1; ++t) {
+        const uint64_t a = agg[t];
+        prefix[t] = ((uint64_t)((uint32_t)run_c & 0x3FFFFFFFu) << 32) | run_l;
+        run_c += a >> 32;
+        run_l = max(run_l, (uint32_t)a);
+    }
+    if (tid == 1023)
+        *total_chars = run_c; // un-truncated count (the table index keeps 30 bits): > 2^30 pieces is an error
+}
+
+// Pass 3.  Persistent and warp-autonomous: a block walks tiles blockIdx.x, + gridDim.x, ... (tiles are independent, so
+// a static stride is safe) with the mask words, the prefix and the per-warp counts of its NEXT tile already requested;
+// a warp numbers the lines of its 2 KiB from {tile prefix, counts of the warps before it} (two REDUX, no block barrier),
+// compacts the newline positions into a list in shared memory and then emits LINE-parallel: lane j writes line j, so the
+// table stores are coalesced and no lane idles behind a neighbour that owns three lines.  With probes the prefix DFAs
+// are staged once per block and candidate lines collect in a queue over 16 tiles, so that the dense probe phase has a
+// line for every thread.
+constexpr uint32_t kSplitList = 96; // newline positions a warp compacts per tile (2 KiB: lines of >= 22 bytes on average;
+                                    // denser text takes the per-lane path)
+template <bool PROBE>
+__global__ void __launch_bounds__(1024, 2)
+    split_emit_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, const void* __restrict__ masks,
+                      const uint64_t* __restrict__ prefix, const uint64_t* __restrict__ wagg, uint32_t ntiles,
+                      uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap, uint32_t* n_out,
+                      SplitProbe pr) {
+    __shared__ uint32_t s_list[32][kSplitList];
+    __shared__ uint32_t s_qn;
+    __shared__ uint32_t s_q[PROBE ? kProbeQueue : 1];
+    __shared__ typename std::conditional<PROBE, ProbeSmem, uint32_t>::type s_probe;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0)
+        s_qn = 0;
+    if constexpr (PROBE) {
+        probe_stage(pr, s_probe);
+        __syncthreads();
+    }
+    using MaskT = typename std::conditional<PROBE, uint4, unsigned long long>::type;
+    const MaskT* mp = reinterpret_cast<const MaskT*>(masks);
+    uint32_t tile = blockIdx.x;
+    MaskT raw_n = MaskT{};
+    uint64_t prefix_n = 0, wa_n = 0;
+    if (tile < ntiles) {
+        raw_n = __ldg(mp + (uint64_t)tile * 1024 + tid);
+        prefix_n = __ldg(prefix + tile);
+        wa_n = __ldg(wagg + (uint64_t)tile * 32 + lane);
+    }
+    auto line_out = [&](uint32_t k, uint32_t start, uint32_t p) { // line k = [start, p)
+        if (k >= cap)
+            return;
+        out_off[k] = start;
+        out_len[k] = p - start;
+        if constexpr (PROBE) {
+            const uint32_t ll = p - start;
+            if (!ll) {
+                pr.flags[k] = (uint8_t)pr.empty_flags;
+                return;
+            }
+            // can the first byte start a match?  recorded by pass 1 at the newline in front of the line
+            uint32_t cand = 1;
+            if (start) {
+                const uint64_t vp = (uint64_t)start - 1 + shift;
+                cand = (__ldg(reinterpret_cast<const uint32_t*>(masks) + (vp >> 4)) >> (16 + (vp & 15))) & 1u;
+            }
+            if (!cand) {
+                pr.flags[k] = 0;
+            } else {
+                const uint32_t q = atomicAdd(&s_qn, 1u);
+                if (q < kProbeQueue)
+                    s_q[q] = k;
+                else
+                    pr.flags[k] = probe_line(pr, buf + start, ll); // queue full: probe in place
+            }
+        }
+    };
+    for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const MaskT raw = raw_n;
+        const uint64_t tile_prefix = prefix_n, wa = wa_n;
+        const uint32_t tn = tile + gridDim.x;
+        if (tn < ntiles) {
+            raw_n = __ldg(mp + (uint64_t)tn * 1024 + tid);
+            prefix_n = __ldg(prefix + tn);
+            wa_n = __ldg(wagg + (uint64_t)tn * 32 + lane);
+        }
+        const uint64_t vpos0 = ((uint64_t)tile * 1024 + tid) * 64;
+        uint64_t mk;
+        if constexpr (PROBE)
+            mk = (uint64_t)__byte_perm(raw.x, raw.y, 0x5410) | ((uint64_t)__byte_perm(raw.z, raw.w, 0x5410) << 32);
+        else
+            mk = raw;
+        // the warps before mine inside the tile: their line count and the end of their last newline
+        const uint32_t before = lane < wid ? 0xFFFFFFFFu : 0u;
+        const uint32_t my_off = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(wa >> 32) & before);
+        uint32_t my_start = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)wa & before);
+        if (!my_start)
+            my_start = OpCountMax::maxv(tile_prefix);
         const uint32_t cnt = __popcll(mk);
-        const uint32_t last = mk ? (uint32_t)(vpos0 + (63 - __clzll((long long)mk)) + 1 - shift) : 0u;
         uint32_t inc = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -441,144 +631,118 @@ __global__ void __launch_bounds__(THREADS, 2)
             if (lane >= d)
                 inc += t;
         }
-        const uint32_t has = __ballot_sync(0xFFFFFFFFu, mk != 0);
-        const uint32_t below = has & ((1u << lane) - 1u);
-        const uint32_t prev_last = __shfl_sync(0xFFFFFFFFu, last, below ? 31 - __clz(below) : 0);
-        const uint32_t warp_last = __shfl_sync(0xFFFFFFFFu, last, has ? 31 - __clz(has) : 0);
-        if (lane == 31) {
-            s_cnt[wid] = inc;
-            s_last[wid] = has ? warp_last : 0u;
-        }
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t c = lane < NW ? s_cnt[lane] : 0u;
-            const uint32_t wl = lane < NW ? s_last[lane] : 0u;
-            uint32_t ci = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ci, d);
-                if (lane >= d)
-                    ci += t;
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const uint32_t k0 = OpCountMax::count(tile_prefix) + my_off;
+        uint32_t end_start = my_start; // start of the piece that is open after the warp's last newline
+        if (total <= kSplitList) {
+            uint32_t idx = inc - cnt;
+            while (mk) {
+                const int b = __ffsll((long long)mk) - 1;
+                mk &= mk - 1;
+                s_list[wid][idx++] = (uint32_t)(vpos0 + b - shift);
             }
-            const uint32_t whas = __ballot_sync(0xFFFFFFFFu, c != 0);
-            const uint32_t wbelow = whas & ((1u << lane) - 1u);
-            const uint32_t st = __shfl_sync(0xFFFFFFFFu, wl, wbelow ? 31 - __clz(wbelow) : 0);
-            const uint32_t tl = __shfl_sync(0xFFFFFFFFu, wl, whas ? 31 - __clz(whas) : 0);
-            const uint32_t totv = __shfl_sync(0xFFFFFFFFu, ci, NW - 1);
-            if (lane < NW) {
-                s_cnt[lane] = ci - c;
-                s_start[lane] = wbelow ? st : 0u;
-            }
-            // the look-back of this tile: the first warp walks while the others wait at the next barrier
-            const uint64_t p = lookback<OpCountMax>(desc, tile, OpCountMax::make(totv, whas ? tl : 0u));
-            if (lane == 0) {
-                s_prefix = p;
-                s_tot = totv;
-                if (totv)
-                    atomicAdd(total_chars, (unsigned long long)totv);
+            __syncwarp();
+            for (uint32_t j = lane; j < total; j += 32)
+                line_out((k0 + j) & 0x3FFFFFFFu, j ? s_list[wid][j - 1] + 1 : my_start, s_list[wid][j]);
+            if (total)
+                end_start = s_list[wid][total - 1] + 1;
+            __syncwarp();
+        } else {
+            // dense text: every lane writes its own lines
+            const uint32_t last = mk ? (uint32_t)(vpos0 + (63 - __clzll((long long)mk)) + 1 - shift) : 0u;
+            const uint32_t has = __ballot_sync(0xFFFFFFFFu, mk != 0);
+            const uint32_t below = has & ((1u << lane) - 1u);
+            const uint32_t prev_last = __shfl_sync(0xFFFFFFFFu, last, below ? 31 - __clz(below) : 0);
+            end_start = __shfl_sync(0xFFFFFFFFu, last, 31 - __clz(has)); // (has != 0: total > 0)
+            uint32_t k = k0 + (inc - cnt), start = below ? prev_last : my_start;
+            while (mk) {
+                const int b = __ffsll((long long)mk) - 1;
+                mk &= mk - 1;
+                const uint32_t p = (uint32_t)(vpos0 + b - shift);
+                line_out(k & 0x3FFFFFFFu, start, p);
+                ++k;
+                start = p + 1;
             }
         }
-        __syncthreads();
-        const uint64_t tile_prefix = s_prefix;
-        uint32_t k = (OpCountMax::count(tile_prefix) + s_cnt[wid] + (inc - cnt)) & 0x3FFFFFFFu;
-        uint32_t start = below ? prev_last : (s_start[wid] ? s_start[wid] : OpCountMax::maxv(tile_prefix));
-        while (mk) {
-            const int b = __ffsll((long long)mk) - 1;
-            mk &= mk - 1;
-            const uint32_t p = (uint32_t)(vpos0 + b - shift);
-            if (k < cap) {
-                out_off[k] = start;
-                out_len[k] = p - start;
-                if (PROBE) {
-                    const uint32_t ll = p - start;
-                    const uint32_t cand = ll ? probe_first(pr, buf[start]) : 0u;
-                    if (!cand) {
-                        pr.flags[k] = ll ? 0 : (uint8_t)pr.empty_flags;
-                    } else {
-                        const uint32_t q = atomicAdd(&s_qn, 1u);
-                        if (q < kProbeQueue)
-                            s_q[q] = k;
-                        else
-                            pr.flags[k] = probe_line(pr, buf + start, ll);
-                    }
-                }
-            }
-            ++k;
-            start = p + 1;
-        }
-        if (tile == ntiles - 1 && tid == THREADS - 1) {
-            if (start < len) { // the unterminated last piece, if any
+        if (tile == ntiles - 1 && wid == 31 && lane == 0) {
+            // inclusive total of the whole buffer: the unterminated last piece, if any
+            uint32_t k = (k0 + total) & 0x3FFFFFFFu;
+            if (end_start < len) {
                 if (k < cap) {
-                    out_off[k] = start;
-                    out_len[k] = len - start;
+                    out_off[k] = end_start;
+                    out_len[k] = len - end_start;
                     if (PROBE)
-                        pr.flags[k] = probe_line(pr, buf + start, len - start);
+                        pr.flags[k] = probe_line(pr, buf + end_start, len - end_start);
                 }
                 ++k;
             }
             *n_out = k;
         }
-        __syncthreads(); // the probe queue is complete, this tile's table entries are visible; s_* may be rewritten
-        if (PROBE) {
-            const uint32_t qn = min(s_qn, kProbeQueue);
-            for (uint32_t q = tid; q < qn; q += THREADS) {
-                const uint32_t kk = s_q[q];
-                pr.flags[kk] = probe_line(pr, buf + out_off[kk], out_len[kk]);
+        if constexpr (PROBE) {
+            if ((it & 15) == 15 || tn >= ntiles) { // (block-uniform) every 16 tiles and after the last one
+                __syncthreads(); // the queue and the line table entries of these tiles are visible to the block
+                const uint32_t qn = min(s_qn, kProbeQueue);
+                for (uint32_t q = tid; q < qn; q += 1024) {
+                    const uint32_t kk = s_q[q];
+                    pr.flags[kk] = probe_line_smem(pr, s_probe, buf + out_off[kk], out_len[kk]);
+                }
+                __syncthreads();
+                if (tid == 0)
+                    s_qn = 0;
             }
-            __syncthreads();
-            if (tid == 0)
-                s_qn = 0;
         }
-        tile = nxt;
-        nxt += gridDim.x;
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-            v[r] = vn[r];
     }
 }
 
 static int split_lookback_warps() {
     static const int w = [] {
-        const char* e = getenv("LC_B200_LOOKBACK_WARPS"); // A/B knob: 1 (default) = single-warp walk, 4 = block-wide
-        int t = e ? atoi(e) : 1;                          // (measured on C1: 4 is 4 % slower -- two more barriers per
-        return t == 4 ? 4 : (t == -8 || t == -4) ? t : 1; // round); -4 / -8 = one warp, 4 / 8 descriptors per lane
+        const char* e = getenv("LC_B200_LOOKBACK_WARPS"); // A/B knob of the single-pass kernel: 1 (default) = one warp walks,
+        int t = e ? atoi(e) : 1;                          // 4 = block-wide (measured 4 % slower), -8 = one warp, 8
+        return t == 4 ? 4 : (t == -8) ? t : 1;            // descriptors per lane (measured 30 % slower)
     }();
     return w;
 }
 
+uint64_t split_scratch_bytes(uint64_t len, bool probe) {
+    const uint64_t nt = (len + 16 + kSplitTileChunks * 16 - 1) / (kSplitTileChunks * 16);
+    return nt * 16 + nt * 256 + nt * kSplitTileChunks * (probe ? 4 : 2) + 256;
+}
+
 template <bool PROBE>
-static void launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
-                              uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
-                              unsigned long long* d_total, const SplitProbe& pr, cudaStream_t st) {
+static int launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
+                             uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
+                             unsigned long long* d_total, uint64_t* d_scratch, const SplitProbe& pr, cudaStream_t st) {
     uint32_t shift = (uint32_t)((uintptr_t)d_buf & 15u);
     uint32_t splat = split_char * 0x01010101u;
+    static const bool lookback_mode = [] {
+        const char* e = getenv("LC_B200_SPLIT"); // A/B knob: "lookback" = the single-pass kernel (split_kernel)
+        return e && !strcmp(e, "lookback");
+    }();
+    if (d_scratch && !lookback_mode && !getenv("LC_B200_SPLIT_TRACE")) {
+        const uint32_t nt = (uint32_t)(((uint64_t)len + shift + kSplitTileChunks * 16 - 1) / (kSplitTileChunks * 16));
+        uint64_t* agg = d_scratch;
+        uint64_t* prefix = d_scratch + nt;
+        uint64_t* wagg = d_scratch + 2 * (uint64_t)nt;
+        void* masks = d_scratch + 34 * (uint64_t)nt;
+        split_mask_kernel<PROBE><<<nt, 1024, 0, st>>>(d_buf, len, shift, splat, masks, agg, wagg, pr);
+        split_scan_kernel<<<1, 1024, 0, st>>>(agg, nt, prefix, d_total);
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const uint32_t grid = std::min<uint32_t>(nt, (uint32_t)sms * 2);
+        split_emit_kernel<PROBE><<<grid, 1024, 0, st>>>(d_buf, len, shift, masks, prefix, wagg, nt, d_off, d_len, cap,
+                                                       d_n_out, pr);
+        return 3;
+    }
     static const int cfg = [] {
         const char* e = getenv("LC_B200_SPLIT_TILE_KB"); // A/B knob: 16, 32 or 64 (descriptors are sized for 16)
         int t = e ? atoi(e) : 64;
         return (t == 16 || t == 32) ? t : 64;
     }();
     volatile uint64_t* desc = (volatile uint64_t*)d_desc;
-    static const bool persist = [] {
-        const char* e = getenv("LC_B200_SPLIT_PERSIST"); // A/B knob: 1 = persistent prefetching blocks (measured slower:
-        return e && !strcmp(e, "1");                     // C1 0.39 ms vs 0.26 ms -- half the resident threads per SM)
-    }();
-    if (persist) {
-        constexpr int T = 512; // 32 KiB tiles (the descriptors are sized for 16 KiB tiles: enough)
-        const uint32_t nt = (uint32_t)(((uint64_t)len + shift + T * 64 - 1) / (T * 64));
-        static int sms = 0, per_sm = 0;
-        if (!sms) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, split_persist_kernel<T, PROBE>, T, 0);
-            if (per_sm < 1)
-                per_sm = 1;
-        }
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(nt, (uint64_t)sms * per_sm);
-        split_persist_kernel<T, PROBE><<<grid, T, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap, desc, d_ticket,
-                                                          nt, d_n_out, d_total, pr);
-        return;
-    }
     const uint64_t tile_bytes = (uint64_t)cfg * 1024;
     uint32_t ntiles = (uint32_t)((len + shift + tile_bytes - 1) / tile_bytes);
     const bool wide = split_lookback_warps() > 1;
@@ -590,14 +754,8 @@ static void launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_
         uint64_t* d_tr = nullptr;
         cudaMalloc(&d_tr, (size_t)ntiles * 64);
         cudaMemsetAsync(d_tr, 0, (size_t)ntiles * 64, st);
-        if (split_lookback_warps() == -8)
-            split_kernel<1024, -8, PROBE, true><<<ntiles, 1024, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
-                                                                         desc, d_ticket, ntiles, d_n_out, d_total, pr,
-                                                                         d_tr);
-        else
-            split_kernel<1024, 1, PROBE, true><<<ntiles, 1024, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap,
-                                                                        desc, d_ticket, ntiles, d_n_out, d_total, pr,
-                                                                        d_tr);
+        split_kernel<1024, 1, PROBE, true><<<ntiles, 1024, 0, st>>>(d_buf, len, shift, splat, d_off, d_len, cap, desc,
+                                                                    d_ticket, ntiles, d_n_out, d_total, pr, d_tr);
         std::vector<uint64_t> h((size_t)ntiles * 8);
         cudaStreamSynchronize(st);
         cudaMemcpy(h.data(), d_tr, h.size() * 8, cudaMemcpyDeviceToHost);
@@ -606,15 +764,13 @@ static void launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_
             fwrite(h.data(), 8, h.size(), f);
             fclose(f);
         }
-        return;
+        return 1;
     }
     if (cfg == 64) {
         if (wide)
             LC_SPLIT_LAUNCH(1024, 4);
         else if (deep == 8)
             LC_SPLIT_LAUNCH(1024, -8);
-        else if (deep == 4)
-            LC_SPLIT_LAUNCH(1024, -4);
         else
             LC_SPLIT_LAUNCH(1024, 1);
     } else if (cfg == 32) {
@@ -626,29 +782,35 @@ static void launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_
             LC_SPLIT_LAUNCH(256, 1);
     }
 #undef LC_SPLIT_LAUNCH
+    return 1;
 }
 
-void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
-                  uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
-                  unsigned long long* d_total, cudaStream_t st) {
+int launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
+                 uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out, unsigned long long* d_total,
+                 uint64_t* d_scratch, cudaStream_t st) {
     SplitProbe pr;
     memset(&pr, 0, sizeof pr);
-    launch_split_impl<false>(d_buf, len, split_char, d_off, d_len, cap, d_desc, d_ticket, d_n_out, d_total, pr, st);
+    return launch_split_impl<false>(d_buf, len, split_char, d_off, d_len, cap, d_desc, d_ticket, d_n_out, d_total,
+                                    d_scratch, pr, st);
 }
 
-void launch_split_probe(const MlConfig& cfg, const uint8_t* d_buf, uint32_t len, uint32_t* d_off, uint32_t* d_len,
-                        uint8_t* d_flags, uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
-                        unsigned long long* d_total, cudaStream_t st) {
+int launch_split_probe(const MlConfig& cfg, const uint8_t* d_buf, uint32_t len, uint32_t* d_off, uint32_t* d_len,
+                       uint8_t* d_flags, uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
+                       unsigned long long* d_total, uint64_t* d_scratch, cudaStream_t st) {
     SplitProbe pr;
     memset(&pr, 0, sizeof pr);
     pr.blob[0] = cfg.blob_start;
     pr.blob[1] = cfg.blob_cont;
     pr.blob[2] = cfg.blob_end;
-    for (int p = 0; p < 3; ++p)
+    for (int p = 0; p < 3; ++p) {
         memcpy(pr.first[p], cfg.first[p], sizeof pr.first[p]);
+        for (int w = 0; w < 8; ++w)
+            pr.any_first[w] |= cfg.first[p][w]; // (the set of an absent pattern is empty)
+    }
     pr.empty_flags = cfg.empty_flags;
     pr.flags = d_flags;
-    launch_split_impl<true>(d_buf, len, '\n', d_off, d_len, cap, d_desc, d_ticket, d_n_out, d_total, pr, st);
+    return launch_split_impl<true>(d_buf, len, '\n', d_off, d_len, cap, d_desc, d_ticket, d_n_out, d_total, d_scratch,
+                                   pr, st);
 }
 
 // ================================================================================================ sums
@@ -3031,7 +3193,7 @@ struct MlMode {
 // Transition of line `fl` from state s_in (0 not partial / 1 partial):
 // s_out and which line (0 none, 1 this line, 2 the next line) becomes multiStartIndex.
 // Restates ProcessorSplitMultilineLogStringNative.cpp:175-283 without the emission side effects.
-__device__ __forceinline__ void ml_trans(const MlMode& m, uint32_t fl, uint32_t s_in, uint32_t& s_out,
+__host__ __device__ __forceinline__ void ml_trans(const MlMode& m, uint32_t fl, uint32_t s_in, uint32_t& s_out,
                                          uint32_t& begin) {
     const bool mS = fl & 1, mC = fl & 2, mE = fl & 4;
     begin = 0;
@@ -3085,7 +3247,7 @@ __device__ __forceinline__ void ml_trans(const MlMode& m, uint32_t fl, uint32_t 
 //   span(lb, j_last, flag_line) unmatched lines lb..j_last, each carrying flag_line's isLast flag
 //   to_eof(lb)                  [start of line lb, end of buffer)     matched record, isLast = true
 template <class Sink>
-__device__ __forceinline__ void ml_actions(const MlMode& m, uint32_t fl, uint32_t s_in, uint32_t lb, uint32_t j,
+__host__ __device__ __forceinline__ void ml_actions(const MlMode& m, uint32_t fl, uint32_t s_in, uint32_t lb, uint32_t j,
                                            uint32_t n, Sink& sink) {
     if (j == n) { // :289-308
         if (s_in && lb < n) {
@@ -3494,6 +3656,281 @@ __global__ void __launch_bounds__(THREADS)
 uint32_t ml_fused_tiles(uint64_t line_cap) {
     const uint64_t per = (uint64_t)kMlFusedThreads * kMlFusedItems;
     return (uint32_t)((line_cap + 1 + per - 1) / per);
+}
+
+// ---- the same back half without look-backs: state pass -> scan -> count pass -> scan -> emission ------------------------
+// ml_fused_kernel chains two decoupled look-backs per tile, and a look-back waits for the slowest of the resident tiles
+// (see the split above: same effect, 0.48 ms for the 22 M lines of C3, i.e. 107 us per tile).  The arithmetic, however,
+// only needs the FLAGS (one byte per line) until the very last step, so the passes are cheap to repeat:
+//   pass 1  per tile of 8192 lines: the composed 2-state transition function            -> agg1[tile]
+//   scan    one block, OpMlState (ordered)                                              -> pre1[tile]
+//   pass 2  per tile: incoming state of every line (from pre1) -> number of events      -> agg2[tile]
+//   scan    one block, OpSum                                                            -> pre2[tile]
+//   pass 3  per tile: states again, exclusive event slots (from pre2), emission (reads off/len of the emitted lines)
+// Tiles never wait for each other.  Lines whose transition is the identity (in start-only mode: every line that does
+// not match) skip the composition.
+constexpr int kMlPassThreads = 512;
+constexpr int kMlPassItems = 16;
+constexpr uint32_t kMlPassTile = kMlPassThreads * kMlPassItems;
+
+uint32_t ml_pass_tiles(uint64_t line_cap) { return (uint32_t)((line_cap + 1 + kMlPassTile - 1) / kMlPassTile); }
+
+template <class Op>
+__global__ void __launch_bounds__(1024)
+    ml_tile_scan_kernel(const uint64_t* __restrict__ agg, const uint32_t* __restrict__ n_lines, uint32_t line_cap,
+                        uint64_t* __restrict__ pre) {
+    __shared__ uint64_t s_scan[33];
+    const uint64_t n = min(*n_lines, line_cap);
+    const uint32_t ntiles = (uint32_t)((n + 1 + kMlPassTile - 1) / kMlPassTile); // (element n = end of buffer)
+    const uint32_t per = (ntiles + 1023) / 1024;
+    const uint32_t t0 = min((uint32_t)threadIdx.x * per, ntiles), t1 = min(t0 + per, ntiles);
+    uint64_t a = Op::identity();
+    for (uint32_t t = t0; t < t1; ++t)
+        a = Op::combine(a, __ldg(agg + t));
+    uint64_t tot;
+    uint64_t run = block_exclusive_scan<Op, 1024>(a, tot, s_scan);
+    for (uint32_t t = t0; t < t1; ++t) {
+        pre[t] = run;
+        run = Op::combine(run, __ldg(agg + t));
+    }
+}
+
+// The state machine as tables over (flags, state), built on the host from ml_trans / ml_actions themselves: stepping a
+// line is then three shifts instead of the branch cascade (the generic code stays the single statement of the rules).
+//   act codes: 0 nothing, 1 single(unmatched), 2 single(matched), 3 to_end, 4 span(lb, j, j), 5 to_prev,
+//              6 to_prev + single(unmatched)
+struct MlTab {
+    uint32_t next;    // bit fl*2+s: state after the line
+    uint32_t begin;   // 2 bits at (fl*2+s)*2: 0 none / 1 this line / 2 the next line becomes multiStartIndex
+    uint64_t act;     // 3 bits at (fl*2+s)*3
+    uint32_t ident;   // bit fl: the line changes neither state (and opens nothing)
+    uint32_t skip[2]; // bit fl: in state s the line does nothing at all (no event, no change)
+};
+
+struct MlRecSink { // records which sink calls ml_actions makes for one (flags, state) pair
+    uint32_t code = 0;
+    bool bad = false;
+    void single(uint32_t, bool matched) { code = code == 5 ? (matched ? (bad = true, 0u) : 6u) : (code ? (bad = true, 0u) : (matched ? 2u : 1u)); }
+    void to_end(uint32_t, uint32_t) { code = code ? (bad = true, 0u) : 3u; }
+    void to_prev(uint32_t, uint32_t) { code = code ? (bad = true, 0u) : 5u; }
+    void to_eof(uint32_t) { bad = true; }
+    void span(uint32_t, uint32_t jl, uint32_t fl) { code = (code || jl != 7 || fl != 7) ? (bad = true, 0u) : 4u; }
+};
+
+static bool ml_build_tab(const MlMode& m, MlTab& t) {
+    memset(&t, 0, sizeof t);
+    for (uint32_t fl = 0; fl < 8; ++fl) {
+        bool id = true;
+        for (uint32_t st = 0; st < 2; ++st) {
+            uint32_t o, b;
+            ml_trans(m, fl, st, o, b);
+            MlRecSink rec;
+            ml_actions(m, fl, st, 3u, 7u, 100u, rec); // (line 7 of 100, multiStartIndex 3)
+            if (rec.bad)
+                return false;
+            const uint32_t idx = fl * 2 + st;
+            t.next |= (o & 1u) << idx;
+            t.begin |= (b & 3u) << (2 * idx);
+            t.act |= (uint64_t)rec.code << (3 * idx);
+            if (o != st || b)
+                id = false;
+            if (o == st && !b && !rec.code)
+                t.skip[st] |= 1u << fl;
+        }
+        if (id)
+            t.ident |= 1u << fl;
+    }
+    return true;
+}
+
+template <class Sink>
+__device__ __forceinline__ void ml_apply(uint32_t code, uint32_t lb, uint32_t j, Sink& sink) {
+    switch (code) {
+    case 1: sink.single(j, false); break;
+    case 2: sink.single(j, true); break;
+    case 3: sink.to_end(lb, j); break;
+    case 4: sink.span(lb, j, j); break;
+    case 5: sink.to_prev(lb, j); break;
+    case 6:
+        sink.to_prev(lb, j);
+        sink.single(j, false);
+        break;
+    default: break;
+    }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kMlPassThreads)
+    ml_pass_kernel(MlMode m, MlTab tb, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ off,
+                   const uint32_t* __restrict__ len, const uint32_t* __restrict__ n_lines, uint32_t line_cap,
+                   uint32_t total_len, uint64_t* __restrict__ agg1, const uint64_t* __restrict__ pre1,
+                   uint64_t* __restrict__ agg2, const uint64_t* __restrict__ pre2, uint32_t* __restrict__ out_off,
+                   uint32_t* __restrict__ out_len, uint8_t* __restrict__ out_flags, uint64_t cap,
+                   unsigned long long* counters, uint64_t* total_out) {
+    constexpr int THREADS = kMlPassThreads, ITEMS = kMlPassItems;
+    static_assert(ITEMS == 16, "one 16-byte load of flags per thread");
+    __shared__ uint64_t s_scan[THREADS / 32 + 1];
+    const int tid = threadIdx.x;
+    const uint32_t tile = blockIdx.x;
+    const uint64_t n = min(*n_lines, line_cap); // (more lines than the table holds: the host repeats the call)
+    if ((uint64_t)tile * kMlPassTile > n)
+        return;
+    const uint64_t base = (uint64_t)tile * kMlPassTile + (uint64_t)tid * ITEMS;
+    uint32_t fw[4] = {0, 0, 0, 0};
+    if (base + ITEMS <= n) {
+        const uint4 f4 = __ldg(reinterpret_cast<const uint4*>(flags + base));
+        fw[0] = f4.x & 0x07070707u, fw[1] = f4.y & 0x07070707u, fw[2] = f4.z & 0x07070707u, fw[3] = f4.w & 0x07070707u;
+    } else {
+        for (int k = 0; k < ITEMS; ++k)
+            if (base + k < n)
+                fw[k >> 2] |= (uint32_t)(flags[base + k] & 7u) << (8 * (k & 3));
+    }
+    const uint32_t nvalid = base >= n ? 0u : (uint32_t)min((uint64_t)ITEMS, n - base); // lines (not the eof element)
+    // ---- the thread's lines composed: both incoming states stepped side by side
+    uint32_t sA = 0, sB = 1, lbA = 0, lbB = 0; // lbX: (index + 1) of the last line opened inside the run, 0 = none
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        if (fw[w] == 0 && (tb.ident & 1u))
+            continue; // four lines that change nothing
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int k = w * 4 + b;
+            const uint32_t fl = (fw[w] >> (8 * b)) & 0xFFu;
+            if ((uint32_t)k < nvalid && !((tb.ident >> fl) & 1u)) {
+                const uint32_t j1 = (uint32_t)(base + k) + 1;
+                const uint32_t ia = fl * 2 + sA, ib = fl * 2 + sB;
+                const uint32_t ba = (tb.begin >> (2 * ia)) & 3u, bb = (tb.begin >> (2 * ib)) & 3u;
+                if (ba)
+                    lbA = j1 + ba - 1;
+                if (bb)
+                    lbB = j1 + bb - 1;
+                sA = (tb.next >> ia) & 1u;
+                sB = (tb.next >> ib) & 1u;
+            }
+        }
+    }
+    const uint64_t agg = OpMlState::make(sA, sB, lbA, lbB);
+    uint64_t tot;
+    const uint64_t ex = block_exclusive_scan<OpMlState, THREADS>(agg, tot, s_scan);
+    if (PASS == 1) {
+        if (tid == 0)
+            agg1[tile] = tot;
+        return;
+    }
+    const uint64_t run0 = OpMlState::combine(__ldg(pre1 + tile), ex);
+    // initial condition (:165-169): End-only mode starts partial with multiStartIndex = line 0
+    const uint32_t s0 = (!m.S && !m.C && m.E) ? 1u : 0u;
+    const uint32_t st0 = OpMlState::f(run0, s0);
+    uint32_t lb0 = OpMlState::lb(run0, s0);
+    if (!lb0)
+        lb0 = s0 ? 1u : 0u;
+    lb0 = lb0 ? lb0 - 1 : 0u; // line index of multiStartIndex (valid only in the partial state)
+    // one sweep over the thread's lines with a concrete state; `Sink` counts (pass 2) or writes (pass 3)
+    auto sweep = [&](auto& sink) {
+        uint32_t st = st0, lb = lb0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            if (fw[w] == 0 && (tb.skip[st] & 1u) && (uint32_t)(w * 4 + 4) <= nvalid)
+                continue; // four lines without any effect in this state
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                const int k = w * 4 + b;
+                if ((uint32_t)k >= nvalid)
+                    break;
+                const uint32_t fl = (fw[w] >> (8 * b)) & 0xFFu;
+                if ((tb.skip[st] >> fl) & 1u)
+                    continue;
+                const uint32_t j = (uint32_t)(base + k);
+                const uint32_t idx = fl * 2 + st;
+                const uint32_t code = (uint32_t)(tb.act >> (3 * idx)) & 7u;
+                if (code) {
+                    sink.prepare(j);
+                    ml_apply(code, lb, j, sink);
+                }
+                const uint32_t bg = (tb.begin >> (2 * idx)) & 3u;
+                if (bg)
+                    lb = j + bg - 1;
+                st = (tb.next >> idx) & 1u;
+            }
+        }
+        if (base <= n && n < base + ITEMS) { // the virtual end-of-buffer element lives in this thread
+            sink.prepare((uint32_t)n);
+            ml_actions(m, 0u, st, lb, (uint32_t)n, (uint32_t)n, sink);
+        }
+    };
+    struct CountSink : MlCountSink {
+        __device__ void prepare(uint32_t) {}
+    } cs;
+    cs.discard = m.discard;
+    cs.len = len;
+    cs.n = (uint32_t)n;
+    sweep(cs);
+    uint64_t tot2;
+    const uint64_t ex2 = block_exclusive_scan<OpSum, THREADS>((uint64_t)cs.cnt, tot2, s_scan);
+    if (PASS == 2) {
+        if (tid == 0)
+            agg2[tile] = tot2;
+        return;
+    }
+    // ---- emission at the exclusive prefix of the counts
+    struct EmitSink : MlEmitSink {
+        uint32_t total_len_;
+        // begin + content.size() == sourceVal.size() (:174): only the last line can end where the buffer ends (every
+        // other line is followed by a '\n'); the end-of-buffer element always passes true
+        __device__ void prepare(uint32_t j) {
+            is_last = (j == n) ? 1u : ((j + 1 == n && off[j] + len[j] == total_len_) ? 1u : 0u);
+        }
+    } es;
+    es.discard = m.discard;
+    es.off = off;
+    es.len = len;
+    es.total_len = total_len;
+    es.total_len_ = total_len;
+    es.out_off = out_off;
+    es.out_len = out_len;
+    es.out_flags = out_flags;
+    es.cap = cap;
+    es.pos = __ldg(pre2 + tile) + ex2;
+    es.n = (uint32_t)n;
+    es.is_last = 0;
+    sweep(es);
+    if (base <= n && n < base + ITEMS)
+        *total_out = es.pos;
+    uint32_t me = es.matched_events, ul = es.unmatch_lines;
+    for (int d = 16; d; d >>= 1) {
+        me += __shfl_down_sync(0xFFFFFFFFu, me, d);
+        ul += __shfl_down_sync(0xFFFFFFFFu, ul, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (me)
+            atomicAdd(&counters[0], (unsigned long long)me);
+        if (ul)
+            atomicAdd(&counters[1], (unsigned long long)ul);
+    }
+}
+
+int launch_ml_passes(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len,
+                     const uint32_t* d_n_lines, uint32_t line_cap, uint32_t total_len, uint32_t* d_out_off,
+                     uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, uint64_t* d_scratch /* 4 x ml_pass_tiles */,
+                     unsigned long long* d_counters, uint64_t* d_total, cudaStream_t st) {
+    MlMode m{cfg.blob_start != nullptr, cfg.blob_cont != nullptr, cfg.blob_end != nullptr, cfg.discard != 0};
+    const uint32_t nt = ml_pass_tiles(line_cap);
+    uint64_t *agg1 = d_scratch, *pre1 = d_scratch + nt, *agg2 = d_scratch + 2 * (uint64_t)nt,
+             *pre2 = d_scratch + 3 * (uint64_t)nt;
+    MlTab tb;
+    if (!ml_build_tab(m, tb))
+        return -1; // (cannot happen: every (flags, state) pair makes at most to_prev + single)
+#define LC_ML_PASS(P)                                                                                                  \
+    ml_pass_kernel<P><<<nt, kMlPassThreads, 0, st>>>(m, tb, d_flags, d_off, d_len, d_n_lines, line_cap, total_len,      \
+                                                     agg1, pre1, agg2, pre2, d_out_off, d_out_len, d_out_flags, cap,   \
+                                                     d_counters, d_total)
+    LC_ML_PASS(1);
+    ml_tile_scan_kernel<OpMlState><<<1, 1024, 0, st>>>(agg1, d_n_lines, line_cap, pre1);
+    LC_ML_PASS(2);
+    ml_tile_scan_kernel<OpSum><<<1, 1024, 0, st>>>(agg2, d_n_lines, line_cap, pre2);
+    LC_ML_PASS(3);
+#undef LC_ML_PASS
+    return 5;
 }
 
 void launch_ml_fused(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len,

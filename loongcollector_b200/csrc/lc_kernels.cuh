@@ -21,9 +21,12 @@ inline uint32_t scan_tiles(uint64_t n) { return (uint32_t)((n + kScanTile - 1) /
 // a1: newline split.  desc: >= split_tiles() u64 (zeroed), ticket: u32 (zeroed), n_out: u32 device counter.
 // d_total: u64 device counter (zeroed) that receives the un-truncated number of split chars (the look-back payload
 // keeps 30 bits of count: the caller reports LC_ERR_TOO_LARGE beyond that).
-void launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
-                  uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
-                  unsigned long long* d_total, cudaStream_t st);
+// d_scratch: split_scratch_bytes(len, probe) bytes (not initialised) for the three-pass formulation (masks, per-tile
+// counts and prefixes); nullptr selects the single-pass look-back kernel.  Returns the number of kernels launched.
+uint64_t split_scratch_bytes(uint64_t len, bool probe);
+int launch_split(const uint8_t* d_buf, uint32_t len, uint8_t split_char, uint32_t* d_off, uint32_t* d_len,
+                 uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out, unsigned long long* d_total,
+                 uint64_t* d_scratch, cudaStream_t st);
 
 // exclusive sum of u32 -> u64 (out has n entries; *d_total receives the grand total)
 void launch_exclusive_sum(const uint32_t* d_in, uint64_t n, uint64_t* d_out, uint64_t* d_total, uint64_t* d_desc,
@@ -183,10 +186,16 @@ void launch_ml_emit(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t*
 // fused multiline path: split + per-line probes in one pass (flags[line]), then state scan + counts + slots + emission
 // in one kernel that reads the line count from d_n_lines (no host round trip in between).  d_desc_state / d_desc_sum:
 // ml_fused_tiles(line_cap) + 1 zeroed u64 each.
-void launch_split_probe(const MlConfig& cfg, const uint8_t* d_buf, uint32_t len, uint32_t* d_off, uint32_t* d_len,
-                        uint8_t* d_flags, uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
-                        unsigned long long* d_total, cudaStream_t st);
+int launch_split_probe(const MlConfig& cfg, const uint8_t* d_buf, uint32_t len, uint32_t* d_off, uint32_t* d_len,
+                       uint8_t* d_flags, uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
+                       unsigned long long* d_total, uint64_t* d_scratch, cudaStream_t st);
 uint32_t ml_fused_tiles(uint64_t line_cap);
+// the same result without look-backs (five launches; d_scratch: 4 * ml_pass_tiles(line_cap) u64, not initialised)
+uint32_t ml_pass_tiles(uint64_t line_cap);
+int launch_ml_passes(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len,
+                     const uint32_t* d_n_lines, uint32_t line_cap, uint32_t total_len, uint32_t* d_out_off,
+                     uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, uint64_t* d_scratch,
+                     unsigned long long* d_counters, uint64_t* d_total, cudaStream_t st);
 void launch_ml_fused(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len,
                      const uint32_t* d_n_lines, uint32_t line_cap, uint32_t total_len, uint32_t* d_out_off,
                      uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, uint64_t* d_desc_state,
