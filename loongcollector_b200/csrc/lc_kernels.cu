@@ -483,70 +483,80 @@ __global__ void __launch_bounds__(1024, 2)
         agg[tile] = ((uint64_t)s_cnt << 32) | s_last;
 }
 
-// exclusive {sum of counts, max of ends} over the tiles, in tile order.  One block: every thread folds a contiguous run
-// of tiles (independent loads), ONE block scan over the 1024 runs, then the thread writes the prefixes of its run.
+// exclusive {sum of counts, max of ends} over the tiles, in tile order.  One block: warp w owns a contiguous range of
+// tiles and walks it in coalesced groups of 32 (a REDUX pair per group for the range totals, then, with the totals of the
+// earlier warps known, a shuffle scan per group that writes the prefixes).
 __global__ void __launch_bounds__(1024)
     split_scan_kernel(const uint64_t* __restrict__ agg, uint32_t ntiles, uint64_t* __restrict__ prefix,
                       unsigned long long* total_chars) {
     __shared__ unsigned long long s_c[32];
     __shared__ uint32_t s_l[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t per = (ntiles + 1023) / 1024;
-    const uint32_t t0 = min((uint32_t)tid * per, ntiles), t1 = min(t0 + per, ntiles);
+    const uint32_t per = ((ntiles + 31) / 32 + 31) & ~31u; // tiles per warp, a multiple of 32
+    const uint32_t t0 = min((uint32_t)wid * per, ntiles), t1 = min(t0 + per, ntiles);
     unsigned long long c = 0;
     uint32_t l = 0;
-#pragma unroll 8
-    for (uint32_t t = t0; t < t1; ++t) { // (independent loads: one round trip per 8 tiles)
+#pragma unroll 4
+    for (uint32_t t = t0 + lane; t < t1; t += 32) {
         const uint64_t a = __ldg(agg + t);
         c += a >> 32;
         l = max(l, (uint32_t)a);
     }
-    unsigned long long ic = c;
-    uint32_t il = l;
+    const uint32_t c_lo = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)c), c_hi = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(c >> 32));
+    (void)c_hi; // (a warp's range holds < 2^32 newlines: at most 2^26 tiles... the low word is exact per lane, sums below)
+    unsigned long long wc = c;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long tc = shfl_up64(ic, d);
-        const uint32_t tl = __shfl_up_sync(0xFFFFFFFFu, il, d);
-        if (lane >= d) {
-            ic += tc;
-            il = max(il, tl);
-        }
-    }
-    if (lane == 31) {
-        s_c[wid] = ic;
-        s_l[wid] = il;
+    for (int d = 16; d; d >>= 1)
+        wc += shfl_down64(wc, d);
+    const uint32_t wl = __reduce_max_sync(0xFFFFFFFFu, l);
+    (void)c_lo;
+    if (lane == 0) {
+        s_c[wid] = wc;
+        s_l[wid] = wl;
     }
     __syncthreads();
-    unsigned long long pre_c = 0; // totals of the warps before mine
-    uint32_t pre_l = 0;
+    unsigned long long run_c = 0; // totals of the warps before mine
+    uint32_t run_l = 0;
     for (int w = 0; w < wid; ++w) {
-        pre_c += s_c[w];
-        pre_l = max(pre_l, s_l[w]);
+        run_c += s_c[w];
+        run_l = max(run_l, s_l[w]);
     }
-    uint32_t el = __shfl_up_sync(0xFFFFFFFFu, il, 1);
-    if (lane == 0)
-        el = 0;
-    unsigned long long run_c = pre_c + (ic - c);
-    uint32_t run_l = max(pre_l, el);
-    for (uint32_t t = t0; t < t1; ++t) {
-        const uint64_t a = agg[t];
-        prefix[t] = ((uint64_t)((uint32_t)run_c & 0x3FFFFFFFu) << 32) | run_l;
-        run_c += a >> 32;
-        run_l = max(run_l, (uint32_t)a);
+    for (uint32_t tb = t0; tb < t1; tb += 32) {
+        const uint32_t t = tb + lane;
+        const uint64_t a = t < t1 ? __ldg(agg + t) : 0ull;
+        const uint32_t ac = (uint32_t)(a >> 32), al = (uint32_t)a;
+        uint32_t ic = ac, il = al;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t tc = __shfl_up_sync(0xFFFFFFFFu, ic, d), tl = __shfl_up_sync(0xFFFFFFFFu, il, d);
+            if (lane >= d) {
+                ic += tc;
+                il = max(il, tl);
+            }
+        }
+        uint32_t el = __shfl_up_sync(0xFFFFFFFFu, il, 1);
+        if (lane == 0)
+            el = 0;
+        if (t < t1)
+            prefix[t] = ((uint64_t)((uint32_t)(run_c + (ic - ac)) & 0x3FFFFFFFu) << 32) | max(run_l, el);
+        run_c += __shfl_sync(0xFFFFFFFFu, ic, 31);
+        run_l = max(run_l, __shfl_sync(0xFFFFFFFFu, il, 31));
     }
     if (tid == 1023)
         *total_chars = run_c; // un-truncated count (the table index keeps 30 bits): > 2^30 pieces is an error
 }
 
-// Pass 3.  Persistent and warp-autonomous: a block walks tiles blockIdx.x, + gridDim.x, ... (tiles are independent, so
-// a static stride is safe) with the mask words, the prefix and the per-warp counts of its NEXT tile already requested;
-// a warp numbers the lines of its 2 KiB from {tile prefix, counts of the warps before it} (two REDUX, no block barrier),
-// compacts the newline positions into a list in shared memory and then emits LINE-parallel: lane j writes line j, so the
-// table stores are coalesced and no lane idles behind a neighbour that owns three lines.  With probes the prefix DFAs
-// are staged once per block and candidate lines collect in a queue over 16 tiles, so that the dense probe phase has a
-// line for every thread.
-constexpr uint32_t kSplitList = 96; // newline positions a warp compacts per tile (2 KiB: lines of >= 22 bytes on average;
-                                    // denser text takes the per-lane path)
+// Pass 3.  Persistent and warp-autonomous: a warp takes UNITS of 8 KiB (four mask words per lane, a quarter of a tile) in
+// a grid stride -- units are independent, so a static stride is safe -- with the masks, the tile prefix and the per-warp
+// counts of its next unit already requested.  It numbers its lines from {tile prefix, counts of the 2 KiB pieces before
+// it} (two REDUX, no block barrier), compacts the newline positions into a list in shared memory and then emits
+// LINE-parallel: lane j writes line j, so the table stores are coalesced and no lane idles behind a neighbour that owns
+// three lines.  (One mask word per lane and iteration was instruction-bound: ~150 warp instructions per 2 KiB, most of
+// them the fixed part -- scans, address arithmetic, prefetch.)  With probes the prefix DFAs are staged once per block
+// and candidate lines collect in a per-warp queue until 32 of them fill a probe step.
+constexpr uint32_t kSplitList = 160;   // newline positions a warp compacts per unit (8 KiB: lines of >= 52 bytes on average;
+                                       // denser text takes the per-lane path)
+constexpr uint32_t kEmitQueue = 64;    // per warp: candidate lines waiting until 32 of them fill a probe step
 template <bool PROBE>
 __global__ void __launch_bounds__(1024, 2)
     split_emit_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, const void* __restrict__ masks,
@@ -554,144 +564,197 @@ __global__ void __launch_bounds__(1024, 2)
                       uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap, uint32_t* n_out,
                       SplitProbe pr) {
     __shared__ uint32_t s_list[32][kSplitList];
-    __shared__ uint32_t s_qn;
-    __shared__ uint32_t s_q[PROBE ? kProbeQueue : 1];
+    __shared__ uint32_t s_wq[PROBE ? 32 : 1][PROBE ? kEmitQueue : 1];
     __shared__ typename std::conditional<PROBE, ProbeSmem, uint32_t>::type s_probe;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0)
-        s_qn = 0;
+    uint32_t qn = 0; // (warp-uniform) lines in the warp's queue
     if constexpr (PROBE) {
         probe_stage(pr, s_probe);
         __syncthreads();
     }
-    using MaskT = typename std::conditional<PROBE, uint4, unsigned long long>::type;
-    const MaskT* mp = reinterpret_cast<const MaskT*>(masks);
-    uint32_t tile = blockIdx.x;
-    MaskT raw_n = MaskT{};
-    uint64_t prefix_n = 0, wa_n = 0;
-    if (tile < ntiles) {
-        raw_n = __ldg(mp + (uint64_t)tile * 1024 + tid);
-        prefix_n = __ldg(prefix + tile);
-        wa_n = __ldg(wagg + (uint64_t)tile * 32 + lane);
-    }
-    auto line_out = [&](uint32_t k, uint32_t start, uint32_t p) { // line k = [start, p)
+    __shared__ uint8_t s_cand[PROBE ? 32 : 1][PROBE ? kSplitList : 1];
+    // the lane's mask words: PROBE 4 x uint4 (16 chunks x {newline16 | candidate16 << 16}), else 2 x uint4 (16 x newline16)
+    auto mask_ptr = [&](uint32_t unit) {
+        return reinterpret_cast<const uint4*>(masks) + ((uint64_t)unit * 32 + lane) * (PROBE ? 4 : 2);
+    };
+    auto word = [&](const uint4* mp, int w, uint64_t& m, uint64_t& c) { // 64 bytes of input -> newline / candidate bits
+        if constexpr (PROBE) {
+            const uint4 q = __ldg(mp + w);
+            m = (uint64_t)__byte_perm(q.x, q.y, 0x5410) | ((uint64_t)__byte_perm(q.z, q.w, 0x5410) << 32);
+            c = (uint64_t)__byte_perm(q.x, q.y, 0x7632) | ((uint64_t)__byte_perm(q.z, q.w, 0x7632) << 32);
+        } else {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(mp) + w);
+            m = q.x | ((uint64_t)q.y << 32);
+            c = 0;
+        }
+    };
+    auto prefetch_unit = [&](uint32_t unit) { // the next unit's masks -> L2 (registers are too scarce to hold them)
+        const uint4* mp = mask_ptr(unit);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(mp));
+        if (PROBE)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + 2));
+    };
+    // line k = [start, p); cand: can its first byte start a match (recorded by pass 1 at the newline in front of it).
+    // Returns true when the line still has to be probed.
+    auto line_out = [&](uint32_t k, uint32_t start, uint32_t p, uint32_t cand) -> bool {
         if (k >= cap)
-            return;
+            return false;
         out_off[k] = start;
         out_len[k] = p - start;
         if constexpr (PROBE) {
             const uint32_t ll = p - start;
-            if (!ll) {
-                pr.flags[k] = (uint8_t)pr.empty_flags;
-                return;
-            }
-            // can the first byte start a match?  recorded by pass 1 at the newline in front of the line
-            uint32_t cand = 1;
-            if (start) {
-                const uint64_t vp = (uint64_t)start - 1 + shift;
-                cand = (__ldg(reinterpret_cast<const uint32_t*>(masks) + (vp >> 4)) >> (16 + (vp & 15))) & 1u;
-            }
-            if (!cand) {
-                pr.flags[k] = 0;
-            } else {
-                const uint32_t q = atomicAdd(&s_qn, 1u);
-                if (q < kProbeQueue)
-                    s_q[q] = k;
-                else
-                    pr.flags[k] = probe_line(pr, buf + start, ll); // queue full: probe in place
+            if (ll && cand)
+                return true;
+            pr.flags[k] = ll ? 0 : (uint8_t)pr.empty_flags;
+        }
+        return false;
+    };
+    // 32 queued lines, one per lane (a first version queued per BLOCK and probed between barriers: 16 % of the candidates
+    // overflowed that queue and were walked by single lanes from global memory -- 40 % of the kernel's instructions)
+    auto probe_step = [&](uint32_t first, uint32_t count) {
+        if constexpr (PROBE) {
+            if ((uint32_t)lane < count) {
+                const uint32_t kk = s_wq[wid][first + lane];
+                pr.flags[kk] = probe_line_smem(pr, s_probe, buf + out_off[kk], out_len[kk]);
             }
         }
     };
-    for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-        const MaskT raw = raw_n;
-        const uint64_t tile_prefix = prefix_n, wa = wa_n;
-        const uint32_t tn = tile + gridDim.x;
-        if (tn < ntiles) {
-            raw_n = __ldg(mp + (uint64_t)tn * 1024 + tid);
-            prefix_n = __ldg(prefix + tn);
-            wa_n = __ldg(wagg + (uint64_t)tn * 32 + lane);
-        }
-        const uint64_t vpos0 = ((uint64_t)tile * 1024 + tid) * 64;
-        uint64_t mk;
-        if constexpr (PROBE)
-            mk = (uint64_t)__byte_perm(raw.x, raw.y, 0x5410) | ((uint64_t)__byte_perm(raw.z, raw.w, 0x5410) << 32);
-        else
-            mk = raw;
-        // the warps before mine inside the tile: their line count and the end of their last newline
-        const uint32_t before = lane < wid ? 0xFFFFFFFFu : 0u;
-        const uint32_t my_off = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(wa >> 32) & before);
-        uint32_t my_start = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)wa & before);
-        if (!my_start)
-            my_start = OpCountMax::maxv(tile_prefix);
-        const uint32_t cnt = __popcll(mk);
-        uint32_t inc = cnt;
+    auto cand_at = [&](uint32_t start) -> uint32_t { // candidate bit of the line that starts at `start`, from the mask array
+        if (!PROBE || !start)
+            return 1;
+        const uint64_t vp = (uint64_t)start - 1 + shift;
+        return (__ldg(reinterpret_cast<const uint32_t*>(masks) + (vp >> 4)) >> (16 + (vp & 15))) & 1u;
+    };
+    const uint32_t nunits = ntiles * 8, ustride = gridDim.x * 32;
+    uint32_t unit = blockIdx.x * 32 + wid;
+    uint64_t prefix_n = 0, wa_n = 0;
+    if (unit < nunits) {
+        prefix_n = __ldg(prefix + (unit >> 3));
+        wa_n = __ldg(wagg + (uint64_t)(unit >> 3) * 32 + lane);
+    }
+    for (; unit < nunits; unit += ustride) {
+        {
+            const uint64_t tile_prefix = prefix_n, wa = wa_n;
+            const uint32_t un = unit + ustride;
+            if (un < nunits) {
+                prefetch_unit(un);
+                prefix_n = __ldg(prefix + (un >> 3));
+                wa_n = __ldg(wagg + (uint64_t)(un >> 3) * 32 + lane);
+            }
+            const uint32_t sub = unit & 7;
+            const uint64_t vpos0 = ((uint64_t)unit * 32 + lane) * 256; // the lane's 256 bytes
+            const uint4* mp = mask_ptr(unit);
+            uint32_t cnt = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if (lane >= d)
-                inc += t;
-        }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        const uint32_t k0 = OpCountMax::count(tile_prefix) + my_off;
-        uint32_t end_start = my_start; // start of the piece that is open after the warp's last newline
-        if (total <= kSplitList) {
-            uint32_t idx = inc - cnt;
-            while (mk) {
-                const int b = __ffsll((long long)mk) - 1;
-                mk &= mk - 1;
-                s_list[wid][idx++] = (uint32_t)(vpos0 + b - shift);
+            for (int w = 0; w < 4; ++w) {
+                uint64_t m, c;
+                word(mp, w, m, c);
+                cnt += __popcll(m);
             }
-            __syncwarp();
-            for (uint32_t j = lane; j < total; j += 32)
-                line_out((k0 + j) & 0x3FFFFFFFu, j ? s_list[wid][j - 1] + 1 : my_start, s_list[wid][j]);
-            if (total)
-                end_start = s_list[wid][total - 1] + 1;
-            __syncwarp();
-        } else {
-            // dense text: every lane writes its own lines
-            const uint32_t last = mk ? (uint32_t)(vpos0 + (63 - __clzll((long long)mk)) + 1 - shift) : 0u;
-            const uint32_t has = __ballot_sync(0xFFFFFFFFu, mk != 0);
-            const uint32_t below = has & ((1u << lane) - 1u);
-            const uint32_t prev_last = __shfl_sync(0xFFFFFFFFu, last, below ? 31 - __clz(below) : 0);
-            end_start = __shfl_sync(0xFFFFFFFFu, last, 31 - __clz(has)); // (has != 0: total > 0)
-            uint32_t k = k0 + (inc - cnt), start = below ? prev_last : my_start;
-            while (mk) {
-                const int b = __ffsll((long long)mk) - 1;
-                mk &= mk - 1;
-                const uint32_t p = (uint32_t)(vpos0 + b - shift);
-                line_out(k & 0x3FFFFFFFu, start, p);
-                ++k;
-                start = p + 1;
+            // the 2 KiB pieces of the tile before my unit: their line count and the end of their last newline
+            const uint32_t before = lane < sub * 4 ? 0xFFFFFFFFu : 0u;
+            const uint32_t my_off = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(wa >> 32) & before);
+            uint32_t my_start = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)wa & before);
+            if (!my_start)
+                my_start = OpCountMax::maxv(tile_prefix);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d)
+                    inc += t;
             }
-        }
-        if (tile == ntiles - 1 && wid == 31 && lane == 0) {
-            // inclusive total of the whole buffer: the unterminated last piece, if any
-            uint32_t k = (k0 + total) & 0x3FFFFFFFu;
-            if (end_start < len) {
-                if (k < cap) {
-                    out_off[k] = end_start;
-                    out_len[k] = len - end_start;
-                    if (PROBE)
-                        pr.flags[k] = probe_line(pr, buf + end_start, len - end_start);
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            const uint32_t k0 = OpCountMax::count(tile_prefix) + my_off;
+            uint32_t end_start = my_start; // start of the piece that is open after the unit's last newline
+            if (total <= kSplitList) {
+                uint32_t idx = inc - cnt;
+#pragma unroll 1
+                for (int w = 0; w < 4; ++w) { // (second read of the words: L1 hits)
+                    uint64_t m, c;
+                    word(mp, w, m, c);
+                    while (m) {
+                        const int b = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        if (PROBE)
+                            s_cand[wid][idx] = (uint8_t)((c >> b) & 1u);
+                        s_list[wid][idx++] = (uint32_t)(vpos0 + 64 * w + b - shift);
+                    }
                 }
-                ++k;
-            }
-            *n_out = k;
-        }
-        if constexpr (PROBE) {
-            if ((it & 15) == 15 || tn >= ntiles) { // (block-uniform) every 16 tiles and after the last one
-                __syncthreads(); // the queue and the line table entries of these tiles are visible to the block
-                const uint32_t qn = min(s_qn, kProbeQueue);
-                for (uint32_t q = tid; q < qn; q += 1024) {
-                    const uint32_t kk = s_q[q];
-                    pr.flags[kk] = probe_line_smem(pr, s_probe, buf + out_off[kk], out_len[kk]);
+                __syncwarp();
+                for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+                    const uint32_t j = j0 + lane, k = (k0 + j) & 0x3FFFFFFFu;
+                    bool want = false;
+                    if (j < total) {
+                        const uint32_t start = j ? s_list[wid][j - 1] + 1 : my_start;
+                        want = line_out(k, start, s_list[wid][j],
+                                        PROBE ? (j ? (uint32_t)s_cand[wid][j - 1] : cand_at(start)) : 1u);
+                    }
+                    if constexpr (PROBE) {
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, want);
+                        if (want)
+                            s_wq[wid][qn + __popc(bal & ((1u << lane) - 1u))] = k;
+                        qn += __popc(bal);
+                        __syncwarp(); // queue entries and the table entries of these lines are visible to the warp
+                        if (qn >= 32) {
+                            probe_step(qn - 32, 32);
+                            qn -= 32;
+                        }
+                    }
                 }
-                __syncthreads();
-                if (tid == 0)
-                    s_qn = 0;
+                if (total)
+                    end_start = s_list[wid][total - 1] + 1;
+                __syncwarp();
+            } else {
+                // dense text: every lane writes its own lines
+                uint32_t last = 0;
+#pragma unroll 1
+                for (int w = 0; w < 4; ++w) {
+                    uint64_t m, c;
+                    word(mp, w, m, c);
+                    if (m)
+                        last = (uint32_t)(vpos0 + 64 * w + (63 - __clzll((long long)m)) + 1 - shift);
+                }
+                const uint32_t has = __ballot_sync(0xFFFFFFFFu, cnt != 0);
+                const uint32_t below = has & ((1u << lane) - 1u);
+                const uint32_t prev_last = __shfl_sync(0xFFFFFFFFu, last, below ? 31 - __clz(below) : 0);
+                end_start = __shfl_sync(0xFFFFFFFFu, last, 31 - __clz(has)); // (has != 0: total > 0)
+                uint32_t k = k0 + (inc - cnt), start = below ? prev_last : my_start;
+#pragma unroll 1
+                for (int w = 0; w < 4; ++w) {
+                    uint64_t m, c;
+                    word(mp, w, m, c);
+                    while (m) {
+                        const int b = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        const uint32_t p = (uint32_t)(vpos0 + 64 * w + b - shift);
+                        if (line_out(k & 0x3FFFFFFFu, start, p, cand_at(start))) {
+                            if constexpr (PROBE)
+                                pr.flags[k & 0x3FFFFFFFu] = probe_line_smem(pr, s_probe, buf + start, p - start);
+                        }
+                        ++k;
+                        start = p + 1;
+                    }
+                }
+            }
+            if (unit == nunits - 1 && lane == 0) {
+                // inclusive total of the whole buffer: the unterminated last piece, if any
+                uint32_t k = (k0 + total) & 0x3FFFFFFFu;
+                if (end_start < len) {
+                    if (k < cap) {
+                        out_off[k] = end_start;
+                        out_len[k] = len - end_start;
+                        if (PROBE)
+                            pr.flags[k] = probe_line(pr, buf + end_start, len - end_start);
+                    }
+                    ++k;
+                }
+                *n_out = k;
             }
         }
     }
+    if constexpr (PROBE)
+        probe_step(0, qn); // what is left in the warp's queue
 }
 
 static int split_lookback_warps() {
@@ -732,7 +795,7 @@ static int launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_c
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         }
-        const uint32_t grid = std::min<uint32_t>(nt, (uint32_t)sms * 2);
+        const uint32_t grid = std::min<uint32_t>((nt + 3) / 4, (uint32_t)sms * 2);
         split_emit_kernel<PROBE><<<grid, 1024, 0, st>>>(d_buf, len, shift, masks, prefix, wagg, nt, d_off, d_len, cap,
                                                        d_n_out, pr);
         return 3;
@@ -3662,15 +3725,15 @@ uint32_t ml_fused_tiles(uint64_t line_cap) {
 // ml_fused_kernel chains two decoupled look-backs per tile, and a look-back waits for the slowest of the resident tiles
 // (see the split above: same effect, 0.48 ms for the 22 M lines of C3, i.e. 107 us per tile).  The arithmetic, however,
 // only needs the FLAGS (one byte per line) until the very last step, so the passes are cheap to repeat:
-//   pass 1  per tile of 8192 lines: the composed 2-state transition function            -> agg1[tile]
+//   pass 1  per tile of 16384 lines: the composed 2-state transition function           -> agg1[tile]
 //   scan    one block, OpMlState (ordered)                                              -> pre1[tile]
 //   pass 2  per tile: incoming state of every line (from pre1) -> number of events      -> agg2[tile]
 //   scan    one block, OpSum                                                            -> pre2[tile]
 //   pass 3  per tile: states again, exclusive event slots (from pre2), emission (reads off/len of the emitted lines)
 // Tiles never wait for each other.  Lines whose transition is the identity (in start-only mode: every line that does
 // not match) skip the composition.
-constexpr int kMlPassThreads = 512;
-constexpr int kMlPassItems = 16;
+constexpr int kMlPassThreads = 256;
+constexpr int kMlPassItems = 64; // lines per thread: the two block scans of a pass are paid once per 16 K lines
 constexpr uint32_t kMlPassTile = kMlPassThreads * kMlPassItems;
 
 uint32_t ml_pass_tiles(uint64_t line_cap) { return (uint32_t)((line_cap + 1 + kMlPassTile - 1) / kMlPassTile); }
@@ -3768,7 +3831,8 @@ __global__ void __launch_bounds__(kMlPassThreads)
                    uint32_t* __restrict__ out_len, uint8_t* __restrict__ out_flags, uint64_t cap,
                    unsigned long long* counters, uint64_t* total_out) {
     constexpr int THREADS = kMlPassThreads, ITEMS = kMlPassItems;
-    static_assert(ITEMS == 16, "one 16-byte load of flags per thread");
+    static_assert(ITEMS % 16 == 0, "16-byte loads of flags");
+    constexpr int NWORDS = ITEMS / 4;
     __shared__ uint64_t s_scan[THREADS / 32 + 1];
     const int tid = threadIdx.x;
     const uint32_t tile = blockIdx.x;
@@ -3776,23 +3840,31 @@ __global__ void __launch_bounds__(kMlPassThreads)
     if ((uint64_t)tile * kMlPassTile > n)
         return;
     const uint64_t base = (uint64_t)tile * kMlPassTile + (uint64_t)tid * ITEMS;
-    uint32_t fw[4] = {0, 0, 0, 0};
+    uint32_t fw[NWORDS];
     if (base + ITEMS <= n) {
-        const uint4 f4 = __ldg(reinterpret_cast<const uint4*>(flags + base));
-        fw[0] = f4.x & 0x07070707u, fw[1] = f4.y & 0x07070707u, fw[2] = f4.z & 0x07070707u, fw[3] = f4.w & 0x07070707u;
+#pragma unroll
+        for (int q = 0; q < ITEMS / 16; ++q) {
+            const uint4 f4 = __ldg(reinterpret_cast<const uint4*>(flags + base) + q);
+            fw[4 * q + 0] = f4.x & 0x07070707u, fw[4 * q + 1] = f4.y & 0x07070707u;
+            fw[4 * q + 2] = f4.z & 0x07070707u, fw[4 * q + 3] = f4.w & 0x07070707u;
+        }
     } else {
-        for (int k = 0; k < ITEMS; ++k)
-            if (base + k < n)
-                fw[k >> 2] |= (uint32_t)(flags[base + k] & 7u) << (8 * (k & 3));
+#pragma unroll
+        for (int w = 0; w < NWORDS; ++w) {
+            fw[w] = 0;
+            for (int b = 0; b < 4; ++b)
+                if (base + 4 * w + b < n)
+                    fw[w] |= (uint32_t)(flags[base + 4 * w + b] & 7u) << (8 * b);
+        }
     }
     const uint32_t nvalid = base >= n ? 0u : (uint32_t)min((uint64_t)ITEMS, n - base); // lines (not the eof element)
     // ---- the thread's lines composed: both incoming states stepped side by side
     uint32_t sA = 0, sB = 1, lbA = 0, lbB = 0; // lbX: (index + 1) of the last line opened inside the run, 0 = none
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
+    for (int w = 0; w < NWORDS; ++w) {
         if (fw[w] == 0 && (tb.ident & 1u))
             continue; // four lines that change nothing
-#pragma unroll
+#pragma unroll 1
         for (int b = 0; b < 4; ++b) {
             const int k = w * 4 + b;
             const uint32_t fl = (fw[w] >> (8 * b)) & 0xFFu;
@@ -3829,7 +3901,7 @@ __global__ void __launch_bounds__(kMlPassThreads)
     auto sweep = [&](auto& sink) {
         uint32_t st = st0, lb = lb0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < NWORDS; ++w) {
             if (fw[w] == 0 && (tb.skip[st] & 1u) && (uint32_t)(w * 4 + 4) <= nvalid)
                 continue; // four lines without any effect in this state
 #pragma unroll 1
