@@ -539,6 +539,148 @@ LC_HD bool lc_delim_fsm(const uint8_t* v, int32_t begin, int32_t end, uint8_t se
     return lc_delim_finish(r, push);
 }
 
+// ---- bit-parallel form for well-formed records ---------------------------------------------------------------------
+// The machine above steps once per separator / quote, and with 32 different lines in a warp the loop over the specials
+// of a chunk runs as often as the busiest lane needs (ncu: the kernel issues ~40 instructions per input byte).  For a
+// record in which every quote sits where the machine accepts one, the columns follow from three masks per chunk:
+//   S = separators, Q = quotes, P = inclusive prefix-XOR of Q (with the carry of the chunks before): P is 1 from an
+//   opening quote up to the byte before its closing quote, so the REAL separators are S & ~P, an opening quote is
+//   Q & P and a closing quote is Q & ~P.
+// Well-formed (exactly the paths of the machine that do not end in an error):
+//   * an opening quote is the first byte of a column (record start or behind a real separator) or directly follows a
+//     closing quote (the escaped quote "" inside a quoted column: DOUBLE_QUOTE -> QUOTE);
+//   * a closing quote is followed by a real separator, by another quote, or by the end of the record
+//     (DOUBLE_QUOTE + ordinary byte is the machine's error, DATA + quote likewise);
+//   * the record does not end inside a quoted column.
+// A column with quotes is then `"` content `"`: content = [first + 1, last - 1), doubled quotes = (quotes - 2) / 2.
+// Anything else returns false and the caller runs lc_delim_fsm on the record (which also decides about errors).
+struct LcDelimFast {
+    uint32_t inq;        // 0 / all ones: inside a quoted section where the step starts
+    uint32_t prev_rs;    // the byte before the step's first byte was a real separator (or the record starts here)
+    uint32_t prev_close; // ... was a closing quote
+    uint32_t nq;         // quotes of the open column so far
+};
+
+LC_HD void lc_delim_fast_start(LcDelimFast& r) {
+    r.inq = 0;
+    r.prev_rs = 1;
+    r.prev_close = 0;
+    r.nq = 0;
+}
+
+LC_HD uint32_t lc_popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+LC_HD uint32_t lc_low_bits(uint32_t n) { return n >= 32 ? 0xFFFFFFFFu : (1u << n) - 1u; } // the n lowest bits
+
+// One step over W (16 or 32) bytes of the record's 16-byte aligned frame, [q0, q0 + W).  ms / mq: masks of the bytes
+// equal to the separator / quote.  mark(p, quotes) is called for every real separator: p = its offset from the line
+// start, quotes = the number of quotes of the column it closes (a caller that wants columns derives them: the column
+// starts behind the previous mark; with quotes it is `"` content `"`, doubled quotes = (quotes - 2) / 2).
+template <int W, class Mark>
+LC_HD bool lc_delim_fast_step(LcDelimFast& r, uint32_t ms, uint32_t mq, uint32_t q0, uint32_t qb, uint32_t qe,
+                              uint32_t mis, Mark& mark) {
+    const uint32_t b0 = q0 < qb ? qb - q0 : 0u;              // first byte of the step that belongs to the record
+    const uint32_t nb = qe - q0 < (uint32_t)W ? qe - q0 : W; // bytes of the step in front of the record's end
+    const uint32_t V = lc_low_bits(nb) & ~lc_low_bits(b0);   // (nb > b0: the caller only passes steps with bytes)
+    const uint32_t S = ms & V, Q = mq & V;
+    uint32_t P = Q;
+    P ^= P << 1;
+    P ^= P << 2;
+    P ^= P << 4;
+    P ^= P << 8;
+    if (W > 16)
+        P ^= P << 16;
+    P = (P ^ r.inq) & lc_low_bits(W);
+    const uint32_t RS = S & ~P, open = Q & P, close = Q & ~P;
+    const uint32_t first = 1u << b0, last = 1u << (nb - 1);
+    const bool ends = qe - q0 <= (uint32_t)W; // the record ends inside this step
+    // opening quotes: behind a real separator / at the record start, or behind a closing quote
+    uint32_t bad = open & ~(((RS | close) << 1) | ((r.prev_rs | r.prev_close) ? first : 0u));
+    // closing quotes: in front of a real separator or a quote; the record's last byte may be one; the successor of
+    // the step's last byte is checked with the next step (prev_close)
+    bad |= close & (ends ? V : (V & ~last)) & ~(((RS | Q) >> 1) | (ends ? last : 0u));
+    if (r.prev_close && !((RS | Q) & first))
+        bad |= 1u;
+    if (bad)
+        return false;
+    uint32_t m = RS, cb = b0, nq = r.nq;
+    while (m) {
+#if defined(__CUDA_ARCH__)
+        const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+#else
+        const uint32_t b = (uint32_t)__builtin_ctz(m);
+#endif
+        m &= m - 1;
+        mark((uint32_t)(q0 + b - mis), nq + lc_popc32(Q & lc_low_bits(b) & ~lc_low_bits(cb)));
+        nq = 0;
+        cb = b + 1;
+    }
+    r.nq = nq + lc_popc32(Q & ~lc_low_bits(cb));
+    r.inq = (P & last) ? 0xFFFFFFFFu : 0u;
+    r.prev_rs = (RS & last) ? 1u : 0u;
+    r.prev_close = (close & last) ? 1u : 0u;
+    return true;
+}
+
+// end of the record: the mark that closes the last column; false = the record ends inside a quoted column
+template <class Mark>
+LC_HD bool lc_delim_fast_finish(LcDelimFast& r, int32_t end, Mark& mark) {
+    if (r.inq)
+        return false;
+    mark((uint32_t)end, r.nq);
+    return true;
+}
+
+// column [start, p) that carries `quotes` quotes -> push(first byte, length, doubled quotes)
+template <class Push>
+LC_HD void lc_delim_fast_column(uint32_t start, uint32_t p, uint32_t quotes, Push& push) {
+    if (quotes)
+        push(start + 1, p - start - 2, (quotes - 2) >> 1);
+    else
+        push(start, p - start, 0u);
+}
+
+// whole record, 32 bytes per step as in the kernel (CPU-tier tests).  Returns false when the record is not well-formed
+// in the sense above -- columns pushed so far are then to be discarded.
+template <class Push>
+LC_HD bool lc_delim_fast(const uint8_t* v, int32_t begin, int32_t end, uint8_t sep, uint8_t quote, Push& push) {
+    const uint32_t sep_splat = sep * 0x01010101u, quote_splat = quote * 0x01010101u;
+    const uint32_t mis = (uint32_t)((uintptr_t)v & 15u);
+    const uint8_t* abase = v - mis;
+    const uint32_t qb = (uint32_t)begin + mis, qe = (uint32_t)end + mis;
+    LcDelimFast r;
+    lc_delim_fast_start(r);
+    uint32_t start = (uint32_t)begin;
+    auto mark = [&](uint32_t p, uint32_t quotes) {
+        lc_delim_fast_column(start, p, quotes, push);
+        start = p + 1;
+    };
+    for (uint32_t qc = (qb >> 4) & ~1u; end > begin && qc <= ((qe - 1) >> 4); qc += 2) {
+        uint32_t ms = 0, mq = 0;
+        for (uint32_t h = 0; h < 2; ++h) {
+            if ((qc + h) * 16 >= qe || (qc + h + 1) * 16 <= qb)
+                continue; // no byte of the record in this half: not read
+            uint32_t w[4];
+#if defined(__CUDA_ARCH__)
+            const uint4 vv = __ldg(reinterpret_cast<const uint4*>(abase) + qc + h);
+            w[0] = vv.x, w[1] = vv.y, w[2] = vv.z, w[3] = vv.w;
+#else
+            memcpy(w, abase + (size_t)(qc + h) * 16, 16);
+#endif
+            ms |= lc_eq_mask16(w, sep_splat) << (16 * h);
+            mq |= lc_eq_mask16(w, quote_splat) << (16 * h);
+        }
+        if (!lc_delim_fast_step<32>(r, ms, mq, qc * 16, qb, qe, mis, mark))
+            return false;
+    }
+    return lc_delim_fast_finish(r, end, mark);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // SLS wire format of LOG events (next row): the hand-rolled protobuf writer of
 // core/protobuf/sls/LogGroupSerializer.cpp:33-143,232-262 as size and emit functions over spans of the arena.

@@ -4330,7 +4330,7 @@ __global__ void __launch_bounds__(1024, 1)
         sts_u64(info_abs + lane * 8, g0, nch);
         const uint32_t max_nch = __reduce_max_sync(0xFFFFFFFFu, nch);
         uint32_t nf = 0;
-        auto push = [&](uint32_t o, uint32_t l, uint32_t dq) {
+        auto push = [&](uint32_t o, uint32_t l, uint32_t dq) { // (the state machine's columns: fallback only)
             if (nf < MF) {
                 fo[nf] = eo + o;
                 fl[nf] = l;
@@ -4338,44 +4338,52 @@ __global__ void __launch_bounds__(1024, 1)
             }
             ++nf;
         };
-        bool ok = true, started = false;
-        LcDelimRun run;
-        run.state = run.dq = run.fs = run.fe = 0;
-        run.cur = 0;
+        // bit-parallel path: a real separator (or the record's end) at offset p closes column nf, which holds `quotes`
+        // quotes; offset and quote count are parked in the row and turned into the column record after the last byte
+        auto mark = [&](uint32_t p, uint32_t quotes) {
+            if (nf < MF) {
+                fo[nf] = p;
+                fd[nf] = quotes;
+            }
+            ++nf;
+        };
+        bool ok = true, started = false, slow = false; // slow: not well-formed for the bit-parallel path
+        LcDelimFast run;
+        lc_delim_fast_start(run);
         const uint32_t qe = mis + (uint32_t)endIdx;
         uint32_t qb = mis; // becomes the frame position of the first non-blank byte
         const bool parse = valid && endIdx > 0;
         __syncwarp();
         for (uint32_t s0 = 0; s0 < max_nch; s0 += LCT_STAGE_CHUNKS) {
             L.stage(s0);
-            if (parse && ok) {
+            if (parse && ok && !slow) {
                 const uint32_t kb = nch < s0 + LCT_STAGE_CHUNKS ? nch : s0 + LCT_STAGE_CHUNKS;
-                for (uint32_t k = s0; k < kb; ++k) {
+                for (uint32_t k = s0; k < kb; k += 2) { // 32 bytes per step (the second chunk may lie behind the record)
                     const uint32_t q = k & 7;
-                    const uint4 vv = lds_u128_v(tile_abs + (q << 9) + (L.rd_lane16 ^ (q << 4)));
-                    const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+                    const uint4 v0 = lds_u128_v(tile_abs + (q << 9) + (L.rd_lane16 ^ (q << 4)));
+                    const uint4 v1 = lds_u128_v(tile_abs + ((q + 1) << 9) + (L.rd_lane16 ^ ((q + 1) << 4)));
                     const uint32_t q0 = k * 16;
                     if (!started) {
                         // leading ' ' (:233-238): the first byte that is not a blank starts the record
-                        uint32_t nb = ~match16b(vv, 0x20202020u) & 0xFFFFu;
+                        uint32_t nb = ~(match16c(v0, 0x20202020u) | (match16c(v1, 0x20202020u) << 16));
                         if (q0 < qb)
-                            nb &= ~((1u << (qb - q0)) - 1u);
-                        if (qe - q0 < 16)
-                            nb &= (1u << (qe - q0)) - 1u;
+                            nb &= ~lc_low_bits(qb - q0);
+                        nb &= lc_low_bits(qe - q0);
                         if (!nb)
                             continue;
                         qb = q0 + (uint32_t)(__ffs((int)nb) - 1);
-                        lc_delim_start(run, (int32_t)(qb - mis), mis);
                         started = true;
                         if (cfg.nkeys == 0) { // nothing to parse into: the line fails once it is known not to be blank
                             ok = false;
                             break;
                         }
                     }
-                    // (one code path for every chunk: a separate fast path for quote-free chunks made the warp run
-                    //  both paths for nearly every chunk -- some lane always sits on a partial or quoted chunk)
-                    if (!lc_delim_chunk(run, w, q0, qb, qe, sep_splat, quote_splat, push)) {
-                        ok = false;
+                    // bit-parallel columns (lc_exec.cuh); a record with a quote the machine would not accept there is
+                    // redone by the machine itself after the batch (rare, and it also decides about the error)
+                    if (!lc_delim_fast_step<32>(run, match16c(v0, sep_splat) | (match16c(v1, sep_splat) << 16),
+                                                match16c(v0, quote_splat) | (match16c(v1, quote_splat) << 16), q0, qb,
+                                                qe, mis, mark)) {
+                        slow = true;
                         break;
                     }
                 }
@@ -4390,8 +4398,25 @@ __global__ void __launch_bounds__(1024, 1)
                 st = 1;
                 nf = 0;
             } else {
-                if (ok)
-                    ok = lc_delim_finish(run, push);
+                if (!slow && !lc_delim_fast_finish(run, endIdx, mark))
+                    slow = true;
+                const uint32_t nf_fast = nf < MF ? nf : MF;
+                if (!slow) {
+                    // marks -> column records: a column starts behind the previous mark
+                    uint32_t prev = qb - mis;
+                    for (uint32_t k = 0; k < nf_fast; ++k) {
+                        const uint32_t p = fo[k], c = fd[k];
+                        fo[k] = eo + prev + (c ? 1u : 0u);
+                        fl[k] = p - prev - (c ? 2u : 0u);
+                        fd[k] = c ? (c - 2) >> 1 : 0u;
+                        prev = p + 1;
+                    }
+                } else { // the state machine over the whole record, straight from global memory
+                    nf = 0;
+                    ok = lc_delim_fsm(base + eo, (int32_t)(qb - mis), endIdx, cfg.sep[0], cfg.quote, push);
+                    for (uint32_t k = nf; ok && k < nf_fast; ++k) // marks only the first attempt left behind
+                        fo[k] = fd[k] = 0;
+                }
                 if (!ok) {
                     st = 1;
                     nf = 0;

@@ -126,6 +126,22 @@ class EmulRegex:
             pass
 
 
+def delim_fast(buf: np.ndarray, line_off: int, begin: int, end: int, sep: int, quote: int, cap: int = 64):
+    """Bit-parallel delimiter path of the kernels (lc_delim_fast); None when the record is handed to the state machine."""
+    L = lib()
+    L.emul_delim_fast.restype = C.c_int64
+    L.emul_delim_fast.argtypes = L.emul_delim_fsm.argtypes
+    fo = np.zeros(cap, np.uint32)
+    fl = np.zeros(cap, np.uint32)
+    fd = np.zeros(cap, np.uint32)
+    n = L.emul_delim_fast(buf.ctypes.data + line_off, begin, end, sep, quote, fo.ctypes.data_as(C.c_void_p),
+                          fl.ctypes.data_as(C.c_void_p), fd.ctypes.data_as(C.c_void_p), cap)
+    if n == -2:
+        return None
+    k = min(n, cap)
+    return int(n), fo[:k].copy(), fl[:k].copy(), fd[:k].copy()
+
+
 def delim_fsm(buf: np.ndarray, line_off: int, begin: int, end: int, sep: int, quote: int, cap: int = 64):
     """Run-skipping delimiter FSM of the kernels on the line starting at buf[line_off] (buf must keep 16 spare
     bytes on both sides of the line).  Returns None on an FSM error, else the list of (off, len, dq) columns."""

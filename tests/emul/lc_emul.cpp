@@ -146,6 +146,24 @@ int64_t emul_delim_fsm(const uint8_t* line, int32_t begin, int32_t end, uint8_t 
 }
 
 extern "C" {
+// bit-parallel form of the same machine for well-formed records (lc_exec.cuh: lc_delim_fast): column count, or -2 when
+// the record has to go through lc_delim_fsm (which then also decides about errors)
+int64_t emul_delim_fast(const uint8_t* line, int32_t begin, int32_t end, uint8_t sep, uint8_t quote, uint32_t* f_off,
+                        uint32_t* f_len, uint32_t* f_dq, int64_t cap) {
+    int64_t n = 0;
+    auto push = [&](uint32_t o, uint32_t l, uint32_t dq) {
+        if (n < cap) {
+            f_off[n] = o;
+            f_len[n] = l;
+            f_dq[n] = dq;
+        }
+        ++n;
+    };
+    return lc_delim_fast(line, begin, end, sep, quote, push) ? n : -2;
+}
+}
+
+extern "C" {
 // SLS wire format, host build of the kernels' size / emit functions (lc_exec.cuh), one "lane".  Returns the total
 // size; writes when out_cap suffices.  Same contract as lc_sls_serialize_logs.
 uint64_t emul_sls_serialize_logs(const uint8_t* base, uint64_t n, const uint32_t* ev_time, const uint32_t* ev_ns,
