@@ -3944,7 +3944,12 @@ __global__ void __launch_bounds__(kMlPassThreads)
             agg2[tile] = tot2;
         return;
     }
-    // ---- emission at the exclusive prefix of the counts
+    // ---- emission at the exclusive prefix of the counts.  The sweep only RECORDS what each event is made of; the records
+    // are then turned into output rows one per thread (independent gathers of off / len, coalesced stores) -- a thread
+    // that emitted its three or four events one after the other paid a DRAM round trip for each of them.
+    constexpr uint32_t LIST = 3072; // events of a tile that fit the list (more: the threads write their events directly)
+    __shared__ uint32_t s_rec[LIST][2];
+    const uint64_t pos0 = __ldg(pre2 + tile);
     struct EmitSink : MlEmitSink {
         uint32_t total_len_;
         // begin + content.size() == sourceVal.size() (:174): only the last line can end where the buffer ends (every
@@ -3952,23 +3957,115 @@ __global__ void __launch_bounds__(kMlPassThreads)
         __device__ void prepare(uint32_t j) {
             is_last = (j == n) ? 1u : ((j + 1 == n && off[j] + len[j] == total_len_) ? 1u : 0u);
         }
-    } es;
-    es.discard = m.discard;
-    es.off = off;
-    es.len = len;
-    es.total_len = total_len;
-    es.total_len_ = total_len;
-    es.out_off = out_off;
-    es.out_len = out_len;
-    es.out_flags = out_flags;
-    es.cap = cap;
-    es.pos = __ldg(pre2 + tile) + ex2;
-    es.n = (uint32_t)n;
-    es.is_last = 0;
-    sweep(es);
-    if (base <= n && n < base + ITEMS)
-        *total_out = es.pos;
-    uint32_t me = es.matched_events, ul = es.unmatch_lines;
+    };
+    // kind: 0 one line (a) | 1 lines a..j up to the end of j | 2 lines a..j-1 (without the line feed) | 3 a..end of buffer
+    struct RecSink {
+        uint32_t (*rec)[2];
+        const uint32_t* off;
+        const uint32_t* len;
+        uint64_t pos0, pos;
+        uint32_t total_len, n, is_last, matched_events, unmatch_lines;
+        bool discard;
+        __device__ void prepare(uint32_t j) {
+            is_last = (j == n) ? 1u : ((j + 1 == n && off[j] + len[j] == total_len) ? 1u : 0u);
+        }
+        __device__ void put(uint32_t kind, uint32_t a, uint32_t j, uint32_t matched) {
+            const uint32_t idx = (uint32_t)(pos - pos0);
+            rec[idx][0] = a | (kind << 30);
+            rec[idx][1] = j | (matched << 30) | (is_last << 31);
+            ++pos;
+        }
+        __device__ void single(uint32_t j, bool matched) {
+            if (matched) {
+                put(0, j, j, 1);
+                ++matched_events;
+            } else if (len[j] != 0) {
+                ++unmatch_lines;
+                if (!discard)
+                    put(0, j, j, 0);
+            }
+        }
+        __device__ void to_end(uint32_t lb, uint32_t j) {
+            put(1, lb, j, 1);
+            ++matched_events;
+        }
+        __device__ void to_prev(uint32_t lb, uint32_t j) {
+            put(2, lb, j, 1);
+            ++matched_events;
+        }
+        __device__ void to_eof(uint32_t lb) {
+            is_last = 1;
+            put(3, lb, 0, 1);
+            ++matched_events;
+        }
+        __device__ void span(uint32_t lb, uint32_t jl, uint32_t flag_line) {
+            bool none;
+            const uint32_t last = ml_span_last(len, lb, jl, flag_line == n, none);
+            if (none)
+                return;
+            unmatch_lines += last - lb + 1;
+            if (!discard)
+                for (uint32_t k = lb; k <= last; ++k)
+                    put(0, k, k, 0);
+        }
+    };
+    uint32_t me, ul;
+    if (tot2 <= LIST) { // (block-uniform)
+        RecSink rs;
+        rs.rec = s_rec;
+        rs.off = off;
+        rs.len = len;
+        rs.pos0 = pos0;
+        rs.pos = pos0 + ex2;
+        rs.total_len = total_len;
+        rs.n = (uint32_t)n;
+        rs.is_last = 0;
+        rs.matched_events = rs.unmatch_lines = 0;
+        rs.discard = m.discard;
+        sweep(rs);
+        if (base <= n && n < base + ITEMS)
+            *total_out = rs.pos;
+        me = rs.matched_events, ul = rs.unmatch_lines;
+        __syncthreads();
+        for (uint32_t e = tid; e < (uint32_t)tot2; e += THREADS) {
+            const uint64_t at = pos0 + e;
+            if (at >= cap)
+                break;
+            const uint32_t w0 = s_rec[e][0], w1 = s_rec[e][1];
+            const uint32_t kind = w0 >> 30, a = w0 & 0x3FFFFFFFu, j = w1 & 0x3FFFFFFFu;
+            const uint32_t o = __ldg(off + a);
+            uint32_t l;
+            if (kind == 0)
+                l = __ldg(len + a);
+            else if (kind == 1)
+                l = __ldg(off + j) + __ldg(len + j) - o;
+            else if (kind == 2)
+                l = __ldg(off + j) - 1 - o;
+            else
+                l = total_len - o;
+            out_off[at] = o;
+            out_len[at] = l;
+            out_flags[at] = (uint8_t)((w1 >> 31) | (((w1 >> 30) & 1u) << 1));
+        }
+    } else {
+        EmitSink es;
+        es.discard = m.discard;
+        es.off = off;
+        es.len = len;
+        es.total_len = total_len;
+        es.total_len_ = total_len;
+        es.out_off = out_off;
+        es.out_len = out_len;
+        es.out_flags = out_flags;
+        es.cap = cap;
+        es.pos = pos0 + ex2;
+        es.n = (uint32_t)n;
+        es.is_last = 0;
+        sweep(es);
+        if (base <= n && n < base + ITEMS)
+            *total_out = es.pos;
+        me = es.matched_events, ul = es.unmatch_lines;
+    }
     for (int d = 16; d; d >>= 1) {
         me += __shfl_down_sync(0xFFFFFFFFu, me, d);
         ul += __shfl_down_sync(0xFFFFFFFFu, ul, d);
