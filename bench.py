@@ -163,6 +163,21 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def pinned_array(pins, src, dtype):
+    """numpy view of a pinned allocation (lc_host_alloc); src = an array to copy in, or a byte count."""
+    import loongcollector_b200 as lc
+    L = lc.lib()
+    nbytes = int(src.nbytes) if isinstance(src, np.ndarray) else int(src)
+    p = L.lc_host_alloc(max(nbytes, 16))
+    if not p:
+        raise RuntimeError("lc_host_alloc failed")
+    pins.append(p)
+    arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(max(nbytes, 1),))[:nbytes].view(dtype)
+    if isinstance(src, np.ndarray):
+        arr[:] = np.ascontiguousarray(src).view(dtype).reshape(-1)
+    return arr
+
+
 def profile_traffic(config):
     """dram bytes per launch of the config's dominant kernel from the committed ncu summary (stamped with the git
     hash of the kernel source it was captured on; None when the source has changed since)."""
@@ -475,7 +490,7 @@ class C2(Config):
 class C1(Config):
     name = "c1"
     metric = "split_log_MBps"
-    dominant = "split_kernel"
+    dominant = "split_mask_kernel + split_scan_kernel + split_emit_kernel"
 
     def workload(self):
         return "C1: ProcessorSplitLogStringNative newline split, %d lines x 512 B per GPU" % self.n
@@ -564,7 +579,7 @@ class C1(Config):
 class C3(Config):
     name = "c3"
     metric = "multiline_split_log_MBps"
-    dominant = "split_kernel + ml_*_kernel"
+    dominant = "split_mask_kernel + split_scan_kernel + split_emit_kernel + ml_pass_kernel<1..3> + ml_tile_scan_kernel"
 
     def workload(self):
         return "C3: ProcessorSplitMultilineLogStringNative Java stack traces, start pattern, %d records (%.0f B avg, " \
@@ -665,7 +680,7 @@ class C3(Config):
 class C4(Config):
     name = "c4"
     metric = "delimiter_regex_chain_log_MBps"
-    dominant = "delim_kernel + regex_tdfa_staged_kernel"
+    dominant = "delim_tiled_kernel + regex_tdfa_staged_kernel"
     MF = 11
 
     def workload(self):
@@ -745,35 +760,46 @@ class C4(Config):
                                 "sample": "%d CSV lines, flat oracle delimiter FSM + PCRE2 on column 3, 1 thread" % ns}}
 
     def e2e_abi_setup(self):
+        # host buffers (pinned) -> H2D once -> delimiter stage with the column tap -> regex stage on the tapped column ->
+        # D2H of both stages' tables: the device-pointer C-ABI calls of the chain plus the copies an integration makes
+        # (the host-pointer entry points would upload the arena twice, once per stage)
+        import torch
         n, MF, G = self.n, self.MF, self.G
-        self.h = {k: np.zeros(s, d) for k, s, d in (("st", n, np.uint8), ("nf", n, np.uint32),
-                                                    ("fo", n * MF, np.uint32), ("fl", n * MF, np.uint32),
-                                                    ("fd", n * MF, np.uint32), ("rs", n, np.uint8),
-                                                    ("rco", n * G, np.uint32), ("rcl", n * G, np.uint32))}
-        self.e2e_h2d = int(2 * (self.in_bytes + 8 * n))
+        self._pins = []
+        self.hin = {k: torch.from_numpy(pinned_array(self._pins, a, a.dtype))
+                    for k, a in (("buf", self.buf), ("off", self.off.view(np.int32)), ("ln", self.ln.view(np.int32)))}
+        self.h = {k: pinned_array(self._pins, s_ * np.dtype(d).itemsize, d)
+                  for k, s_, d in (("st", n, np.uint8), ("nf", n, np.int32), ("fo", n * MF, np.int32),
+                                   ("fl", n * MF, np.int32), ("fd", n * MF, np.int32), ("rs", n, np.uint8),
+                                   ("rco", n * G, np.int32), ("rcl", n * G, np.int32))}
+        self.ht = {k: torch.from_numpy(v) for k, v in self.h.items()}
+        self._stream = torch.cuda.Stream(self.dev)
+        self.eng.set_stream(self._stream.cuda_stream)  # copies and kernels in one queue
+        self.e2e_h2d = int(self.in_bytes + 8 * n)
         self.e2e_d2h = int(n * (5 + 12 * MF) + n * (1 + 8 * G))
 
     def e2e_abi_step(self):
-        import loongcollector_b200 as lc
-        L = lc.lib()
-        h, n, MF = self.h, self.n, self.MF
-        sep = np.frombuffer(b",", np.uint8)
-        rc = L.lc_delim_parse(self.eng._h, _vp(self.buf), self.in_bytes, _vp(self.off), _vp(self.ln), n, _vp(sep), 1,
-                              ord('"'), 10, 1, 1, MF, _vp(h["st"]), _vp(h["nf"]), _vp(h["fo"]), _vp(h["fl"]),
-                              _vp(h["fd"]))
-        if rc == 0:
-            uo = np.ascontiguousarray(h["fo"].reshape(n, MF)[:, 3])
-            ul = np.ascontiguousarray(h["fl"].reshape(n, MF)[:, 3])
-            rc = L.lc_regex_parse(self.eng._h, self.rx._h, _vp(self.buf), self.in_bytes, _vp(uo), _vp(ul), n, self.G,
-                                  _vp(h["rs"]), _vp(h["rco"]), _vp(h["rcl"]))
-        if rc != 0:
-            raise RuntimeError(L.lc_last_error().decode())
+        import torch
+        with torch.cuda.stream(self._stream):
+            self.d_buf.copy_(self.hin["buf"], non_blocking=True)
+            self.d_off.copy_(self.hin["off"], non_blocking=True)
+            self.d_len.copy_(self.hin["ln"], non_blocking=True)
+            self.step()
+            for k, d in (("st", self.st), ("nf", self.nf), ("fo", self.fo), ("fl", self.fl), ("fd", self.fd),
+                         ("rs", self.rs), ("rco", self.rco), ("rcl", self.rcl)):
+                self.ht[k].copy_(d, non_blocking=True)
+        self._stream.synchronize()
 
     def e2e_abi_check(self, st):
         assert np.array_equal(self.h["rs"], self.rs.cpu().numpy())
+        assert np.array_equal(self.h["fo"], self.fo.cpu().numpy())
 
     def e2e_abi_free(self):
-        pass
+        import loongcollector_b200 as lc
+        self.eng.set_stream(None)  # back to the engine's own stream
+        self.hin = self.ht = self.h = None
+        for p_ in self._pins:
+            lc.lib().lc_host_free(p_)
 
     def cpu_baseline(self):
         from loongcollector_b200 import synth
@@ -919,19 +945,28 @@ class C5(Config):
 
     def e2e_abi_setup(self):
         b = self.subs[0]
-        self.hb = b["buf"][:b["bytes"]].cpu().numpy()
-        self.ho = b["off"].cpu().numpy().view(np.uint32)
-        self.hl = b["len"].cpu().numpy().view(np.uint32)
+        self._pins = []
+        self.hb = pinned_array(self._pins, b["buf"][:b["bytes"]].cpu().numpy(), np.uint8)
+        self.ho = pinned_array(self._pins, b["off"].cpu().numpy().view(np.uint32), np.uint32)
+        self.hl = pinned_array(self._pins, b["len"].cpu().numpy().view(np.uint32), np.uint32)
         n = self.sub
-        self.h = {"wh": np.zeros(n, np.uint8), "st": np.zeros(n, np.uint8), "co": np.zeros(n * self.GP, np.uint32),
-                  "cl": np.zeros(n * self.GP, np.uint32)}
+        self.h = {"wh": pinned_array(self._pins, n, np.uint8), "st": pinned_array(self._pins, n, np.uint8),
+                  "co": pinned_array(self._pins, n * self.GP * 4, np.uint32),
+                  "cl": pinned_array(self._pins, n * self.GP * 4, np.uint32)}
+        self._multi = self.eng._multi_handles(self.rxs, self.nkeys)
         self.e2e_h2d = int(b["bytes"] + 8 * n)
         self.e2e_d2h = int(n * (2 + 8 * self.GP))
         self.e2e_bytes = int(b["bytes"])
 
     def e2e_abi_step(self):
-        got = self.eng.regex_parse_multi(self.rxs, self.nkeys, self.hb, self.ho, self.hl, row_pitch=self.GP)
-        self.h["st"] = got[1]
+        import loongcollector_b200 as lc
+        L = lc.lib()
+        arr, nk = self._multi
+        rc = L.lc_regex_parse_multi(self.eng._h, arr, len(self.rxs), _vp(nk), _vp(self.hb), self.hb.size, _vp(self.ho),
+                                    _vp(self.hl), self.sub, None, _vp(self.h["wh"]), _vp(self.h["st"]), self.GP,
+                                    _vp(self.h["co"]), _vp(self.h["cl"]))
+        if rc != 0:
+            raise RuntimeError(L.lc_last_error().decode())
 
     def e2e_abi_check(self, st):
         pass
@@ -1113,6 +1148,8 @@ def run_ours(args):
     if mode == "auto":
         mode = "plugin" if args.config == "c2" else "abi"
     if mode in ("plugin", "abi"):
+        import torch
+        torch.cuda.synchronize()
         cfg.e2e_abi_setup()
         cfg.e2e_abi_step()
         barrier()

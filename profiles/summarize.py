@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Turns an .ncu-rep (read with `ncu -i ... --page raw --csv`) into the small JSON/markdown summaries committed
-under profiles/.  Usage: python profiles/summarize.py <rep> <kernel-substring> <tag>"""
+under profiles/.  Usage: python profiles/summarize.py <rep> <kernel-substring> <tag> [output directory]"""
 import csv
 import json
 import os
@@ -41,10 +41,10 @@ def main():
                 rec.setdefault("stalls_per_issue", {})[
                     h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")] = r[i]
         out.append(rec)
-    here = os.path.dirname(os.path.abspath(__file__))
+    here = sys.argv[4] if len(sys.argv) > 4 else os.path.dirname(os.path.abspath(__file__))
     with open(os.path.join(here, tag + ".json"), "w") as f:
         json.dump(out, f, indent=1)
-    print(json.dumps(out, indent=1))
+    print(json.dumps([{k: v for k, v in r.items() if k in ("kernel", "gpu__time_duration.sum")} for r in out]))
 
 
 if __name__ == "__main__":

@@ -682,3 +682,17 @@ def test_split_reports_too_large_beyond_2_pow_30_pieces(eng):
                                      C.c_void_p(ln.data_ptr()), 1024, C.byref(got))
     assert rc == lc.capi.LC_ERR_TOO_LARGE, (rc, got.value)
     del d
+
+
+@pytest.mark.timeout(600)
+def test_single_pass_lookback_kernels_stay_parity_checked():
+    """The look-back formulations of the split (split_kernel) and of the multiline back half (ml_fused_kernel) are
+    kept as A/B knobs; the knobs are read once per process, so the split / multiline / roll-back tests of this file are
+    repeated in a fresh interpreter with both set."""
+    import subprocess
+    import sys
+    env = dict(os.environ, LC_B200_SPLIT="lookback", LC_B200_ML="lookback")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", __file__, "-k",
+                        "split_lines or multiline or remove_last or full_size_c1 or full_size_c3"], env=env,
+                       capture_output=True, text=True, timeout=560, cwd=os.path.dirname(HERE))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,6 +1,13 @@
-timeout 900 python -m pytest tests -m gpu -q -x -k "multiline or rollback or golden or c3" 2>&1 | tail -2
-B="timeout 300 python bench.py --steps 10 --no-e2e --no-cpu-baseline"
-echo "== c3"; $B --config c3 2>&1 | grep -o '"ms_per_step": [0-9.]*'
-N="ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 100 --csv"
-B2="python bench.py --steps 2 --warmup 3 --region-s 0.01 --no-e2e --no-cpu-baseline"
-$N --log-file gpurun_out/r02h_launches_c3_warm.csv $B2 --config c3 > /dev/null 2>&1; grep -E "ml_" gpurun_out/r02h_launches_c3_warm.csv | tail -5 | awk -F'","' '{print substr($5,1,34), $NF}'
+timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+bash tools/profile_r02.sh r02k > gpurun_out/r02k_profile.log 2>&1
+for c in c1 c2 c3 c4 c5; do
+  timeout 900 python bench.py --config $c > gpurun_out/r02k_bench_$c.json 2> gpurun_out/r02k_bench_$c.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/r02k_bench_$c.json').read().strip().splitlines()[-1])
+    print('$c', d['metric'], round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'frac', round(d['roofline']['frac'],4), 'e2e', round(d['e2e']['value'],1) if d.get('e2e') else None, 'cpu', d.get('cpu_baseline',{}).get('value'))
+except Exception as e:
+    print('$c failed', e)
+PY
+done

@@ -16,10 +16,11 @@ SOURCES = ["loongcollector_b200/csrc/lc_kernels.cu", "loongcollector_b200/csrc/l
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 TUNIT = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 STEP_KERNELS = {  # kernels of one step per config and how many launches of each a step holds
-    "c1": {"split_kernel": 1},
+    "c1": {"split_mask_kernel": 1, "split_scan_kernel": 1, "split_emit_kernel": 1},
     "c2": {"regex_tdfa_staged_kernel": 1},
-    "c3": {"split_kernel": 1, "ml_fused_kernel": 1},
-    "c4": {"delim": 1, "regex_tdfa_staged_kernel": 1},
+    "c3": {"split_mask_kernel": 1, "split_scan_kernel": 1, "split_emit_kernel": 1, "ml_pass_kernel<1>": 1,
+           "ml_pass_kernel<2>": 1, "ml_pass_kernel<3>": 1},
+    "c4": {"delim_tiled_kernel": 1, "regex_tdfa_staged_kernel": 1},
     "c5": {"regex_tdfa_multi_kernel": 8},
 }
 
