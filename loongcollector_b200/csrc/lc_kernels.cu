@@ -376,7 +376,16 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
 // must be numbered in buffer order, so with a decoupled look-back a tile finishes only after EVERY earlier tile has
 // published its count, and the per-tile service time has a heavy tail (mask work p50 3.5 us, p90 6.7, max 14 us with
 // two 1024-thread blocks on an SM).  296 resident tiles wait for the slowest of them, every generation; all variants
-// ended at 8 us per 64 KiB tile = 2 TB/s.  The order constraint only concerns the NUMBERS, though, not the bytes:
+// ended at 8 us per 64 KiB tile = 2 TB/s.  Per tile, thread 0's %globaltimer stamps on C1 (512 MiB, 1 Mi lines):
+//   split_kernel<1024> (above)        ticket 0.5 + loads 2.1 + block scan 0.9 + look-back 4.4 + stores 0.4 = 8.2 us  0.262 ms
+//   persistent, cp.async-prefetched   wait for bytes 0.09 + masks 3.6 + scan and walk 3.7 (2.2 rounds of 32) + emit 0.7  0.261 ms
+//     ... same, 8 descriptors per lane and round: walk 6.9 us                                                          0.369 ms
+//   scanner warp + 31 data warps, two tiles of slack, aggregates published by the last data warp:
+//                                      masks 4.2, data warps wait for the prefix 3.3, walk 6.2 (ONE round of 256
+//                                      descriptors, but 8.8 re-polls: it waits for unpublished predecessors)           0.287 ms
+//     ... its first version took three tickets at once (tiles 3b, 3b+1, 3b+2 in block b): a serial chain, 4.06 ms
+// (those kernels are not kept; split_kernel is, behind LC_B200_SPLIT=lookback.)
+// The order constraint only concerns the NUMBERS, though, not the bytes:
 //   pass 1  split_mask_kernel   reads the buffer once, fully coalesced (one 512-byte row per load instruction), and
 //                               writes one mask bit per byte (len/8 bytes) plus {count, end of last newline} per tile;
 //                               tiles are independent -- no descriptor, no ticket, no waiting;
