@@ -221,62 +221,6 @@ __device__ __forceinline__ uint64_t lookback_deep(volatile uint64_t* desc, uint3
     return prefix;
 }
 
-// The walk alone, for pipelined kernels that published the tile's descriptor (AGGREGATE, or INCLUSIVE for tile 0) some
-// time ago: returns the exclusive prefix of `tile` and upgrades its descriptor to INCLUSIVE.  One full warp.
-template <class Op, int D>
-__device__ __forceinline__ uint64_t lookback_walk(volatile uint64_t* desc, uint32_t tile, uint32_t* polls = nullptr) {
-    const int lane = threadIdx.x & 31;
-    if (tile == 0)
-        return Op::identity();
-    uint64_t prefix = Op::identity();
-    int64_t base = (int64_t)tile - 1;
-    for (;;) {
-        if (polls)
-            ++*polls;
-        uint64_t d[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const int64_t idx = base - (lane * D + j);
-            d[j] = idx >= 0 ? ld_desc(desc + idx) : (kFlagInclusive | Op::identity());
-        }
-        uint64_t r = Op::identity();
-        bool found = false, blocked = false;
-#pragma unroll
-        for (int j = 0; j < D; ++j) { // nearest first; stop at the first inclusive or unpublished descriptor
-            const uint32_t fl = (uint32_t)(d[j] >> 62);
-            if (!found && !blocked) {
-                if (fl == 0) {
-                    blocked = true;
-                } else {
-                    r = Op::combine(d[j] & kPayloadMask, r);
-                    found = fl == 2;
-                }
-            }
-        }
-        const unsigned incl = __ballot_sync(0xFFFFFFFFu, found), blk = __ballot_sync(0xFFFFFFFFu, blocked);
-        const int fi = incl ? (__ffs(incl) - 1) : 32, bi = blk ? (__ffs(blk) - 1) : 32;
-        if (bi < fi)
-            continue; // an unpublished tile in front of the nearest inclusive prefix: poll the window again
-        if (lane > fi)
-            r = Op::identity();
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) { // ordered reduction: higher lanes are EARLIER tiles
-            const uint64_t t = shfl_down64(r, s);
-            if (lane + s < 32)
-                r = Op::combine(t, r);
-        }
-        prefix = Op::combine(shfl64(r, 0), prefix);
-        if (incl)
-            break;
-        base -= 32 * D;
-    }
-    if (lane == 0) {
-        const uint64_t own = desc[tile] & kPayloadMask;
-        desc[tile] = kFlagInclusive | (Op::combine(prefix, own) & kPayloadMask);
-    }
-    return prefix;
-}
-
 // Block-cooperative look-back: ALL threads of the block call (uniform control flow); the first WARPS warps poll
 // WARPS * 32 predecessors per round.  Why: a tile's walk ends at the nearest predecessor that already holds an
 // INCLUSIVE prefix, and every predecessor that is itself still walking only offers its aggregate -- so the faster the
