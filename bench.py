@@ -779,16 +779,45 @@ class C4(Config):
         self.e2e_d2h = int(n * (5 + 12 * MF) + n * (1 + 8 * G))
 
     def e2e_abi_step(self):
+        # chunks of whole lines flow through three queues (upload / the two stages / tables back), so that the copies of
+        # both directions overlap each other and the kernels -- what lc_regex_parse does inside the library for C2
         import torch
-        with torch.cuda.stream(self._stream):
-            self.d_buf.copy_(self.hin["buf"], non_blocking=True)
-            self.d_off.copy_(self.hin["off"], non_blocking=True)
-            self.d_len.copy_(self.hin["ln"], non_blocking=True)
-            self.step()
-            for k, d in (("st", self.st), ("nf", self.nf), ("fo", self.fo), ("fl", self.fl), ("fd", self.fd),
-                         ("rs", self.rs), ("rco", self.rco), ("rcl", self.rcl)):
-                self.ht[k].copy_(d, non_blocking=True)
-        self._stream.synchronize()
+        n, MF, G = self.n, self.MF, self.G
+        NC = 8
+        if not hasattr(self, "_cuts"):
+            lines = [n * c // NC for c in range(NC + 1)]
+            off64 = self.off.astype(np.int64)
+            byte = [int(off64[l]) if l < n else self.in_bytes for l in lines]
+            byte[0] = 0
+            self._cuts = list(zip(lines[:-1], lines[1:], byte[:-1], byte[1:]))
+            self._s_in, self._s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+            self._ev_in = [torch.cuda.Event() for _ in range(NC)]
+            self._ev_comp = [torch.cuda.Event() for _ in range(NC)]
+        for c, (l0, l1, b0, b1) in enumerate(self._cuts):
+            with torch.cuda.stream(self._s_in):
+                self.d_buf[b0:b1].copy_(self.hin["buf"][b0:b1], non_blocking=True)
+                self.d_off[l0:l1].copy_(self.hin["off"][l0:l1], non_blocking=True)
+                self.d_len[l0:l1].copy_(self.hin["ln"][l0:l1], non_blocking=True)
+                self._ev_in[c].record(self._s_in)
+            with torch.cuda.stream(self._stream):
+                self._stream.wait_event(self._ev_in[c])
+                m = l1 - l0
+                self.eng.delim_parse_dev(self.d_buf.data_ptr(), self.in_bytes, self.d_off.data_ptr() + 4 * l0,
+                                         self.d_len.data_ptr() + 4 * l0, m, b",", ord('"'), 10, True, True, MF,
+                                         self.st.data_ptr() + l0, self.nf.data_ptr() + 4 * l0,
+                                         self.fo.data_ptr() + 4 * l0 * MF, self.fl.data_ptr() + 4 * l0 * MF,
+                                         self.fd.data_ptr() + 4 * l0 * MF, 3, self.to.data_ptr() + 4 * l0,
+                                         self.tl.data_ptr() + 4 * l0)
+                self.eng.regex_parse_dev(self.rx, self.d_buf.data_ptr(), self.in_bytes, self.to.data_ptr() + 4 * l0,
+                                         self.tl.data_ptr() + 4 * l0, m, G, self.rs.data_ptr() + l0,
+                                         self.rco.data_ptr() + 4 * l0 * G, self.rcl.data_ptr() + 4 * l0 * G)
+                self._ev_comp[c].record(self._stream)
+            with torch.cuda.stream(self._s_out):
+                self._s_out.wait_event(self._ev_comp[c])
+                for k, d, w in (("st", self.st, 1), ("nf", self.nf, 1), ("fo", self.fo, MF), ("fl", self.fl, MF),
+                                ("fd", self.fd, MF), ("rs", self.rs, 1), ("rco", self.rco, G), ("rcl", self.rcl, G)):
+                    self.ht[k][l0 * w:l1 * w].copy_(d[l0 * w:l1 * w], non_blocking=True)
+        self._s_out.synchronize()
 
     def e2e_abi_check(self, st):
         assert np.array_equal(self.h["rs"], self.rs.cpu().numpy())
