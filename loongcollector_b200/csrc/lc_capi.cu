@@ -1412,7 +1412,7 @@ int lc_multiline_split_dev(lc_engine_t* e, const uint8_t* d_buf, uint64_t len, c
                                      &ds->total, e->stream);
                 e->launches += 2;
             } else {
-                CU_TRY(e->state.ensure((size_t)lck::ml_pass_tiles(lcap) * 32 + 64));
+                CU_TRY(e->state.ensure((size_t)lck::ml_pass_scratch_bytes(lcap)));
                 e->launches += 1 + lck::launch_ml_passes(cfg, e->flags.as<uint8_t>(), e->lines_off.as<uint32_t>(),
                                                          e->lines_len.as<uint32_t>(), &ds->n_out, (uint32_t)lcap,
                                                          (uint32_t)len, d_out_off, d_out_len, d_out_flags, cap,

@@ -3746,6 +3746,10 @@ constexpr int kMlPassItems = 64; // lines per thread: the two block scans of a p
 constexpr uint32_t kMlPassTile = kMlPassThreads * kMlPassItems;
 
 uint32_t ml_pass_tiles(uint64_t line_cap) { return (uint32_t)((line_cap + 1 + kMlPassTile - 1) / kMlPassTile); }
+// scratch of launch_ml_passes: four u64 per tile + {u64 incoming state, u32 event count} per thread of a tile
+uint64_t ml_pass_scratch_bytes(uint64_t line_cap) {
+    return (uint64_t)ml_pass_tiles(line_cap) * (32 + (uint64_t)kMlPassThreads * 12) + 64;
+}
 
 template <class Op>
 __global__ void __launch_bounds__(1024)
@@ -3838,7 +3842,9 @@ __global__ void __launch_bounds__(kMlPassThreads)
                    uint32_t total_len, uint64_t* __restrict__ agg1, const uint64_t* __restrict__ pre1,
                    uint64_t* __restrict__ agg2, const uint64_t* __restrict__ pre2, uint32_t* __restrict__ out_off,
                    uint32_t* __restrict__ out_len, uint8_t* __restrict__ out_flags, uint64_t cap,
-                   unsigned long long* counters, uint64_t* total_out) {
+                   unsigned long long* counters, uint64_t* total_out,
+                   uint64_t* __restrict__ t_run0 /* [tile][thread]: pass 2 -> pass 3 */,
+                   uint32_t* __restrict__ t_cnt /* [tile][thread]: pass 2 -> pass 3 */) {
     constexpr int THREADS = kMlPassThreads, ITEMS = kMlPassItems;
     static_assert(ITEMS % 16 == 0, "16-byte loads of flags");
     constexpr int NWORDS = ITEMS / 4;
@@ -3867,10 +3873,12 @@ __global__ void __launch_bounds__(kMlPassThreads)
         }
     }
     const uint32_t nvalid = base >= n ? 0u : (uint32_t)min((uint64_t)ITEMS, n - base); // lines (not the eof element)
-    // ---- the thread's lines composed: both incoming states stepped side by side
+    // ---- the thread's lines composed: both incoming states stepped side by side (passes 1 and 2; pass 3 takes the
+    // thread's incoming state and its event count from pass 2)
+    const uint64_t slot = (uint64_t)tile * THREADS + tid;
     uint32_t sA = 0, sB = 1, lbA = 0, lbB = 0; // lbX: (index + 1) of the last line opened inside the run, 0 = none
 #pragma unroll
-    for (int w = 0; w < NWORDS; ++w) {
+    for (int w = 0; w < NWORDS && PASS != 3; ++w) {
         if (fw[w] == 0 && (tb.ident & 1u))
             continue; // four lines that change nothing
 #pragma unroll 1
@@ -3890,15 +3898,21 @@ __global__ void __launch_bounds__(kMlPassThreads)
             }
         }
     }
-    const uint64_t agg = OpMlState::make(sA, sB, lbA, lbB);
-    uint64_t tot;
-    const uint64_t ex = block_exclusive_scan<OpMlState, THREADS>(agg, tot, s_scan);
-    if (PASS == 1) {
-        if (tid == 0)
-            agg1[tile] = tot;
-        return;
+    uint64_t run0;
+    if (PASS != 3) {
+        const uint64_t agg = OpMlState::make(sA, sB, lbA, lbB);
+        uint64_t tot;
+        const uint64_t ex = block_exclusive_scan<OpMlState, THREADS>(agg, tot, s_scan);
+        if (PASS == 1) {
+            if (tid == 0)
+                agg1[tile] = tot;
+            return;
+        }
+        run0 = OpMlState::combine(__ldg(pre1 + tile), ex);
+        t_run0[slot] = run0;
+    } else {
+        run0 = __ldg(t_run0 + slot);
     }
-    const uint64_t run0 = OpMlState::combine(__ldg(pre1 + tile), ex);
     // initial condition (:165-169): End-only mode starts partial with multiStartIndex = line 0
     const uint32_t s0 = (!m.S && !m.C && m.E) ? 1u : 0u;
     const uint32_t st0 = OpMlState::f(run0, s0);
@@ -3942,10 +3956,15 @@ __global__ void __launch_bounds__(kMlPassThreads)
     struct CountSink : MlCountSink {
         __device__ void prepare(uint32_t) {}
     } cs;
-    cs.discard = m.discard;
-    cs.len = len;
-    cs.n = (uint32_t)n;
-    sweep(cs);
+    if (PASS == 2) {
+        cs.discard = m.discard;
+        cs.len = len;
+        cs.n = (uint32_t)n;
+        sweep(cs);
+        t_cnt[slot] = cs.cnt;
+    } else {
+        cs.cnt = __ldg(t_cnt + slot);
+    }
     uint64_t tot2;
     const uint64_t ex2 = block_exclusive_scan<OpSum, THREADS>((uint64_t)cs.cnt, tot2, s_scan);
     if (PASS == 2) {
@@ -4089,19 +4108,20 @@ __global__ void __launch_bounds__(kMlPassThreads)
 
 int launch_ml_passes(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len,
                      const uint32_t* d_n_lines, uint32_t line_cap, uint32_t total_len, uint32_t* d_out_off,
-                     uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, uint64_t* d_scratch /* 4 x ml_pass_tiles */,
+                     uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, uint64_t* d_scratch /* ml_pass_scratch_bytes */,
                      unsigned long long* d_counters, uint64_t* d_total, cudaStream_t st) {
     MlMode m{cfg.blob_start != nullptr, cfg.blob_cont != nullptr, cfg.blob_end != nullptr, cfg.discard != 0};
     const uint32_t nt = ml_pass_tiles(line_cap);
     uint64_t *agg1 = d_scratch, *pre1 = d_scratch + nt, *agg2 = d_scratch + 2 * (uint64_t)nt,
-             *pre2 = d_scratch + 3 * (uint64_t)nt;
+             *pre2 = d_scratch + 3 * (uint64_t)nt, *t_run0 = d_scratch + 4 * (uint64_t)nt;
+    uint32_t* t_cnt = reinterpret_cast<uint32_t*>(t_run0 + (uint64_t)nt * kMlPassThreads);
     MlTab tb;
     if (!ml_build_tab(m, tb))
         return -1; // (cannot happen: every (flags, state) pair makes at most to_prev + single)
 #define LC_ML_PASS(P)                                                                                                  \
     ml_pass_kernel<P><<<nt, kMlPassThreads, 0, st>>>(m, tb, d_flags, d_off, d_len, d_n_lines, line_cap, total_len,      \
                                                      agg1, pre1, agg2, pre2, d_out_off, d_out_len, d_out_flags, cap,   \
-                                                     d_counters, d_total)
+                                                     d_counters, d_total, t_run0, t_cnt)
     LC_ML_PASS(1);
     ml_tile_scan_kernel<OpMlState><<<1, 1024, 0, st>>>(agg1, d_n_lines, line_cap, pre1);
     LC_ML_PASS(2);

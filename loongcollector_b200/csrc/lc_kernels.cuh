@@ -190,8 +190,9 @@ int launch_split_probe(const MlConfig& cfg, const uint8_t* d_buf, uint32_t len, 
                        uint8_t* d_flags, uint32_t cap, uint64_t* d_desc, uint32_t* d_ticket, uint32_t* d_n_out,
                        unsigned long long* d_total, uint64_t* d_scratch, cudaStream_t st);
 uint32_t ml_fused_tiles(uint64_t line_cap);
-// the same result without look-backs (five launches; d_scratch: 4 * ml_pass_tiles(line_cap) u64, not initialised)
+// the same result without look-backs (five launches; d_scratch: ml_pass_scratch_bytes(line_cap), not initialised)
 uint32_t ml_pass_tiles(uint64_t line_cap);
+uint64_t ml_pass_scratch_bytes(uint64_t line_cap);
 int launch_ml_passes(const MlConfig& cfg, const uint8_t* d_flags, const uint32_t* d_off, const uint32_t* d_len,
                      const uint32_t* d_n_lines, uint32_t line_cap, uint32_t total_len, uint32_t* d_out_off,
                      uint32_t* d_out_len, uint8_t* d_out_flags, uint64_t cap, uint64_t* d_scratch,

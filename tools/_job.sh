@@ -1,11 +1,6 @@
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519"
-timeout 600 $T bench.py --gpus 8 > gpurun_out/r02k_n8_bench_c2.json 2> gpurun_out/r02k_n8_bench_c2.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r02k_n8_bench_c2.json').read().strip().splitlines()[-1])
-print('N=8 value', d['value'], 'ms', d['ms_per_step'], 'frac', d['roofline']['frac'], 'e2e', d['e2e']['value'], 'e2e_plugin', (d.get('e2e_plugin') or {}).get('value'))
-print('per rank ms', d['timing'].get('per_rank_ms'))
-print('e2e per rank', d['e2e'].get('per_rank_ms'))
-print('clocks', d.get('clocks'))
-PY
-tail -2 gpurun_out/r02k_n8_bench_c2.err
+timeout 900 python -m pytest tests -m gpu -q -x -k "multiline or rollback or golden or c3 or remove_last" 2>&1 | tail -2
+B="timeout 300 python bench.py --steps 10 --no-e2e --no-cpu-baseline"
+echo "== c3"; $B --config c3 2>&1 | grep -o '"ms_per_step": [0-9.]*'
+bash tools/profile_r02.sh r02l "c3" > gpurun_out/r02l_profile.log 2>&1
+grep -E "ml_" gpurun_out/r02l_launches_c3.csv | tail -5 | awk -F'","' '{print substr($5,1,34), $NF}'
+timeout 600 python bench.py --config c3 > gpurun_out/r02l_bench_c3.json 2>/dev/null; tail -c 300 gpurun_out/r02l_bench_c3.json

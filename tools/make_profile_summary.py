@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Builds profiles/summary.json from the per-config `ncu --set full` summaries (profiles/<tag>_full_cN.json, written by
-profiles/summarize.py from the captures of tools/profile_r02.sh):  python tools/make_profile_summary.py <tag>
+profiles/summarize.py from the captures of tools/profile_r02.sh):  python tools/make_profile_summary.py <tag> [cN=<tag of a later capture> ...]
 
 Per config: the kernels of one step, their per-launch duration and DRAM bytes (dram__bytes_read.sum +
 dram__bytes_write.sum), the sum per step, and a hash of the kernel sources the capture was taken on -- bench.py reports
@@ -27,13 +27,15 @@ STEP_KERNELS = {  # kernels of one step per config and how many launches of each
 
 def main():
     tag = sys.argv[1]
+    override = dict(a.split("=", 1) for a in sys.argv[2:])
     h = hashlib.sha256()
     for name in SOURCES:
         with open(os.path.join(ROOT, name), "rb") as f:
             h.update(f.read())
     out = {}
     for cfg, kernels in STEP_KERNELS.items():
-        p = os.path.join(ROOT, "profiles", "%s_full_%s.json" % (tag, cfg))
+        ctag = override.get(cfg, tag)
+        p = os.path.join(ROOT, "profiles", "%s_full_%s.json" % (ctag, cfg))
         if not os.path.exists(p):
             continue
         recs = json.load(open(p))
@@ -50,7 +52,7 @@ def main():
             continue
         out[cfg] = {"kernel": " + ".join(per), "kernels": per,
                     "dram_bytes_per_step": sum(v["dram_bytes_per_launch"] * v["launches_per_step"] for v in per.values()),
-                    "capture": "profiles/%s_full_%s.json (ncu --set full --clock-control none)" % (tag, cfg),
+                    "capture": "profiles/%s_full_%s.json (ncu --set full --clock-control none)" % (ctag, cfg),
                     "sources": SOURCES, "sources_sha16": h.hexdigest()[:16]}
     with open(os.path.join(ROOT, "profiles", "summary.json"), "w") as f:
         json.dump(out, f, indent=1)
