@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
 //     ... its first version took three tickets at once (tiles 3b, 3b+1, 3b+2 in block b): a serial chain, 4.06 ms
 // (those kernels are not kept; split_kernel is, behind LC_B200_SPLIT=lookback.)
 // The order constraint only concerns the NUMBERS, though, not the bytes:
-//   pass 1  split_mask_kernel   reads the buffer once, fully coalesced (one 512-byte row per load instruction), and
+//   pass 1  split_mask_kernel   reads the buffer once (a warp covers 2 KiB with four 16-byte loads per lane), and
 //                               writes one mask bit per byte (len/8 bytes) plus {count, end of last newline} per tile;
 //                               tiles are independent -- no descriptor, no ticket, no waiting;
 //   pass 2  split_scan_kernel   one block turns the per-tile pairs into exclusive prefixes (8 K tiles for 512 MiB);
@@ -410,7 +410,8 @@ __device__ __forceinline__ uint32_t match16c(uint4 v, uint32_t splat) {
 template <bool PROBE>
 __global__ void __launch_bounds__(1024, 2)
     split_mask_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, uint32_t splat,
-                      void* __restrict__ masks /* u16 (PROBE: u32 = newline | candidate << 16) per chunk */,
+                      uint16_t* __restrict__ masks /* [chunk] newline bits; PROBE: + [chunk] candidate bits behind them */,
+                      uint64_t nchunks /* chunks the mask arrays hold (tiles x 4096) */,
                       uint64_t* __restrict__ agg /* [tile] */, uint64_t* __restrict__ wagg /* [tile][warp] */,
                       SplitProbe pr) {
     __shared__ uint32_t s_cnt, s_last;
@@ -421,25 +422,30 @@ __global__ void __launch_bounds__(1024, 2)
     __syncthreads();
     const uint4* vbuf = reinterpret_cast<const uint4*>(buf - shift);
     const uint64_t total_v = (uint64_t)len + shift; // virtual length including the alignment lead-in
-    const uint64_t c0 = (uint64_t)tile * kSplitTileChunks + (uint32_t)wid * 128 + lane; // row r: chunk c0 + 32 r
+    // The warp's 2 KiB = 128 chunks, four per lane.  Plain split: slot r = chunk 32 r + lane (every load instruction reads
+    // one contiguous 512-byte row; measured best).  With probes a lane owns two ADJACENT chunks in each of two 1 KiB rows
+    // (slot r: row r / 2, half r % 2), so that newline and candidate masks leave as 4-byte stores -- 2-byte stores into
+    // two arrays cost the pass 11 %.
+    const uint64_t c0 = (uint64_t)tile * kSplitTileChunks + (uint32_t)wid * 128 + (uint32_t)lane * (PROBE ? 2 : 1);
+#define LC_SLOT_CHUNK(r) (PROBE ? c0 + 64 * ((r) >> 1) + ((r)&1) : c0 + 32 * (r))
     const bool full = ((uint64_t)(tile + 1) * kSplitTileChunks * 16 <= total_v) && !(tile == 0 && shift);
     uint4 v[4];
     uint32_t m[4];
     if (full) {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
-            v[r] = __ldg(vbuf + c0 + 32 * r);
+            v[r] = __ldg(vbuf + LC_SLOT_CHUNK(r));
 #pragma unroll
         for (int r = 0; r < 4; ++r)
             m[r] = match16c(v[r], splat);
     } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const uint64_t vpos = (c0 + 32 * r) * 16;
+            const uint64_t vpos = LC_SLOT_CHUNK(r) * 16;
             m[r] = 0;
             v[r] = make_uint4(0, 0, 0, 0);
             if (vpos < total_v) {
-                v[r] = __ldg(vbuf + c0 + 32 * r);
+                v[r] = __ldg(vbuf + LC_SLOT_CHUNK(r));
                 m[r] = match16c(v[r], splat);
                 if (vpos == 0 && shift) // alignment lead-in bytes in front of the buffer (shift < 16)
                     m[r] &= ~((1u << shift) - 1u);
@@ -451,11 +457,19 @@ __global__ void __launch_bounds__(1024, 2)
     uint32_t last = 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
-        if (m[r]) // rows ascend, so the last hit wins
-            last = (uint32_t)((c0 + 32 * r) * 16 + (31 - __clz(m[r])) + 1 - shift);
+        if (m[r]) // slots ascend, so the last hit wins
+            last = (uint32_t)(LC_SLOT_CHUNK(r) * 16 + (31 - __clz(m[r])) + 1 - shift);
     const uint32_t cnt = __popc(m[0] | (m[1] << 16)) + __popc(m[2] | (m[3] << 16));
-    if constexpr (PROBE) {
-        uint32_t* mc = reinterpret_cast<uint32_t*>(masks);
+    if constexpr (!PROBE) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            masks[LC_SLOT_CHUNK(r)] = (uint16_t)m[r];
+    } else {
+        uint32_t* nl32 = reinterpret_cast<uint32_t*>(masks); // (c0 is even)
+        nl32[c0 >> 1] = m[0] | (m[1] << 16);
+        nl32[(c0 + 64) >> 1] = m[2] | (m[3] << 16);
+        uint32_t* cand32 = reinterpret_cast<uint32_t*>(masks + nchunks);
+        uint32_t cm[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             uint32_t c16 = 0, mm = m[r];
@@ -471,14 +485,12 @@ __global__ void __launch_bounds__(1024, 2)
                     c16 |= ((pr.any_first[nb >> 5] >> (nb & 31)) & 1u) << b;
                 }
             }
-            mc[c0 + 32 * r] = m[r] | (c16 << 16);
+            cm[r] = c16;
         }
-    } else {
-        uint16_t* m16 = reinterpret_cast<uint16_t*>(masks);
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-            m16[c0 + 32 * r] = (uint16_t)m[r];
+        cand32[c0 >> 1] = cm[0] | (cm[1] << 16);
+        cand32[(c0 + 64) >> 1] = cm[2] | (cm[3] << 16);
     }
+#undef LC_SLOT_CHUNK
     const uint32_t wc = __reduce_add_sync(0xFFFFFFFFu, cnt), wl = __reduce_max_sync(0xFFFFFFFFu, last);
     if (lane == 0) {
         wagg[(uint64_t)tile * 32 + wid] = ((uint64_t)wc << 32) | wl; // the warp's 2 KiB: pass 3 needs no block scan
@@ -563,12 +575,13 @@ __global__ void __launch_bounds__(1024)
 // three lines.  (One mask word per lane and iteration was instruction-bound: ~150 warp instructions per 2 KiB, most of
 // them the fixed part -- scans, address arithmetic, prefetch.)  With probes the prefix DFAs are staged once per block
 // and candidate lines collect in a per-warp queue until 32 of them fill a probe step.
-constexpr uint32_t kSplitList = 160;   // newline positions a warp compacts per unit (8 KiB: lines of >= 52 bytes on average;
+constexpr uint32_t kSplitList = 192;   // newline positions a warp compacts per unit (8 KiB: lines of >= 43 bytes on average;
                                        // denser text takes the per-lane path)
 constexpr uint32_t kEmitQueue = 64;    // per warp: candidate lines waiting until 32 of them fill a probe step
 template <bool PROBE>
 __global__ void __launch_bounds__(1024, 2)
-    split_emit_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift, const void* __restrict__ masks,
+    split_emit_kernel(const uint8_t* __restrict__ buf, uint32_t len, uint32_t shift,
+                      const uint16_t* __restrict__ masks /* newline bits, then (PROBE) candidate bits */,
                       const uint64_t* __restrict__ prefix, const uint64_t* __restrict__ wagg, uint32_t ntiles,
                       uint32_t* __restrict__ out_off, uint32_t* __restrict__ out_len, uint32_t cap, uint32_t* n_out,
                       SplitProbe pr) {
@@ -581,27 +594,10 @@ __global__ void __launch_bounds__(1024, 2)
         probe_stage(pr, s_probe);
         __syncthreads();
     }
-    __shared__ uint8_t s_cand[PROBE ? 32 : 1][PROBE ? kSplitList : 1];
-    // the lane's mask words: PROBE 4 x uint4 (16 chunks x {newline16 | candidate16 << 16}), else 2 x uint4 (16 x newline16)
-    auto mask_ptr = [&](uint32_t unit) {
-        return reinterpret_cast<const uint4*>(masks) + ((uint64_t)unit * 32 + lane) * (PROBE ? 4 : 2);
-    };
-    auto word = [&](const uint4* mp, int w, uint64_t& m, uint64_t& c) { // 64 bytes of input -> newline / candidate bits
-        if constexpr (PROBE) {
-            const uint4 q = __ldg(mp + w);
-            m = (uint64_t)__byte_perm(q.x, q.y, 0x5410) | ((uint64_t)__byte_perm(q.z, q.w, 0x5410) << 32);
-            c = (uint64_t)__byte_perm(q.x, q.y, 0x7632) | ((uint64_t)__byte_perm(q.z, q.w, 0x7632) << 32);
-        } else {
-            const uint2 q = __ldg(reinterpret_cast<const uint2*>(mp) + w);
-            m = q.x | ((uint64_t)q.y << 32);
-            c = 0;
-        }
-    };
-    auto prefetch_unit = [&](uint32_t unit) { // the next unit's masks -> L2 (registers are too scarce to hold them)
-        const uint4* mp = mask_ptr(unit);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(mp));
-        if (PROBE)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + 2));
+    // the lane's 16 chunks = four 64-bit words of newline bits
+    auto mask_ptr = [&](uint32_t unit) { return reinterpret_cast<const uint4*>(masks) + ((uint64_t)unit * 32 + lane) * 2; };
+    auto prefetch_unit = [&](uint32_t unit) { // the next unit's masks -> L2
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_ptr(unit)));
     };
     // line k = [start, p); cand: can its first byte start a match (recorded by pass 1 at the newline in front of it).
     // Returns true when the line still has to be probed.
@@ -628,11 +624,12 @@ __global__ void __launch_bounds__(1024, 2)
             }
         }
     };
-    auto cand_at = [&](uint32_t start) -> uint32_t { // candidate bit of the line that starts at `start`, from the mask array
+    const uint16_t* cand16 = masks + (uint64_t)ntiles * kSplitTileChunks;
+    auto cand_at = [&](uint32_t start) -> uint32_t { // candidate bit of the line that starts at `start`
         if (!PROBE || !start)
             return 1;
         const uint64_t vp = (uint64_t)start - 1 + shift;
-        return (__ldg(reinterpret_cast<const uint32_t*>(masks) + (vp >> 4)) >> (16 + (vp & 15))) & 1u;
+        return ((uint32_t)__ldg(cand16 + (vp >> 4)) >> (vp & 15)) & 1u;
     };
     const uint32_t nunits = ntiles * 8, ustride = gridDim.x * 32;
     uint32_t unit = blockIdx.x * 32 + wid;
@@ -653,13 +650,10 @@ __global__ void __launch_bounds__(1024, 2)
             const uint32_t sub = unit & 7;
             const uint64_t vpos0 = ((uint64_t)unit * 32 + lane) * 256; // the lane's 256 bytes
             const uint4* mp = mask_ptr(unit);
-            uint32_t cnt = 0;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                uint64_t m, c;
-                word(mp, w, m, c);
-                cnt += __popcll(m);
-            }
+            const uint4 q0 = __ldg(mp), q1 = __ldg(mp + 1);
+            uint64_t mk[4] = {q0.x | ((uint64_t)q0.y << 32), q0.z | ((uint64_t)q0.w << 32), q1.x | ((uint64_t)q1.y << 32),
+                              q1.z | ((uint64_t)q1.w << 32)};
+            const uint32_t cnt = __popcll(mk[0]) + __popcll(mk[1]) + __popcll(mk[2]) + __popcll(mk[3]);
             // the 2 KiB pieces of the tile before my unit: their line count and the end of their last newline
             const uint32_t before = lane < sub * 4 ? 0xFFFFFFFFu : 0u;
             const uint32_t my_off = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(wa >> 32) & before);
@@ -678,15 +672,12 @@ __global__ void __launch_bounds__(1024, 2)
             uint32_t end_start = my_start; // start of the piece that is open after the unit's last newline
             if (total <= kSplitList) {
                 uint32_t idx = inc - cnt;
-#pragma unroll 1
-                for (int w = 0; w < 4; ++w) { // (second read of the words: L1 hits)
-                    uint64_t m, c;
-                    word(mp, w, m, c);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    uint64_t m = mk[w];
                     while (m) {
                         const int b = __ffsll((long long)m) - 1;
                         m &= m - 1;
-                        if (PROBE)
-                            s_cand[wid][idx] = (uint8_t)((c >> b) & 1u);
                         s_list[wid][idx++] = (uint32_t)(vpos0 + 64 * w + b - shift);
                     }
                 }
@@ -696,8 +687,7 @@ __global__ void __launch_bounds__(1024, 2)
                     bool want = false;
                     if (j < total) {
                         const uint32_t start = j ? s_list[wid][j - 1] + 1 : my_start;
-                        want = line_out(k, start, s_list[wid][j],
-                                        PROBE ? (j ? (uint32_t)s_cand[wid][j - 1] : cand_at(start)) : 1u);
+                        want = line_out(k, start, s_list[wid][j], cand_at(start));
                     }
                     if constexpr (PROBE) {
                         const uint32_t bal = __ballot_sync(0xFFFFFFFFu, want);
@@ -717,22 +707,18 @@ __global__ void __launch_bounds__(1024, 2)
             } else {
                 // dense text: every lane writes its own lines
                 uint32_t last = 0;
-#pragma unroll 1
-                for (int w = 0; w < 4; ++w) {
-                    uint64_t m, c;
-                    word(mp, w, m, c);
-                    if (m)
-                        last = (uint32_t)(vpos0 + 64 * w + (63 - __clzll((long long)m)) + 1 - shift);
-                }
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    if (mk[w])
+                        last = (uint32_t)(vpos0 + 64 * w + (63 - __clzll((long long)mk[w])) + 1 - shift);
                 const uint32_t has = __ballot_sync(0xFFFFFFFFu, cnt != 0);
                 const uint32_t below = has & ((1u << lane) - 1u);
                 const uint32_t prev_last = __shfl_sync(0xFFFFFFFFu, last, below ? 31 - __clz(below) : 0);
                 end_start = __shfl_sync(0xFFFFFFFFu, last, 31 - __clz(has)); // (has != 0: total > 0)
                 uint32_t k = k0 + (inc - cnt), start = below ? prev_last : my_start;
-#pragma unroll 1
+#pragma unroll
                 for (int w = 0; w < 4; ++w) {
-                    uint64_t m, c;
-                    word(mp, w, m, c);
+                    uint64_t m = mk[w];
                     while (m) {
                         const int b = __ffsll((long long)m) - 1;
                         m &= m - 1;
@@ -795,8 +781,9 @@ static int launch_split_impl(const uint8_t* d_buf, uint32_t len, uint8_t split_c
         uint64_t* agg = d_scratch;
         uint64_t* prefix = d_scratch + nt;
         uint64_t* wagg = d_scratch + 2 * (uint64_t)nt;
-        void* masks = d_scratch + 34 * (uint64_t)nt;
-        split_mask_kernel<PROBE><<<nt, 1024, 0, st>>>(d_buf, len, shift, splat, masks, agg, wagg, pr);
+        uint16_t* masks = reinterpret_cast<uint16_t*>(d_scratch + 34 * (uint64_t)nt);
+        split_mask_kernel<PROBE><<<nt, 1024, 0, st>>>(d_buf, len, shift, splat, masks, (uint64_t)nt * kSplitTileChunks, agg,
+                                                     wagg, pr);
         split_scan_kernel<<<1, 1024, 0, st>>>(agg, nt, prefix, d_total);
         static int sms = 0;
         if (!sms) {

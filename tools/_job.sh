@@ -1,6 +1,9 @@
-timeout 900 python -m pytest tests -m gpu -q -x -k "multiline or rollback or golden or c3 or remove_last" 2>&1 | tail -2
-B="timeout 300 python bench.py --steps 10 --no-e2e --no-cpu-baseline"
-echo "== c3"; $B --config c3 2>&1 | grep -o '"ms_per_step": [0-9.]*'
-bash tools/profile_r02.sh r02l "c3" > gpurun_out/r02l_profile.log 2>&1
-grep -E "ml_" gpurun_out/r02l_launches_c3.csv | tail -5 | awk -F'","' '{print substr($5,1,34), $NF}'
-timeout 600 python bench.py --config c3 > gpurun_out/r02l_bench_c3.json 2>/dev/null; tail -c 300 gpurun_out/r02l_bench_c3.json
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+bash tools/profile_r02.sh r02m "c1 c3" > gpurun_out/r02m_profile.log 2>&1
+for c in c1 c3; do timeout 600 python bench.py --config $c > gpurun_out/r02m_bench_$c.json 2>/dev/null; python - <<PY
+import json
+d=json.loads(open('gpurun_out/r02m_bench_$c.json').read().strip().splitlines()[-1])
+print('$c', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'frac', round(d['roofline']['frac'],4), 'e2e', round(d['e2e']['value'],1))
+PY
+done
+du -sh gpurun_out
