@@ -3773,11 +3773,11 @@ struct MlTab {
 struct MlRecSink { // records which sink calls ml_actions makes for one (flags, state) pair
     uint32_t code = 0;
     bool bad = false;
-    void single(uint32_t, bool matched) { code = code == 5 ? (matched ? (bad = true, 0u) : 6u) : (code ? (bad = true, 0u) : (matched ? 2u : 1u)); }
-    void to_end(uint32_t, uint32_t) { code = code ? (bad = true, 0u) : 3u; }
-    void to_prev(uint32_t, uint32_t) { code = code ? (bad = true, 0u) : 5u; }
-    void to_eof(uint32_t) { bad = true; }
-    void span(uint32_t, uint32_t jl, uint32_t fl) { code = (code || jl != 7 || fl != 7) ? (bad = true, 0u) : 4u; }
+    __host__ __device__ void single(uint32_t, bool matched) { code = code == 5 ? (matched ? (bad = true, 0u) : 6u) : (code ? (bad = true, 0u) : (matched ? 2u : 1u)); }
+    __host__ __device__ void to_end(uint32_t, uint32_t) { code = code ? (bad = true, 0u) : 3u; }
+    __host__ __device__ void to_prev(uint32_t, uint32_t) { code = code ? (bad = true, 0u) : 5u; }
+    __host__ __device__ void to_eof(uint32_t) { bad = true; }
+    __host__ __device__ void span(uint32_t, uint32_t jl, uint32_t fl) { code = (code || jl != 7 || fl != 7) ? (bad = true, 0u) : 4u; }
 };
 
 static bool ml_build_tab(const MlMode& m, MlTab& t) {
