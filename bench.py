@@ -760,73 +760,39 @@ class C4(Config):
                                 "sample": "%d CSV lines, flat oracle delimiter FSM + PCRE2 on column 3, 1 thread" % ns}}
 
     def e2e_abi_setup(self):
-        # host buffers (pinned) -> H2D once -> delimiter stage with the column tap -> regex stage on the tapped column ->
-        # D2H of both stages' tables: the device-pointer C-ABI calls of the chain plus the copies an integration makes
-        # (the host-pointer entry points would upload the arena twice, once per stage)
-        import torch
+        # lc_delim_regex_chain: pinned host buffers in, both stages' tables out; inside the library the arena goes up once,
+        # in chunks of whole lines through three streams (upload / the two stages / tables back)
         n, MF, G = self.n, self.MF, self.G
         self._pins = []
-        self.hin = {k: torch.from_numpy(pinned_array(self._pins, a, a.dtype))
-                    for k, a in (("buf", self.buf), ("off", self.off.view(np.int32)), ("ln", self.ln.view(np.int32)))}
+        self.hin = {k: pinned_array(self._pins, a, a.dtype)
+                    for k, a in (("buf", self.buf), ("off", self.off), ("ln", self.ln))}
         self.h = {k: pinned_array(self._pins, s_ * np.dtype(d).itemsize, d)
-                  for k, s_, d in (("st", n, np.uint8), ("nf", n, np.int32), ("fo", n * MF, np.int32),
-                                   ("fl", n * MF, np.int32), ("fd", n * MF, np.int32), ("rs", n, np.uint8),
-                                   ("rco", n * G, np.int32), ("rcl", n * G, np.int32))}
-        self.ht = {k: torch.from_numpy(v) for k, v in self.h.items()}
-        self._stream = torch.cuda.Stream(self.dev)
-        self.eng.set_stream(self._stream.cuda_stream)  # copies and kernels in one queue
+                  for k, s_, d in (("st", n, np.uint8), ("nf", n, np.uint32), ("fo", n * MF, np.uint32),
+                                   ("fl", n * MF, np.uint32), ("fd", n * MF, np.uint32), ("rs", n, np.uint8),
+                                   ("rco", n * G, np.uint32), ("rcl", n * G, np.uint32))}
         self.e2e_h2d = int(self.in_bytes + 8 * n)
         self.e2e_d2h = int(n * (5 + 12 * MF) + n * (1 + 8 * G))
 
     def e2e_abi_step(self):
-        # chunks of whole lines flow through three queues (upload / the two stages / tables back), so that the copies of
-        # both directions overlap each other and the kernels -- what lc_regex_parse does inside the library for C2
-        import torch
-        n, MF, G = self.n, self.MF, self.G
-        NC = 8
-        if not hasattr(self, "_cuts"):
-            lines = [n * c // NC for c in range(NC + 1)]
-            off64 = self.off.astype(np.int64)
-            byte = [int(off64[l]) if l < n else self.in_bytes for l in lines]
-            byte[0] = 0
-            self._cuts = list(zip(lines[:-1], lines[1:], byte[:-1], byte[1:]))
-            self._s_in, self._s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
-            self._ev_in = [torch.cuda.Event() for _ in range(NC)]
-            self._ev_comp = [torch.cuda.Event() for _ in range(NC)]
-        for c, (l0, l1, b0, b1) in enumerate(self._cuts):
-            with torch.cuda.stream(self._s_in):
-                self.d_buf[b0:b1].copy_(self.hin["buf"][b0:b1], non_blocking=True)
-                self.d_off[l0:l1].copy_(self.hin["off"][l0:l1], non_blocking=True)
-                self.d_len[l0:l1].copy_(self.hin["ln"][l0:l1], non_blocking=True)
-                self._ev_in[c].record(self._s_in)
-            with torch.cuda.stream(self._stream):
-                self._stream.wait_event(self._ev_in[c])
-                m = l1 - l0
-                self.eng.delim_parse_dev(self.d_buf.data_ptr(), self.in_bytes, self.d_off.data_ptr() + 4 * l0,
-                                         self.d_len.data_ptr() + 4 * l0, m, b",", ord('"'), 10, True, True, MF,
-                                         self.st.data_ptr() + l0, self.nf.data_ptr() + 4 * l0,
-                                         self.fo.data_ptr() + 4 * l0 * MF, self.fl.data_ptr() + 4 * l0 * MF,
-                                         self.fd.data_ptr() + 4 * l0 * MF, 3, self.to.data_ptr() + 4 * l0,
-                                         self.tl.data_ptr() + 4 * l0)
-                self.eng.regex_parse_dev(self.rx, self.d_buf.data_ptr(), self.in_bytes, self.to.data_ptr() + 4 * l0,
-                                         self.tl.data_ptr() + 4 * l0, m, G, self.rs.data_ptr() + l0,
-                                         self.rco.data_ptr() + 4 * l0 * G, self.rcl.data_ptr() + 4 * l0 * G)
-                self._ev_comp[c].record(self._stream)
-            with torch.cuda.stream(self._s_out):
-                self._s_out.wait_event(self._ev_comp[c])
-                for k, d, w in (("st", self.st, 1), ("nf", self.nf, 1), ("fo", self.fo, MF), ("fl", self.fl, MF),
-                                ("fd", self.fd, MF), ("rs", self.rs, 1), ("rco", self.rco, G), ("rcl", self.rcl, G)):
-                    self.ht[k][l0 * w:l1 * w].copy_(d[l0 * w:l1 * w], non_blocking=True)
-        self._s_out.synchronize()
+        import loongcollector_b200 as lc
+        L = lc.lib()
+        h, n, MF = self.h, self.n, self.MF
+        sep = np.frombuffer(b",", np.uint8)
+        rc = L.lc_delim_regex_chain(self.eng._h, _vp(self.hin["buf"]), self.in_bytes, _vp(self.hin["off"]),
+                                    _vp(self.hin["ln"]), n, _vp(sep), 1, ord('"'), 10, 1, 1, MF, _vp(h["st"]),
+                                    _vp(h["nf"]), _vp(h["fo"]), _vp(h["fl"]), _vp(h["fd"]), 3, self.rx._h, self.G,
+                                    _vp(h["rs"]), _vp(h["rco"]), _vp(h["rcl"]))
+        if rc != 0:
+            raise RuntimeError(L.lc_last_error().decode())
 
     def e2e_abi_check(self, st):
         assert np.array_equal(self.h["rs"], self.rs.cpu().numpy())
-        assert np.array_equal(self.h["fo"], self.fo.cpu().numpy())
+        assert np.array_equal(self.h["fo"], self.fo.cpu().numpy().view(np.uint32))
+        assert np.array_equal(self.h["rcl"], self.rcl.cpu().numpy().view(np.uint32))
 
     def e2e_abi_free(self):
         import loongcollector_b200 as lc
-        self.eng.set_stream(None)  # back to the engine's own stream
-        self.hin = self.ht = self.h = None
+        self.hin = self.h = None
         for p_ in self._pins:
             lc.lib().lc_host_free(p_)
 

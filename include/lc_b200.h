@@ -228,6 +228,21 @@ int lc_delim_parse_tap_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_
                            uint32_t* d_nfields, uint32_t* d_f_off, uint32_t* d_f_len, uint32_t* d_f_dq,
                            uint32_t tap_col, uint32_t* d_tap_off, uint32_t* d_tap_len);
 
+/* The same chain with HOST buffers (pinned memory recommended: lc_host_alloc): the arena is uploaded ONCE, in chunks of
+ * whole events; per chunk the delimiter stage runs with the column tap and the regex stage on the tapped column, and both
+ * stages' tables travel back while later chunks are still being uploaded (three streams, as in lc_regex_parse).
+ * Outputs: the delimiter tables of lc_delim_parse ([n], [n][max_fields]) and the regex tables of lc_regex_parse for
+ * column `column` ([n], [n][regex_nkeys groups]; a line whose delimiter stage failed or that has no such column is
+ * parsed as the empty value).  Replaces: ProcessorParseDelimiterNative::Process followed by
+ * ProcessorParseRegexNative::Process on one of its keys (core/plugin/processor/ProcessorParseDelimiterNative.cpp:206-364,
+ * ProcessorParseRegexNative.cpp:132-168) -- a pipeline's `processors` list, collection_pipeline/CollectionPipeline.cpp. */
+int lc_delim_regex_chain(lc_engine_t* e, const uint8_t* base, uint64_t base_len, const uint32_t* ev_off,
+                         const uint32_t* ev_len, uint64_t n, const uint8_t* sep, uint32_t sep_len, uint8_t quote,
+                         uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* status,
+                         uint32_t* nfields, uint32_t* f_off, uint32_t* f_len, uint32_t* f_dq, uint32_t column,
+                         const lc_regex_t* re, uint32_t regex_nkeys, uint8_t* re_status, uint32_t* cap_off,
+                         uint32_t* cap_len);
+
 /* ---- f4 (next row): SLSEventGroupSerializer::Serialize for LOG events
  *          (core/collection_pipeline/serializer/SLSSerializer.cpp:254-269,377-395 over the writer of
  *           core/protobuf/sls/LogGroupSerializer.cpp:33-143,232-262)

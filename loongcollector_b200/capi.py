@@ -80,6 +80,7 @@ def lib():
     L.lc_delim_parse.argtypes = dl_args
     L.lc_delim_parse_dev.argtypes = dl_args
     L.lc_delim_parse_tap_dev.argtypes = dl_args + [u32, vp, vp]
+    L.lc_delim_regex_chain.argtypes = dl_args + [u32, vp, u32, vp, vp, vp]
     L.lc_sls_serialize_logs.argtypes = [vp, vp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, u64, C.POINTER(u64)]
     _LIB = L
     return L
@@ -350,6 +351,25 @@ class Engine:
                                             int(bool(discard)), _p(d_off), _p(d_len), _p(d_flags), cap, C.byref(n),
                                             _p(ctr)))
         return n.value, ctr
+
+    def delim_regex_chain(self, base, ev_off, ev_len, sep: bytes, quote, nkeys, extend, allow_short, max_fields, column,
+                          rx, regex_nkeys=None):
+        """Delimiter stage + regex stage on one column with host buffers (lc_delim_regex_chain); returns
+        (status, nfields, f_off, f_len, f_dq, re_status, cap_off, cap_len)."""
+        a = _u8(base)
+        ev_off = np.ascontiguousarray(ev_off, np.uint32)
+        ev_len = np.ascontiguousarray(ev_len, np.uint32)
+        n, MF, G = ev_off.size, int(max_fields), rx.ngroups
+        st, nf = np.empty(n, np.uint8), np.empty(n, np.uint32)
+        fo, fl, fd = (np.empty((n, MF), np.uint32) for _ in range(3))
+        rs = np.empty(n, np.uint8)
+        co, cl = np.empty((n, G), np.uint32), np.empty((n, G), np.uint32)
+        sp = np.frombuffer(sep, np.uint8)
+        _check(lib().lc_delim_regex_chain(self._h, _p(a), a.size, _p(ev_off), _p(ev_len), n, _p(sp), len(sep), quote,
+                                          nkeys, int(bool(extend)), int(bool(allow_short)), MF, _p(st), _p(nf), _p(fo),
+                                          _p(fl), _p(fd), column, rx._h, G if regex_nkeys is None else regex_nkeys,
+                                          _p(rs), _p(co), _p(cl)))
+        return st, nf, fo, fl, fd, rs, co, cl
 
     def delim_parse_dev(self, d_base, base_len, d_ev_off, d_ev_len, n, sep: bytes, quote, nkeys, extend, allow_short,
                         max_fields, d_status, d_nf, d_fo, d_fl, d_fd, tap_col=None, d_tap_off=None, d_tap_len=None):

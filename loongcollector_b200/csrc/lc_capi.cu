@@ -1662,6 +1662,81 @@ int lc_delim_parse_tap_dev(lc_engine_t* e, const uint8_t* d_base, uint64_t base_
     return LC_OK;
 }
 
+int lc_delim_regex_chain(lc_engine_t* e, const uint8_t* base, uint64_t base_len, const uint32_t* ev_off,
+                         const uint32_t* ev_len, uint64_t n, const uint8_t* sep, uint32_t sep_len, uint8_t quote,
+                         uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* status,
+                         uint32_t* nfields, uint32_t* f_off, uint32_t* f_len, uint32_t* f_dq, uint32_t column,
+                         const lc_regex_t* re, uint32_t regex_nkeys, uint8_t* re_status, uint32_t* cap_off,
+                         uint32_t* cap_len) {
+    if (!e || !re || !sep || sep_len < 1 || sep_len > 4 || max_fields == 0 || column >= max_fields ||
+        (n && (!ev_off || !ev_len || !status || !nfields || !f_off || !f_len || !f_dq || !re_status)) ||
+        (base_len && !base))
+        return fail(LC_ERR_INVALID_ARG, "lc_delim_regex_chain: bad arguments");
+    int rc = check_regex_usable(re, "lc_delim_regex_chain");
+    if (rc)
+        return rc;
+    if (n == 0)
+        return LC_OK;
+    const uint32_t G = re->res.ngroups;
+    if (G && (!cap_off || !cap_len))
+        return fail(LC_ERR_INVALID_ARG, "lc_delim_regex_chain: bad arguments");
+    if (base_len >= 0xFFFFFFF0ull || n >= (1ull << 30) || n * (uint64_t)max_fields >= (1ull << 32))
+        return fail(LC_ERR_TOO_LARGE, "buffer must be < 4 GiB, < 2^30 events and < 2^32 columns per call");
+    rc = bind(e);
+    if (rc)
+        return rc;
+    const uint64_t MF = max_fields, fbytes = n * MF * 4;
+    CU_TRY(e->in.ensure(base_len + 16));
+    CU_TRY(e->ev_off.ensure(n * 4));
+    CU_TRY(e->ev_len.ensure(n * 4));
+    CU_TRY(e->out_a.ensure(n));
+    CU_TRY(e->out_b.ensure(n * 4));
+    CU_TRY(e->out_c.ensure(fbytes));
+    CU_TRY(e->out_d.ensure(fbytes));
+    CU_TRY(e->out_e.ensure(fbytes));
+    CU_TRY(e->lines_off.ensure(n * 4)); // the tapped column = the regex stage's event table
+    CU_TRY(e->lines_len.ensure(n * 4));
+    CU_TRY(e->flags.ensure(n));
+    CU_TRY(e->cnt.ensure(n * G * 4 + 4));
+    CU_TRY(e->pos.ensure(n * G * 4 + 4));
+    uint8_t* d_in = e->in.as<uint8_t>();
+    auto run = [&](uint64_t, uint64_t i0, uint64_t cnt, uint64_t span) {
+        int r = lc_delim_parse_tap_dev(e, d_in, base_len, e->ev_off.as<uint32_t>() + i0, e->ev_len.as<uint32_t>() + i0,
+                                       cnt, sep, sep_len, quote, nkeys, extend, allow_short, max_fields,
+                                       e->out_a.as<uint8_t>() + i0, e->out_b.as<uint32_t>() + i0,
+                                       e->out_c.as<uint32_t>() + i0 * MF, e->out_d.as<uint32_t>() + i0 * MF,
+                                       e->out_e.as<uint32_t>() + i0 * MF, column, e->lines_off.as<uint32_t>() + i0,
+                                       e->lines_len.as<uint32_t>() + i0);
+        if (r)
+            return r;
+        return regex_parse_dev_impl(e, re, d_in, base_len, span, e->lines_off.as<uint32_t>() + i0,
+                                    e->lines_len.as<uint32_t>() + i0, 1, cnt, regex_nkeys, e->flags.as<uint8_t>() + i0,
+                                    e->cnt.as<uint32_t>() + i0 * G, e->pos.as<uint32_t>() + i0 * G, false);
+    };
+    auto down = [&](uint64_t, uint64_t i0, uint64_t cnt) {
+        CU_TRY(cudaMemcpyAsync(status + i0, e->out_a.as<uint8_t>() + i0, cnt, cudaMemcpyDeviceToHost, e->s_d2h));
+        CU_TRY(cudaMemcpyAsync(nfields + i0, e->out_b.as<uint32_t>() + i0, cnt * 4, cudaMemcpyDeviceToHost, e->s_d2h));
+        CU_TRY(cudaMemcpyAsync(f_off + i0 * MF, e->out_c.as<uint32_t>() + i0 * MF, cnt * MF * 4, cudaMemcpyDeviceToHost,
+                               e->s_d2h));
+        CU_TRY(cudaMemcpyAsync(f_len + i0 * MF, e->out_d.as<uint32_t>() + i0 * MF, cnt * MF * 4, cudaMemcpyDeviceToHost,
+                               e->s_d2h));
+        CU_TRY(cudaMemcpyAsync(f_dq + i0 * MF, e->out_e.as<uint32_t>() + i0 * MF, cnt * MF * 4, cudaMemcpyDeviceToHost,
+                               e->s_d2h));
+        CU_TRY(cudaMemcpyAsync(re_status + i0, e->flags.as<uint8_t>() + i0, cnt, cudaMemcpyDeviceToHost, e->s_d2h));
+        if (G) {
+            CU_TRY(cudaMemcpyAsync(cap_off + i0 * G, e->cnt.as<uint32_t>() + i0 * G, cnt * G * 4, cudaMemcpyDeviceToHost,
+                                   e->s_d2h));
+            CU_TRY(cudaMemcpyAsync(cap_len + i0 * G, e->pos.as<uint32_t>() + i0 * G, cnt * G * 4, cudaMemcpyDeviceToHost,
+                                   e->s_d2h));
+        }
+        return (int)LC_OK;
+    };
+    uint64_t nchunks = pipeline_chunks(base_len, n);
+    if (nchunks > 1 && nchunks < 8 && n >= 8 * 1024)
+        nchunks = 8; // the tables going back are as large as the arena going up: shorter chunks, earlier overlap
+    return pipelined_events(e, base, base_len, ev_off, ev_len, n, nchunks, "lc_delim_regex_chain", run, down);
+}
+
 int lc_delim_parse(lc_engine_t* e, const uint8_t* base, uint64_t base_len, const uint32_t* ev_off,
                    const uint32_t* ev_len, uint64_t n, const uint8_t* sep, uint32_t sep_len, uint8_t quote,
                    uint32_t nkeys, int extend, int allow_short, uint32_t max_fields, uint8_t* status,

@@ -389,3 +389,33 @@ def test_plugin_batched_and_per_group_process_match_the_oracle(eng):
     for k, v in want.items():
         assert cstats[k] == v, ("cpu arm", k)
     assert cstats["ctr_in_bytes"] * 2 == stats["ctr_in_bytes"] and cstats["ctr_out_bytes"] * 2 == stats["ctr_out_bytes"]
+
+
+@pytest.mark.gpu
+def test_delimiter_regex_chain_host_call_matches_the_two_stages(eng):
+    """lc_delim_regex_chain (one upload, chunked through three streams) = lc_delim_parse followed by lc_regex_parse on the
+    column, and both equal the oracle; large enough for several chunks, with quoted / malformed lines and blank lines."""
+    from loongcollector_b200 import synth
+    import loongcollector_b200 as lc
+    n = 1 << 20
+    buf, off, ln = synth.csv_lines(n, seed=77)
+    buf = buf.copy()
+    # a few malformed and blank lines
+    for i in range(0, n, 9973):
+        buf[off[i]] = ord('"')
+    for i in range(5, n, 19997):
+        buf[off[i]:off[i] + ln[i]] = ord(" ")
+    rx = lc.Regex(synth.CSV_URL_PATTERN)
+    MF = 11
+    st, nf, fo, fl, fd, rs, co, cl = eng.delim_regex_chain(buf, off, ln, b",", ord('"'), 10, True, True, MF, 3, rx)
+    st2, nf2, fo2, fl2, fd2 = eng.delim_parse(buf, off, ln, b",", ord('"'), 10, True, True, MF)
+    assert np.array_equal(st, st2) and np.array_equal(nf, nf2)
+    assert np.array_equal(fo, fo2) and np.array_equal(fl, fl2) and np.array_equal(fd, fd2)
+    rs2, co2, cl2 = eng.regex_parse(rx, buf, fo2[:, 3].copy(), fl2[:, 3].copy(), rx.ngroups)
+    assert np.array_equal(rs, rs2) and np.array_equal(co, co2) and np.array_equal(cl, cl2)
+    ns = 1 << 15
+    est, enf, efo, efl, efd = orc.delim_parse_batch(buf, off[:ns], ln[:ns], b",", ord('"'), 10, True, True, MF)
+    assert np.array_equal(st[:ns], est) and np.array_equal(fo[:ns], efo) and np.array_equal(fl[:ns], efl)
+    erst, eco, ecl = orc.regex_parse_batch(orc.Regex(synth.CSV_URL_PATTERN), buf, efo[:, 3].copy(), efl[:, 3].copy(), 2)
+    assert np.array_equal(rs[:ns], erst) and np.array_equal(co[:ns], eco) and np.array_equal(cl[:ns], ecl)
+    assert (st != 0).any() and (rs == 0).any()

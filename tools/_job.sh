@@ -1,9 +1,7 @@
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
-bash tools/profile_r02.sh r02m "c1 c3" > gpurun_out/r02m_profile.log 2>&1
-for c in c1 c3; do timeout 600 python bench.py --config $c > gpurun_out/r02m_bench_$c.json 2>/dev/null; python - <<PY
-import json
-d=json.loads(open('gpurun_out/r02m_bench_$c.json').read().strip().splitlines()[-1])
-print('$c', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'frac', round(d['roofline']['frac'],4), 'e2e', round(d['e2e']['value'],1))
-PY
-done
-du -sh gpurun_out
+timeout 600 python -m pytest tests/test_gpu_configs.py -m gpu -q -x -k "chain" 2>&1 | tail -3
+timeout 600 python bench.py --config c4 --no-cpu-baseline 2> gpurun_out/c4.err | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('c4 e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'value', d['value'], 'stale', d['roofline']['traffic_source'])
+"; tail -2 gpurun_out/c4.err
