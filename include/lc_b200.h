@@ -36,7 +36,7 @@ extern "C" {
 #define LC_ERR_INVALID_ARG 1
 #define LC_ERR_CUDA 2          /* no device / CUDA runtime failure (message in lc_last_error) */
 #define LC_ERR_REGEX_INVALID 3 /* pattern does not parse (reference: Init returns false, ParamExtractor.cpp:199-209) */
-#define LC_ERR_REGEX_UNSUPPORTED 4 /* valid for boost but outside the automaton subset (back-refs, look-around...) */
+#define LC_ERR_REGEX_UNSUPPORTED 4 /* valid for boost but outside the automaton subset (back-refs, look-behind, multi-byte look-ahead...) */
 #define LC_ERR_CAPACITY 5      /* caller-provided output capacity too small; *n_out holds the needed count */
 #define LC_ERR_TOO_LARGE 6     /* buffer >= 4 GiB or >= 2^30 lines in one call */
 

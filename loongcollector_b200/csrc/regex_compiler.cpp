@@ -123,7 +123,9 @@ enum AssertKind : uint32_t {
     A_EOT = 1u << 3,   // \z \'
     A_WORDB = 1u << 4, // \b
     A_NWORDB = 1u << 5, // \B
+    A_LA0 = 1u << 8,    // bits 8..15: single-byte look-ahead i, (?=[set]) or (?![set]) -- Parser::las[i]
 };
+constexpr int kMaxLookAheads = 8;
 
 enum NodeKind { N_EMPTY, N_SET, N_CAT, N_ALT, N_REP, N_GROUP, N_ASSERT };
 
@@ -144,10 +146,16 @@ struct Invalid : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
+struct LookAhead {
+    ByteSet set;
+    bool neg;
+};
+
 struct Parser {
     const unsigned char* p;
     size_t n, i = 0;
     std::vector<Node> nodes;
+    std::vector<LookAhead> las; // (?=x) / (?!x) with a one-byte body: assertions on the NEXT byte
     int ncap = 0;
     bool icase = false;
 
@@ -330,7 +338,26 @@ struct Parser {
                 ++i;
                 cap = ++ncap;
             } else if (c == '=' || c == '!') {
-                throw Unsupported("look-ahead assertion");
+                // look-ahead whose body is exactly one byte (a literal, an escape, a class, '.'): an assertion on the
+                // next byte, like $ and \b.  Anything longer would need the automaton to run ahead of itself.
+                ++i;
+                if (peek() == ')')
+                    throw Unsupported("empty look-ahead");
+                const int body = parse_alt();
+                if (!more() || peek() != ')')
+                    throw Invalid("unterminated look-ahead");
+                ++i;
+                icase = saved_icase;
+                if (body < 0 || nodes[body].kind != N_SET)
+                    throw Unsupported("look-ahead of more than one byte");
+                if ((int)las.size() >= kMaxLookAheads)
+                    throw Unsupported("more than 8 look-ahead assertions");
+                las.push_back({nodes[body].set, c == '!'});
+                int id = (int)nodes.size();
+                nodes.push_back(Node());
+                nodes[id].kind = N_ASSERT;
+                nodes[id].akind = A_LA0 << (las.size() - 1);
+                return id;
             } else if (c == '>') {
                 throw Unsupported("atomic group");
             } else if (c == 'P') {
@@ -1164,6 +1191,8 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                 sig.reserve(cc.sets.size() + 1);
                 for (auto& s : cc.sets)
                     sig.push_back(s.test(b));
+                for (auto& la : ps.las) // a look-ahead set is a union of classes
+                    sig.push_back(la.set.test(b));
                 sig.push_back((uint8_t)kind_of(b));
                 auto it = sig_to_class.find(sig);
                 if (it == sig_to_class.end()) {
@@ -1179,6 +1208,27 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
         for (int c = 0; c < nclasses; ++c)
             class_kind[c] = (uint8_t)kind_of(class_rep[c]);
         auto walker_has = [&](int w, int c) { return cc.sets[prog[inst_of_walker[w]].arg].test(class_rep[c]); };
+        // Single-byte look-aheads look at the NEXT byte itself, not only at its kind: where the automata carry the
+        // "next" context in their states (the reverse DFA) it is the byte CLASS + 1 (0 = end of input) instead of the
+        // kind when the pattern has such assertions; forward automata know the class of the byte they are consuming.
+        const bool has_la = !ps.las.empty();
+        auto ctx_kind = [&](int ctx) { return has_la ? (ctx == 0 ? (int)K_EDGE : (int)class_kind[ctx - 1]) : ctx; };
+        auto ctx_class = [&](int ctx) { return has_la ? ctx - 1 : -2; }; // -1 = end of input, -2 = not tracked
+        auto ctx_of_class = [&](int c) { return has_la ? c + 1 : (int)class_kind[c]; };
+        // all assertions of `mask` with previous kind pk, next kind nk and next class ncls (-1 = end of input)
+        auto holds = [&](uint32_t mask, int pk, int nk, int ncls) {
+            if (!asserts_hold(mask, pk, nk))
+                return false;
+            for (size_t q = 0; q < ps.las.size(); ++q)
+                if (mask & (A_LA0 << q)) {
+                    if (ncls == -2)
+                        throw Unsupported("look-ahead in this automaton");
+                    const bool member = ncls >= 0 && ps.las[q].set.test(class_rep[ncls]);
+                    if (member == ps.las[q].neg)
+                        return false;
+                }
+            return true;
+        };
         // kinds the byte consumed by walker w can have (prev context when standing in w)
         std::vector<uint32_t> walker_pcs(nw, 0);
         walker_pcs[0] = 1u << 0; // START: K_EDGE (or the single collapsed kind)
@@ -1238,7 +1288,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                 int pk = cur.second;
                 for (int w : cur.first)
                     for (auto& cd : cand_prefix[w])
-                        if (cd.target < 0 && asserts_hold(cd.asserts, pk, K_EDGE))
+                        if (cd.target < 0 && holds(cd.asserts, pk, K_EDGE, -1))
                             pre_acc[s] = 1;
                 for (int c = 0; c < nclasses; ++c) {
                     int nk = class_kind[c];
@@ -1246,7 +1296,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                     std::set<int> nxt;
                     for (int w : cur.first)
                         for (auto& cd : cand_prefix[w]) {
-                            if (cd.asserts && !asserts_hold(cd.asserts, pk, nk))
+                            if (cd.asserts && !holds(cd.asserts, pk, nk, c))
                                 continue;
                             if (cd.target < 0)
                                 accept_now = true;
@@ -1303,7 +1353,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                     else
                         inR[t] = 1;
                 }
-                int nk = cur.second;
+                const int nk = ctx_kind(cur.second), nkc = ctx_class(cur.second);
                 for (int c = 0; c < nclasses; ++c) {
                     int pk = class_kind[c];
                     std::vector<int> nxt;
@@ -1313,7 +1363,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                         bool viable = false;
                         for (auto& cd : cand[q]) {
                             bool in = cd.target < 0 ? match_in : (bool)inR[cd.target];
-                            if (in && asserts_hold(cd.asserts, pk, nk)) {
+                            if (in && holds(cd.asserts, pk, nk, nkc)) {
                                 viable = true;
                                 break;
                             }
@@ -1321,7 +1371,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                         if (viable)
                             nxt.push_back(q);
                     }
-                    uint32_t v = intern(RKey(nxt, ctx_full ? pk : 0));
+                    uint32_t v = intern(RKey(nxt, ctx_full ? ctx_of_class(c) : 0));
                     rev_next[s * nclasses + c] = (uint16_t)v;
                     rev_incoming.resize(rstates.size());
                     if (v)
@@ -1338,7 +1388,8 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
             for (size_t ci = 0; ci < cand[w].size(); ++ci) {
                 const Cand& cd = cand[w][ci];
                 int t = cd.target < 0 ? 0 : cd.target;
-                if (std::binary_search(k.first.begin(), k.first.end(), t) && asserts_hold(cd.asserts, pk, k.second))
+                if (std::binary_search(k.first.begin(), k.first.end(), t) &&
+                    holds(cd.asserts, pk, ctx_kind(k.second), ctx_class(k.second)))
                     return (int)ci;
             }
             return -1;
@@ -1348,7 +1399,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
             int nk = c < 0 ? K_EDGE : class_kind[c];
             for (size_t ci = 0; ci < cand[w].size(); ++ci) {
                 const Cand& cd = cand[w][ci];
-                if (cd.asserts && !asserts_hold(cd.asserts, pk, nk))
+                if (cd.asserts && !holds(cd.asserts, pk, nk, c < 0 ? -1 : c))
                     continue;
                 if (c < 0) {
                     if (cd.target < 0)
@@ -1738,7 +1789,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                 // end of input: the first thread that can take MATCH wins
                 for (size_t i = 0; i < cur.th.size() && eof[s] == LC_NONE_ENTRY; ++i)
                     for (auto& cd : cand[cur.th[i].w]) {
-                        if (cd.target >= 0 || !asserts_hold(cd.asserts, cur.pk, K_EDGE))
+                        if (cd.target >= 0 || !holds(cd.asserts, cur.pk, K_EDGE, -1))
                             continue;
                         std::vector<uint16_t> lst;
                         for (uint32_t t = 0; t < T; ++t) {
@@ -1765,7 +1816,7 @@ CompileResult compile_regex(const char* pattern, size_t len, size_t max_table_by
                         for (auto& cd : cand[cur.th[i].w]) {
                             if (cd.target < 0 || taken[cd.target])
                                 continue;
-                            if (cd.asserts && !asserts_hold(cd.asserts, cur.pk, nk))
+                            if (cd.asserts && !holds(cd.asserts, cur.pk, nk, (int)c))
                                 continue;
                             if (!walker_has(cd.target, (int)c))
                                 continue;

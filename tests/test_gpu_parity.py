@@ -142,6 +142,8 @@ PATTERNS = [
     r"(?:(a)|b)*c",
     r"(\d{1,3})\.(\d{1,3})\.(\d{1,3})\.(\d{1,3}).*",
     r"\s*(\S+)\s*=\s*(\S*?)\s*",
+    r"(?!\s)(\S+)\s(?=\[)(\S+)(?!.)",     # single-byte look-aheads (assertions on the next byte)
+    r"(\w+)(?=[ =:])(.)(?![ab])(.*)",
 ]
 
 
@@ -194,6 +196,24 @@ def test_prefix_match_matches_oracle(eng):
         o = orc.Regex(p)
         want = np.array([o.prefix_match(x) for x in lines])
         assert np.array_equal(got, want), p
+
+
+def test_multiline_start_pattern_with_a_look_ahead(eng):
+    """A start pattern the reference's users write: "(?!\\s).*" = the record begins at a line that does not start with a
+    blank.  Lines, flags and records against the oracle."""
+    rng = random.Random(31)
+    lines = []
+    for _ in range(4000):
+        head = rng.choice([b"", b" ", b"\t", b"    at ", b"Exception: ", b"x", b"[1] "])
+        lines.append(head + bytes(rng.choice(b"ab c.") for _ in range(rng.randint(0, 30))))
+    buf = np.frombuffer(b"\n".join(lines) + b"\n", np.uint8)
+    lc = _lc()
+    for discard in (False, True):
+        off, ln, fl, ctr = eng.multiline_split(buf, lc.Regex(r"(?!\s).*"), None, None, discard)
+        eo, el, ef, ectr = orc.multiline_split(buf, orc.Regex(r"(?!\s).*"), None, None, discard)
+        assert np.array_equal(off, eo) and np.array_equal(ln, el) and np.array_equal(fl, ef)
+        assert ctr.tolist() == ectr.tolist()
+        assert 100 < len(eo) < 4000
 
 
 def test_unsupported_regex_fails_loudly(eng):

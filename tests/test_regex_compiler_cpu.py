@@ -48,7 +48,8 @@ def test_multiline_unit_patterns_prefix():
 
 
 @pytest.mark.parametrize("pattern,why", [
-    (r"(a)\1", "back-reference"), (r"a(?=b)", "look-ahead"), (r"(?<=a)b", "look-behind"), (r"(a*)*", "empty"),
+    (r"(a)\1", "back-reference"), (r"a(?=bc)", "look-ahead"), (r"a(?!b|cd)", "look-ahead"), (r"(?<=a)b", "look-behind"),
+    (r"(a*)*", "empty"),
     (r"a++", "possessive"), (r"(?>a)", "atomic"), (r"\Zx", "escape"), (r"\<x", "escape"),
 ])
 def test_unsupported_is_reported_not_guessed(pattern, why):
@@ -81,6 +82,38 @@ def test_not_word_boundary_inside_the_value_agrees_with_pcre2_and_python():
     tail = EmulRegex(r"(.*)-\B")
     assert tail.full_match(b"x-") is None                           # Perl / PCRE2 would match (end, after '-')
     assert EmulRegex(r"(.*)a\Bb").full_match(b"xab") is not None
+
+
+def test_single_byte_look_ahead_agrees_with_pcre2_and_python():
+    """(?=x) / (?!x) with a one-byte body (literal, escape, class, '.'): an assertion on the next byte, compiled into
+    every automaton -- full match with captures through the two-pass / forward tables and the single-pass tagged DFA,
+    and the anchored prefix probe of the multiline patterns (the case the reference's users write: a start pattern like
+    (?!\\s) for "the line does not begin with a blank")."""
+    rng = random.Random(4711)
+    pats = [r"(?!\s)(\S+) (\d+)(.*)", r"(\w+)(?=,)(.*)", r"a(?![bc])(.)(.*)", r"(?=\[)\[(\d+)\] (.*)", r"(\d+)(?!\d)(.*)",
+            r"(.*?)(?=x)x(.*)", r"([a-c]*)(?!.)", r"(a|b(?=c))(.*)", r"(?i)(\w+) (?=Q)(.)(.*)", r"(\S*)(?![^ ])( ?)(.*)",
+            r"(?=[a-c])(?!b)(\w+)(.*)", r"(x(?!y))*(.*)"]
+    alpha = "abcxyq 1,[]Q"
+    for p in pats:
+        e, o, py = EmulRegex(p), orc.Regex(p), re.compile(p.encode(), re.S | re.M)
+        assert e.supported, (p, e.error)
+        for _ in range(500):
+            v = "".join(rng.choice(alpha) for _ in range(rng.randint(0, 10))).encode()
+            got, want = e.full_match(v), o.full_match(v)
+            m = py.fullmatch(v)
+            assert (got is None) == (want is None) == (m is None), (p, v, got, want)
+            if got is not None:
+                assert got == want, (p, v)
+            if e.tdfa_info["states"] > 1:
+                for mis in (0, 1):
+                    assert e.full_match_tdfa(v, mis) == want, (p, v, mis)
+            assert e.prefix_match(v) == o.prefix_match(v), (p, v)
+    # the multiline use: start pattern "not a blank first"
+    start = EmulRegex(r"(?!\s).*")
+    assert start.supported
+    assert start.prefix_match(b"Exception in thread") and not start.prefix_match(b"    at com.x.Y") \
+        and not start.prefix_match(b"\tat z")
+    assert start.prefix_match(b"") == orc.Regex(r"(?!\s).*").prefix_match(b"")
 
 
 @pytest.mark.parametrize("pattern", [r"(", r"a)", r"[a", r"*a", r"a{2,1}", "a\\"])
