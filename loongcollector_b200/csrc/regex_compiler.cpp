@@ -123,6 +123,8 @@ enum AssertKind : uint32_t {
     A_EOT = 1u << 3,   // \z \'
     A_WORDB = 1u << 4, // \b
     A_NWORDB = 1u << 5, // \B
+    A_WSTART = 1u << 6, // \<  (boost match_word_start: the next byte is a word byte, the previous one is not / absent)
+    A_WEND = 1u << 7,   // \>  (boost match_word_end: the previous byte is a word byte, the next one is not / absent)
     A_LA0 = 1u << 8,    // bits 8..15: single-byte look-ahead i, (?=[set]) or (?![set]) -- Parser::las[i]
 };
 constexpr int kMaxLookAheads = 8;
@@ -542,6 +544,12 @@ struct Parser {
             case 'B':
                 ak = A_NWORDB;
                 break;
+            case '<':
+                ak = A_WSTART;
+                break;
+            case '>':
+                ak = A_WEND;
+                break;
             case 'A':
             case '`':
                 ak = A_BOT;
@@ -574,8 +582,6 @@ struct Parser {
                 return id;
             }
             case 'Z':
-            case '<':
-            case '>':
             case 'G':
             case 'K':
             case 'X':
@@ -1048,6 +1054,13 @@ bool asserts_hold(uint32_t mask, int pk, int nk) {
         if ((pk == K_WORD) == (nk == K_WORD))
             return false;
     }
+    // perl_matcher::match_word_start / match_word_end (boost 1.68 perl_matcher_common.hpp): \< needs a word byte next
+    // (never at the end of the buffer) and no word byte before it; \> needs a word byte before it (never at the start)
+    // and no word byte next
+    if ((mask & A_WSTART) && !(nk == K_WORD && pk != K_WORD))
+        return false;
+    if ((mask & A_WEND) && !(pk == K_WORD && nk != K_WORD))
+        return false;
     if (mask & A_NWORDB) {
         // perl_matcher::match_within_word (boost 1.68 perl_matcher_common.hpp): false at either edge of the buffer
         // (position == last, or position == backstop without match_prev_avail) -- unlike Perl / PCRE, which let \B

@@ -101,6 +101,48 @@ def _as_u8(buf) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------- flat API
+def _boost_to_pcre2(pattern: bytes) -> bytes:
+    """Boost-only escapes PCRE2 reads differently: \\< and \\> (word start / end, perl_matcher::match_word_start /
+    match_word_end) are literal '<' / '>' for PCRE2; outside character classes they become \\b(?=\\w) and
+    \\b(?<=\\w), which is also how PCRE2 itself expands [[:<:]] and [[:>:]]."""
+    out = bytearray()
+    i, in_set = 0, False
+    while i < len(pattern):
+        c = pattern[i:i + 1]
+        if c == b"\\" and i + 1 < len(pattern):
+            e = pattern[i + 1:i + 2]
+            if not in_set and e == b"Q":  # \\Q ... \\E is literal text
+                j = pattern.find(b"\\E", i + 2)
+                j = len(pattern) if j < 0 else j + 2
+                out += pattern[i:j]
+                i = j
+                continue
+            if not in_set and e == b"<":
+                out += b"\\b(?=\\w)"
+            elif not in_set and e == b">":
+                out += b"\\b(?<=\\w)"
+            else:
+                out += c + e
+            i += 2
+            continue
+        if c == b"[" and not in_set:
+            in_set = True
+            out += c
+            i += 1
+            if pattern[i:i + 1] == b"^":
+                out += b"^"
+                i += 1
+            if pattern[i:i + 1] == b"]":  # a leading ']' is a literal
+                out += b"]"
+                i += 1
+            continue
+        if c == b"]" and in_set:
+            in_set = False
+        out += c
+        i += 1
+    return bytes(out)
+
+
 class Regex:
     """boost::regex(pattern) stand-in (PCRE2, DOTALL|MULTILINE, bytes). One matcher scratch per object."""
 
@@ -108,6 +150,7 @@ class Regex:
         if isinstance(pattern, str):
             pattern = pattern.encode("utf-8")
         self.pattern = pattern
+        pattern = _boost_to_pcre2(pattern)
         L = lib()
         self._re = L.orc_regex_compile(pattern, len(pattern), 1 if jit else 0)
         if not self._re:

@@ -50,7 +50,7 @@ def test_multiline_unit_patterns_prefix():
 @pytest.mark.parametrize("pattern,why", [
     (r"(a)\1", "back-reference"), (r"a(?=bc)", "look-ahead"), (r"a(?!b|cd)", "look-ahead"), (r"(?<=a)b", "look-behind"),
     (r"(a*)*", "empty"),
-    (r"a++", "possessive"), (r"(?>a)", "atomic"), (r"\Zx", "escape"), (r"\<x", "escape"),
+    (r"a++", "possessive"), (r"(?>a)", "atomic"), (r"\Zx", "escape"), (r"\Gx", "escape"),
 ])
 def test_unsupported_is_reported_not_guessed(pattern, why):
     r = EmulRegex(pattern)
@@ -82,6 +82,33 @@ def test_not_word_boundary_inside_the_value_agrees_with_pcre2_and_python():
     tail = EmulRegex(r"(.*)-\B")
     assert tail.full_match(b"x-") is None                           # Perl / PCRE2 would match (end, after '-')
     assert EmulRegex(r"(.*)a\Bb").full_match(b"xab") is not None
+
+
+def test_word_start_and_end_assertions():
+    """\\< and \\> (boost: match_word_start / match_word_end) = \\b(?=\\w) and \\b(?<=\\w); the oracle hands PCRE2 that
+    translation (PCRE2 reads \\< as a literal '<'), Python gets the same one as an independent check."""
+    rng = random.Random(99)
+    pats = [r"(.*?)\<(\w+)\>(.*)", r"\<(\w+) (.*)", r"(.*) (\w+)\>", r"(\W*)\<a(.*)", r"(.*)b\>(\W*)", r"(a|\<b)(.*)",
+            r"(\w*)\>(.?)(.*)"]
+    alpha = "ab_1 -,."
+    for p in pats:
+        e, o = EmulRegex(p), orc.Regex(p)
+        py = re.compile(p.replace(r"\<", r"\b(?=\w)").replace(r"\>", r"\b(?<=\w)").encode(), re.S | re.M)
+        assert e.supported, (p, e.error)
+        for _ in range(500):
+            v = "".join(rng.choice(alpha) for _ in range(rng.randint(0, 10))).encode()
+            got, want = e.full_match(v), o.full_match(v)
+            m = py.fullmatch(v)
+            assert (got is None) == (want is None) == (m is None), (p, v, got, want)
+            if got is not None:
+                assert got == want, (p, v)
+            if e.tdfa_info["states"] > 1:
+                assert e.full_match_tdfa(v, 0) == want and e.full_match_tdfa(v, 1) == want, (p, v)
+            assert e.prefix_match(v) == o.prefix_match(v), (p, v)
+    assert EmulRegex(r"\<x").full_match(b"x") == []          # start of the value counts as "no word byte before"
+    assert EmulRegex(r"x\>").full_match(b"x") == []          # end of the value counts as "no word byte next"
+    assert EmulRegex(r"\>x").full_match(b"x") is None and EmulRegex(r"x\<").full_match(b"x") is None
+    assert orc.Regex(r"[\<a]+").full_match(b"<a<") is not None    # inside a set the escape stays a literal
 
 
 def test_single_byte_look_ahead_agrees_with_pcre2_and_python():
